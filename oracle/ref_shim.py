@@ -1,0 +1,141 @@
+"""Import the UNMODIFIED reference hot-path modules from /root/reference (build container only).
+
+Test infrastructure.  The reference cannot be imported as shipped:
+``models/__init__.py:8`` imports a missing module, ``yacs`` is not installed, and the HRNet
+architecture YAML lives outside the repo at a cwd-relative, file-name-fixed path
+(``models/HRnet.py:280-283``, ``CONFIG.py:14``).  This shim works around exactly those three
+things and nothing else; every FLOP still runs through the reference's own code.
+
+Used only by ``oracle/make_golden.py`` and by tests that are skipped when /root/reference is
+absent (it does not exist on the GPU box).
+"""
+import copy
+import importlib
+import os
+import sys
+import tempfile
+import types
+
+REF_SRC = os.environ.get("STLPOSE_REFERENCE_SRC", "/root/reference/src")
+
+
+def available():
+    return os.path.isfile(os.path.join(REF_SRC, "models", "HRnet.py"))
+
+
+class _CfgNode(dict):
+    """Minimal stand-in for yacs.config.CfgNode (dict + attribute access).
+
+    Attribute misses must raise AttributeError (not KeyError): the reference stores cfg nodes
+    as module attributes (HRnet.py:299,309,320) and copy.deepcopy probes dunder attributes.
+    """
+
+    def __init__(self, init=None, new_allowed=False):
+        super().__init__()
+        for k, v in (init or {}).items():
+            self[k] = _CfgNode(v) if isinstance(v, dict) and not isinstance(v, _CfgNode) else v
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        self[name] = value
+
+    def __deepcopy__(self, memo):
+        return _CfgNode({k: copy.deepcopy(v, memo) for k, v in self.items()})
+
+    def defrost(self):
+        pass
+
+    def freeze(self):
+        pass
+
+    def merge_from_file(self, path):
+        import yaml
+        with open(path) as f:
+            data = yaml.safe_load(f)
+        self._merge(data)
+
+    def _merge(self, data):
+        for k, v in data.items():
+            if isinstance(v, dict):
+                if k not in self or not isinstance(self[k], _CfgNode):
+                    self[k] = _CfgNode()
+                self[k]._merge(v)
+            else:
+                self[k] = v
+
+
+def _yaml_text(width, image_hw):
+    h, w = image_hw
+    c = [width, 2 * width, 4 * width, 8 * width]
+    return f"""MODEL:
+  NAME: pose_hrnet
+  NUM_JOINTS: 17
+  IMAGE_SIZE: [{w}, {h}]
+  HEATMAP_SIZE: [{w // 4}, {h // 4}]
+  SIGMA: 2
+  EXTRA:
+    PRETRAINED_LAYERS: ['*']
+    FINAL_CONV_KERNEL: 1
+    STAGE2: {{NUM_MODULES: 1, NUM_BRANCHES: 2, BLOCK: BASIC, NUM_BLOCKS: [4, 4], NUM_CHANNELS: [{c[0]}, {c[1]}], FUSE_METHOD: SUM}}
+    STAGE3: {{NUM_MODULES: 4, NUM_BRANCHES: 3, BLOCK: BASIC, NUM_BLOCKS: [4, 4, 4], NUM_CHANNELS: [{c[0]}, {c[1]}, {c[2]}], FUSE_METHOD: SUM}}
+    STAGE4: {{NUM_MODULES: 3, NUM_BRANCHES: 4, BLOCK: BASIC, NUM_BLOCKS: [4, 4, 4, 4], NUM_CHANNELS: [{c[0]}, {c[1]}, {c[2]}, {c[3]}], FUSE_METHOD: SUM}}
+"""
+
+
+_installed = False
+
+
+def _install():
+    global _installed
+    if _installed:
+        return
+    if not available():
+        raise RuntimeError(f"reference not found at {REF_SRC}")
+    if REF_SRC not in sys.path:
+        sys.path.insert(0, REF_SRC)
+    yacs = types.ModuleType("yacs")
+    yacs_config = types.ModuleType("yacs.config")
+    yacs_config.CfgNode = _CfgNode
+    yacs.config = yacs_config
+    sys.modules.setdefault("yacs", yacs)
+    sys.modules.setdefault("yacs.config", yacs_config)
+    # bypass the broken models/__init__.py (imports a module that is not in the repo)
+    pkg = types.ModuleType("models")
+    pkg.__path__ = [os.path.join(REF_SRC, "models")]
+    sys.modules["models"] = pkg
+    _installed = True
+
+
+def build_reference_hrnet(width=32, image_hw=(256, 192)):
+    """Construct the reference PoseHighResolutionNet (HRnet.py:275-339) for the given width."""
+    _install()
+    tmp = tempfile.mkdtemp(prefix="stlpose_ref_")
+    os.makedirs(os.path.join(tmp, "resources", "HRnet"))
+    os.makedirs(os.path.join(tmp, "src"))
+    with open(os.path.join(tmp, "resources", "HRnet", "cfg_hrnet_w32_256x192.yaml"), "w") as f:
+        f.write(_yaml_text(width, image_hw))
+    cwd = os.getcwd()
+    os.chdir(os.path.join(tmp, "src"))
+    try:
+        hr = importlib.import_module("models.HRnet")
+        model = hr.PoseHighResolutionNet(is_train=False)
+    finally:
+        os.chdir(cwd)
+    return model
+
+
+def lib():
+    """Return the reference's lib.inference / lib.pose_parsing / lib.transforms / lib.loss."""
+    _install()
+    ns = types.SimpleNamespace()
+    ns.inference = importlib.import_module("lib.inference")
+    ns.pose_parsing = importlib.import_module("lib.pose_parsing")
+    ns.transforms = importlib.import_module("lib.transforms")
+    ns.loss = importlib.import_module("lib.loss")
+    ns.CONSTANTS = importlib.import_module("CONSTANTS")
+    return ns

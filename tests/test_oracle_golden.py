@@ -1,0 +1,98 @@
+"""Pin the CPU oracle against fixtures produced by the UNMODIFIED reference (oracle/make_golden.py)."""
+import numpy as np
+import torch
+
+from oracle import hrnet_oracle, pose_oracle
+
+
+def _decode_case(golden, golden_inputs, tag):
+    g = golden("decode.npz")
+    if tag == "rand64":
+        return g, golden_inputs["hm_rand_64x48"], golden_inputs["center_a"], golden_inputs["scale_a"]
+    if tag == "rand96":
+        return g, golden_inputs["hm_rand_96x72"], golden_inputs["center_b"], golden_inputs["scale_b"]
+    c, s = pose_oracle.synth_boxes(2, seed=9)
+    return g, g["hm_blobs_f16"].astype(np.float32), c, s
+
+
+def test_get_max_preds_bit_exact(golden, golden_inputs):
+    for tag in ("rand64", "rand96", "blobs"):
+        g, hm, _, _ = _decode_case(golden, golden_inputs, tag)
+        p, m = pose_oracle.get_max_preds(hm)
+        assert np.array_equal(p, g[f"{tag}_max_preds"])
+        assert np.array_equal(m, g[f"{tag}_max_vals"])
+        assert p.dtype == np.float32 and m.dtype == np.float32
+
+
+def test_get_final_preds(golden, golden_inputs):
+    for tag in ("rand64", "rand96", "blobs"):
+        g, hm, c, s = _decode_case(golden, golden_inputs, tag)
+        preds, maxvals, coords = pose_oracle.get_final_preds(hm, c, s)
+        assert np.array_equal(coords, g[f"{tag}_coords"])          # quarter-pixel offsets are exact
+        assert np.array_equal(maxvals, g[f"{tag}_maxvals"])
+        # float64 3-point solve vs cv2.getAffineTransform: 1e-3 px bound
+        assert np.abs(preds - g[f"{tag}_preds"]).max() < 1e-3
+        frac = np.mod(coords, 1.0)
+        assert np.all(np.isin(frac, [0.0, 0.25, 0.75]))
+
+
+def test_flip_average_bit_exact(golden, golden_inputs):
+    g = golden("flip.npz")
+    fb = pose_oracle.flip_back(golden_inputs["flip_out_f"])
+    assert np.array_equal(fb, g["flip_back"])
+    avg = pose_oracle.flip_average(golden_inputs["flip_out"], golden_inputs["flip_out_f"])
+    assert np.array_equal(avg, g["avg"])
+
+
+def test_person_mse_loss(golden, golden_inputs):
+    g = golden("loss.npz")
+    loss, grad = pose_oracle.person_mse_loss(golden_inputs["loss_out"], golden_inputs["loss_tgt"],
+                                             golden_inputs["loss_tw"])
+    assert abs(loss - float(g["loss"])) < 1e-6 * max(1.0, abs(loss))
+    assert np.abs(grad - g["grad"]).max() < 1e-9
+
+
+def test_hrnet_forward_w32(golden, golden_inputs):
+    y_ref = golden("hrnet_w32_fwd.npz")["y"]
+    sd = hrnet_oracle.synth_state_dict(32, seed=0)
+    y = hrnet_oracle.hrnet_forward(sd, torch.from_numpy(golden_inputs["x_w32"]), 32).numpy()
+    assert y.shape == (2, 17, 64, 48)
+    # same fp32 library kernels; allow for thread-count dependent summation order
+    assert np.abs(y - y_ref).max() < 1e-4
+
+
+def test_hrnet_forward_w48(golden, golden_inputs):
+    y_ref = golden("hrnet_w48_fwd.npz")["y"]
+    sd = hrnet_oracle.synth_state_dict(48, seed=0)
+    y = hrnet_oracle.hrnet_forward(sd, torch.from_numpy(golden_inputs["x_w48"]), 48).numpy()
+    assert y.shape == (1, 17, 96, 72)
+    assert np.abs(y - y_ref).max() < 1e-4
+
+
+def test_flop_count_matches_survey():
+    assert abs(hrnet_oracle.conv_flops_per_crop(32, (256, 192)) / 1e9 - 15.290) < 1e-3
+    assert abs(hrnet_oracle.conv_flops_per_crop(48, (384, 288)) / 1e9 - 70.613) < 1e-3
+
+
+def test_known_answers():
+    """Hand-made cases: ties -> first index; all<=0 -> (0,0); border peaks unrefined."""
+    hm = np.full((1, 4, 8, 6), -1.0, np.float32)
+    hm[0, 0, 3, 2] = 5.0
+    hm[0, 0, 5, 4] = 5.0                     # tie: first (row-major) wins
+    hm[0, 2, 0, 5] = 2.0                     # border peak: no refinement
+    hm[0, 3, 4, 3] = 1.0
+    hm[0, 3, 4, 4] = 0.5                     # dx>0 -> +0.25 ; dy: hm[5,3]-hm[3,3] = 0 -> 0
+    c = np.array([[100.0, 100.0]])
+    s = np.array([[0.75, 1.0]])
+    preds, maxvals, coords = pose_oracle.get_final_preds(hm, c, s)
+    assert coords[0, 0].tolist() == [2.0, 3.0]   # flat neighbourhood: sign(0) = 0, no shift
+    p0, m0 = pose_oracle.get_max_preds(hm)
+    assert p0[0, 0].tolist() == [2.0, 3.0]
+    assert p0[0, 1].tolist() == [0.0, 0.0] and m0[0, 1, 0] == -1.0
+    assert coords[0, 2].tolist() == [5.0, 0.0]
+    assert coords[0, 3].tolist() == [3.25, 4.0]
+    # closed form of the inverse affine with rot=0: k = scale[0]*200/w
+    k = s[0, 0] * 200.0 / 6
+    expect = c[0] + (coords[0, 3] - np.array([3.0, 4.0])) * k
+    assert np.abs(preds[0, 3] - expect).max() < 1e-3
+    assert pose_oracle.get_max_preds(np.zeros((0, 17, 8, 6), np.float32)) == ([], [])

@@ -1,0 +1,42 @@
+"""Oracle vs the live reference code (only where /root/reference exists, i.e. the build container)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hrnet_oracle, pose_oracle, ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference not mounted")
+
+
+def test_schema_matches_reference_state_dict():
+    for width, hw in ((32, (256, 192)), (48, (384, 288))):
+        m = ref_shim.build_reference_hrnet(width, hw)
+        sd = m.state_dict()
+        schema = hrnet_oracle.hrnet_schema(width)
+        assert [k for k, _ in schema] == list(sd.keys())
+        assert all(tuple(sd[k].shape) == s for k, s in schema)
+        m.load_state_dict(hrnet_oracle.synth_state_dict(width), strict=True)
+
+
+def test_forward_matches_reference_module():
+    m = ref_shim.build_reference_hrnet(32).eval()
+    sd = hrnet_oracle.default_init_state_dict(32, seed=3)
+    m.load_state_dict(sd, strict=True)
+    x = torch.randn(1, 3, 256, 192, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        y_ref = m(x)
+    assert (hrnet_oracle.hrnet_forward(sd, x, 32) - y_ref).abs().max().item() < 1e-5
+
+
+def test_decode_matches_reference_random():
+    L = ref_shim.lib()
+    rng = np.random.default_rng(0)
+    for (h, w) in ((64, 48), (96, 72), (16, 12)):
+        hm = rng.standard_normal((5, 17, h, w)).astype(np.float32)
+        hm[0, 0] = -np.abs(hm[0, 0])      # all-negative map
+        hm[1, 1] = 0.0                     # all ties at zero
+        c, s = pose_oracle.synth_boxes(5, seed=h)
+        ref = L.pose_parsing.get_final_preds_hrnet(hm.copy(), c, s)
+        got = pose_oracle.get_final_preds(hm, c, s)
+        assert np.array_equal(got[2], ref[2]) and np.array_equal(got[1], ref[1])
+        assert np.abs(got[0] - ref[0]).max() < 1e-3
