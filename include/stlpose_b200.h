@@ -1,0 +1,147 @@
+/* stlpose_b200 -- C ABI of the B200-native HRNet keypoint hot path.
+ *
+ * Drop-in boundary for the top-down HRNet pipeline of angelvillar96/STLPose.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference's src/).  Conventions:
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - the caller owns all buffers; nothing is allocated behind the caller's back;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work on it and never synchronise;
+ *   - return value 0 = OK, non-zero = error; stl_last_error() returns the message (thread-local);
+ *   - there is no CPU fallback anywhere: without a CUDA device every compute entry point fails.
+ */
+#ifndef STLPOSE_B200_H_
+#define STLPOSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STL_ABI_VERSION 1
+#define STL_MAX_UP 3
+
+int stl_abi_version(void);
+const char* stl_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Heatmap post-processing (fp32 NCHW heatmaps [B][J][h][w]).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* lib/transforms.py:147-164 flip_back + lib/inference.py:25-26 (1-px shift keeping column 0, average):
+ *   out = 0.5 * (heat + shift_right_1(flip_W(heat_flipped)[:, swapped joints]))
+ * pairs_host: n_pairs x 2 joint indices to swap (CONSTANTS.py:65 FLIP_PAIRS). */
+int stl_flip_avg(const float* heat, const float* heat_flipped, float* out, int B, int J, int h, int w,
+                 const int* pairs_host, int n_pairs, void* stream);
+
+/* lib/transforms.py:147-164 flip_back alone: out[n,j,y,x] = in[n,swap(j),y,w-1-x]. */
+int stl_flip_back(const float* in, float* out, int B, int J, int h, int w, const int* pairs_host, int n_pairs,
+                  void* stream);
+
+/* lib/pose_parsing.py:16-55 get_max_preds_hrnet (refine = 0) and :58-92 get_final_preds_hrnet (refine = 1,
+ * center/scale/preds given).  When heat_flipped is non-null the flip-test average above is fused in front of
+ * the argmax (and written to avg_out if non-null).
+ *   coords  [B][J][2]  heat-map space (x, y), zeroed where maxval <= 0, +-0.25 px refinement when refine
+ *   maxvals [B][J]
+ *   preds   [B][J][2]  image space through the inverse crop affine (lib/transforms.py:184-240; rot = 0, only
+ *                      scale[:,0] is used, as in the reference); may be null together with center/scale.
+ *   center, scale: [B][2] fp32. */
+int stl_decode(const float* heat, const float* heat_flipped, const float* center, const float* scale, int B, int J,
+               int h, int w, const int* pairs_host, int n_pairs, int refine, float* avg_out, float* preds,
+               float* maxvals, float* coords, void* stream);
+
+/* lib/loss.py:61-94 PersonMSELoss.forward and its gradient:
+ *   loss = 0.5/(J*B*hw) * sum (tw*(out-tgt))^2 ;  grad = tw^2*(out-tgt)/(J*B*hw)   (grad may be null)
+ * out/tgt [B][J][hw] fp32, tw [B][J] fp32, loss: 1 float.  workspace: stl_mse_workspace_bytes() bytes. */
+size_t stl_mse_workspace_bytes(void);
+int stl_mse_loss_fwd_bwd(const float* out, const float* tgt, const float* tw, int B, int J, int hw, float* loss,
+                         float* grad, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Single fused convolution (unit-test entry points; replaces one nn.Conv2d + nn.BatchNorm2d [+ add] [+ ReLU]
+ * group of models/HRnet.py, e.g. :48-59, :85-100, :198-240).
+ *
+ * Activations use the engine's padded-linear NHWC bf16 layout: N*(H+1)*(W+1) pixels of C channels, local row H
+ * and local column W of every image zero (see stlpose_b200/csrc/conv.h).
+ * ---------------------------------------------------------------------------------------------- */
+size_t stl_padded_bytes(int N, int C, int H, int W);
+int stl_nchw_to_padded(const float* x_nchw, void* y_padded, int N, int C, int H, int W, int C_pad, void* stream);
+int stl_padded_to_nchw(const void* y_padded, float* x_nchw, int N, int C, int H, int W, int C_pad, void* stream);
+
+/* OIHW fp32 weights (+ optional eval-mode BatchNorm gamma/beta/mean/var, + optional conv bias) ->
+ * [k*k][Cout_pad][Cin_pad] bf16 with the BN scale folded in, and a [Cout_pad] fp32 bias. */
+int stl_pack_conv_weights(const float* w_oihw, const float* bn_gamma, const float* bn_beta, const float* bn_mean,
+                          const float* bn_var, const float* conv_bias, float eps, int Cout, int Cin, int ksize,
+                          int Cout_pad, int Cin_pad, void* w_packed, float* bias_packed, void* stream);
+
+typedef struct stl_conv_desc {
+  const void* in;          /* padded-linear bf16 [N][H+1][W+1][Cin] */
+  int N, H, W, Cin;        /* input geometry */
+  void* out;               /* padded-linear bf16 (out_nchw = 0) or fp32 [N][Cout][Ho][Wo] (out_nchw = 1) */
+  int Cout, Cout_pad;
+  int ksize, stride;       /* 1|3, 1|2 (padding = ksize/2) */
+  const void* w_packed;
+  const float* bias_packed;
+  const void* residual;    /* optional, same geometry as out (may alias out) */
+  int n_up;                /* optional nearest-upsampled addends (fuse layers) */
+  const void* up_src[STL_MAX_UP];
+  int up_shift[STL_MAX_UP];
+  int relu;
+  int out_nchw;
+  int impl;                /* 0 = tcgen05 (shifted-descriptor taps), 1 = tcgen05 (one TMA load per tap),
+                              2 = CUDA-core reference kernel (validation only) */
+  int force_mb;            /* 0 = auto */
+  int max_ctas;            /* 0 = auto */
+} stl_conv_desc;
+
+int stl_conv2d(const stl_conv_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-network plan: replaces PoseHighResolutionNet.forward (models/HRnet.py:433-468) in eval mode and the
+ * two-pass flip test of lib/inference.py:18-22.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct stl_plan stl_plan;
+
+typedef struct stl_hrnet_cfg {
+  int width;            /* 32 or 48: branch widths are width * {1,2,4,8}   (MODEL.EXTRA.STAGE*.NUM_CHANNELS) */
+  int num_joints;       /* MODEL.NUM_JOINTS (17) */
+  int stage_modules[3]; /* NUM_MODULES of STAGE2..4 ({1,4,3}) */
+  int blocks;           /* NUM_BLOCKS per branch (4) */
+  int image_h, image_w; /* crop size, multiples of 32 */
+} stl_hrnet_cfg;
+
+typedef struct stl_conv_info {
+  char conv_key[96];  /* state_dict prefix of the conv   ("stage3.1.branches.0.2.conv1") */
+  char bn_key[96];    /* state_dict prefix of its BN, "" when the conv has a bias instead (final_layer) */
+  int cout, cin, ksize, stride;
+} stl_conv_info;
+
+stl_plan* stl_plan_create(const stl_hrnet_cfg* cfg);
+void stl_plan_destroy(stl_plan* plan);
+int stl_plan_num_convs(const stl_plan* plan);
+int stl_plan_conv_info(const stl_plan* plan, int index, stl_conv_info* info);
+
+/* Packed-parameter arena (bf16 folded weights + fp32 biases for every conv). */
+size_t stl_plan_weight_bytes(const stl_plan* plan);
+/* Fold and pack conv `index` from fp32 device tensors (models/HRnet.py state_dict entries). */
+int stl_plan_pack_conv(stl_plan* plan, int index, const float* w_oihw, const float* bn_gamma, const float* bn_beta,
+                       const float* bn_mean, const float* bn_var, const float* conv_bias, float eps,
+                       void* weight_arena, void* stream);
+
+/* Activation workspace for n_images images (n_images = 2*B when the flip-test pass is batched in). */
+size_t stl_plan_workspace_bytes(const stl_plan* plan, int n_images);
+
+/* x_nchw: fp32 [B][3][H][W].  flip_pair != 0 runs the mirrored crops as images B..2B-1 of the same batch.
+ * heat_nchw: fp32 [(flip_pair ? 2 : 1) * B][J][H/4][W/4]  (second half = raw flipped-pass heatmaps; feed both
+ * halves to stl_decode / stl_flip_avg).  The workspace is zero-initialised by the plan whenever the
+ * (workspace, n_images) binding changes. */
+int stl_plan_forward(stl_plan* plan, const float* x_nchw, int B, int flip_pair, float* heat_nchw,
+                     const void* weight_arena, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernels one stl_plan_forward enqueues (for launch accounting). */
+int stl_plan_launches_per_forward(const stl_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STLPOSE_B200_H_ */

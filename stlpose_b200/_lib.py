@@ -1,0 +1,105 @@
+"""ctypes binding of libstlpose_b200.so (the C ABI declared in include/stlpose_b200.h).
+
+There is no fallback: if the shared library is missing the import of any compute entry point raises,
+and every entry point itself fails without a CUDA device.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstlpose_b200.so")
+STL_MAX_UP = 3
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+vp = ctypes.c_void_p
+
+
+class StlError(RuntimeError):
+    pass
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [
+        ("in_", vp), ("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("Cin", ctypes.c_int),
+        ("out", vp), ("Cout", ctypes.c_int), ("Cout_pad", ctypes.c_int),
+        ("ksize", ctypes.c_int), ("stride", ctypes.c_int),
+        ("w_packed", vp), ("bias_packed", vp), ("residual", vp),
+        ("n_up", ctypes.c_int), ("up_src", vp * STL_MAX_UP), ("up_shift", ctypes.c_int * STL_MAX_UP),
+        ("relu", ctypes.c_int), ("out_nchw", ctypes.c_int), ("impl", ctypes.c_int),
+        ("force_mb", ctypes.c_int), ("max_ctas", ctypes.c_int),
+    ]
+
+
+class HrnetCfg(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_int), ("num_joints", ctypes.c_int), ("stage_modules", ctypes.c_int * 3),
+                ("blocks", ctypes.c_int), ("image_h", ctypes.c_int), ("image_w", ctypes.c_int)]
+
+
+class ConvInfo(ctypes.Structure):
+    _fields_ = [("conv_key", ctypes.c_char * 96), ("bn_key", ctypes.c_char * 96),
+                ("cout", ctypes.c_int), ("cin", ctypes.c_int), ("ksize", ctypes.c_int), ("stride", ctypes.c_int)]
+
+
+# name -> (restype, argtypes); mirrors include/stlpose_b200.h one to one
+PROTOTYPES = {
+    "stl_abi_version": (ctypes.c_int, []),
+    "stl_last_error": (ctypes.c_char_p, []),
+    "stl_flip_avg": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p,
+                                    ctypes.c_int, vp]),
+    "stl_flip_back": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p,
+                                     ctypes.c_int, vp]),
+    "stl_decode": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p,
+                                  ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]),
+    "stl_mse_workspace_bytes": (ctypes.c_size_t, []),
+    "stl_mse_loss_fwd_bwd": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]),
+    "stl_padded_bytes": (ctypes.c_size_t, [ctypes.c_int] * 4),
+    "stl_nchw_to_padded": (ctypes.c_int, [vp, vp] + [ctypes.c_int] * 5 + [vp]),
+    "stl_padded_to_nchw": (ctypes.c_int, [vp, vp] + [ctypes.c_int] * 5 + [vp]),
+    "stl_pack_conv_weights": (ctypes.c_int, [vp] * 6 + [ctypes.c_float] + [ctypes.c_int] * 5 + [vp, vp, vp]),
+    "stl_conv2d": (ctypes.c_int, [ctypes.POINTER(ConvDesc), vp]),
+    "stl_plan_create": (vp, [ctypes.POINTER(HrnetCfg)]),
+    "stl_plan_destroy": (None, [vp]),
+    "stl_plan_num_convs": (ctypes.c_int, [vp]),
+    "stl_plan_conv_info": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(ConvInfo)]),
+    "stl_plan_weight_bytes": (ctypes.c_size_t, [vp]),
+    "stl_plan_pack_conv": (ctypes.c_int, [vp, ctypes.c_int] + [vp] * 6 + [ctypes.c_float, vp, vp]),
+    "stl_plan_workspace_bytes": (ctypes.c_size_t, [vp, ctypes.c_int]),
+    "stl_plan_forward": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_size_t, vp]),
+    "stl_plan_launches_per_forward": (ctypes.c_int, [vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once). Raises StlError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise StlError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           f"or `make -C stlpose_b200/csrc`. There is no CPU fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.stl_abi_version() != 1:
+            raise StlError("libstlpose_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise StlError(lib().stl_last_error().decode() or "stlpose_b200 call failed")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

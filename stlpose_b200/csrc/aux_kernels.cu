@@ -1,0 +1,325 @@
+// Layout conversion, weight packing (BatchNorm folding), the stem convolution, the fuse-layer sum and a
+// CUDA-core reference convolution used to validate the tensor-core kernel on the device.
+#include <stdio.h>
+
+#include "aux_kernels.h"
+#include "conv.h"
+
+namespace stl {
+
+namespace {
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// ------------------------------------------------------------------ fp32 NCHW -> padded-linear NHWC bf16
+__global__ void nchw_to_padded_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C,
+                                      int H, int W, int Cp) {
+  const long long total = (long long)N * (H + 1) * (W + 1) * Cp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    long long q = i / Cp;
+    const int w = (int)(q % (W + 1));
+    q /= (W + 1);
+    const int h = (int)(q % (H + 1));
+    const int n = (int)(q / (H + 1));
+    float v = 0.f;
+    if (c < C && h < H && w < W) v = x[(((size_t)n * C + c) * H + h) * W + w];
+    y[i] = __float2bfloat16(v);
+  }
+}
+
+__global__ void padded_to_nchw_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ x, int N, int C,
+                                      int H, int W, int Cp) {
+  const long long total = (long long)N * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long long t = i / W;
+    const int h = (int)(t % H);
+    t /= H;
+    const int c = (int)(t % C);
+    const int n = (int)(t / C);
+    x[i] = __bfloat162float(y[(((size_t)n * (H + 1) + h) * (W + 1) + w) * Cp + c]);
+  }
+}
+
+// ------------------------------------------------------------------ weight packing with BN folding
+// w_oihw [Cout][Cin][k][k] fp32  ->  wp [k*k][Cout_pad][Cin_pad] bf16 scaled by gamma/sqrt(var+eps);
+// bias_out[c] = beta - mean*scale (+ conv bias * scale).  Padding rows/columns are zero.
+__global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ mean,
+                                    const float* __restrict__ var, const float* __restrict__ cbias, float eps,
+                                    int Cout, int Cin, int k, int Cout_pad, int Cin_pad,
+                                    __nv_bfloat16* __restrict__ wp, float* __restrict__ bias_out) {
+  const int taps = k * k;
+  const long long total = (long long)taps * Cout_pad * Cin_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin_pad);
+    const int co = (int)((i / Cin_pad) % Cout_pad);
+    const int t = (int)(i / ((long long)Cin_pad * Cout_pad));
+    float v = 0.f;
+    if (co < Cout && ci < Cin) {
+      const float scale = gamma ? gamma[co] / sqrtf(var[co] + eps) : 1.f;
+      v = w[((size_t)co * Cin + ci) * taps + t] * scale;
+    }
+    wp[i] = __float2bfloat16(v);
+  }
+  for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < Cout_pad; co += gridDim.x * blockDim.x) {
+    float b = 0.f;
+    if (co < Cout) {
+      const float scale = gamma ? gamma[co] / sqrtf(var[co] + eps) : 1.f;
+      b = (cbias ? cbias[co] * scale : 0.f) + (gamma ? beta[co] - mean[co] * scale : 0.f);
+    }
+    bias_out[co] = b;
+  }
+}
+
+// ------------------------------------------------------------------ stem conv1: 3 -> 64, 3x3, stride 2, pad 1
+// Reads the fp32 NCHW network input directly (images n >= n_plain are image n - n_plain mirrored in W: the
+// flip-test pass of lib/inference.py:21), applies folded BN + ReLU, writes padded-linear NHWC bf16.
+// 256 threads = 64 output pixels x 4 groups of 16 output channels; a warp shares its weight reads (broadcast).
+constexpr int kStemCout = 64;
+__global__ void __launch_bounds__(256) stem_conv1_kernel(const float* __restrict__ x, const float* __restrict__ wf,
+                                                         const float* __restrict__ bias,
+                                                         __nv_bfloat16* __restrict__ y, int n_total, int n_plain,
+                                                         int H, int W) {
+  __shared__ float ws[27 * kStemCout];  // [tap*3+ci][cout]
+  __shared__ float bs[kStemCout];
+  for (int i = threadIdx.x; i < 27 * kStemCout; i += blockDim.x) ws[i] = wf[i];
+  if (threadIdx.x < kStemCout) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int Ho = H / 2, Wo = W / 2;
+  const long long pix = (long long)blockIdx.x * 64 + (threadIdx.x & 63);
+  const int cg = threadIdx.x >> 6;
+  if (pix >= (long long)n_total * Ho * Wo) return;
+  const int wo = (int)(pix % Wo);
+  const int ho = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((long long)Wo * Ho));
+  const bool flip = n >= n_plain;
+  const float* xin = x + (size_t)(flip ? n - n_plain : n) * 3 * H * W;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = bs[cg * 16 + i];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int h = 2 * ho + kh - 1;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int w = 2 * wo + kw - 1;
+      const bool ok = h >= 0 && h < H && w >= 0 && w < W;
+      const int wsrc = flip ? W - 1 - w : w;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float v = ok ? __ldg(xin + ((size_t)ci * H + h) * W + wsrc) : 0.f;
+        const float4* wrow = reinterpret_cast<const float4*>(ws + ((kh * 3 + kw) * 3 + ci) * kStemCout + cg * 16);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 w4 = wrow[g];
+          acc[g * 4 + 0] = fmaf(v, w4.x, acc[g * 4 + 0]);
+          acc[g * 4 + 1] = fmaf(v, w4.y, acc[g * 4 + 1]);
+          acc[g * 4 + 2] = fmaf(v, w4.z, acc[g * 4 + 2]);
+          acc[g * 4 + 3] = fmaf(v, w4.w, acc[g * 4 + 3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = fmaxf(acc[i], 0.f);
+  const size_t q = ((size_t)n * (Ho + 1) + ho) * (Wo + 1) + wo;
+  uint4* o = reinterpret_cast<uint4*>(y + q * kStemCout + cg * 16);
+  o[0] = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
+                    pack_bf16(acc[6], acc[7]));
+  o[1] = make_uint4(pack_bf16(acc[8], acc[9]), pack_bf16(acc[10], acc[11]), pack_bf16(acc[12], acc[13]),
+                    pack_bf16(acc[14], acc[15]));
+}
+
+// w_oihw [64][3][3][3] (+BN) -> wf [kh][kw][ci][64] fp32 (the stem runs on CUDA cores in full fp32)
+__global__ void pack_stem_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, const float* __restrict__ mean,
+                                 const float* __restrict__ var, float eps, float* __restrict__ wf,
+                                 float* __restrict__ bias) {
+  for (int i = threadIdx.x; i < 27 * kStemCout; i += blockDim.x) {
+    const int co = i % kStemCout;
+    const int ci = (i / kStemCout) % 3;
+    const int t = i / (kStemCout * 3);
+    const float scale = gamma[co] / sqrtf(var[co] + eps);
+    wf[i] = w[((size_t)co * 3 + ci) * 9 + t] * scale;
+  }
+  for (int co = threadIdx.x; co < kStemCout; co += blockDim.x)
+    bias[co] = beta[co] - mean[co] * gamma[co] / sqrtf(var[co] + eps);
+}
+
+// ------------------------------------------------------------------ fuse-layer sum at the highest resolution
+// y = relu(x + sum_u upsample_nearest(z_u))   (HRnet.py:258-264, row i = 0), padded-linear layout, 8 ch / thread
+struct FuseArgs {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* z[kMaxUp];
+  int shift[kMaxUp];
+  int n_up;
+  __nv_bfloat16* y;
+  int N, H, W, C;
+};
+
+__global__ void fuse_sum_kernel(const FuseArgs a) {
+  const int c8n = a.C / 8;
+  const long long total = (long long)a.N * (a.H + 1) * (a.W + 1) * c8n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % c8n);
+    const long long q = i / c8n;
+    const int w = (int)(q % (a.W + 1));
+    const long long t = q / (a.W + 1);
+    const int h = (int)(t % (a.H + 1));
+    const int n = (int)(t / (a.H + 1));
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (h < a.H && w < a.W) {
+      const uint4 u = *reinterpret_cast<const uint4*>(a.x + (size_t)q * a.C + c8 * 8);
+      float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                    bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+      for (int k = 0; k < a.n_up; ++k) {
+        const int s = a.shift[k];
+        const size_t qs = ((size_t)n * ((a.H >> s) + 1) + (h >> s)) * ((a.W >> s) + 1) + (w >> s);
+        const uint4 z = *reinterpret_cast<const uint4*>(a.z[k] + qs * a.C + c8 * 8);
+        f[0] += bf16_lo(z.x); f[1] += bf16_hi(z.x); f[2] += bf16_lo(z.y); f[3] += bf16_hi(z.y);
+        f[4] += bf16_lo(z.z); f[5] += bf16_hi(z.z); f[6] += bf16_lo(z.w); f[7] += bf16_hi(z.w);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+      out = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    }
+    *reinterpret_cast<uint4*>(a.y + (size_t)q * a.C + c8 * 8) = out;
+  }
+}
+
+// ------------------------------------------------------------------ CUDA-core reference convolution
+struct NaiveArgs {
+  const __nv_bfloat16* in;
+  const __nv_bfloat16* w;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  const __nv_bfloat16* up_src[kMaxUp];
+  int up_shift[kMaxUp];
+  int n_up, relu, out_nchw;
+  void* out;
+  int N, Hi, Wi, Cin, Ho, Wo, cout, cout_pad, k, stride;
+};
+
+__global__ void conv_naive_kernel(const NaiveArgs a) {
+  const long long total = (long long)a.N * (a.Ho + 1) * (a.Wo + 1) * a.cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % a.cout);
+    const long long q = i / a.cout;
+    const int wo = (int)(q % (a.Wo + 1));
+    const long long t = q / (a.Wo + 1);
+    const int ho = (int)(t % (a.Ho + 1));
+    const int n = (int)(t / (a.Ho + 1));
+    const bool pad = ho == a.Ho || wo == a.Wo;
+    float acc = 0.f;
+    if (!pad) {
+      const int r = a.k / 2;
+      for (int kh = 0; kh < a.k; ++kh)
+        for (int kw = 0; kw < a.k; ++kw) {
+          const int h = ho * a.stride + kh - r, w = wo * a.stride + kw - r;
+          if (h < 0 || h >= a.Hi || w < 0 || w >= a.Wi) continue;
+          const __nv_bfloat16* ip = a.in + (((size_t)n * (a.Hi + 1) + h) * (a.Wi + 1) + w) * a.Cin;
+          const __nv_bfloat16* wp = a.w + ((size_t)(kh * a.k + kw) * a.cout_pad + co) * a.Cin;
+          for (int ci = 0; ci < a.Cin; ++ci) acc = fmaf(__bfloat162float(ip[ci]), __bfloat162float(wp[ci]), acc);
+        }
+      acc += a.bias[co];
+      if (a.residual) acc += __bfloat162float(a.residual[(size_t)q * a.cout + co]);
+      for (int u = 0; u < a.n_up; ++u) {
+        const int s = a.up_shift[u];
+        const size_t qs = ((size_t)n * ((a.Ho >> s) + 1) + (ho >> s)) * ((a.Wo >> s) + 1) + (wo >> s);
+        acc += __bfloat162float(a.up_src[u][qs * a.cout + co]);
+      }
+      if (a.relu) acc = fmaxf(acc, 0.f);
+    }
+    if (a.out_nchw) {
+      if (!pad) reinterpret_cast<float*>(a.out)[(((size_t)n * a.cout + co) * a.Ho + ho) * a.Wo + wo] = acc;
+    } else {
+      reinterpret_cast<__nv_bfloat16*>(a.out)[(size_t)q * a.cout + co] = __float2bfloat16(pad ? 0.f : acc);
+    }
+  }
+}
+
+int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148ll * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+}  // namespace
+
+int nchw_to_padded(const float* x, __nv_bfloat16* y, int N, int C, int H, int W, int Cp, cudaStream_t st) {
+  const long long total = (long long)N * (H + 1) * (W + 1) * Cp;
+  nchw_to_padded_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, y, N, C, H, W, Cp);
+  return check("nchw_to_padded");
+}
+
+int padded_to_nchw(const __nv_bfloat16* y, float* x, int N, int C, int H, int W, int Cp, cudaStream_t st) {
+  const long long total = (long long)N * C * H * W;
+  padded_to_nchw_kernel<<<grid_for(total, 256), 256, 0, st>>>(y, x, N, C, H, W, Cp);
+  return check("padded_to_nchw");
+}
+
+int pack_weights(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
+                 const float* cbias, float eps, int Cout, int Cin, int k, int Cout_pad, int Cin_pad,
+                 __nv_bfloat16* wp, float* bias_out, cudaStream_t st) {
+  const long long total = (long long)k * k * Cout_pad * Cin_pad;
+  pack_weights_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, gamma, beta, mean, var, cbias, eps, Cout, Cin, k,
+                                                            Cout_pad, Cin_pad, wp, bias_out);
+  return check("pack_weights");
+}
+
+int pack_stem(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+              float* wf, float* bias, cudaStream_t st) {
+  pack_stem_kernel<<<1, 256, 0, st>>>(w, gamma, beta, mean, var, eps, wf, bias);
+  return check("pack_stem");
+}
+
+int stem_conv1(const float* x, const float* wf, const float* bias, __nv_bfloat16* y, int n_total, int n_plain, int H,
+               int W, cudaStream_t st) {
+  const long long pix = (long long)n_total * (H / 2) * (W / 2);
+  const long long blocks = (pix + 63) / 64;
+  stem_conv1_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, wf, bias, y, n_total, n_plain, H, W);
+  return check("stem_conv1");
+}
+
+int fuse_sum(const __nv_bfloat16* x, const __nv_bfloat16* const* z, const int* shift, int n_up, __nv_bfloat16* y,
+             int N, int H, int W, int C, cudaStream_t st) {
+  FuseArgs a{};
+  a.x = x; a.y = y; a.n_up = n_up; a.N = N; a.H = H; a.W = W; a.C = C;
+  for (int i = 0; i < n_up; ++i) { a.z[i] = z[i]; a.shift[i] = shift[i]; }
+  const long long total = (long long)N * (H + 1) * (W + 1) * (C / 8);
+  fuse_sum_kernel<<<grid_for(total, 256), 256, 0, st>>>(a);
+  return check("fuse_sum");
+}
+
+int conv_launch_naive(const ConvSpec& s, cudaStream_t st) {
+  NaiveArgs a{};
+  a.in = s.in; a.w = s.weights; a.bias = s.bias; a.residual = s.residual;
+  for (int i = 0; i < kMaxUp; ++i) { a.up_src[i] = s.up_src[i]; a.up_shift[i] = s.up_shift[i]; }
+  a.n_up = s.n_up; a.relu = s.relu; a.out_nchw = s.out_nchw; a.out = s.out;
+  a.N = s.in_geom.N; a.Hi = s.in_geom.H; a.Wi = s.in_geom.W; a.Cin = s.in_geom.C;
+  a.Ho = a.Hi / s.stride; a.Wo = a.Wi / s.stride;
+  a.cout = s.cout; a.cout_pad = s.cout_pad; a.k = s.ksize; a.stride = s.stride;
+  const long long total = (long long)a.N * (a.Ho + 1) * (a.Wo + 1) * a.cout;
+  conv_naive_kernel<<<grid_for(total, 128), 128, 0, st>>>(a);
+  return check("conv_naive");
+}
+
+}  // namespace stl

@@ -1,0 +1,185 @@
+// extern "C" surface of libstlpose_b200.so (declared in include/stlpose_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/stlpose_b200.h"
+#include "aux_kernels.h"
+#include "conv.h"
+#include "plan.h"
+#include "pose_kernels.h"
+
+namespace stl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+static int have_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device: stlpose_b200 has no CPU fallback");
+    return 0;
+  }
+  return 1;
+}
+
+}  // namespace stl
+
+using namespace stl;
+
+struct stl_plan {
+  Plan* impl;
+};
+
+extern "C" {
+
+int stl_abi_version(void) { return STL_ABI_VERSION; }
+const char* stl_last_error(void) { return g_err; }
+
+int stl_flip_avg(const float* heat, const float* heat_flipped, float* out, int B, int J, int h, int w,
+                 const int* pairs_host, int n_pairs, void* stream) {
+  if (!have_device()) return 1;
+  if (!heat || !heat_flipped || !out) { set_error("stl_flip_avg: null pointer"); return 1; }
+  return flip_avg(heat, heat_flipped, out, B, J, h, w, pairs_host, n_pairs, (cudaStream_t)stream);
+}
+
+int stl_flip_back(const float* in, float* out, int B, int J, int h, int w, const int* pairs_host, int n_pairs,
+                  void* stream) {
+  if (!have_device()) return 1;
+  if (!in || !out) { set_error("stl_flip_back: null pointer"); return 1; }
+  return flip_back(in, out, B, J, h, w, pairs_host, n_pairs, (cudaStream_t)stream);
+}
+
+int stl_decode(const float* heat, const float* heat_flipped, const float* center, const float* scale, int B, int J,
+               int h, int w, const int* pairs_host, int n_pairs, int refine, float* avg_out, float* preds,
+               float* maxvals, float* coords, void* stream) {
+  if (!have_device()) return 1;
+  if (B > 0 && (!heat || !maxvals || !coords)) { set_error("stl_decode: null pointer"); return 1; }
+  if (preds && (!center || !scale)) { set_error("stl_decode: preds requested without center/scale"); return 1; }
+  return decode(heat, heat_flipped, center, scale, B, J, h, w, pairs_host, n_pairs, refine, avg_out, preds, maxvals,
+                coords, (cudaStream_t)stream);
+}
+
+size_t stl_mse_workspace_bytes(void) { return mse_workspace_bytes(); }
+
+int stl_mse_loss_fwd_bwd(const float* out, const float* tgt, const float* tw, int B, int J, int hw, float* loss,
+                         float* grad, void* workspace, void* stream) {
+  if (!have_device()) return 1;
+  if (!out || !tgt || !tw || !loss || !workspace) { set_error("stl_mse_loss_fwd_bwd: null pointer"); return 1; }
+  if (B <= 0 || J <= 0 || hw <= 0) { set_error("stl_mse_loss_fwd_bwd: empty problem"); return 1; }
+  return mse_loss(out, tgt, tw, B, J, hw, loss, grad, workspace, (cudaStream_t)stream);
+}
+
+size_t stl_padded_bytes(int N, int C, int H, int W) { return PaddedGeom{N, H, W, C}.bytes(); }
+
+int stl_nchw_to_padded(const float* x, void* y, int N, int C, int H, int W, int C_pad, void* stream) {
+  if (!have_device()) return 1;
+  return nchw_to_padded(x, reinterpret_cast<__nv_bfloat16*>(y), N, C, H, W, C_pad, (cudaStream_t)stream);
+}
+
+int stl_padded_to_nchw(const void* y, float* x, int N, int C, int H, int W, int C_pad, void* stream) {
+  if (!have_device()) return 1;
+  return padded_to_nchw(reinterpret_cast<const __nv_bfloat16*>(y), x, N, C, H, W, C_pad, (cudaStream_t)stream);
+}
+
+int stl_pack_conv_weights(const float* w, const float* g, const float* b, const float* m, const float* v,
+                          const float* cbias, float eps, int Cout, int Cin, int ksize, int Cout_pad, int Cin_pad,
+                          void* w_packed, float* bias_packed, void* stream) {
+  if (!have_device()) return 1;
+  if (g && (!b || !m || !v)) { set_error("stl_pack_conv_weights: incomplete BatchNorm parameters"); return 1; }
+  return pack_weights(w, g, b, m, v, cbias, eps, Cout, Cin, ksize, Cout_pad, Cin_pad,
+                      reinterpret_cast<__nv_bfloat16*>(w_packed), bias_packed, (cudaStream_t)stream);
+}
+
+int stl_conv2d(const stl_conv_desc* d, void* stream) {
+  if (!have_device()) return 1;
+  if (!d || !d->in || !d->out || !d->w_packed || !d->bias_packed) { set_error("stl_conv2d: null pointer"); return 1; }
+  if (d->n_up < 0 || d->n_up > STL_MAX_UP) { set_error("stl_conv2d: n_up out of range"); return 1; }
+  ConvSpec s;
+  s.in = reinterpret_cast<const __nv_bfloat16*>(d->in);
+  s.in_geom = PaddedGeom{d->N, d->H, d->W, d->Cin};
+  s.out = d->out;
+  s.cout = d->Cout;
+  s.cout_pad = d->Cout_pad;
+  s.ksize = d->ksize;
+  s.stride = d->stride;
+  s.weights = reinterpret_cast<const __nv_bfloat16*>(d->w_packed);
+  s.bias = d->bias_packed;
+  s.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+  s.n_up = d->n_up;
+  for (int i = 0; i < d->n_up; ++i) {
+    s.up_src[i] = reinterpret_cast<const __nv_bfloat16*>(d->up_src[i]);
+    s.up_shift[i] = d->up_shift[i];
+  }
+  s.relu = d->relu;
+  s.out_nchw = d->out_nchw;
+  s.force_tap_reload = d->impl == 1;
+  s.force_mb = d->force_mb;
+  s.max_ctas = d->max_ctas;
+  if (d->impl == 2) return conv_launch_naive(s, (cudaStream_t)stream);
+  return conv_launch(s, (cudaStream_t)stream);
+}
+
+stl_plan* stl_plan_create(const stl_hrnet_cfg* cfg) {
+  if (!cfg) { set_error("stl_plan_create: null cfg"); return nullptr; }
+  Plan* p = Plan::create(*cfg);
+  if (!p) return nullptr;
+  stl_plan* h = new stl_plan;
+  h->impl = p;
+  const char* e = getenv("STLPOSE_TAP_RELOAD");
+  if (e && e[0] == '1') p->tap_reload = 1;
+  return h;
+}
+
+void stl_plan_destroy(stl_plan* plan) {
+  if (!plan) return;
+  delete plan->impl;
+  delete plan;
+}
+
+int stl_plan_num_convs(const stl_plan* plan) { return plan ? (int)plan->impl->layers.size() : 0; }
+
+int stl_plan_conv_info(const stl_plan* plan, int index, stl_conv_info* info) {
+  if (!plan || !info || index < 0 || index >= (int)plan->impl->layers.size()) {
+    set_error("stl_plan_conv_info: bad arguments");
+    return 1;
+  }
+  const Plan::Layer& L = plan->impl->layers[index];
+  memset(info, 0, sizeof(*info));
+  snprintf(info->conv_key, sizeof info->conv_key, "%s", L.conv_key.c_str());
+  snprintf(info->bn_key, sizeof info->bn_key, "%s", L.bn_key.c_str());
+  info->cout = L.cout; info->cin = L.cin; info->ksize = L.k; info->stride = L.stride;
+  return 0;
+}
+
+size_t stl_plan_weight_bytes(const stl_plan* plan) { return plan ? plan->impl->weight_bytes : 0; }
+
+int stl_plan_pack_conv(stl_plan* plan, int index, const float* w, const float* g, const float* b, const float* m,
+                       const float* v, const float* cbias, float eps, void* arena, void* stream) {
+  if (!have_device()) return 1;
+  if (!plan || !w || !arena) { set_error("stl_plan_pack_conv: null pointer"); return 1; }
+  if (g && (!b || !m || !v)) { set_error("stl_plan_pack_conv: incomplete BatchNorm parameters"); return 1; }
+  return plan->impl->pack_conv(index, w, g, b, m, v, cbias, eps, arena, (cudaStream_t)stream);
+}
+
+size_t stl_plan_workspace_bytes(const stl_plan* plan, int n_images) {
+  return plan && n_images > 0 ? plan->impl->workspace_bytes(n_images) : 0;
+}
+
+int stl_plan_forward(stl_plan* plan, const float* x, int B, int flip_pair, float* heat, const void* arena,
+                     void* workspace, size_t ws_bytes, void* stream) {
+  if (!have_device()) return 1;
+  if (!plan || !x || !heat || !arena || !workspace) { set_error("stl_plan_forward: null pointer"); return 1; }
+  return plan->impl->forward(x, B, flip_pair, heat, arena, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+int stl_plan_launches_per_forward(const stl_plan* plan) { return plan ? (int)plan->impl->ops.size() : 0; }
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// Convolution engine: problem description (host) and kernel parameters (device).
+//
+// Activation layout ("padded-linear NHWC", bf16): a tensor of N images, H x W pixels, C channels is stored
+// as N*(H+1)*(W+1) pixels of C contiguous channels; local row H and local column W of every image are zero.
+// One shared zero row/column is enough for 3x3/pad-1 convolutions: pixel q = (n*(H+1)+h)*(W+1)+w has its
+// 9 neighbours at q + (kh-1)*(W+1) + (kw-1), and every neighbour that falls outside the image lands on a zero
+// cell (or outside the tensor, where TMA zero-fills).  A stride-1 conv is then out[q] = sum_t W_t . in[q+off_t]
+// over the flat pixel index, for any batch and any tile boundary.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace stl {
+
+constexpr int kMaxUp = 3;
+constexpr int kMaxStages = 12;
+
+struct PaddedGeom {
+  int N, H, W, C;
+  __host__ __device__ int Hp() const { return H + 1; }
+  __host__ __device__ int Wp() const { return W + 1; }
+  __host__ __device__ long long pixels() const { return (long long)N * (H + 1) * (W + 1); }
+  __host__ __device__ size_t bytes() const { return (size_t)pixels() * C * 2; }
+};
+
+// Host-side description of one fused convolution.
+struct ConvSpec {
+  const __nv_bfloat16* in = nullptr;   // padded-linear NHWC, Cin channels
+  PaddedGeom in_geom{};
+  void* out = nullptr;                 // padded-linear NHWC bf16 (out_nchw=0) or fp32 NCHW (out_nchw=1)
+  int cout = 0;                        // real output channels
+  int cout_pad = 0;                    // multiple of 16; packed weights/bias have this many rows
+  int ksize = 1;                       // 1 or 3 (pad = ksize/2)
+  int stride = 1;                      // 1 or 2
+  const __nv_bfloat16* weights = nullptr;  // [taps][cout_pad][cin] bf16 (BN scale folded)
+  const float* bias = nullptr;             // [cout_pad] fp32 (BN shift folded)
+  const __nv_bfloat16* residual = nullptr; // same geometry as out, added before ReLU (may alias out)
+  int n_up = 0;                            // nearest-upsampled addends (HRNet fuse layers, HRnet.py:198-209)
+  const __nv_bfloat16* up_src[kMaxUp] = {nullptr, nullptr, nullptr};
+  int up_shift[kMaxUp] = {0, 0, 0};        // log2 of the upsampling factor
+  int relu = 0;
+  int out_nchw = 0;                        // 1: write fp32 [N][cout][H][W] (heatmap head)
+  // tuning / debugging knobs (0 = let the engine decide)
+  int force_tap_reload = 0;                // 1: one aligned TMA load per filter tap instead of shifted descriptors
+  int force_mb = 0;
+  int max_ctas = 0;
+};
+
+// Kernel parameters (passed __grid_constant__).
+struct ConvParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int mode;        // 0: stride-1 flat-pixel tiles, 1: stride-2 structured tiles
+  int taps;        // 1 or 9
+  int n_chunks;    // Cin / ck
+  int ck;          // channels per K chunk: 16, 32 or 64 (row = 2*ck bytes = swizzle span)
+  int nt;          // UMMA N
+  int n_ntiles;
+  int mb;          // 128-row accumulator blocks per tile
+  int a_shift;     // 1: halo'd tile loaded once per chunk, taps addressed by shifted descriptors
+  int halo;        // rows in front of the tile in shift mode (Wp+1 for 3x3, 0 for 1x1)
+  int a_box_rows, a_pieces;
+  int a_stages, b_stages;
+  uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
+  int n_accbuf;
+  uint32_t tmem_cols;
+  long long total_tiles;
+  // input / output geometry
+  int in_Wp;
+  int N, H, W, Hp, Wp;   // OUTPUT geometry
+  long long P;           // output padded pixel count
+  int bw, bh, bn, tiles_w, tiles_h, tiles_n;  // structured tiles (mode 1)
+  // epilogue
+  void* out;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  const __nv_bfloat16* up_src[kMaxUp];
+  int up_shift[kMaxUp];
+  int n_up;
+  int relu;
+  int out_nchw;
+  int cout, cout_pad;
+};
+
+// Fills ConvParams (tensor maps included) and returns the launch configuration. 0 on success.
+int conv_prepare(const ConvSpec& spec, ConvParams* p, int* grid, size_t* smem_bytes);
+int conv_launch_prepared(const ConvParams& p, int grid, size_t smem_bytes, cudaStream_t stream);
+int conv_launch(const ConvSpec& spec, cudaStream_t stream);
+
+// Reference CUDA-core direct convolution with the same fused epilogue (validation only; slow).
+int conv_launch_naive(const ConvSpec& spec, cudaStream_t stream);
+
+void set_error(const char* fmt, ...);
+
+}  // namespace stl

@@ -1,0 +1,511 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+//   D[pixels, Cout] = sum over taps t, channel chunks c :  A_t,c[pixels, ck] * W_t,c[Cout, ck]^T
+//
+// Persistent, warp-specialised CTA (one per SM):
+//   warp 0 / lane 0 : TMA producer   (activation ring + weight ring, mbarrier full/empty pairs)
+//   warp 1 / lane 0 : tcgen05.mma issuer, fp32 accumulators in TMEM (double-buffered across tiles)
+//   warps 2..5      : epilogue - tcgen05.ld, + bias (folded BN) [+ residual] [+ upsampled addends] [ReLU],
+//                     bf16 padded-NHWC store or fp32 NCHW store (heatmap head)
+//
+// Stride-1 convs ("flat" mode) exploit the padded-linear layout (conv.h): a tile is 128*mb consecutive padded
+// pixels; the 3x3 taps are the same smem tile read at 9 row offsets, so each activation byte is fetched from
+// L2 once per tile (plus halo) instead of 9 times.  The K-major, swizzled smem rows are addressed by UMMA
+// descriptors whose start address is advanced by whole rows; the swizzle is a function of absolute smem
+// address bits (the same property the usual +32 B K-advance relies on), so any row offset is legal.
+// `a_shift = 0` falls back to one aligned TMA load per tap.
+// Stride-2 convs ("structured" mode) load each tap with a 4-D tensor map whose W/H traversal stride is 2.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "conv.h"
+#include "ptx.cuh"
+
+namespace stl {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr uint32_t kCtlBytes = 1024;
+constexpr size_t kMaxSmem = 227 * 1024;
+
+struct Ctl {
+  uint64_t a_full[kMaxStages], a_empty[kMaxStages];
+  uint64_t b_full[kMaxStages], b_empty[kMaxStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Ctl) <= kCtlBytes, "control block too large");
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int NC>
+__device__ __forceinline__ void add_bf16_row(float (&f)[NC], const __nv_bfloat16* src) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int g = 0; g < NC / 8; ++g) {
+    uint4 u = s[g];
+    f[g * 8 + 0] += bf16_lo(u.x); f[g * 8 + 1] += bf16_hi(u.x);
+    f[g * 8 + 2] += bf16_lo(u.y); f[g * 8 + 3] += bf16_hi(u.y);
+    f[g * 8 + 4] += bf16_lo(u.z); f[g * 8 + 5] += bf16_hi(u.z);
+    f[g * 8 + 6] += bf16_lo(u.w); f[g * 8 + 7] += bf16_hi(u.w);
+  }
+}
+
+struct RowPos {
+  bool valid;    // row maps to a pixel of the output tensor
+  bool is_pad;   // ... which is one of the zero cells of the padded layout
+  int q;         // padded-linear pixel index
+  int n, h, w;
+};
+
+// Epilogue for NC consecutive output channels of one pixel.
+template <int NC>
+__device__ __forceinline__ void epilogue_store(const ConvParams& p, const uint32_t (&v)[NC], int ch0,
+                                               const RowPos& r) {
+  if (!r.valid) return;
+  if (p.out_nchw) {
+    if (r.is_pad) return;
+    float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int c = ch0 + i;
+      if (c < p.cout) {
+        float f = __uint_as_float(v[i]) + __ldg(p.bias + c);
+        if (p.relu) f = fmaxf(f, 0.f);
+        out[(((size_t)r.n * p.cout + c) * p.H + r.h) * p.W + r.w] = f;
+      }
+    }
+    return;
+  }
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.q * p.cout + ch0;
+  uint4* o = reinterpret_cast<uint4*>(out);
+  if (r.is_pad) {
+#pragma unroll
+    for (int g = 0; g < NC / 8; ++g) o[g] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  float f[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) f[i] = __uint_as_float(v[i]) + __ldg(p.bias + ch0 + i);
+  if (p.residual) add_bf16_row<NC>(f, p.residual + (size_t)r.q * p.cout + ch0);
+  for (int u = 0; u < p.n_up; ++u) {
+    const int s = p.up_shift[u];
+    const int hs = p.H >> s, ws = p.W >> s;
+    const size_t qs = ((size_t)r.n * (hs + 1) + (r.h >> s)) * (ws + 1) + (r.w >> s);
+    add_bf16_row<NC>(f, p.up_src[u] + qs * p.cout + ch0);
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) f[i] = fmaxf(f[i], 0.f);
+  }
+#pragma unroll
+  for (int g = 0; g < NC / 8; ++g) {
+    o[g] = make_uint4(pack_bf16(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
+                      pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: swizzle-128B atoms (8 rows x 128 B) must start on their natural boundary.
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem);
+  uint8_t* a_smem = smem + kCtlBytes;
+  uint8_t* b_smem = a_smem + (size_t)p.a_stages * p.a_stage_bytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t span = 2u * p.ck;
+  const uint32_t acc_cols = (uint32_t)(p.mb * p.nt);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&ctl->a_full[i], 1); mbar_init(&ctl->a_empty[i], 1); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], 1); mbar_init(&ctl->acc_empty[i], 4); }
+    fence_mbar_init();
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1) tmem_alloc(&ctl->tmem_base, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t a_it = 0, b_it = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nti = (int)(tile % p.n_ntiles);
+        const long long mt = tile / p.n_ntiles;
+        int q0 = 0, wo0 = 0, ho0 = 0, n0 = 0;
+        if (p.mode == 0) {
+          q0 = (int)(mt * (128 * p.mb));
+        } else {
+          wo0 = (int)(mt % p.tiles_w) * p.bw;
+          ho0 = (int)((mt / p.tiles_w) % p.tiles_h) * p.bh;
+          n0 = (int)(mt / ((long long)p.tiles_w * p.tiles_h)) * p.bn;
+        }
+        for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
+          for (int tap = 0; tap < p.taps; ++tap) {
+            if (!p.a_shift || tap == 0) {
+              const uint32_t s = a_it % p.a_stages, ph = (a_it / p.a_stages) & 1;
+              mbar_wait(&ctl->a_empty[s], ph ^ 1);
+              mbar_expect_tx(&ctl->a_full[s], p.a_tx_bytes);
+              uint8_t* dst = a_smem + (size_t)s * p.a_stage_bytes;
+              const int kh = p.taps == 9 ? tap / 3 : 1, kw = p.taps == 9 ? tap % 3 : 1;
+              if (p.mode == 0) {
+                const int row0 = p.a_shift ? q0 - p.halo : q0 + (kh - 1) * p.in_Wp + (kw - 1);
+                for (int i = 0; i < p.a_pieces; ++i)
+                  tma_load_2d(dst + (size_t)i * p.a_box_rows * span, &p.tmA, &ctl->a_full[s], chunk * p.ck,
+                              row0 + i * p.a_box_rows);
+              } else {
+                tma_load_4d(dst, &p.tmA, &ctl->a_full[s], chunk * p.ck, 2 * wo0 + kw - 1, 2 * ho0 + kh - 1, n0);
+              }
+              ++a_it;
+            }
+            const uint32_t s = b_it % p.b_stages, ph = (b_it / p.b_stages) & 1;
+            mbar_wait(&ctl->b_empty[s], ph ^ 1);
+            mbar_expect_tx(&ctl->b_full[s], p.b_tx_bytes);
+            tma_load_3d(b_smem + (size_t)s * p.b_stage_bytes, &p.tmB, &ctl->b_full[s], chunk * p.ck, nti * p.nt,
+                        tap);
+            ++b_it;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.nt);
+      const int ksteps = p.ck / 16;
+      uint32_t a_it = 0, b_it = 0, acc_it = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const uint32_t buf = acc_it % p.n_accbuf, aph = (acc_it / p.n_accbuf) & 1;
+        mbar_wait(&ctl->acc_empty[buf], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + buf * acc_cols;
+        uint32_t a_stage = 0;
+        for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
+          for (int tap = 0; tap < p.taps; ++tap) {
+            if (!p.a_shift || tap == 0) {
+              a_stage = a_it % p.a_stages;
+              mbar_wait(&ctl->a_full[a_stage], (a_it / p.a_stages) & 1);
+            }
+            const uint32_t bs = b_it % p.b_stages;
+            mbar_wait(&ctl->b_full[bs], (b_it / p.b_stages) & 1);
+            tc_fence_after();
+            uint32_t row_off = 0;
+            if (p.a_shift && p.taps == 9) row_off = (uint32_t)((tap / 3) * p.in_Wp + (tap % 3));
+            const uint32_t a_addr = smem_u32(a_smem + (size_t)a_stage * p.a_stage_bytes) + row_off * span;
+            const uint32_t b_addr = smem_u32(b_smem + (size_t)bs * p.b_stage_bytes);
+            for (int m = 0; m < p.mb; ++m) {
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t da = make_kmajor_desc(a_addr + (uint32_t)m * 128u * span + (uint32_t)k * 32u, span);
+                const uint64_t db = make_kmajor_desc(b_addr + (uint32_t)k * 32u, span);
+                umma_bf16(d_base + (uint32_t)(m * p.nt), da, db, idesc, (chunk | tap | k) != 0);
+              }
+            }
+            umma_commit(&ctl->b_empty[bs]);
+            ++b_it;
+            if (!p.a_shift || tap == p.taps - 1) {
+              umma_commit(&ctl->a_empty[a_stage]);
+              ++a_it;
+            }
+          }
+        }
+        umma_commit(&ctl->acc_full[buf]);
+        ++acc_it;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+    uint32_t acc_it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nti = (int)(tile % p.n_ntiles);
+      const long long mt = tile / p.n_ntiles;
+      const uint32_t buf = acc_it % p.n_accbuf, aph = (acc_it / p.n_accbuf) & 1;
+      mbar_wait(&ctl->acc_full[buf], aph);
+      tc_fence_after();
+      for (int m = 0; m < p.mb; ++m) {
+        const int r = m * 128 + quarter * 32 + lane;
+        RowPos pos;
+        if (p.mode == 0) {
+          const long long q = mt * (128 * p.mb) + r;
+          pos.valid = q < p.P;
+          pos.q = (int)q;
+          pos.w = pos.q % p.Wp;
+          const int t = pos.q / p.Wp;
+          pos.h = t % p.Hp;
+          pos.n = t / p.Hp;
+          pos.is_pad = (pos.w == p.W) || (pos.h == p.H);
+        } else {
+          const int wl = r % p.bw, t = r / p.bw;
+          const int hl = t % p.bh, nl = t / p.bh;
+          pos.w = (int)(mt % p.tiles_w) * p.bw + wl;
+          pos.h = (int)((mt / p.tiles_w) % p.tiles_h) * p.bh + hl;
+          pos.n = (int)(mt / ((long long)p.tiles_w * p.tiles_h)) * p.bn + nl;
+          pos.valid = pos.w < p.W && pos.h < p.H && pos.n < p.N;
+          pos.is_pad = false;
+          pos.q = (pos.n * p.Hp + pos.h) * p.Wp + pos.w;
+        }
+        const uint32_t t_row = tmem_base + buf * acc_cols + (uint32_t)(m * p.nt) + ((uint32_t)(quarter * 32) << 16);
+        int c = 0;
+        for (; c + 32 <= p.nt; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)c, v);
+          tmem_ld_wait();
+          epilogue_store<32>(p, v, nti * p.nt + c, pos);
+        }
+        if (c < p.nt) {
+          uint32_t v[16];
+          tmem_ld16(t_row + (uint32_t)c, v);
+          tmem_ld_wait();
+          epilogue_store<16>(p, v, nti * p.nt + c, pos);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
+      ++acc_it;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+           const cuuint32_t* box, const cuuint32_t* estrides, uint32_t span) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return 1; }
+  CUtensorMapSwizzle sw = span == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                      : (span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                  strides_bytes, box, estrides, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims %llu,%llu box %u,%u span %u", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1], span);
+    return 1;
+  }
+  return 0;
+}
+
+int pick_ck(int cin) {
+  if (cin % 64 == 0) return 64;
+  if (cin % 32 == 0) return 32;
+  if (cin % 16 == 0) return 16;
+  return 0;
+}
+
+int pick_nt(int cout_pad) {
+  // largest multiple of 16 that divides cout_pad and is <= 128
+  for (int nt = 128; nt >= 16; nt -= 16)
+    if (cout_pad % nt == 0) return nt;
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_bytes) {
+  ConvParams& p = *pp;
+  memset(&p, 0, sizeof(p));
+  const PaddedGeom& gi = s.in_geom;
+  if (!(s.ksize == 1 || s.ksize == 3) || !(s.stride == 1 || s.stride == 2) || (s.stride == 2 && s.ksize != 3)) {
+    set_error("conv: unsupported ksize %d / stride %d", s.ksize, s.stride);
+    return 1;
+  }
+  if (s.cout_pad % 16 || s.cout_pad < s.cout || (!s.out_nchw && s.cout != s.cout_pad)) {
+    set_error("conv: bad cout %d / cout_pad %d", s.cout, s.cout_pad);
+    return 1;
+  }
+  p.ck = pick_ck(gi.C);
+  p.nt = pick_nt(s.cout_pad);
+  if (!p.ck || !p.nt) { set_error("conv: channels must be multiples of 16 (cin %d cout_pad %d)", gi.C, s.cout_pad); return 1; }
+  if (s.stride == 2 && ((gi.H | gi.W) & 1)) { set_error("conv: stride 2 needs even H, W"); return 1; }
+  const uint32_t span = 2u * p.ck;
+  p.mode = s.stride == 2 ? 1 : 0;
+  p.taps = s.ksize * s.ksize;
+  p.n_chunks = gi.C / p.ck;
+  p.n_ntiles = s.cout_pad / p.nt;
+  p.in_Wp = gi.Wp();
+  p.N = gi.N;
+  p.H = gi.H / s.stride;
+  p.W = gi.W / s.stride;
+  p.Hp = p.H + 1;
+  p.Wp = p.W + 1;
+  p.P = (long long)p.N * p.Hp * p.Wp;
+  if ((long long)gi.pixels() >= (1ll << 31) || p.P >= (1ll << 31)) { set_error("conv: tensor too large"); return 1; }
+
+  // accumulator blocks per tile: keep two accumulator buffers in 512 TMEM columns when possible
+  int mb = s.force_mb ? s.force_mb : (p.nt <= 64 ? 3 : 2);
+  while (mb > 1 && mb * p.nt > 256) --mb;
+  if (p.mode == 0) {
+    // do not make tiles larger than the problem
+    while (mb > 1 && (long long)(mb - 1) * 128 >= p.P) --mb;
+  }
+
+  if (p.mode == 0) {
+    p.mb = mb;
+    p.a_shift = (p.taps == 9 && !s.force_tap_reload) ? 1 : 0;
+    p.halo = p.a_shift ? p.in_Wp + 1 : 0;
+    const int rows_needed = 128 * mb + 2 * p.halo;
+    p.a_pieces = (rows_needed + 255) / 256;
+    p.a_box_rows = (((rows_needed + p.a_pieces - 1) / p.a_pieces) + 7) & ~7;
+    p.total_tiles = ((p.P + 128 * mb - 1) / (128 * mb)) * p.n_ntiles;
+    cuuint64_t dims[2] = {(cuuint64_t)gi.C, (cuuint64_t)gi.pixels()};
+    cuuint64_t strides[1] = {(cuuint64_t)gi.C * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.ck, (cuuint32_t)p.a_box_rows};
+    cuuint32_t es[2] = {1, 1};
+    if (encode(&p.tmA, s.in, 2, dims, strides, box, es, span)) return 1;
+  } else {
+    // structured tile (bw x bh x bn output pixels) with bw*bh*bn = 128*mb
+    bool found = false;
+    for (; mb >= 1 && !found; --mb) {
+      const int R = 128 * mb;
+      for (int bw = p.W; bw >= 1 && !found; --bw) {
+        if (p.W % bw || R % bw || bw > 128) continue;
+        const int rem = R / bw;
+        for (int bh = p.H; bh >= 1 && !found; --bh) {
+          if (p.H % bh || rem % bh || bh > 128) continue;
+          const int bn = rem / bh;
+          if (bn > 256) continue;
+          p.bw = bw; p.bh = bh; p.bn = bn; p.mb = mb;
+          found = true;
+        }
+      }
+    }
+    if (!found) { set_error("conv: no structured tile for %dx%d output", p.H, p.W); return 1; }
+    p.a_shift = 0;
+    p.halo = 0;
+    p.a_pieces = 1;
+    p.a_box_rows = 128 * p.mb;
+    p.tiles_w = p.W / p.bw;
+    p.tiles_h = p.H / p.bh;
+    p.tiles_n = (p.N + p.bn - 1) / p.bn;
+    p.total_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_ntiles;
+    cuuint64_t dims[4] = {(cuuint64_t)gi.C, (cuuint64_t)gi.Wp(), (cuuint64_t)gi.Hp(), (cuuint64_t)gi.N};
+    cuuint64_t strides[3] = {(cuuint64_t)gi.C * 2, (cuuint64_t)gi.C * 2 * gi.Wp(),
+                             (cuuint64_t)gi.C * 2 * gi.Wp() * gi.Hp()};
+    cuuint32_t box[4] = {(cuuint32_t)p.ck, (cuuint32_t)(2 * p.bw), (cuuint32_t)(2 * p.bh), (cuuint32_t)p.bn};
+    cuuint32_t es[4] = {1, 2, 2, 1};
+    if (encode(&p.tmA, s.in, 4, dims, strides, box, es, span)) return 1;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)gi.C, (cuuint64_t)s.cout_pad, (cuuint64_t)p.taps};
+    cuuint64_t strides[2] = {(cuuint64_t)gi.C * 2, (cuuint64_t)gi.C * 2 * s.cout_pad};
+    cuuint32_t box[3] = {(cuuint32_t)p.ck, (cuuint32_t)p.nt, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    if (encode(&p.tmB, s.weights, 3, dims, strides, box, es, span)) return 1;
+  }
+
+  p.a_tx_bytes = (uint32_t)p.a_pieces * p.a_box_rows * span;
+  p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
+  p.b_tx_bytes = (uint32_t)p.nt * span;
+  p.b_stage_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
+  p.n_accbuf = (2 * p.mb * p.nt <= 512) ? 2 : 1;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(p.n_accbuf * p.mb * p.nt)) cols <<= 1;
+  p.tmem_cols = cols;
+
+  // ring depths: as many as fit, weights ring up to one chunk's worth of taps (+ slack), activations >= 2
+  const size_t budget = kMaxSmem - kCtlBytes - 1024;
+  const int a_loads_per_tile = p.n_chunks * (p.a_shift || p.taps == 1 ? 1 : p.taps);
+  int a_st = 2, b_st = 2;
+  auto used = [&](int a, int b) { return (size_t)a * p.a_stage_bytes + (size_t)b * p.b_stage_bytes; };
+  if (used(2, 2) > budget) { a_st = 1; }
+  if (used(a_st, b_st) > budget) { set_error("conv: tile does not fit shared memory"); return 1; }
+  const int a_want = a_loads_per_tile >= 4 ? 4 : (p.a_shift ? 3 : 4);
+  const int b_want = 8;
+  bool grew = true;
+  while (grew) {
+    grew = false;
+    if (b_st < b_want && b_st < kMaxStages && used(a_st, b_st + 1) <= budget) { ++b_st; grew = true; }
+    if (a_st < a_want && a_st < kMaxStages && used(a_st + 1, b_st) <= budget) { ++a_st; grew = true; }
+  }
+  p.a_stages = a_st;
+  p.b_stages = b_st;
+  *smem_bytes = kCtlBytes + 1024 + used(a_st, b_st);
+
+  p.out = s.out;
+  p.bias = s.bias;
+  p.residual = s.residual;
+  p.n_up = s.n_up;
+  for (int i = 0; i < kMaxUp; ++i) { p.up_src[i] = s.up_src[i]; p.up_shift[i] = s.up_shift[i]; }
+  p.relu = s.relu;
+  p.out_nchw = s.out_nchw;
+  p.cout = s.cout;
+  p.cout_pad = s.cout_pad;
+
+  long long g = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  if (s.max_ctas > 0 && g > s.max_ctas) g = s.max_ctas;
+  *grid = (int)g;
+  return 0;
+}
+
+int conv_launch_prepared(const ConvParams& p, int grid, size_t smem_bytes, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+    attr_set = true;
+  }
+  if (grid <= 0) return 0;
+  conv_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("conv_tc_kernel launch: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+int conv_launch(const ConvSpec& spec, cudaStream_t stream) {
+  ConvParams p;
+  int grid = 0;
+  size_t smem = 0;
+  if (conv_prepare(spec, &p, &grid, &smem)) return 1;
+  return conv_launch_prepared(p, grid, smem, stream);
+}
+
+}  // namespace stl

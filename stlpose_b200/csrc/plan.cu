@@ -1,0 +1,347 @@
+// Whole-network plan: HRNet topology -> static schedule of fused convolution launches.
+//
+// Mirrors the wiring of /root/reference/src/models/HRnet.py (PoseHighResolutionNet.forward :433-468,
+// HighResolutionModule.forward :248-266, transitions :341-380) but as a flat list of device ops over pooled
+// activation buffers; BatchNorm is folded into the packed weights, ReLU / residual / fuse-layer additions live in
+// the convolution epilogues.
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "aux_kernels.h"
+#include "conv.h"
+#include "plan.h"
+
+namespace stl {
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct Plan::Builder {
+  Plan& P;
+  std::map<std::tuple<int, int, int>, std::vector<int>> free_slots;
+
+  explicit Builder(Plan& p) : P(p) {}
+
+  int layer(const std::string& conv_key, const std::string& bn_key, int cout, int cin, int k, int stride) {
+    Layer L;
+    L.conv_key = conv_key;
+    L.bn_key = bn_key;
+    L.cout = cout; L.cin = cin; L.k = k; L.stride = stride;
+    L.cout_pad = (int)align_up(cout, 16);
+    L.is_stem = (cin == 3);
+    L.w_off = P.weight_bytes;
+    if (L.is_stem) {
+      P.weight_bytes += align_up(sizeof(float) * 27 * 64, 256);
+    } else {
+      P.weight_bytes += align_up((size_t)k * k * L.cout_pad * cin * 2, 256);
+    }
+    L.b_off = P.weight_bytes;
+    P.weight_bytes += align_up(sizeof(float) * L.cout_pad, 256);
+    P.layers.push_back(L);
+    return (int)P.layers.size() - 1;
+  }
+
+  int acquire(int C, int H, int W) {
+    auto key = std::make_tuple(C, H, W);
+    auto& fl = free_slots[key];
+    if (!fl.empty()) {
+      int id = fl.back();
+      fl.pop_back();
+      return id;
+    }
+    Plan::Slot s;
+    s.C = C; s.H = H; s.W = W;
+    P.slots.push_back(s);
+    return (int)P.slots.size() - 1;
+  }
+  void release(int id) {
+    const Plan::Slot& s = P.slots[id];
+    free_slots[std::make_tuple(s.C, s.H, s.W)].push_back(id);
+  }
+
+  void conv(int layer, int in, int out, int res, bool relu, int n_up = 0, const int* up = nullptr,
+            const int* up_shift = nullptr, bool out_nchw = false) {
+    Plan::Op op;
+    op.kind = P.layers[layer].is_stem ? Plan::OP_STEM : Plan::OP_CONV;
+    op.layer = layer; op.in = in; op.out = out; op.res = res; op.relu = relu; op.out_nchw = out_nchw;
+    op.n_up = n_up;
+    for (int i = 0; i < n_up; ++i) { op.up[i] = up[i]; op.up_shift[i] = up_shift[i]; }
+    P.ops.push_back(op);
+  }
+  void fuse(int x, int out, int n_up, const int* up, const int* up_shift) {
+    Plan::Op op;
+    op.kind = Plan::OP_FUSE;
+    op.in = x; op.out = out; op.n_up = n_up; op.relu = true;
+    for (int i = 0; i < n_up; ++i) { op.up[i] = up[i]; op.up_shift[i] = up_shift[i]; }
+    P.ops.push_back(op);
+  }
+
+  void build() {
+    const stl_hrnet_cfg& c = P.cfg;
+    const int H4 = c.image_h / 4, W4 = c.image_w / 4;
+    const int ch[4] = {c.width, 2 * c.width, 4 * c.width, 8 * c.width};
+    auto bh = [&](int b) { return H4 >> b; };
+    auto bw = [&](int b) { return W4 >> b; };
+    char k1[128], k2[128];
+
+    // stem (HRnet.py:434-439)
+    int t0 = acquire(64, c.image_h / 2, c.image_w / 2);
+    conv(layer("conv1", "bn1", 64, 3, 3, 2), -1, t0, -1, true);
+    int x = acquire(64, H4, W4);
+    conv(layer("conv2", "bn2", 64, 64, 3, 2), t0, x, -1, true);
+    release(t0);
+
+    // layer1: 4 Bottlenecks (HRnet.py:297, 64-102)
+    for (int b = 0; b < 4; ++b) {
+      const int cin = b == 0 ? 64 : 256;
+      snprintf(k1, sizeof k1, "layer1.%d", b);
+      const std::string p = k1;
+      int a = acquire(64, H4, W4);
+      conv(layer(p + ".conv1", p + ".bn1", 64, cin, 1, 1), x, a, -1, true);
+      int bb = acquire(64, H4, W4);
+      conv(layer(p + ".conv2", p + ".bn2", 64, 64, 3, 1), a, bb, -1, true);
+      release(a);
+      int res = x;
+      if (b == 0) {
+        res = acquire(256, H4, W4);
+        conv(layer(p + ".downsample.0", p + ".downsample.1", 256, 64, 1, 1), x, res, -1, false);
+        release(x);
+      }
+      int o = acquire(256, H4, W4);
+      conv(layer(p + ".conv3", p + ".bn3", 256, 64, 1, 1), bb, o, res, true);
+      release(bb);
+      release(res);
+      x = o;
+    }
+
+    // transition1 (HRnet.py:442-447)
+    std::vector<int> xs(2);
+    xs[0] = acquire(ch[0], bh(0), bw(0));
+    conv(layer("transition1.0.0", "transition1.0.1", ch[0], 256, 3, 1), x, xs[0], -1, true);
+    xs[1] = acquire(ch[1], bh(1), bw(1));
+    conv(layer("transition1.1.0.0", "transition1.1.0.1", ch[1], 256, 3, 2), x, xs[1], -1, true);
+    release(x);
+
+    for (int stage = 2; stage <= 4; ++stage) {
+      const int nb = stage;
+      if (stage > 2) {  // new lowest-resolution branch from the previous stage's last output (HRnet.py:450-463)
+        snprintf(k1, sizeof k1, "transition%d.%d.0.0", stage - 1, nb - 1);
+        snprintf(k2, sizeof k2, "transition%d.%d.0.1", stage - 1, nb - 1);
+        int nbuf = acquire(ch[nb - 1], bh(nb - 1), bw(nb - 1));
+        conv(layer(k1, k2, ch[nb - 1], ch[nb - 2], 3, 2), xs[nb - 2], nbuf, -1, true);
+        xs.push_back(nbuf);
+      }
+      const int n_mod = c.stage_modules[stage - 2];
+      for (int m = 0; m < n_mod; ++m) {
+        const int n_out = (stage == 4 && m == n_mod - 1) ? 1 : nb;  // HRnet.py:413-416
+        snprintf(k1, sizeof k1, "stage%d.%d", stage, m);
+        const std::string mp = k1;
+        // branches: `blocks` BasicBlocks each (HRnet.py:32-61, 252-253)
+        for (int b = 0; b < nb; ++b) {
+          for (int k = 0; k < c.blocks; ++k) {
+            snprintf(k1, sizeof k1, "%s.branches.%d.%d", mp.c_str(), b, k);
+            const std::string bp = k1;
+            int tmp = acquire(ch[b], bh(b), bw(b));
+            conv(layer(bp + ".conv1", bp + ".bn1", ch[b], ch[b], 3, 1), xs[b], tmp, -1, true);
+            int o = acquire(ch[b], bh(b), bw(b));
+            conv(layer(bp + ".conv2", bp + ".bn2", ch[b], ch[b], 3, 1), tmp, o, xs[b], true);
+            release(tmp);
+            release(xs[b]);
+            xs[b] = o;
+          }
+        }
+        // fuse layers (HRnet.py:188-243, 255-264)
+        std::vector<int> ys(n_out);
+        for (int i = 0; i < n_out; ++i) {
+          int z[kMaxUp], zs[kMaxUp], nz = 0;
+          for (int j = i + 1; j < nb; ++j) {
+            snprintf(k1, sizeof k1, "%s.fuse_layers.%d.%d.0", mp.c_str(), i, j);
+            snprintf(k2, sizeof k2, "%s.fuse_layers.%d.%d.1", mp.c_str(), i, j);
+            z[nz] = acquire(ch[i], bh(j), bw(j));
+            zs[nz] = j - i;
+            conv(layer(k1, k2, ch[i], ch[j], 1, 1), xs[j], z[nz], -1, false);
+            ++nz;
+          }
+          int y = acquire(ch[i], bh(i), bw(i));
+          if (i == 0) {
+            fuse(xs[0], y, nz, z, zs);
+          } else {
+            int running = xs[i];
+            for (int j = 0; j < i; ++j) {
+              int t = xs[j];
+              for (int k = 0; k < i - j; ++k) {
+                const bool last = k == i - j - 1;
+                snprintf(k1, sizeof k1, "%s.fuse_layers.%d.%d.%d.0", mp.c_str(), i, j, k);
+                snprintf(k2, sizeof k2, "%s.fuse_layers.%d.%d.%d.1", mp.c_str(), i, j, k);
+                if (!last) {
+                  int t2 = acquire(ch[j], bh(j + k + 1), bw(j + k + 1));
+                  conv(layer(k1, k2, ch[j], ch[j], 3, 2), t, t2, -1, true);
+                  if (t != xs[j]) release(t);
+                  t = t2;
+                } else {
+                  const bool final_term = j == i - 1;
+                  conv(layer(k1, k2, ch[i], ch[j], 3, 2), t, y, running, final_term, final_term ? nz : 0, z, zs);
+                  if (t != xs[j]) release(t);
+                  running = y;
+                }
+              }
+            }
+          }
+          for (int u = 0; u < nz; ++u) release(z[u]);
+          ys[i] = y;
+        }
+        for (int b = 0; b < nb; ++b) release(xs[b]);
+        if (n_out == nb) {
+          xs = ys;
+        } else {
+          xs.assign(1, ys[0]);
+        }
+      }
+    }
+    // head (HRnet.py:331-337, 466): 1x1 conv with bias, no activation, fp32 NCHW out
+    conv(layer("final_layer", "", c.num_joints, ch[0], 1, 1), xs[0], -1, -1, false, 0, nullptr, nullptr, true);
+    release(xs[0]);
+  }
+};
+
+Plan* Plan::create(const stl_hrnet_cfg& cfg) {
+  if (cfg.width < 16 || cfg.width % 16 || cfg.num_joints < 1 || cfg.num_joints > 64 || cfg.blocks < 1 ||
+      cfg.image_h % 32 || cfg.image_w % 32 || cfg.image_h < 32 || cfg.image_w < 32) {
+    set_error("plan: unsupported config (width %d joints %d blocks %d image %dx%d)", cfg.width, cfg.num_joints,
+              cfg.blocks, cfg.image_h, cfg.image_w);
+    return nullptr;
+  }
+  for (int i = 0; i < 3; ++i)
+    if (cfg.stage_modules[i] < 1) { set_error("plan: stage_modules must be >= 1"); return nullptr; }
+  Plan* p = new Plan();
+  p->cfg = cfg;
+  Builder b(*p);
+  b.build();
+  return p;
+}
+
+size_t Plan::workspace_bytes(int n_images) const {
+  size_t total = 0;
+  for (const Slot& s : slots) {
+    PaddedGeom g{n_images, s.H, s.W, s.C};
+    total += align_up(g.bytes(), 1024);
+  }
+  return total;
+}
+
+int Plan::pack_conv(int index, const float* w, const float* gamma, const float* beta, const float* mean,
+                    const float* var, const float* cbias, float eps, void* arena, cudaStream_t st) {
+  if (index < 0 || index >= (int)layers.size()) { set_error("pack_conv: index %d out of range", index); return 1; }
+  const Layer& L = layers[index];
+  uint8_t* base = reinterpret_cast<uint8_t*>(arena);
+  bound = false;  // packed parameters changed; tensor maps stay valid but be conservative
+  if (L.is_stem) {
+    if (!gamma) { set_error("pack_conv: stem needs BatchNorm parameters"); return 1; }
+    return pack_stem(w, gamma, beta, mean, var, eps, reinterpret_cast<float*>(base + L.w_off),
+                     reinterpret_cast<float*>(base + L.b_off), st);
+  }
+  return pack_weights(w, gamma, beta, mean, var, cbias, eps, L.cout, L.cin, L.k, L.cout_pad, L.cin,
+                      reinterpret_cast<__nv_bfloat16*>(base + L.w_off), reinterpret_cast<float*>(base + L.b_off), st);
+}
+
+int Plan::bind(int n_images, const void* arena, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  if (bound && n_images == bound_images && arena == bound_arena && workspace == bound_ws) return 0;
+  const size_t need = workspace_bytes(n_images);
+  if (ws_bytes < need) { set_error("plan: workspace too small (%zu < %zu)", ws_bytes, need); return 1; }
+  if (reinterpret_cast<uintptr_t>(workspace) % 1024 || reinterpret_cast<uintptr_t>(arena) % 256) {
+    set_error("plan: workspace must be 1024-byte aligned and the weight arena 256-byte aligned");
+    return 1;
+  }
+  size_t off = 0;
+  slot_ptr.resize(slots.size());
+  for (size_t i = 0; i < slots.size(); ++i) {
+    PaddedGeom g{n_images, slots[i].H, slots[i].W, slots[i].C};
+    slot_ptr[i] = reinterpret_cast<uint8_t*>(workspace) + off;
+    off += align_up(g.bytes(), 1024);
+  }
+  // zero cells of the padded layout are established once; no kernel ever writes a non-zero there
+  cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
+  if (e != cudaSuccess) { set_error("plan: memset workspace: %s", cudaGetErrorString(e)); return 1; }
+
+  const uint8_t* wbase = reinterpret_cast<const uint8_t*>(arena);
+  prepared.assign(ops.size(), Prepared());
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const Op& op = ops[i];
+    if (op.kind != OP_CONV) continue;
+    const Layer& L = layers[op.layer];
+    const Slot& si = slots[op.in];
+    ConvSpec s;
+    s.in = reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.in]);
+    s.in_geom = PaddedGeom{n_images, si.H, si.W, si.C};
+    s.out = op.out >= 0 ? slot_ptr[op.out] : nullptr;  // head output is patched per forward
+    s.cout = L.cout;
+    s.cout_pad = L.cout_pad;
+    s.ksize = L.k;
+    s.stride = L.stride;
+    s.weights = reinterpret_cast<const __nv_bfloat16*>(wbase + L.w_off);
+    s.bias = reinterpret_cast<const float*>(wbase + L.b_off);
+    s.residual = op.res >= 0 ? reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.res]) : nullptr;
+    s.n_up = op.n_up;
+    for (int u = 0; u < op.n_up; ++u) {
+      s.up_src[u] = reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.up[u]]);
+      s.up_shift[u] = op.up_shift[u];
+    }
+    s.relu = op.relu;
+    s.out_nchw = op.out_nchw;
+    s.force_tap_reload = tap_reload;
+    Prepared& pr = prepared[i];
+    if (conv_prepare(s, &pr.params, &pr.grid, &pr.smem)) return 1;
+  }
+  bound = true;
+  bound_images = n_images;
+  bound_arena = arena;
+  bound_ws = workspace;
+  return 0;
+}
+
+int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void* arena, void* workspace,
+                  size_t ws_bytes, cudaStream_t st) {
+  if (B <= 0) { set_error("plan: batch must be positive"); return 1; }
+  const int n_images = flip_pair ? 2 * B : B;
+  if (bind(n_images, arena, workspace, ws_bytes, st)) return 1;
+  const uint8_t* wbase = reinterpret_cast<const uint8_t*>(arena);
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const Op& op = ops[i];
+    switch (op.kind) {
+      case OP_STEM: {
+        const Layer& L = layers[op.layer];
+        if (stem_conv1(x, reinterpret_cast<const float*>(wbase + L.w_off),
+                       reinterpret_cast<const float*>(wbase + L.b_off),
+                       reinterpret_cast<__nv_bfloat16*>(slot_ptr[op.out]), n_images, B, cfg.image_h, cfg.image_w, st))
+          return 1;
+        break;
+      }
+      case OP_CONV: {
+        Prepared& pr = prepared[i];
+        if (op.out_nchw) pr.params.out = heat;
+        if (conv_launch_prepared(pr.params, pr.grid, pr.smem, st)) return 1;
+        break;
+      }
+      case OP_FUSE: {
+        const Slot& so = slots[op.out];
+        const __nv_bfloat16* z[kMaxUp];
+        for (int u = 0; u < op.n_up; ++u) z[u] = reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.up[u]]);
+        if (fuse_sum(reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.in]), z, op.up_shift, op.n_up,
+                     reinterpret_cast<__nv_bfloat16*>(slot_ptr[op.out]), n_images, so.H, so.W, so.C, st))
+          return 1;
+        break;
+      }
+    }
+  }
+  return 0;
+}
+
+}  // namespace stl

@@ -1,0 +1,62 @@
+// Plan: static schedule for one HRNet configuration (see plan.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/stlpose_b200.h"
+#include "conv.h"
+
+namespace stl {
+
+struct Plan {
+  struct Layer {
+    std::string conv_key, bn_key;
+    int cout, cin, k, stride, cout_pad;
+    bool is_stem;
+    size_t w_off, b_off;
+  };
+  struct Slot { int C, H, W; };
+  enum OpKind { OP_STEM, OP_CONV, OP_FUSE };
+  struct Op {
+    OpKind kind = OP_CONV;
+    int layer = -1, in = -1, out = -1, res = -1;
+    int n_up = 0;
+    int up[kMaxUp] = {-1, -1, -1};
+    int up_shift[kMaxUp] = {0, 0, 0};
+    bool relu = false, out_nchw = false;
+  };
+  struct Prepared {
+    ConvParams params;
+    int grid = 0;
+    size_t smem = 0;
+  };
+  struct Builder;
+
+  stl_hrnet_cfg cfg{};
+  std::vector<Layer> layers;
+  std::vector<Slot> slots;
+  std::vector<Op> ops;
+  size_t weight_bytes = 0;
+  int tap_reload = 0;  // debugging: force one TMA load per filter tap
+
+  // binding state
+  bool bound = false;
+  int bound_images = 0;
+  const void* bound_arena = nullptr;
+  void* bound_ws = nullptr;
+  std::vector<uint8_t*> slot_ptr;
+  std::vector<Prepared> prepared;
+
+  static Plan* create(const stl_hrnet_cfg& cfg);
+  size_t workspace_bytes(int n_images) const;
+  int pack_conv(int index, const float* w, const float* gamma, const float* beta, const float* mean,
+                const float* var, const float* cbias, float eps, void* arena, cudaStream_t st);
+  int bind(int n_images, const void* arena, void* workspace, size_t ws_bytes, cudaStream_t st);
+  int forward(const float* x, int B, int flip_pair, float* heat, const void* arena, void* workspace, size_t ws_bytes,
+              cudaStream_t st);
+};
+
+}  // namespace stl

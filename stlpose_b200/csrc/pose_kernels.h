@@ -1,0 +1,23 @@
+// Host launchers for the bandwidth-bound pose kernels (pose_kernels.cu). Return 0 on success; enqueue on `st`.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace stl {
+
+constexpr int kMaxJoints = 64;
+
+int flip_avg(const float* heat, const float* heat_f, float* out, int B, int J, int h, int w, const int* pairs,
+             int n_pairs, cudaStream_t st);
+int flip_back(const float* in, float* out, int B, int J, int h, int w, const int* pairs, int n_pairs,
+              cudaStream_t st);
+// heat_f may be null (plain decode). avg_out (may be null) receives the flip-averaged heatmaps when heat_f is given.
+// preds/center/scale may be null (heatmap-space decode only); refine=0 gives get_max_preds_hrnet's raw argmax.
+int decode(const float* heat, const float* heat_f, const float* center, const float* scale, int B, int J, int h,
+           int w, const int* pairs, int n_pairs, int refine, float* avg_out, float* preds, float* maxvals,
+           float* coords, cudaStream_t st);
+size_t mse_workspace_bytes();
+int mse_loss(const float* out, const float* tgt, const float* tw, int B, int J, int hw, float* loss, float* grad,
+             void* workspace, cudaStream_t st);
+
+}  // namespace stl

@@ -1,0 +1,55 @@
+"""GPU parity: the tcgen05 implicit-GEMM convolution vs torch fp32 conv2d on the same bf16-rounded operands.
+
+Tolerance: both sides multiply identical bf16 values and accumulate in fp32, so they differ only by summation
+order and the final bf16 rounding of our output (2^-9 relative): |diff| <= 1e-2 * max|ref|.
+"""
+import pytest
+
+from gpu_util import conv_case
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    # every conv family of SURVEY.md appendix A (W32) at small batch, plus W48 channel counts
+    dict(N=2, cin=32, cout=32, H=64, W=48, k=3, stride=1),
+    dict(N=3, cin=64, cout=64, H=32, W=24, k=3, stride=1, with_res=True),
+    dict(N=5, cin=128, cout=128, H=16, W=12, k=3, stride=1, with_res=True),
+    dict(N=9, cin=256, cout=256, H=8, W=6, k=3, stride=1),
+    dict(N=2, cin=64, cout=64, H=64, W=48, k=3, stride=1),
+    dict(N=2, cin=64, cout=256, H=64, W=48, k=1, stride=1, with_res=True),
+    dict(N=1, cin=256, cout=32, H=64, W=48, k=3, stride=1),
+    dict(N=2, cin=256, cout=64, H=64, W=48, k=1, stride=1),
+    dict(N=2, cin=64, cout=64, H=128, W=96, k=3, stride=2),
+    dict(N=1, cin=256, cout=64, H=64, W=48, k=3, stride=2),
+    dict(N=3, cin=32, cout=64, H=64, W=48, k=3, stride=2, with_res=True, n_up=2),
+    dict(N=3, cin=64, cout=128, H=32, W=24, k=3, stride=2, with_res=True, n_up=1),
+    dict(N=3, cin=32, cout=32, H=64, W=48, k=3, stride=2),
+    dict(N=5, cin=128, cout=256, H=16, W=12, k=3, stride=2, with_res=True),
+    dict(N=3, cin=64, cout=32, H=32, W=24, k=1, stride=1, relu=False),
+    dict(N=3, cin=256, cout=32, H=8, W=6, k=1, stride=1, relu=False),
+    dict(N=3, cin=32, cout=17, H=64, W=48, k=1, stride=1, relu=False, out_nchw=True, with_bias=True),
+    dict(N=4, cin=48, cout=48, H=24, W=18, k=3, stride=1),
+    dict(N=2, cin=96, cout=96, H=48, W=36, k=3, stride=1),
+    dict(N=3, cin=192, cout=192, H=24, W=18, k=3, stride=1),
+    dict(N=3, cin=384, cout=384, H=12, W=9, k=3, stride=1),
+    dict(N=2, cin=48, cout=96, H=96, W=72, k=3, stride=2),
+]
+
+
+@pytest.mark.parametrize("case", SHAPES, ids=lambda c: "c{cin}-{cout}_k{k}s{stride}_{H}x{W}_N{N}".format(**c))
+@pytest.mark.parametrize("impl", [0, 1])
+def test_conv_matches_torch(case, impl):
+    err, scale = conv_case(impl=impl, **case)
+    assert err <= 1e-2 * max(scale, 1.0), f"max err {err} vs ref max {scale}"
+
+
+def test_reference_kernel_matches_torch():
+    err, scale = conv_case(impl=2, N=2, cin=32, cout=32, H=16, W=12, k=3, stride=1, with_res=True)
+    assert err <= 1e-2 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("mb", [1, 2, 3])
+def test_conv_tile_sizes_and_persistence(mb):
+    # few CTAs -> every CTA walks many tiles: exercises ring wrap-around and accumulator double buffering
+    err, scale = conv_case(N=6, cin=64, cout=64, H=32, W=24, k=3, stride=1, with_res=True, force_mb=mb, max_ctas=3)
+    assert err <= 1e-2 * max(scale, 1.0)

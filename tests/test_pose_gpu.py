@@ -1,0 +1,114 @@
+"""GPU parity: decode / flip-average / loss kernels (through the C ABI) vs the CPU oracle and the golden fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pose_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_decode_matches_reference_goldens(golden, golden_inputs):
+    import stlpose_b200 as S
+    g = golden("decode.npz")
+    cases = {
+        "rand64": (golden_inputs["hm_rand_64x48"], golden_inputs["center_a"], golden_inputs["scale_a"]),
+        "rand96": (golden_inputs["hm_rand_96x72"], golden_inputs["center_b"], golden_inputs["scale_b"]),
+        "blobs": (g["hm_blobs_f16"].astype(np.float32),) + pose_oracle.synth_boxes(2, seed=9),
+    }
+    for tag, (hm, c, s) in cases.items():
+        p0, m0 = S.get_max_preds_hrnet(hm)
+        assert np.array_equal(p0, g[f"{tag}_max_preds"]) and np.array_equal(m0, g[f"{tag}_max_vals"])
+        preds, maxvals, coords = S.get_final_preds_hrnet(hm, c, s)
+        assert preds.dtype == np.float32 and preds.shape == (hm.shape[0], 17, 2)
+        assert np.array_equal(coords, g[f"{tag}_coords"])       # bit-exact indices and quarter-pixel offsets
+        assert np.array_equal(maxvals, g[f"{tag}_maxvals"])     # bit-exact max values
+        assert np.abs(preds - g[f"{tag}_preds"]).max() < 1e-3   # px; closed-form affine vs cv2
+        # CUDA-tensor input, tensor output
+        p2, m2, c2 = S.get_final_preds_hrnet(_cuda(hm), _cuda(c), _cuda(s), as_tensor=True)
+        assert p2.is_cuda and np.array_equal(c2.cpu().numpy(), coords)
+
+
+def test_decode_edge_cases():
+    import stlpose_b200 as S
+    rng = np.random.default_rng(5)
+    for (h, w) in ((64, 48), (96, 72), (16, 12), (9, 7)):     # 9x7: width not a multiple of 4 (scalar path)
+        hm = rng.standard_normal((6, 17, h, w)).astype(np.float32)
+        hm[0, 0] = -np.abs(hm[0, 0])          # all negative -> coords (0,0)
+        hm[1, 1] = 0.0                        # all ties at 0 -> idx 0, masked
+        hm[2, 2] = 1.0                        # all ties positive -> first index
+        hm[3, 3, 0, 0] = 50.0                 # corner peaks: no refinement
+        hm[3, 4, h - 1, w - 1] = 50.0
+        hm[3, 5, 1, 1] = 50.0                 # px = 1 is outside the refinement window (1 < px)
+        hm[3, 6, 2, 2] = 50.0                 # first refined position
+        hm[3, 7, h - 2, w - 2] = 50.0         # last refined position
+        hm[4, 8, 3, 3] = 7.0; hm[4, 8, 3, 4] = 7.0   # tie between neighbours -> lower index
+        c, s = pose_oracle.synth_boxes(6, seed=h)
+        ref = pose_oracle.get_final_preds(hm, c, s)
+        got = S.get_final_preds_hrnet(hm, c, s)
+        assert np.array_equal(got[2], ref[2]) and np.array_equal(got[1], ref[1])
+        assert np.abs(got[0] - ref[0]).max() < 1e-3
+    assert S.get_max_preds_hrnet(np.zeros((0, 17, 64, 48), np.float32)) == ([], [])
+
+
+def test_flip_average_bit_exact(golden, golden_inputs):
+    import stlpose_b200 as S
+    from stlpose_b200 import _lib
+    from stlpose_b200.transforms import _pairs_array
+    g = golden("flip.npz")
+    fb = S.flip_back(golden_inputs["flip_out_f"], S.FLIP_PAIRS)
+    assert not fb.is_cuda and np.array_equal(fb.numpy(), g["flip_back"])
+    a, f = _cuda(golden_inputs["flip_out"]), _cuda(golden_inputs["flip_out_f"])
+    out = torch.empty_like(a)
+    pairs, n = _pairs_array(S.FLIP_PAIRS)
+    B, J, h, w = a.shape
+    _lib.check(_lib.lib().stl_flip_avg(_lib.ptr(a), _lib.ptr(f), _lib.ptr(out), B, J, h, w, pairs, n,
+                                       _lib.current_stream()))
+    assert np.array_equal(out.cpu().numpy(), g["avg"])
+
+
+def test_fused_flip_decode_equals_two_step(golden_inputs):
+    from stlpose_b200.pose_parsing import _decode
+    import stlpose_b200 as S
+    a, f = golden_inputs["flip_out"], golden_inputs["flip_out_f"]
+    c, s = pose_oracle.synth_boxes(2, seed=1)
+    avg_ref = pose_oracle.flip_average(a, f)
+    ref = pose_oracle.get_final_preds(avg_ref, c, s)
+    preds, maxvals, coords, avg = _decode(a, c, s, True, heat_flipped=f, pairs=S.FLIP_PAIRS, want_avg=True)
+    assert np.array_equal(avg.cpu().numpy(), avg_ref)
+    assert np.array_equal(coords.cpu().numpy(), ref[2]) and np.array_equal(maxvals.cpu().numpy(), ref[1])
+    assert np.abs(preds.cpu().numpy() - ref[0]).max() < 1e-3
+
+
+def test_loss_forward_backward(golden, golden_inputs):
+    import stlpose_b200 as S
+    g = golden("loss.npz")
+    o = _cuda(golden_inputs["loss_out"]).requires_grad_(True)
+    loss = S.PersonMSELoss()(o, _cuda(golden_inputs["loss_tgt"]), _cuda(golden_inputs["loss_tw"]))
+    assert loss.dim() == 0
+    (loss * 3.0).backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-6 * max(1.0, abs(float(g["loss"])))
+    assert np.abs(o.grad.cpu().numpy() / 3.0 - g["grad"]).max() < 1e-9 + 1e-6 * np.abs(g["grad"]).max()
+    with pytest.raises(TypeError):
+        S.PersonMSELoss()(o, o)
+
+
+@pytest.mark.parametrize("batch", [1024, 16384])
+def test_decode_full_size_properties(batch):
+    """BASELINE config 5 sizes: size-independent properties instead of a CPU oracle pass."""
+    import stlpose_b200 as S
+    gen = torch.Generator(device="cuda").manual_seed(batch)
+    hm = torch.randn(batch, 17, 64, 48, device="cuda", generator=gen)
+    coords, maxvals = S.get_max_preds_hrnet(hm, as_tensor=True)
+    flat = hm.view(batch, 17, -1)
+    mx, idx = flat.max(dim=2)          # torch's own reduction as an independent check of value and location
+    assert torch.equal(maxvals[..., 0], mx)
+    gathered = flat.gather(2, (coords[..., 1] * 48 + coords[..., 0]).long().unsqueeze(-1))[..., 0]
+    assert torch.equal(gathered, mx)
+    # shifting a map by a constant does not move its argmax; scaling by a positive constant neither
+    c2, m2 = S.get_max_preds_hrnet(hm * 2.0 + 100.0, as_tensor=True)
+    assert torch.equal(c2, coords)
