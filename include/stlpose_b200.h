@@ -141,6 +141,22 @@ int stl_plan_forward(stl_plan* plan, const float* x_nchw, int B, int flip_pair, 
 /* Number of kernels one stl_plan_forward enqueues (for launch accounting). */
 int stl_plan_launches_per_forward(const stl_plan* plan);
 
+/* Measurement aid: same as stl_plan_forward, but brackets every launch with CUDA events on `stream`, waits for
+ * the stream and writes the per-launch durations (ms) to op_ms_host[stl_plan_launches_per_forward()]. */
+int stl_plan_forward_timed(stl_plan* plan, const float* x_nchw, int B, int flip_pair, float* heat_nchw,
+                           const void* weight_arena, void* workspace, size_t workspace_bytes, void* stream,
+                           float* op_ms_host);
+
+typedef struct stl_op_info {
+  int kind;                 /* 0 = stem conv (CUDA cores), 1 = tcgen05 conv, 2 = fuse-sum */
+  int layer;                /* conv index for stl_plan_conv_info, -1 for fuse-sum */
+  int cin, cout, ksize, stride, out_h, out_w;
+  double flops_per_image;   /* 2*MACs */
+  double bytes_per_image;   /* algorithmic: input + output (+ residual / upsampled addends) read or written once */
+  int grid, smem, mb, nt, ck, a_stages, b_stages, a_shift, tiles;   /* launch shape (valid once the plan has run) */
+} stl_op_info;
+int stl_plan_op_info(const stl_plan* plan, int op_index, stl_op_info* info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -182,4 +182,19 @@ int stl_plan_forward(stl_plan* plan, const float* x, int B, int flip_pair, float
 
 int stl_plan_launches_per_forward(const stl_plan* plan) { return plan ? (int)plan->impl->ops.size() : 0; }
 
+int stl_plan_forward_timed(stl_plan* plan, const float* x, int B, int flip_pair, float* heat, const void* arena,
+                           void* workspace, size_t ws_bytes, void* stream, float* op_ms_host) {
+  if (!have_device()) return 1;
+  if (!plan || !x || !heat || !arena || !workspace || !op_ms_host) {
+    set_error("stl_plan_forward_timed: null pointer");
+    return 1;
+  }
+  return plan->impl->forward(x, B, flip_pair, heat, arena, workspace, ws_bytes, (cudaStream_t)stream, op_ms_host);
+}
+
+int stl_plan_op_info(const stl_plan* plan, int op_index, stl_op_info* info) {
+  if (!plan) { set_error("stl_plan_op_info: null plan"); return 1; }
+  return plan->impl->op_info(op_index, info);
+}
+
 }  // extern "C"

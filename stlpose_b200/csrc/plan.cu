@@ -308,11 +308,21 @@ int Plan::bind(int n_images, const void* arena, void* workspace, size_t ws_bytes
 }
 
 int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void* arena, void* workspace,
-                  size_t ws_bytes, cudaStream_t st) {
+                  size_t ws_bytes, cudaStream_t st, float* op_ms_host) {
   if (B <= 0) { set_error("plan: batch must be positive"); return 1; }
   const int n_images = flip_pair ? 2 * B : B;
   if (bind(n_images, arena, workspace, ws_bytes, st)) return 1;
   const uint8_t* wbase = reinterpret_cast<const uint8_t*>(arena);
+  std::vector<cudaEvent_t> ev;
+  if (op_ms_host) {
+    ev.resize(ops.size() + 1);
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], st);
+  }
+  struct EvGuard {
+    std::vector<cudaEvent_t>& v;
+    ~EvGuard() { for (auto e : v) cudaEventDestroy(e); }
+  } guard{ev};
   for (size_t i = 0; i < ops.size(); ++i) {
     const Op& op = ops[i];
     switch (op.kind) {
@@ -340,6 +350,44 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
         break;
       }
     }
+    if (op_ms_host) cudaEventRecord(ev[i + 1], st);
+  }
+  if (op_ms_host) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("plan: timed forward failed: %s", cudaGetErrorString(e)); return 1; }
+    for (size_t i = 0; i < ops.size(); ++i) cudaEventElapsedTime(&op_ms_host[i], ev[i], ev[i + 1]);
+  }
+  return 0;
+}
+
+int Plan::op_info(int i, stl_op_info* info) const {
+  if (i < 0 || i >= (int)ops.size() || !info) { set_error("op_info: bad arguments"); return 1; }
+  memset(info, 0, sizeof(*info));
+  const Op& op = ops[i];
+  info->kind = (int)op.kind;
+  info->layer = op.layer;
+  const Slot* so = op.out >= 0 ? &slots[op.out] : nullptr;
+  const Slot* si = op.in >= 0 ? &slots[op.in] : nullptr;
+  if (op.kind == OP_FUSE) {
+    info->out_h = so->H; info->out_w = so->W; info->cout = so->C; info->cin = so->C;
+    info->bytes_per_image = 2.0 * so->H * so->W * so->C * 2;
+    for (int u = 0; u < op.n_up; ++u) info->bytes_per_image += (double)slots[op.up[u]].H * slots[op.up[u]].W * so->C * 2;
+    return 0;
+  }
+  const Layer& L = layers[op.layer];
+  const int ih = si ? si->H : cfg.image_h, iw = si ? si->W : cfg.image_w;
+  info->out_h = ih / L.stride; info->out_w = iw / L.stride;
+  info->cin = L.cin; info->cout = L.cout; info->ksize = L.k; info->stride = L.stride;
+  info->flops_per_image = 2.0 * L.cout * L.cin * L.k * L.k * info->out_h * info->out_w;
+  const double in_b = (double)ih * iw * L.cin * (si ? 2 : 4);
+  const double out_b = (double)info->out_h * info->out_w * L.cout * (op.out_nchw ? 4 : 2);
+  info->bytes_per_image = in_b + out_b + (op.res >= 0 ? out_b : 0);
+  for (int u = 0; u < op.n_up; ++u) info->bytes_per_image += (double)slots[op.up[u]].H * slots[op.up[u]].W * L.cout * 2;
+  if (bound && op.kind == OP_CONV) {
+    const Prepared& pr = prepared[i];
+    info->grid = pr.grid; info->smem = (int)pr.smem; info->mb = pr.params.mb; info->nt = pr.params.nt;
+    info->ck = pr.params.ck; info->a_stages = pr.params.a_stages; info->b_stages = pr.params.b_stages;
+    info->a_shift = pr.params.a_shift; info->tiles = (int)pr.params.total_tiles;
   }
   return 0;
 }

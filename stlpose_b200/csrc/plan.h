@@ -56,7 +56,8 @@ struct Plan {
                 const float* var, const float* cbias, float eps, void* arena, cudaStream_t st);
   int bind(int n_images, const void* arena, void* workspace, size_t ws_bytes, cudaStream_t st);
   int forward(const float* x, int B, int flip_pair, float* heat, const void* arena, void* workspace, size_t ws_bytes,
-              cudaStream_t st);
+              cudaStream_t st, float* op_ms_host = nullptr);
+  int op_info(int i, stl_op_info* info) const;
 };
 
 }  // namespace stl

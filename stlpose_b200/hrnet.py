@@ -287,6 +287,44 @@ class PoseHighResolutionNet(nn.Module):
                                           _lib.ptr(ws), ws.numel(), _lib.current_stream()))
         return heat
 
+    def profile_ops(self, x, flip_pair=False):
+        """Measurement aid: one forward with every launch bracketed by CUDA events.
+
+        Returns a list of dicts (one per launch): kind, conv key, shapes, algorithmic flops/bytes for this batch,
+        launch shape and the measured duration in ms."""
+        L = _lib.lib()
+        x = x.detach().float().contiguous()
+        B, _, H, W = x.shape
+        n_img = 2 * B if flip_pair else B
+        heat = torch.empty((n_img, self.num_joints, H // 4, W // 4), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            plan = self._plan(H, W)
+            self._ensure_packed(plan)
+            need = L.stl_plan_workspace_bytes(plan, n_img)
+            ws = self._workspaces.get((H, W))
+            if ws is None or ws.numel() < need:
+                ws = self._workspaces[(H, W)] = torch.empty(need, dtype=torch.uint8, device=x.device)
+            n_ops = L.stl_plan_launches_per_forward(plan)
+            ms = (ctypes.c_float * n_ops)()
+            _lib.check(L.stl_plan_forward_timed(plan, _lib.ptr(x), B, int(flip_pair), _lib.ptr(heat),
+                                                _lib.ptr(self._arena), _lib.ptr(ws), ws.numel(),
+                                                _lib.current_stream(), ms))
+        out = []
+        info, cinfo = _lib.OpInfo(), _lib.ConvInfo()
+        for i in range(n_ops):
+            _lib.check(L.stl_plan_op_info(plan, i, ctypes.byref(info)))
+            d = {n: getattr(info, n) for n, _ in _lib.OpInfo._fields_}
+            d["kind"] = ("stem", "conv_tc", "fuse_sum")[info.kind]
+            d["key"] = ""
+            if info.layer >= 0:
+                _lib.check(L.stl_plan_conv_info(plan, info.layer, ctypes.byref(cinfo)))
+                d["key"] = cinfo.conv_key.decode()
+            d["flops"] = info.flops_per_image * n_img
+            d["bytes"] = info.bytes_per_image * n_img
+            d["ms"] = ms[i]
+            out.append(d)
+        return out
+
     def forward(self, x):
         """HRnet.py:433-468 (eval mode)."""
         return self._run(x, flip_pair=False)

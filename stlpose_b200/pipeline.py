@@ -1,0 +1,80 @@
+"""Fixed-shape inference pipeline: forward (+ flip-test pass) + fused flip-average/decode, replayed as a CUDA graph.
+
+This is the evaluation hot loop of the reference (03_evaluate.py:124-152: forward_pass(flip=True) followed by
+get_final_preds_hrnet) for a fixed batch size, with every launch captured once and replayed.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .hrnet import PoseHighResolutionNet
+from .transforms import FLIP_PAIRS, _pairs_array
+
+
+class KeypointPipeline:
+    def __init__(self, model, batch, image_size=(256, 192), flip=True, use_graph=True, pairs=FLIP_PAIRS):
+        if not isinstance(model, PoseHighResolutionNet):
+            raise TypeError("KeypointPipeline expects stlpose_b200.PoseHighResolutionNet")
+        self.model, self.B, self.flip = model, int(batch), bool(flip)
+        dev = model.conv1.weight.device
+        if dev.type != "cuda":
+            raise _lib.StlError("model must live on a CUDA device")
+        self.device = dev
+        H, W = image_size
+        J = model.num_joints
+        self.x = torch.zeros((self.B, 3, H, W), dtype=torch.float32, device=dev)
+        self.center = torch.zeros((self.B, 2), dtype=torch.float32, device=dev)
+        self.scale = torch.ones((self.B, 2), dtype=torch.float32, device=dev)
+        self.preds = torch.zeros((self.B, J, 2), dtype=torch.float32, device=dev)
+        self.maxvals = torch.zeros((self.B, J, 1), dtype=torch.float32, device=dev)
+        self.coords = torch.zeros((self.B, J, 2), dtype=torch.float32, device=dev)
+        self.h, self.w = H // 4, W // 4
+        self._pairs, self._n_pairs = _pairs_array(pairs)
+        self.graph = None
+        self.launches_per_step = model.launches_per_forward(H, W) + 1
+        with torch.cuda.device(dev):
+            self._step_eager()                       # packs weights, binds the workspace, warms everything up
+            torch.cuda.synchronize()
+            if use_graph:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._step_eager()
+                torch.cuda.current_stream().wait_stream(s)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_eager()
+                self.graph = g
+
+    def _step_eager(self):
+        L = _lib.lib()
+        heat = self.model._run(self.x, flip_pair=self.flip)
+        self._heat = heat                            # keep the graph's output buffer alive
+        hf = heat[self.B:] if self.flip else None
+        _lib.check(L.stl_decode(_lib.ptr(heat), _lib.ptr(hf), _lib.ptr(self.center), _lib.ptr(self.scale), self.B,
+                                self.model.num_joints, self.h, self.w, self._pairs, self._n_pairs, 1, None,
+                                _lib.ptr(self.preds), _lib.ptr(self.maxvals), _lib.ptr(self.coords),
+                                _lib.current_stream()))
+
+    def step(self):
+        """Run one batch from the static device buffers (x, center, scale) into (preds, maxvals, coords)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_eager()
+
+    def __call__(self, x_host, center_host, scale_host, preds_host=None, maxvals_host=None):
+        """End-to-end call with HOST (ideally pinned) buffers: H2D copies, step, D2H of preds and maxvals.
+
+        Everything is enqueued on the current stream; synchronise it before reading the returned host tensors."""
+        self.x.copy_(x_host, non_blocking=True)
+        self.center.copy_(center_host, non_blocking=True)
+        self.scale.copy_(scale_host, non_blocking=True)
+        self.step()
+        if preds_host is None:
+            preds_host = torch.empty(tuple(self.preds.shape), dtype=torch.float32).pin_memory()
+            maxvals_host = torch.empty(tuple(self.maxvals.shape), dtype=torch.float32).pin_memory()
+        preds_host.copy_(self.preds, non_blocking=True)
+        maxvals_host.copy_(self.maxvals, non_blocking=True)
+        return preds_host, maxvals_host

@@ -73,7 +73,9 @@ def run_conv(x, w, bn=None, bias=None, stride=1, relu=False, residual=None, ups=
     if out_nchw:
         out = torch.full((N, cout, Ho, Wo), float("nan"), dtype=torch.float32, device=x.device)
     else:
-        out = torch.full((L.stl_padded_bytes(N, cout, Ho, Wo),), 0x7f, dtype=torch.uint8, device=x.device)
+        # zero cells as the engine's workspaces have them (stride-2 convs never touch them), every real cell
+        # poisoned with a huge value so that an unwritten output is caught
+        out = to_padded(torch.full((N, cout, Ho, Wo), 3.0e38, dtype=torch.float32, device=x.device))
     d.out = out.data_ptr(); d.Cout, d.Cout_pad = cout, cout_pad
     d.ksize, d.stride = k, stride
     d.w_packed = wp.data_ptr(); d.bias_packed = bp.data_ptr()
