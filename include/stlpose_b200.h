@@ -92,6 +92,8 @@ typedef struct stl_conv_desc {
                               2 = CUDA-core reference kernel (validation only) */
   int force_mb;            /* 0 = auto */
   int max_ctas;            /* 0 = auto */
+  void* dbg_counters;      /* optional int64 [148][3][4]: per-CTA cycle counters of the producer / MMA / epilogue
+                              roles (measurement aid; null in normal use) */
 } stl_conv_desc;
 
 int stl_conv2d(const stl_conv_desc* desc, void* stream);

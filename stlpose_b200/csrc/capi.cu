@@ -123,6 +123,7 @@ int stl_conv2d(const stl_conv_desc* d, void* stream) {
   s.force_tap_reload = d->impl == 1;
   s.force_mb = d->force_mb;
   s.max_ctas = d->max_ctas;
+  s.dbg_counters = d->dbg_counters;
   if (d->impl == 2) return conv_launch_naive(s, (cudaStream_t)stream);
   return conv_launch(s, (cudaStream_t)stream);
 }

@@ -45,12 +45,14 @@ struct ConvSpec {
   int force_tap_reload = 0;                // 1: one aligned TMA load per filter tap instead of shifted descriptors
   int force_mb = 0;
   int max_ctas = 0;
+  void* dbg_counters = nullptr;            // optional [grid][3][4] int64 cycle counters (measurement aid)
 };
 
 // Kernel parameters (passed __grid_constant__).
 struct ConvParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmR;   // residual tensor (flat mode only): used for L2 prefetch of the epilogue's reads
   int mode;        // 0: stride-1 flat-pixel tiles, 1: stride-2 structured tiles
   int taps;        // 1 or 9
   int n_chunks;    // Cin / ck
@@ -62,7 +64,9 @@ struct ConvParams {
   int halo;        // rows in front of the tile in shift mode (Wp+1 for 3x3, 0 for 1x1)
   int a_box_rows, a_pieces;
   int a_stages, b_stages;
-  uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
+  int b_resident;  // 1: all weight tiles of the layer stay in shared memory for the whole kernel
+  int res_prefetch;  // 1: producer prefetches the residual rows of each tile into L2 (tmR valid)
+  uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes, b_resident_bytes;
   int n_accbuf;
   uint32_t tmem_cols;
   long long total_tiles;
@@ -81,6 +85,8 @@ struct ConvParams {
   int relu;
   int out_nchw;
   int cout, cout_pad;
+  int dbg_skip_epilogue;  // measurement only
+  long long* dbg_counters;  // measurement only: [grid][3 roles][4] cycle counters, or null
 };
 
 // Fills ConvParams (tensor maps included) and returns the launch configuration. 0 on success.

@@ -17,6 +17,7 @@
 // Stride-2 convs ("structured" mode) load each tap with a 4-D tensor map whose W/H traversal stride is 2.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv.h"
@@ -26,8 +27,10 @@ namespace stl {
 
 namespace {
 
-constexpr int kThreads = 192;
-constexpr uint32_t kCtlBytes = 1024;
+constexpr int kThreads = 320;          // warp 0: TMA, warp 1: MMA, warps 2..9: two epilogue groups of 4 warps
+constexpr uint32_t kCtlBytes = 4096;   // [0,1024): barriers + TMEM base ; [1024,4096): fp32 bias for all channels
+constexpr uint32_t kBiasOffset = 1024;
+constexpr int kMaxCoutPad = 768;
 constexpr size_t kMaxSmem = 227 * 1024;
 
 struct Ctl {
@@ -36,7 +39,7 @@ struct Ctl {
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
-static_assert(sizeof(Ctl) <= kCtlBytes, "control block too large");
+static_assert(sizeof(Ctl) <= kBiasOffset, "control block too large");
 
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
@@ -46,16 +49,21 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 template <int NC>
-__device__ __forceinline__ void add_bf16_row(float (&f)[NC], const __nv_bfloat16* src) {
-  const uint4* s = reinterpret_cast<const uint4*>(src);
+__device__ __forceinline__ void add_bf16_regs(float (&f)[NC], const uint4 (&r)[NC / 8]) {
 #pragma unroll
   for (int g = 0; g < NC / 8; ++g) {
-    uint4 u = s[g];
-    f[g * 8 + 0] += bf16_lo(u.x); f[g * 8 + 1] += bf16_hi(u.x);
-    f[g * 8 + 2] += bf16_lo(u.y); f[g * 8 + 3] += bf16_hi(u.y);
-    f[g * 8 + 4] += bf16_lo(u.z); f[g * 8 + 5] += bf16_hi(u.z);
-    f[g * 8 + 6] += bf16_lo(u.w); f[g * 8 + 7] += bf16_hi(u.w);
+    f[g * 8 + 0] += bf16_lo(r[g].x); f[g * 8 + 1] += bf16_hi(r[g].x);
+    f[g * 8 + 2] += bf16_lo(r[g].y); f[g * 8 + 3] += bf16_hi(r[g].y);
+    f[g * 8 + 4] += bf16_lo(r[g].z); f[g * 8 + 5] += bf16_hi(r[g].z);
+    f[g * 8 + 6] += bf16_lo(r[g].w); f[g * 8 + 7] += bf16_hi(r[g].w);
   }
+}
+
+template <int NC>
+__device__ __forceinline__ void load_bf16_row(uint4 (&r)[NC / 8], const __nv_bfloat16* src, bool pred) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int g = 0; g < NC / 8; ++g) r[g] = pred ? __ldg(s + g) : make_uint4(0, 0, 0, 0);
 }
 
 struct RowPos {
@@ -65,66 +73,110 @@ struct RowPos {
   int n, h, w;
 };
 
-// Epilogue for NC consecutive output channels of one pixel.
-template <int NC>
-__device__ __forceinline__ void epilogue_store(const ConvParams& p, const uint32_t (&v)[NC], int ch0,
-                                               const RowPos& r) {
-  if (!r.valid) return;
-  if (p.out_nchw) {
+__device__ __forceinline__ RowPos row_position(const ConvParams& p, long long mt, int r) {
+  RowPos pos;
+  if (p.mode == 0) {
+    const long long q = mt * (128 * p.mb) + r;
+    pos.valid = q < p.P;
+    pos.q = (int)q;
+    pos.w = pos.q % p.Wp;
+    const int t = pos.q / p.Wp;
+    pos.h = t % p.Hp;
+    pos.n = t / p.Hp;
+    pos.is_pad = (pos.w == p.W) || (pos.h == p.H);
+  } else {
+    const int wl = r % p.bw, t = r / p.bw;
+    const int hl = t % p.bh, nl = t / p.bh;
+    pos.w = (int)(mt % p.tiles_w) * p.bw + wl;
+    pos.h = (int)((mt / p.tiles_w) % p.tiles_h) * p.bh + hl;
+    pos.n = (int)(mt / ((long long)p.tiles_w * p.tiles_h)) * p.bn + nl;
+    pos.valid = pos.w < p.W && pos.h < p.H && pos.n < p.N;
+    pos.is_pad = false;
+    pos.q = (pos.n * p.Hp + pos.h) * p.Wp + pos.w;
+  }
+  return pos;
+}
+
+// Epilogue for NC consecutive output channels of one pixel; `res` holds the (pre-fetched) residual values.
+template <int NC, bool NCHW>
+__device__ __forceinline__ void epilogue_store(const ConvParams& p, const uint32_t (&v)[NC], int ch0, const RowPos& r,
+                                               const uint4 (&res)[NC / 8], const float* sbias) {
+  if (!r.valid || p.dbg_skip_epilogue) return;
+  if constexpr (NCHW) {
     if (r.is_pad) return;
-    float* out = reinterpret_cast<float*>(p.out);
+    float* out = reinterpret_cast<float*>(p.out) + (((size_t)r.n * p.cout + ch0) * p.H + r.h) * p.W + r.w;
+    const size_t plane = (size_t)p.H * p.W;
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-      const int c = ch0 + i;
-      if (c < p.cout) {
-        float f = __uint_as_float(v[i]) + __ldg(p.bias + c);
+      if (ch0 + i < p.cout) {
+        float f = __uint_as_float(v[i]) + sbias[ch0 + i];
         if (p.relu) f = fmaxf(f, 0.f);
-        out[(((size_t)r.n * p.cout + c) * p.H + r.h) * p.W + r.w] = f;
+        out[i * plane] = f;
       }
     }
-    return;
-  }
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.q * p.cout + ch0;
-  uint4* o = reinterpret_cast<uint4*>(out);
-  if (r.is_pad) {
+  } else {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.q * p.cout + ch0;
+    uint4* o = reinterpret_cast<uint4*>(out);
+    if (r.is_pad) {
 #pragma unroll
-    for (int g = 0; g < NC / 8; ++g) o[g] = make_uint4(0, 0, 0, 0);
-    return;
-  }
-  float f[NC];
+      for (int g = 0; g < NC / 8; ++g) o[g] = make_uint4(0, 0, 0, 0);
+      return;
+    }
+    float f[NC];
+    const float4* b4 = reinterpret_cast<const float4*>(sbias + ch0);
 #pragma unroll
-  for (int i = 0; i < NC; ++i) f[i] = __uint_as_float(v[i]) + __ldg(p.bias + ch0 + i);
-  if (p.residual) add_bf16_row<NC>(f, p.residual + (size_t)r.q * p.cout + ch0);
-  for (int u = 0; u < p.n_up; ++u) {
-    const int s = p.up_shift[u];
-    const int hs = p.H >> s, ws = p.W >> s;
-    const size_t qs = ((size_t)r.n * (hs + 1) + (r.h >> s)) * (ws + 1) + (r.w >> s);
-    add_bf16_row<NC>(f, p.up_src[u] + qs * p.cout + ch0);
-  }
-  if (p.relu) {
+    for (int g = 0; g < NC / 4; ++g) {
+      const float4 b = b4[g];
+      f[g * 4 + 0] = __uint_as_float(v[g * 4 + 0]) + b.x;
+      f[g * 4 + 1] = __uint_as_float(v[g * 4 + 1]) + b.y;
+      f[g * 4 + 2] = __uint_as_float(v[g * 4 + 2]) + b.z;
+      f[g * 4 + 3] = __uint_as_float(v[g * 4 + 3]) + b.w;
+    }
+    if (p.residual) add_bf16_regs<NC>(f, res);
+#pragma unroll 1
+    for (int u = 0; u < p.n_up; ++u) {
+      const int s = p.up_shift[u];
+      const int hs = p.H >> s, ws = p.W >> s;
+      const size_t qs = ((size_t)r.n * (hs + 1) + (r.h >> s)) * (ws + 1) + (r.w >> s);
+      uint4 t[NC / 8];
+      load_bf16_row<NC>(t, p.up_src[u] + qs * p.cout + ch0, true);
+      add_bf16_regs<NC>(f, t);
+    }
+    if (p.relu) {
 #pragma unroll
-    for (int i = 0; i < NC; ++i) f[i] = fmaxf(f[i], 0.f);
-  }
+      for (int i = 0; i < NC; ++i) f[i] = fmaxf(f[i], 0.f);
+    }
 #pragma unroll
-  for (int g = 0; g < NC / 8; ++g) {
-    o[g] = make_uint4(pack_bf16(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
-                      pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
+    for (int g = 0; g < NC / 8; ++g) {
+      o[g] = make_uint4(pack_bf16(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
+                        pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
+    }
   }
 }
 
+// MB    : 128-row accumulator blocks per tile (compile time so that the MMA issue loop fully unrolls)
+// KSTEPS: UMMA K-steps (16 channels each) per K chunk; the smem row / swizzle span is 32*KSTEPS bytes
+// TAPS  : 1 (1x1) or 9 (3x3)
+// NCHW  : epilogue writes fp32 NCHW (heatmap head) instead of bf16 padded NHWC
+// Code size matters here: ten warps run four different roles out of one instruction cache, so everything that
+// does not have to be unrolled is a rolled loop and every epilogue path exists exactly once per kernel.
+template <int MB, int KSTEPS, int TAPS, bool NCHW>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle-128B atoms (8 rows x 128 B) must start on their natural boundary.
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
-  uint8_t* a_smem = smem + kCtlBytes;
-  uint8_t* b_smem = a_smem + (size_t)p.a_stages * p.a_stage_bytes;
+  float* sbias = reinterpret_cast<float*>(smem + kBiasOffset);
+  const uint32_t a_base = smem_u32(smem + kCtlBytes);
+  const uint32_t b_base = a_base + (uint32_t)p.a_stages * p.a_stage_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t span = 2u * p.ck;
-  const uint32_t acc_cols = (uint32_t)(p.mb * p.nt);
+  constexpr uint32_t kSpan = 32u * KSTEPS;
+  const uint32_t acc_cols = (uint32_t)(MB * p.nt);
+  // weights resident + (shifted-descriptor taps or 1x1): the whole K loop of a chunk is one straight MMA burst
+  const bool burst = p.b_resident && (p.a_shift || TAPS == 1);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&ctl->a_full[i], 1); mbar_init(&ctl->a_empty[i], 1); }
@@ -133,153 +185,272 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     fence_mbar_init();
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    if (p.res_prefetch) tma_prefetch_desc(&p.tmR);
   }
+  for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) sbias[i] = p.bias[i];
   if (warp == 1) tmem_alloc(&ctl->tmem_base, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
+  long long dbg[4] = {0, 0, 0, 0};
+  long long dbg_t = 0;
+#define DBG_TICK() do { if (p.dbg_counters) dbg_t = clock64(); } while (0)
+#define DBG_TOCK(i) do { if (p.dbg_counters) { const long long t_ = clock64(); dbg[i] += t_ - dbg_t; dbg_t = t_; } } while (0)
+
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t a_it = 0, b_it = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nti = (int)(tile % p.n_ntiles);
-        const long long mt = tile / p.n_ntiles;
-        int q0 = 0, wo0 = 0, ho0 = 0, n0 = 0;
-        if (p.mode == 0) {
-          q0 = (int)(mt * (128 * p.mb));
-        } else {
-          wo0 = (int)(mt % p.tiles_w) * p.bw;
-          ho0 = (int)((mt / p.tiles_w) % p.tiles_h) * p.bh;
-          n0 = (int)(mt / ((long long)p.tiles_w * p.tiles_h)) * p.bn;
-        }
-        for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
-          for (int tap = 0; tap < p.taps; ++tap) {
-            if (!p.a_shift || tap == 0) {
-              const uint32_t s = a_it % p.a_stages, ph = (a_it / p.a_stages) & 1;
-              mbar_wait(&ctl->a_empty[s], ph ^ 1);
-              mbar_expect_tx(&ctl->a_full[s], p.a_tx_bytes);
-              uint8_t* dst = a_smem + (size_t)s * p.a_stage_bytes;
-              const int kh = p.taps == 9 ? tap / 3 : 1, kw = p.taps == 9 ? tap % 3 : 1;
-              if (p.mode == 0) {
-                const int row0 = p.a_shift ? q0 - p.halo : q0 + (kh - 1) * p.in_Wp + (kw - 1);
-                for (int i = 0; i < p.a_pieces; ++i)
-                  tma_load_2d(dst + (size_t)i * p.a_box_rows * span, &p.tmA, &ctl->a_full[s], chunk * p.ck,
-                              row0 + i * p.a_box_rows);
-              } else {
-                tma_load_4d(dst, &p.tmA, &ctl->a_full[s], chunk * p.ck, 2 * wo0 + kw - 1, 2 * ho0 + kh - 1, n0);
-              }
-              ++a_it;
-            }
-            const uint32_t s = b_it % p.b_stages, ph = (b_it / p.b_stages) & 1;
-            mbar_wait(&ctl->b_empty[s], ph ^ 1);
-            mbar_expect_tx(&ctl->b_full[s], p.b_tx_bytes);
-            tma_load_3d(b_smem + (size_t)s * p.b_stage_bytes, &p.tmB, &ctl->b_full[s], chunk * p.ck, nti * p.nt,
-                        tap);
-            ++b_it;
-          }
-        }
-      }
+    // ------------------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
+    uint32_t a_it = 0, b_it = 0;
+    DBG_TICK();
+    if (p.b_resident && elect_one()) {
+      mbar_expect_tx(&ctl->b_full[0], p.b_resident_bytes);
+      uint32_t dst = b_base;
+      for (int nti = 0; nti < p.n_ntiles; ++nti)
+        for (int chunk = 0; chunk < p.n_chunks; ++chunk)
+          for (int tap = 0; tap < TAPS; ++tap, dst += p.b_stage_bytes)
+            tma_load_3d_s(dst, &p.tmB, &ctl->b_full[0], chunk * p.ck, nti * p.nt, tap);
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.nt);
-      const int ksteps = p.ck / 16;
-      uint32_t a_it = 0, b_it = 0, acc_it = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const uint32_t buf = acc_it % p.n_accbuf, aph = (acc_it / p.n_accbuf) & 1;
-        mbar_wait(&ctl->acc_empty[buf], aph ^ 1);
-        tc_fence_after();
-        const uint32_t d_base = tmem_base + buf * acc_cols;
-        uint32_t a_stage = 0;
-        for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
-          for (int tap = 0; tap < p.taps; ++tap) {
-            if (!p.a_shift || tap == 0) {
-              a_stage = a_it % p.a_stages;
-              mbar_wait(&ctl->a_full[a_stage], (a_it / p.a_stages) & 1);
-            }
-            const uint32_t bs = b_it % p.b_stages;
-            mbar_wait(&ctl->b_full[bs], (b_it / p.b_stages) & 1);
-            tc_fence_after();
-            uint32_t row_off = 0;
-            if (p.a_shift && p.taps == 9) row_off = (uint32_t)((tap / 3) * p.in_Wp + (tap % 3));
-            const uint32_t a_addr = smem_u32(a_smem + (size_t)a_stage * p.a_stage_bytes) + row_off * span;
-            const uint32_t b_addr = smem_u32(b_smem + (size_t)bs * p.b_stage_bytes);
-            for (int m = 0; m < p.mb; ++m) {
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t da = make_kmajor_desc(a_addr + (uint32_t)m * 128u * span + (uint32_t)k * 32u, span);
-                const uint64_t db = make_kmajor_desc(b_addr + (uint32_t)k * 32u, span);
-                umma_bf16(d_base + (uint32_t)(m * p.nt), da, db, idesc, (chunk | tap | k) != 0);
-              }
-            }
-            umma_commit(&ctl->b_empty[bs]);
-            ++b_it;
-            if (!p.a_shift || tap == p.taps - 1) {
-              umma_commit(&ctl->a_empty[a_stage]);
-              ++a_it;
-            }
-          }
-        }
-        umma_commit(&ctl->acc_full[buf]);
-        ++acc_it;
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
-    uint32_t acc_it = 0;
+    __syncwarp();
+#pragma unroll 1
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nti = (int)(tile % p.n_ntiles);
       const long long mt = tile / p.n_ntiles;
+      int q0 = 0, wo0 = 0, ho0 = 0, n0 = 0;
+      if (p.mode == 0) {
+        q0 = (int)(mt * (128 * MB));
+        if (p.res_prefetch && elect_one()) {
+#pragma unroll
+          for (int m = 0; m < MB; ++m) tma_prefetch_l2_2d(&p.tmR, nti * p.nt, q0 + m * 128);
+        }
+        __syncwarp();
+      } else {
+        wo0 = (int)(mt % p.tiles_w) * p.bw;
+        ho0 = (int)((mt / p.tiles_w) % p.tiles_h) * p.bh;
+        n0 = (int)(mt / ((long long)p.tiles_w * p.tiles_h)) * p.bn;
+      }
+#pragma unroll 1
+      for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
+        int kh = TAPS == 9 ? 0 : 1, kw = TAPS == 9 ? 0 : 1;
+#pragma unroll 1
+        for (int tap = 0; tap < TAPS; ++tap) {
+          if (!p.a_shift || tap == 0) {
+            const uint32_t s = a_it % p.a_stages, ph = (a_it / p.a_stages) & 1;
+            mbar_wait(&ctl->a_empty[s], ph ^ 1);
+            DBG_TOCK(0);
+            if (elect_one()) {
+              mbar_expect_tx(&ctl->a_full[s], p.a_tx_bytes);
+              const uint32_t dst = a_base + s * p.a_stage_bytes;
+              if (p.mode == 0) {
+                const int row0 = p.a_shift ? q0 - p.halo : q0 + (kh - 1) * p.in_Wp + (kw - 1);
+                for (int i = 0; i < p.a_pieces; ++i)
+                  tma_load_2d_s(dst + (uint32_t)(i * p.a_box_rows) * kSpan, &p.tmA, &ctl->a_full[s], chunk * p.ck,
+                              row0 + i * p.a_box_rows);
+              } else {
+                tma_load_4d_s(dst, &p.tmA, &ctl->a_full[s], chunk * p.ck, 2 * wo0 + kw - 1, 2 * ho0 + kh - 1, n0);
+              }
+            }
+            __syncwarp();
+            ++a_it;
+            DBG_TOCK(2);
+          }
+          if (!p.b_resident) {
+            const uint32_t s = b_it % p.b_stages, ph = (b_it / p.b_stages) & 1;
+            mbar_wait(&ctl->b_empty[s], ph ^ 1);
+            DBG_TOCK(1);
+            if (elect_one()) {
+              mbar_expect_tx(&ctl->b_full[s], p.b_tx_bytes);
+              tma_load_3d_s(b_base + s * p.b_stage_bytes, &p.tmB, &ctl->b_full[s], chunk * p.ck, nti * p.nt, tap);
+            }
+            __syncwarp();
+            ++b_it;
+            DBG_TOCK(2);
+          }
+          if (++kw == 3) { kw = 0; ++kh; }
+        }
+      }
+    }
+    if (p.dbg_counters && lane == 0)
+      for (int i = 0; i < 4; ++i) p.dbg_counters[(blockIdx.x * 3 + 0) * 4 + i] = dbg[i];
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.nt);
+    const uint64_t desc_hi = make_kmajor_desc(0, kSpan) & 0xFFFFFFFF00000000ull;
+    const uint32_t desc_lo_flags = (uint32_t)(make_kmajor_desc(0, kSpan) & 0xFFFFFFFFull);
+    // descriptors differ only in the 14-bit start-address field (16-byte units) of the low word
+    const uint32_t a_lo_base = desc_lo_flags | (a_base >> 4);
+    const uint32_t b_lo_base = desc_lo_flags | (b_base >> 4);
+    const uint32_t a_stage_u = p.a_stage_bytes >> 4, b_stage_u = p.b_stage_bytes >> 4;
+    const uint32_t wp_u = (uint32_t)p.in_Wp * (kSpan >> 4);  // one padded image row, in 16-byte units
+    const uint32_t nt = (uint32_t)p.nt;
+    uint32_t a_it = 0, b_it = 0, acc_it = 0;
+    DBG_TICK();
+    if (p.b_resident) {
+      mbar_wait(&ctl->b_full[0], 0);
+      DBG_TOCK(2);
+    }
+#pragma unroll 1
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const uint32_t nti = (uint32_t)(tile % p.n_ntiles);
       const uint32_t buf = acc_it % p.n_accbuf, aph = (acc_it / p.n_accbuf) & 1;
-      mbar_wait(&ctl->acc_full[buf], aph);
+      mbar_wait(&ctl->acc_empty[buf], aph ^ 1);
+      DBG_TOCK(0);
       tc_fence_after();
-      for (int m = 0; m < p.mb; ++m) {
-        const int r = m * 128 + quarter * 32 + lane;
-        RowPos pos;
-        if (p.mode == 0) {
-          const long long q = mt * (128 * p.mb) + r;
-          pos.valid = q < p.P;
-          pos.q = (int)q;
-          pos.w = pos.q % p.Wp;
-          const int t = pos.q / p.Wp;
-          pos.h = t % p.Hp;
-          pos.n = t / p.Hp;
-          pos.is_pad = (pos.w == p.W) || (pos.h == p.H);
-        } else {
-          const int wl = r % p.bw, t = r / p.bw;
-          const int hl = t % p.bh, nl = t / p.bh;
-          pos.w = (int)(mt % p.tiles_w) * p.bw + wl;
-          pos.h = (int)((mt / p.tiles_w) % p.tiles_h) * p.bh + hl;
-          pos.n = (int)(mt / ((long long)p.tiles_w * p.tiles_h)) * p.bn + nl;
-          pos.valid = pos.w < p.W && pos.h < p.H && pos.n < p.N;
-          pos.is_pad = false;
-          pos.q = (pos.n * p.Hp + pos.h) * p.Wp + pos.w;
+      const uint32_t d_base = tmem_base + buf * acc_cols;
+      if (burst) {
+#pragma unroll 1
+        for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
+          const uint32_t a_stage = a_it % p.a_stages;
+          mbar_wait(&ctl->a_full[a_stage], (a_it / p.a_stages) & 1);
+          DBG_TOCK(1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_lo0 = a_lo_base + a_stage * a_stage_u;
+            const uint32_t b_lo0 = b_lo_base + ((nti * p.n_chunks + chunk) * TAPS) * b_stage_u;
+#pragma unroll
+            for (int tap = 0; tap < TAPS; ++tap) {
+              const uint32_t a_lo = a_lo0 + (TAPS == 9 ? (uint32_t)(tap / 3) * wp_u + (uint32_t)(tap % 3) * (kSpan >> 4) : 0u);
+              const uint32_t b_lo = b_lo0 + (uint32_t)tap * b_stage_u;
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+#pragma unroll
+                for (int m = 0; m < MB; ++m) {
+                  const uint64_t da = desc_hi | (uint64_t)(a_lo + (uint32_t)((m * 128 * (int)kSpan + k * 32) >> 4));
+                  const uint64_t db = desc_hi | (uint64_t)(b_lo + (uint32_t)((k * 32) >> 4));
+                  umma_bf16(d_base + (uint32_t)m * nt, da, db, idesc, (tap | k) != 0 ? 1u : (uint32_t)chunk);
+                }
+              }
+            }
+            umma_commit(&ctl->a_empty[a_stage]);
+          }
+          __syncwarp();
+          ++a_it;
+          DBG_TOCK(3);
         }
-        const uint32_t t_row = tmem_base + buf * acc_cols + (uint32_t)(m * p.nt) + ((uint32_t)(quarter * 32) << 16);
-        int c = 0;
-        for (; c + 32 <= p.nt; c += 32) {
+      } else {
+        uint32_t a_stage = 0;
+#pragma unroll 1
+        for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
+          uint32_t tap_u = 0;  // row offset of the current tap inside the halo'd tile, 16-byte units
+          int kw = 0;
+#pragma unroll 1
+          for (int tap = 0; tap < TAPS; ++tap) {
+            if (!p.a_shift || tap == 0) {
+              a_stage = a_it % p.a_stages;
+              mbar_wait(&ctl->a_full[a_stage], (a_it / p.a_stages) & 1);
+              DBG_TOCK(1);
+            }
+            uint32_t bs;
+            if (p.b_resident) {
+              bs = (nti * p.n_chunks + chunk) * TAPS + tap;
+            } else {
+              bs = b_it % p.b_stages;
+              mbar_wait(&ctl->b_full[bs], (b_it / p.b_stages) & 1);
+              DBG_TOCK(2);
+            }
+            tc_fence_after();
+            const bool release_a = !p.a_shift || tap == TAPS - 1;
+            if (elect_one()) {
+              const uint32_t a_lo = a_lo_base + a_stage * a_stage_u + (p.a_shift ? tap_u : 0u);
+              const uint32_t b_lo = b_lo_base + bs * b_stage_u;
+              const uint32_t first = (uint32_t)(chunk | tap);
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+#pragma unroll
+                for (int m = 0; m < MB; ++m) {
+                  const uint64_t da = desc_hi | (uint64_t)(a_lo + (uint32_t)((m * 128 * (int)kSpan + k * 32) >> 4));
+                  const uint64_t db = desc_hi | (uint64_t)(b_lo + (uint32_t)((k * 32) >> 4));
+                  umma_bf16(d_base + (uint32_t)m * nt, da, db, idesc, first | (uint32_t)k);
+                }
+              }
+              if (!p.b_resident) umma_commit(&ctl->b_empty[bs]);
+              if (release_a) umma_commit(&ctl->a_empty[a_stage]);
+            }
+            __syncwarp();
+            if (!p.b_resident) ++b_it;
+            if (release_a) ++a_it;
+            tap_u += kSpan >> 4;
+            if (++kw == 3) { kw = 0; tap_u += wp_u - 3 * (kSpan >> 4); }
+            DBG_TOCK(3);
+          }
+        }
+      }
+      if (elect_one()) umma_commit(&ctl->acc_full[buf]);
+      __syncwarp();
+      ++acc_it;
+    }
+    if (p.dbg_counters && lane == 0)
+      for (int i = 0; i < 4; ++i) p.dbg_counters[(blockIdx.x * 3 + 1) * 4 + i] = dbg[i];
+  } else {
+    // ------------------------------------------------------------------ epilogue: two groups of 4 warps, one per
+    // accumulator buffer, so the TMEM drain of tile t overlaps both the MMAs of tile t+1 and the drain of t+1.
+    const int group = (warp - 2) >> 2;
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+    const int nfull = p.nt >> 5;
+    const bool has_res = !NCHW && p.residual != nullptr;
+    uint32_t acc_it = 0;
+    DBG_TICK();
+#pragma unroll 1
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++acc_it) {
+      if (p.n_accbuf == 2 ? (int)(acc_it & 1) != group : group != 0) continue;
+      const int nti = (int)(tile % p.n_ntiles);
+      const long long mt = tile / p.n_ntiles;
+      const uint32_t buf = p.n_accbuf == 2 ? (uint32_t)group : 0u;
+      const uint32_t aph = (acc_it / p.n_accbuf) & 1;
+      const int chbase = nti * p.nt;
+      const int row0 = quarter * 32 + lane;
+      RowPos pos = row_position(p, mt, row0);
+      // residual of the first 32-channel unit is fetched before waiting for the accumulator; afterwards the
+      // fetch of unit u+1 is issued before unit u is processed
+      uint4 rcur[4], rnext[4];
+      if (has_res && nfull > 0)
+        load_bf16_row<32>(rcur, p.residual + (size_t)pos.q * p.cout + chbase, pos.valid && !pos.is_pad);
+      DBG_TOCK(1);
+      mbar_wait(&ctl->acc_full[buf], aph);
+      DBG_TOCK(0);
+      tc_fence_after();
+      const uint32_t t_tile = tmem_base + buf * acc_cols + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int m = 0; m < MB; ++m) {
+        RowPos pos_next = pos;
+        if (m + 1 < MB) pos_next = row_position(p, mt, (m + 1) * 128 + row0);
+#pragma unroll 1
+        for (int j = 0; j < nfull; ++j) {
           uint32_t v[32];
-          tmem_ld32(t_row + (uint32_t)c, v);
+          tmem_ld32(t_tile + (uint32_t)(m * p.nt + j * 32), v);
+          if (has_res) {
+            const bool same_row = j + 1 < nfull;
+            const RowPos& pn = same_row ? pos : pos_next;
+            const int cn = same_row ? (j + 1) * 32 : 0;
+            if (same_row || m + 1 < MB)
+              load_bf16_row<32>(rnext, p.residual + (size_t)pn.q * p.cout + chbase + cn, pn.valid && !pn.is_pad);
+          }
           tmem_ld_wait();
-          epilogue_store<32>(p, v, nti * p.nt + c, pos);
+          epilogue_store<32, NCHW>(p, v, chbase + j * 32, pos, rcur, sbias);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
         }
-        if (c < p.nt) {
+        if (p.nt & 16) {
           uint32_t v[16];
-          tmem_ld16(t_row + (uint32_t)c, v);
+          uint4 r2[2];
+          tmem_ld16(t_tile + (uint32_t)(m * p.nt + nfull * 32), v);
+          load_bf16_row<16>(r2, has_res ? p.residual + (size_t)pos.q * p.cout + chbase + nfull * 32 : nullptr,
+                            has_res && pos.valid && !pos.is_pad);
           tmem_ld_wait();
-          epilogue_store<16>(p, v, nti * p.nt + c, pos);
+          epilogue_store<16, NCHW>(p, v, chbase + nfull * 32, pos, r2, sbias);
         }
+        pos = pos_next;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
-      ++acc_it;
+      DBG_TOCK(1);
     }
+    if (p.dbg_counters && warp == 2 && lane == 0)
+      for (int i = 0; i < 4; ++i) p.dbg_counters[(blockIdx.x * 3 + 2) * 4 + i] = dbg[i];
   }
+#undef DBG_TICK
+#undef DBG_TOCK
 
   tc_fence_before();
   __syncthreads();
@@ -311,7 +482,9 @@ int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, 
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return 1; }
   CUtensorMapSwizzle sw = span == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                      : (span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+                          : span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : span == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                       : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
                   strides_bytes, box, estrides, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -358,7 +531,7 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     set_error("conv: unsupported ksize %d / stride %d", s.ksize, s.stride);
     return 1;
   }
-  if (s.cout_pad % 16 || s.cout_pad < s.cout || (!s.out_nchw && s.cout != s.cout_pad)) {
+  if (s.cout_pad % 16 || s.cout_pad < s.cout || s.cout_pad > kMaxCoutPad || (!s.out_nchw && s.cout != s.cout_pad)) {
     set_error("conv: bad cout %d / cout_pad %d", s.cout, s.cout_pad);
     return 1;
   }
@@ -382,6 +555,7 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
 
   // accumulator blocks per tile: keep two accumulator buffers in 512 TMEM columns when possible
   int mb = s.force_mb ? s.force_mb : (p.nt <= 64 ? 3 : 2);
+  if (mb > 3) mb = 3;
   while (mb > 1 && mb * p.nt > 256) --mb;
   if (p.mode == 0) {
     // do not make tiles larger than the problem
@@ -451,24 +625,51 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   while (cols < (uint32_t)(p.n_accbuf * p.mb * p.nt)) cols <<= 1;
   p.tmem_cols = cols;
 
-  // ring depths: as many as fit, weights ring up to one chunk's worth of taps (+ slack), activations >= 2
+  // weights stay resident in shared memory when every tile of the layer fits next to >= 2 activation stages;
+  // otherwise they stream through a ring (one stage per (chunk, tap))
   const size_t budget = kMaxSmem - kCtlBytes - 1024;
+  const size_t resident = (size_t)p.n_ntiles * p.n_chunks * p.taps * p.b_stage_bytes;
   const int a_loads_per_tile = p.n_chunks * (p.a_shift || p.taps == 1 ? 1 : p.taps);
-  int a_st = 2, b_st = 2;
-  auto used = [&](int a, int b) { return (size_t)a * p.a_stage_bytes + (size_t)b * p.b_stage_bytes; };
-  if (used(2, 2) > budget) { a_st = 1; }
-  if (used(a_st, b_st) > budget) { set_error("conv: tile does not fit shared memory"); return 1; }
   const int a_want = a_loads_per_tile >= 4 ? 4 : (p.a_shift ? 3 : 4);
-  const int b_want = 8;
-  bool grew = true;
-  while (grew) {
-    grew = false;
-    if (b_st < b_want && b_st < kMaxStages && used(a_st, b_st + 1) <= budget) { ++b_st; grew = true; }
-    if (a_st < a_want && a_st < kMaxStages && used(a_st + 1, b_st) <= budget) { ++a_st; grew = true; }
+  int a_st = 2, b_st = 2;
+  p.b_resident = (resident <= 120 * 1024 && resident + 2 * (size_t)p.a_stage_bytes <= budget &&
+                  resident < (1u << 20) && !getenv("STL_DBG_NO_RESIDENT")) ? 1 : 0;
+  size_t b_bytes_total;
+  if (p.b_resident) {
+    p.b_resident_bytes = (uint32_t)((size_t)p.n_ntiles * p.n_chunks * p.taps * p.b_tx_bytes);
+    while (a_st < a_want && resident + (size_t)(a_st + 1) * p.a_stage_bytes <= budget) ++a_st;
+    b_st = 1;
+    b_bytes_total = resident;
+  } else {
+    auto used = [&](int a, int b) { return (size_t)a * p.a_stage_bytes + (size_t)b * p.b_stage_bytes; };
+    if (used(2, 2) > budget) a_st = 1;
+    if (used(a_st, b_st) > budget) { set_error("conv: tile does not fit shared memory"); return 1; }
+    const int b_want = 8;
+    bool grew = true;
+    while (grew) {
+      grew = false;
+      if (b_st < b_want && b_st < kMaxStages && used(a_st, b_st + 1) <= budget) { ++b_st; grew = true; }
+      if (a_st < a_want && a_st < kMaxStages && used(a_st + 1, b_st) <= budget) { ++a_st; grew = true; }
+    }
+    if (const char* e = getenv("STL_DBG_B_STAGES")) { int v = atoi(e); if (v >= 1 && v <= b_st) b_st = v; }
+    b_bytes_total = (size_t)b_st * p.b_stage_bytes;
   }
+  if (const char* e = getenv("STL_DBG_A_STAGES")) { int v = atoi(e); if (v >= 1 && v <= a_st) a_st = v; }
   p.a_stages = a_st;
   p.b_stages = b_st;
-  *smem_bytes = kCtlBytes + 1024 + used(a_st, b_st);
+  *smem_bytes = kCtlBytes + 1024 + (size_t)a_st * p.a_stage_bytes + b_bytes_total;
+
+  // L2 prefetch of the residual rows the epilogue will read (flat mode): the producer warp touches them
+  // a few tiles ahead so the epilogue's loads hit L2 instead of exposing DRAM latency per 32-channel unit
+  p.res_prefetch = 0;
+  if (p.mode == 0 && s.residual && !s.out_nchw && !getenv("STL_DBG_NO_RES_PREFETCH")) {
+    cuuint64_t dims[2] = {(cuuint64_t)s.cout, (cuuint64_t)p.P};
+    cuuint64_t strides[1] = {(cuuint64_t)s.cout * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.nt, 128};
+    cuuint32_t es[2] = {1, 1};
+    if (encode(&p.tmR, s.residual, 2, dims, strides, box, es, 0)) return 1;
+    p.res_prefetch = 1;
+  }
 
   p.out = s.out;
   p.bias = s.bias;
@@ -477,6 +678,8 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   for (int i = 0; i < kMaxUp; ++i) { p.up_src[i] = s.up_src[i]; p.up_shift[i] = s.up_shift[i]; }
   p.relu = s.relu;
   p.out_nchw = s.out_nchw;
+  p.dbg_skip_epilogue = getenv("STL_DBG_SKIP_EPILOGUE") ? 1 : 0;
+  p.dbg_counters = reinterpret_cast<long long*>(s.dbg_counters);
   p.cout = s.cout;
   p.cout_pad = s.cout_pad;
 
@@ -486,15 +689,48 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   return 0;
 }
 
+namespace {
+typedef void (*ConvKernel)(const ConvParams);
+template <int MB, int KSTEPS>
+ConvKernel pick_variant(int taps, bool nchw) {
+  if (nchw) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, true> : nullptr;
+  return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, false> : conv_tc_kernel<MB, KSTEPS, 9, false>;
+}
+template <int MB>
+ConvKernel pick_ksteps(int ksteps, int taps, bool nchw) {
+  switch (ksteps) {
+    case 1: return pick_variant<MB, 1>(taps, nchw);
+    case 2: return pick_variant<MB, 2>(taps, nchw);
+    case 4: return pick_variant<MB, 4>(taps, nchw);
+  }
+  return nullptr;
+}
+ConvKernel pick_kernel(int mb, int ksteps, int taps, bool nchw) {
+  switch (mb) {
+    case 1: return pick_ksteps<1>(ksteps, taps, nchw);
+    case 2: return pick_ksteps<2>(ksteps, taps, nchw);
+    case 3: return pick_ksteps<3>(ksteps, taps, nchw);
+  }
+  return nullptr;
+}
+}  // namespace
+
 int conv_launch_prepared(const ConvParams& p, int grid, size_t smem_bytes, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+    for (int mb = 1; mb <= 3; ++mb)
+      for (int ks = 1; ks <= 4; ks *= 2)
+        for (int v = 0; v < 3; ++v) {
+          ConvKernel k = pick_kernel(mb, ks, v == 1 ? 9 : 1, v == 2);
+          cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+          if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+        }
     attr_set = true;
   }
   if (grid <= 0) return 0;
-  conv_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+  ConvKernel kern = pick_kernel(p.mb, p.ck / 16, p.taps, p.out_nchw != 0);
+  if (!kern) { set_error("conv: no kernel for mb %d ck %d taps %d nchw %d", p.mb, p.ck, p.taps, p.out_nchw); return 1; }
+  kern<<<grid, kThreads, smem_bytes, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv_tc_kernel launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;
