@@ -48,11 +48,27 @@ struct ConvSpec {
   void* dbg_counters = nullptr;            // optional [grid][3][4] int64 cycle counters (measurement aid)
 };
 
+// Exact division of a 31-bit unsigned value by a small constant: q = (x * mul) >> shift  (mul < 2^32, 64-bit product).
+struct FastDiv {
+  uint32_t d, mul, shift;
+  __host__ void init(uint32_t div) {
+    d = div;
+    uint32_t s = 0;
+    while ((1u << s) < div) ++s;
+    shift = 31 + s;
+    mul = (uint32_t)((((unsigned long long)1 << shift) + div - 1) / div);
+  }
+  __host__ __device__ __forceinline__ uint32_t div(uint32_t x) const {
+    return (uint32_t)(((unsigned long long)x * mul) >> shift);
+  }
+};
+
 // Kernel parameters (passed __grid_constant__).
 struct ConvParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
-  CUtensorMap tmR;   // residual tensor (flat mode only): used for L2 prefetch of the epilogue's reads
+  CUtensorMap tmO;   // output tensor   (flat mode, bf16 out): epilogue stores whole panels with TMA
+  CUtensorMap tmR;   // residual tensor (same geometry): panels are pre-loaded into the staging buffer
   int mode;        // 0: stride-1 flat-pixel tiles, 1: stride-2 structured tiles
   int taps;        // 1 or 9
   int n_chunks;    // Cin / ck
@@ -65,8 +81,13 @@ struct ConvParams {
   int a_box_rows, a_pieces;
   int a_stages, b_stages;
   int b_resident;  // 1: all weight tiles of the layer stay in shared memory for the whole kernel
-  int res_prefetch;  // 1: producer prefetches the residual rows of each tile into L2 (tmR valid)
-  uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes, b_resident_bytes;
+  int epi_tma;     // 1: epilogue stages 128-row x panel_ch panels in shared memory and moves them with TMA
+  int panel_ch;    // channels per staged panel (64, or nt when nt is not a multiple of 64)
+  int panel_swz;   // swizzle span of a panel row in bytes (128, 64) or 0 for none
+  uint32_t epi_base_off;  // byte offset of the staging panels from the start of the activation stages
+  int epi_batch;          // panels per staging buffer (a whole tile when panels are small)
+  uint32_t epi_panel_bytes;
+  uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes, b_resident_bytes, b_bytes_total;
   int n_accbuf;
   uint32_t tmem_cols;
   long long total_tiles;
@@ -74,6 +95,7 @@ struct ConvParams {
   int in_Wp;
   int N, H, W, Hp, Wp;   // OUTPUT geometry
   long long P;           // output padded pixel count
+  FastDiv fd_Wp, fd_Hp, fd_bw, fd_bh;  // exact dividers for the epilogue's row -> (n, h, w) decode
   int bw, bh, bn, tiles_w, tiles_h, tiles_n;  // structured tiles (mode 1)
   // epilogue
   void* out;

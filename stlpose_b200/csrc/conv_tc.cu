@@ -27,16 +27,19 @@ namespace stl {
 
 namespace {
 
-constexpr int kThreads = 320;          // warp 0: TMA, warp 1: MMA, warps 2..9: two epilogue groups of 4 warps
+constexpr int kThreads = 640;          // warp 0: TMA, warp 1: MMA, warps 2..17: two epilogue groups of 8 warps,
+                                       // warps 18..19: one epilogue DMA warp per group (panel loads / stores)
 constexpr uint32_t kCtlBytes = 4096;   // [0,1024): barriers + TMEM base ; [1024,4096): fp32 bias for all channels
 constexpr uint32_t kBiasOffset = 1024;
 constexpr int kMaxCoutPad = 768;
+constexpr int kEpiStaged = 0, kEpiDirect = 1, kEpiNchw = 2;
 constexpr size_t kMaxSmem = 227 * 1024;
 
 struct Ctl {
   uint64_t a_full[kMaxStages], a_empty[kMaxStages];
   uint64_t b_full[kMaxStages], b_empty[kMaxStages];
   uint64_t acc_full[2], acc_empty[2];
+  uint64_t res_full[4], epi_free[4], epi_done[4];  // [epilogue group][staging buffer]
   uint32_t tmem_base;
 };
 static_assert(sizeof(Ctl) <= kBiasOffset, "control block too large");
@@ -79,14 +82,16 @@ __device__ __forceinline__ RowPos row_position(const ConvParams& p, long long mt
     const long long q = mt * (128 * p.mb) + r;
     pos.valid = q < p.P;
     pos.q = (int)q;
-    pos.w = pos.q % p.Wp;
-    const int t = pos.q / p.Wp;
-    pos.h = t % p.Hp;
-    pos.n = t / p.Hp;
+    const uint32_t t = p.fd_Wp.div((uint32_t)pos.q);
+    pos.w = pos.q - (int)t * p.Wp;
+    pos.n = (int)p.fd_Hp.div(t);
+    pos.h = (int)t - pos.n * p.Hp;
     pos.is_pad = (pos.w == p.W) || (pos.h == p.H);
   } else {
-    const int wl = r % p.bw, t = r / p.bw;
-    const int hl = t % p.bh, nl = t / p.bh;
+    const uint32_t t = p.fd_bw.div((uint32_t)r);
+    const int wl = r - (int)t * p.bw;
+    const int nl = (int)p.fd_bh.div(t);
+    const int hl = (int)t - nl * p.bh;
     pos.w = (int)(mt % p.tiles_w) * p.bw + wl;
     pos.h = (int)((mt / p.tiles_w) % p.tiles_h) * p.bh + hl;
     pos.n = (int)(mt / ((long long)p.tiles_w * p.tiles_h)) * p.bn + nl;
@@ -97,59 +102,95 @@ __device__ __forceinline__ RowPos row_position(const ConvParams& p, long long mt
   return pos;
 }
 
-// Epilogue for NC consecutive output channels of one pixel; `res` holds the (pre-fetched) residual values.
+// Epilogue parameters copied into registers once per kernel: the tcgen05/TMA asm statements carry memory
+// clobbers, so anything read through `p.` inside the unit loop would be re-fetched from the constant bank
+// every iteration.
+struct EpiParams {
+  void* out;
+  const __nv_bfloat16* residual;
+  int cout, relu, n_up, H, W, skip;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));  // first source -> upper half
+  return r;
+}
+
+// Epilogue for NC consecutive output channels of one pixel; `res` holds the (pre-fetched) residual values and
+// `bias` the per-channel bias (fetched from shared memory while the TMEM load was in flight).
 template <int NC, bool NCHW>
-__device__ __forceinline__ void epilogue_store(const ConvParams& p, const uint32_t (&v)[NC], int ch0, const RowPos& r,
-                                               const uint4 (&res)[NC / 8], const float* sbias) {
-  if (!r.valid || p.dbg_skip_epilogue) return;
+__device__ __forceinline__ void epilogue_store(const ConvParams& p, const EpiParams& e, uint32_t (&v)[NC], int ch0,
+                                               const RowPos& r, const uint4 (&res)[NC / 8],
+                                               const float4 (&bias)[NC / 4]) {
+  if (!r.valid || e.skip == 1) return;
+  float* f = reinterpret_cast<float*>(v);
   if constexpr (NCHW) {
     if (r.is_pad) return;
-    float* out = reinterpret_cast<float*>(p.out) + (((size_t)r.n * p.cout + ch0) * p.H + r.h) * p.W + r.w;
-    const size_t plane = (size_t)p.H * p.W;
+    float* out = reinterpret_cast<float*>(e.out) + (((size_t)r.n * e.cout + ch0) * e.H + r.h) * e.W + r.w;
+    const size_t plane = (size_t)e.H * e.W;
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-      if (ch0 + i < p.cout) {
-        float f = __uint_as_float(v[i]) + sbias[ch0 + i];
-        if (p.relu) f = fmaxf(f, 0.f);
-        out[i * plane] = f;
+      if (ch0 + i < e.cout) {
+        const float b = i % 4 == 0 ? bias[i / 4].x : i % 4 == 1 ? bias[i / 4].y : i % 4 == 2 ? bias[i / 4].z : bias[i / 4].w;
+        float t = f[i] + b;
+        if (e.relu) t = fmaxf(t, 0.f);
+        out[i * plane] = t;
       }
     }
   } else {
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)r.q * p.cout + ch0;
-    uint4* o = reinterpret_cast<uint4*>(out);
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)r.q * e.cout + ch0);
     if (r.is_pad) {
 #pragma unroll
       for (int g = 0; g < NC / 8; ++g) o[g] = make_uint4(0, 0, 0, 0);
       return;
     }
-    float f[NC];
-    const float4* b4 = reinterpret_cast<const float4*>(sbias + ch0);
 #pragma unroll
     for (int g = 0; g < NC / 4; ++g) {
-      const float4 b = b4[g];
-      f[g * 4 + 0] = __uint_as_float(v[g * 4 + 0]) + b.x;
-      f[g * 4 + 1] = __uint_as_float(v[g * 4 + 1]) + b.y;
-      f[g * 4 + 2] = __uint_as_float(v[g * 4 + 2]) + b.z;
-      f[g * 4 + 3] = __uint_as_float(v[g * 4 + 3]) + b.w;
+      f[g * 4 + 0] += bias[g].x; f[g * 4 + 1] += bias[g].y; f[g * 4 + 2] += bias[g].z; f[g * 4 + 3] += bias[g].w;
     }
-    if (p.residual) add_bf16_regs<NC>(f, res);
+    if (e.residual) {
+#pragma unroll
+      for (int g = 0; g < NC / 8; ++g) {
+        f[g * 8 + 0] += bf16_lo(res[g].x); f[g * 8 + 1] += bf16_hi(res[g].x);
+        f[g * 8 + 2] += bf16_lo(res[g].y); f[g * 8 + 3] += bf16_hi(res[g].y);
+        f[g * 8 + 4] += bf16_lo(res[g].z); f[g * 8 + 5] += bf16_hi(res[g].z);
+        f[g * 8 + 6] += bf16_lo(res[g].w); f[g * 8 + 7] += bf16_hi(res[g].w);
+      }
+    }
+    if (e.n_up) {
 #pragma unroll 1
-    for (int u = 0; u < p.n_up; ++u) {
-      const int s = p.up_shift[u];
-      const int hs = p.H >> s, ws = p.W >> s;
-      const size_t qs = ((size_t)r.n * (hs + 1) + (r.h >> s)) * (ws + 1) + (r.w >> s);
-      uint4 t[NC / 8];
-      load_bf16_row<NC>(t, p.up_src[u] + qs * p.cout + ch0, true);
-      add_bf16_regs<NC>(f, t);
-    }
-    if (p.relu) {
+      for (int u = 0; u < e.n_up; ++u) {
+        const int s = p.up_shift[u];
+        const int hs = e.H >> s, ws = e.W >> s;
+        const size_t qs = ((size_t)r.n * (hs + 1) + (r.h >> s)) * (ws + 1) + (r.w >> s);
+        const uint4* src = reinterpret_cast<const uint4*>(p.up_src[u] + qs * e.cout + ch0);
 #pragma unroll
-      for (int i = 0; i < NC; ++i) f[i] = fmaxf(f[i], 0.f);
+        for (int g = 0; g < NC / 8; ++g) {
+          const uint4 t = __ldg(src + g);
+          f[g * 8 + 0] += bf16_lo(t.x); f[g * 8 + 1] += bf16_hi(t.x);
+          f[g * 8 + 2] += bf16_lo(t.y); f[g * 8 + 3] += bf16_hi(t.y);
+          f[g * 8 + 4] += bf16_lo(t.z); f[g * 8 + 5] += bf16_hi(t.z);
+          f[g * 8 + 6] += bf16_lo(t.w); f[g * 8 + 7] += bf16_hi(t.w);
+        }
+      }
     }
+    if (e.skip == 2) {  // measurement: keep the loads and the math alive, drop (almost) all stores
+      float acc = 0.f;
 #pragma unroll
-    for (int g = 0; g < NC / 8; ++g) {
-      o[g] = make_uint4(pack_bf16(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
-                        pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
+      for (int i = 0; i < NC; ++i) acc += f[i];
+      if (acc != 12345.678f) return;
+    }
+    if (e.relu) {
+#pragma unroll
+      for (int g = 0; g < NC / 8; ++g)
+        o[g] = make_uint4(pack_bf16_relu(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16_relu(f[g * 8 + 2], f[g * 8 + 3]),
+                          pack_bf16_relu(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16_relu(f[g * 8 + 6], f[g * 8 + 7]));
+    } else {
+#pragma unroll
+      for (int g = 0; g < NC / 8; ++g)
+        o[g] = make_uint4(pack_bf16(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
+                          pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
     }
   }
 }
@@ -157,10 +198,13 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, const uint32
 // MB    : 128-row accumulator blocks per tile (compile time so that the MMA issue loop fully unrolls)
 // KSTEPS: UMMA K-steps (16 channels each) per K chunk; the smem row / swizzle span is 32*KSTEPS bytes
 // TAPS  : 1 (1x1) or 9 (3x3)
-// NCHW  : epilogue writes fp32 NCHW (heatmap head) instead of bf16 padded NHWC
+// EPI   : which epilogue the kernel contains (each kernel carries exactly one, for instruction-cache footprint):
+//         kEpiStaged - flat mode, bf16 out: panels staged in shared memory, moved by TMA (the common case)
+//         kEpiDirect - per-thread global loads/stores: stride-2 convs, upsampled addends, odd channel counts
+//         kEpiNchw   - fp32 NCHW store of the heatmap head
 // Code size matters here: ten warps run four different roles out of one instruction cache, so everything that
 // does not have to be unrolled is a rolled loop and every epilogue path exists exactly once per kernel.
-template <int MB, int KSTEPS, int TAPS, bool NCHW>
+template <int MB, int KSTEPS, int TAPS, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle-128B atoms (8 rows x 128 B) must start on their natural boundary.
@@ -171,6 +215,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t a_base = smem_u32(smem + kCtlBytes);
   const uint32_t b_base = a_base + (uint32_t)p.a_stages * p.a_stage_bytes;
 
+  constexpr bool NCHW = EPI == kEpiNchw;
+  constexpr bool kFlatOnly = EPI != kEpiDirect;  // staged / NCHW kernels are only ever launched in flat mode
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kSpan = 32u * KSTEPS;
@@ -181,11 +227,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&ctl->a_full[i], 1); mbar_init(&ctl->a_empty[i], 1); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], 1); mbar_init(&ctl->acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], 1); mbar_init(&ctl->acc_empty[i], 8); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&ctl->res_full[i], 1); mbar_init(&ctl->epi_free[i], 1); mbar_init(&ctl->epi_done[i], 8); }
     fence_mbar_init();
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
-    if (p.res_prefetch) tma_prefetch_desc(&p.tmR);
+    if (p.epi_tma) { tma_prefetch_desc(&p.tmO); if (p.residual) tma_prefetch_desc(&p.tmR); }
   }
   for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) sbias[i] = p.bias[i];
   if (warp == 1) tmem_alloc(&ctl->tmem_base, p.tmem_cols);
@@ -194,10 +241,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
+#ifdef STL_CONV_COUNTERS
   long long dbg[4] = {0, 0, 0, 0};
   long long dbg_t = 0;
+#endif
+#ifdef STL_CONV_COUNTERS
 #define DBG_TICK() do { if (p.dbg_counters) dbg_t = clock64(); } while (0)
 #define DBG_TOCK(i) do { if (p.dbg_counters) { const long long t_ = clock64(); dbg[i] += t_ - dbg_t; dbg_t = t_; } } while (0)
+#define DBG_DUMP(role) do { if (p.dbg_counters && lane == 0) for (int i_ = 0; i_ < 4; ++i_) p.dbg_counters[(blockIdx.x * 3 + (role)) * 4 + i_] = dbg[i_]; } while (0)
+#else
+#define DBG_TICK() do { } while (0)
+#define DBG_TOCK(i) do { } while (0)
+#define DBG_DUMP(role) do { } while (0)
+#endif
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
@@ -217,13 +273,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int nti = (int)(tile % p.n_ntiles);
       const long long mt = tile / p.n_ntiles;
       int q0 = 0, wo0 = 0, ho0 = 0, n0 = 0;
-      if (p.mode == 0) {
+      if (kFlatOnly || p.mode == 0) {
         q0 = (int)(mt * (128 * MB));
-        if (p.res_prefetch && elect_one()) {
-#pragma unroll
-          for (int m = 0; m < MB; ++m) tma_prefetch_l2_2d(&p.tmR, nti * p.nt, q0 + m * 128);
-        }
-        __syncwarp();
       } else {
         wo0 = (int)(mt % p.tiles_w) * p.bw;
         ho0 = (int)((mt / p.tiles_w) % p.tiles_h) * p.bh;
@@ -241,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (elect_one()) {
               mbar_expect_tx(&ctl->a_full[s], p.a_tx_bytes);
               const uint32_t dst = a_base + s * p.a_stage_bytes;
-              if (p.mode == 0) {
+              if (kFlatOnly || p.mode == 0) {
                 const int row0 = p.a_shift ? q0 - p.halo : q0 + (kh - 1) * p.in_Wp + (kw - 1);
                 for (int i = 0; i < p.a_pieces; ++i)
                   tma_load_2d_s(dst + (uint32_t)(i * p.a_box_rows) * kSpan, &p.tmA, &ctl->a_full[s], chunk * p.ck,
@@ -270,8 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
     }
-    if (p.dbg_counters && lane == 0)
-      for (int i = 0; i < 4; ++i) p.dbg_counters[(blockIdx.x * 3 + 0) * 4 + i] = dbg[i];
+    DBG_DUMP(0);
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.nt);
@@ -379,32 +429,213 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       __syncwarp();
       ++acc_it;
     }
-    if (p.dbg_counters && lane == 0)
-      for (int i = 0; i < 4; ++i) p.dbg_counters[(blockIdx.x * 3 + 1) * 4 + i] = dbg[i];
+    DBG_DUMP(1);
+  } else if (warp >= 18) {
+    // ------------------------------------------------------------------ epilogue DMA warp of one group: moves staged
+    // panels between shared and global memory with TMA so that the 8 compute warps never wait on an issue slot
+    const int group = warp - 18;
+    if (EPI == kEpiStaged && (p.n_accbuf == 2 || group == 0)) {
+      const int nt = p.nt, n_ntiles = p.n_ntiles;
+      const int panel_ch = p.panel_ch, npanels = nt / panel_ch;
+      const int PT = MB * npanels, bp = p.epi_batch;
+      const uint32_t panel_bytes = p.epi_panel_bytes, pitch = (uint32_t)panel_ch * 2u;
+      const uint32_t stage0 = a_base + p.epi_base_off + (uint32_t)group * 2u * (uint32_t)bp * panel_bytes;
+      const bool has_res = p.residual != nullptr;
+      const long long total_tiles = p.total_tiles;
+      const long long tile_step = (long long)gridDim.x * (p.n_accbuf == 2 ? 2 : 1);
+      const long long first_tile = (long long)blockIdx.x + (p.n_accbuf == 2 ? (long long)group * gridDim.x : 0);
+      const int skip = p.dbg_skip_epilogue;
+      if (lane == 0) {
+        // residual of batch (tile, b0) -> staging buffer sb
+        auto load_res = [&](long long t, int b0, uint32_t sb) {
+          const int nti_ = (int)(t % n_ntiles);
+          const int q0 = (int)((t / n_ntiles) * (128 * MB));
+          const int cnt = PT - b0 < bp ? PT - b0 : bp;
+          uint64_t* bar = &ctl->res_full[group * 2 + sb];
+          mbar_expect_tx(bar, (uint32_t)cnt * 128u * pitch);
+          for (int i = 0; i < cnt; ++i) {
+            const int idx = b0 + i, m = idx / npanels, pn = idx - m * npanels;
+            tma_load_2d_s(stage0 + (sb * (uint32_t)bp + (uint32_t)i) * panel_bytes, &p.tmR, bar,
+                          nti_ * nt + pn * panel_ch, q0 + m * 128);
+          }
+        };
+        uint32_t kb = 0;
+        if (has_res && first_tile < total_tiles) load_res(first_tile, 0, 0);
+#pragma unroll 1
+        for (long long tile = first_tile; tile < total_tiles; tile += tile_step) {
+          const int nti = (int)(tile % n_ntiles);
+          const int q0 = (int)((tile / n_ntiles) * (128 * MB));
+#pragma unroll 1
+          for (int b0 = 0; b0 < PT; b0 += bp, ++kb) {
+            const uint32_t sb = kb & 1;
+            // the other buffer was last read by the stores of batch kb-1: once they have drained it, it can take the
+            // next batch (its residual, or just become writable)
+            bulk_wait_read<0>();
+            {
+              long long t2 = tile;
+              int b2 = b0 + bp;
+              if (b2 >= PT) { b2 = 0; t2 += tile_step; }
+              if (t2 < total_tiles) {
+                if (has_res) load_res(t2, b2, sb ^ 1);
+                else if (kb >= 1) mbar_arrive(&ctl->epi_free[group * 2 + (sb ^ 1)]);
+              }
+            }
+            // all 8 compute warps have written (and fenced) their cells of batch kb
+            mbar_wait(&ctl->epi_done[group * 2 + sb], (kb >> 1) & 1);
+            if (skip != 1) {
+              const int cnt = PT - b0 < bp ? PT - b0 : bp;
+              for (int i = 0; i < cnt; ++i) {
+                const int idx = b0 + i, m = idx / npanels, pn = idx - m * npanels;
+                tma_store_2d_s(&p.tmO, stage0 + (sb * (uint32_t)bp + (uint32_t)i) * panel_bytes,
+                               nti * nt + pn * panel_ch, q0 + m * 128);
+              }
+              bulk_commit();
+            }
+          }
+        }
+        bulk_wait<0>();
+      }
+    }
   } else {
-    // ------------------------------------------------------------------ epilogue: two groups of 4 warps, one per
-    // accumulator buffer, so the TMEM drain of tile t overlaps both the MMAs of tile t+1 and the drain of t+1.
-    const int group = (warp - 2) >> 2;
+    // ------------------------------------------------------------------ epilogue: two groups of 8 warps, one group
+    // per accumulator buffer (the TMEM drain of tile t overlaps the MMAs of tile t+1 and the drain of t+1).
+    // Inside a group every TMEM lane quarter has two warps; a work unit is one 128-row block x 16 channels and
+    // the two warps take alternate 16-channel slices.  Many warps with short dependent chains: the drain is
+    // latency-bound per warp, so throughput comes from warp-level parallelism.
+    const int e_idx = warp - 2;
+    const int group = e_idx >> 3;
+    const int sub = (e_idx >> 2) & 1;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
-    const int nfull = p.nt >> 5;
-    const bool has_res = !NCHW && p.residual != nullptr;
+    const int nt = p.nt;
+    const int nslices = nt >> 4;
+    const int n_ntiles = p.n_ntiles, n_accbuf = p.n_accbuf;
+    EpiParams e;
+    e.out = p.out; e.residual = NCHW ? nullptr : p.residual; e.cout = p.cout; e.relu = p.relu; e.n_up = p.n_up;
+    e.H = p.H; e.W = p.W; e.skip = p.dbg_skip_epilogue;
+    const bool has_res = e.residual != nullptr;
+    const long long total_tiles = p.total_tiles;
+    const int row0 = quarter * 32 + lane;
     uint32_t acc_it = 0;
     DBG_TICK();
+    if constexpr (EPI == kEpiStaged) {
+      // ---- staged epilogue: batches of 128-row x panel_ch panels live in shared memory; the residual arrives by
+      // TMA, each thread updates its own row cells in place, finished panels leave by TMA (issued by this group's
+      // DMA warp).  Global memory only ever sees whole lines; no block-wide barrier is involved.
+      const int panel_ch = p.panel_ch, npanels = nt / panel_ch, spp = panel_ch >> 4;  // 16-channel slices per panel
+      const int PT = MB * npanels, bp = p.epi_batch;
+      const uint32_t pitch = (uint32_t)panel_ch * 2u, swz = (uint32_t)p.panel_swz;
+      const uint32_t panel_bytes = p.epi_panel_bytes;
+      const uint32_t stage0 = a_base + p.epi_base_off + (uint32_t)group * 2u * (uint32_t)bp * panel_bytes;
+      const long long tile_step = (long long)gridDim.x * (n_accbuf == 2 ? 2 : 1);
+      const long long first_tile = (long long)blockIdx.x + (n_accbuf == 2 ? (long long)group * gridDim.x : 0);
+      const bool active = n_accbuf == 2 || group == 0;
+      const int upp = (spp - sub + 1) >> 1;  // 16-channel units of one panel handled by this warp
+      const uint32_t xr = swz == 128 ? (uint32_t)(row0 & 7) : (swz == 64 ? (uint32_t)((row0 >> 1) & 3) : 0u);
+      uint32_t kb = 0;  // batches processed by this group
+      acc_it = n_accbuf == 2 ? (uint32_t)group : 0u;
 #pragma unroll 1
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++acc_it) {
-      if (p.n_accbuf == 2 ? (int)(acc_it & 1) != group : group != 0) continue;
-      const int nti = (int)(tile % p.n_ntiles);
-      const long long mt = tile / p.n_ntiles;
-      const uint32_t buf = p.n_accbuf == 2 ? (uint32_t)group : 0u;
-      const uint32_t aph = (acc_it / p.n_accbuf) & 1;
-      const int chbase = nti * p.nt;
-      const int row0 = quarter * 32 + lane;
+      for (long long tile = first_tile; active && tile < total_tiles; tile += tile_step, acc_it += (n_accbuf == 2 ? 2 : 1)) {
+        const int nti = (int)(tile % n_ntiles);
+        const long long mt = tile / n_ntiles;
+        const uint32_t buf = n_accbuf == 2 ? (uint32_t)group : 0u;
+        const uint32_t aph = (acc_it / n_accbuf) & 1;
+        const int chbase = nti * nt;
+        const uint32_t t_tile = tmem_base + buf * acc_cols + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int b0 = 0; b0 < PT; b0 += bp, ++kb) {
+          const int cnt = PT - b0 < bp ? PT - b0 : bp;
+          const int nunits = cnt * upp;  // <= 3 by construction (host)
+          const uint32_t sbuf = kb & 1;
+          const uint32_t stage = stage0 + sbuf * (uint32_t)bp * panel_bytes;
+          if (b0 == 0) {
+            DBG_TOCK(1);
+            mbar_wait(&ctl->acc_full[buf], aph);
+            DBG_TOCK(0);
+            tc_fence_after();
+          }
+          bool ready = false;
+#pragma unroll 1
+          for (int u = 0; u < nunits; ++u) {
+            const int pi = u / upp;                  // panel inside the batch
+            const int sl = sub + 2 * (u - pi * upp);  // 16-channel slice inside the panel
+            const int idx = b0 + pi;
+            const int m = idx / npanels, pn = idx - m * npanels;
+            const int ch = pn * panel_ch + sl * 16;
+            uint32_t v[16];
+            tmem_ld16(t_tile + (uint32_t)(m * nt + ch), v);
+            const RowPos pos = row_position(p, mt, m * 128 + row0);
+            const uint32_t base = stage + (uint32_t)pi * panel_bytes + (uint32_t)row0 * pitch;
+            const uint32_t c0 = (uint32_t)sl * 2u;  // 16-byte chunks of the slice in its panel row
+            const uint32_t ad0 = base + ((c0 ^ xr) << 4), ad1 = base + (((c0 + 1) ^ xr) << 4);
+            float4 bias[4];
+            const float4* b4 = reinterpret_cast<const float4*>(sbias + chbase + ch);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) bias[g] = b4[g];
+            if (!ready) {
+              // staging buffer ready: residual landed (which implies the buffer was free), or buffer free
+              if (has_res) mbar_wait(&ctl->res_full[group * 2 + sbuf], (kb >> 1) & 1);
+              else mbar_wait(&ctl->epi_free[group * 2 + sbuf], ((kb >> 1) & 1) ^ 1);
+              ready = true;
+              DBG_TOCK(3);
+            }
+            uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+            if (has_res) { r0 = lds128(ad0); r1 = lds128(ad1); }
+            tmem_ld_wait();
+            float* f = reinterpret_cast<float*>(v);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              f[g * 4 + 0] += bias[g].x; f[g * 4 + 1] += bias[g].y; f[g * 4 + 2] += bias[g].z; f[g * 4 + 3] += bias[g].w;
+            }
+            f[0] += bf16_lo(r0.x); f[1] += bf16_hi(r0.x); f[2] += bf16_lo(r0.y); f[3] += bf16_hi(r0.y);
+            f[4] += bf16_lo(r0.z); f[5] += bf16_hi(r0.z); f[6] += bf16_lo(r0.w); f[7] += bf16_hi(r0.w);
+            f[8] += bf16_lo(r1.x); f[9] += bf16_hi(r1.x); f[10] += bf16_lo(r1.y); f[11] += bf16_hi(r1.y);
+            f[12] += bf16_lo(r1.z); f[13] += bf16_hi(r1.z); f[14] += bf16_lo(r1.w); f[15] += bf16_hi(r1.w);
+            uint4 o0, o1;
+            if (e.relu) {
+              o0 = make_uint4(pack_bf16_relu(f[0], f[1]), pack_bf16_relu(f[2], f[3]), pack_bf16_relu(f[4], f[5]),
+                              pack_bf16_relu(f[6], f[7]));
+              o1 = make_uint4(pack_bf16_relu(f[8], f[9]), pack_bf16_relu(f[10], f[11]), pack_bf16_relu(f[12], f[13]),
+                              pack_bf16_relu(f[14], f[15]));
+            } else {
+              o0 = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+              o1 = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
+                              pack_bf16(f[14], f[15]));
+            }
+            if (pos.is_pad) { o0 = make_uint4(0, 0, 0, 0); o1 = o0; }  // zero cells of the padded layout stay zero
+            sts128(ad0, o0);
+            sts128(ad1, o1);
+          }
+          if (!ready) {  // a warp without units in this batch still has to observe the buffer hand-over in order
+            if (has_res) mbar_wait(&ctl->res_full[group * 2 + sbuf], (kb >> 1) & 1);
+            else mbar_wait(&ctl->epi_free[group * 2 + sbuf], ((kb >> 1) & 1) ^ 1);
+          }
+          if (b0 + bp >= PT) {  // accumulator fully drained: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
+          }
+          DBG_TOCK(1);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->epi_done[group * 2 + sbuf]);
+          DBG_TOCK(2);
+        }
+      }
+    } else
+#pragma unroll 1
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
+      if (n_accbuf == 2 ? (int)(acc_it & 1) != group : group != 0) continue;
+      const int nti = (int)(tile % n_ntiles);
+      const long long mt = tile / n_ntiles;
+      const uint32_t buf = n_accbuf == 2 ? (uint32_t)group : 0u;
+      const uint32_t aph = (acc_it / n_accbuf) & 1;
+      const int chbase = nti * nt;
       RowPos pos = row_position(p, mt, row0);
-      // residual of the first 32-channel unit is fetched before waiting for the accumulator; afterwards the
-      // fetch of unit u+1 is issued before unit u is processed
-      uint4 rcur[4], rnext[4];
-      if (has_res && nfull > 0)
-        load_bf16_row<32>(rcur, p.residual + (size_t)pos.q * p.cout + chbase, pos.valid && !pos.is_pad);
+      // the residual of the first slice is fetched before waiting for the accumulator; afterwards the fetch of
+      // slice s+1 is issued before slice s is processed
+      uint4 rcur[2], rnext[2];
+      if (has_res && sub < nslices)
+        load_bf16_row<16>(rcur, e.residual + (size_t)pos.q * e.cout + chbase + sub * 16, pos.valid && !pos.is_pad);
       DBG_TOCK(1);
       mbar_wait(&ctl->acc_full[buf], aph);
       DBG_TOCK(0);
@@ -415,29 +646,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         RowPos pos_next = pos;
         if (m + 1 < MB) pos_next = row_position(p, mt, (m + 1) * 128 + row0);
 #pragma unroll 1
-        for (int j = 0; j < nfull; ++j) {
-          uint32_t v[32];
-          tmem_ld32(t_tile + (uint32_t)(m * p.nt + j * 32), v);
+        for (int sl = sub; sl < nslices; sl += 2) {
+          uint32_t v[16];
+          tmem_ld16(t_tile + (uint32_t)(m * nt + sl * 16), v);
+          float4 bias[4];
+          const float4* b4 = reinterpret_cast<const float4*>(sbias + chbase + sl * 16);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) bias[g] = b4[g];
           if (has_res) {
-            const bool same_row = j + 1 < nfull;
+            const bool same_row = sl + 2 < nslices;
             const RowPos& pn = same_row ? pos : pos_next;
-            const int cn = same_row ? (j + 1) * 32 : 0;
+            const int cn = same_row ? (sl + 2) * 16 : sub * 16;
             if (same_row || m + 1 < MB)
-              load_bf16_row<32>(rnext, p.residual + (size_t)pn.q * p.cout + chbase + cn, pn.valid && !pn.is_pad);
+              load_bf16_row<16>(rnext, e.residual + (size_t)pn.q * e.cout + chbase + cn, pn.valid && !pn.is_pad);
           }
           tmem_ld_wait();
-          epilogue_store<32, NCHW>(p, v, chbase + j * 32, pos, rcur, sbias);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
-        }
-        if (p.nt & 16) {
-          uint32_t v[16];
-          uint4 r2[2];
-          tmem_ld16(t_tile + (uint32_t)(m * p.nt + nfull * 32), v);
-          load_bf16_row<16>(r2, has_res ? p.residual + (size_t)pos.q * p.cout + chbase + nfull * 32 : nullptr,
-                            has_res && pos.valid && !pos.is_pad);
-          tmem_ld_wait();
-          epilogue_store<16, NCHW>(p, v, chbase + nfull * 32, pos, r2, sbias);
+          epilogue_store<16, NCHW>(p, e, v, chbase + sl * 16, pos, rcur, bias);
+          rcur[0] = rnext[0];
+          rcur[1] = rnext[1];
         }
         pos = pos_next;
       }
@@ -446,11 +672,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
       DBG_TOCK(1);
     }
-    if (p.dbg_counters && warp == 2 && lane == 0)
-      for (int i = 0; i < 4; ++i) p.dbg_counters[(blockIdx.x * 3 + 2) * 4 + i] = dbg[i];
+    if (warp == 2) DBG_DUMP(2);
   }
 #undef DBG_TICK
 #undef DBG_TOCK
+#undef DBG_DUMP
 
   tc_fence_before();
   __syncthreads();
@@ -616,6 +842,10 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     if (encode(&p.tmB, s.weights, 3, dims, strides, box, es, span)) return 1;
   }
 
+  p.fd_Wp.init((uint32_t)p.Wp);
+  p.fd_Hp.init((uint32_t)p.Hp);
+  p.fd_bw.init((uint32_t)(p.bw > 0 ? p.bw : 1));
+  p.fd_bh.init((uint32_t)(p.bh > 0 ? p.bh : 1));
   p.a_tx_bytes = (uint32_t)p.a_pieces * p.a_box_rows * span;
   p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
   p.b_tx_bytes = (uint32_t)p.nt * span;
@@ -627,19 +857,33 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
 
   // weights stay resident in shared memory when every tile of the layer fits next to >= 2 activation stages;
   // otherwise they stream through a ring (one stage per (chunk, tap))
-  const size_t budget = kMaxSmem - kCtlBytes - 1024;
+  // staged (TMA) epilogue for flat-mode bf16 outputs: 2 groups x 2 panel buffers x 16 KB
+  p.epi_tma = (p.mode == 0 && !s.out_nchw && s.n_up == 0 && !getenv("STL_DBG_NO_EPI_TMA")) ? 1 : 0;
+  p.panel_ch = (p.nt % 64 == 0) ? 64 : p.nt;
+  p.panel_swz = p.panel_ch == 64 ? 128 : (p.panel_ch == 32 ? 64 : 0);
+  p.epi_panel_bytes = (uint32_t)((p.panel_ch * 2 * 128 + 1023) & ~1023);
+  if (p.epi_panel_bytes > 16384) p.epi_tma = 0;
+  // panels per batch: a whole tile when its panels are small (8 KB), else one; each warp then has at most 3
+  // 16-channel units per batch (slices of a panel alternate between the two warps of a TMEM lane quarter)
+  p.epi_batch = p.epi_panel_bytes <= 8192 ? mb : 1;
+  {
+    const int spp = p.panel_ch / 16;
+    while (p.epi_batch > 1 && p.epi_batch * ((spp + 1) / 2) > 3) --p.epi_batch;
+    if ((spp + 1) / 2 > 3) p.epi_tma = 0;
+  }
+  const size_t epi_bytes = p.epi_tma ? (size_t)2 * 2 * p.epi_batch * p.epi_panel_bytes : 0;
+  const size_t budget = kMaxSmem - kCtlBytes - 1024 - epi_bytes;
   const size_t resident = (size_t)p.n_ntiles * p.n_chunks * p.taps * p.b_stage_bytes;
   const int a_loads_per_tile = p.n_chunks * (p.a_shift || p.taps == 1 ? 1 : p.taps);
   const int a_want = a_loads_per_tile >= 4 ? 4 : (p.a_shift ? 3 : 4);
   int a_st = 2, b_st = 2;
   p.b_resident = (resident <= 120 * 1024 && resident + 2 * (size_t)p.a_stage_bytes <= budget &&
                   resident < (1u << 20) && !getenv("STL_DBG_NO_RESIDENT")) ? 1 : 0;
-  size_t b_bytes_total;
   if (p.b_resident) {
     p.b_resident_bytes = (uint32_t)((size_t)p.n_ntiles * p.n_chunks * p.taps * p.b_tx_bytes);
     while (a_st < a_want && resident + (size_t)(a_st + 1) * p.a_stage_bytes <= budget) ++a_st;
     b_st = 1;
-    b_bytes_total = resident;
+    p.b_bytes_total = (uint32_t)resident;
   } else {
     auto used = [&](int a, int b) { return (size_t)a * p.a_stage_bytes + (size_t)b * p.b_stage_bytes; };
     if (used(2, 2) > budget) a_st = 1;
@@ -652,23 +896,20 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
       if (a_st < a_want && a_st < kMaxStages && used(a_st + 1, b_st) <= budget) { ++a_st; grew = true; }
     }
     if (const char* e = getenv("STL_DBG_B_STAGES")) { int v = atoi(e); if (v >= 1 && v <= b_st) b_st = v; }
-    b_bytes_total = (size_t)b_st * p.b_stage_bytes;
+    p.b_bytes_total = (uint32_t)((size_t)b_st * p.b_stage_bytes);
   }
   if (const char* e = getenv("STL_DBG_A_STAGES")) { int v = atoi(e); if (v >= 1 && v <= a_st) a_st = v; }
   p.a_stages = a_st;
   p.b_stages = b_st;
-  *smem_bytes = kCtlBytes + 1024 + (size_t)a_st * p.a_stage_bytes + b_bytes_total;
-
-  // L2 prefetch of the residual rows the epilogue will read (flat mode): the producer warp touches them
-  // a few tiles ahead so the epilogue's loads hit L2 instead of exposing DRAM latency per 32-channel unit
-  p.res_prefetch = 0;
-  if (p.mode == 0 && s.residual && !s.out_nchw && !getenv("STL_DBG_NO_RES_PREFETCH")) {
+  *smem_bytes = kCtlBytes + 1024 + (size_t)a_st * p.a_stage_bytes + p.b_bytes_total + epi_bytes;
+  p.epi_base_off = (uint32_t)((size_t)a_st * p.a_stage_bytes + p.b_bytes_total);
+  if (p.epi_tma) {
     cuuint64_t dims[2] = {(cuuint64_t)s.cout, (cuuint64_t)p.P};
     cuuint64_t strides[1] = {(cuuint64_t)s.cout * 2};
-    cuuint32_t box[2] = {(cuuint32_t)p.nt, 128};
+    cuuint32_t box[2] = {(cuuint32_t)p.panel_ch, 128};
     cuuint32_t es[2] = {1, 1};
-    if (encode(&p.tmR, s.residual, 2, dims, strides, box, es, 0)) return 1;
-    p.res_prefetch = 1;
+    if (encode(&p.tmO, s.out, 2, dims, strides, box, es, (uint32_t)p.panel_swz)) return 1;
+    if (s.residual && encode(&p.tmR, s.residual, 2, dims, strides, box, es, (uint32_t)p.panel_swz)) return 1;
   }
 
   p.out = s.out;
@@ -678,7 +919,7 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   for (int i = 0; i < kMaxUp; ++i) { p.up_src[i] = s.up_src[i]; p.up_shift[i] = s.up_shift[i]; }
   p.relu = s.relu;
   p.out_nchw = s.out_nchw;
-  p.dbg_skip_epilogue = getenv("STL_DBG_SKIP_EPILOGUE") ? 1 : 0;
+  p.dbg_skip_epilogue = getenv("STL_DBG_SKIP_EPILOGUE") ? 1 : (getenv("STL_DBG_SKIP_STORE") ? 2 : 0);
   p.dbg_counters = reinterpret_cast<long long*>(s.dbg_counters);
   p.cout = s.cout;
   p.cout_pad = s.cout_pad;
@@ -686,33 +927,52 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   long long g = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   if (s.max_ctas > 0 && g > s.max_ctas) g = s.max_ctas;
   *grid = (int)g;
+
+  // a smaller tile can make the difference between streaming the weights for every tile and keeping them resident
+  if (p.mode == 0 && !p.b_resident && !s.force_mb && p.mb > 1 && resident <= 120 * 1024) {
+    ConvSpec s2 = s;
+    ConvParams p2;
+    int g2 = 0;
+    size_t sm2 = 0;
+    for (int mb2 = p.mb - 1; mb2 >= 1; --mb2) {
+      s2.force_mb = mb2;
+      if (conv_prepare(s2, &p2, &g2, &sm2) == 0 && p2.b_resident) {
+        p = p2;
+        *grid = g2;
+        *smem_bytes = sm2;
+        break;
+      }
+    }
+  }
   return 0;
 }
 
 namespace {
 typedef void (*ConvKernel)(const ConvParams);
 template <int MB, int KSTEPS>
-ConvKernel pick_variant(int taps, bool nchw) {
-  if (nchw) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, true> : nullptr;
-  return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, false> : conv_tc_kernel<MB, KSTEPS, 9, false>;
+ConvKernel pick_variant(int taps, int epi) {
+  if (epi == kEpiNchw) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiNchw> : nullptr;
+  if (epi == kEpiStaged) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiStaged> : conv_tc_kernel<MB, KSTEPS, 9, kEpiStaged>;
+  return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiDirect> : conv_tc_kernel<MB, KSTEPS, 9, kEpiDirect>;
 }
 template <int MB>
-ConvKernel pick_ksteps(int ksteps, int taps, bool nchw) {
+ConvKernel pick_ksteps(int ksteps, int taps, int epi) {
   switch (ksteps) {
-    case 1: return pick_variant<MB, 1>(taps, nchw);
-    case 2: return pick_variant<MB, 2>(taps, nchw);
-    case 4: return pick_variant<MB, 4>(taps, nchw);
+    case 1: return pick_variant<MB, 1>(taps, epi);
+    case 2: return pick_variant<MB, 2>(taps, epi);
+    case 4: return pick_variant<MB, 4>(taps, epi);
   }
   return nullptr;
 }
-ConvKernel pick_kernel(int mb, int ksteps, int taps, bool nchw) {
+ConvKernel pick_kernel(int mb, int ksteps, int taps, int epi) {
   switch (mb) {
-    case 1: return pick_ksteps<1>(ksteps, taps, nchw);
-    case 2: return pick_ksteps<2>(ksteps, taps, nchw);
-    case 3: return pick_ksteps<3>(ksteps, taps, nchw);
+    case 1: return pick_ksteps<1>(ksteps, taps, epi);
+    case 2: return pick_ksteps<2>(ksteps, taps, epi);
+    case 3: return pick_ksteps<3>(ksteps, taps, epi);
   }
   return nullptr;
 }
+int epi_kind(const ConvParams& p) { return p.out_nchw ? kEpiNchw : (p.epi_tma ? kEpiStaged : kEpiDirect); }
 }  // namespace
 
 int conv_launch_prepared(const ConvParams& p, int grid, size_t smem_bytes, cudaStream_t stream) {
@@ -720,15 +980,17 @@ int conv_launch_prepared(const ConvParams& p, int grid, size_t smem_bytes, cudaS
   if (!attr_set) {
     for (int mb = 1; mb <= 3; ++mb)
       for (int ks = 1; ks <= 4; ks *= 2)
-        for (int v = 0; v < 3; ++v) {
-          ConvKernel k = pick_kernel(mb, ks, v == 1 ? 9 : 1, v == 2);
-          cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-          if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
-        }
+        for (int epi = 0; epi < 3; ++epi)
+          for (int taps = 1; taps <= 9; taps += 8) {
+            ConvKernel k = pick_kernel(mb, ks, taps, epi);
+            if (!k) continue;
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+          }
     attr_set = true;
   }
   if (grid <= 0) return 0;
-  ConvKernel kern = pick_kernel(p.mb, p.ck / 16, p.taps, p.out_nchw != 0);
+  ConvKernel kern = pick_kernel(p.mb, p.ck / 16, p.taps, epi_kind(p));
   if (!kern) { set_error("conv: no kernel for mb %d ck %d taps %d nchw %d", p.mb, p.ck, p.taps, p.out_nchw); return 1; }
   kern<<<grid, kThreads, smem_bytes, stream>>>(p);
   cudaError_t e = cudaGetLastError();

@@ -26,6 +26,7 @@ CASES = {
     "l1c1": dict(cin=256, cout=64, H=64, W=48, k=1, stride=1, res=False),
     "l1c2": dict(cin=64, cout=64, H=64, W=48, k=3, stride=1, res=False),
     "l1c3": dict(cin=64, cout=256, H=64, W=48, k=1, stride=1, res=True),
+    "l1c3nr": dict(cin=64, cout=256, H=64, W=48, k=1, stride=1, res=False),
     "t1": dict(cin=256, cout=32, H=64, W=48, k=3, stride=1, res=False),
     "s2": dict(cin=32, cout=64, H=64, W=48, k=3, stride=2, res=True),
     "stem2": dict(cin=64, cout=64, H=128, W=96, k=3, stride=2, res=False),
@@ -87,8 +88,9 @@ def main():
         if args.counters:
             c = counters.float().mean(dim=0).cpu() / 1e3
             print("        kcycles/CTA  producer: wait_a_empty %.0f wait_b_empty %.0f issue %.0f | mma: wait_acc %.0f "
-                  "wait_a %.0f wait_b %.0f issue %.0f | epilogue(w2): wait_acc_full %.0f work %.0f"
-                  % (c[0, 0], c[0, 1], c[0, 2], c[1, 0], c[1, 1], c[1, 2], c[1, 3], c[2, 0], c[2, 1]), flush=True)
+                  "wait_a %.0f wait_b %.0f issue %.0f | epilogue(w2): bar1 %.0f compute %.0f fence+bar2 %.0f acc/res wait %.0f"
+                  % (c[0, 0], c[0, 1], c[0, 2], c[1, 0], c[1, 1], c[1, 2], c[1, 3], c[2, 0], c[2, 1], c[2, 2], c[2, 3]),
+                  flush=True)
 
 
 if __name__ == "__main__":
