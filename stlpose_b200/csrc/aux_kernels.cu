@@ -167,34 +167,35 @@ struct FuseArgs {
   int N, H, W, C;
 };
 
-__global__ void fuse_sum_kernel(const FuseArgs a) {
+__global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseArgs a) {
+  // blockIdx.x walks padded image rows (n, h); threads walk (w, 8-channel group) of that row: no per-element div/mod
   const int c8n = a.C / 8;
-  const long long total = (long long)a.N * (a.H + 1) * (a.W + 1) * c8n;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % c8n);
-    const long long q = i / c8n;
-    const int w = (int)(q % (a.W + 1));
-    const long long t = q / (a.W + 1);
-    const int h = (int)(t % (a.H + 1));
-    const int n = (int)(t / (a.H + 1));
-    uint4 out = make_uint4(0, 0, 0, 0);
-    if (h < a.H && w < a.W) {
-      const uint4 u = *reinterpret_cast<const uint4*>(a.x + (size_t)q * a.C + c8 * 8);
-      float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                    bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
-      for (int k = 0; k < a.n_up; ++k) {
-        const int s = a.shift[k];
-        const size_t qs = ((size_t)n * ((a.H >> s) + 1) + (h >> s)) * ((a.W >> s) + 1) + (w >> s);
-        const uint4 z = *reinterpret_cast<const uint4*>(a.z[k] + qs * a.C + c8 * 8);
-        f[0] += bf16_lo(z.x); f[1] += bf16_hi(z.x); f[2] += bf16_lo(z.y); f[3] += bf16_hi(z.y);
-        f[4] += bf16_lo(z.z); f[5] += bf16_hi(z.z); f[6] += bf16_lo(z.w); f[7] += bf16_hi(z.w);
-      }
+  const int row_items = (a.W + 1) * c8n;
+  const int rows = a.N * (a.H + 1);
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int n = r / (a.H + 1), h = r - n * (a.H + 1);
+    const size_t rowq = (size_t)r * (a.W + 1);
+    for (int i = threadIdx.x; i < row_items; i += blockDim.x) {
+      const int w = i / c8n, c8 = i - w * c8n;
+      const size_t off = (rowq + w) * a.C + c8 * 8;
+      uint4 out = make_uint4(0, 0, 0, 0);
+      if (h < a.H && w < a.W) {
+        const uint4 u = __ldcs(reinterpret_cast<const uint4*>(a.x + off));
+        float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                      bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+        for (int k = 0; k < a.n_up; ++k) {
+          const int s = a.shift[k];
+          const size_t qs = ((size_t)n * ((a.H >> s) + 1) + (h >> s)) * ((a.W >> s) + 1) + (w >> s);
+          const uint4 z = __ldg(reinterpret_cast<const uint4*>(a.z[k] + qs * a.C + c8 * 8));
+          f[0] += bf16_lo(z.x); f[1] += bf16_hi(z.x); f[2] += bf16_lo(z.y); f[3] += bf16_hi(z.y);
+          f[4] += bf16_lo(z.z); f[5] += bf16_hi(z.z); f[6] += bf16_lo(z.w); f[7] += bf16_hi(z.w);
+        }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
-      out = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+        out = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+      }
+      __stcs(reinterpret_cast<uint4*>(a.y + off), out);
     }
-    *reinterpret_cast<uint4*>(a.y + (size_t)q * a.C + c8 * 8) = out;
   }
 }
 
@@ -304,8 +305,8 @@ int fuse_sum(const __nv_bfloat16* x, const __nv_bfloat16* const* z, const int* s
   FuseArgs a{};
   a.x = x; a.y = y; a.n_up = n_up; a.N = N; a.H = H; a.W = W; a.C = C;
   for (int i = 0; i < n_up; ++i) { a.z[i] = z[i]; a.shift[i] = shift[i]; }
-  const long long total = (long long)N * (H + 1) * (W + 1) * (C / 8);
-  fuse_sum_kernel<<<grid_for(total, 256), 256, 0, st>>>(a);
+  const int rows = N * (H + 1);
+  fuse_sum_kernel<<<rows < 148 * 16 ? rows : 148 * 16, 256, 0, st>>>(a);
   return check("fuse_sum");
 }
 
