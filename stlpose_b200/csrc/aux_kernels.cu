@@ -168,33 +168,45 @@ struct FuseArgs {
 };
 
 __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseArgs a) {
-  // blockIdx.x walks padded image rows (n, h); threads walk (w, 8-channel group) of that row: no per-element div/mod
+  // flat walk over (padded pixel, 8-channel group) items, 4 independent items per thread per iteration so that
+  // four 16-byte loads are in flight before the first one is consumed
   const int c8n = a.C / 8;
-  const int row_items = (a.W + 1) * c8n;
-  const int rows = a.N * (a.H + 1);
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int n = r / (a.H + 1), h = r - n * (a.H + 1);
-    const size_t rowq = (size_t)r * (a.W + 1);
-    for (int i = threadIdx.x; i < row_items; i += blockDim.x) {
-      const int w = i / c8n, c8 = i - w * c8n;
-      const size_t off = (rowq + w) * a.C + c8 * 8;
+  const int Wp = a.W + 1, Hp = a.H + 1;
+  const long long total = (long long)a.N * Hp * Wp * c8n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    uint4 u[4];
+    long long idx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      idx[k] = i0 + k * stride;
+      u[k] = idx[k] < total ? __ldcs(reinterpret_cast<const uint4*>(a.x) + idx[k]) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (idx[k] >= total) continue;
+      const int c8 = (int)(idx[k] % c8n);
+      const long long q = idx[k] / c8n;
+      const int w = (int)(q % Wp);
+      const long long t = q / Wp;
+      const int h = (int)(t % Hp);
+      const int n = (int)(t / Hp);
       uint4 out = make_uint4(0, 0, 0, 0);
       if (h < a.H && w < a.W) {
-        const uint4 u = __ldcs(reinterpret_cast<const uint4*>(a.x + off));
-        float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                      bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
-        for (int k = 0; k < a.n_up; ++k) {
-          const int s = a.shift[k];
+        float f[8] = {bf16_lo(u[k].x), bf16_hi(u[k].x), bf16_lo(u[k].y), bf16_hi(u[k].y),
+                      bf16_lo(u[k].z), bf16_hi(u[k].z), bf16_lo(u[k].w), bf16_hi(u[k].w)};
+        for (int j = 0; j < a.n_up; ++j) {
+          const int s = a.shift[j];
           const size_t qs = ((size_t)n * ((a.H >> s) + 1) + (h >> s)) * ((a.W >> s) + 1) + (w >> s);
-          const uint4 z = __ldg(reinterpret_cast<const uint4*>(a.z[k] + qs * a.C + c8 * 8));
+          const uint4 z = __ldg(reinterpret_cast<const uint4*>(a.z[j] + qs * a.C + c8 * 8));
           f[0] += bf16_lo(z.x); f[1] += bf16_hi(z.x); f[2] += bf16_lo(z.y); f[3] += bf16_hi(z.y);
           f[4] += bf16_lo(z.z); f[5] += bf16_hi(z.z); f[6] += bf16_lo(z.w); f[7] += bf16_hi(z.w);
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
         out = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
       }
-      __stcs(reinterpret_cast<uint4*>(a.y + off), out);
+      __stcs(reinterpret_cast<uint4*>(a.y) + idx[k], out);
     }
   }
 }
@@ -305,8 +317,10 @@ int fuse_sum(const __nv_bfloat16* x, const __nv_bfloat16* const* z, const int* s
   FuseArgs a{};
   a.x = x; a.y = y; a.n_up = n_up; a.N = N; a.H = H; a.W = W; a.C = C;
   for (int i = 0; i < n_up; ++i) { a.z[i] = z[i]; a.shift[i] = shift[i]; }
-  const int rows = N * (H + 1);
-  fuse_sum_kernel<<<rows < 148 * 16 ? rows : 148 * 16, 256, 0, st>>>(a);
+  const long long total = (long long)N * (H + 1) * (W + 1) * (C / 8);
+  long long blocks = (total + 4 * 256 - 1) / (4 * 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  fuse_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
   return check("fuse_sum");
 }
 

@@ -27,8 +27,9 @@ namespace stl {
 
 namespace {
 
-constexpr int kThreads = 640;          // warp 0: TMA, warp 1: MMA, warps 2..17: two epilogue groups of 8 warps,
-                                       // warps 18..19: one epilogue DMA warp per group (panel loads / stores)
+constexpr int kThreads = 672;          // warp 0: TMA, warp 1: MMA, warps 2..17: two epilogue groups of 8 warps,
+                                       // warps 18..19: one epilogue DMA warp per group (panel loads / stores),
+                                       // warp 20: second MMA issuer (burst mode: the 128-row blocks of a tile are split)
 constexpr uint32_t kCtlBytes = 4096;   // [0,1024): barriers + TMEM base ; [1024,4096): fp32 bias for all channels
 constexpr uint32_t kBiasOffset = 1024;
 constexpr int kMaxCoutPad = 768;
@@ -225,9 +226,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const bool burst = p.b_resident && (p.a_shift || TAPS == 1);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&ctl->a_full[i], 1); mbar_init(&ctl->a_empty[i], 1); }
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&ctl->a_full[i], 1); mbar_init(&ctl->a_empty[i], p.n_mma); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], 1); mbar_init(&ctl->acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], p.n_mma); mbar_init(&ctl->acc_empty[i], 8); }
     for (int i = 0; i < 4; ++i) { mbar_init(&ctl->res_full[i], 1); mbar_init(&ctl->epi_free[i], 1); mbar_init(&ctl->epi_done[i], 8); }
     fence_mbar_init();
     tma_prefetch_desc(&p.tmA);
@@ -322,8 +323,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
     DBG_DUMP(0);
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
+  } else if (warp == 1 || warp == 20) {
+    // ------------------------------------------------------------------ MMA issuer(s) (whole warp loops, one lane issues).
+    // A single thread sustains one tcgen05.mma per ~45 cycles, more than the math of an N <= 64 instruction, so in
+    // burst mode a second warp issues the upper 128-row blocks of every tile (disjoint accumulators).
+    const int part = warp == 20 ? 1 : 0;
+    const int m_split = p.n_mma == 2 ? (MB + 1) / 2 : MB;
+    const int m_lo = part == 0 ? 0 : m_split, m_hi = part == 0 ? m_split : MB;
+    if (part == 1 && p.n_mma != 2) goto role_done;
+    {
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.nt);
     const uint64_t desc_hi = make_kmajor_desc(0, kSpan) & 0xFFFFFFFF00000000ull;
     const uint32_t desc_lo_flags = (uint32_t)(make_kmajor_desc(0, kSpan) & 0xFFFFFFFFull);
@@ -365,6 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               for (int k = 0; k < KSTEPS; ++k) {
 #pragma unroll
                 for (int m = 0; m < MB; ++m) {
+                  if (m < m_lo || m >= m_hi) continue;
                   const uint64_t da = desc_hi | (uint64_t)(a_lo + (uint32_t)((m * 128 * (int)kSpan + k * 32) >> 4));
                   const uint64_t db = desc_hi | (uint64_t)(b_lo + (uint32_t)((k * 32) >> 4));
                   umma_bf16(d_base + (uint32_t)m * nt, da, db, idesc, (tap | k) != 0 ? 1u : (uint32_t)chunk);
@@ -429,7 +438,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       __syncwarp();
       ++acc_it;
     }
-    DBG_DUMP(1);
+    if (part == 0) DBG_DUMP(1);
+    }
   } else if (warp >= 18) {
     // ------------------------------------------------------------------ epilogue DMA warp of one group: moves staged
     // panels between shared and global memory with TMA so that the 8 compute warps never wait on an issue slot
@@ -556,10 +566,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           bool ready = false;
 #pragma unroll 1
           for (int u = 0; u < nunits; ++u) {
-            const int pi = u / upp;                  // panel inside the batch
-            const int sl = sub + 2 * (u - pi * upp);  // 16-channel slice inside the panel
+            const int pi = upp == 1 ? u : (upp == 2 ? u >> 1 : u / upp);   // panel inside the batch
+            const int sl = sub + 2 * (u - pi * upp);                        // 16-channel slice inside the panel
             const int idx = b0 + pi;
-            const int m = idx / npanels, pn = idx - m * npanels;
+            const int m = npanels == 1 ? idx : (npanels == 2 ? idx >> 1 : idx / npanels), pn = idx - m * npanels;
             const int ch = pn * panel_ch + sl * 16;
             uint32_t v[16];
             tmem_ld16(t_tile + (uint32_t)(m * nt + ch), v);
@@ -674,6 +684,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     if (warp == 2) DBG_DUMP(2);
   }
+role_done:
 #undef DBG_TICK
 #undef DBG_TOCK
 #undef DBG_DUMP
@@ -901,6 +912,8 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   if (const char* e = getenv("STL_DBG_A_STAGES")) { int v = atoi(e); if (v >= 1 && v <= a_st) a_st = v; }
   p.a_stages = a_st;
   p.b_stages = b_st;
+  // measured on B200: a second issuer pays off only for N <= 32 (16-cycle MMAs); at N = 64 the two streams interfere
+  p.n_mma = (p.b_resident && (p.a_shift || p.taps == 1) && p.mb >= 2 && p.nt <= 32 && !getenv("STL_DBG_SINGLE_MMA")) ? 2 : 1;
   *smem_bytes = kCtlBytes + 1024 + (size_t)a_st * p.a_stage_bytes + p.b_bytes_total + epi_bytes;
   p.epi_base_off = (uint32_t)((size_t)a_st * p.a_stage_bytes + p.b_bytes_total);
   if (p.epi_tma) {
