@@ -181,13 +181,10 @@ def run_ours(args):
         gather_results()
 
     def step_e2e():
-        pipe.x.copy_(x_host, non_blocking=True)
-        pipe.center.copy_(c_host, non_blocking=True)
-        pipe.scale.copy_(s_host, non_blocking=True)
-        pipe.step()
+        # the public call: pinned host crops/boxes in, pinned host keypoints out (H2D of the next batch overlaps
+        # the current pass inside KeypointPipeline)
+        pipe(x_host, c_host, s_host, p_host, m_host)
         gather_results()
-        p_host.copy_(pipe.preds, non_blocking=True)
-        m_host.copy_(pipe.maxvals, non_blocking=True)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):

@@ -81,79 +81,28 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
   }
 }
 
-// ------------------------------------------------------------------ stem conv1: 3 -> 64, 3x3, stride 2, pad 1
-// Reads the fp32 NCHW network input directly (images n >= n_plain are image n - n_plain mirrored in W: the
-// flip-test pass of lib/inference.py:21), applies folded BN + ReLU, writes padded-linear NHWC bf16.
-// 256 threads = 64 output pixels x 4 groups of 16 output channels; a warp shares its weight reads (broadcast).
-constexpr int kStemCout = 64;
-__global__ void __launch_bounds__(256) stem_conv1_kernel(const float* __restrict__ x, const float* __restrict__ wf,
-                                                         const float* __restrict__ bias,
-                                                         __nv_bfloat16* __restrict__ y, int n_total, int n_plain,
-                                                         int H, int W) {
-  __shared__ float ws[27 * kStemCout];  // [tap*3+ci][cout]
-  __shared__ float bs[kStemCout];
-  for (int i = threadIdx.x; i < 27 * kStemCout; i += blockDim.x) ws[i] = wf[i];
-  if (threadIdx.x < kStemCout) bs[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const int Ho = H / 2, Wo = W / 2;
-  const long long pix = (long long)blockIdx.x * 64 + (threadIdx.x & 63);
-  const int cg = threadIdx.x >> 6;
-  if (pix >= (long long)n_total * Ho * Wo) return;
-  const int wo = (int)(pix % Wo);
-  const int ho = (int)((pix / Wo) % Ho);
-  const int n = (int)(pix / ((long long)Wo * Ho));
-  const bool flip = n >= n_plain;
-  const float* xin = x + (size_t)(flip ? n - n_plain : n) * 3 * H * W;
-  float acc[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = bs[cg * 16 + i];
-#pragma unroll
-  for (int kh = 0; kh < 3; ++kh) {
-    const int h = 2 * ho + kh - 1;
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int w = 2 * wo + kw - 1;
-      const bool ok = h >= 0 && h < H && w >= 0 && w < W;
-      const int wsrc = flip ? W - 1 - w : w;
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        const float v = ok ? __ldg(xin + ((size_t)ci * H + h) * W + wsrc) : 0.f;
-        const float4* wrow = reinterpret_cast<const float4*>(ws + ((kh * 3 + kw) * 3 + ci) * kStemCout + cg * 16);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float4 w4 = wrow[g];
-          acc[g * 4 + 0] = fmaf(v, w4.x, acc[g * 4 + 0]);
-          acc[g * 4 + 1] = fmaf(v, w4.y, acc[g * 4 + 1]);
-          acc[g * 4 + 2] = fmaf(v, w4.z, acc[g * 4 + 2]);
-          acc[g * 4 + 3] = fmaf(v, w4.w, acc[g * 4 + 3]);
-        }
-      }
-    }
+// ------------------------------------------------------------------ network input -> tensor-core layout
+// fp32 NCHW [B][3][H][W] -> padded-linear NHWC bf16 with the 3 channels padded to 16 (one UMMA K-step), so that the
+// stem's 3->64 stride-2 conv runs on the same tcgen05 kernel as every other layer.  Images n >= n_plain are image
+// n - n_plain mirrored in W: the flip-test pass of lib/inference.py:21 costs no extra input traffic.
+constexpr int kStemCin = 16;
+__global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                        int n_total, int n_plain, int H, int W) {
+  const long long total = (long long)n_total * H * W;
+  const size_t plane = (size_t)H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const long long t = i / W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    const bool flip = n >= n_plain;
+    const float* src = x + (size_t)(flip ? n - n_plain : n) * 3 * plane + (size_t)h * W + (flip ? W - 1 - w : w);
+    const float r = __ldcs(src), g = __ldcs(src + plane), b = __ldcs(src + 2 * plane);
+    uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)n * (H + 1) + h) * (W + 1) + w) * kStemCin);
+    dst[0] = make_uint4(pack_bf16(r, g), pack_bf16(b, 0.f), 0u, 0u);
+    dst[1] = make_uint4(0u, 0u, 0u, 0u);
   }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = fmaxf(acc[i], 0.f);
-  const size_t q = ((size_t)n * (Ho + 1) + ho) * (Wo + 1) + wo;
-  uint4* o = reinterpret_cast<uint4*>(y + q * kStemCout + cg * 16);
-  o[0] = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
-                    pack_bf16(acc[6], acc[7]));
-  o[1] = make_uint4(pack_bf16(acc[8], acc[9]), pack_bf16(acc[10], acc[11]), pack_bf16(acc[12], acc[13]),
-                    pack_bf16(acc[14], acc[15]));
-}
-
-// w_oihw [64][3][3][3] (+BN) -> wf [kh][kw][ci][64] fp32 (the stem runs on CUDA cores in full fp32)
-__global__ void pack_stem_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, const float* __restrict__ mean,
-                                 const float* __restrict__ var, float eps, float* __restrict__ wf,
-                                 float* __restrict__ bias) {
-  for (int i = threadIdx.x; i < 27 * kStemCout; i += blockDim.x) {
-    const int co = i % kStemCout;
-    const int ci = (i / kStemCout) % 3;
-    const int t = i / (kStemCout * 3);
-    const float scale = gamma[co] / sqrtf(var[co] + eps);
-    wf[i] = w[((size_t)co * 3 + ci) * 9 + t] * scale;
-  }
-  for (int co = threadIdx.x; co < kStemCout; co += blockDim.x)
-    bias[co] = beta[co] - mean[co] * gamma[co] / sqrtf(var[co] + eps);
 }
 
 // ------------------------------------------------------------------ fuse-layer sum at the highest resolution
@@ -298,18 +247,10 @@ int pack_weights(const float* w, const float* gamma, const float* beta, const fl
   return check("pack_weights");
 }
 
-int pack_stem(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
-              float* wf, float* bias, cudaStream_t st) {
-  pack_stem_kernel<<<1, 256, 0, st>>>(w, gamma, beta, mean, var, eps, wf, bias);
-  return check("pack_stem");
-}
-
-int stem_conv1(const float* x, const float* wf, const float* bias, __nv_bfloat16* y, int n_total, int n_plain, int H,
-               int W, cudaStream_t st) {
-  const long long pix = (long long)n_total * (H / 2) * (W / 2);
-  const long long blocks = (pix + 63) / 64;
-  stem_conv1_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, wf, bias, y, n_total, n_plain, H, W);
-  return check("stem_conv1");
+int stem_pack_input(const float* x, __nv_bfloat16* y, int n_total, int n_plain, int H, int W, cudaStream_t st) {
+  const long long total = (long long)n_total * H * W;
+  stem_pack_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, y, n_total, n_plain, H, W);
+  return check("stem_pack_input");
 }
 
 int fuse_sum(const __nv_bfloat16* x, const __nv_bfloat16* const* z, const int* shift, int n_up, __nv_bfloat16* y,

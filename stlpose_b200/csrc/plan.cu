@@ -36,13 +36,9 @@ struct Plan::Builder {
     L.bn_key = bn_key;
     L.cout = cout; L.cin = cin; L.k = k; L.stride = stride;
     L.cout_pad = (int)align_up(cout, 16);
-    L.is_stem = (cin == 3);
+    L.cin_pad = (int)align_up(cin, 16);   // the 3-channel network input is padded to one UMMA K-step
     L.w_off = P.weight_bytes;
-    if (L.is_stem) {
-      P.weight_bytes += align_up(sizeof(float) * 27 * 64, 256);
-    } else {
-      P.weight_bytes += align_up((size_t)k * k * L.cout_pad * cin * 2, 256);
-    }
+    P.weight_bytes += align_up((size_t)k * k * L.cout_pad * L.cin_pad * 2, 256);
     L.b_off = P.weight_bytes;
     P.weight_bytes += align_up(sizeof(float) * L.cout_pad, 256);
     P.layers.push_back(L);
@@ -70,7 +66,7 @@ struct Plan::Builder {
   void conv(int layer, int in, int out, int res, bool relu, int n_up = 0, const int* up = nullptr,
             const int* up_shift = nullptr, bool out_nchw = false) {
     Plan::Op op;
-    op.kind = P.layers[layer].is_stem ? Plan::OP_STEM : Plan::OP_CONV;
+    op.kind = Plan::OP_CONV;
     op.layer = layer; op.in = in; op.out = out; op.res = res; op.relu = relu; op.out_nchw = out_nchw;
     op.n_up = n_up;
     for (int i = 0; i < n_up; ++i) { op.up[i] = up[i]; op.up_shift[i] = up_shift[i]; }
@@ -93,8 +89,16 @@ struct Plan::Builder {
     char k1[128], k2[128];
 
     // stem (HRnet.py:434-439)
+    int xin = acquire(16, c.image_h, c.image_w);
+    {
+      Plan::Op op;
+      op.kind = Plan::OP_STEM;   // fp32 NCHW network input -> padded NHWC bf16 (3 -> 16 channels, flip half mirrored)
+      op.out = xin;
+      P.ops.push_back(op);
+    }
     int t0 = acquire(64, c.image_h / 2, c.image_w / 2);
-    conv(layer("conv1", "bn1", 64, 3, 3, 2), -1, t0, -1, true);
+    conv(layer("conv1", "bn1", 64, 3, 3, 2), xin, t0, -1, true);
+    release(xin);
     int x = acquire(64, H4, W4);
     conv(layer("conv2", "bn2", 64, 64, 3, 2), t0, x, -1, true);
     release(t0);
@@ -243,12 +247,7 @@ int Plan::pack_conv(int index, const float* w, const float* gamma, const float* 
   const Layer& L = layers[index];
   uint8_t* base = reinterpret_cast<uint8_t*>(arena);
   bound = false;  // packed parameters changed; tensor maps stay valid but be conservative
-  if (L.is_stem) {
-    if (!gamma) { set_error("pack_conv: stem needs BatchNorm parameters"); return 1; }
-    return pack_stem(w, gamma, beta, mean, var, eps, reinterpret_cast<float*>(base + L.w_off),
-                     reinterpret_cast<float*>(base + L.b_off), st);
-  }
-  return pack_weights(w, gamma, beta, mean, var, cbias, eps, L.cout, L.cin, L.k, L.cout_pad, L.cin,
+  return pack_weights(w, gamma, beta, mean, var, cbias, eps, L.cout, L.cin, L.k, L.cout_pad, L.cin_pad,
                       reinterpret_cast<__nv_bfloat16*>(base + L.w_off), reinterpret_cast<float*>(base + L.b_off), st);
 }
 
@@ -327,10 +326,8 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
     const Op& op = ops[i];
     switch (op.kind) {
       case OP_STEM: {
-        const Layer& L = layers[op.layer];
-        if (stem_conv1(x, reinterpret_cast<const float*>(wbase + L.w_off),
-                       reinterpret_cast<const float*>(wbase + L.b_off),
-                       reinterpret_cast<__nv_bfloat16*>(slot_ptr[op.out]), n_images, B, cfg.image_h, cfg.image_w, st))
+        if (stem_pack_input(x, reinterpret_cast<__nv_bfloat16*>(slot_ptr[op.out]), n_images, B, cfg.image_h,
+                            cfg.image_w, st))
           return 1;
         break;
       }
@@ -368,6 +365,11 @@ int Plan::op_info(int i, stl_op_info* info) const {
   info->layer = op.layer;
   const Slot* so = op.out >= 0 ? &slots[op.out] : nullptr;
   const Slot* si = op.in >= 0 ? &slots[op.in] : nullptr;
+  if (op.kind == OP_STEM) {
+    info->out_h = cfg.image_h; info->out_w = cfg.image_w; info->cin = 3; info->cout = 16;
+    info->bytes_per_image = (double)cfg.image_h * cfg.image_w * (3 * 4 + 16 * 2);
+    return 0;
+  }
   if (op.kind == OP_FUSE) {
     info->out_h = so->H; info->out_w = so->W; info->cout = so->C; info->cin = so->C;
     info->bytes_per_image = 2.0 * so->H * so->W * so->C * 2;

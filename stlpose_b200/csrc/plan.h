@@ -14,8 +14,7 @@ namespace stl {
 struct Plan {
   struct Layer {
     std::string conv_key, bn_key;
-    int cout, cin, k, stride, cout_pad;
-    bool is_stem;
+    int cout, cin, k, stride, cout_pad, cin_pad;
     size_t w_off, b_off;
   };
   struct Slot { int C, H, W; };

@@ -36,7 +36,7 @@ def test_plan_topology_without_gpu():
         plan = m._plan(*hw)
         n = L.stl_plan_num_convs(plan)
         assert n == 293                                   # 293 convs
-        assert L.stl_plan_launches_per_forward(plan) == 293 + 8   # + one fuse-sum kernel per HRModule
+        assert L.stl_plan_launches_per_forward(plan) == 293 + 8 + 1   # + fuse-sum per HRModule + input packing
         schema = dict(hrnet_oracle.hrnet_schema(width))
         info = _lib.ConvInfo()
         seen = set()

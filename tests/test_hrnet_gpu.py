@@ -93,3 +93,22 @@ def test_module_contract():
     # DataParallel-wrapped module works as the reference's callers pass it (03_evaluate.py:100)
     out = S.forward_pass(torch.nn.DataParallel(mc, device_ids=[0]), x, "HRNet", device="cuda", flip=False)
     assert torch.equal(out, y1)
+
+
+def test_pipeline_graph_matches_eager_calls():
+    """KeypointPipeline (CUDA graph + double-buffered H2D staging) == forward_pass + get_final_preds_hrnet."""
+    import stlpose_b200 as S
+    from stlpose_b200.pipeline import KeypointPipeline
+    B = 6
+    m = _model(32, (256, 192))
+    pipe = KeypointPipeline(m, B, (256, 192), flip=True, use_graph=True)
+    for seed in (1, 2, 3):
+        x = torch.randn(B, 3, 256, 192, generator=torch.Generator().manual_seed(seed)).pin_memory()
+        c_np, s_np = pose_oracle.synth_boxes(B, seed=seed)
+        c = torch.from_numpy(c_np).float().pin_memory()
+        s = torch.from_numpy(s_np).float().pin_memory()
+        p_host, m_host = pipe(x, c, s)
+        torch.cuda.synchronize()
+        heat = S.forward_pass(m, x.cuda(), "HRNet", device="cuda", flip=True)
+        preds, maxv, _ = S.get_final_preds_hrnet(heat, c_np.astype(np.float32), s_np.astype(np.float32))
+        assert np.array_equal(p_host.numpy(), preds) and np.array_equal(m_host.numpy(), maxv)
