@@ -84,8 +84,12 @@ def cpu_port_crops_per_sec(n_crops, repeats=1, threads=None):
     """Time the oracle port of the reference path (forward_pass(flip=True) + get_final_preds_hrnet) on host cores."""
     import torch
     from oracle import hrnet_oracle, pose_oracle
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it is allowed to run on
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(threads or avail)
     sd = hrnet_oracle.synth_state_dict(WIDTH, seed=0)
     x = torch.randn(n_crops, 3, *IMAGE, generator=torch.Generator().manual_seed(0))
     center, scale = pose_oracle.synth_boxes(n_crops, seed=0)
