@@ -25,6 +25,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WIDTH, IMAGE = 32, (256, 192)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel shape, from the committed
+# `ncu --set full` capture profiles/r01_ncu_conv.md (prof5_c32): 417.67 MB read + 176.53 MB written
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 594.2e6
+NCU_TRAFFIC_NOTE = ("conv_tc_kernel<3,2,9,staged>, 32->32 3x3 @64x48 + residual over 1024 images (64 of the 293 conv "
+                    "launches per forward, 22 % of step time); algorithmic bytes of that launch: 604 MB")
 FLOPS_PER_FORWARD = 15.290007552e9   # HRNet-W32 @256x192, 2*MACs over the 293 convs (oracle.conv_flops_per_crop)
 
 
@@ -252,7 +257,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": pipe.launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": achieved_tf, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                         "traffic_note": NCU_TRAFFIC_NOTE,
                          "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)",
                          "launches_per_step": conv_n, "conv_ms_per_step": conv_ms, "other_kernels_ms": other_ms,
                          "whole_step_frac": (2 * FLOPS_PER_FORWARD * B / (ms_step * 1e-3) / 1e12) / peak_tf},
@@ -286,6 +292,14 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1 and the OpenMP pool is sized when torch is first imported: give the
+        # CPU arm every core this process may run on BEFORE that import
+        try:
+            avail = len(os.sched_getaffinity(0))
+        except AttributeError:
+            avail = os.cpu_count() or 1
+        os.environ["OMP_NUM_THREADS"] = str(avail)
+        os.environ["MKL_NUM_THREADS"] = str(avail)
         run_reference(args)
     else:
         run_ours(args)

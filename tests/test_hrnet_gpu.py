@@ -112,3 +112,17 @@ def test_pipeline_graph_matches_eager_calls():
         heat = S.forward_pass(m, x.cuda(), "HRNet", device="cuda", flip=True)
         preds, maxv, _ = S.get_final_preds_hrnet(heat, c_np.astype(np.float32), s_np.astype(np.float32))
         assert np.array_equal(p_host.numpy(), preds) and np.array_equal(m_host.numpy(), maxv)
+
+
+def test_batch_independence_at_bench_scale():
+    """Crops are independent units: any crop's heatmaps are bit-identical whatever batch (and tile boundaries) it
+    travels in.  Run at a batch where every layer spans many tiles and CTAs walk several tiles each."""
+    B = 160
+    m = _model(32, (256, 192))
+    x = torch.randn(B, 3, 256, 192, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    big = m.forward_flip_pair(x).clone()
+    for lo, hi in ((0, 3), (77, 80), (157, 160)):
+        small = m.forward_flip_pair(x[lo:hi])
+        n = hi - lo
+        assert torch.equal(small[:n], big[lo:hi]) and torch.equal(small[n:], big[B + lo:B + hi])
+    assert torch.isfinite(big).all()

@@ -97,7 +97,7 @@ def test_loss_forward_backward(golden, golden_inputs):
         S.PersonMSELoss()(o, o)
 
 
-@pytest.mark.parametrize("batch", [1024, 16384])
+@pytest.mark.parametrize("batch", [1024, 16384, 65536])
 def test_decode_full_size_properties(batch):
     """BASELINE config 5 sizes: size-independent properties instead of a CPU oracle pass."""
     import stlpose_b200 as S
@@ -112,3 +112,30 @@ def test_decode_full_size_properties(batch):
     # shifting a map by a constant does not move its argmax; scaling by a positive constant neither
     c2, m2 = S.get_max_preds_hrnet(hm * 2.0 + 100.0, as_tensor=True)
     assert torch.equal(c2, coords)
+
+
+def test_decode_96x72_full_size_properties():
+    """BASELINE config 5, 96x72 maps: flip-fused decode == decode of the separately averaged maps (bit-exact)."""
+    import stlpose_b200 as S
+    from stlpose_b200 import _lib
+    from stlpose_b200.pose_parsing import _decode
+    from stlpose_b200.transforms import _pairs_array
+    B = 4096
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    a = torch.randn(B, 17, 96, 72, device="cuda", generator=gen)
+    f = torch.randn(B, 17, 96, 72, device="cuda", generator=gen)
+    avg = torch.empty_like(a)
+    pairs, n = _pairs_array(S.FLIP_PAIRS)
+    _lib.check(_lib.lib().stl_flip_avg(_lib.ptr(a), _lib.ptr(f), _lib.ptr(avg), B, 17, 96, 72, pairs, n,
+                                       _lib.current_stream()))
+    _, m1, c1, _ = _decode(avg, None, None, True)
+    _, m2, c2, avg2 = _decode(a, None, None, True, heat_flipped=f, pairs=S.FLIP_PAIRS, want_avg=True)
+    assert torch.equal(avg, avg2) and torch.equal(m1, m2) and torch.equal(c1, c2)
+    # linearity of the loss gradient in (out - tgt) and its closed form at full size
+    tw = torch.ones(B, 17, 1, device="cuda")
+    o = a.clone().requires_grad_(True)
+    loss = S.PersonMSELoss()(o, f, tw)
+    loss.backward()
+    denom = 17 * B * 96 * 72
+    assert torch.allclose(o.grad, (a - f) / denom, rtol=1e-5, atol=1e-12)
+    assert abs(loss.item() - 0.5 * ((a - f).double() ** 2).sum().item() / denom) < 1e-6 * loss.item()
