@@ -80,6 +80,7 @@ struct ConvParams {
   int halo;        // rows in front of the tile in shift mode (Wp+1 for 3x3, 0 for 1x1)
   int a_box_rows, a_pieces;
   int a_stages, b_stages;
+  int pair;        // 1: launched as clusters of two CTAs sharing cta_group::2 MMAs (M = 256)
   int n_mma;       // MMA-issuing warps (2 in burst mode with >= 2 blocks per tile)
   int b_resident;  // 1: all weight tiles of the layer stay in shared memory for the whole kernel
   int epi_tma;     // 1: epilogue stages 128-row x panel_ch panels in shared memory and moves them with TMA

@@ -205,7 +205,7 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, const EpiPar
 //         kEpiNchw   - fp32 NCHW store of the heatmap head
 // Code size matters here: ten warps run four different roles out of one instruction cache, so everything that
 // does not have to be unrolled is a rolled loop and every epilogue path exists exactly once per kernel.
-template <int MB, int KSTEPS, int TAPS, int EPI>
+template <int MB, int KSTEPS, int TAPS, int EPI, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle-128B atoms (8 rows x 128 B) must start on their natural boundary.
@@ -224,11 +224,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t acc_cols = (uint32_t)(MB * p.nt);
   // weights resident + (shifted-descriptor taps or 1x1): the whole K loop of a chunk is one straight MMA burst
   const bool burst = p.b_resident && (p.a_shift || TAPS == 1);
+  // PAIR: two CTAs (one cluster) share every tcgen05.mma: cta_group::2, M = 256 = 128 rows of each CTA, each CTA
+  // holds half of the weight rows.  The leader issues for both, which halves the per-SM instruction issue load
+  // (the bottleneck for N <= 64) and the weight bytes each CTA keeps resident.  Only used in burst mode.
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const long long tile0 = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long tstride = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  auto mtile = [&](long long t) { return PAIR ? 2 * (t / p.n_ntiles) + cta_rank : t / p.n_ntiles; };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&ctl->a_full[i], 1); mbar_init(&ctl->a_empty[i], p.n_mma); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], p.n_mma); mbar_init(&ctl->acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], p.n_mma); mbar_init(&ctl->acc_empty[i], PAIR ? 16 : 8); }
     for (int i = 0; i < 4; ++i) { mbar_init(&ctl->res_full[i], 1); mbar_init(&ctl->epi_free[i], 1); mbar_init(&ctl->epi_done[i], 8); }
     fence_mbar_init();
     tma_prefetch_desc(&p.tmA);
@@ -236,11 +244,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (p.epi_tma) { tma_prefetch_desc(&p.tmO); if (p.residual) tma_prefetch_desc(&p.tmR); }
   }
   for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) sbias[i] = p.bias[i];
-  if (warp == 1) tmem_alloc(&ctl->tmem_base, p.tmem_cols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(&ctl->tmem_base, p.tmem_cols); else tmem_alloc(&ctl->tmem_base, p.tmem_cols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  if (PAIR && p.b_resident) {
+    // resident weights, this CTA's half of the output-channel rows of every (n-tile, chunk, tap) tile
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&ctl->b_full[0], p.b_resident_bytes);
+      uint32_t dst = b_base;
+      for (int nti = 0; nti < p.n_ntiles; ++nti)
+        for (int chunk = 0; chunk < p.n_chunks; ++chunk)
+          for (int tap = 0; tap < TAPS; ++tap, dst += p.b_stage_bytes)
+            tma_load_3d_s(dst, &p.tmB, &ctl->b_full[0], chunk * p.ck, nti * p.nt + (int)cta_rank * (p.nt / 2), tap);
+    }
+    mbar_wait(&ctl->b_full[0], 0);
+    cluster_sync();  // both halves are in place before the leader's first MMA reads them
+  }
 
 #ifdef STL_CONV_COUNTERS
   long long dbg[4] = {0, 0, 0, 0};
@@ -260,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ------------------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
     uint32_t a_it = 0, b_it = 0;
     DBG_TICK();
-    if (p.b_resident && elect_one()) {
+    if (!PAIR && p.b_resident && elect_one()) {  // (PAIR: done before the role split)
       mbar_expect_tx(&ctl->b_full[0], p.b_resident_bytes);
       uint32_t dst = b_base;
       for (int nti = 0; nti < p.n_ntiles; ++nti)
@@ -270,9 +293,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     __syncwarp();
 #pragma unroll 1
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (long long tile = tile0; tile < p.total_tiles; tile += tstride) {
       const int nti = (int)(tile % p.n_ntiles);
-      const long long mt = tile / p.n_ntiles;
+      const long long mt = mtile(tile);
       int q0 = 0, wo0 = 0, ho0 = 0, n0 = 0;
       if (kFlatOnly || p.mode == 0) {
         q0 = (int)(mt * (128 * MB));
@@ -291,13 +314,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_wait(&ctl->a_empty[s], ph ^ 1);
             DBG_TOCK(0);
             if (elect_one()) {
-              mbar_expect_tx(&ctl->a_full[s], p.a_tx_bytes);
+              // PAIR: both CTAs' tiles complete on the leader's barrier, which expects the bytes of both
+              if (!PAIR) mbar_expect_tx(&ctl->a_full[s], p.a_tx_bytes);
+              else if (is_leader) mbar_expect_tx(&ctl->a_full[s], 2u * p.a_tx_bytes);
               const uint32_t dst = a_base + s * p.a_stage_bytes;
               if (kFlatOnly || p.mode == 0) {
                 const int row0 = p.a_shift ? q0 - p.halo : q0 + (kh - 1) * p.in_Wp + (kw - 1);
-                for (int i = 0; i < p.a_pieces; ++i)
-                  tma_load_2d_s(dst + (uint32_t)(i * p.a_box_rows) * kSpan, &p.tmA, &ctl->a_full[s], chunk * p.ck,
-                              row0 + i * p.a_box_rows);
+                for (int i = 0; i < p.a_pieces; ++i) {
+                  if (PAIR)
+                    tma_load_2d_pair(dst + (uint32_t)(i * p.a_box_rows) * kSpan, &p.tmA, &ctl->a_full[s], chunk * p.ck,
+                                     row0 + i * p.a_box_rows);
+                  else
+                    tma_load_2d_s(dst + (uint32_t)(i * p.a_box_rows) * kSpan, &p.tmA, &ctl->a_full[s], chunk * p.ck,
+                                  row0 + i * p.a_box_rows);
+                }
               } else {
                 tma_load_4d_s(dst, &p.tmA, &ctl->a_full[s], chunk * p.ck, 2 * wo0 + kw - 1, 2 * ho0 + kh - 1, n0);
               }
@@ -311,8 +341,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_wait(&ctl->b_empty[s], ph ^ 1);
             DBG_TOCK(1);
             if (elect_one()) {
-              mbar_expect_tx(&ctl->b_full[s], p.b_tx_bytes);
-              tma_load_3d_s(b_base + s * p.b_stage_bytes, &p.tmB, &ctl->b_full[s], chunk * p.ck, nti * p.nt, tap);
+              if (PAIR) {  // each CTA streams its half of the weight rows; both halves complete on the leader's barrier
+                if (is_leader) mbar_expect_tx(&ctl->b_full[s], 2u * p.b_tx_bytes);
+                tma_load_3d_pair(b_base + s * p.b_stage_bytes, &p.tmB, &ctl->b_full[s], chunk * p.ck,
+                                 nti * p.nt + (int)cta_rank * (p.nt / 2), tap);
+              } else {
+                mbar_expect_tx(&ctl->b_full[s], p.b_tx_bytes);
+                tma_load_3d_s(b_base + s * p.b_stage_bytes, &p.tmB, &ctl->b_full[s], chunk * p.ck, nti * p.nt, tap);
+              }
             }
             __syncwarp();
             ++b_it;
@@ -330,9 +366,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int part = warp == 20 ? 1 : 0;
     const int m_split = p.n_mma == 2 ? (MB + 1) / 2 : MB;
     const int m_lo = part == 0 ? 0 : m_split, m_hi = part == 0 ? m_split : MB;
-    if (part == 1 && p.n_mma != 2) goto role_done;
+    if ((part == 1 && p.n_mma != 2) || (PAIR && !is_leader)) goto role_done;
     {
-    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.nt);
+    const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, (uint32_t)p.nt);
     const uint64_t desc_hi = make_kmajor_desc(0, kSpan) & 0xFFFFFFFF00000000ull;
     const uint32_t desc_lo_flags = (uint32_t)(make_kmajor_desc(0, kSpan) & 0xFFFFFFFFull);
     // descriptors differ only in the 14-bit start-address field (16-byte units) of the low word
@@ -343,12 +379,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t nt = (uint32_t)p.nt;
     uint32_t a_it = 0, b_it = 0, acc_it = 0;
     DBG_TICK();
-    if (p.b_resident) {
+    if (!PAIR && p.b_resident) {
       mbar_wait(&ctl->b_full[0], 0);
       DBG_TOCK(2);
     }
 #pragma unroll 1
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (long long tile = tile0; tile < p.total_tiles; tile += tstride) {
       const uint32_t nti = (uint32_t)(tile % p.n_ntiles);
       const uint32_t buf = acc_it % p.n_accbuf, aph = (acc_it / p.n_accbuf) & 1;
       mbar_wait(&ctl->acc_empty[buf], aph ^ 1);
@@ -376,11 +412,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                   if (m < m_lo || m >= m_hi) continue;
                   const uint64_t da = desc_hi | (uint64_t)(a_lo + (uint32_t)((m * 128 * (int)kSpan + k * 32) >> 4));
                   const uint64_t db = desc_hi | (uint64_t)(b_lo + (uint32_t)((k * 32) >> 4));
-                  umma_bf16(d_base + (uint32_t)m * nt, da, db, idesc, (tap | k) != 0 ? 1u : (uint32_t)chunk);
+                  if (PAIR) umma_bf16_pair(d_base + (uint32_t)m * nt, da, db, idesc, (tap | k) != 0 ? 1u : (uint32_t)chunk);
+                  else umma_bf16(d_base + (uint32_t)m * nt, da, db, idesc, (tap | k) != 0 ? 1u : (uint32_t)chunk);
                 }
               }
             }
-            umma_commit(&ctl->a_empty[a_stage]);
+            if (PAIR) umma_commit_pair(&ctl->a_empty[a_stage]); else umma_commit(&ctl->a_empty[a_stage]);
           }
           __syncwarp();
           ++a_it;
@@ -419,11 +456,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 for (int m = 0; m < MB; ++m) {
                   const uint64_t da = desc_hi | (uint64_t)(a_lo + (uint32_t)((m * 128 * (int)kSpan + k * 32) >> 4));
                   const uint64_t db = desc_hi | (uint64_t)(b_lo + (uint32_t)((k * 32) >> 4));
-                  umma_bf16(d_base + (uint32_t)m * nt, da, db, idesc, first | (uint32_t)k);
+                  if (PAIR) umma_bf16_pair(d_base + (uint32_t)m * nt, da, db, idesc, first | (uint32_t)k);
+                  else umma_bf16(d_base + (uint32_t)m * nt, da, db, idesc, first | (uint32_t)k);
                 }
               }
-              if (!p.b_resident) umma_commit(&ctl->b_empty[bs]);
-              if (release_a) umma_commit(&ctl->a_empty[a_stage]);
+              if (PAIR) {
+                if (!p.b_resident) umma_commit_pair(&ctl->b_empty[bs]);
+                if (release_a) umma_commit_pair(&ctl->a_empty[a_stage]);
+              } else {
+                if (!p.b_resident) umma_commit(&ctl->b_empty[bs]);
+                if (release_a) umma_commit(&ctl->a_empty[a_stage]);
+              }
             }
             __syncwarp();
             if (!p.b_resident) ++b_it;
@@ -434,7 +477,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         }
       }
-      if (elect_one()) umma_commit(&ctl->acc_full[buf]);
+      if (elect_one()) {
+        if (PAIR) umma_commit_pair(&ctl->acc_full[buf]); else umma_commit(&ctl->acc_full[buf]);
+      }
       __syncwarp();
       ++acc_it;
     }
@@ -452,14 +497,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t stage0 = a_base + p.epi_base_off + (uint32_t)group * 2u * (uint32_t)bp * panel_bytes;
       const bool has_res = p.residual != nullptr;
       const long long total_tiles = p.total_tiles;
-      const long long tile_step = (long long)gridDim.x * (p.n_accbuf == 2 ? 2 : 1);
-      const long long first_tile = (long long)blockIdx.x + (p.n_accbuf == 2 ? (long long)group * gridDim.x : 0);
+      const long long tile_step = tstride * (p.n_accbuf == 2 ? 2 : 1);
+      const long long first_tile = tile0 + (p.n_accbuf == 2 ? (long long)group * tstride : 0);
       const int skip = p.dbg_skip_epilogue;
       if (lane == 0) {
         // residual of batch (tile, b0) -> staging buffer sb
         auto load_res = [&](long long t, int b0, uint32_t sb) {
           const int nti_ = (int)(t % n_ntiles);
-          const int q0 = (int)((t / n_ntiles) * (128 * MB));
+          const int q0 = (int)(mtile(t) * (128 * MB));
           const int cnt = PT - b0 < bp ? PT - b0 : bp;
           uint64_t* bar = &ctl->res_full[group * 2 + sb];
           mbar_expect_tx(bar, (uint32_t)cnt * 128u * pitch);
@@ -474,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll 1
         for (long long tile = first_tile; tile < total_tiles; tile += tile_step) {
           const int nti = (int)(tile % n_ntiles);
-          const int q0 = (int)((tile / n_ntiles) * (128 * MB));
+          const int q0 = (int)(mtile(tile) * (128 * MB));
 #pragma unroll 1
           for (int b0 = 0; b0 < PT; b0 += bp, ++kb) {
             const uint32_t sb = kb & 1;
@@ -536,8 +581,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t pitch = (uint32_t)panel_ch * 2u, swz = (uint32_t)p.panel_swz;
       const uint32_t panel_bytes = p.epi_panel_bytes;
       const uint32_t stage0 = a_base + p.epi_base_off + (uint32_t)group * 2u * (uint32_t)bp * panel_bytes;
-      const long long tile_step = (long long)gridDim.x * (n_accbuf == 2 ? 2 : 1);
-      const long long first_tile = (long long)blockIdx.x + (n_accbuf == 2 ? (long long)group * gridDim.x : 0);
+      const long long tile_step = tstride * (n_accbuf == 2 ? 2 : 1);
+      const long long first_tile = tile0 + (n_accbuf == 2 ? (long long)group * tstride : 0);
       const bool active = n_accbuf == 2 || group == 0;
       const int upp = (spp - sub + 1) >> 1;  // 16-channel units of one panel handled by this warp
       const uint32_t xr = swz == 128 ? (uint32_t)(row0 & 7) : (swz == 64 ? (uint32_t)((row0 >> 1) & 3) : 0u);
@@ -546,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll 1
       for (long long tile = first_tile; active && tile < total_tiles; tile += tile_step, acc_it += (n_accbuf == 2 ? 2 : 1)) {
         const int nti = (int)(tile % n_ntiles);
-        const long long mt = tile / n_ntiles;
+        const long long mt = mtile(tile);
         const uint32_t buf = n_accbuf == 2 ? (uint32_t)group : 0u;
         const uint32_t aph = (acc_it / n_accbuf) & 1;
         const int chbase = nti * nt;
@@ -622,7 +667,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (b0 + bp >= PT) {  // accumulator fully drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_cluster(map_to_cta(smem_u32(&ctl->acc_empty[buf]), 0));  // leader's barrier
+              else mbar_arrive(&ctl->acc_empty[buf]);
+            }
           }
           DBG_TOCK(1);
           fence_async_smem();
@@ -690,10 +738,10 @@ role_done:
 #undef DBG_DUMP
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync(); else __syncthreads();  // PAIR: neither CTA may retire while the other can still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -845,22 +893,12 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     cuuint32_t es[4] = {1, 2, 2, 1};
     if (encode(&p.tmA, s.in, 4, dims, strides, box, es, span)) return 1;
   }
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)gi.C, (cuuint64_t)s.cout_pad, (cuuint64_t)p.taps};
-    cuuint64_t strides[2] = {(cuuint64_t)gi.C * 2, (cuuint64_t)gi.C * 2 * s.cout_pad};
-    cuuint32_t box[3] = {(cuuint32_t)p.ck, (cuuint32_t)p.nt, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    if (encode(&p.tmB, s.weights, 3, dims, strides, box, es, span)) return 1;
-  }
-
   p.fd_Wp.init((uint32_t)p.Wp);
   p.fd_Hp.init((uint32_t)p.Hp);
   p.fd_bw.init((uint32_t)(p.bw > 0 ? p.bw : 1));
   p.fd_bh.init((uint32_t)(p.bh > 0 ? p.bh : 1));
   p.a_tx_bytes = (uint32_t)p.a_pieces * p.a_box_rows * span;
   p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
-  p.b_tx_bytes = (uint32_t)p.nt * span;
-  p.b_stage_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
   p.n_accbuf = (2 * p.mb * p.nt <= 512) ? 2 : 1;
   uint32_t cols = 32;
   while (cols < (uint32_t)(p.n_accbuf * p.mb * p.nt)) cols <<= 1;
@@ -884,7 +922,36 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   }
   const size_t epi_bytes = p.epi_tma ? (size_t)2 * 2 * p.epi_batch * p.epi_panel_bytes : 0;
   const size_t budget = kMaxSmem - kCtlBytes - 1024 - epi_bytes;
-  const size_t resident = (size_t)p.n_ntiles * p.n_chunks * p.taps * p.b_stage_bytes;
+  // CTA pairs (cta_group::2): flat mode, staged epilogue, burst-capable; each CTA then keeps half of the weight rows
+  // Measured on B200: for layers whose weights stay resident (N <= 64, every 1x1) pairs are slower - the MMA rate is
+  // bound by the A-operand fetch (128 rows x 32 B per SM per instruction), which pairing does not reduce.  For
+  // layers that stream their weights (C >= 128) each CTA of a pair streams only half of the rows: half the L2 traffic.
+  const bool pair_ok = p.mode == 0 && p.epi_tma && p.nt % 32 == 0 && !s.max_ctas && !getenv("STL_DBG_NO_PAIR");
+  size_t resident = 0;
+  p.pair = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    p.b_tx_bytes = (uint32_t)(p.pair ? p.nt / 2 : p.nt) * span;
+    p.b_stage_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
+    resident = (size_t)p.n_ntiles * p.n_chunks * p.taps * p.b_stage_bytes;
+    const bool fits = resident <= 120 * 1024 && resident + 2 * (size_t)p.a_stage_bytes <= budget &&
+                      !getenv("STL_DBG_NO_RESIDENT");
+    if (fits || !pair_ok || p.pair || (getenv("STL_DBG_PAIR_ALL") == nullptr && resident <= 120 * 1024)) break;
+    p.pair = 1;  // weights must stream: share every weight tile between the two CTAs of a pair
+  }
+  if (getenv("STL_DBG_PAIR_ALL") && pair_ok && !p.pair) {
+    p.pair = 1;
+    p.b_tx_bytes = (uint32_t)(p.nt / 2) * span;
+    p.b_stage_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
+    resident = (size_t)p.n_ntiles * p.n_chunks * p.taps * p.b_stage_bytes;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)gi.C, (cuuint64_t)s.cout_pad, (cuuint64_t)p.taps};
+    cuuint64_t strides[2] = {(cuuint64_t)gi.C * 2, (cuuint64_t)gi.C * 2 * s.cout_pad};
+    cuuint32_t box[3] = {(cuuint32_t)p.ck, (cuuint32_t)(p.pair ? p.nt / 2 : p.nt), 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    if (encode(&p.tmB, s.weights, 3, dims, strides, box, es, span)) return 1;
+  }
+  if (p.pair) p.total_tiles = (((p.P + 128 * p.mb - 1) / (128 * p.mb) + 1) / 2) * p.n_ntiles;
   const int a_loads_per_tile = p.n_chunks * (p.a_shift || p.taps == 1 ? 1 : p.taps);
   const int a_want = a_loads_per_tile >= 4 ? 4 : (p.a_shift ? 3 : 4);
   int a_st = 2, b_st = 2;
@@ -939,6 +1006,10 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
 
   long long g = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   if (s.max_ctas > 0 && g > s.max_ctas) g = s.max_ctas;
+  if (p.pair) {  // one cluster of two CTAs per tile pair
+    const long long pairs = p.total_tiles < num_sms() / 2 ? p.total_tiles : num_sms() / 2;
+    g = 2 * pairs;
+  }
   *grid = (int)g;
 
   // a smaller tile can make the difference between streaming the weights for every tile and keeping them resident
@@ -963,25 +1034,28 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
 namespace {
 typedef void (*ConvKernel)(const ConvParams);
 template <int MB, int KSTEPS>
-ConvKernel pick_variant(int taps, int epi) {
-  if (epi == kEpiNchw) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiNchw> : nullptr;
-  if (epi == kEpiStaged) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiStaged> : conv_tc_kernel<MB, KSTEPS, 9, kEpiStaged>;
-  return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiDirect> : conv_tc_kernel<MB, KSTEPS, 9, kEpiDirect>;
+ConvKernel pick_variant(int taps, int epi, bool pair) {
+  if (epi == kEpiNchw) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiNchw, false> : nullptr;
+  if (epi == kEpiStaged) {
+    if (pair) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiStaged, true> : conv_tc_kernel<MB, KSTEPS, 9, kEpiStaged, true>;
+    return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiStaged, false> : conv_tc_kernel<MB, KSTEPS, 9, kEpiStaged, false>;
+  }
+  return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiDirect, false> : conv_tc_kernel<MB, KSTEPS, 9, kEpiDirect, false>;
 }
 template <int MB>
-ConvKernel pick_ksteps(int ksteps, int taps, int epi) {
+ConvKernel pick_ksteps(int ksteps, int taps, int epi, bool pair) {
   switch (ksteps) {
-    case 1: return pick_variant<MB, 1>(taps, epi);
-    case 2: return pick_variant<MB, 2>(taps, epi);
-    case 4: return pick_variant<MB, 4>(taps, epi);
+    case 1: return pick_variant<MB, 1>(taps, epi, pair);
+    case 2: return pick_variant<MB, 2>(taps, epi, pair);
+    case 4: return pick_variant<MB, 4>(taps, epi, pair);
   }
   return nullptr;
 }
-ConvKernel pick_kernel(int mb, int ksteps, int taps, int epi) {
+ConvKernel pick_kernel(int mb, int ksteps, int taps, int epi, bool pair) {
   switch (mb) {
-    case 1: return pick_ksteps<1>(ksteps, taps, epi);
-    case 2: return pick_ksteps<2>(ksteps, taps, epi);
-    case 3: return pick_ksteps<3>(ksteps, taps, epi);
+    case 1: return pick_ksteps<1>(ksteps, taps, epi, pair);
+    case 2: return pick_ksteps<2>(ksteps, taps, epi, pair);
+    case 3: return pick_ksteps<3>(ksteps, taps, epi, pair);
   }
   return nullptr;
 }
@@ -994,19 +1068,39 @@ int conv_launch_prepared(const ConvParams& p, int grid, size_t smem_bytes, cudaS
     for (int mb = 1; mb <= 3; ++mb)
       for (int ks = 1; ks <= 4; ks *= 2)
         for (int epi = 0; epi < 3; ++epi)
-          for (int taps = 1; taps <= 9; taps += 8) {
-            ConvKernel k = pick_kernel(mb, ks, taps, epi);
-            if (!k) continue;
-            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
-          }
+          for (int taps = 1; taps <= 9; taps += 8)
+            for (int pair = 0; pair < 2; ++pair) {
+              if (pair && epi != kEpiStaged) continue;
+              ConvKernel k = pick_kernel(mb, ks, taps, epi, pair != 0);
+              if (!k) continue;
+              cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+              if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+            }
     attr_set = true;
   }
   if (grid <= 0) return 0;
-  ConvKernel kern = pick_kernel(p.mb, p.ck / 16, p.taps, epi_kind(p));
+  ConvKernel kern = pick_kernel(p.mb, p.ck / 16, p.taps, epi_kind(p), p.pair != 0);
   if (!kern) { set_error("conv: no kernel for mb %d ck %d taps %d nchw %d", p.mb, p.ck, p.taps, p.out_nchw); return 1; }
-  kern<<<grid, kThreads, smem_bytes, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if (p.pair) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e != cudaSuccess) { set_error("conv_tc_kernel (pair) launch: %s", cudaGetErrorString(e)); return 1; }
+  } else {
+    kern<<<grid, kThreads, smem_bytes, stream>>>(p);
+  }
+  e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv_tc_kernel launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;
 }
