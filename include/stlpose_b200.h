@@ -140,8 +140,10 @@ size_t stl_plan_workspace_bytes(const stl_plan* plan, int n_images);
 int stl_plan_forward(stl_plan* plan, const float* x_nchw, int B, int flip_pair, float* heat_nchw,
                      const void* weight_arena, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Number of kernels one stl_plan_forward enqueues (for launch accounting). */
+/* Number of ops of the plan (size of the per-op timing array) and number of kernels one stl_plan_forward enqueues
+ * for the current binding (an op of a sub-batched group is launched once per sub-batch). */
 int stl_plan_launches_per_forward(const stl_plan* plan);
+int stl_plan_kernel_launches(const stl_plan* plan);
 
 /* Measurement aid: same as stl_plan_forward, but brackets every launch with CUDA events on `stream`, waits for
  * the stream and writes the per-launch durations (ms) to op_ms_host[stl_plan_launches_per_forward()]. */
@@ -156,6 +158,7 @@ typedef struct stl_op_info {
   double flops_per_image;   /* 2*MACs */
   double bytes_per_image;   /* algorithmic: input + output (+ residual / upsampled addends) read or written once */
   int grid, smem, mb, nt, ck, a_stages, b_stages, a_shift, tiles;   /* launch shape (valid once the plan has run) */
+  int subs;                 /* sub-batches this op is launched in (L2-resident branch groups), 1 otherwise */
 } stl_op_info;
 int stl_plan_op_info(const stl_plan* plan, int op_index, stl_op_info* info);
 

@@ -45,7 +45,7 @@ class OpInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in ("kind", "layer", "cin", "cout", "ksize", "stride", "out_h", "out_w")] + \
                [("flops_per_image", ctypes.c_double), ("bytes_per_image", ctypes.c_double)] + \
                [(n, ctypes.c_int) for n in ("grid", "smem", "mb", "nt", "ck", "a_stages", "b_stages", "a_shift",
-                                            "tiles")]
+                                            "tiles", "subs")]
 
 
 # name -> (restype, argtypes); mirrors include/stlpose_b200.h one to one
@@ -74,6 +74,7 @@ PROTOTYPES = {
     "stl_plan_workspace_bytes": (ctypes.c_size_t, [vp, ctypes.c_int]),
     "stl_plan_forward": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_size_t, vp]),
     "stl_plan_launches_per_forward": (ctypes.c_int, [vp]),
+    "stl_plan_kernel_launches": (ctypes.c_int, [vp]),
     "stl_plan_forward_timed": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_size_t, vp,
                                               c_float_p]),
     "stl_plan_op_info": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(OpInfo)]),

@@ -182,6 +182,10 @@ int stl_plan_forward(stl_plan* plan, const float* x, int B, int flip_pair, float
 }
 
 int stl_plan_launches_per_forward(const stl_plan* plan) { return plan ? (int)plan->impl->ops.size() : 0; }
+int stl_plan_kernel_launches(const stl_plan* plan) {
+  if (!plan) return 0;
+  return plan->impl->bound ? (int)plan->impl->launches.size() : (int)plan->impl->ops.size();
+}
 
 int stl_plan_forward_timed(stl_plan* plan, const float* x, int B, int flip_pair, float* heat, const void* arena,
                            void* workspace, size_t ws_bytes, void* stream, float* op_ms_host) {

@@ -45,6 +45,7 @@ struct ConvSpec {
   int force_tap_reload = 0;                // 1: one aligned TMA load per filter tap instead of shifted descriptors
   int force_mb = 0;
   int max_ctas = 0;
+  int img_lo = 0, img_hi = 0;              // stride-1 convs only: restrict the launch to images [img_lo, img_hi) (0,0 = all)
   void* dbg_counters = nullptr;            // optional [grid][3][4] int64 cycle counters (measurement aid)
 };
 
@@ -96,7 +97,8 @@ struct ConvParams {
   // input / output geometry
   int in_Wp;
   int N, H, W, Hp, Wp;   // OUTPUT geometry
-  long long P;           // output padded pixel count
+  long long P;           // output padded pixel count (end of the processed image range)
+  int q_lo;              // first padded pixel of the processed image range (flat mode)
   FastDiv fd_Wp, fd_Hp, fd_bw, fd_bh;  // exact dividers for the epilogue's row -> (n, h, w) decode
   int bw, bh, bn, tiles_w, tiles_h, tiles_n;  // structured tiles (mode 1)
   // epilogue

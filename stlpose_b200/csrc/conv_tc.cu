@@ -39,7 +39,7 @@ constexpr size_t kMaxSmem = 227 * 1024;
 struct Ctl {
   uint64_t a_full[kMaxStages], a_empty[kMaxStages];
   uint64_t b_full[kMaxStages], b_empty[kMaxStages];
-  uint64_t acc_full[2], acc_empty[2];
+  uint64_t acc_full[4], acc_empty[4];
   uint64_t res_full[4], epi_free[4], epi_done[4];  // [epilogue group][staging buffer]
   uint32_t tmem_base;
 };
@@ -80,7 +80,7 @@ struct RowPos {
 __device__ __forceinline__ RowPos row_position(const ConvParams& p, long long mt, int r) {
   RowPos pos;
   if (p.mode == 0) {
-    const long long q = mt * (128 * p.mb) + r;
+    const long long q = p.q_lo + mt * (128 * p.mb) + r;
     pos.valid = q < p.P;
     pos.q = (int)q;
     const uint32_t t = p.fd_Wp.div((uint32_t)pos.q);
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&ctl->a_full[i], 1); mbar_init(&ctl->a_empty[i], p.n_mma); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], p.n_mma); mbar_init(&ctl->acc_empty[i], PAIR ? 16 : 8); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&ctl->acc_full[i], p.n_mma); mbar_init(&ctl->acc_empty[i], PAIR ? 16 : 8); }
     for (int i = 0; i < 4; ++i) { mbar_init(&ctl->res_full[i], 1); mbar_init(&ctl->epi_free[i], 1); mbar_init(&ctl->epi_done[i], 8); }
     fence_mbar_init();
     tma_prefetch_desc(&p.tmA);
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const long long mt = mtile(tile);
       int q0 = 0, wo0 = 0, ho0 = 0, n0 = 0;
       if (kFlatOnly || p.mode == 0) {
-        q0 = (int)(mt * (128 * MB));
+        q0 = p.q_lo + (int)(mt * (128 * MB));
       } else {
         wo0 = (int)(mt % p.tiles_w) * p.bw;
         ho0 = (int)((mt / p.tiles_w) % p.tiles_h) * p.bh;
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ------------------------------------------------------------------ epilogue DMA warp of one group: moves staged
     // panels between shared and global memory with TMA so that the 8 compute warps never wait on an issue slot
     const int group = warp - 18;
-    if (EPI == kEpiStaged && (p.n_accbuf == 2 || group == 0)) {
+    if (EPI == kEpiStaged && (p.n_accbuf >= 2 || group == 0)) {
       const int nt = p.nt, n_ntiles = p.n_ntiles;
       const int panel_ch = p.panel_ch, npanels = nt / panel_ch;
       const int PT = MB * npanels, bp = p.epi_batch;
@@ -497,14 +497,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t stage0 = a_base + p.epi_base_off + (uint32_t)group * 2u * (uint32_t)bp * panel_bytes;
       const bool has_res = p.residual != nullptr;
       const long long total_tiles = p.total_tiles;
-      const long long tile_step = tstride * (p.n_accbuf == 2 ? 2 : 1);
-      const long long first_tile = tile0 + (p.n_accbuf == 2 ? (long long)group * tstride : 0);
+      const long long tile_step = tstride * (p.n_accbuf >= 2 ? 2 : 1);
+      const long long first_tile = tile0 + (p.n_accbuf >= 2 ? (long long)group * tstride : 0);
       const int skip = p.dbg_skip_epilogue;
       if (lane == 0) {
         // residual of batch (tile, b0) -> staging buffer sb
         auto load_res = [&](long long t, int b0, uint32_t sb) {
           const int nti_ = (int)(t % n_ntiles);
-          const int q0 = (int)(mtile(t) * (128 * MB));
+          const int q0 = p.q_lo + (int)(mtile(t) * (128 * MB));
           const int cnt = PT - b0 < bp ? PT - b0 : bp;
           uint64_t* bar = &ctl->res_full[group * 2 + sb];
           mbar_expect_tx(bar, (uint32_t)cnt * 128u * pitch);
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll 1
         for (long long tile = first_tile; tile < total_tiles; tile += tile_step) {
           const int nti = (int)(tile % n_ntiles);
-          const int q0 = (int)(mtile(tile) * (128 * MB));
+          const int q0 = p.q_lo + (int)(mtile(tile) * (128 * MB));
 #pragma unroll 1
           for (int b0 = 0; b0 < PT; b0 += bp, ++kb) {
             const uint32_t sb = kb & 1;
@@ -581,18 +581,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t pitch = (uint32_t)panel_ch * 2u, swz = (uint32_t)p.panel_swz;
       const uint32_t panel_bytes = p.epi_panel_bytes;
       const uint32_t stage0 = a_base + p.epi_base_off + (uint32_t)group * 2u * (uint32_t)bp * panel_bytes;
-      const long long tile_step = tstride * (n_accbuf == 2 ? 2 : 1);
-      const long long first_tile = tile0 + (n_accbuf == 2 ? (long long)group * tstride : 0);
-      const bool active = n_accbuf == 2 || group == 0;
+      const long long tile_step = tstride * (n_accbuf >= 2 ? 2 : 1);
+      const long long first_tile = tile0 + (n_accbuf >= 2 ? (long long)group * tstride : 0);
+      const bool active = n_accbuf >= 2 || group == 0;
       const int upp = (spp - sub + 1) >> 1;  // 16-channel units of one panel handled by this warp
       const uint32_t xr = swz == 128 ? (uint32_t)(row0 & 7) : (swz == 64 ? (uint32_t)((row0 >> 1) & 3) : 0u);
       uint32_t kb = 0;  // batches processed by this group
-      acc_it = n_accbuf == 2 ? (uint32_t)group : 0u;
+      acc_it = n_accbuf >= 2 ? (uint32_t)group : 0u;
 #pragma unroll 1
-      for (long long tile = first_tile; active && tile < total_tiles; tile += tile_step, acc_it += (n_accbuf == 2 ? 2 : 1)) {
+      for (long long tile = first_tile; active && tile < total_tiles; tile += tile_step, acc_it += (n_accbuf >= 2 ? 2 : 1)) {
         const int nti = (int)(tile % n_ntiles);
         const long long mt = mtile(tile);
-        const uint32_t buf = n_accbuf == 2 ? (uint32_t)group : 0u;
+        const uint32_t buf = acc_it % (uint32_t)n_accbuf;
         const uint32_t aph = (acc_it / n_accbuf) & 1;
         const int chbase = nti * nt;
         const uint32_t t_tile = tmem_base + buf * acc_cols + ((uint32_t)(quarter * 32) << 16);
@@ -682,10 +682,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     } else
 #pragma unroll 1
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
-      if (n_accbuf == 2 ? (int)(acc_it & 1) != group : group != 0) continue;
+      if (n_accbuf >= 2 ? (int)(acc_it & 1) != group : group != 0) continue;
       const int nti = (int)(tile % n_ntiles);
       const long long mt = tile / n_ntiles;
-      const uint32_t buf = n_accbuf == 2 ? (uint32_t)group : 0u;
+      const uint32_t buf = acc_it % (uint32_t)n_accbuf;
       const uint32_t aph = (acc_it / n_accbuf) & 1;
       const int chbase = nti * nt;
       RowPos pos = row_position(p, mt, row0);
@@ -836,6 +836,16 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   p.Hp = p.H + 1;
   p.Wp = p.W + 1;
   p.P = (long long)p.N * p.Hp * p.Wp;
+  p.q_lo = 0;
+  if (s.img_hi > 0) {  // only images [img_lo, img_hi): the tiles start at the first image's row and the kernel's notion
+                       // of "end of tensor" (P, and the bounds of the output / residual tensor maps) is the range end
+    if (s.img_lo < 0 || s.img_hi > gi.N || s.img_lo >= s.img_hi || (p.mode != 0 && (s.img_lo != 0 || s.img_hi != gi.N))) {
+      set_error("conv: bad image range [%d,%d) of %d (sub-ranges need a stride-1 conv)", s.img_lo, s.img_hi, gi.N);
+      return 1;
+    }
+    p.q_lo = s.img_lo * p.Hp * p.Wp;
+    p.P = (long long)s.img_hi * p.Hp * p.Wp;
+  }
   if ((long long)gi.pixels() >= (1ll << 31) || p.P >= (1ll << 31)) { set_error("conv: tensor too large"); return 1; }
 
   // accumulator blocks per tile: keep two accumulator buffers in 512 TMEM columns when possible
@@ -844,7 +854,7 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   while (mb > 1 && mb * p.nt > 256) --mb;
   if (p.mode == 0) {
     // do not make tiles larger than the problem
-    while (mb > 1 && (long long)(mb - 1) * 128 >= p.P) --mb;
+    while (mb > 1 && (long long)(mb - 1) * 128 >= p.P - p.q_lo) --mb;
   }
 
   if (p.mode == 0) {
@@ -854,7 +864,7 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     const int rows_needed = 128 * mb + 2 * p.halo;
     p.a_pieces = (rows_needed + 255) / 256;
     p.a_box_rows = (((rows_needed + p.a_pieces - 1) / p.a_pieces) + 7) & ~7;
-    p.total_tiles = ((p.P + 128 * mb - 1) / (128 * mb)) * p.n_ntiles;
+    p.total_tiles = ((p.P - p.q_lo + 128 * mb - 1) / (128 * mb)) * p.n_ntiles;
     cuuint64_t dims[2] = {(cuuint64_t)gi.C, (cuuint64_t)gi.pixels()};
     cuuint64_t strides[1] = {(cuuint64_t)gi.C * 2};
     cuuint32_t box[2] = {(cuuint32_t)p.ck, (cuuint32_t)p.a_box_rows};
@@ -899,7 +909,10 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   p.fd_bh.init((uint32_t)(p.bh > 0 ? p.bh : 1));
   p.a_tx_bytes = (uint32_t)p.a_pieces * p.a_box_rows * span;
   p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
-  p.n_accbuf = (2 * p.mb * p.nt <= 512) ? 2 : 1;
+  // accumulator buffers in the 512 TMEM columns: 2 (tile t+1 is multiplied while tile t drains), else 1.
+  // Four buffers (STL_DBG_ACC4) were measured on B200 and change nothing: the narrow layers are not limited by the
+  // TMEM hand-off but by operand fetch and HBM.
+  p.n_accbuf = (4 * p.mb * p.nt <= 512 && getenv("STL_DBG_ACC4")) ? 4 : ((2 * p.mb * p.nt <= 512) ? 2 : 1);
   uint32_t cols = 32;
   while (cols < (uint32_t)(p.n_accbuf * p.mb * p.nt)) cols <<= 1;
   p.tmem_cols = cols;
@@ -951,7 +964,7 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     cuuint32_t es[3] = {1, 1, 1};
     if (encode(&p.tmB, s.weights, 3, dims, strides, box, es, span)) return 1;
   }
-  if (p.pair) p.total_tiles = (((p.P + 128 * p.mb - 1) / (128 * p.mb) + 1) / 2) * p.n_ntiles;
+  if (p.pair) p.total_tiles = (((p.P - p.q_lo + 128 * p.mb - 1) / (128 * p.mb) + 1) / 2) * p.n_ntiles;
   const int a_loads_per_tile = p.n_chunks * (p.a_shift || p.taps == 1 ? 1 : p.taps);
   const int a_want = a_loads_per_tile >= 4 ? 4 : (p.a_shift ? 3 : 4);
   int a_st = 2, b_st = 2;

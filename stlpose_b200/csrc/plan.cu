@@ -5,6 +5,7 @@
 // activation buffers; BatchNorm is folded into the packed weights, ReLU / residual / fuse-layer additions live in
 // the convolution epilogues.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -150,6 +151,10 @@ struct Plan::Builder {
         const std::string mp = k1;
         // branches: `blocks` BasicBlocks each (HRnet.py:32-61, 252-253)
         for (int b = 0; b < nb; ++b) {
+          // the 2 x blocks convs of a branch form a group: executed sub-batch by sub-batch so that the three
+          // activation buffers they cycle through stay resident in L2 (bind() picks the sub-batch size)
+          Plan::Group grp;
+          grp.first = (int)P.ops.size();
           for (int k = 0; k < c.blocks; ++k) {
             snprintf(k1, sizeof k1, "%s.branches.%d.%d", mp.c_str(), b, k);
             const std::string bp = k1;
@@ -161,6 +166,9 @@ struct Plan::Builder {
             release(xs[b]);
             xs[b] = o;
           }
+          grp.count = (int)P.ops.size() - grp.first;
+          for (int i = 0; i < grp.count; ++i) P.ops[grp.first + i].group = (int)P.groups.size();
+          P.groups.push_back(grp);
         }
         // fuse layers (HRnet.py:188-243, 255-264)
         std::vector<int> ys(n_out);
@@ -270,8 +278,28 @@ int Plan::bind(int n_images, const void* arena, void* workspace, size_t ws_bytes
   cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
   if (e != cudaSuccess) { set_error("plan: memset workspace: %s", cudaGetErrorString(e)); return 1; }
 
+  // sub-batch count of every group: keep one activation tensor of the group near `sub_bytes` so that the input,
+  // intermediate and output buffers of a branch (3 tensors) fit in the 126 MB L2 together
+  // Measured on B200 (round 1): with one launch per layer the fixed cost of a launch (pipeline fill, TMEM/barrier
+  // set-up, weight load: ~8 us) outweighs the L2 hits for every sub-batch size tried (14/28/56 MB: 35.2/34.5/33.4 ms
+  // per step vs 32.3 ms unsplit), so the default is off; the mechanism stays for the multi-layer kernels to come.
+  size_t sub_bytes = 0;
+  if (const char* e = getenv("STLPOSE_SUB_MB")) { long v = atol(e); sub_bytes = v > 0 ? (size_t)v << 20 : 0; }
+  std::vector<int> group_subs(groups.size(), 1);
+  for (size_t g = 0; g < groups.size(); ++g) {
+    const Slot& so = slots[ops[groups[g].first].out];
+    const size_t tensor = PaddedGeom{n_images, so.H, so.W, so.C}.bytes();
+    int subs = sub_bytes ? (int)((tensor + sub_bytes / 2) / sub_bytes) : 1;
+    if (subs > 8) subs = 8;
+    // a sub-batch must still fill the machine a few times over: >= 4 tiles of 384 rows per SM
+    const long long rows = (long long)n_images * (so.H + 1) * (so.W + 1);
+    while (subs > 1 && rows / subs < 4ll * 148 * 384) --subs;
+    if (subs < 1) subs = 1;
+    if (subs > n_images) subs = n_images;
+    group_subs[g] = subs;
+  }
   const uint8_t* wbase = reinterpret_cast<const uint8_t*>(arena);
-  prepared.assign(ops.size(), Prepared());
+  prepared.assign(ops.size(), std::vector<Prepared>());
   for (size_t i = 0; i < ops.size(); ++i) {
     const Op& op = ops[i];
     if (op.kind != OP_CONV) continue;
@@ -296,8 +324,31 @@ int Plan::bind(int n_images, const void* arena, void* workspace, size_t ws_bytes
     s.relu = op.relu;
     s.out_nchw = op.out_nchw;
     s.force_tap_reload = tap_reload;
-    Prepared& pr = prepared[i];
-    if (conv_prepare(s, &pr.params, &pr.grid, &pr.smem)) return 1;
+    const int subs = op.group >= 0 ? group_subs[op.group] : 1;
+    prepared[i].resize(subs);
+    const int chunk = (n_images + subs - 1) / subs;
+    for (int sb = 0; sb < subs; ++sb) {
+      if (subs > 1) {
+        s.img_lo = sb * chunk;
+        s.img_hi = s.img_lo + chunk < n_images ? s.img_lo + chunk : n_images;
+      }
+      Prepared& pr = prepared[i][sb];
+      if (s.img_lo >= n_images && subs > 1) { pr.grid = 0; continue; }
+      if (conv_prepare(s, &pr.params, &pr.grid, &pr.smem)) return 1;
+    }
+  }
+  launches.clear();
+  for (size_t i = 0; i < ops.size();) {
+    const Op& op = ops[i];
+    if (op.group >= 0 && groups[op.group].first == (int)i) {
+      const Group& g = groups[op.group];
+      for (int sb = 0; sb < group_subs[op.group]; ++sb)
+        for (int j = 0; j < g.count; ++j) launches.push_back(Launch{g.first + j, sb});
+      i += g.count;
+    } else {
+      launches.push_back(Launch{(int)i, 0});
+      ++i;
+    }
   }
   bound = true;
   bound_images = n_images;
@@ -314,7 +365,7 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
   const uint8_t* wbase = reinterpret_cast<const uint8_t*>(arena);
   std::vector<cudaEvent_t> ev;
   if (op_ms_host) {
-    ev.resize(ops.size() + 1);
+    ev.resize(launches.size() + 1);
     for (auto& e : ev) cudaEventCreate(&e);
     cudaEventRecord(ev[0], st);
   }
@@ -322,7 +373,8 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
     std::vector<cudaEvent_t>& v;
     ~EvGuard() { for (auto e : v) cudaEventDestroy(e); }
   } guard{ev};
-  for (size_t i = 0; i < ops.size(); ++i) {
+  for (size_t li = 0; li < launches.size(); ++li) {
+    const int i = launches[li].op;
     const Op& op = ops[i];
     switch (op.kind) {
       case OP_STEM: {
@@ -332,7 +384,7 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
         break;
       }
       case OP_CONV: {
-        Prepared& pr = prepared[i];
+        Prepared& pr = prepared[i][launches[li].sub];
         if (op.out_nchw) pr.params.out = heat;
         if (conv_launch_prepared(pr.params, pr.grid, pr.smem, st)) return 1;
         break;
@@ -347,12 +399,17 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
         break;
       }
     }
-    if (op_ms_host) cudaEventRecord(ev[i + 1], st);
+    if (op_ms_host) cudaEventRecord(ev[li + 1], st);
   }
   if (op_ms_host) {
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { set_error("plan: timed forward failed: %s", cudaGetErrorString(e)); return 1; }
-    for (size_t i = 0; i < ops.size(); ++i) cudaEventElapsedTime(&op_ms_host[i], ev[i], ev[i + 1]);
+    for (size_t i = 0; i < ops.size(); ++i) op_ms_host[i] = 0.f;
+    for (size_t li = 0; li < launches.size(); ++li) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[li], ev[li + 1]);
+      op_ms_host[launches[li].op] += ms;   // a sub-batched op reports the sum over its sub-batches
+    }
   }
   return 0;
 }
@@ -386,10 +443,11 @@ int Plan::op_info(int i, stl_op_info* info) const {
   info->bytes_per_image = in_b + out_b + (op.res >= 0 ? out_b : 0);
   for (int u = 0; u < op.n_up; ++u) info->bytes_per_image += (double)slots[op.up[u]].H * slots[op.up[u]].W * L.cout * 2;
   if (bound && op.kind == OP_CONV) {
-    const Prepared& pr = prepared[i];
+    const Prepared& pr = prepared[i][0];
     info->grid = pr.grid; info->smem = (int)pr.smem; info->mb = pr.params.mb; info->nt = pr.params.nt;
     info->ck = pr.params.ck; info->a_stages = pr.params.a_stages; info->b_stages = pr.params.b_stages;
     info->a_shift = pr.params.a_shift; info->tiles = (int)pr.params.total_tiles;
+    info->subs = (int)prepared[i].size();
   }
   return 0;
 }

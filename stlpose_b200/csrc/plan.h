@@ -26,7 +26,10 @@ struct Plan {
     int up[kMaxUp] = {-1, -1, -1};
     int up_shift[kMaxUp] = {0, 0, 0};
     bool relu = false, out_nchw = false;
+    int group = -1;  // ops of one group run sub-batch by sub-batch (L2-resident working set), see Plan::bind
   };
+  struct Group { int first = 0, count = 0; };
+  struct Launch { int op, sub; };
   struct Prepared {
     ConvParams params;
     int grid = 0;
@@ -47,7 +50,9 @@ struct Plan {
   const void* bound_arena = nullptr;
   void* bound_ws = nullptr;
   std::vector<uint8_t*> slot_ptr;
-  std::vector<Prepared> prepared;
+  std::vector<std::vector<Prepared>> prepared;  // [op][sub-batch]
+  std::vector<Group> groups;
+  std::vector<Launch> launches;                 // execution order for the current binding
 
   static Plan* create(const stl_hrnet_cfg& cfg);
   size_t workspace_bytes(int n_images) const;

@@ -334,8 +334,10 @@ class PoseHighResolutionNet(nn.Module):
         return self._run(x, flip_pair=True)
 
     def launches_per_forward(self, h=None, w=None):
+        """Kernels one forward enqueues (for the plan's current batch binding; ops of a sub-batched branch group
+        count once per sub-batch)."""
         h, w = (h, w) if h else self._image_size
-        return _lib.lib().stl_plan_launches_per_forward(self._plan(h, w))
+        return _lib.lib().stl_plan_kernel_launches(self._plan(h, w))
 
     def __del__(self):
         try:

@@ -39,10 +39,10 @@ class KeypointPipeline:
         self._copy_stream = torch.cuda.Stream(device=dev)
         self._calls = 0
         self.graph = None
-        self.launches_per_step = model.launches_per_forward(H, W) + 1
         with torch.cuda.device(dev):
             self._step_eager()                       # packs weights, binds the workspace, warms everything up
             torch.cuda.synchronize()
+            self.launches_per_step = model.launches_per_forward(H, W) + 1   # + the decode kernel
             if use_graph:
                 s = torch.cuda.Stream()
                 s.wait_stream(torch.cuda.current_stream())
