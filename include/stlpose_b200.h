@@ -162,6 +162,42 @@ typedef struct stl_op_info {
 } stl_op_info;
 int stl_plan_op_info(const stl_plan* plan, int op_index, stl_op_info* info);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training path (fine-tuning step, 02_train.py:203-218: model.train() forward, loss.backward()).
+ * Activations / activation gradients: padded-linear NHWC bf16.  Statistics and parameter gradients: fp32.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* nn.BatchNorm2d in training mode fused with the block's residual add and ReLU (HRnet.py:48-59, 85-100):
+ *   batch mean / biased variance of z over N*H*W -> y = [relu](gamma*(z-mean)*rstd + beta [+ residual]);
+ *   running_mean / running_var (may be null) updated with `momentum` and the unbiased variance.
+ * sums: 2*C fp32 scratch; mean, rstd: C fp32 outputs kept for the backward. */
+int stl_bn_train_forward(const void* z, const float* gamma, const float* beta, const void* residual, int relu,
+                         float eps, float momentum, int N, int H, int W, int C, void* y, float* sums, float* mean,
+                         float* rstd, float* running_mean, float* running_var, void* stream);
+
+/* Backward of the same unit: g = dy masked by (y > 0) when relu; sums[0:C] = dbeta = sum g, sums[C:2C] = dgamma =
+ * sum g*xhat; dz = gamma*rstd*(g - dbeta/cnt - xhat*dgamma/cnt); dres (may be null) = g. */
+int stl_bn_train_backward(const void* dy, const void* y, const void* z, const float* mean, const float* rstd,
+                          const float* gamma, int relu, int N, int H, int W, int C, void* dz, void* dres, float* sums,
+                          void* stream);
+
+/* Fuse-layer row (HRnet.py:255-264): y = relu(sum same[i] + sum nearest_upsample(up[j], 2^shift[j])).
+ * same_host / up_host: host arrays of device pointers (n_same <= 4, n_up <= 3). */
+int stl_sum_relu_forward(const void* const* same_host, int n_same, const void* const* up_host, const int* shift_host,
+                         int n_up, void* y, int N, int H, int W, int C, void* stream);
+/* g = dy * (y > 0): gradient of every same-resolution addend of the row above. */
+int stl_relu_mask(const void* dy, const void* y, void* g, long long elems, void* stream);
+/* gradient of a nearest-upsampled addend: dlow = sum of g over each 2^shift x 2^shift window. */
+int stl_upsample_backward(const void* g, void* dlow, int N, int H, int W, int C, int shift, void* stream);
+
+/* Convolution gradients (autograd of nn.Conv2d).  w_packed: [k*k][Cout][Cin] bf16 as produced by
+ * stl_pack_conv_weights without BatchNorm.  dx: padded-linear bf16 [N][Hi+1][Wi+1][Cin];
+ * dw: fp32 [Cout][cin_real][k][k] (OIHW), zeroed by the call. */
+int stl_conv_dgrad(const void* dz, const void* w_packed, void* dx, int N, int Hi, int Wi, int Cin, int Cout, int ksize,
+                   int stride, void* stream);
+int stl_conv_wgrad(const void* x, const void* dz, float* dw, int N, int Hi, int Wi, int Cin, int Cout, int ksize,
+                   int stride, int cin_real, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -150,30 +150,45 @@ def default_init_state_dict(width=32, seed=0, joints=NUM_JOINTS):
 # ----------------------------------------------------------------------------------------------
 # forward
 # ----------------------------------------------------------------------------------------------
-def _conv_bn(sd, x, conv, bn, stride=1, relu=False):
-    w = sd[conv + ".weight"]
-    y = F.conv2d(x, w, None, stride, w.shape[-1] // 2)
+_TRAIN = False  # set by hrnet_forward_train: BatchNorm uses batch statistics and updates the running ones in place
+_BF16 = False   # set by hrnet_forward_train(bf16_storage=True): tensors are rounded to bf16 where the device path stores them
+
+
+def _q(t):
+    """Round to bf16 and back (identity unless bf16 storage is emulated).  Autograd rounds the gradient that flows
+    back through this point to bf16 as well, which is where the device path stores activation gradients."""
+    return t.bfloat16().float() if _BF16 else t
+
+
+def _qw(w):
+    """bf16-rounded weights with a straight-through fp32 gradient (the device path keeps parameter gradients fp32)."""
+    return w + (w.detach().bfloat16().float() - w.detach()) if _BF16 else w
+
+
+def _conv_bn(sd, x, conv, bn, stride=1, relu=False, res=None):
+    w = _qw(sd[conv + ".weight"])
+    y = _q(F.conv2d(x, w, None, stride, w.shape[-1] // 2))
     y = F.batch_norm(y, sd[bn + ".running_mean"], sd[bn + ".running_var"], sd[bn + ".weight"],
-                     sd[bn + ".bias"], False, 0.1, BN_EPS)
-    return F.relu(y) if relu else y
+                     sd[bn + ".bias"], _TRAIN, 0.1, BN_EPS)
+    if res is not None:
+        y = y + res
+    return _q(F.relu(y) if relu else y)
 
 
 def _bottleneck(sd, x, p):
     """Bottleneck.forward, HRnet.py:82-102."""
     out = _conv_bn(sd, x, p + ".conv1", p + ".bn1", relu=True)
     out = _conv_bn(sd, out, p + ".conv2", p + ".bn2", relu=True)
-    out = _conv_bn(sd, out, p + ".conv3", p + ".bn3")
     res = x
     if (p + ".downsample.0.weight") in sd:
         res = _conv_bn(sd, x, p + ".downsample.0", p + ".downsample.1")
-    return F.relu(out + res)
+    return _conv_bn(sd, out, p + ".conv3", p + ".bn3", relu=True, res=res)   # relu(bn3(conv3) + residual)
 
 
 def _basic_block(sd, x, p):
     """BasicBlock.forward, HRnet.py:45-61."""
     out = _conv_bn(sd, x, p + ".conv1", p + ".bn1", relu=True)
-    out = _conv_bn(sd, out, p + ".conv2", p + ".bn2")
-    return F.relu(out + x)
+    return _conv_bn(sd, out, p + ".conv2", p + ".bn2", relu=True, res=x)     # relu(bn2(conv2) + x)
 
 
 def _hr_module(sd, xs, mp, n_out):
@@ -198,7 +213,7 @@ def _hr_module(sd, xs, mp, n_out):
                 for k in range(i - j):
                     t = _conv_bn(sd, t, f"{fp}.{k}.0", f"{fp}.{k}.1", stride=2, relu=(k != i - j - 1))
             y = t if y is None else y + t
-        outs.append(F.relu(y))
+        outs.append(_q(F.relu(y)))
     return outs
 
 
@@ -223,10 +238,31 @@ def _transition(sd, stage, ys, width):
     return xs
 
 
+def hrnet_forward_train(sd, x, width=32, bf16_storage=False):
+    """PoseHighResolutionNet.forward under model.train() (02_train.py:153, 208): BatchNorm normalises with batch
+    statistics (per replica, momentum 0.1 running-stat update in place on `sd`) and autograd is live, so
+    ``loss.backward()`` fills ``.grad`` of every tensor of `sd` that requires grad.
+
+    bf16_storage=True restates the SAME graph with every tensor rounded to bf16 at the points where the device path
+    stores it (input, conv weights, raw conv outputs, block outputs and their gradients; arithmetic stays fp32).
+    Batch-statistics BatchNorm over a few crops amplifies rounding differences chaotically with depth, so the fp32
+    result is only a loose anchor for a bf16 pipeline in train mode; this variant is the tight one."""
+    global _TRAIN, _BF16
+    _TRAIN, _BF16 = True, bool(bf16_storage)
+    try:
+        return _forward(sd, x, width)
+    finally:
+        _TRAIN, _BF16 = False, False
+
+
 @torch.no_grad()
 def hrnet_forward(sd, x, width=32):
     """PoseHighResolutionNet.forward in eval mode, HRnet.py:433-468.  x: f32 [B,3,H,W] -> [B,J,H/4,W/4]."""
-    x = _conv_bn(sd, x, "conv1", "bn1", stride=2, relu=True)
+    return _forward(sd, x, width)
+
+
+def _forward(sd, x, width):
+    x = _conv_bn(sd, _q(x), "conv1", "bn1", stride=2, relu=True)
     x = _conv_bn(sd, x, "conv2", "bn2", stride=2, relu=True)
     for b in range(4):
         x = _bottleneck(sd, x, f"layer1.{b}")
@@ -238,7 +274,7 @@ def hrnet_forward(sd, x, width=32):
             n_out = 1 if (stage == 4 and m == n_mod - 1) else stage
             xs = _hr_module(sd, xs, f"stage{stage}.{m}", n_out)
         ys = xs
-    return F.conv2d(ys[0], sd["final_layer.weight"], sd["final_layer.bias"])
+    return F.conv2d(ys[0], _qw(sd["final_layer.weight"]), sd["final_layer.bias"])
 
 
 def conv_flops_per_crop(width=32, image_hw=(256, 192), joints=NUM_JOINTS):

@@ -8,6 +8,7 @@
 #include "conv.h"
 #include "plan.h"
 #include "pose_kernels.h"
+#include "train_kernels.h"
 
 namespace stl {
 
@@ -200,6 +201,69 @@ int stl_plan_forward_timed(stl_plan* plan, const float* x, int B, int flip_pair,
 int stl_plan_op_info(const stl_plan* plan, int op_index, stl_op_info* info) {
   if (!plan) { set_error("stl_plan_op_info: null plan"); return 1; }
   return plan->impl->op_info(op_index, info);
+}
+
+int stl_bn_train_forward(const void* z, const float* gamma, const float* beta, const void* residual, int relu,
+                         float eps, float momentum, int N, int H, int W, int C, void* y, float* sums, float* mean,
+                         float* rstd, float* running_mean, float* running_var, void* stream) {
+  if (!have_device()) return 1;
+  if (!z || !gamma || !beta || !y || !sums || !mean || !rstd) { set_error("stl_bn_train_forward: null pointer"); return 1; }
+  typedef const __nv_bfloat16* P;
+  return bn_train_forward((P)z, gamma, beta, (P)residual, relu, eps, momentum, N, H, W, C, (__nv_bfloat16*)y, sums, mean,
+                          rstd, running_mean, running_var, (cudaStream_t)stream);
+}
+
+int stl_bn_train_backward(const void* dy, const void* y, const void* z, const float* mean, const float* rstd,
+                          const float* gamma, int relu, int N, int H, int W, int C, void* dz, void* dres, float* sums,
+                          void* stream) {
+  if (!have_device()) return 1;
+  if (!dy || !z || !mean || !rstd || !gamma || !dz || !sums || (relu && !y)) {
+    set_error("stl_bn_train_backward: null pointer");
+    return 1;
+  }
+  typedef const __nv_bfloat16* P;
+  return bn_train_backward((P)dy, (P)y, (P)z, mean, rstd, gamma, relu, N, H, W, C, (__nv_bfloat16*)dz,
+                           (__nv_bfloat16*)dres, sums, (cudaStream_t)stream);
+}
+
+int stl_sum_relu_forward(const void* const* same_host, int n_same, const void* const* up_host, const int* shift_host,
+                         int n_up, void* y, int N, int H, int W, int C, void* stream) {
+  if (!have_device()) return 1;
+  if (!y || (n_same > 0 && !same_host) || (n_up > 0 && (!up_host || !shift_host))) {
+    set_error("stl_sum_relu_forward: null pointer");
+    return 1;
+  }
+  return sum_relu_forward(reinterpret_cast<const __nv_bfloat16* const*>(same_host), n_same,
+                          reinterpret_cast<const __nv_bfloat16* const*>(up_host), shift_host, n_up, (__nv_bfloat16*)y, N,
+                          H, W, C, (cudaStream_t)stream);
+}
+
+int stl_relu_mask(const void* dy, const void* y, void* g, long long elems, void* stream) {
+  if (!have_device()) return 1;
+  if (!dy || !y || !g || elems % 8) { set_error("stl_relu_mask: bad arguments"); return 1; }
+  return relu_mask((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (__nv_bfloat16*)g, elems, (cudaStream_t)stream);
+}
+
+int stl_upsample_backward(const void* g, void* dlow, int N, int H, int W, int C, int shift, void* stream) {
+  if (!have_device()) return 1;
+  if (!g || !dlow || C % 8 || shift < 1 || shift > 3) { set_error("stl_upsample_backward: bad arguments"); return 1; }
+  return upsample_backward((const __nv_bfloat16*)g, (__nv_bfloat16*)dlow, N, H, W, C, shift, (cudaStream_t)stream);
+}
+
+int stl_conv_dgrad(const void* dz, const void* w_packed, void* dx, int N, int Hi, int Wi, int Cin, int Cout, int ksize,
+                   int stride, void* stream) {
+  if (!have_device()) return 1;
+  if (!dz || !w_packed || !dx) { set_error("stl_conv_dgrad: null pointer"); return 1; }
+  return conv_dgrad_naive((const __nv_bfloat16*)dz, (const __nv_bfloat16*)w_packed, (__nv_bfloat16*)dx, N, Hi, Wi, Cin,
+                          Cout, ksize, stride, (cudaStream_t)stream);
+}
+
+int stl_conv_wgrad(const void* x, const void* dz, float* dw, int N, int Hi, int Wi, int Cin, int Cout, int ksize,
+                   int stride, int cin_real, void* stream) {
+  if (!have_device()) return 1;
+  if (!x || !dz || !dw) { set_error("stl_conv_wgrad: null pointer"); return 1; }
+  return conv_wgrad_naive((const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, dw, N, Hi, Wi, Cin, Cout, ksize, stride,
+                          cin_real, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,454 @@
+// Training-path kernels (fine-tuning step of /root/reference/src/02_train.py:203-218): BatchNorm with batch
+// statistics (forward and backward), the fuse-layer sum with its backward, and CUDA-core convolution gradients for
+// the cases the tensor-core kernel does not cover yet (stride-2 dgrad, every wgrad).
+//
+// All activations and activation gradients use the engine's padded-linear NHWC bf16 layout (conv.h); zero cells are
+// kept zero by every kernel here.  Statistics and parameter gradients are fp32.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "conv.h"
+#include "train_kernels.h"
+
+namespace stl {
+
+namespace {
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+int check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+// ------------------------------------------------------------------ per-channel reductions over all pixels
+// MODE 0: sums[c] = sum a, sums[C+c] = sum a^2                      (BatchNorm forward statistics; a = z)
+// MODE 1: sums[c] = sum g, sums[C+c] = sum g * xhat                 (BatchNorm backward; g = dy masked by y > 0)
+// Zero cells of the padded layout contribute zero to every sum, so the kernel walks the flat tensor.
+// Block = 256 threads = (C/8 channel groups) x (256 / (C/8) pixel lanes); fp32 register partials, shared-memory
+// reduction over the pixel lanes, one atomicAdd per channel per block.
+template <int MODE>
+__global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16* __restrict__ a,
+                                                             const __nv_bfloat16* __restrict__ y,
+                                                             const __nv_bfloat16* __restrict__ z,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, long long pixels, int C,
+                                                             int relu_mask, float* __restrict__ sums) {
+  const int c8n = C / 8;
+  const int lanes = 256 / c8n;          // pixel lanes per block (C <= 2048 / 8 ... C/8 <= 256)
+  const int cg = threadIdx.x % c8n, pl = threadIdx.x / c8n;
+  float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float mu[8], rs[8];
+  if (MODE == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mu[i] = mean[cg * 8 + i]; rs[i] = rstd[cg * 8 + i]; }
+  }
+  if (pl < lanes) {
+    for (long long p = (long long)blockIdx.x * lanes + pl; p < pixels; p += (long long)gridDim.x * lanes) {
+      const size_t off = (size_t)p * C + cg * 8;
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(a + off), f);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s0[i] += f[i]; s1[i] += f[i] * f[i]; }
+      } else {
+        float yy[8], zz[8];
+        unpack8(*reinterpret_cast<const uint4*>(z + off), zz);
+        if (relu_mask) unpack8(*reinterpret_cast<const uint4*>(y + off), yy);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float g = (relu_mask && !(yy[i] > 0.f)) ? 0.f : f[i];
+          s0[i] += g;
+          s1[i] += g * (zz[i] - mu[i]) * rs[i];
+        }
+      }
+    }
+  }
+  __shared__ float red[2][256][8 + 1];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[0][threadIdx.x][i] = s0[i]; red[1][threadIdx.x][i] = s1[i]; }
+  __syncthreads();
+  if (pl == 0) {
+    for (int l = 1; l < lanes; ++l)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s0[i] += red[0][l * c8n + cg][i]; s1[i] += red[1][l * c8n + cg][i]; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(sums + cg * 8 + i, s0[i]);
+      atomicAdd(sums + C + cg * 8 + i, s1[i]);
+    }
+  }
+}
+
+// mean / rstd from the sums, running-statistics update (momentum, unbiased variance: nn.BatchNorm2d semantics)
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, float count, float eps, float momentum, int C,
+                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ run_mean,
+                                   float* __restrict__ run_var) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    const float m = sums[c] / count;
+    float var = sums[C + c] / count - m * m;
+    var = var > 0.f ? var : 0.f;
+    mean[c] = m;
+    rstd[c] = rsqrtf(var + eps);
+    if (run_mean) {
+      const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m;
+      run_var[c] = (1.f - momentum) * run_var[c] + momentum * unbiased;
+    }
+  }
+}
+
+// y = [relu]( gamma * (z - mean) * rstd + beta [+ residual] ) on the valid pixels, zero on the zero cells
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ z,
+                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const __nv_bfloat16* __restrict__ residual, int relu,
+                                                       __nv_bfloat16* __restrict__ y, int N, int H, int W, int C) {
+  const int c8n = C / 8, Wp = W + 1, Hp = H + 1;
+  const long long total = (long long)N * Hp * Wp * c8n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c8n);
+    const long long q = i / c8n;
+    const int w = (int)(q % Wp), h = (int)((q / Wp) % Hp);
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (h < H && w < W) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(z + (size_t)i * 8), f);
+      float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (residual) unpack8(*reinterpret_cast<const uint4*>(residual + (size_t)i * 8), r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = cg * 8 + k;
+        float v = gamma[c] * (f[k] - mean[c]) * rstd[c] + beta[c] + r[k];
+        f[k] = relu ? fmaxf(v, 0.f) : v;
+      }
+      out = pack8(f);
+    }
+    *reinterpret_cast<uint4*>(y + (size_t)i * 8) = out;
+  }
+}
+
+// dz = gamma * rstd * (g - sum_g/cnt - xhat * sum_gx/cnt),  g = dy masked by (y > 0) when relu; d_res = g
+__global__ void __launch_bounds__(256) bn_backward_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                          const __nv_bfloat16* __restrict__ y,
+                                                          const __nv_bfloat16* __restrict__ z,
+                                                          const float* __restrict__ mean,
+                                                          const float* __restrict__ rstd,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ sums, float count, int relu_mask,
+                                                          __nv_bfloat16* __restrict__ dz,
+                                                          __nv_bfloat16* __restrict__ dres, int N, int H, int W,
+                                                          int C) {
+  const int c8n = C / 8, Wp = W + 1, Hp = H + 1;
+  const long long total = (long long)N * Hp * Wp * c8n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c8n);
+    const long long q = i / c8n;
+    const int w = (int)(q % Wp), h = (int)((q / Wp) % Hp);
+    uint4 o_dz = make_uint4(0, 0, 0, 0), o_dr = o_dz;
+    if (h < H && w < W) {
+      float g[8], yy[8], zz[8], d[8];
+      unpack8(*reinterpret_cast<const uint4*>(dy + (size_t)i * 8), g);
+      unpack8(*reinterpret_cast<const uint4*>(z + (size_t)i * 8), zz);
+      if (relu_mask) unpack8(*reinterpret_cast<const uint4*>(y + (size_t)i * 8), yy);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = cg * 8 + k;
+        if (relu_mask && !(yy[k] > 0.f)) g[k] = 0.f;
+        const float xhat = (zz[k] - mean[c]) * rstd[c];
+        d[k] = gamma[c] * rstd[c] * (g[k] - sums[c] / count - xhat * sums[C + c] / count);
+      }
+      o_dz = pack8(d);
+      o_dr = pack8(g);
+    }
+    *reinterpret_cast<uint4*>(dz + (size_t)i * 8) = o_dz;
+    if (dres) *reinterpret_cast<uint4*>(dres + (size_t)i * 8) = o_dr;
+  }
+}
+
+// ------------------------------------------------------------------ fuse-layer sum (HRnet.py:255-264) and backward
+struct SumArgs {
+  const __nv_bfloat16* same[4];
+  const __nv_bfloat16* up[kMaxUp];
+  int shift[kMaxUp];
+  int n_same, n_up;
+};
+
+__global__ void __launch_bounds__(256) sum_relu_kernel(const SumArgs a, __nv_bfloat16* __restrict__ y, int N, int H,
+                                                       int W, int C) {
+  const int c8n = C / 8, Wp = W + 1, Hp = H + 1;
+  const long long total = (long long)N * Hp * Wp * c8n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c8n);
+    const long long q = i / c8n;
+    const int w = (int)(q % Wp);
+    const long long t = q / Wp;
+    const int h = (int)(t % Hp), n = (int)(t / Hp);
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (h < H && w < W) {
+      float f[8] = {0, 0, 0, 0, 0, 0, 0, 0}, r[8];
+      for (int k = 0; k < a.n_same; ++k) {
+        unpack8(*reinterpret_cast<const uint4*>(a.same[k] + (size_t)i * 8), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += r[j];
+      }
+      for (int k = 0; k < a.n_up; ++k) {
+        const int s = a.shift[k];
+        const size_t qs = ((size_t)n * ((H >> s) + 1) + (h >> s)) * ((W >> s) + 1) + (w >> s);
+        unpack8(*reinterpret_cast<const uint4*>(a.up[k] + qs * C + cg * 8), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += r[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      out = pack8(f);
+    }
+    *reinterpret_cast<uint4*>(y + (size_t)i * 8) = out;
+  }
+}
+
+// g = dy masked by (y > 0), at full resolution (gradient of every same-resolution addend)
+__global__ void __launch_bounds__(256) relu_mask_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                        const __nv_bfloat16* __restrict__ y,
+                                                        __nv_bfloat16* __restrict__ g, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float d[8], yy[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy + (size_t)i * 8), d);
+    unpack8(*reinterpret_cast<const uint4*>(y + (size_t)i * 8), yy);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (!(yy[k] > 0.f)) d[k] = 0.f;
+    *reinterpret_cast<uint4*>(g + (size_t)i * 8) = pack8(d);
+  }
+}
+
+// gradient of a nearest-upsampled addend: sum of g over each 2^s x 2^s window -> low-resolution tensor
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const __nv_bfloat16* __restrict__ g,
+                                                           __nv_bfloat16* __restrict__ dlow, int N, int H, int W,
+                                                           int C, int s) {
+  const int c8n = C / 8, Hs = H >> s, Ws = W >> s;
+  const long long total = (long long)N * (Hs + 1) * (Ws + 1) * c8n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c8n);
+    const long long q = i / c8n;
+    const int w = (int)(q % (Ws + 1));
+    const long long t = q / (Ws + 1);
+    const int h = (int)(t % (Hs + 1)), n = (int)(t / (Hs + 1));
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (h < Hs && w < Ws) {
+      float f[8] = {0, 0, 0, 0, 0, 0, 0, 0}, r[8];
+      for (int dh = 0; dh < (1 << s); ++dh)
+        for (int dw = 0; dw < (1 << s); ++dw) {
+          const size_t qf = ((size_t)n * (H + 1) + ((h << s) + dh)) * (W + 1) + ((w << s) + dw);
+          unpack8(*reinterpret_cast<const uint4*>(g + qf * C + cg * 8), r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += r[j];
+        }
+      out = pack8(f);
+    }
+    *reinterpret_cast<uint4*>(dlow + (size_t)i * 8) = out;
+  }
+}
+
+// ------------------------------------------------------------------ CUDA-core convolution gradients
+// dgrad for any (k, stride): dx[n,h,w,ci] = sum_{kh,kw,co} dz[n,ho,wo,co] * W[co,ci,kh,kw] with ho*stride+kh-pad = h.
+// One thread per (pixel, 8 input channels); weights [taps][cout][cin] bf16 (the forward packing, unscaled).
+__global__ void __launch_bounds__(128) conv_dgrad_kernel(const __nv_bfloat16* __restrict__ dz,
+                                                         const __nv_bfloat16* __restrict__ wp,
+                                                         __nv_bfloat16* __restrict__ dx, int N, int Hi, int Wi,
+                                                         int Cin, int Cout, int k, int stride) {
+  const int c8n = Cin / 8, Ho = Hi / stride, Wo = Wi / stride, pad = k / 2;
+  const long long total = (long long)N * (Hi + 1) * (Wi + 1) * c8n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c8n);
+    const long long q = i / c8n;
+    const int w = (int)(q % (Wi + 1));
+    const long long t = q / (Wi + 1);
+    const int h = (int)(t % (Hi + 1)), n = (int)(t / (Hi + 1));
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (h < Hi && w < Wi) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int kh = 0; kh < k; ++kh) {
+        const int hn = h + pad - kh;
+        if (hn < 0 || hn % stride) continue;
+        const int ho = hn / stride;
+        if (ho >= Ho) continue;
+        for (int kw = 0; kw < k; ++kw) {
+          const int wn = w + pad - kw;
+          if (wn < 0 || wn % stride) continue;
+          const int wo = wn / stride;
+          if (wo >= Wo) continue;
+          const __nv_bfloat16* g = dz + (((size_t)n * (Ho + 1) + ho) * (Wo + 1) + wo) * Cout;
+          const __nv_bfloat16* ww = wp + (size_t)(kh * k + kw) * Cout * Cin + cg * 8;
+          for (int co = 0; co < Cout; ++co) {
+            const float gv = __bfloat162float(g[co]);
+            float r[8];
+            unpack8(*reinterpret_cast<const uint4*>(ww + (size_t)co * Cin), r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv, r[j], acc[j]);
+          }
+        }
+      }
+      out = pack8(acc);
+    }
+    *reinterpret_cast<uint4*>(dx + (size_t)i * 8) = out;
+  }
+}
+
+// wgrad: dW[co][ci][kh][kw] = sum_{n,ho,wo} dz[n,ho,wo,co] * x[n,ho*s+kh-pad,wo*s+kw-pad,ci]   (fp32, OIHW)
+// Block = one (tap, 16 x 16 (co, ci) tile) x one slice of the pixels; 256 threads = the 16 x 16 tile, each thread
+// walks its pixel slice with both operands staged in shared memory 64 pixels at a time; partial sums are added to
+// dW with atomics (the slices of one tile live in different blocks).
+constexpr int kWgPix = 64;
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const __nv_bfloat16* __restrict__ x,
+                                                         const __nv_bfloat16* __restrict__ dz,
+                                                         float* __restrict__ dw, int N, int Hi, int Wi, int Cin,
+                                                         int Cout, int k, int stride, int cin_real, int slices) {
+  const int Ho = Hi / stride, Wo = Wi / stride, pad = k / 2, taps = k * k;
+  const int ci_tiles = Cin / 16, co_tiles = Cout / 16;
+  int b = blockIdx.x;
+  const int slice = b % slices; b /= slices;
+  const int cit = b % ci_tiles; b /= ci_tiles;
+  const int cot = b % co_tiles; b /= co_tiles;
+  const int tap = b;
+  const int kh = tap / k, kw = tap % k;
+  const int tci = threadIdx.x & 15, tco = threadIdx.x >> 4;
+  __shared__ float sx[kWgPix][16 + 1], sg[kWgPix][16 + 1];
+  const long long pix = (long long)N * Ho * Wo;
+  const long long per = (pix + slices - 1) / slices;
+  const long long p0 = (long long)slice * per, p1 = p0 + per < pix ? p0 + per : pix;
+  float acc = 0.f;
+  for (long long base = p0; base < p1; base += kWgPix) {
+    // stage 64 pixels x 16 channels of both operands (256 threads: 4 pixels x 16 channels per pass, 16 passes ... 4 passes of 64x16/256)
+    for (int e = threadIdx.x; e < kWgPix * 16; e += 256) {
+      const int pp = e >> 4, c = e & 15;
+      const long long p = base + pp;
+      float xv = 0.f, gv = 0.f;
+      if (p < p1) {
+        const int wo = (int)(p % Wo);
+        const long long t = p / Wo;
+        const int ho = (int)(t % Ho), n = (int)(t / Ho);
+        const int h = ho * stride + kh - pad, w = wo * stride + kw - pad;
+        gv = __bfloat162float(dz[(((size_t)n * (Ho + 1) + ho) * (Wo + 1) + wo) * Cout + cot * 16 + c]);
+        if (h >= 0 && h < Hi && w >= 0 && w < Wi)
+          xv = __bfloat162float(x[(((size_t)n * (Hi + 1) + h) * (Wi + 1) + w) * Cin + cit * 16 + c]);
+      }
+      sx[pp][c] = xv;
+      sg[pp][c] = gv;
+    }
+    __syncthreads();
+#pragma unroll 16
+    for (int pp = 0; pp < kWgPix; ++pp) acc = fmaf(sg[pp][tco], sx[pp][tci], acc);
+    __syncthreads();
+  }
+  const int co = cot * 16 + tco, ci = cit * 16 + tci;
+  if (ci < cin_real) atomicAdd(dw + ((size_t)co * cin_real + ci) * taps + tap, acc);
+}
+
+int grid_for(long long total, int block, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* beta, const __nv_bfloat16* residual,
+                     int relu, float eps, float momentum, int N, int H, int W, int C, __nv_bfloat16* y, float* sums,
+                     float* mean, float* rstd, float* run_mean, float* run_var, cudaStream_t st) {
+  if (C % 8 || C > 2048) { set_error("bn_train_forward: C=%d unsupported", C); return 1; }
+  const long long pixels = (long long)N * (H + 1) * (W + 1);
+  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st);
+  const int lanes = 256 / (C / 8);
+  channel_reduce_kernel<0><<<grid_for(pixels, lanes, 148 * 4), 256, 0, st>>>(z, nullptr, nullptr, nullptr, nullptr,
+                                                                            pixels, C, 0, sums);
+  if (check("bn stats")) return 1;
+  bn_finalize_kernel<<<1, 256, 0, st>>>(sums, (float)((long long)N * H * W), eps, momentum, C, mean, rstd, run_mean,
+                                        run_var);
+  if (check("bn finalize")) return 1;
+  bn_apply_kernel<<<grid_for(pixels * (C / 8), 256), 256, 0, st>>>(z, mean, rstd, gamma, beta, residual, relu, y, N, H,
+                                                                  W, C);
+  return check("bn apply");
+}
+
+int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* z, const float* mean,
+                      const float* rstd, const float* gamma, int relu, int N, int H, int W, int C,
+                      __nv_bfloat16* dz, __nv_bfloat16* dres, float* sums, cudaStream_t st) {
+  if (C % 8 || C > 2048) { set_error("bn_train_backward: C=%d unsupported", C); return 1; }
+  const long long pixels = (long long)N * (H + 1) * (W + 1);
+  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st);
+  const int lanes = 256 / (C / 8);
+  channel_reduce_kernel<1><<<grid_for(pixels, lanes, 148 * 4), 256, 0, st>>>(dy, y, z, mean, rstd, pixels, C, relu,
+                                                                            sums);
+  if (check("bn backward reduce")) return 1;
+  bn_backward_kernel<<<grid_for(pixels * (C / 8), 256), 256, 0, st>>>(dy, y, z, mean, rstd, gamma, sums,
+                                                                     (float)((long long)N * H * W), relu, dz, dres, N,
+                                                                     H, W, C);
+  return check("bn backward");
+}
+
+int sum_relu_forward(const __nv_bfloat16* const* same, int n_same, const __nv_bfloat16* const* up, const int* shift,
+                     int n_up, __nv_bfloat16* y, int N, int H, int W, int C, cudaStream_t st) {
+  if (n_same < 0 || n_same > 4 || n_up < 0 || n_up > kMaxUp || C % 8) { set_error("sum_relu: bad arguments"); return 1; }
+  SumArgs a{};
+  a.n_same = n_same; a.n_up = n_up;
+  for (int i = 0; i < n_same; ++i) a.same[i] = same[i];
+  for (int i = 0; i < n_up; ++i) { a.up[i] = up[i]; a.shift[i] = shift[i]; }
+  const long long total = (long long)N * (H + 1) * (W + 1) * (C / 8);
+  sum_relu_kernel<<<grid_for(total, 256), 256, 0, st>>>(a, y, N, H, W, C);
+  return check("sum_relu");
+}
+
+int relu_mask(const __nv_bfloat16* dy, const __nv_bfloat16* y, __nv_bfloat16* g, long long elems, cudaStream_t st) {
+  relu_mask_kernel<<<grid_for(elems / 8, 256), 256, 0, st>>>(dy, y, g, elems / 8);
+  return check("relu_mask");
+}
+
+int upsample_backward(const __nv_bfloat16* g, __nv_bfloat16* dlow, int N, int H, int W, int C, int shift,
+                      cudaStream_t st) {
+  const long long total = (long long)N * ((H >> shift) + 1) * ((W >> shift) + 1) * (C / 8);
+  upsample_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(g, dlow, N, H, W, C, shift);
+  return check("upsample_backward");
+}
+
+int conv_dgrad_naive(const __nv_bfloat16* dz, const __nv_bfloat16* w_packed, __nv_bfloat16* dx, int N, int Hi, int Wi,
+                     int Cin, int Cout, int k, int stride, cudaStream_t st) {
+  if (Cin % 8) { set_error("conv_dgrad: Cin must be a multiple of 8"); return 1; }
+  const long long total = (long long)N * (Hi + 1) * (Wi + 1) * (Cin / 8);
+  conv_dgrad_kernel<<<grid_for(total, 128, 148 * 32), 128, 0, st>>>(dz, w_packed, dx, N, Hi, Wi, Cin, Cout, k, stride);
+  return check("conv_dgrad");
+}
+
+int conv_wgrad_naive(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, int N, int Hi, int Wi, int Cin,
+                     int Cout, int k, int stride, int cin_real, cudaStream_t st) {
+  if (Cin % 16 || Cout % 16) { set_error("conv_wgrad: channels must be multiples of 16"); return 1; }
+  const int tiles = k * k * (Cin / 16) * (Cout / 16);
+  const long long pix = (long long)N * (Hi / stride) * (Wi / stride);
+  int slices = (148 * 8 + tiles - 1) / tiles;
+  const long long max_slices = (pix + 4 * kWgPix - 1) / (4 * kWgPix);
+  if (slices > max_slices) slices = (int)max_slices;
+  if (slices < 1) slices = 1;
+  cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * cin_real * k * k, st);
+  conv_wgrad_kernel<<<tiles * slices, 256, 0, st>>>(x, dz, dw, N, Hi, Wi, Cin, Cout, k, stride, cin_real, slices);
+  return check("conv_wgrad");
+}
+
+}  // namespace stl

@@ -1,0 +1,24 @@
+// Host launchers of the training-path kernels (train_kernels.cu). Return 0 on success; enqueue on `st`.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace stl {
+
+int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* beta, const __nv_bfloat16* residual,
+                     int relu, float eps, float momentum, int N, int H, int W, int C, __nv_bfloat16* y, float* sums,
+                     float* mean, float* rstd, float* run_mean, float* run_var, cudaStream_t st);
+int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* z, const float* mean,
+                      const float* rstd, const float* gamma, int relu, int N, int H, int W, int C,
+                      __nv_bfloat16* dz, __nv_bfloat16* dres, float* sums, cudaStream_t st);
+int sum_relu_forward(const __nv_bfloat16* const* same, int n_same, const __nv_bfloat16* const* up, const int* shift,
+                     int n_up, __nv_bfloat16* y, int N, int H, int W, int C, cudaStream_t st);
+int relu_mask(const __nv_bfloat16* dy, const __nv_bfloat16* y, __nv_bfloat16* g, long long elems, cudaStream_t st);
+int upsample_backward(const __nv_bfloat16* g, __nv_bfloat16* dlow, int N, int H, int W, int C, int shift,
+                      cudaStream_t st);
+int conv_dgrad_naive(const __nv_bfloat16* dz, const __nv_bfloat16* w_packed, __nv_bfloat16* dx, int N, int Hi, int Wi,
+                     int Cin, int Cout, int k, int stride, cudaStream_t st);
+int conv_wgrad_naive(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, int N, int Hi, int Wi, int Cin,
+                     int Cout, int k, int stride, int cin_real, cudaStream_t st);
+
+}  // namespace stl

@@ -259,8 +259,12 @@ class PoseHighResolutionNet(nn.Module):
 
     def _run(self, x, flip_pair):
         if self.training:
-            raise NotImplementedError(
-                "train-mode forward (batch-statistics BatchNorm + dgrad/wgrad) is not built yet; call .eval()")
+            if flip_pair:
+                raise NotImplementedError("the flip test is an evaluation feature; call .eval() first")
+            from .training import train_forward
+            out = train_forward(self, x)
+            self.invalidate_packed_weights()     # running statistics moved: the folded eval weights are stale
+            return out
         if x.dim() != 4 or x.shape[1] != 3:
             raise ValueError(f"expected input [B,3,H,W], got {tuple(x.shape)}")
         if not x.is_cuda:

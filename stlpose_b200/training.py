@@ -1,0 +1,237 @@
+"""Train-mode forward and backward of the HRNet pose network (the fine-tuning step of the reference,
+/root/reference/src/02_train.py:203-218: ``model.train()``, ``forward_pass``, ``loss.backward()``, ``optimizer.step()``).
+
+BatchNorm cannot be folded in training mode (batch statistics, HRnet.py:38-59 under ``model.train()``), so every
+conv + BN [+ residual] [+ ReLU] unit is an autograd node of three device steps:
+
+    z = conv(x, W)                      tcgen05 implicit-GEMM kernel, raw bf16 output
+    mean, var over N*H*W of z           per-channel reduction; running statistics updated like nn.BatchNorm2d
+    y = [relu](gamma*(z-mean)*rstd + beta [+ residual])
+
+and its backward (BN backward, conv dgrad, conv wgrad).  torch.autograd provides the graph (fan-out accumulation,
+ordering); every tensor operation on an activation is one of this library's kernels.  Activations and their gradients
+stay in the engine's padded-linear NHWC bf16 layout; parameter gradients are fp32 tensors shaped like the parameters,
+so ``torch.optim`` works unchanged.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+BN_EPS = 1e-5
+
+
+def _stream():
+    return _lib.current_stream()
+
+
+def _padded_zeros(n, h, w, c, device):
+    return torch.zeros((n, h + 1, w + 1, c), dtype=torch.bfloat16, device=device)
+
+
+def _pack_weights(w, cin_pad):
+    """fp32 OIHW -> ([k*k][cout_pad][cin_pad] bf16 buffer, zero fp32 bias)."""
+    L = _lib.lib()
+    cout, cin, k, _ = w.shape
+    cout_pad = (cout + 15) // 16 * 16
+    wp = torch.empty(k * k * cout_pad * cin_pad * 2, dtype=torch.uint8, device=w.device)
+    bp = torch.zeros(cout_pad, dtype=torch.float32, device=w.device)
+    w32 = w.detach().float().contiguous()
+    _lib.check(L.stl_pack_conv_weights(_lib.ptr(w32), None, None, None, None, None, 0.0, cout, cin, k, cout_pad,
+                                       cin_pad, _lib.ptr(wp), _lib.ptr(bp), _stream()))
+    return wp, bp, cout_pad
+
+
+def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bias=None):
+    """Tensor-core convolution on a padded bf16 tensor; returns padded bf16 [N,Ho+1,Wo+1,cout] (or fp32 NCHW)."""
+    L = _lib.lib()
+    n, hp, wpd, cin = x.shape
+    h, w = hp - 1, wpd - 1
+    ho, wo = h // stride, w // stride
+    d = _lib.ConvDesc()
+    d.in_ = x.data_ptr(); d.N, d.H, d.W, d.Cin = n, h, w, cin
+    if out is None:
+        out = (torch.empty((n, cout, ho, wo), dtype=torch.float32, device=x.device) if out_nchw
+               else _padded_zeros(n, ho, wo, cout, x.device))
+    d.out = out.data_ptr(); d.Cout, d.Cout_pad = cout, cout_pad
+    d.ksize, d.stride = k, stride
+    d.w_packed = wp.data_ptr(); d.bias_packed = (bias if bias is not None else bp).data_ptr()
+    d.relu = 0; d.out_nchw = int(out_nchw)
+    _lib.check(L.stl_conv2d(ctypes.byref(d), _stream()))
+    return out
+
+
+class _ConvBN(torch.autograd.Function):
+    """conv (no bias) + train-mode BatchNorm [+ residual] [+ ReLU] on padded bf16 activations."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, residual, run_mean, run_var, stride, relu, momentum):
+        L = _lib.lib()
+        n, hp, wpd, cin_pad = x.shape
+        h, w = hp - 1, wpd - 1
+        cout, cin_real, k, _ = weight.shape
+        wp, bp, cout_pad = _pack_weights(weight, cin_pad)
+        z = _conv_raw(x, wp, bp, cout, cout_pad, k, stride)
+        ho, wo = h // stride, w // stride
+        y = torch.empty_like(z)
+        sums = torch.empty(2 * cout, dtype=torch.float32, device=x.device)
+        mean = torch.empty(cout, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(cout, dtype=torch.float32, device=x.device)
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        _lib.check(L.stl_bn_train_forward(_lib.ptr(z), _lib.ptr(g32), _lib.ptr(b32), _lib.ptr(residual), int(relu),
+                                          BN_EPS, float(momentum), n, ho, wo, cout, _lib.ptr(y), _lib.ptr(sums),
+                                          _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(run_mean), _lib.ptr(run_var),
+                                          _stream()))
+        ctx.save_for_backward(x, wp, z, y, mean, rstd, g32)
+        ctx.meta = (n, h, w, cin_pad, cin_real, cout, k, stride, bool(relu), residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        x, wp, z, y, mean, rstd, g32 = ctx.saved_tensors
+        n, h, w, cin_pad, cin_real, cout, k, stride, relu, has_res = ctx.meta
+        ho, wo = h // stride, w // stride
+        dy = dy.contiguous()
+        dz = torch.empty_like(z)
+        dres = torch.empty_like(z) if has_res else None
+        sums = torch.empty(2 * cout, dtype=torch.float32, device=x.device)
+        _lib.check(L.stl_bn_train_backward(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(z), _lib.ptr(mean), _lib.ptr(rstd),
+                                           _lib.ptr(g32), int(relu), n, ho, wo, cout, _lib.ptr(dz), _lib.ptr(dres),
+                                           _lib.ptr(sums), _stream()))
+        dbeta, dgamma = sums[:cout].clone(), sums[cout:].clone()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _lib.check(L.stl_conv_dgrad(_lib.ptr(dz), _lib.ptr(wp), _lib.ptr(dx), n, h, w, cin_pad, cout, k, stride,
+                                        _stream()))
+        dw = torch.empty((cout, cin_real, k, k), dtype=torch.float32, device=x.device)
+        _lib.check(L.stl_conv_wgrad(_lib.ptr(x), _lib.ptr(dz), _lib.ptr(dw), n, h, w, cin_pad, cout, k, stride,
+                                    cin_real, _stream()))
+        return dx, dw, dgamma, dbeta, dres, None, None, None, None, None
+
+
+class _Head(torch.autograd.Function):
+    """final_layer: 1x1 conv with bias, no activation, fp32 NCHW out (HRnet.py:331-337, 466)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        n, hp, wpd, cin = x.shape
+        cout = weight.shape[0]
+        wp, bp, cout_pad = _pack_weights(weight, cin)
+        bp[:cout] = bias.detach().float()
+        heat = _conv_raw(x, wp, bp, cout, cout_pad, 1, 1, out_nchw=True)
+        ctx.save_for_backward(x, wp)
+        ctx.meta = (n, hp - 1, wpd - 1, cin, cout, cout_pad)
+        return heat
+
+    @staticmethod
+    def backward(ctx, dheat):
+        L = _lib.lib()
+        x, wp = ctx.saved_tensors
+        n, h, w, cin, cout, cout_pad = ctx.meta
+        dheat = dheat.contiguous().float()
+        dz = torch.empty((n, h + 1, w + 1, cout_pad), dtype=torch.bfloat16, device=x.device)
+        _lib.check(L.stl_nchw_to_padded(_lib.ptr(dheat), _lib.ptr(dz), n, cout, h, w, cout_pad, _stream()))
+        dx = torch.empty_like(x)
+        _lib.check(L.stl_conv_dgrad(_lib.ptr(dz), _lib.ptr(wp), _lib.ptr(dx), n, h, w, cin, cout_pad, 1, 1, _stream()))
+        dw = torch.empty((cout_pad, cin, 1, 1), dtype=torch.float32, device=x.device)
+        _lib.check(L.stl_conv_wgrad(_lib.ptr(x), _lib.ptr(dz), _lib.ptr(dw), n, h, w, cin, cout_pad, 1, 1, cin,
+                                    _stream()))
+        return dx, dw[:cout].contiguous(), dheat.sum(dim=(0, 2, 3))
+
+
+class _FuseSum(torch.autograd.Function):
+    """One output row of HighResolutionModule.forward (HRnet.py:255-264): relu(sum of same-resolution terms +
+    nearest-upsampled low-resolution terms)."""
+
+    @staticmethod
+    def forward(ctx, n_same, shifts, *tensors):
+        L = _lib.lib()
+        same, ups = tensors[:n_same], tensors[n_same:]
+        n, hp, wpd, c = same[0].shape
+        y = torch.empty_like(same[0])
+        sp = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in same])
+        up = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in ups])
+        sh = (ctypes.c_int * 3)(*shifts)
+        _lib.check(L.stl_sum_relu_forward(sp, len(same), up, sh, len(ups), _lib.ptr(y), n, hp - 1, wpd - 1, c,
+                                          _stream()))
+        ctx.save_for_backward(y)
+        ctx.meta = (n_same, tuple(shifts), [tuple(t.shape) for t in ups])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        (y,) = ctx.saved_tensors
+        n_same, shifts, up_shapes = ctx.meta
+        n, hp, wpd, c = y.shape
+        g = torch.empty_like(y)
+        _lib.check(L.stl_relu_mask(_lib.ptr(dy.contiguous()), _lib.ptr(y), _lib.ptr(g), y.numel(), _stream()))
+        grads = [g] * n_same
+        for s, shp in zip(shifts, up_shapes):
+            dlow = torch.empty(shp, dtype=torch.bfloat16, device=y.device)
+            _lib.check(L.stl_upsample_backward(_lib.ptr(g), _lib.ptr(dlow), n, hp - 1, wpd - 1, c, s, _stream()))
+            grads.append(dlow)
+        return (None, None, *grads)
+
+
+def _convbn(x, conv, bn, stride, relu, residual=None):
+    bn.num_batches_tracked += 1
+    return _ConvBN.apply(x, conv.weight, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, stride, relu,
+                         bn.momentum)
+
+
+def train_forward(model, x):
+    """PoseHighResolutionNet.forward in training mode (HRnet.py:433-468) -> fp32 heatmaps [B,J,H/4,W/4] with grad_fn."""
+    L = _lib.lib()
+    if not x.is_cuda:
+        raise _lib.StlError("input must be a CUDA tensor (there is no CPU fallback)")
+    x = x.detach().float().contiguous()
+    B, _, H, W = x.shape
+    with torch.cuda.device(x.device):
+        t = torch.empty((B, H + 1, W + 1, 16), dtype=torch.bfloat16, device=x.device)
+        _lib.check(L.stl_nchw_to_padded(_lib.ptr(x), _lib.ptr(t), B, 3, H, W, 16, _stream()))
+        t = _convbn(t, model.conv1, model.bn1, 2, True)
+        t = _convbn(t, model.conv2, model.bn2, 2, True)
+        for blk in model.layer1:                                     # Bottleneck.forward, HRnet.py:82-102
+            res = t
+            o = _convbn(t, blk.conv1, blk.bn1, 1, True)
+            o = _convbn(o, blk.conv2, blk.bn2, 1, True)
+            if hasattr(blk, "downsample"):
+                res = _convbn(t, blk.downsample[0], blk.downsample[1], 1, False)
+            t = _convbn(o, blk.conv3, blk.bn3, 1, True, residual=res)
+        tr = model.transition1
+        xs = [_convbn(t, tr[0][0], tr[0][1], 1, True), _convbn(t, tr[1][0][0], tr[1][0][1], 2, True)]
+        for stage in (2, 3, 4):
+            if stage > 2:                                            # HRnet.py:450-463: new branch from y_list[-1]
+                seq = getattr(model, f"transition{stage - 1}")[stage - 1][0]
+                xs.append(_convbn(xs[-1], seq[0], seq[1], 2, True))
+            for mod in getattr(model, f"stage{stage}"):
+                xs = _hr_module(mod, xs)
+        return _Head.apply(xs[0], model.final_layer.weight, model.final_layer.bias)
+
+
+def _hr_module(mod, xs):
+    """HighResolutionModule.forward, HRnet.py:248-266."""
+    xs = list(xs)
+    for b, branch in enumerate(mod.branches):
+        for blk in branch:                                           # BasicBlock.forward, HRnet.py:45-61
+            o = _convbn(xs[b], blk.conv1, blk.bn1, 1, True)
+            xs[b] = _convbn(o, blk.conv2, blk.bn2, 1, True, residual=xs[b])
+    outs = []
+    for i, row in enumerate(mod.fuse_layers):
+        same, ups, shifts = [xs[i]], [], []
+        for j in range(len(xs)):
+            if j > i:
+                ups.append(_convbn(xs[j], row[j][0], row[j][1], 1, False))
+                shifts.append(j - i)
+            elif j < i:
+                t = xs[j]
+                hops = len(row[j])
+                for k, seq in enumerate(row[j]):
+                    t = _convbn(t, seq[0], seq[1], 2, k != hops - 1)
+                same.append(t)
+        outs.append(_FuseSum.apply(len(same), shifts, *same, *ups))
+    return outs

@@ -40,3 +40,26 @@ def test_decode_matches_reference_random():
         got = pose_oracle.get_final_preds(hm, c, s)
         assert np.array_equal(got[2], ref[2]) and np.array_equal(got[1], ref[1])
         assert np.abs(got[0] - ref[0]).max() < 1e-3
+
+
+def test_train_step_matches_reference_module():
+    """model.train() forward, PersonMSELoss-style loss, backward: heatmaps, every parameter gradient and the updated
+    running statistics of the oracle equal the reference module's (02_train.py:203-218)."""
+    m = ref_shim.build_reference_hrnet(32).train()
+    sd0 = hrnet_oracle.synth_state_dict(32, seed=0)
+    m.load_state_dict(sd0, strict=True)
+    x = torch.randn(2, 3, 128, 96, generator=torch.Generator().manual_seed(7))
+    tgt = torch.from_numpy(pose_oracle.blob_heatmaps(2, 17, 32, 24, seed=1, noise=0.0))
+    y_ref = m(x)
+    (0.5 * ((y_ref - tgt) ** 2).mean()).backward()
+    sd = {k: (v.clone().requires_grad_(True) if v.dtype == torch.float32 and "running" not in k else v.clone())
+          for k, v in sd0.items()}
+    y = hrnet_oracle.hrnet_forward_train(sd, x, 32)
+    (0.5 * ((y - tgt) ** 2).mean()).backward()
+    assert (y - y_ref).abs().max().item() < 1e-5
+    ref_sd = m.state_dict()
+    for name, p in m.named_parameters():
+        assert (sd[name].grad - p.grad).abs().max().item() <= 1e-5 * max(1.0, p.grad.abs().max().item()), name
+    for k, v in ref_sd.items():
+        if "running" in k:
+            assert (sd[k] - v).abs().max().item() < 1e-5, k

@@ -1,0 +1,138 @@
+"""GPU parity of the individual training kernels (through the C ABI) vs torch fp32 autograd on identical
+bf16-rounded operands."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import bf16_round, from_padded, to_padded
+from stlpose_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _padded(t):                      # fp32 NCHW -> padded bf16 tensor view [N,H+1,W+1,C]
+    n, c, h, w = t.shape
+    return to_padded(t).view(torch.bfloat16).view(n, h + 1, w + 1, c)
+
+
+def _unpadded(p):                    # padded bf16 [N,H+1,W+1,C] -> fp32 NCHW
+    n, hp, wp, c = p.shape
+    return from_padded(p.contiguous().view(torch.uint8).view(-1), n, c, hp - 1, wp - 1)
+
+
+@pytest.mark.parametrize("shape", [(3, 32, 16, 12), (2, 64, 8, 6), (5, 48, 12, 9), (2, 256, 8, 6)])
+@pytest.mark.parametrize("relu,with_res", [(True, True), (True, False), (False, False)])
+def test_bn_train_forward_backward(shape, relu, with_res):
+    L = _lib.lib()
+    n, c, h, w = shape
+    g = torch.Generator(device=DEV).manual_seed(c + h)
+    z = bf16_round(torch.randn(shape, device=DEV, generator=g) * 1.5 + 0.3)
+    res = bf16_round(torch.randn(shape, device=DEV, generator=g)) if with_res else None
+    gamma = torch.rand(c, device=DEV, generator=g) + 0.5
+    beta = torch.randn(c, device=DEV, generator=g) * 0.1
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    zp = _padded(z)
+    y = torch.empty_like(zp)
+    sums = torch.empty(2 * c, device=DEV); mean = torch.empty(c, device=DEV); rstd = torch.empty(c, device=DEV)
+    resp = _padded(res) if with_res else None
+    _lib.check(L.stl_bn_train_forward(_lib.ptr(zp), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(resp), int(relu), 1e-5, 0.1,
+                                      n, h, w, c, _lib.ptr(y), _lib.ptr(sums), _lib.ptr(mean), _lib.ptr(rstd),
+                                      _lib.ptr(rm), _lib.ptr(rv), _lib.current_stream()))
+    # reference
+    zr = z.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True) if with_res else None
+    rm_ref, rv_ref = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    yr = F.batch_norm(zr, rm_ref, rv_ref, gr, br, True, 0.1, 1e-5)
+    if with_res:
+        yr = yr + rr
+    if relu:
+        yr = F.relu(yr)
+    got = _unpadded(y)
+    assert (got - yr.detach()).abs().max().item() < 2e-2 * max(1.0, yr.abs().max().item())
+    assert (rm - rm_ref).abs().max().item() < 1e-4 and (rv - rv_ref).abs().max().item() < 1e-3
+    assert (y[:, h] == 0).all() and (y[:, :, w] == 0).all()
+    # backward
+    dy = bf16_round(torch.randn(shape, device=DEV, generator=g))
+    yr.backward(dy)
+    dyp = _padded(dy)
+    dz = torch.empty_like(zp); dres = torch.empty_like(zp) if with_res else None
+    sums2 = torch.empty(2 * c, device=DEV)
+    _lib.check(L.stl_bn_train_backward(_lib.ptr(dyp), _lib.ptr(y), _lib.ptr(zp), _lib.ptr(mean), _lib.ptr(rstd),
+                                       _lib.ptr(gamma), int(relu), n, h, w, c, _lib.ptr(dz), _lib.ptr(dres),
+                                       _lib.ptr(sums2), _lib.current_stream()))
+    scale = max(1.0, zr.grad.abs().max().item())
+    assert (_unpadded(dz) - zr.grad).abs().max().item() < 3e-2 * scale
+    assert (sums2[:c] - br.grad).abs().max().item() < 2e-2 * max(1.0, br.grad.abs().max().item())
+    assert (sums2[c:] - gr.grad).abs().max().item() < 2e-2 * max(1.0, gr.grad.abs().max().item())
+    if with_res:
+        assert (_unpadded(dres) - rr.grad).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("case", [
+    dict(n=2, cin=32, cout=32, h=16, w=12, k=3, s=1), dict(n=3, cin=64, cout=32, h=16, w=12, k=1, s=1),
+    dict(n=2, cin=32, cout=64, h=16, w=12, k=3, s=2), dict(n=2, cin=16, cout=64, h=32, w=24, k=3, s=2, cin_real=3),
+    dict(n=2, cin=128, cout=256, h=16, w=12, k=3, s=2), dict(n=3, cin=32, cout=32, h=64, w=48, k=1, s=1, cout_real=17),
+])
+def test_conv_gradients(case):
+    L = _lib.lib()
+    n, cin, cout, h, w, k, s = (case[x] for x in ("n", "cin", "cout", "h", "w", "k", "s"))
+    cin_real = case.get("cin_real", cin)
+    g = torch.Generator(device=DEV).manual_seed(cin * cout + k)
+    x = bf16_round(torch.randn(n, cin, h, w, device=DEV, generator=g))
+    x[:, cin_real:] = 0
+    wt = bf16_round(torch.randn(cout, cin_real, k, k, device=DEV, generator=g) / (cin_real * k * k) ** 0.5)
+    ho, wo = h // s, w // s
+    dz = bf16_round(torch.randn(n, cout, ho, wo, device=DEV, generator=g))
+    if "cout_real" in case:
+        dz[:, case["cout_real"]:] = 0
+    # reference via autograd
+    xr, wr = x[:, :cin_real].clone().requires_grad_(True), wt.clone().requires_grad_(True)
+    F.conv2d(xr, wr, None, s, k // 2).backward(dz)
+    # ours
+    wp = torch.empty(k * k * cout * cin * 2, dtype=torch.uint8, device=DEV)
+    bp = torch.empty(cout, device=DEV)
+    _lib.check(L.stl_pack_conv_weights(_lib.ptr(wt.contiguous()), None, None, None, None, None, 0.0, cout, cin_real, k,
+                                       cout, cin, _lib.ptr(wp), _lib.ptr(bp), _lib.current_stream()))
+    xp, dzp = _padded(x), _padded(dz)
+    dx = torch.empty_like(xp)
+    _lib.check(L.stl_conv_dgrad(_lib.ptr(dzp), _lib.ptr(wp), _lib.ptr(dx), n, h, w, cin, cout, k, s, _lib.current_stream()))
+    dw = torch.empty((cout, cin_real, k, k), device=DEV)
+    _lib.check(L.stl_conv_wgrad(_lib.ptr(xp), _lib.ptr(dzp), _lib.ptr(dw), n, h, w, cin, cout, k, s, cin_real,
+                                _lib.current_stream()))
+    got_dx = _unpadded(dx)[:, :cin_real]
+    assert (got_dx - xr.grad).abs().max().item() < 2e-2 * max(1.0, xr.grad.abs().max().item())
+    assert (dx[:, h] == 0).all() and (dx[:, :, w] == 0).all()
+    assert (dw - wr.grad).abs().max().item() < 1e-3 * max(1.0, wr.grad.abs().max().item())
+
+
+def test_sum_relu_and_backward():
+    L = _lib.lib()
+    n, c, h, w = 3, 32, 16, 12
+    g = torch.Generator(device=DEV).manual_seed(1)
+    a = bf16_round(torch.randn(n, c, h, w, device=DEV, generator=g)).requires_grad_(True)
+    b = bf16_round(torch.randn(n, c, h, w, device=DEV, generator=g)).requires_grad_(True)
+    u1 = bf16_round(torch.randn(n, c, h // 2, w // 2, device=DEV, generator=g)).requires_grad_(True)
+    u2 = bf16_round(torch.randn(n, c, h // 4, w // 4, device=DEV, generator=g)).requires_grad_(True)
+    ref = F.relu(a + b + F.interpolate(u1, scale_factor=2, mode="nearest") + F.interpolate(u2, scale_factor=4, mode="nearest"))
+    ap, bp_, u1p, u2p = _padded(a.detach()), _padded(b.detach()), _padded(u1.detach()), _padded(u2.detach())
+    y = torch.empty_like(ap)
+    same = (ctypes.c_void_p * 4)(ap.data_ptr(), bp_.data_ptr())
+    ups = (ctypes.c_void_p * 3)(u1p.data_ptr(), u2p.data_ptr())
+    sh = (ctypes.c_int * 3)(1, 2)
+    _lib.check(L.stl_sum_relu_forward(same, 2, ups, sh, 2, _lib.ptr(y), n, h, w, c, _lib.current_stream()))
+    assert (_unpadded(y) - ref.detach()).abs().max().item() < 2e-2 * ref.abs().max().item()
+    dy = bf16_round(torch.randn(n, c, h, w, device=DEV, generator=g))
+    ref.backward(dy)
+    gm = torch.empty_like(ap)
+    _lib.check(L.stl_relu_mask(_lib.ptr(_padded(dy)), _lib.ptr(y), _lib.ptr(gm), y.numel(), _lib.current_stream()))
+    mask_ok = (ref.detach() > 1e-2) | (ref.detach() == 0)       # away from the bf16 rounding of the zero crossing
+    assert ((_unpadded(gm) - a.grad).abs() * mask_ok).max().item() < 1e-6
+    for up, shift in ((u1, 1), (u2, 2)):
+        dlow = torch.empty((n, (h >> shift) + 1, (w >> shift) + 1, c), dtype=torch.bfloat16, device=DEV)
+        _lib.check(L.stl_upsample_backward(_lib.ptr(gm), _lib.ptr(dlow), n, h, w, c, shift, _lib.current_stream()))
+        want = F.avg_pool2d(_unpadded(gm), 1 << shift) * (1 << shift) ** 2
+        assert (_unpadded(dlow) - want).abs().max().item() < 3e-2 * max(1.0, want.abs().max().item())
