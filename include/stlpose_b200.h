@@ -197,6 +197,10 @@ int stl_conv_dgrad(const void* dz, const void* w_packed, void* dx, int N, int Hi
                    int stride, void* stream);
 int stl_conv_wgrad(const void* x, const void* dz, float* dw, int N, int Hi, int Wi, int Cin, int Cout, int ksize,
                    int stride, int cin_real, void* stream);
+/* stl_conv_wgrad runs stride-1 layers with channel counts of 32/64/128/256 on the tcgen05 tensor cores and the rest
+ * (stride 2, the 3-channel stem) on a CUDA-core kernel; this entry forces the CUDA-core kernel (validation). */
+int stl_conv_wgrad_naive(const void* x, const void* dz, float* dw, int N, int Hi, int Wi, int Cin, int Cout, int ksize,
+                         int stride, int cin_real, void* stream);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,7 @@ PROTOTYPES = {
     "stl_upsample_backward": (ctypes.c_int, [vp, vp] + [ctypes.c_int] * 5 + [vp]),
     "stl_conv_dgrad": (ctypes.c_int, [vp, vp, vp] + [ctypes.c_int] * 7 + [vp]),
     "stl_conv_wgrad": (ctypes.c_int, [vp, vp, vp] + [ctypes.c_int] * 8 + [vp]),
+    "stl_conv_wgrad_naive": (ctypes.c_int, [vp, vp, vp] + [ctypes.c_int] * 8 + [vp]),
 }
 
 _lib = None

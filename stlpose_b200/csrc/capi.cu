@@ -262,6 +262,17 @@ int stl_conv_wgrad(const void* x, const void* dz, float* dw, int N, int Hi, int 
                    int stride, int cin_real, void* stream) {
   if (!have_device()) return 1;
   if (!x || !dz || !dw) { set_error("stl_conv_wgrad: null pointer"); return 1; }
+  if (wgrad_tc_supported(Wi, Cin, Cout, cin_real, ksize, stride))
+    return wgrad_tc_launch((const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, dw, N, Hi, Wi, Cin, Cout, ksize, cin_real,
+                           (cudaStream_t)stream);
+  return conv_wgrad_naive((const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, dw, N, Hi, Wi, Cin, Cout, ksize, stride,
+                          cin_real, (cudaStream_t)stream);
+}
+
+int stl_conv_wgrad_naive(const void* x, const void* dz, float* dw, int N, int Hi, int Wi, int Cin, int Cout, int ksize,
+                         int stride, int cin_real, void* stream) {
+  if (!have_device()) return 1;
+  if (!x || !dz || !dw) { set_error("stl_conv_wgrad_naive: null pointer"); return 1; }
   return conv_wgrad_naive((const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, dw, N, Hi, Wi, Cin, Cout, ksize, stride,
                           cin_real, (cudaStream_t)stream);
 }

@@ -21,4 +21,9 @@ int conv_dgrad_naive(const __nv_bfloat16* dz, const __nv_bfloat16* w_packed, __n
 int conv_wgrad_naive(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, int N, int Hi, int Wi, int Cin,
                      int Cout, int k, int stride, int cin_real, cudaStream_t st);
 
+// tcgen05 weight gradient for stride-1 convolutions (wgrad_tc.cu)
+bool wgrad_tc_supported(int W, int cin, int cout, int cin_real, int k, int stride);
+int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, int N, int H, int W, int cin, int cout,
+                    int k, int cin_real, cudaStream_t stream);
+
 }  // namespace stl

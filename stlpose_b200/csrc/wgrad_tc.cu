@@ -1,0 +1,330 @@
+// Weight gradient of a stride-1 convolution on the tcgen05 tensor cores.
+//
+//   dW[co][ci][kh][kw] = sum_q dz[q][co] * x[q + (kh-1)*Wp + (kw-1)][ci]        q over the padded-linear pixels
+//
+// (the reference gets this from autograd of nn.Conv2d, HRnet.py:48-59 under 02_train.py:216).  In the padded-linear
+// layout (conv.h) the filter taps are flat row shifts, zero cells contribute zero, and rows outside the tensor are
+// zero-filled by TMA, so the whole batch is ONE GEMM per tap with the pixel index as the reduction dimension:
+// M = output channels, N = input channels, K = pixels.  Both operands are "MN-major" for the tensor core (channels
+// contiguous, K = rows), which the UMMA shared-memory descriptor supports for bf16 directly: a TMA box of
+// [rows][<=64 channels] with the hardware swizzle IS the canonical MN-major layout, and a filter tap is a row
+// offset added to the descriptor's start address.
+//
+// Narrow layers fill the 128 accumulator rows with row-shifted replicas of dz: with co = 32 the A descriptor's
+// leading-dimension stride is one pixel row, so MN blocks 0..3 of the same tile are dz shifted by 0..3 pixels and a
+// single MMA yields three taps of a filter row ( sum_q dz[q+j] x[q+b] = dW(offset b-j) ); with co = 64 two replicas
+// give two taps per MMA.  Pixel tiles therefore start at row -4 (TMA zero-fills) so that every replica covers [0,P).
+//
+// Work decomposition: CTA = (128-row block of co, 128-column block of ci, tap group, pixel range); partial sums are
+// accumulated in TMEM over the CTA's pixel range and added to the fp32 OIHW result with red.global.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "conv.h"
+#include "ptx.cuh"
+#include "train_kernels.h"
+
+namespace stl {
+namespace {
+
+constexpr int kKT = 128;          // pixel rows per pipeline stage
+constexpr int kLead = 4;          // tiles start at row -kLead (room for 3 replica shifts)
+constexpr int kMaxMma = 6;        // MMAs per 16-row K step
+constexpr int kMaxStagesW = 8;
+constexpr int kThreadsW = 192;    // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
+
+struct WgradParams {
+  CUtensorMap tmDz, tmX;
+  int m_real, m_blks, n_blks, n_groups, nt, n_mma, n_acc;
+  int a_panels, b_panels, pitch_a, pitch_b, dz_rows, x_rows;
+  uint32_t a_panel_bytes, b_panel_bytes, stage_bytes, lbo_a, lbo_b;
+  int stages, tmem_cols;
+  int x_row0[3];                  // first x row of a tile relative to q0, per tap group
+  int mma_b[3][kMaxMma];          // B operand row offset inside the x tile, per tap group and MMA
+  int mma_acc[kMaxMma];
+  int tap_of[3][kMaxMma][4];      // filter tap produced by (group, accumulator, replica) or -1
+  int tiles_total, tiles_per_split, n_splits;
+  float* dw;
+  int co, ci, ci_real, taps;
+};
+
+// MN-major operand: rows (K) are `pitch` bytes apart (pitch = swizzle span), 8-row groups contiguous, 64-channel
+// (32 for the 64-byte span) MN blocks `lbo` bytes apart.
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t pitch, uint32_t lbo) {
+  const uint64_t layout = pitch == 128 ? 2ull : 4ull;
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((8u * pitch) >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= layout << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kMaxStagesW], empty_bar[kMaxStagesW], done_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  // work item
+  const int group = blockIdx.x % p.n_groups, split = blockIdx.x / p.n_groups;
+  const int tg = group % ((p.n_groups / (p.m_blks * p.n_blks)));
+  const int mn = group / (p.n_groups / (p.m_blks * p.n_blks));
+  const int n_blk = mn % p.n_blks, m_blk = mn / p.n_blks;
+  const int t_lo = split * p.tiles_per_split;
+  int t_hi = t_lo + p.tiles_per_split;
+  if (t_hi > p.tiles_total) t_hi = p.tiles_total;
+  const int n_tiles = t_hi > t_lo ? t_hi - t_lo : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (n_tiles > 0) {
+    if (warp == 0) {
+      // ------------------------------------------------------------ TMA producer
+      if (elect_one()) {
+        tma_prefetch_desc(&p.tmDz);
+        tma_prefetch_desc(&p.tmX);
+        for (int i = 0; i < n_tiles; ++i) {
+          const int s = i % p.stages;
+          const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          const int q0 = -kLead + (t_lo + i) * kKT;
+          const uint32_t a_dst = smem0 + (uint32_t)s * p.stage_bytes;
+          const uint32_t b_dst = a_dst + (uint32_t)p.a_panels * p.a_panel_bytes;
+          mbar_expect_tx(&full_bar[s], (uint32_t)p.a_panels * (uint32_t)(p.dz_rows * p.pitch_a) +
+                                           (uint32_t)p.b_panels * (uint32_t)(p.x_rows * p.pitch_b));
+          for (int a = 0; a < p.a_panels; ++a)
+            tma_load_2d_s(a_dst + a * p.a_panel_bytes, &p.tmDz, &full_bar[s], m_blk * 128 + a * 64, q0);
+          for (int b = 0; b < p.b_panels; ++b)
+            tma_load_2d_s(b_dst + b * p.b_panel_bytes, &p.tmX, &full_bar[s], n_blk * 128 + b * 64, q0 + p.x_row0[tg]);
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------ MMA issuer
+      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.nt) | (1u << 15) | (1u << 16);   // A and B MN-major
+      for (int i = 0; i < n_tiles; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_src = smem0 + (uint32_t)s * p.stage_bytes;
+          const uint32_t b_src = a_src + (uint32_t)p.a_panels * p.a_panel_bytes;
+#pragma unroll 1
+          for (int ks = 0; ks < kKT / 16; ++ks) {
+            const uint64_t adesc = make_mnmajor_desc(a_src + (uint32_t)(ks * 16 * p.pitch_a), (uint32_t)p.pitch_a, p.lbo_a);
+#pragma unroll 1
+            for (int m = 0; m < p.n_mma; ++m) {
+              const uint64_t bdesc = make_mnmajor_desc(b_src + (uint32_t)((p.mma_b[tg][m] + ks * 16) * p.pitch_b),
+                                                       (uint32_t)p.pitch_b, p.lbo_b);
+              umma_bf16(tmem_base + (uint32_t)(p.mma_acc[m] * p.nt), adesc, bdesc, idesc, (i | ks) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (i == n_tiles - 1) umma_commit(&done_bar);
+        }
+        __syncwarp();
+      }
+    } else {
+      // ------------------------------------------------------------ epilogue: TMEM -> red.global into dW (OIHW fp32)
+      mbar_wait(&done_bar, 0);
+      tc_fence_after();
+      const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+      const int row = quad * 32 + lane;                // accumulator row
+      const int rep = row / p.m_real;
+      const int co = m_blk * 128 + row % p.m_real;
+      for (int a = 0; a < p.n_acc; ++a) {
+        const int tap = p.tap_of[tg][a][rep];
+        for (int c0 = 0; c0 < p.nt; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.nt + c0), v);
+          tmem_ld_wait();
+          if (tap >= 0 && co < p.co) {
+            float* dst = p.dw + ((size_t)co * p.ci_real + (size_t)(n_blk * 128 + c0)) * p.taps + tap;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (n_blk * 128 + c0 + c < p.ci_real) atomicAdd(dst + (size_t)c * p.taps, __uint_as_float(v[c]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_rows(CUtensorMap* tm, const void* base, int channels, long long rows, int box_c, int box_rows) {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || !ptr) {
+      set_error("cuTensorMapEncodeTiled entry point not available");
+      return 1;
+    }
+    fn = reinterpret_cast<EncodeFn>(ptr);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)channels, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)channels * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_rows};
+  const cuuint32_t es[2] = {1, 1};
+  const CUtensorMapSwizzle sw = box_c * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("wgrad: cuTensorMapEncodeTiled failed (CUresult %d) channels %d rows %lld box %d x %d", (int)r, channels,
+              rows, box_c, box_rows);
+    return 1;
+  }
+  return 0;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+bool wgrad_tc_supported(int W, int cin, int cout, int cin_real, int k, int stride) {
+  if (stride != 1 || (k != 1 && k != 3)) return false;
+  if (k == 3 && cout < 128 && kKT + 2 * (W + 2) > 256) return false;     // halo'd x tile must fit one TMA box
+  if (cout % 32 || cin % 32 || cin_real > cin) return false;
+  if (cout > 64 && cout % 128) return false;
+  if (cin > 64 && cin % 128) return false;
+  const int m_real = cout < 128 ? cout : 128, R = 128 / m_real, nt = cin < 128 ? cin : 128;
+  const int n_acc = k == 1 ? 1 : (R >= 3 ? 3 : (R == 2 ? 6 : 3));
+  return n_acc * nt <= 512;
+}
+
+int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, int N, int H, int W, int cin, int cout,
+                    int k, int cin_real, cudaStream_t stream) {
+  if (!wgrad_tc_supported(W, cin, cout, cin_real, k, 1)) { set_error("wgrad_tc: unsupported shape"); return 1; }
+  WgradParams p{};
+  const int Wp = W + 1;
+  const long long P = (long long)N * (H + 1) * Wp;
+  p.co = cout; p.ci = cin; p.ci_real = cin_real; p.taps = k * k; p.dw = dw;
+  p.m_real = cout < 128 ? cout : 128;
+  const int R = 128 / p.m_real;
+  p.m_blks = (cout + 127) / 128;
+  p.n_blks = (cin + 127) / 128;
+  p.nt = cin < 128 ? cin : 128;
+  p.pitch_a = (cout < 64 ? cout : 64) * 2;
+  p.pitch_b = (cin < 64 ? cin : 64) * 2;
+  p.a_panels = p.m_real > 64 ? 2 : 1;
+  p.b_panels = p.nt > 64 ? 2 : 1;
+  p.dz_rows = kKT + kLead;
+  int tap_groups = 1;
+  for (int g = 0; g < 3; ++g)
+    for (int m = 0; m < kMaxMma; ++m)
+      for (int j = 0; j < 4; ++j) p.tap_of[g][m][j] = -1;
+  if (k == 1) {
+    p.n_mma = p.n_acc = 1;
+    p.x_rows = kKT;
+    p.x_row0[0] = 0;
+    p.mma_b[0][0] = 0;
+    p.mma_acc[0] = 0;
+    p.tap_of[0][0][0] = 0;
+  } else if (R >= 3) {          // one MMA per filter row: replicas 0,1,2 -> kw = 2,1,0
+    p.n_mma = p.n_acc = 3;
+    p.x_rows = kKT + 2 * (Wp + 1);
+    p.x_row0[0] = -(Wp + 1);
+    for (int kh = 0; kh < 3; ++kh) {
+      p.mma_b[0][kh] = (kh - 1) * Wp + 1 - p.x_row0[0];
+      p.mma_acc[kh] = kh;
+      for (int j = 0; j < 3; ++j) p.tap_of[0][kh][j] = kh * 3 + (2 - j);
+    }
+  } else if (R == 2) {          // two MMAs per filter row: (kw = 2,1) and (kw = 0, unused)
+    p.n_mma = p.n_acc = 6;
+    p.x_rows = kKT + 2 * (Wp + 1);
+    p.x_row0[0] = -(Wp + 1);
+    for (int kh = 0; kh < 3; ++kh) {
+      p.mma_b[0][2 * kh] = (kh - 1) * Wp + 1 - p.x_row0[0];
+      p.mma_b[0][2 * kh + 1] = (kh - 1) * Wp - 1 - p.x_row0[0];
+      p.mma_acc[2 * kh] = 2 * kh;
+      p.mma_acc[2 * kh + 1] = 2 * kh + 1;
+      p.tap_of[0][2 * kh][0] = kh * 3 + 2;
+      p.tap_of[0][2 * kh][1] = kh * 3 + 1;
+      p.tap_of[0][2 * kh + 1][0] = kh * 3 + 0;
+    }
+  } else {                      // full-height operand: one tap group per filter row, one MMA per tap
+    tap_groups = 3;
+    p.n_mma = p.n_acc = 3;
+    p.x_rows = kKT + 2;
+    for (int kh = 0; kh < 3; ++kh) {
+      p.x_row0[kh] = (kh - 1) * Wp - 1;
+      for (int kw = 0; kw < 3; ++kw) {
+        p.mma_b[kh][kw] = kw;
+        p.tap_of[kh][kw][0] = kh * 3 + kw;
+      }
+    }
+    for (int kw = 0; kw < 3; ++kw) p.mma_acc[kw] = kw;
+  }
+  if (p.x_rows > 256) { set_error("wgrad_tc: image too wide for one TMA box (Wp %d)", Wp); return 1; }
+  p.n_groups = p.m_blks * p.n_blks * tap_groups;
+  p.a_panel_bytes = ((uint32_t)(p.dz_rows * p.pitch_a) + 1023u) & ~1023u;
+  p.b_panel_bytes = ((uint32_t)(p.x_rows * p.pitch_b) + 1023u) & ~1023u;
+  p.stage_bytes = p.a_panels * p.a_panel_bytes + p.b_panels * p.b_panel_bytes;
+  p.lbo_a = R > 1 ? (uint32_t)p.pitch_a : p.a_panel_bytes;
+  p.lbo_b = p.b_panel_bytes;
+  p.stages = (int)((200u * 1024u) / p.stage_bytes);
+  if (p.stages > kMaxStagesW) p.stages = kMaxStagesW;
+  if (p.stages < 2) { set_error("wgrad_tc: stage too large"); return 1; }
+  int cols = p.n_acc * p.nt;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < cols) p.tmem_cols *= 2;
+  p.tiles_total = (int)((P + kLead + kKT - 1) / kKT);
+  p.n_splits = sm_count() / p.n_groups;
+  if (p.n_splits < 1) p.n_splits = 1;
+  if (p.n_splits > p.tiles_total) p.n_splits = p.tiles_total;
+  p.tiles_per_split = (p.tiles_total + p.n_splits - 1) / p.n_splits;
+  p.n_splits = (p.tiles_total + p.tiles_per_split - 1) / p.tiles_per_split;
+  if (encode_rows(&p.tmDz, dz, cout, P, cout < 64 ? cout : 64, p.dz_rows)) return 1;
+  if (encode_rows(&p.tmX, x, cin, P, cin < 64 ? cin : 64, p.x_rows)) return 1;
+
+  cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)cout * cin_real * k * k * sizeof(float), stream);
+  if (e != cudaSuccess) { set_error("wgrad_tc memset: %s", cudaGetErrorString(e)); return 1; }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  static bool attr = false;
+  if (!attr) {
+    e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    if (e != cudaSuccess) { set_error("wgrad_tc attribute: %s", cudaGetErrorString(e)); return 1; }
+    attr = true;
+  }
+  wgrad_tc_kernel<<<p.n_groups * p.n_splits, kThreadsW, smem, stream>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("wgrad_tc launch: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+}  // namespace stl

@@ -62,6 +62,22 @@ def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bi
     return out
 
 
+def conv_dgrad(dz, weight, n, h, w, cin_pad, stride):
+    """Gradient of a pad-k//2 convolution wrt its input, on padded bf16 tensors: dz [n,h/s+1,w/s+1,cout_pad] ->
+    dx [n,h+1,w+1,cin_pad].  Stride 1 is itself a convolution of dz with the spatially flipped, channel-transposed
+    filter and runs on the tcgen05 kernel; stride 2 (30 of the 293 layers) uses the CUDA-core gather kernel."""
+    L = _lib.lib()
+    cout, cin_real, k, _ = weight.shape
+    if stride == 1 and cin_real == cin_pad:
+        wt = weight.detach().float().flip(2, 3).transpose(0, 1).contiguous()       # [cin][cout][k][k]
+        wp, bp, cpad = _pack_weights(wt, dz.shape[3])
+        return _conv_raw(dz, wp, bp, cin_real, cpad, k, 1)
+    wp, _, cout_pad = _pack_weights(weight, cin_pad)
+    dx = torch.empty((n, h + 1, w + 1, cin_pad), dtype=torch.bfloat16, device=dz.device)
+    _lib.check(L.stl_conv_dgrad(_lib.ptr(dz), _lib.ptr(wp), _lib.ptr(dx), n, h, w, cin_pad, cout_pad, k, stride, _stream()))
+    return dx
+
+
 class _ConvBN(torch.autograd.Function):
     """conv (no bias) + train-mode BatchNorm [+ residual] [+ ReLU] on padded bf16 activations."""
 
@@ -83,14 +99,14 @@ class _ConvBN(torch.autograd.Function):
                                           BN_EPS, float(momentum), n, ho, wo, cout, _lib.ptr(y), _lib.ptr(sums),
                                           _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(run_mean), _lib.ptr(run_var),
                                           _stream()))
-        ctx.save_for_backward(x, wp, z, y, mean, rstd, g32)
+        ctx.save_for_backward(x, weight, z, y, mean, rstd, g32)
         ctx.meta = (n, h, w, cin_pad, cin_real, cout, k, stride, bool(relu), residual is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         L = _lib.lib()
-        x, wp, z, y, mean, rstd, g32 = ctx.saved_tensors
+        x, weight, z, y, mean, rstd, g32 = ctx.saved_tensors
         n, h, w, cin_pad, cin_real, cout, k, stride, relu, has_res = ctx.meta
         ho, wo = h // stride, w // stride
         dy = dy.contiguous()
@@ -103,9 +119,7 @@ class _ConvBN(torch.autograd.Function):
         dbeta, dgamma = sums[:cout].clone(), sums[cout:].clone()
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            _lib.check(L.stl_conv_dgrad(_lib.ptr(dz), _lib.ptr(wp), _lib.ptr(dx), n, h, w, cin_pad, cout, k, stride,
-                                        _stream()))
+            dx = conv_dgrad(dz, weight, n, h, w, cin_pad, stride)
         dw = torch.empty((cout, cin_real, k, k), dtype=torch.float32, device=x.device)
         _lib.check(L.stl_conv_wgrad(_lib.ptr(x), _lib.ptr(dz), _lib.ptr(dw), n, h, w, cin_pad, cout, k, stride,
                                     cin_real, _stream()))
@@ -122,20 +136,19 @@ class _Head(torch.autograd.Function):
         wp, bp, cout_pad = _pack_weights(weight, cin)
         bp[:cout] = bias.detach().float()
         heat = _conv_raw(x, wp, bp, cout, cout_pad, 1, 1, out_nchw=True)
-        ctx.save_for_backward(x, wp)
+        ctx.save_for_backward(x, weight)
         ctx.meta = (n, hp - 1, wpd - 1, cin, cout, cout_pad)
         return heat
 
     @staticmethod
     def backward(ctx, dheat):
         L = _lib.lib()
-        x, wp = ctx.saved_tensors
+        x, weight = ctx.saved_tensors
         n, h, w, cin, cout, cout_pad = ctx.meta
         dheat = dheat.contiguous().float()
         dz = torch.empty((n, h + 1, w + 1, cout_pad), dtype=torch.bfloat16, device=x.device)
         _lib.check(L.stl_nchw_to_padded(_lib.ptr(dheat), _lib.ptr(dz), n, cout, h, w, cout_pad, _stream()))
-        dx = torch.empty_like(x)
-        _lib.check(L.stl_conv_dgrad(_lib.ptr(dz), _lib.ptr(wp), _lib.ptr(dx), n, h, w, cin, cout_pad, 1, 1, _stream()))
+        dx = conv_dgrad(dz, weight, n, h, w, cin, 1)
         dw = torch.empty((cout_pad, cin, 1, 1), dtype=torch.float32, device=x.device)
         _lib.check(L.stl_conv_wgrad(_lib.ptr(x), _lib.ptr(dz), _lib.ptr(dw), n, h, w, cin, cout_pad, 1, 1, cin,
                                     _stream()))

@@ -1,7 +1,7 @@
 """Measure the accumulation error of the tcgen05 conv (fp32 NCHW output path) against an fp64 convolution."""
 import sys, os, ctypes
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import torch, torch.nn.functional as F
 from gpu_util import bf16_round, to_padded
 from stlpose_b200 import _lib

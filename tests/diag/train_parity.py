@@ -1,7 +1,7 @@
 """Diagnostic: device train step vs the fp32 oracle and vs the bf16-storage oracle (prints, asserts nothing)."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import torch
 from oracle import hrnet_oracle, pose_oracle
 import stlpose_b200 as S

@@ -136,3 +136,46 @@ def test_sum_relu_and_backward():
         _lib.check(L.stl_upsample_backward(_lib.ptr(gm), _lib.ptr(dlow), n, h, w, c, shift, _lib.current_stream()))
         want = F.avg_pool2d(_unpadded(gm), 1 << shift) * (1 << shift) ** 2
         assert (_unpadded(dlow) - want).abs().max().item() < 3e-2 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,cout,k,hw", [(32, 32, 3, (64, 48)), (64, 64, 3, (32, 24)), (128, 128, 3, (16, 12)),
+                                           (256, 256, 3, (8, 6)), (256, 64, 1, (64, 48)), (64, 256, 1, (64, 48)),
+                                           (256, 32, 3, (64, 48)), (128, 32, 1, (16, 12)), (256, 128, 1, (8, 6))])
+def test_stride1_dgrad_on_tensor_cores(cin, cout, k, hw):
+    """training.conv_dgrad (stride 1 = tcgen05 convolution with the flipped, transposed filter) vs autograd."""
+    from stlpose_b200 import training
+    n, (h, w) = 3, hw
+    g = torch.Generator(device=DEV).manual_seed(cin + cout + k)
+    wt = bf16_round(torch.randn(cout, cin, k, k, device=DEV, generator=g) / (cin * k * k) ** 0.5)
+    dz = bf16_round(torch.randn(n, cout, h, w, device=DEV, generator=g))
+    x = torch.zeros(n, cin, h, w, device=DEV, requires_grad=True)
+    F.conv2d(x, wt, None, 1, k // 2).backward(dz)
+    dx = training.conv_dgrad(_padded(dz), wt, n, h, w, cin, 1)
+    assert (_unpadded(dx) - x.grad).abs().max().item() < 2e-2 * max(1.0, x.grad.abs().max().item())
+    assert (dx[:, h] == 0).all() and (dx[:, :, w] == 0).all()
+
+
+@pytest.mark.parametrize("cin,cout,k,hw,n", [
+    (32, 32, 3, (64, 48), 3), (64, 64, 3, (32, 24), 3), (128, 128, 3, (16, 12), 5), (256, 256, 3, (8, 6), 7),
+    (64, 256, 1, (64, 48), 2), (256, 64, 1, (64, 48), 2), (256, 32, 3, (64, 48), 2), (128, 32, 1, (16, 12), 3),
+    (256, 128, 1, (8, 6), 3), (32, 32, 1, (64, 48), 2), (64, 64, 1, (64, 48), 1), (32, 32, 3, (16, 12), 1)])
+def test_stride1_wgrad_on_tensor_cores(cin, cout, k, hw, n):
+    """stl_conv_wgrad (tcgen05, pixels as the reduction dimension) vs autograd and vs the CUDA-core kernel."""
+    L = _lib.lib()
+    h, w = hw
+    g = torch.Generator(device=DEV).manual_seed(cin * 3 + cout + k)
+    x = bf16_round(torch.randn(n, cin, h, w, device=DEV, generator=g))
+    dz = bf16_round(torch.randn(n, cout, h, w, device=DEV, generator=g))
+    wr = torch.zeros(cout, cin, k, k, device=DEV, requires_grad=True)
+    F.conv2d(x, wr, None, 1, k // 2).backward(dz)
+    xp, dzp = _padded(x), _padded(dz)
+    dw = torch.full((cout, cin, k, k), 7.0, device=DEV)
+    _lib.check(L.stl_conv_wgrad(_lib.ptr(xp), _lib.ptr(dzp), _lib.ptr(dw), n, h, w, cin, cout, k, 1, cin,
+                                _lib.current_stream()))
+    dn = torch.empty_like(dw)
+    _lib.check(L.stl_conv_wgrad_naive(_lib.ptr(xp), _lib.ptr(dzp), _lib.ptr(dn), n, h, w, cin, cout, k, 1, cin,
+                                      _lib.current_stream()))
+    scale = wr.grad.abs().max().item()
+    assert (dn - wr.grad).abs().max().item() < 1e-3 * scale
+    err = (dw - wr.grad).abs().max().item()
+    assert err < 1e-3 * scale, (err, scale)
