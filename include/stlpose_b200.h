@@ -170,13 +170,16 @@ int stl_plan_op_info(const stl_plan* plan, int op_index, stl_op_info* info);
 /* nn.BatchNorm2d in training mode fused with the block's residual add and ReLU (HRnet.py:48-59, 85-100):
  *   batch mean / biased variance of z over N*H*W -> y = [relu](gamma*(z-mean)*rstd + beta [+ residual]);
  *   running_mean / running_var (may be null) updated with `momentum` and the unbiased variance.
- * sums: 2*C fp32 scratch; mean, rstd: C fp32 outputs kept for the backward. */
+ * sums: fp32 workspace of stl_bn_workspace_floats(C) elements (per-block partial sums; the reduction uses no
+ * floating-point atomics and is deterministic); sums[0:2C] holds the channel sums on return.
+ * mean, rstd: C fp32 outputs kept for the backward. */
+size_t stl_bn_workspace_floats(int C);
 int stl_bn_train_forward(const void* z, const float* gamma, const float* beta, const void* residual, int relu,
                          float eps, float momentum, int N, int H, int W, int C, void* y, float* sums, float* mean,
                          float* rstd, float* running_mean, float* running_var, void* stream);
 
-/* Backward of the same unit: g = dy masked by (y > 0) when relu; sums[0:C] = dbeta = sum g, sums[C:2C] = dgamma =
- * sum g*xhat; dz = gamma*rstd*(g - dbeta/cnt - xhat*dgamma/cnt); dres (may be null) = g. */
+/* Backward of the same unit: g = dy masked by (y > 0) when relu; sums (same workspace size as above): sums[0:C] =
+ * dbeta = sum g, sums[C:2C] = dgamma = sum g*xhat; dz = gamma*rstd*(g - dbeta/cnt - xhat*dgamma/cnt); dres (may be null) = g. */
 int stl_bn_train_backward(const void* dy, const void* y, const void* z, const float* mean, const float* rstd,
                           const float* gamma, int relu, int N, int H, int W, int C, void* dz, void* dres, float* sums,
                           void* stream);
@@ -190,15 +193,23 @@ int stl_relu_mask(const void* dy, const void* y, void* g, long long elems, void*
 /* gradient of a nearest-upsampled addend: dlow = sum of g over each 2^shift x 2^shift window. */
 int stl_upsample_backward(const void* g, void* dlow, int N, int H, int W, int C, int shift, void* stream);
 
+/* u[n,h,w] = dz[n,h/2,w/2] at even (h,w), 0 elsewhere: dz is padded-linear [N][H/2+1][W/2+1][C], u is [N][H+1][W+1][C].
+ * Gradients of a stride-2 convolution are the stride-1 gradients of the stuffed dz. */
+int stl_zero_stuff(const void* dz, void* u, int N, int H, int W, int C, void* stream);
+
 /* Convolution gradients (autograd of nn.Conv2d).  w_packed: [k*k][Cout][Cin] bf16 as produced by
  * stl_pack_conv_weights without BatchNorm.  dx: padded-linear bf16 [N][Hi+1][Wi+1][Cin];
  * dw: fp32 [Cout][cin_real][k][k] (OIHW), zeroed by the call. */
 int stl_conv_dgrad(const void* dz, const void* w_packed, void* dx, int N, int Hi, int Wi, int Cin, int Cout, int ksize,
                    int stride, void* stream);
+/* stl_conv_wgrad runs stride-1 problems with channel counts of 32/64/128/256 on the tcgen05 tensor cores (stride-2
+ * layers get there through stl_zero_stuff): every CTA accumulates a pixel range in TMEM and writes a slab of partial
+ * sums to `workspace` (stl_conv_wgrad_workspace_bytes, 0 when the CUDA-core kernel will be used); a second kernel adds
+ * the slabs in a fixed order, so the result is deterministic.  Other shapes (native stride 2, the 3-channel stem) use
+ * a CUDA-core kernel with fp32 atomics.  stl_conv_wgrad_naive forces the CUDA-core kernel (validation). */
+size_t stl_conv_wgrad_workspace_bytes(int N, int Hi, int Wi, int Cin, int Cout, int ksize, int stride, int cin_real);
 int stl_conv_wgrad(const void* x, const void* dz, float* dw, int N, int Hi, int Wi, int Cin, int Cout, int ksize,
-                   int stride, int cin_real, void* stream);
-/* stl_conv_wgrad runs stride-1 layers with channel counts of 32/64/128/256 on the tcgen05 tensor cores and the rest
- * (stride 2, the 3-channel stem) on a CUDA-core kernel; this entry forces the CUDA-core kernel (validation). */
+                   int stride, int cin_real, void* workspace, size_t workspace_bytes, void* stream);
 int stl_conv_wgrad_naive(const void* x, const void* dz, float* dw, int N, int Hi, int Wi, int Cin, int Cout, int ksize,
                          int stride, int cin_real, void* stream);
 

@@ -12,4 +12,5 @@ from .hrnet import PoseHighResolutionNet  # noqa: F401
 from .inference import forward_pass  # noqa: F401
 from .loss import PersonMSELoss  # noqa: F401
 from .pose_parsing import get_final_preds_hrnet, get_max_preds_hrnet  # noqa: F401
+from .train_step import TrainStep  # noqa: F401
 from .transforms import FLIP_PAIRS, flip_back  # noqa: F401

@@ -86,7 +86,10 @@ PROTOTYPES = {
     "stl_relu_mask": (ctypes.c_int, [vp, vp, vp, ctypes.c_longlong, vp]),
     "stl_upsample_backward": (ctypes.c_int, [vp, vp] + [ctypes.c_int] * 5 + [vp]),
     "stl_conv_dgrad": (ctypes.c_int, [vp, vp, vp] + [ctypes.c_int] * 7 + [vp]),
-    "stl_conv_wgrad": (ctypes.c_int, [vp, vp, vp] + [ctypes.c_int] * 8 + [vp]),
+    "stl_conv_wgrad_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 8),
+    "stl_conv_wgrad": (ctypes.c_int, [vp, vp, vp] + [ctypes.c_int] * 8 + [vp, ctypes.c_size_t, vp]),
+    "stl_bn_workspace_floats": (ctypes.c_size_t, [ctypes.c_int]),
+    "stl_zero_stuff": (ctypes.c_int, [vp, vp] + [ctypes.c_int] * 4 + [vp]),
     "stl_conv_wgrad_naive": (ctypes.c_int, [vp, vp, vp] + [ctypes.c_int] * 8 + [vp]),
 }
 

@@ -40,14 +40,25 @@ int check(const char* what) {
 // MODE 1: sums[c] = sum g, sums[C+c] = sum g * xhat                 (BatchNorm backward; g = dy masked by y > 0)
 // Zero cells of the padded layout contribute zero to every sum, so the kernel walks the flat tensor.
 // Block = 256 threads = (C/8 channel groups) x (256 / (C/8) pixel lanes); fp32 register partials, shared-memory
-// reduction over the pixel lanes, one atomicAdd per channel per block.
+// reduction over the pixel lanes, one row of per-block partials in global memory.  The last block to finish (ticket
+// counter) adds the rows in a fixed order -- no floating-point atomics, so the statistics are deterministic -- and, in
+// MODE 0, also derives mean / rstd and updates the running statistics (momentum, unbiased variance: nn.BatchNorm2d).
+constexpr int kReduceBlocks = 296;   // 2 per SM
+
+struct BnFinalize {
+  float count, eps, momentum;
+  float *mean, *rstd, *run_mean, *run_var;
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16* __restrict__ a,
                                                              const __nv_bfloat16* __restrict__ y,
                                                              const __nv_bfloat16* __restrict__ z,
                                                              const float* __restrict__ mean,
                                                              const float* __restrict__ rstd, long long pixels, int C,
-                                                             int relu_mask, float* __restrict__ sums) {
+                                                             int relu_mask, float* __restrict__ sums,
+                                                             float* __restrict__ partial, unsigned* __restrict__ counter,
+                                                             const BnFinalize fin) {
   const int c8n = C / 8;
   const int lanes = 256 / c8n;          // pixel lanes per block (C <= 2048 / 8 ... C/8 <= 256)
   const int cg = threadIdx.x % c8n, pl = threadIdx.x / c8n;
@@ -58,6 +69,7 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
     for (int i = 0; i < 8; ++i) { mu[i] = mean[cg * 8 + i]; rs[i] = rstd[cg * 8 + i]; }
   }
   if (pl < lanes) {
+#pragma unroll 4
     for (long long p = (long long)blockIdx.x * lanes + pl; p < pixels; p += (long long)gridDim.x * lanes) {
       const size_t off = (size_t)p * C + cg * 8;
       float f[8];
@@ -79,6 +91,7 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
     }
   }
   __shared__ float red[2][256][8 + 1];
+  __shared__ bool is_last;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { red[0][threadIdx.x][i] = s0[i]; red[1][threadIdx.x][i] = s1[i]; }
   __syncthreads();
@@ -86,28 +99,35 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
     for (int l = 1; l < lanes; ++l)
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s0[i] += red[0][l * c8n + cg][i]; s1[i] += red[1][l * c8n + cg][i]; }
+    float* row = partial + (size_t)blockIdx.x * 2 * C;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(sums + cg * 8 + i, s0[i]);
-      atomicAdd(sums + C + cg * 8 + i, s1[i]);
-    }
+    for (int i = 0; i < 8; ++i) { row[cg * 8 + i] = s0[i]; row[C + cg * 8 + i] = s1[i]; }
   }
-}
-
-// mean / rstd from the sums, running-statistics update (momentum, unbiased variance: nn.BatchNorm2d semantics)
-__global__ void bn_finalize_kernel(const float* __restrict__ sums, float count, float eps, float momentum, int C,
-                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ run_mean,
-                                   float* __restrict__ run_var) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
-    const float m = sums[c] / count;
-    float var = sums[C + c] / count - m * m;
-    var = var > 0.f ? var : 0.f;
-    mean[c] = m;
-    rstd[c] = rsqrtf(var + eps);
-    if (run_mean) {
-      const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
-      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m;
-      run_var[c] = (1.f - momentum) * run_var[c] + momentum * unbiased;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < 2 * C; c += 256) {
+    float acc = 0.f;
+    for (unsigned b2 = 0; b2 < gridDim.x; ++b2) acc += __ldcg(partial + (size_t)b2 * 2 * C + c);
+    sums[c] = acc;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+  if (MODE == 0) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      const float m = sums[c] / fin.count;
+      float var = sums[C + c] / fin.count - m * m;
+      var = var > 0.f ? var : 0.f;
+      fin.mean[c] = m;
+      fin.rstd[c] = rsqrtf(var + fin.eps);
+      if (fin.run_mean) {
+        const float unbiased = fin.count > 1.f ? var * fin.count / (fin.count - 1.f) : var;
+        fin.run_mean[c] = (1.f - fin.momentum) * fin.run_mean[c] + fin.momentum * m;
+        fin.run_var[c] = (1.f - fin.momentum) * fin.run_var[c] + fin.momentum * unbiased;
+      }
     }
   }
 }
@@ -268,7 +288,79 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const __nv_bfloat16* 
   }
 }
 
+// Zero-stuffing: u[n,h,w] = dz[n,h/2,w/2] where h and w are even, 0 elsewhere.  A stride-2 convolution is the stride-1
+// convolution sampled at even positions, so its input and weight gradients are the stride-1 ones of the stuffed dz.
+__global__ void __launch_bounds__(256) zero_stuff_kernel(const __nv_bfloat16* __restrict__ dz,
+                                                         __nv_bfloat16* __restrict__ u, int N, int H, int W, int C) {
+  const int c8n = C / 8, Wp = W + 1, Hp = H + 1, Wo = W / 2, Ho = H / 2;
+  const long long total = (long long)N * Hp * Wp * c8n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c8n);
+    const long long q = i / c8n;
+    const int w = (int)(q % Wp);
+    const long long t = q / Wp;
+    const int h = (int)(t % Hp), n = (int)(t / Hp);
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (h < H && w < W && !(h & 1) && !(w & 1)) {
+      const size_t qs = ((size_t)n * (Ho + 1) + (h >> 1)) * (Wo + 1) + (w >> 1);
+      out = *reinterpret_cast<const uint4*>(dz + qs * C + cg * 8);
+    }
+    *reinterpret_cast<uint4*>(u + (size_t)i * 8) = out;
+  }
+}
+
 // ------------------------------------------------------------------ CUDA-core convolution gradients
+// wgrad of the stem's first convolution (HRnet.py:286: 3 -> 64 channels, 3x3, stride 2): 1 728 outputs reduced over
+// N*Ho*Wo pixels.  Thread = (output channel, pixel lane); the 27 input values of a pixel are staged in shared memory
+// and broadcast, each thread keeps 27 fp32 accumulators; block partials are added with atomics (148*4 blocks).
+constexpr int kStemPix = 32;   // output pixels per block iteration
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const __nv_bfloat16* __restrict__ x,
+                                                         const __nv_bfloat16* __restrict__ dz,
+                                                         float* __restrict__ dw, int N, int Hi, int Wi, int Cin,
+                                                         int Cout, int cin_real, long long pix_total) {
+  __shared__ float patch[kStemPix][28];
+  const int Ho = Hi / 2, Wo = Wi / 2, Wip = Wi + 1, Hip = Hi + 1, Wop = Wo + 1, Hop = Ho + 1;
+  const int co = threadIdx.x % 64, lane4 = threadIdx.x / 64;          // 4 pixel lanes x 64 channels
+  float acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  for (long long p0 = (long long)blockIdx.x * kStemPix; p0 < pix_total; p0 += (long long)gridDim.x * kStemPix) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kStemPix * 27; i += 256) {
+      const int pp = i / 27, r = i % 27, tap = r / 3, ci = r % 3;
+      const long long pix = p0 + pp;
+      float v = 0.f;
+      if (pix < pix_total && ci < cin_real) {
+        const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+        const int h = 2 * ho + tap / 3 - 1, w = 2 * wo + tap % 3 - 1;
+        if (h >= 0 && h < Hi && w >= 0 && w < Wi) v = __bfloat162float(x[(((size_t)n * Hip + h) * Wip + w) * Cin + ci]);
+      }
+      patch[pp][r] = v;
+    }
+    __syncthreads();
+    for (int pp = lane4; pp < kStemPix; pp += 4) {
+      const long long pix = p0 + pp;
+      if (pix >= pix_total) break;
+      const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+      const float g = __bfloat162float(dz[(((size_t)n * Hop + ho) * Wop + wo) * Cout + co]);
+#pragma unroll
+      for (int i = 0; i < 27; ++i) acc[i] += g * patch[pp][i];
+    }
+  }
+  __shared__ float red[4][64][28];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) red[lane4][co][i] = acc[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 27; i += 256) {
+    const int c = i / 27, r = i % 27, tap = r / 3, ci = r % 3;
+    if (ci >= cin_real) continue;
+    const float v = red[0][c][r] + red[1][c][r] + red[2][c][r] + red[3][c][r];
+    atomicAdd(dw + ((size_t)c * cin_real + ci) * 9 + tap, v);
+  }
+}
+
+
 // dgrad for any (k, stride): dx[n,h,w,ci] = sum_{kh,kw,co} dz[n,ho,wo,co] * W[co,ci,kh,kw] with ho*stride+kh-pad = h.
 // One thread per (pixel, 8 input channels); weights [taps][cout][cin] bf16 (the forward packing, unscaled).
 __global__ void __launch_bounds__(128) conv_dgrad_kernel(const __nv_bfloat16* __restrict__ dz,
@@ -371,19 +463,20 @@ int grid_for(long long total, int block, int cap = 148 * 16) {
 
 }  // namespace
 
+size_t bn_workspace_floats(int C) { return (size_t)2 * C * (1 + kReduceBlocks) + 32; }
+
 int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* beta, const __nv_bfloat16* residual,
                      int relu, float eps, float momentum, int N, int H, int W, int C, __nv_bfloat16* y, float* sums,
                      float* mean, float* rstd, float* run_mean, float* run_var, cudaStream_t st) {
   if (C % 8 || C > 2048) { set_error("bn_train_forward: C=%d unsupported", C); return 1; }
   const long long pixels = (long long)N * (H + 1) * (W + 1);
-  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st);
+  unsigned* counter = reinterpret_cast<unsigned*>(sums + (size_t)2 * C * (1 + kReduceBlocks));
+  cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   const int lanes = 256 / (C / 8);
-  channel_reduce_kernel<0><<<grid_for(pixels, lanes, 148 * 4), 256, 0, st>>>(z, nullptr, nullptr, nullptr, nullptr,
-                                                                            pixels, C, 0, sums);
+  BnFinalize fin{(float)((long long)N * H * W), eps, momentum, mean, rstd, run_mean, run_var};
+  channel_reduce_kernel<0><<<grid_for(pixels, lanes * 4, kReduceBlocks), 256, 0, st>>>(
+      z, nullptr, nullptr, nullptr, nullptr, pixels, C, 0, sums, sums + 2 * C, counter, fin);
   if (check("bn stats")) return 1;
-  bn_finalize_kernel<<<1, 256, 0, st>>>(sums, (float)((long long)N * H * W), eps, momentum, C, mean, rstd, run_mean,
-                                        run_var);
-  if (check("bn finalize")) return 1;
   bn_apply_kernel<<<grid_for(pixels * (C / 8), 256), 256, 0, st>>>(z, mean, rstd, gamma, beta, residual, relu, y, N, H,
                                                                   W, C);
   return check("bn apply");
@@ -394,10 +487,11 @@ int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __n
                       __nv_bfloat16* dz, __nv_bfloat16* dres, float* sums, cudaStream_t st) {
   if (C % 8 || C > 2048) { set_error("bn_train_backward: C=%d unsupported", C); return 1; }
   const long long pixels = (long long)N * (H + 1) * (W + 1);
-  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st);
+  unsigned* counter = reinterpret_cast<unsigned*>(sums + (size_t)2 * C * (1 + kReduceBlocks));
+  cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   const int lanes = 256 / (C / 8);
-  channel_reduce_kernel<1><<<grid_for(pixels, lanes, 148 * 4), 256, 0, st>>>(dy, y, z, mean, rstd, pixels, C, relu,
-                                                                            sums);
+  channel_reduce_kernel<1><<<grid_for(pixels, lanes * 4, kReduceBlocks), 256, 0, st>>>(
+      dy, y, z, mean, rstd, pixels, C, relu, sums, sums + 2 * C, counter, BnFinalize{});
   if (check("bn backward reduce")) return 1;
   bn_backward_kernel<<<grid_for(pixels * (C / 8), 256), 256, 0, st>>>(dy, y, z, mean, rstd, gamma, sums,
                                                                      (float)((long long)N * H * W), relu, dz, dres, N,
@@ -437,9 +531,24 @@ int conv_dgrad_naive(const __nv_bfloat16* dz, const __nv_bfloat16* w_packed, __n
   return check("conv_dgrad");
 }
 
+int zero_stuff(const __nv_bfloat16* dz, __nv_bfloat16* u, int N, int H, int W, int C, cudaStream_t st) {
+  if (C % 8 || (H & 1) || (W & 1)) { set_error("zero_stuff: C %% 8 and even H, W required"); return 1; }
+  const long long total = (long long)N * (H + 1) * (W + 1) * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  zero_stuff_kernel<<<(int)blocks, 256, 0, st>>>(dz, u, N, H, W, C);
+  return check("zero_stuff");
+}
+
 int conv_wgrad_naive(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, int N, int Hi, int Wi, int Cin,
                      int Cout, int k, int stride, int cin_real, cudaStream_t st) {
   if (Cin % 16 || Cout % 16) { set_error("conv_wgrad: channels must be multiples of 16"); return 1; }
+  if (k == 3 && stride == 2 && Cout == 64 && cin_real <= 3) {      // the stem's first convolution
+    const long long pix = (long long)N * (Hi / 2) * (Wi / 2);
+    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * cin_real * 9, st);
+    stem_wgrad_kernel<<<grid_for(pix, kStemPix, 148 * 4), 256, 0, st>>>(x, dz, dw, N, Hi, Wi, Cin, Cout, cin_real, pix);
+    return check("stem_wgrad");
+  }
   const int tiles = k * k * (Cin / 16) * (Cout / 16);
   const long long pix = (long long)N * (Hi / stride) * (Wi / stride);
   int slices = (148 * 8 + tiles - 1) / tiles;

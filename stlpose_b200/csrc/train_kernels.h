@@ -5,6 +5,7 @@
 
 namespace stl {
 
+size_t bn_workspace_floats(int C);
 int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* beta, const __nv_bfloat16* residual,
                      int relu, float eps, float momentum, int N, int H, int W, int C, __nv_bfloat16* y, float* sums,
                      float* mean, float* rstd, float* run_mean, float* run_var, cudaStream_t st);
@@ -16,6 +17,7 @@ int sum_relu_forward(const __nv_bfloat16* const* same, int n_same, const __nv_bf
 int relu_mask(const __nv_bfloat16* dy, const __nv_bfloat16* y, __nv_bfloat16* g, long long elems, cudaStream_t st);
 int upsample_backward(const __nv_bfloat16* g, __nv_bfloat16* dlow, int N, int H, int W, int C, int shift,
                       cudaStream_t st);
+int zero_stuff(const __nv_bfloat16* dz, __nv_bfloat16* u, int N, int H, int W, int C, cudaStream_t st);
 int conv_dgrad_naive(const __nv_bfloat16* dz, const __nv_bfloat16* w_packed, __nv_bfloat16* dx, int N, int Hi, int Wi,
                      int Cin, int Cout, int k, int stride, cudaStream_t st);
 int conv_wgrad_naive(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, int N, int Hi, int Wi, int Cin,
@@ -23,7 +25,8 @@ int conv_wgrad_naive(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw,
 
 // tcgen05 weight gradient for stride-1 convolutions (wgrad_tc.cu)
 bool wgrad_tc_supported(int W, int cin, int cout, int cin_real, int k, int stride);
+size_t wgrad_tc_workspace_bytes(int N, int H, int W, int cin, int cout, int k, int cin_real);
 int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, int N, int H, int W, int cin, int cout,
-                    int k, int cin_real, cudaStream_t stream);
+                    int k, int cin_real, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 }  // namespace stl

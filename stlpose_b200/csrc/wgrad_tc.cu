@@ -47,6 +47,7 @@ struct WgradParams {
   int tap_of[3][kMaxMma][4];      // filter tap produced by (group, accumulator, replica) or -1
   int tiles_total, tiles_per_split, n_splits;
   float* dw;
+  float* ws;                      // [grid][n_acc][128][nt] fp32 partial sums, one slab per CTA
   int co, ci, ci_real, taps;
 };
 
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
           for (int a = 0; a < p.a_panels; ++a)
             tma_load_2d_s(a_dst + a * p.a_panel_bytes, &p.tmDz, &full_bar[s], m_blk * 128 + a * 64, q0);
           for (int b = 0; b < p.b_panels; ++b)
-            tma_load_2d_s(b_dst + b * p.b_panel_bytes, &p.tmX, &full_bar[s], n_blk * 128 + b * 64, q0 + p.x_row0[tg]);
+            tma_load_2d_s(b_dst + b * p.b_panel_bytes, &p.tmX, &full_bar[s], n_blk * p.nt + b * 64, q0 + p.x_row0[tg]);
         }
       }
     } else if (warp == 1) {
@@ -140,24 +141,23 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
         __syncwarp();
       }
     } else {
-      // ------------------------------------------------------------ epilogue: TMEM -> red.global into dW (OIHW fp32)
+      // ------------------------------------------------------------ epilogue: TMEM -> this CTA's slab of partial sums
       mbar_wait(&done_bar, 0);
       tc_fence_after();
       const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
       const int row = quad * 32 + lane;                // accumulator row
       const int rep = row / p.m_real;
-      const int co = m_blk * 128 + row % p.m_real;
+      float* slab = p.ws + (size_t)blockIdx.x * p.n_acc * 128 * p.nt;
       for (int a = 0; a < p.n_acc; ++a) {
-        const int tap = p.tap_of[tg][a][rep];
+        const bool valid = p.tap_of[tg][a][rep] >= 0;
         for (int c0 = 0; c0 < p.nt; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.nt + c0), v);
           tmem_ld_wait();
-          if (tap >= 0 && co < p.co) {
-            float* dst = p.dw + ((size_t)co * p.ci_real + (size_t)(n_blk * 128 + c0)) * p.taps + tap;
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(slab + ((size_t)a * 128 + row) * p.nt + c0);
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (n_blk * 128 + c0 + c < p.ci_real) atomicAdd(dst + (size_t)c * p.taps, __uint_as_float(v[c]));
+            for (int c = 0; c < 8; ++c) dst[c] = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           }
         }
       }
@@ -168,6 +168,25 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// Sum of the per-CTA slabs over the pixel splits, in a fixed order (deterministic), scattered to OIHW.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgradParams p) {
+  const int per_group = p.n_acc * 128 * p.nt;
+  const int total = p.n_groups * per_group;
+  const int tap_groups = p.n_groups / (p.m_blks * p.n_blks);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int group = i / per_group, r = i % per_group;
+    const int a = r / (128 * p.nt), row = (r / p.nt) % 128, col = r % p.nt;
+    const int tg = group % tap_groups, mn = group / tap_groups;
+    const int n_blk = mn % p.n_blks, m_blk = mn / p.n_blks;
+    const int tap = p.tap_of[tg][a][row / p.m_real];
+    const int co = m_blk * 128 + row % p.m_real, ci = n_blk * p.nt + col;
+    if (tap < 0 || co >= p.co || ci >= p.ci_real) continue;
+    float acc = 0.f;
+    for (int sp = 0; sp < p.n_splits; ++sp) acc += __ldcg(p.ws + ((size_t)sp * p.n_groups + group) * per_group + r);
+    p.dw[((size_t)co * p.ci_real + ci) * p.taps + tap] = acc;
   }
 }
 
@@ -216,29 +235,46 @@ int sm_count() {
 
 }  // namespace
 
-bool wgrad_tc_supported(int W, int cin, int cout, int cin_real, int k, int stride) {
+namespace {
+struct WgradShape { int m_real, R, nt, n_acc, per_kh; };
+bool wgrad_shape(int W, int cin, int cout, int cin_real, int k, int stride, WgradShape* o) {
   if (stride != 1 || (k != 1 && k != 3)) return false;
-  if (k == 3 && cout < 128 && kKT + 2 * (W + 2) > 256) return false;     // halo'd x tile must fit one TMA box
   if (cout % 32 || cin % 32 || cin_real > cin) return false;
   if (cout > 64 && cout % 128) return false;
-  if (cin > 64 && cin % 128) return false;
-  const int m_real = cout < 128 ? cout : 128, R = 128 / m_real, nt = cin < 128 ? cin : 128;
-  const int n_acc = k == 1 ? 1 : (R >= 3 ? 3 : (R == 2 ? 6 : 3));
-  return n_acc * nt <= 512;
+  o->m_real = cout < 128 ? cout : 128;
+  o->R = 128 / o->m_real;
+  // one CTA covers all nine taps when the halo'd x tile fits a TMA box (<= 256 rows); otherwise one filter row per CTA
+  o->per_kh = k == 3 && (o->R == 1 || kKT + 2 * (W + 2) > 256);
+  if (k == 1) o->n_acc = 1;
+  else if (o->per_kh) o->n_acc = o->R >= 3 ? 1 : (o->R == 2 ? 2 : 3);
+  else o->n_acc = o->R >= 3 ? 3 : 6;
+  o->nt = 0;
+  for (int nt = 128; nt >= 32; nt /= 2)
+    if (nt <= cin && cin % nt == 0 && o->n_acc * nt <= 512) { o->nt = nt; break; }
+  return o->nt != 0;
+}
+}  // namespace
+
+bool wgrad_tc_supported(int W, int cin, int cout, int cin_real, int k, int stride) {
+  WgradShape sh;
+  return wgrad_shape(W, cin, cout, cin_real, k, stride, &sh);
 }
 
-int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, int N, int H, int W, int cin, int cout,
-                    int k, int cin_real, cudaStream_t stream) {
-  if (!wgrad_tc_supported(W, cin, cout, cin_real, k, 1)) { set_error("wgrad_tc: unsupported shape"); return 1; }
-  WgradParams p{};
+namespace {
+// Everything but the tensor maps and buffers.
+int wgrad_setup(int N, int H, int W, int cin, int cout, int k, int cin_real, WgradParams* pp) {
+  WgradShape sh;
+  if (!wgrad_shape(W, cin, cout, cin_real, k, 1, &sh)) { set_error("wgrad_tc: unsupported shape"); return 1; }
+  WgradParams& p = *pp;
   const int Wp = W + 1;
   const long long P = (long long)N * (H + 1) * Wp;
-  p.co = cout; p.ci = cin; p.ci_real = cin_real; p.taps = k * k; p.dw = dw;
-  p.m_real = cout < 128 ? cout : 128;
-  const int R = 128 / p.m_real;
+  p.co = cout; p.ci = cin; p.ci_real = cin_real; p.taps = k * k;
+  p.m_real = sh.m_real;
+  const int R = sh.R;
   p.m_blks = (cout + 127) / 128;
-  p.n_blks = (cin + 127) / 128;
-  p.nt = cin < 128 ? cin : 128;
+  p.nt = sh.nt;
+  p.n_blks = cin / p.nt;
+  p.n_acc = sh.n_acc;
   p.pitch_a = (cout < 64 ? cout : 64) * 2;
   p.pitch_b = (cin < 64 ? cin : 64) * 2;
   p.a_panels = p.m_real > 64 ? 2 : 1;
@@ -248,47 +284,54 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, 
   for (int g = 0; g < 3; ++g)
     for (int m = 0; m < kMaxMma; ++m)
       for (int j = 0; j < 4; ++j) p.tap_of[g][m][j] = -1;
+  for (int m = 0; m < kMaxMma; ++m) p.mma_acc[m] = m;
   if (k == 1) {
-    p.n_mma = p.n_acc = 1;
+    p.n_mma = 1;
     p.x_rows = kKT;
     p.x_row0[0] = 0;
     p.mma_b[0][0] = 0;
-    p.mma_acc[0] = 0;
     p.tap_of[0][0][0] = 0;
-  } else if (R >= 3) {          // one MMA per filter row: replicas 0,1,2 -> kw = 2,1,0
-    p.n_mma = p.n_acc = 3;
+  } else if (!sh.per_kh && R >= 3) {   // one MMA per filter row: replicas 0,1,2 -> kw = 2,1,0
+    p.n_mma = 3;
     p.x_rows = kKT + 2 * (Wp + 1);
     p.x_row0[0] = -(Wp + 1);
     for (int kh = 0; kh < 3; ++kh) {
       p.mma_b[0][kh] = (kh - 1) * Wp + 1 - p.x_row0[0];
-      p.mma_acc[kh] = kh;
       for (int j = 0; j < 3; ++j) p.tap_of[0][kh][j] = kh * 3 + (2 - j);
     }
-  } else if (R == 2) {          // two MMAs per filter row: (kw = 2,1) and (kw = 0, unused)
-    p.n_mma = p.n_acc = 6;
+  } else if (!sh.per_kh) {             // R == 2: two MMAs per filter row: (kw = 2,1) and (kw = 0, unused)
+    p.n_mma = 6;
     p.x_rows = kKT + 2 * (Wp + 1);
     p.x_row0[0] = -(Wp + 1);
     for (int kh = 0; kh < 3; ++kh) {
       p.mma_b[0][2 * kh] = (kh - 1) * Wp + 1 - p.x_row0[0];
       p.mma_b[0][2 * kh + 1] = (kh - 1) * Wp - 1 - p.x_row0[0];
-      p.mma_acc[2 * kh] = 2 * kh;
-      p.mma_acc[2 * kh + 1] = 2 * kh + 1;
       p.tap_of[0][2 * kh][0] = kh * 3 + 2;
       p.tap_of[0][2 * kh][1] = kh * 3 + 1;
       p.tap_of[0][2 * kh + 1][0] = kh * 3 + 0;
     }
-  } else {                      // full-height operand: one tap group per filter row, one MMA per tap
+  } else {                             // one tap group (CTA) per filter row; x tile = rows [q0 + (kh-1)Wp - 2, +KT+4)
     tap_groups = 3;
-    p.n_mma = p.n_acc = 3;
-    p.x_rows = kKT + 2;
+    p.x_rows = kKT + 4;
+    p.n_mma = p.n_acc;
     for (int kh = 0; kh < 3; ++kh) {
-      p.x_row0[kh] = (kh - 1) * Wp - 1;
-      for (int kw = 0; kw < 3; ++kw) {
-        p.mma_b[kh][kw] = kw;
-        p.tap_of[kh][kw][0] = kh * 3 + kw;
+      p.x_row0[kh] = (kh - 1) * Wp - 2;
+      if (R >= 3) {
+        p.mma_b[kh][0] = 3;
+        for (int j = 0; j < 3; ++j) p.tap_of[kh][0][j] = kh * 3 + (2 - j);
+      } else if (R == 2) {
+        p.mma_b[kh][0] = 3;
+        p.mma_b[kh][1] = 1;
+        p.tap_of[kh][0][0] = kh * 3 + 2;
+        p.tap_of[kh][0][1] = kh * 3 + 1;
+        p.tap_of[kh][1][0] = kh * 3 + 0;
+      } else {
+        for (int kw = 0; kw < 3; ++kw) {
+          p.mma_b[kh][kw] = kw + 1;
+          p.tap_of[kh][kw][0] = kh * 3 + kw;
+        }
       }
     }
-    for (int kw = 0; kw < 3; ++kw) p.mma_acc[kw] = kw;
   }
   if (p.x_rows > 256) { set_error("wgrad_tc: image too wide for one TMA box (Wp %d)", Wp); return 1; }
   p.n_groups = p.m_blks * p.n_blks * tap_groups;
@@ -309,11 +352,34 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, 
   if (p.n_splits > p.tiles_total) p.n_splits = p.tiles_total;
   p.tiles_per_split = (p.tiles_total + p.n_splits - 1) / p.n_splits;
   p.n_splits = (p.tiles_total + p.tiles_per_split - 1) / p.tiles_per_split;
+  return 0;
+}
+size_t slab_bytes(const WgradParams& p) {
+  return (size_t)p.n_groups * p.n_splits * p.n_acc * 128 * p.nt * sizeof(float);
+}
+}  // namespace
+
+size_t wgrad_tc_workspace_bytes(int N, int H, int W, int cin, int cout, int k, int cin_real) {
+  WgradParams p{};
+  if (wgrad_setup(N, H, W, cin, cout, k, cin_real, &p)) return 0;
+  return slab_bytes(p);
+}
+
+int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, int N, int H, int W, int cin, int cout,
+                    int k, int cin_real, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  WgradParams p{};
+  if (wgrad_setup(N, H, W, cin, cout, k, cin_real, &p)) return 1;
+  if (!workspace || workspace_bytes < slab_bytes(p)) {
+    set_error("wgrad_tc: workspace of %zu bytes required (stl_conv_wgrad_workspace_bytes), got %zu", slab_bytes(p),
+              workspace_bytes);
+    return 1;
+  }
+  p.dw = dw;
+  p.ws = static_cast<float*>(workspace);
+  const long long P = (long long)N * (H + 1) * (W + 1);
   if (encode_rows(&p.tmDz, dz, cout, P, cout < 64 ? cout : 64, p.dz_rows)) return 1;
   if (encode_rows(&p.tmX, x, cin, P, cin < 64 ? cin : 64, p.x_rows)) return 1;
-
-  cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)cout * cin_real * k * k * sizeof(float), stream);
-  if (e != cudaSuccess) { set_error("wgrad_tc memset: %s", cudaGetErrorString(e)); return 1; }
+  cudaError_t e;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   static bool attr = false;
   if (!attr) {
@@ -324,6 +390,10 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, 
   wgrad_tc_kernel<<<p.n_groups * p.n_splits, kThreadsW, smem, stream>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("wgrad_tc launch: %s", cudaGetErrorString(e)); return 1; }
+  const int total = p.n_groups * p.n_acc * 128 * p.nt;
+  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("wgrad_reduce launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;
 }
 

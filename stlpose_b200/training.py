@@ -62,13 +62,40 @@ def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bi
     return out
 
 
+def zero_stuff(dz, n, h, w):
+    """dz of a stride-2 convolution -> full-resolution tensor with dz at the even positions and zeros elsewhere; the
+    stride-2 gradients are then the stride-1 gradients (tensor-core kernels) of the stuffed tensor."""
+    u = torch.empty((n, h + 1, w + 1, dz.shape[3]), dtype=torch.bfloat16, device=dz.device)
+    _lib.check(_lib.lib().stl_zero_stuff(_lib.ptr(dz), _lib.ptr(u), n, h, w, dz.shape[3], _stream()))
+    return u
+
+
+def conv_wgrad(x, dz, weight_shape, n, h, w, stride):
+    """Gradient wrt the OIHW weights (fp32).  `dz` may already be zero-stuffed for a stride-2 layer."""
+    L = _lib.lib()
+    cout, cin_real, k, _ = weight_shape
+    cin_pad, cout_pad = x.shape[3], dz.shape[3]
+    dw = torch.empty((cout_pad, cin_real, k, k), dtype=torch.float32, device=x.device)
+    stuffed = dz.shape[1] == h + 1
+    if stride == 2 and not stuffed and cin_pad % 32 == 0 and cout_pad % 32 == 0:
+        dz, stuffed = zero_stuff(dz, n, h, w), True
+    s_eff = 1 if stuffed else stride
+    ws_bytes = L.stl_conv_wgrad_workspace_bytes(n, h, w, cin_pad, cout_pad, k, s_eff, cin_real)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+    _lib.check(L.stl_conv_wgrad(_lib.ptr(x), _lib.ptr(dz), _lib.ptr(dw), n, h, w, cin_pad, cout_pad, k, s_eff, cin_real,
+                                _lib.ptr(ws), ws_bytes, _stream()))
+    return dw if cout_pad == cout else dw[:cout].contiguous()
+
+
 def conv_dgrad(dz, weight, n, h, w, cin_pad, stride):
     """Gradient of a pad-k//2 convolution wrt its input, on padded bf16 tensors: dz [n,h/s+1,w/s+1,cout_pad] ->
     dx [n,h+1,w+1,cin_pad].  Stride 1 is itself a convolution of dz with the spatially flipped, channel-transposed
     filter and runs on the tcgen05 kernel; stride 2 (30 of the 293 layers) uses the CUDA-core gather kernel."""
     L = _lib.lib()
     cout, cin_real, k, _ = weight.shape
-    if stride == 1 and cin_real == cin_pad:
+    if stride == 2 and cin_real == cin_pad and dz.shape[1] != h + 1:
+        dz = zero_stuff(dz, n, h, w)
+    if cin_real == cin_pad and dz.shape[1] == h + 1:
         wt = weight.detach().float().flip(2, 3).transpose(0, 1).contiguous()       # [cin][cout][k][k]
         wp, bp, cpad = _pack_weights(wt, dz.shape[3])
         return _conv_raw(dz, wp, bp, cin_real, cpad, k, 1)
@@ -91,7 +118,7 @@ class _ConvBN(torch.autograd.Function):
         z = _conv_raw(x, wp, bp, cout, cout_pad, k, stride)
         ho, wo = h // stride, w // stride
         y = torch.empty_like(z)
-        sums = torch.empty(2 * cout, dtype=torch.float32, device=x.device)
+        sums = torch.empty(L.stl_bn_workspace_floats(cout), dtype=torch.float32, device=x.device)
         mean = torch.empty(cout, dtype=torch.float32, device=x.device)
         rstd = torch.empty(cout, dtype=torch.float32, device=x.device)
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
@@ -112,17 +139,15 @@ class _ConvBN(torch.autograd.Function):
         dy = dy.contiguous()
         dz = torch.empty_like(z)
         dres = torch.empty_like(z) if has_res else None
-        sums = torch.empty(2 * cout, dtype=torch.float32, device=x.device)
+        sums = torch.empty(L.stl_bn_workspace_floats(cout), dtype=torch.float32, device=x.device)
         _lib.check(L.stl_bn_train_backward(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(z), _lib.ptr(mean), _lib.ptr(rstd),
                                            _lib.ptr(g32), int(relu), n, ho, wo, cout, _lib.ptr(dz), _lib.ptr(dres),
                                            _lib.ptr(sums), _stream()))
-        dbeta, dgamma = sums[:cout].clone(), sums[cout:].clone()
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx = conv_dgrad(dz, weight, n, h, w, cin_pad, stride)
-        dw = torch.empty((cout, cin_real, k, k), dtype=torch.float32, device=x.device)
-        _lib.check(L.stl_conv_wgrad(_lib.ptr(x), _lib.ptr(dz), _lib.ptr(dw), n, h, w, cin_pad, cout, k, stride,
-                                    cin_real, _stream()))
+        dbeta, dgamma = sums[:cout].clone(), sums[cout:2 * cout].clone()
+        if stride == 2 and cin_pad % 32 == 0:
+            dz = zero_stuff(dz, n, h, w)               # shared by dgrad and wgrad
+        dx = conv_dgrad(dz, weight, n, h, w, cin_pad, stride) if ctx.needs_input_grad[0] else None
+        dw = conv_wgrad(x, dz, weight.shape, n, h, w, stride)
         return dx, dw, dgamma, dbeta, dres, None, None, None, None, None
 
 
@@ -149,10 +174,8 @@ class _Head(torch.autograd.Function):
         dz = torch.empty((n, h + 1, w + 1, cout_pad), dtype=torch.bfloat16, device=x.device)
         _lib.check(L.stl_nchw_to_padded(_lib.ptr(dheat), _lib.ptr(dz), n, cout, h, w, cout_pad, _stream()))
         dx = conv_dgrad(dz, weight, n, h, w, cin, 1)
-        dw = torch.empty((cout_pad, cin, 1, 1), dtype=torch.float32, device=x.device)
-        _lib.check(L.stl_conv_wgrad(_lib.ptr(x), _lib.ptr(dz), _lib.ptr(dw), n, h, w, cin, cout_pad, 1, 1, cin,
-                                    _stream()))
-        return dx, dw[:cout].contiguous(), dheat.sum(dim=(0, 2, 3))
+        dw = conv_wgrad(x, dz, weight.shape, n, h, w, 1)
+        return dx, dw, dheat.sum(dim=(0, 2, 3))
 
 
 class _FuseSum(torch.autograd.Function):

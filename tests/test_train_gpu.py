@@ -174,3 +174,35 @@ def test_sgd_step_reduces_loss():
         opt.step()
         losses.append(loss.item())
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_graph_captured_step_matches_eager_steps():
+    """TrainStep (forward + loss + backward + SGD update replayed as one CUDA graph) vs the same steps issued eagerly."""
+    S, sd0, x, tgt, tw, m_eager = _setup(B=4, seed=5)
+    m_graph = S.PoseHighResolutionNet(width=32)
+    m_graph.load_state_dict(sd0, strict=True)
+    m_graph = m_graph.cuda()
+    mk = lambda m: torch.optim.SGD(m.parameters(), lr=0.02, momentum=0.9, weight_decay=5e-4)
+    opt_e, crit = mk(m_eager), S.PersonMSELoss()
+    step = S.TrainStep(m_graph, mk(m_graph), crit, batch=4)
+    assert step.graph is not None
+    for k, v in m_graph.state_dict().items():            # warm-up and capture left the checkpoint untouched
+        assert torch.equal(v.cpu(), sd0[k]), k
+    m_eager.train()
+    xs, tg, tws = x.cuda(), tgt.cuda(), tw.cuda()
+    le, lg = [], []
+    for _ in range(3):
+        out = S.forward_pass(m_eager, xs, "HRNet", device="cuda", flip=False)
+        loss = crit(out, tg, tws)
+        opt_e.zero_grad(); loss.backward(); opt_e.step()
+        le.append(loss.item())
+        lg.append(step(x, tgt, tw).item())                # host tensors in, device loss out
+    assert all(abs(a - b) < 2e-2 * abs(a) for a, b in zip(le, lg)), (le, lg)
+    assert lg[-1] < lg[0]
+    sd_e, sd_g = m_eager.state_dict(), m_graph.state_dict()
+    assert int(sd_g["bn1.num_batches_tracked"]) == 3
+    for k in ("conv1.weight", "stage4.2.branches.0.3.conv2.weight", "final_layer.weight", "bn1.running_var"):
+        assert _rel(sd_g[k].cpu(), sd_e[k].cpu()) < 2e-2, k
+    m_graph.eval()                                         # folded weights are rebuilt from the trained parameters
+    m_eager.eval()
+    assert _rel(m_graph(xs).cpu(), m_eager(xs).cpu()) < 5e-2

@@ -36,7 +36,7 @@ def test_bn_train_forward_backward(shape, relu, with_res):
     rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
     zp = _padded(z)
     y = torch.empty_like(zp)
-    sums = torch.empty(2 * c, device=DEV); mean = torch.empty(c, device=DEV); rstd = torch.empty(c, device=DEV)
+    sums = torch.empty(L.stl_bn_workspace_floats(c), device=DEV); mean = torch.empty(c, device=DEV); rstd = torch.empty(c, device=DEV)
     resp = _padded(res) if with_res else None
     _lib.check(L.stl_bn_train_forward(_lib.ptr(zp), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(resp), int(relu), 1e-5, 0.1,
                                       n, h, w, c, _lib.ptr(y), _lib.ptr(sums), _lib.ptr(mean), _lib.ptr(rstd),
@@ -60,14 +60,14 @@ def test_bn_train_forward_backward(shape, relu, with_res):
     yr.backward(dy)
     dyp = _padded(dy)
     dz = torch.empty_like(zp); dres = torch.empty_like(zp) if with_res else None
-    sums2 = torch.empty(2 * c, device=DEV)
+    sums2 = torch.empty(L.stl_bn_workspace_floats(c), device=DEV)
     _lib.check(L.stl_bn_train_backward(_lib.ptr(dyp), _lib.ptr(y), _lib.ptr(zp), _lib.ptr(mean), _lib.ptr(rstd),
                                        _lib.ptr(gamma), int(relu), n, h, w, c, _lib.ptr(dz), _lib.ptr(dres),
                                        _lib.ptr(sums2), _lib.current_stream()))
     scale = max(1.0, zr.grad.abs().max().item())
     assert (_unpadded(dz) - zr.grad).abs().max().item() < 3e-2 * scale
     assert (sums2[:c] - br.grad).abs().max().item() < 2e-2 * max(1.0, br.grad.abs().max().item())
-    assert (sums2[c:] - gr.grad).abs().max().item() < 2e-2 * max(1.0, gr.grad.abs().max().item())
+    assert (sums2[c:2 * c] - gr.grad).abs().max().item() < 2e-2 * max(1.0, gr.grad.abs().max().item())
     if with_res:
         assert (_unpadded(dres) - rr.grad).abs().max().item() < 1e-2
 
@@ -101,8 +101,10 @@ def test_conv_gradients(case):
     dx = torch.empty_like(xp)
     _lib.check(L.stl_conv_dgrad(_lib.ptr(dzp), _lib.ptr(wp), _lib.ptr(dx), n, h, w, cin, cout, k, s, _lib.current_stream()))
     dw = torch.empty((cout, cin_real, k, k), device=DEV)
+    wsb = L.stl_conv_wgrad_workspace_bytes(n, h, w, cin, cout, k, s, cin_real)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=DEV)
     _lib.check(L.stl_conv_wgrad(_lib.ptr(xp), _lib.ptr(dzp), _lib.ptr(dw), n, h, w, cin, cout, k, s, cin_real,
-                                _lib.current_stream()))
+                                _lib.ptr(ws), wsb, _lib.current_stream()))
     got_dx = _unpadded(dx)[:, :cin_real]
     assert (got_dx - xr.grad).abs().max().item() < 2e-2 * max(1.0, xr.grad.abs().max().item())
     assert (dx[:, h] == 0).all() and (dx[:, :, w] == 0).all()
@@ -170,8 +172,15 @@ def test_stride1_wgrad_on_tensor_cores(cin, cout, k, hw, n):
     F.conv2d(x, wr, None, 1, k // 2).backward(dz)
     xp, dzp = _padded(x), _padded(dz)
     dw = torch.full((cout, cin, k, k), 7.0, device=DEV)
+    wsb = L.stl_conv_wgrad_workspace_bytes(n, h, w, cin, cout, k, 1, cin)
+    assert wsb > 0                                       # tensor-core path
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
     _lib.check(L.stl_conv_wgrad(_lib.ptr(xp), _lib.ptr(dzp), _lib.ptr(dw), n, h, w, cin, cout, k, 1, cin,
-                                _lib.current_stream()))
+                                _lib.ptr(ws), wsb, _lib.current_stream()))
+    dw2 = torch.empty_like(dw)
+    _lib.check(L.stl_conv_wgrad(_lib.ptr(xp), _lib.ptr(dzp), _lib.ptr(dw2), n, h, w, cin, cout, k, 1, cin,
+                                _lib.ptr(ws), wsb, _lib.current_stream()))
+    assert torch.equal(dw, dw2)                          # fixed-order reduction: bit-reproducible
     dn = torch.empty_like(dw)
     _lib.check(L.stl_conv_wgrad_naive(_lib.ptr(xp), _lib.ptr(dzp), _lib.ptr(dn), n, h, w, cin, cout, k, 1, cin,
                                       _lib.current_stream()))
@@ -179,3 +188,26 @@ def test_stride1_wgrad_on_tensor_cores(cin, cout, k, hw, n):
     assert (dn - wr.grad).abs().max().item() < 1e-3 * scale
     err = (dw - wr.grad).abs().max().item()
     assert err < 1e-3 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("cin,cout,hw,n", [(32, 64, (64, 48), 2), (64, 128, (32, 24), 3), (32, 32, (64, 48), 2),
+                                           (128, 256, (16, 12), 3), (256, 64, (64, 48), 2), (64, 64, (128, 96), 2),
+                                           (32, 128, (32, 24), 2), (64, 256, (16, 12), 2), (32, 256, (16, 12), 2)])
+def test_stride2_gradients_via_zero_stuffing(cin, cout, hw, n):
+    """Stride-2 3x3 layers: zero-stuffed dz + the stride-1 tensor-core dgrad / wgrad kernels vs autograd."""
+    from stlpose_b200 import training
+    h, w = hw
+    g = torch.Generator(device=DEV).manual_seed(cin + 7 * cout)
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, device=DEV, generator=g) / (cin * 9) ** 0.5)
+    x = bf16_round(torch.randn(n, cin, h, w, device=DEV, generator=g))
+    dz = bf16_round(torch.randn(n, cout, h // 2, w // 2, device=DEV, generator=g))
+    xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+    F.conv2d(xr, wr, None, 2, 1).backward(dz)
+    dzp = _padded(dz)
+    u = training.zero_stuff(dzp, n, h, w)
+    assert (u[:, h] == 0).all() and (u[:, :, w] == 0).all() and (u[:, 1::2] == 0).all() and (u[:, :, 1::2] == 0).all()
+    assert torch.equal(u[:, 0:h:2, 0:w:2], dzp[:, :h // 2, :w // 2])
+    dx = training.conv_dgrad(dzp, wt, n, h, w, cin, 2)
+    assert (_unpadded(dx) - xr.grad).abs().max().item() < 2e-2 * max(1.0, xr.grad.abs().max().item())
+    dw = training.conv_wgrad(_padded(x), dzp, wt.shape, n, h, w, 2)
+    assert (dw - wr.grad).abs().max().item() < 1e-3 * wr.grad.abs().max().item()

@@ -10,43 +10,51 @@ def main():
     ap.add_argument("--batches", default="32,64,128")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--width", type=int, default=32)
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (TrainStep)")
     a = ap.parse_args()
-    torch.manual_seed(0)
-    m = S.PoseHighResolutionNet(width=a.width).cuda().train()
-    opt = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9, weight_decay=5e-4)      # model_setup.py:138-139
     crit = S.PersonMSELoss()
     flops = 45.8e9 if a.width == 32 else None
     for B in [int(b) for b in a.batches.split(",")]:
+        torch.manual_seed(0)
+        m = S.PoseHighResolutionNet(width=a.width).cuda().train()        # fresh per batch size (one TrainStep per optimizer)
+        opt = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9, weight_decay=5e-4)      # model_setup.py:138-139
         g = torch.Generator(device="cuda").manual_seed(0)
         x = torch.randn(B, 3, 256, 192, device="cuda", generator=g)
         tgt = torch.rand(B, 17, 64, 48, device="cuda", generator=g)
         tw = torch.tensor([0.0, 1.0, 1.2, 1.5], device="cuda")[torch.randint(0, 4, (B, 17, 1), device="cuda", generator=g)]
-        def step():
-            out = S.forward_pass(m, x, "HRNet", device="cuda", flip=False)
-            loss = crit(out, tgt, tw)
-            opt.zero_grad()
-            loss.backward()
-            opt.step()
-            return loss
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        for _ in range(2):
+        fwd = bwd = upd = None
+        if a.graph:
+            gstep = S.TrainStep(m, opt, crit, batch=B)
+            step = lambda: gstep(x, tgt, tw)
+        else:
+            def step():
+                out = S.forward_pass(m, x, "HRNet", device="cuda", flip=False)
+                loss = crit(out, tgt, tw)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                return loss.detach()
+        for _ in range(3):
             step()
         torch.cuda.synchronize()
-        # phase split on one extra step
-        ev[0].record(); out = S.forward_pass(m, x, "HRNet", device="cuda", flip=False); loss = crit(out, tgt, tw)
-        ev[1].record(); opt.zero_grad(); loss.backward(); ev[2].record(); opt.step(); ev[3].record()
-        torch.cuda.synchronize()
-        fwd, bwd, upd = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
+        if not a.graph:                                                  # phase split on one extra eager step
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record(); out = S.forward_pass(m, x, "HRNet", device="cuda", flip=False); loss = crit(out, tgt, tw)
+            ev[1].record(); opt.zero_grad(); loss.backward(); ev[2].record(); opt.step(); ev[3].record()
+            torch.cuda.synchronize()
+            fwd, bwd, upd = (round(ev[i].elapsed_time(ev[i + 1]), 2) for i in range(3))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(a.steps):
             loss = step()
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.steps
-        line = dict(workload=f"hrnet_w{a.width}_256x192 train step", batch=B, ms_per_step=round(ms, 2),
-                    crops_per_s=round(B / ms * 1e3, 1), fwd_ms=round(fwd, 2), bwd_ms=round(bwd, 2), opt_ms=round(upd, 2),
+        line = dict(workload=f"hrnet_w{a.width}_256x192 train step (fwd + PersonMSELoss + bwd + SGD)", graph=bool(a.graph),
+                    batch=B, ms_per_step=round(ms, 2), crops_per_s=round(B / ms * 1e3, 1), fwd_ms=fwd, bwd_ms=bwd, opt_ms=upd,
                     tflops=round(flops * B / ms / 1e9, 1) if flops else None, loss=float(loss))
         print(json.dumps(line))
+        del m, opt
+        torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":
