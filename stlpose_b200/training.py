@@ -52,8 +52,12 @@ def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bi
     d = _lib.ConvDesc()
     d.in_ = x.data_ptr(); d.N, d.H, d.W, d.Cin = n, h, w, cin
     if out is None:
-        out = (torch.empty((n, cout, ho, wo), dtype=torch.float32, device=x.device) if out_nchw
-               else _padded_zeros(n, ho, wo, cout, x.device))
+        if out_nchw:
+            out = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=x.device)
+        elif stride == 1:      # flat-pixel tiles write every cell of the output, zero cells included
+            out = torch.empty((n, ho + 1, wo + 1, cout), dtype=torch.bfloat16, device=x.device)
+        else:                  # structured stride-2 tiles write the valid pixels only
+            out = _padded_zeros(n, ho, wo, cout, x.device)
     d.out = out.data_ptr(); d.Cout, d.Cout_pad = cout, cout_pad
     d.ksize, d.stride = k, stride
     d.w_packed = wp.data_ptr(); d.bias_packed = (bias if bias is not None else bp).data_ptr()
