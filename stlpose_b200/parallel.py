@@ -72,3 +72,111 @@ class ShardedKeypointInference:
             preds = torch.zeros((0, J, 2), dtype=torch.float32, device=dev)
             maxvals = torch.zeros((0, J, 1), dtype=torch.float32, device=dev)
         return gather_keypoints(preds, maxvals, n, self.group)
+
+
+class GradientReducer:
+    """The one exchange step of data-parallel fine-tuning (replaces DataParallel's replicate / gather / reduce of
+    02_train.py:109,203-218): every rank runs forward + backward on its own slice of the batch with its own BatchNorm
+    batch statistics (as DataParallel's replicas do), then the parameter gradients are summed over the ranks.
+
+    The reference computes ONE loss over the gathered batch (loss.py:87 averages over all B crops), so a rank that
+    averaged over its B_r local crops contributes its gradient scaled by B_r / B.  Gradients are packed into flat fp32
+    buckets in reverse parameter order (the order backward produces them) and each bucket is all-reduced as soon as
+    its last gradient exists (``attach_hooks``: overlaps the remaining backward kernels), or all at once after a
+    graph-replayed backward (``reduce_all``).  Works on NCCL (CUDA) and gloo (CPU) process groups.
+
+    BatchNorm running statistics are not exchanged: like the reference, which keeps the statistics of GPU 0's
+    replica, every rank keeps its own and rank 0's are the ones to checkpoint.
+    """
+
+    def __init__(self, params, local_batch, group=None, bucket_bytes=32 << 20):
+        self.group = group
+        self.params = [p for p in params if p.requires_grad]
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        dev = self.params[0].device
+        total = torch.tensor([float(local_batch)], device=dev)
+        if self.world > 1:
+            dist.all_reduce(total, group=group)
+        self.scale = float(local_batch) / float(total.item())
+        self.global_batch = int(round(total.item()))
+        # buckets in reverse registration order
+        self.buckets, cur, cur_bytes = [], [], 0
+        for p in reversed(self.params):
+            cur.append(p)
+            cur_bytes += p.numel() * 4
+            if cur_bytes >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.flat = [torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=dev) for b in self.buckets]
+        self.bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self._pending = [0] * len(self.buckets)
+        self._works = []
+        self._hooks = []
+        self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+
+    # ---- one bucket: pack (scaled) -> all-reduce -> unpack
+    def _launch(self, i):
+        bucket, flat = self.buckets[i], self.flat[i]
+        views = list(torch.split(flat, [p.numel() for p in bucket]))
+        grads = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in bucket]
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream(flat.device))
+            ctx = torch.cuda.stream(self.comm_stream)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            torch._foreach_copy_(views, grads)
+            flat.mul_(self.scale)
+            work = dist.all_reduce(flat, group=self.group, async_op=True) if self.world > 1 else None
+        self._works.append((i, work))
+
+    def _finish(self):
+        for i, work in self._works:
+            if work is not None:
+                work.wait()          # NCCL: makes the current stream wait for the collective
+            bucket, flat = self.buckets[i], self.flat[i]
+            views = torch.split(flat, [p.numel() for p in bucket])
+            if self.comm_stream is not None:
+                torch.cuda.current_stream(flat.device).wait_stream(self.comm_stream)
+            for p, v in zip(bucket, views):
+                if p.grad is None:
+                    p.grad = v.view_as(p).clone()
+                else:
+                    p.grad.copy_(v.view_as(p))
+        self._works = []
+
+    def reduce_all(self):
+        """All buckets, after backward has finished (graph-replayed steps)."""
+        for i in range(len(self.buckets)):
+            self._launch(i)
+        self._finish()
+
+    def attach_hooks(self):
+        """Eager steps: all-reduce each bucket as soon as backward has produced its last gradient; call
+        ``finish_step()`` after ``loss.backward()`` and before ``optimizer.step()``."""
+        self._pending = [len(b) for b in self.buckets]
+
+        def hook(p):
+            i = self.bucket_of[id(p)]
+            self._pending[i] -= 1
+            if self._pending[i] == 0:
+                self._launch(i)
+
+        for p in self.params:
+            self._hooks.append(p.register_post_accumulate_grad_hook(hook))
+        return self
+
+    def finish_step(self):
+        for i, n in enumerate(self._pending):          # parameters that received no gradient this step
+            if n != 0 and not any(j == i for j, _ in self._works):
+                self._launch(i)
+        self._finish()
+        self._pending = [len(b) for b in self.buckets]
+
+    def detach_hooks(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

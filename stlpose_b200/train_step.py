@@ -19,12 +19,15 @@ from .inference import forward_pass
 
 
 class TrainStep:
-    def __init__(self, model, optimizer, criterion, batch, image_size=(256, 192), joints=17, use_graph=True, warmup=3):
+    def __init__(self, model, optimizer, criterion, batch, image_size=(256, 192), joints=17, use_graph=True, warmup=3,
+                 reducer=None):
+        """reducer: a ``parallel.GradientReducer`` for data-parallel runs (one process per GPU).  The graph then holds
+        forward + loss + backward of this rank's slice; the gradient all-reduce and the optimizer step follow it."""
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("TrainStep needs the model on a CUDA device (there is no CPU fallback)")
         H, W = image_size
-        self.model, self.optimizer, self.criterion = model, optimizer, criterion
+        self.model, self.optimizer, self.criterion, self.reducer = model, optimizer, criterion, reducer
         self.x = torch.zeros((batch, 3, H, W), dtype=torch.float32, device=dev)
         self.target = torch.zeros((batch, joints, H // 4, W // 4), dtype=torch.float32, device=dev)
         self.target_weight = torch.ones((batch, joints, 1), dtype=torch.float32, device=dev)
@@ -39,6 +42,7 @@ class TrainStep:
             with torch.cuda.stream(side):                      # warm-up: lazy optimizer state, one-time attributes
                 for _ in range(warmup):
                     self._eager()
+                    self._exchange_and_update()
             torch.cuda.current_stream(dev).wait_stream(side)
             self._restore(snapshot)                            # warm-up steps must not count as training
             self.optimizer.zero_grad(set_to_none=True)
@@ -66,9 +70,15 @@ class TrainStep:
         loss = self.criterion(out, self.target, self.target_weight)
         self.optimizer.zero_grad()
         loss.backward()
-        self.optimizer.step()
+        if self.reducer is None:
+            self.optimizer.step()
         self.output = out.detach()
         self.loss.copy_(loss.detach())
+
+    def _exchange_and_update(self):
+        if self.reducer is not None:
+            self.reducer.reduce_all()
+            self.optimizer.step()
 
     def __call__(self, imgs, target, target_weight):
         """Copies the batch into the static buffers (host or device sources), runs the step, returns the device loss."""
@@ -79,5 +89,6 @@ class TrainStep:
             self.graph.replay()
         else:
             self._eager()
+        self._exchange_and_update()
         self.model.invalidate_packed_weights()
         return self.loss

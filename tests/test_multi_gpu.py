@@ -1,0 +1,74 @@
+"""Data-parallel fine-tuning step on 2 GPUs (NCCL): per-rank forward/backward on a slice of the batch, GradientReducer
+all-reduce weighted by the slice sizes, identical SGD update on both ranks.  Needs >= 2 GPUs (gpurun --gpus 2);
+skipped on the single-GPU box of the regular GPU tier."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import test_train_gpu as T
+        import stlpose_b200 as S
+        from stlpose_b200.parallel import GradientReducer
+        B, lr = 6, 0.05
+        bounds = [(0, 4), (4, 6)]
+        S_, sd0, x, tgt, tw, m = T._setup(B, seed=11)          # same checkpoint and batch on both ranks
+        lo, hi = bounds[rank]
+        opt = torch.optim.SGD(m.parameters(), lr=lr)
+        red = GradientReducer(m.parameters(), local_batch=hi - lo)
+        assert red.global_batch == B
+        step = S.TrainStep(m, opt, S.PersonMSELoss(), batch=hi - lo, reducer=red)
+        step(x[lo:hi], tgt[lo:hi], tw[lo:hi])
+        torch.cuda.synchronize()
+        names = ["conv1.weight", "layer1.0.conv1.weight", "stage3.1.branches.2.1.bn2.weight", "final_layer.weight"]
+        sd = dict(m.named_parameters())
+        same = True
+        for n in names:
+            mine = sd[n].detach().clone()
+            both = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(both, mine)
+            same = same and torch.equal(both[0], both[1])
+        ok_ref = True
+        if rank == 0:                                          # expected update from the two slices' own gradients
+            grads = []
+            for (a, b) in bounds:
+                ref = S.PoseHighResolutionNet(width=32)
+                ref.load_state_dict(sd0, strict=True)
+                ref = ref.cuda().train()
+                S.PersonMSELoss()(ref(x[a:b].cuda()), tgt[a:b].cuda(), tw[a:b].cuda()).backward()
+                grads.append({k: p.grad.clone() for k, p in ref.named_parameters()})
+            for n in names:
+                g = grads[0][n] * (4 / B) + grads[1][n] * (2 / B)
+                want = sd0[n].cuda() - lr * g
+                err = (sd[n].detach() - want).norm() / (lr * g).norm().clamp_min(1e-12)
+                ok_ref = ok_ref and err.item() < 2e-2
+        q.put((rank, bool(same), bool(ok_ref)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_train_step_matches_weighted_slice_gradients():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    results = sorted(q.get(timeout=10) for _ in procs)
+    assert results == [(0, True, True), (1, True, True)], results
