@@ -45,6 +45,8 @@ struct ConvSpec {
   int force_tap_reload = 0;                // 1: one aligned TMA load per filter tap instead of shifted descriptors
   int force_mb = 0;
   int max_ctas = 0;
+  int pdl = 0;                             // 1: programmatic dependent launch (weights and bias must not be produced
+                                           //    by the preceding kernel in the stream; activations may be)
   int img_lo = 0, img_hi = 0;              // stride-1 convs only: restrict the launch to images [img_lo, img_hi) (0,0 = all)
   void* dbg_counters = nullptr;            // optional [grid][3][4] int64 cycle counters (measurement aid)
 };
@@ -111,6 +113,7 @@ struct ConvParams {
   int relu;
   int out_nchw;
   int cout, cout_pad;
+  int pdl;                // launched with programmatic stream serialization
   int dbg_skip_epilogue;  // measurement only
   long long* dbg_counters;  // measurement only: [grid][3 roles][4] cycle counters, or null
 };

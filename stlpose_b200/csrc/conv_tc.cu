@@ -233,6 +233,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const long long tstride = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
   auto mtile = [&](long long t) { return PAIR ? 2 * (t / p.n_ntiles) + cta_rank : t / p.n_ntiles; };
 
+  // Programmatic dependent launch: let the next layer's CTAs take over SMs as ours retire and run their prologue
+  // (barriers, TMEM, resident weights); everything that touches activations waits for the previous layer below.
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&ctl->a_full[i], 1); mbar_init(&ctl->a_empty[i], p.n_mma); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->b_empty[i], 1); }
@@ -264,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     mbar_wait(&ctl->b_full[0], 0);
     cluster_sync();  // both halves are in place before the leader's first MMA reads them
   }
+  if (warp != 0) pdl_wait();   // (the producer warp first queues the resident weights, which no kernel produces)
 
 #ifdef STL_CONV_COUNTERS
   long long dbg[4] = {0, 0, 0, 0};
@@ -291,6 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int tap = 0; tap < TAPS; ++tap, dst += p.b_stage_bytes)
             tma_load_3d_s(dst, &p.tmB, &ctl->b_full[0], chunk * p.ck, nti * p.nt, tap);
     }
+    pdl_wait();
     __syncwarp();
 #pragma unroll 1
     for (long long tile = tile0; tile < p.total_tiles; tile += tstride) {
@@ -1012,6 +1017,7 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   for (int i = 0; i < kMaxUp; ++i) { p.up_src[i] = s.up_src[i]; p.up_shift[i] = s.up_shift[i]; }
   p.relu = s.relu;
   p.out_nchw = s.out_nchw;
+  p.pdl = s.pdl;
   p.dbg_skip_epilogue = getenv("STL_DBG_SKIP_EPILOGUE") ? 1 : (getenv("STL_DBG_SKIP_STORE") ? 2 : 0);
   p.dbg_counters = reinterpret_cast<long long*>(s.dbg_counters);
   p.cout = s.cout;
@@ -1095,21 +1101,30 @@ int conv_launch_prepared(const ConvParams& p, int grid, size_t smem_bytes, cudaS
   ConvKernel kern = pick_kernel(p.mb, p.ck / 16, p.taps, epi_kind(p), p.pair != 0);
   if (!kern) { set_error("conv: no kernel for mb %d ck %d taps %d nchw %d", p.mb, p.ck, p.taps, p.out_nchw); return 1; }
   cudaError_t e;
-  if (p.pair) {
+  if (p.pair || p.pdl) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (p.pair) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (p.pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     e = cudaLaunchKernelEx(&cfg, kern, p);
-    if (e != cudaSuccess) { set_error("conv_tc_kernel (pair) launch: %s", cudaGetErrorString(e)); return 1; }
+    if (e != cudaSuccess) { set_error("conv_tc_kernel (attributed) launch: %s", cudaGetErrorString(e)); return 1; }
   } else {
     kern<<<grid, kThreads, smem_bytes, stream>>>(p);
   }

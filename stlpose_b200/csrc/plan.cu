@@ -299,6 +299,8 @@ int Plan::bind(int n_images, const void* arena, void* workspace, size_t ws_bytes
     group_subs[g] = subs;
   }
   const uint8_t* wbase = reinterpret_cast<const uint8_t*>(arena);
+  // programmatic dependent launch between consecutive layers (the weight arena is static during a forward)
+  const int use_pdl = getenv("STLPOSE_PDL") ? atoi(getenv("STLPOSE_PDL")) : 1;
   prepared.assign(ops.size(), std::vector<Prepared>());
   for (size_t i = 0; i < ops.size(); ++i) {
     const Op& op = ops[i];
@@ -324,6 +326,7 @@ int Plan::bind(int n_images, const void* arena, void* workspace, size_t ws_bytes
     s.relu = op.relu;
     s.out_nchw = op.out_nchw;
     s.force_tap_reload = tap_reload;
+    s.pdl = use_pdl;
     const int subs = op.group >= 0 ? group_subs[op.group] : 1;
     prepared[i].resize(subs);
     const int chunk = (n_images + subs - 1) / subs;

@@ -280,6 +280,12 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// wait: all prerequisite grids have completed and their memory is visible (no-op without the launch attribute).
+// launch_dependents: the next kernel in the stream may start launching (it still waits before touching our output).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor for a K-major operand whose rows are exactly one swizzle span wide
 // (span = 32, 64 or 128 bytes): 8-row groups are contiguous, so SBO = 8 * span; LBO is unused for
