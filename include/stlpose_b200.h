@@ -54,6 +54,28 @@ int stl_decode(const float* heat, const float* heat_flipped, const float* center
  *   loss = 0.5/(J*B*hw) * sum (tw*(out-tgt))^2 ;  grad = tw^2*(out-tgt)/(J*B*hw)   (grad may be null)
  * out/tgt [B][J][hw] fp32, tw [B][J] fp32, loss: 1 float.  workspace: stl_mse_workspace_bytes() bytes. */
 size_t stl_mse_workspace_bytes(void);
+/* Crop extraction, the step in front of the network: TransformDetection.__call__ / crop
+ * (lib/transforms.py:30-58, 259-268) and JointsDataset.__getitem__ (data/JointsDataset.py:189-197) call
+ * cv2.warpAffine(img, M, (out_w, out_h), flags=INTER_LINEAR) per box.  img: uint8 [img_h][img_w][3] on the device;
+ * minv: [N][6] float64 on the device, the INVERTED 2x3 matrices (crop -> image) exactly as cv2.warpAffine derives them;
+ * outputs (either may be null): uint8 [N][3][out_h][out_w], and the network input fp32 [N][3][out_h][out_w] =
+ * (v/255 - mean[c]) / std[c] (ToTensor + Normalize; mean3_host / std3_host: 3 host floats each, null = 0 / 1).
+ * OpenCV's fixed-point bilinear arithmetic is reproduced bit for bit. */
+int stl_warp_affine_crops(const void* img_u8_hwc, int img_h, int img_w, const double* minv, int N, int out_h, int out_w,
+                          void* out_u8_nchw, float* out_f32_nchw, const float* mean3_host, const float* std3_host,
+                          void* stream);
+
+/* PCK accuracy of the training / evaluation loops (lib/metrics.py:268-364 accuracy -> calc_dists -> dist_acc, called at
+ * 02_train.py:223,277 and 03_evaluate.py:142 on output.cpu()): pred_coords / target_coords are the [B][J][2] arg-max
+ * coordinates of the predicted and the ground-truth heatmaps (stl_decode with refine = 0).  A joint is counted when its
+ * target has x > 1 and y > 1 and is a hit when ||(pred - target) / (h/10, w/10)|| < thr.  acc: [J+1] (acc[0] = mean of
+ * the per-joint accuracies that are >= 0, acc[1+j] = hits/counted or -1), avg_acc: 1 float, cnt: 1 int. */
+int stl_pck_accuracy(const float* pred_coords, const float* target_coords, int B, int J, int h, int w, float thr,
+                     float* acc, float* avg_acc, int* cnt, void* stream);
+
+/* x[0:n] *= *scale_dev unless *scale_dev == 1 (then no memory is touched): applies autograd's upstream gradient of the
+ * loss to the gradient stl_mse_loss_fwd_bwd already produced, without a host read of the scalar. */
+int stl_scale_inplace(float* x, const float* scale_dev, long long n, void* stream);
 int stl_mse_loss_fwd_bwd(const float* out, const float* tgt, const float* tw, int B, int J, int hw, float* loss,
                          float* grad, void* workspace, void* stream);
 

@@ -50,7 +50,71 @@ class _TwoShotModel:
         return r
 
 
+def pck_inputs():
+    """Predicted / ground-truth heatmaps for the PCK fixture: blobs whose predicted peak is displaced by 0-4 pixels,
+    some joints unlabeled (all-zero target -> arg-max (0,0) -> not counted), one joint never labeled."""
+    rng = np.random.default_rng(77)
+    B, J, h, w = 6, 17, 64, 48
+    tgt = np.zeros((B, J, h, w), np.float32)
+    out = (rng.standard_normal((B, J, h, w)) * 0.05).astype(np.float32)
+    for n in range(B):
+        for j in range(J):
+            if j == 5 or rng.random() < 0.2:
+                continue
+            x, y = int(rng.integers(0, w)), int(rng.integers(0, h))
+            tgt[n, j, y, x] = 1.0
+            dx, dy = rng.integers(-4, 5, size=2)
+            out[n, j, min(max(y + dy, 0), h - 1), min(max(x + dx, 0), w - 1)] += 1.0
+    return out, tgt
+
+
+def make_pck():
+    """PCK fixture: the reference's own calc_dists / dist_acc (source text, see ref_shim.metrics_functions) on the
+    arg-max coordinates produced by the reference's get_max_preds_hrnet."""
+    L, M = ref_shim.lib(), ref_shim.metrics_functions()
+    out, tgt = pck_inputs()
+    pred, _ = L.pose_parsing.get_max_preds_hrnet(out)
+    tcoord, _ = L.pose_parsing.get_max_preds_hrnet(tgt)
+    norm = np.ones((pred.shape[0], 2)) * np.array([out.shape[2], out.shape[3]]) / 10      # metrics.py:347
+    dists = M.calc_dists(pred, tcoord, norm)
+    per_joint = np.array([M.dist_acc(dists[j]) for j in range(out.shape[1])], np.float64)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "pck.npz"), dists=dists, per_joint=per_joint, pred=pred)
+    print("pck per-joint", np.round(per_joint, 3))
+
+
+def crop_inputs():
+    """A 427x640 uint8 image (smooth ramps + blobs + sparse texture, so the fixture compresses) and person boxes that
+    cover: a plain box, fractional coordinates, boxes leaving the image on every side, a wide box (aspect fix-up)."""
+    rng = np.random.default_rng(2024)
+    H, W = 427, 640
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = np.stack([(xx * 255 // W), (yy * 255 // H), ((xx + yy) % 256)], axis=2).astype(np.float64)
+    for _ in range(40):
+        cx, cy, r = rng.uniform(0, W), rng.uniform(0, H), rng.uniform(5, 40)
+        img += rng.uniform(-120, 120, size=3) * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * r * r))[..., None]
+    tex = rng.integers(-60, 60, size=(H // 4 + 1, W // 4 + 1, 3)).repeat(4, 0).repeat(4, 1)[:H, :W]
+    img = np.clip(img + tex, 0, 255).astype(np.uint8)
+    boxes = [[50, 30, 210, 400], [300.5, 100.2, 420.7, 380.1], [-20, -10, 120, 200], [500, 300, 700, 500],
+             [10, 10, 630, 100]]
+    return img, boxes
+
+
+def make_crops():
+    """Crop-extraction fixture: the reference's TransformDetection.__call__ (cv2.warpAffine inside) and crop() with a
+    rotation, run here with OpenCV 4.13."""
+    L = ref_shim.lib()
+    img, boxes = crop_inputs()
+    dets, centers, scales = L.transforms.TransformDetection()(img, boxes)
+    rot = L.transforms.crop(img, centers[1], scales[1], np.array([192, 256]), rot=30)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "crops.npz"), dets=dets, centers=centers, scales=scales, rot30=rot)
+    print("crops", dets.shape, dets.dtype, "mean", dets.mean())
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "pck":
+        return make_pck()
+    if len(sys.argv) > 1 and sys.argv[1] == "crops":
+        return make_crops()
     if not ref_shim.available():
         sys.exit("reference not available; goldens can only be generated in the build container")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -94,6 +158,8 @@ def main():
             y = m(torch.from_numpy(g[key]))
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"hrnet_w{width}_fwd.npz"), y=y.numpy())
         print(f"w{width}: y range [{y.min():.3f}, {y.max():.3f}] std {y.std():.3f}")
+    make_pck()
+    make_crops()
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))
 

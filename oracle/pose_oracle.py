@@ -126,6 +126,194 @@ def person_mse_loss(output, target, target_weight):
     return loss, grad
 
 
+# ----------------------------------------------------------------------------------------------
+# crop extraction (the step before the hot path): lib/transforms.py:14-82, 197-233, 259-268
+# ----------------------------------------------------------------------------------------------
+def coords2cs(coords, det_width=192, det_height=256):
+    """TransformDetection._coords2cs, lib/transforms.py:60-82: (xmin,ymin,xmax,ymax) -> (center f32[2], scale f32[2])."""
+    xmin, ymin, xmax, ymax = coords
+    aspect = det_width * 1.0 / det_height
+    w, h = (xmax - xmin), (ymax - ymin)
+    center = np.zeros((2), dtype=np.float32)
+    center[0] = xmin + w * 0.5
+    center[1] = ymin + h * 0.5
+    if w > aspect * h:
+        h = w * 1.0 / aspect
+    elif w < aspect * h:
+        w = h * aspect
+    scale = np.array([w * 1.0 / 200, h * 1.0 / 200], dtype=np.float32)
+    if center[0] != -1:
+        scale = scale * 1.25
+    return center, scale
+
+
+def cv_affine_solve(src, dst):
+    """cv2.getAffineTransform(src, dst): the 6x6 system [x y 1 0 0 0; 0 0 0 x y 1] m = [u; v] solved by OpenCV's own
+    LU with partial pivoting (core/matrix_decomp.cpp LUImpl, float64), restated operation by operation so that the
+    matrix is bit-identical (checked against cv2 in tests/test_oracle_vs_reference.py) -- a last-bit difference in
+    the matrix moves 1/32-pixel source coordinates across rounding boundaries in warp_affine_u8."""
+    src = np.asarray(src, np.float64)
+    dst = np.asarray(dst, np.float64)
+    a = np.zeros((6, 6))
+    b = np.zeros(6)
+    for i in range(3):
+        a[2 * i, 0:3] = [src[i, 0], src[i, 1], 1.0]
+        a[2 * i + 1, 3:6] = [src[i, 0], src[i, 1], 1.0]
+        b[2 * i], b[2 * i + 1] = dst[i, 0], dst[i, 1]
+    n = 6
+    for i in range(n):
+        k = i
+        for j in range(i + 1, n):
+            if abs(a[j, i]) > abs(a[k, i]):
+                k = j
+        if k != i:
+            a[[i, k], i:] = a[[k, i], i:]
+            b[[i, k]] = b[[k, i]]
+        d = -1.0 / a[i, i]
+        for j in range(i + 1, n):
+            alpha = a[j, i] * d
+            for kk in range(i + 1, n):
+                a[j, kk] += alpha * a[i, kk]
+            b[j] += alpha * b[i]
+    for i in range(n - 1, -1, -1):
+        sacc = b[i]
+        for kk in range(i + 1, n):
+            sacc -= a[i, kk] * b[kk]
+        b[i] = sacc / a[i, i]
+    return b.reshape(2, 3)
+
+
+def forward_affine(center, scale, rot, output_size):
+    """get_affine_transform(center, scale, rot, output_size) with inv=0, lib/transforms.py:197-233: the 2x3 float64
+    matrix image -> crop.  Points assembled in float32 as the reference does, 3-point solve in float64
+    (cv2.getAffineTransform, OpenCV 3.4.2 / 4.2.0 pinned in environment.yml; any version: plain 6x6 solve)."""
+    center = np.asarray(center)
+    scale = np.asarray(scale)
+    scale_tmp = scale * 200.0
+    src_w = scale_tmp[0]
+    dst_w, dst_h = output_size[0], output_size[1]
+    rot_rad = np.pi * rot / 180
+    sn, cs = np.sin(rot_rad), np.cos(rot_rad)
+    p = [0, src_w * -0.5]
+    src_dir = [p[0] * cs - p[1] * sn, p[0] * sn + p[1] * cs]                     # get_dir :249-256
+    dst_dir = np.array([0, dst_w * -0.5], np.float32)
+    src = np.zeros((3, 2), dtype=np.float32)
+    dst = np.zeros((3, 2), dtype=np.float32)
+    src[0, :] = center
+    src[1, :] = center + src_dir
+    dst[0, :] = [dst_w * 0.5, dst_h * 0.5]
+    dst[1, :] = np.array([dst_w * 0.5, dst_h * 0.5]) + dst_dir
+    src[2, :] = _third_point(src[0, :], src[1, :])
+    dst[2, :] = _third_point(dst[0, :], dst[1, :])
+    return cv_affine_solve(src, dst)
+
+
+def invert_affine(m):
+    """cv2.warpAffine's inversion of the 2x3 matrix (dst -> src), float64 (imgwarp.cpp, invertAffineTransform inline)."""
+    m = np.asarray(m, np.float64).reshape(6).copy()
+    d = m[0] * m[4] - m[1] * m[3]
+    d = 1.0 / d if d != 0 else 0.0
+    a11, a22 = m[4] * d, m[0] * d
+    m[0] = a11
+    m[1] *= -d
+    m[3] *= -d
+    m[4] = a22
+    b1 = -m[0] * m[2] - m[1] * m[5]
+    b2 = -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    return m
+
+
+def warp_affine_u8(img, m, dsize):
+    """cv2.warpAffine(img, m, dsize, flags=INTER_LINEAR) for uint8 HWC images, borderMode CONSTANT 0: OpenCV's fixed-point
+    algorithm (imgwarp.cpp WarpAffineInvoker + remap bilinear): source coordinates in 1/1024 px, rounded to 1/32 px
+    (INTER_BITS = 5), bilinear weights (32-fx)(32-fy)/1024 in 15-bit fixed point, result (sum + 2^14) >> 15.
+    Bit-exact against cv2 4.13 in this container (tests/test_oracle_vs_reference.py)."""
+    W, H = dsize
+    mi = invert_affine(m)
+    ab = 1024
+    xs = np.arange(W)
+    adelta = np.rint(mi[0] * xs * ab).astype(np.int64)
+    bdelta = np.rint(mi[3] * xs * ab).astype(np.int64)
+    ih, iw, ch = img.shape
+    pad = np.zeros((ih + 2, iw + 2, ch), np.int64)
+    pad[1:-1, 1:-1] = img
+    out = np.zeros((H, W, ch), np.uint8)
+
+    def px(yy, xx):
+        ok = (yy >= 0) & (yy < ih) & (xx >= 0) & (xx < iw)
+        return pad[np.clip(yy, -1, ih) + 1, np.clip(xx, -1, iw) + 1] * ok[:, None]
+
+    for y in range(H):
+        x0 = int(np.rint((mi[1] * y + mi[2]) * ab)) + 16
+        y0 = int(np.rint((mi[4] * y + mi[5]) * ab)) + 16
+        X, Y = (x0 + adelta) >> 5, (y0 + bdelta) >> 5
+        sx, sy, fx, fy = X >> 5, Y >> 5, X & 31, Y & 31
+        acc = (px(sy, sx) * ((32 - fx) * (32 - fy))[:, None] + px(sy, sx + 1) * (fx * (32 - fy))[:, None] +
+               px(sy + 1, sx) * ((32 - fx) * fy)[:, None] + px(sy + 1, sx + 1) * (fx * fy)[:, None])
+        out[y] = ((acc * 32 + 16384) >> 15).astype(np.uint8)
+    return out
+
+
+def transform_detection(img, list_coords, det_width=192, det_height=256):
+    """TransformDetection.__call__, lib/transforms.py:30-58 -> (detections u8 [N,3,H,W], centers [N,2], scales [N,2])."""
+    dets, centers, scales = [], [], []
+    for coords in list_coords:
+        c, s = coords2cs(coords, det_width, det_height)
+        m = forward_affine(c, s, 0, (det_width, det_height))
+        dets.append(warp_affine_u8(img, m, (det_width, det_height)))
+        centers.append(c)
+        scales.append(s)
+    dets, centers, scales = np.array(dets), np.array(centers), np.array(scales)
+    if len(dets) == 0:
+        return dets, centers, scales
+    return dets.transpose(0, 3, 1, 2), centers, scales
+
+
+def calc_dists(preds, target, normalize):
+    """metrics.py:268-296: normalised distance per (joint, sample); -1 where the target is not > 1 in x and y."""
+    preds = preds.astype(np.float32)
+    target = target.astype(np.float32)
+    dists = np.zeros((preds.shape[1], preds.shape[0]))
+    for n in range(preds.shape[0]):
+        for c in range(preds.shape[1]):
+            if target[n, c, 0] > 1 and target[n, c, 1] > 1:
+                d = preds[n, c, :] / normalize[n] - target[n, c, :] / normalize[n]
+                dists[c, n] = np.sqrt((d * d).sum())
+            else:
+                dists[c, n] = -1
+    return dists
+
+
+def dist_acc(dists, thr=0.5):
+    """metrics.py:299-317: fraction of the counted distances below thr, -1 when nothing is counted."""
+    counted = dists != -1
+    n = counted.sum()
+    return (dists[counted] < thr).sum() * 1.0 / n if n > 0 else -1
+
+
+def accuracy(output, target, thr=0.5):
+    """metrics.py:321-364 (hm_type='gaussian').  Lines 355-356 of the reference are corrupted; the evident intent
+    (upstream HRNet) is ``acc[i + 1] = dist_acc(dists[idx[i]])``.  -> (acc [J+1], avg_acc, cnt, pred)."""
+    pred, _ = get_max_preds(output)
+    tgt, _ = get_max_preds(target)
+    h, w = output.shape[2], output.shape[3]
+    norm = np.ones((pred.shape[0], 2)) * np.array([h, w]) / 10
+    dists = calc_dists(pred, tgt, norm)
+    J = output.shape[1]
+    acc = np.zeros(J + 1)
+    avg_acc, cnt = 0, 0
+    for i in range(J):
+        acc[i + 1] = dist_acc(dists[i], thr)
+        if acc[i + 1] >= 0:
+            avg_acc += acc[i + 1]
+            cnt += 1
+    avg_acc = avg_acc / cnt if cnt != 0 else 0
+    if cnt != 0:
+        acc[0] = avg_acc
+    return acc, avg_acc, cnt, pred
+
+
 def synth_boxes(n, seed=0):
     """Synthetic person boxes as SURVEY.md 8(d) config 1: center, scale as _xywh2cs would make them
     (data/HRNet_Coco.py:233-248): scale = (0.75*h, h)/200*1.25."""

@@ -139,3 +139,20 @@ def lib():
     ns.loss = importlib.import_module("lib.loss")
     ns.CONSTANTS = importlib.import_module("CONSTANTS")
     return ns
+
+
+def metrics_functions():
+    """``calc_dists`` and ``dist_acc`` of the reference's lib/metrics.py, executed from their unmodified source text.
+
+    The module itself cannot be imported (it needs pycocotools, and lines 355-356 inside ``accuracy`` are corrupted and
+    do not parse), so the two self-contained helper functions are cut out by their ``def`` blocks and exec'd with NumPy
+    in scope; ``accuracy`` is restated in oracle/pose_oracle.py around them."""
+    import numpy as np
+    path = os.path.join(REF_SRC, "lib", "metrics.py")
+    lines = open(path).read().split("\n")
+    ns = {"np": np}
+    for name in ("calc_dists", "dist_acc"):
+        start = next(i for i, l in enumerate(lines) if l.startswith(f"def {name}("))
+        end = next(i for i in range(start + 1, len(lines)) if lines[i].startswith("def "))
+        exec(compile("\n".join(lines[start:end]), f"{path}:{start + 1}", "exec"), ns)
+    return types.SimpleNamespace(calc_dists=ns["calc_dists"], dist_acc=ns["dist_acc"])

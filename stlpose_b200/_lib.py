@@ -59,6 +59,9 @@ PROTOTYPES = {
     "stl_decode": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p,
                                   ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]),
     "stl_mse_workspace_bytes": (ctypes.c_size_t, []),
+    "stl_warp_affine_crops": (ctypes.c_int, [vp] + [ctypes.c_int] * 2 + [vp] + [ctypes.c_int] * 3 + [vp, vp, vp, vp, vp]),
+    "stl_pck_accuracy": (ctypes.c_int, [vp, vp] + [ctypes.c_int] * 4 + [ctypes.c_float, vp, vp, vp, vp]),
+    "stl_scale_inplace": (ctypes.c_int, [vp, vp, ctypes.c_longlong, vp]),
     "stl_mse_loss_fwd_bwd": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]),
     "stl_padded_bytes": (ctypes.c_size_t, [ctypes.c_int] * 4),
     "stl_nchw_to_padded": (ctypes.c_int, [vp, vp] + [ctypes.c_int] * 5 + [vp]),

@@ -70,6 +70,31 @@ int stl_decode(const float* heat, const float* heat_flipped, const float* center
 
 size_t stl_mse_workspace_bytes(void) { return mse_workspace_bytes(); }
 
+int stl_warp_affine_crops(const void* img_u8_hwc, int img_h, int img_w, const double* minv, int N, int out_h, int out_w,
+                          void* out_u8_nchw, float* out_f32_nchw, const float* mean3_host, const float* std3_host,
+                          void* stream) {
+  if (!have_device()) return 1;
+  if (N > 0 && (!img_u8_hwc || !minv || (!out_u8_nchw && !out_f32_nchw))) {
+    set_error("stl_warp_affine_crops: null pointer");
+    return 1;
+  }
+  return warp_affine_crops((const uint8_t*)img_u8_hwc, img_h, img_w, minv, N, out_h, out_w, (uint8_t*)out_u8_nchw,
+                           out_f32_nchw, mean3_host, std3_host, (cudaStream_t)stream);
+}
+
+int stl_pck_accuracy(const float* pred_coords, const float* target_coords, int B, int J, int h, int w, float thr,
+                     float* acc, float* avg_acc, int* cnt, void* stream) {
+  if (!have_device()) return 1;
+  if (!pred_coords || !target_coords || !acc || !avg_acc || !cnt) { set_error("stl_pck_accuracy: null pointer"); return 1; }
+  return pck_accuracy(pred_coords, target_coords, B, J, h, w, thr, acc, avg_acc, cnt, (cudaStream_t)stream);
+}
+
+int stl_scale_inplace(float* x, const float* scale_dev, long long n, void* stream) {
+  if (!have_device()) return 1;
+  if (!x || !scale_dev) { set_error("stl_scale_inplace: null pointer"); return 1; }
+  return scale_inplace(x, scale_dev, n, (cudaStream_t)stream);
+}
+
 int stl_mse_loss_fwd_bwd(const float* out, const float* tgt, const float* tw, int B, int J, int hw, float* loss,
                          float* grad, void* workspace, void* stream) {
   if (!have_device()) return 1;

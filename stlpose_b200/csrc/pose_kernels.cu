@@ -194,6 +194,107 @@ __global__ void mse_final_kernel(const double* __restrict__ partial, int n, doub
   }
 }
 
+// ------------------------------------------------------------------ crop extraction (the step before the network)
+// cv2.warpAffine(img, M, (out_w, out_h), flags=INTER_LINEAR) of lib/transforms.py:38-43 / JointsDataset.py:189-197 for
+// uint8 HWC images, one launch for all boxes of an image: OpenCV's fixed-point algorithm -- source coordinates in
+// 1/1024 px from the inverted matrix (float64, rounded to nearest even like cvRound), reduced to 1/32 px, bilinear
+// weights (32-fx)(32-fy) in 15-bit fixed point, (sum + 2^14) >> 15, constant 0 outside the image -- so the crops are
+// bit-identical to the reference's.  minv: [N][6] float64 (dst -> src).  Outputs (each optional): the uint8 crops as
+// [N][3][out_h][out_w] (what TransformDetection returns) and the network input fp32 [N][3][out_h][out_w] =
+// (v / 255 - mean[c]) / std[c] (ToTensor + Normalize, data_loaders.py:59-61) in the same float32 operation order.
+struct Norm3 { float mean[3], stdv[3]; };
+__global__ void __launch_bounds__(256) warp_affine_kernel(const uint8_t* __restrict__ img, int ih, int iw,
+                                                          const double* __restrict__ minv, int out_h, int out_w,
+                                                          uint8_t* __restrict__ out_u8, float* __restrict__ out_f,
+                                                          const Norm3 nm) {
+  const int n = blockIdx.z, y = blockIdx.y;
+  const double* m = minv + (size_t)n * 6;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < out_w; x += gridDim.x * blockDim.x) {
+    const long long adelta = __double2ll_rn(__dmul_rn(__dmul_rn(m[0], (double)x), 1024.0));
+    const long long bdelta = __double2ll_rn(__dmul_rn(__dmul_rn(m[3], (double)x), 1024.0));
+    const long long x0 = __double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[1], (double)y), m[2]), 1024.0)) + 16;
+    const long long y0 = __double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[4], (double)y), m[5]), 1024.0)) + 16;
+    const long long X = (x0 + adelta) >> 5, Y = (y0 + bdelta) >> 5;
+    // OpenCV stores the integer part as a saturated short
+    long long sxl = X >> 5, syl = Y >> 5;
+    sxl = sxl < -32768 ? -32768 : (sxl > 32767 ? 32767 : sxl);
+    syl = syl < -32768 ? -32768 : (syl > 32767 ? 32767 : syl);
+    const int sx = (int)sxl, sy = (int)syl, fx = (int)(X & 31), fy = (int)(Y & 31);
+    const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy), w10 = (32 - fx) * fy, w11 = fx * fy;
+    const bool r0 = sy >= 0 && sy < ih, r1 = sy + 1 >= 0 && sy + 1 < ih;
+    const bool c0 = sx >= 0 && sx < iw, c1 = sx + 1 >= 0 && sx + 1 < iw;
+    const uint8_t* p00 = img + ((size_t)sy * iw + sx) * 3;
+    const uint8_t* p10 = p00 + (size_t)iw * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int v00 = (r0 && c0) ? p00[c] : 0, v01 = (r0 && c1) ? p00[3 + c] : 0;
+      const int v10 = (r1 && c0) ? p10[c] : 0, v11 = (r1 && c1) ? p10[3 + c] : 0;
+      const int v = ((v00 * w00 + v01 * w01 + v10 * w10 + v11 * w11) * 32 + 16384) >> 15;
+      const size_t o = (((size_t)n * 3 + c) * out_h + y) * out_w + x;
+      if (out_u8) out_u8[o] = (uint8_t)v;
+      if (out_f) out_f[o] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), nm.mean[c]), nm.stdv[c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ PCK accuracy on heatmap arg-max coordinates
+// metrics.py:268-364 (calc_dists, dist_acc, accuracy): a joint counts when its target arg-max has x > 1 and y > 1; it is
+// a hit when || (pred - target) / (h/10, w/10) || < thr (the reference divides x by h/10 and y by w/10); acc[1+j] =
+// hits / counted or -1; acc[0] = mean over joints with acc >= 0.  One block, one warp per joint.
+__global__ void pck_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, int B, int J, double nx,
+                           double ny, double thr, float* __restrict__ acc, float* __restrict__ avg_acc,
+                           int* __restrict__ cnt) {
+  __shared__ float s_acc[kMaxJoints];
+  const int lane = threadIdx.x & 31;
+  for (int j = threadIdx.x >> 5; j < J; j += blockDim.x >> 5) {
+    int counted = 0, hits = 0;
+    for (int n = lane; n < B; n += 32) {
+      const float tx = tgt[((size_t)n * J + j) * 2], ty = tgt[((size_t)n * J + j) * 2 + 1];
+      if (tx > 1.f && ty > 1.f) {
+        const double dx = (double)pred[((size_t)n * J + j) * 2] / nx - (double)tx / nx;
+        const double dy = (double)pred[((size_t)n * J + j) * 2 + 1] / ny - (double)ty / ny;
+        ++counted;
+        hits += sqrt(dx * dx + dy * dy) < thr;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      counted += __shfl_xor_sync(0xffffffffu, counted, off);
+      hits += __shfl_xor_sync(0xffffffffu, hits, off);
+    }
+    if (lane == 0) s_acc[j] = counted > 0 ? (float)((double)hits / (double)counted) : -1.f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sum = 0.0;
+    int c = 0;
+    for (int j = 0; j < J; ++j) {
+      acc[j + 1] = s_acc[j];
+      if (s_acc[j] >= 0.f) { sum += (double)s_acc[j]; ++c; }
+    }
+    const float avg = c ? (float)(sum / c) : 0.f;
+    acc[0] = c ? avg : 0.f;
+    *avg_acc = avg;
+    *cnt = c;
+  }
+}
+
+// x *= *scale unless *scale == 1 (the usual upstream gradient of a loss): then the kernel touches no memory.
+__global__ void __launch_bounds__(256) scale_unless_one_kernel(float* __restrict__ x, const float* __restrict__ scale,
+                                                               long long n4, long long n) {
+  const float s = __ldg(scale);
+  if (s == 1.0f) return;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v = x4[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    x4[i] = v;
+  }
+  if (blockIdx.x == 0)
+    for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) x[i] *= s;
+}
+
 int make_perm(int J, const int* pairs, int n_pairs, Perm* perm) {
   if (J > kMaxJoints || J <= 0) { set_error("decode: J=%d out of range (max %d)", J, kMaxJoints); return 1; }
   for (int j = 0; j < kMaxJoints; ++j) perm->src[j] = j;
@@ -251,6 +352,38 @@ int decode(const float* heat, const float* heat_f, const float* center, const fl
   decode_kernel<<<(unsigned)((maps + warps_per_block - 1) / warps_per_block), warps_per_block * 32, 0, st>>>(
       heat, heat_f, center, scale, B, J, h, w, perm, refine, avg_out, preds, maxvals, coords);
   return check("decode");
+}
+
+int warp_affine_crops(const uint8_t* img, int ih, int iw, const double* minv, int N, int out_h, int out_w,
+                      uint8_t* out_u8, float* out_f, const float* mean3, const float* std3, cudaStream_t st) {
+  if (N <= 0) return 0;
+  if (ih <= 0 || iw <= 0 || out_h <= 0 || out_w <= 0 || out_h > 65535 || N > 65535) {
+    set_error("warp_affine_crops: bad geometry");
+    return 1;
+  }
+  Norm3 nm{};
+  for (int c = 0; c < 3; ++c) { nm.mean[c] = mean3 ? mean3[c] : 0.f; nm.stdv[c] = std3 ? std3[c] : 1.f; }
+  dim3 grid((out_w + 255) / 256, out_h, N);
+  warp_affine_kernel<<<grid, 256, 0, st>>>(img, ih, iw, minv, out_h, out_w, out_u8, out_f, nm);
+  return check("warp_affine_crops");
+}
+
+int pck_accuracy(const float* pred, const float* tgt, int B, int J, int h, int w, float thr, float* acc, float* avg_acc,
+                 int* cnt, cudaStream_t st) {
+  if (J <= 0 || J > kMaxJoints) { set_error("pck_accuracy: J=%d out of range (max %d)", J, kMaxJoints); return 1; }
+  pck_kernel<<<1, 32 * (J < 32 ? J : 32), 0, st>>>(pred, tgt, B, J, (double)h / 10.0, (double)w / 10.0, (double)thr, acc,
+                                                  avg_acc, cnt);
+  return check("pck_accuracy");
+}
+
+int scale_inplace(float* x, const float* scale_dev, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  scale_unless_one_kernel<<<(int)blocks, 256, 0, st>>>(x, scale_dev, n4, n);
+  return check("scale_inplace");
 }
 
 size_t mse_workspace_bytes() { return sizeof(double) * 148 * 8; }

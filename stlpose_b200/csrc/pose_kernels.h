@@ -1,5 +1,6 @@
 // Host launchers for the bandwidth-bound pose kernels (pose_kernels.cu). Return 0 on success; enqueue on `st`.
 #pragma once
+#include <stdint.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 
@@ -16,6 +17,11 @@ int flip_back(const float* in, float* out, int B, int J, int h, int w, const int
 int decode(const float* heat, const float* heat_f, const float* center, const float* scale, int B, int J, int h,
            int w, const int* pairs, int n_pairs, int refine, float* avg_out, float* preds, float* maxvals,
            float* coords, cudaStream_t st);
+int warp_affine_crops(const uint8_t* img, int ih, int iw, const double* minv, int N, int out_h, int out_w,
+                      uint8_t* out_u8, float* out_f, const float* mean3, const float* std3, cudaStream_t st);
+int pck_accuracy(const float* pred, const float* tgt, int B, int J, int h, int w, float thr, float* acc, float* avg_acc,
+                 int* cnt, cudaStream_t st);
+int scale_inplace(float* x, const float* scale_dev, long long n, cudaStream_t st);
 size_t mse_workspace_bytes();
 int mse_loss(const float* out, const float* tgt, const float* tw, int B, int J, int hw, float* loss, float* grad,
              void* workspace, cudaStream_t st);

@@ -25,15 +25,23 @@ class _PersonMSE(torch.autograd.Function):
         with torch.cuda.device(o.device):
             _lib.check(L.stl_mse_loss_fwd_bwd(_lib.ptr(o), _lib.ptr(t), _lib.ptr(tw), B, J, hw, _lib.ptr(loss),
                                               _lib.ptr(grad), _lib.ptr(ws), _lib.current_stream()))
-        ctx.save_for_backward(grad)
+        ctx.grad = grad                      # dloss/doutput for an upstream gradient of 1, consumed by backward
         ctx.out_shape = output.shape
         ctx.out_dtype = output.dtype
         return loss
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
-        (grad,) = ctx.saved_tensors
-        return (grad * g).reshape(ctx.out_shape).to(ctx.out_dtype), None, None
+        grad = ctx.grad
+        if grad is None:
+            raise RuntimeError("PersonMSELoss: backward called twice; the fused gradient buffer is consumed by the "
+                               "first call (run the forward again)")
+        ctx.grad = None
+        g = g.detach().reshape(1).float().contiguous()
+        with torch.cuda.device(grad.device):     # scales in place, and touches no memory when g == 1
+            _lib.check(_lib.lib().stl_scale_inplace(_lib.ptr(grad), _lib.ptr(g), grad.numel(), _lib.current_stream()))
+        return grad.reshape(ctx.out_shape).to(ctx.out_dtype), None, None
 
 
 class PersonMSELoss(nn.Module):

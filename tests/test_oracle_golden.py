@@ -96,3 +96,35 @@ def test_known_answers():
     expect = c[0] + (coords[0, 3] - np.array([3.0, 4.0])) * k
     assert np.abs(preds[0, 3] - expect).max() < 1e-3
     assert pose_oracle.get_max_preds(np.zeros((0, 17, 8, 6), np.float32)) == ([], [])
+
+
+def test_pck_accuracy_oracle_matches_reference_fixture(golden):
+    """oracle calc_dists / dist_acc / accuracy vs the fixture produced by the reference's own function bodies."""
+    from oracle.make_golden import pck_inputs
+    g = golden("pck.npz")
+    out, tgt = pck_inputs()
+    acc, avg, cnt, pred = pose_oracle.accuracy(out, tgt)
+    assert np.array_equal(pred, g["pred"])
+    assert np.allclose(acc[1:], g["per_joint"], atol=0, rtol=0)
+    valid = g["per_joint"] >= 0
+    assert cnt == int(valid.sum()) and abs(avg - g["per_joint"][valid].mean()) < 1e-12 and acc[0] == avg
+    p2, _ = pose_oracle.get_max_preds(out)
+    t2, _ = pose_oracle.get_max_preds(tgt)
+    d = pose_oracle.calc_dists(p2, t2, np.ones((out.shape[0], 2)) * np.array([64, 48]) / 10)
+    assert np.allclose(d, g["dists"], atol=1e-12)
+    assert g["per_joint"][5] == -1                          # never-labeled joint
+
+
+def test_crop_extraction_oracle_matches_reference_fixture(golden):
+    """TransformDetection / crop restatement (cv2.getAffineTransform LU + cv2.warpAffine fixed-point bilinear) is
+    bit-exact against crops produced by the reference's own code."""
+    from oracle.make_golden import crop_inputs
+    g = golden("crops.npz")
+    img, boxes = crop_inputs()
+    dets, centers, scales = pose_oracle.transform_detection(img, boxes)
+    assert np.array_equal(centers, g["centers"]) and np.array_equal(scales, g["scales"])
+    assert dets.dtype == np.uint8 and np.array_equal(dets, g["dets"])
+    m = pose_oracle.forward_affine(g["centers"][1], g["scales"][1], 30, (192, 256))
+    assert np.array_equal(pose_oracle.warp_affine_u8(img, m, (192, 256)), g["rot30"])
+    d0, c0, s0 = pose_oracle.transform_detection(img, [])
+    assert len(d0) == 0 and len(c0) == 0

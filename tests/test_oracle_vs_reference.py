@@ -63,3 +63,38 @@ def test_train_step_matches_reference_module():
     for k, v in ref_sd.items():
         if "running" in k:
             assert (sd[k] - v).abs().max().item() < 1e-5, k
+
+
+def test_pck_helpers_match_reference_source():
+    M = ref_shim.metrics_functions()
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        pred = rng.integers(0, 48, size=(7, 17, 2)).astype(np.float32)
+        tgt = rng.integers(0, 48, size=(7, 17, 2)).astype(np.float32)
+        tgt[rng.random((7, 17)) < 0.3] = 0
+        norm = np.ones((7, 2)) * np.array([64, 48]) / 10
+        d_ref, d = M.calc_dists(pred, tgt, norm), pose_oracle.calc_dists(pred, tgt, norm)
+        assert np.allclose(d, d_ref, atol=1e-12)
+        for j in range(17):
+            assert pose_oracle.dist_acc(d[j]) == M.dist_acc(d_ref[j])
+
+
+def test_affine_solve_and_warp_match_cv2_bit_exact():
+    import cv2
+    L = ref_shim.lib()
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, size=(120, 160, 3), dtype=np.uint8)
+    for t in range(40):
+        c = rng.uniform(10, 150, 2).astype(np.float32)
+        s = rng.uniform(0.1, 1.2, 2).astype(np.float32)
+        rot = float(rng.uniform(-80, 80)) if t % 2 else 0
+        m_ref = L.transforms.get_affine_transform(c, s, rot, np.array([48, 64]))
+        m = pose_oracle.forward_affine(c, s, rot, (48, 64))
+        assert np.array_equal(m, m_ref)
+        assert np.array_equal(pose_oracle.warp_affine_u8(img, m, (48, 64)),
+                              cv2.warpAffine(img, m_ref, (48, 64), flags=cv2.INTER_LINEAR))
+    td = L.transforms.TransformDetection()
+    for box in ([5, 5, 60, 100], [-30, 20, 90, 80], [100, 60, 200, 140]):
+        rc, rs = td._coords2cs(box)
+        oc, os_ = pose_oracle.coords2cs(box)
+        assert np.array_equal(rc, oc) and np.array_equal(rs, os_)

@@ -140,3 +140,58 @@ def test_decode_96x72_full_size_properties():
     denom = 17 * B * 96 * 72
     assert torch.allclose(o.grad, (a - f) / denom, rtol=1e-5, atol=1e-12)
     assert abs(loss.item() - 0.5 * ((a - f).double() ** 2).sum().item() / denom) < 1e-6 * loss.item()
+
+
+def test_pck_accuracy_matches_oracle_and_fixture(golden):
+    """stlpose_b200.metrics.accuracy (device decode x2 + PCK kernel) vs the oracle and the reference fixture."""
+    from oracle.make_golden import pck_inputs
+    from stlpose_b200 import metrics
+    out, tgt = pck_inputs()
+    acc, avg, cnt, pred = metrics.accuracy(out, tgt)
+    o_acc, o_avg, o_cnt, o_pred = pose_oracle.accuracy(out, tgt)
+    assert np.array_equal(pred, o_pred) and cnt == o_cnt
+    assert np.abs(acc - o_acc).max() < 1e-6 and abs(avg - o_avg) < 1e-6
+    assert np.abs(acc[1:] - golden("pck.npz")["per_joint"]).max() < 1e-6
+    # CUDA tensors in, tensors out (no host copy), other threshold, larger random batch
+    rng = np.random.default_rng(5)
+    big_o = rng.standard_normal((300, 17, 64, 48)).astype(np.float32)
+    big_t = np.where(rng.random((300, 17, 1, 1)) < 0.25, 0, rng.standard_normal((300, 17, 64, 48))).astype(np.float32)
+    a_t, avg_t, cnt_t, _ = metrics.accuracy(torch.from_numpy(big_o).cuda(), torch.from_numpy(big_t).cuda(), thr=3.0,
+                                            as_tensor=True)
+    r_acc, r_avg, r_cnt, _ = pose_oracle.accuracy(big_o, big_t, thr=3.0)
+    assert a_t.is_cuda and int(cnt_t) == r_cnt and np.abs(a_t.cpu().numpy() - r_acc).max() < 1e-6
+    # nothing labeled: every joint -1, average 0, cnt 0 (metrics.py:359-362)
+    acc0, avg0, cnt0, _ = metrics.accuracy(out, np.zeros_like(tgt))
+    assert cnt0 == 0 and avg0 == 0 and (acc0[1:] == -1).all() and acc0[0] == 0
+
+
+def test_crop_extraction_bit_exact(golden):
+    """stlpose_b200.transforms.TransformDetection / crop (device warp) vs the reference fixture and the oracle."""
+    from oracle.make_golden import crop_inputs
+    from stlpose_b200 import transforms as T
+    g = golden("crops.npz")
+    img, boxes = crop_inputs()
+    td = T.TransformDetection()
+    dets, centers, scales = td(img, boxes)
+    assert dets.dtype == np.uint8 and dets.shape == (5, 3, 256, 192)
+    assert np.array_equal(centers, g["centers"]) and np.array_equal(scales, g["scales"])
+    assert np.array_equal(dets, g["dets"])
+    assert np.array_equal(T.crop(img, g["centers"][1], g["scales"][1], np.array([192, 256]), rot=30), g["rot30"])
+    # fused ToTensor + Normalize: same float32 operation order as torchvision on the reference's uint8 crops
+    x, _, _ = td.extract_normalized(img, boxes)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    want = (torch.from_numpy(g["dets"]).float().div(255) - mean) / std
+    assert x.is_cuda and x.dtype == torch.float32 and torch.equal(x.cpu(), want)
+    # other geometry, random rotations, CUDA image input, vs the oracle
+    rng = np.random.default_rng(3)
+    img2 = rng.integers(0, 256, size=(97, 131, 3), dtype=np.uint8)
+    mats = [pose_oracle.forward_affine(rng.uniform(0, 130, 2).astype(np.float32), rng.uniform(0.1, 1.0, 2).astype(np.float32),
+                                       float(rng.uniform(-90, 90)), (72, 96)) for _ in range(7)]
+    got = T.warp_affine_crops(torch.from_numpy(img2).cuda(), mats, (72, 96), as_tensor=True).cpu().numpy()
+    for i, m in enumerate(mats):
+        assert np.array_equal(got[i].transpose(1, 2, 0), pose_oracle.warp_affine_u8(img2, m, (72, 96))), i
+    e_d, e_c, e_s = td(img, [])
+    assert len(e_d) == 0 and len(e_c) == 0 and len(e_s) == 0
+    # end to end: boxes -> network input -> keypoints runs without touching the host with the crops
+    assert x.shape == (5, 3, 256, 192)
