@@ -95,6 +95,11 @@ int stl_padded_to_nchw(const void* y_padded, float* x_nchw, int N, int C, int H,
 int stl_pack_conv_weights(const float* w_oihw, const float* bn_gamma, const float* bn_beta, const float* bn_mean,
                           const float* bn_var, const float* conv_bias, float eps, int Cout, int Cin, int ksize,
                           int Cout_pad, int Cin_pad, void* w_packed, float* bias_packed, void* stream);
+/* Weights for the convolution that IS the stride-1 input gradient: dx = stl_conv2d(dz, W'), W'[ci][co][kh][kw] =
+ * W[co][ci][k-1-kh][k-1-kw].  w: fp32 OIHW of the forward layer; result [k*k][Rows_pad][K_pad] bf16 with Rows_pad >= Cin
+ * (multiple of 16) and K_pad >= Cout (the channel count of dz); bias_packed (Rows_pad floats, may be null) is zeroed. */
+int stl_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, int Rows_pad, int K_pad, void* w_packed,
+                                float* bias_packed, void* stream);
 
 typedef struct stl_conv_desc {
   const void* in;          /* padded-linear bf16 [N][H+1][W+1][Cin] */

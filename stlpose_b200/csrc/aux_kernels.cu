@@ -81,6 +81,26 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
   }
 }
 
+// Weights of the convolution that computes a stride-1 dgrad: dx = conv(dz, W') with W'[ci][co][kh][kw] =
+// W[co][ci][k-1-kh][k-1-kw].  w_oihw [Cout][Cin][k][k] fp32 -> wp [k*k][Rows_pad][K_pad] bf16, rows = input channels of
+// the forward layer, columns = its output channels, taps reversed.  bias_out (Rows_pad) is zeroed.
+__global__ void pack_weights_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int Rows_pad,
+                                          int K_pad, __nv_bfloat16* __restrict__ wp, float* __restrict__ bias_out) {
+  const int taps = k * k;
+  const long long total = (long long)taps * Rows_pad * K_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % K_pad);
+    const int ci = (int)((i / K_pad) % Rows_pad);
+    const int t = (int)(i / ((long long)K_pad * Rows_pad));
+    float v = 0.f;
+    if (co < Cout && ci < Cin) v = w[((size_t)co * Cin + ci) * taps + (taps - 1 - t)];
+    wp[i] = __float2bfloat16(v);
+  }
+  if (bias_out)
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < Rows_pad; r += gridDim.x * blockDim.x) bias_out[r] = 0.f;
+}
+
 // ------------------------------------------------------------------ network input -> tensor-core layout
 // fp32 NCHW [B][3][H][W] -> padded-linear NHWC bf16 with the 3 channels padded to 16 (one UMMA K-step), so that the
 // stem's 3->64 stride-2 conv runs on the same tcgen05 kernel as every other layer.  Images n >= n_plain are image
@@ -245,6 +265,14 @@ int pack_weights(const float* w, const float* gamma, const float* beta, const fl
   pack_weights_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, gamma, beta, mean, var, cbias, eps, Cout, Cin, k,
                                                             Cout_pad, Cin_pad, wp, bias_out);
   return check("pack_weights");
+}
+
+int pack_weights_dgrad(const float* w, int Cout, int Cin, int k, int Rows_pad, int K_pad, __nv_bfloat16* wp,
+                       float* bias_out, cudaStream_t st) {
+  if (Rows_pad < Cin || K_pad < Cout) { set_error("pack_weights_dgrad: padded sizes smaller than the real ones"); return 1; }
+  const long long total = (long long)k * k * Rows_pad * K_pad;
+  pack_weights_dgrad_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, Cout, Cin, k, Rows_pad, K_pad, wp, bias_out);
+  return check("pack_weights_dgrad");
 }
 
 int stem_pack_input(const float* x, __nv_bfloat16* y, int n_total, int n_plain, int H, int W, cudaStream_t st) {

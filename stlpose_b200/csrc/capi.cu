@@ -124,6 +124,14 @@ int stl_pack_conv_weights(const float* w, const float* g, const float* b, const 
                       reinterpret_cast<__nv_bfloat16*>(w_packed), bias_packed, (cudaStream_t)stream);
 }
 
+int stl_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, int Rows_pad, int K_pad, void* w_packed,
+                                float* bias_packed, void* stream) {
+  if (!have_device()) return 1;
+  if (!w || !w_packed) { set_error("stl_pack_conv_weights_dgrad: null pointer"); return 1; }
+  return pack_weights_dgrad(w, Cout, Cin, ksize, Rows_pad, K_pad, reinterpret_cast<__nv_bfloat16*>(w_packed),
+                            bias_packed, (cudaStream_t)stream);
+}
+
 int stl_conv2d(const stl_conv_desc* d, void* stream) {
   if (!have_device()) return 1;
   if (!d || !d->in || !d->out || !d->w_packed || !d->bias_packed) { set_error("stl_conv2d: null pointer"); return 1; }

@@ -109,10 +109,40 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  for (int c = threadIdx.x; c < 2 * C; c += 256) {
-    float acc = 0.f;
-    for (unsigned b2 = 0; b2 < gridDim.x; ++b2) acc += __ldcg(partial + (size_t)b2 * 2 * C + c);
-    sums[c] = acc;
+  // fixed-order sum of the rows: `parts` thread groups each take an interleaved quarter (or less) of the rows with four
+  // independent accumulators (loads in flight), then the groups are combined in order through shared memory
+  {
+    const int C2 = 2 * C;
+    const int parts = C2 >= 256 ? 1 : 256 / C2;                 // C2 is a multiple of 16
+    const int part = threadIdx.x / C2, cc = threadIdx.x % C2;
+    float* comb = &red[0][0][0];                                // 256 x 9 floats >= parts * C2 when parts > 1
+    for (int c0 = 0; c0 < C2; c0 += 256) {
+      const int c = c0 + cc;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      if (part < parts && c < C2) {
+        unsigned b2 = part;
+        for (; b2 + 3 * parts < gridDim.x; b2 += 4 * parts) {
+          a0 += __ldcg(partial + (size_t)b2 * C2 + c);
+          a1 += __ldcg(partial + (size_t)(b2 + parts) * C2 + c);
+          a2 += __ldcg(partial + (size_t)(b2 + 2 * parts) * C2 + c);
+          a3 += __ldcg(partial + (size_t)(b2 + 3 * parts) * C2 + c);
+        }
+        for (; b2 < gridDim.x; b2 += parts) a0 += __ldcg(partial + (size_t)b2 * C2 + c);
+      }
+      const float acc = (a0 + a1) + (a2 + a3);
+      if (parts == 1) {
+        if (c < C2) sums[c] = acc;
+      } else {
+        __syncthreads();
+        if (part < parts) comb[part * C2 + cc] = acc;
+        __syncthreads();
+        if (part == 0) {
+          float t = 0.f;
+          for (int q = 0; q < parts; ++q) t += comb[q * C2 + cc];
+          sums[cc] = t;
+        }
+      }
+    }
   }
   if (threadIdx.x == 0) *counter = 0u;
   if (MODE == 0) {
@@ -474,7 +504,7 @@ int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* be
   cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   const int lanes = 256 / (C / 8);
   BnFinalize fin{(float)((long long)N * H * W), eps, momentum, mean, rstd, run_mean, run_var};
-  channel_reduce_kernel<0><<<grid_for(pixels, lanes * 4, kReduceBlocks), 256, 0, st>>>(
+  channel_reduce_kernel<0><<<grid_for(pixels, lanes * 16, kReduceBlocks), 256, 0, st>>>(
       z, nullptr, nullptr, nullptr, nullptr, pixels, C, 0, sums, sums + 2 * C, counter, fin);
   if (check("bn stats")) return 1;
   bn_apply_kernel<<<grid_for(pixels * (C / 8), 256), 256, 0, st>>>(z, mean, rstd, gamma, beta, residual, relu, y, N, H,
@@ -490,7 +520,7 @@ int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __n
   unsigned* counter = reinterpret_cast<unsigned*>(sums + (size_t)2 * C * (1 + kReduceBlocks));
   cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   const int lanes = 256 / (C / 8);
-  channel_reduce_kernel<1><<<grid_for(pixels, lanes * 4, kReduceBlocks), 256, 0, st>>>(
+  channel_reduce_kernel<1><<<grid_for(pixels, lanes * 16, kReduceBlocks), 256, 0, st>>>(
       dy, y, z, mean, rstd, pixels, C, relu, sums, sums + 2 * C, counter, BnFinalize{});
   if (check("bn backward reduce")) return 1;
   bn_backward_kernel<<<grid_for(pixels * (C / 8), 256), 256, 0, st>>>(dy, y, z, mean, rstd, gamma, sums,

@@ -184,9 +184,18 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant
     const int tap = p.tap_of[tg][a][row / p.m_real];
     const int co = m_blk * 128 + row % p.m_real, ci = n_blk * p.nt + col;
     if (tap < 0 || co >= p.co || ci >= p.ci_real) continue;
-    float acc = 0.f;
-    for (int sp = 0; sp < p.n_splits; ++sp) acc += __ldcg(p.ws + ((size_t)sp * p.n_groups + group) * per_group + r);
-    p.dw[((size_t)co * p.ci_real + ci) * p.taps + tap] = acc;
+    const size_t stride = (size_t)p.n_groups * per_group;
+    const float* src = p.ws + (size_t)group * per_group + r;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int sp = 0;
+    for (; sp + 3 < p.n_splits; sp += 4) {                      // four loads in flight, fixed summation order
+      a0 += __ldcg(src + (size_t)sp * stride);
+      a1 += __ldcg(src + (size_t)(sp + 1) * stride);
+      a2 += __ldcg(src + (size_t)(sp + 2) * stride);
+      a3 += __ldcg(src + (size_t)(sp + 3) * stride);
+    }
+    for (; sp < p.n_splits; ++sp) a0 += __ldcg(src + (size_t)sp * stride);
+    p.dw[((size_t)co * p.ci_real + ci) * p.taps + tap] = (a0 + a1) + (a2 + a3);
   }
 }
 

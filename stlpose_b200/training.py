@@ -30,17 +30,40 @@ def _padded_zeros(n, h, w, c, device):
     return torch.zeros((n, h + 1, w + 1, c), dtype=torch.bfloat16, device=device)
 
 
-def _pack_weights(w, cin_pad):
+_ZERO_BIAS = {}
+
+
+def _zero_bias(n, device):
+    """Shared all-zero fp32 bias (BatchNorm follows every conv of the training graph; only the head has a bias)."""
+    key = (device, n)
+    if key not in _ZERO_BIAS:
+        _ZERO_BIAS[key] = torch.zeros(n, dtype=torch.float32, device=device)
+    return _ZERO_BIAS[key]
+
+
+def _pack_weights(w, cin_pad, own_bias=False):
     """fp32 OIHW -> ([k*k][cout_pad][cin_pad] bf16 buffer, zero fp32 bias)."""
     L = _lib.lib()
     cout, cin, k, _ = w.shape
     cout_pad = (cout + 15) // 16 * 16
     wp = torch.empty(k * k * cout_pad * cin_pad * 2, dtype=torch.uint8, device=w.device)
-    bp = torch.zeros(cout_pad, dtype=torch.float32, device=w.device)
+    bp = torch.empty(cout_pad, dtype=torch.float32, device=w.device) if own_bias else None
     w32 = w.detach().float().contiguous()
+    scratch = bp if own_bias else torch.empty(cout_pad, dtype=torch.float32, device=w.device)
     _lib.check(L.stl_pack_conv_weights(_lib.ptr(w32), None, None, None, None, None, 0.0, cout, cin, k, cout_pad,
-                                       cin_pad, _lib.ptr(wp), _lib.ptr(bp), _stream()))
-    return wp, bp, cout_pad
+                                       cin_pad, _lib.ptr(wp), _lib.ptr(scratch), _stream()))
+    return wp, (bp if own_bias else _zero_bias(cout_pad, w.device)), cout_pad
+
+
+def _pack_weights_dgrad(w, k_pad):
+    """fp32 OIHW of a forward layer -> weights of the convolution computing its stride-1 input gradient."""
+    L = _lib.lib()
+    cout, cin, k, _ = w.shape
+    rows_pad = (cin + 15) // 16 * 16
+    wp = torch.empty(k * k * rows_pad * k_pad * 2, dtype=torch.uint8, device=w.device)
+    w32 = w.detach().float().contiguous()
+    _lib.check(L.stl_pack_conv_weights_dgrad(_lib.ptr(w32), cout, cin, k, rows_pad, k_pad, _lib.ptr(wp), None, _stream()))
+    return wp, _zero_bias(rows_pad, w.device), rows_pad
 
 
 def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bias=None):
@@ -100,8 +123,7 @@ def conv_dgrad(dz, weight, n, h, w, cin_pad, stride):
     if stride == 2 and cin_real == cin_pad and dz.shape[1] != h + 1:
         dz = zero_stuff(dz, n, h, w)
     if cin_real == cin_pad and dz.shape[1] == h + 1:
-        wt = weight.detach().float().flip(2, 3).transpose(0, 1).contiguous()       # [cin][cout][k][k]
-        wp, bp, cpad = _pack_weights(wt, dz.shape[3])
+        wp, bp, cpad = _pack_weights_dgrad(weight, dz.shape[3])                     # flipped, transposed filter
         return _conv_raw(dz, wp, bp, cin_real, cpad, k, 1)
     wp, _, cout_pad = _pack_weights(weight, cin_pad)
     dx = torch.empty((n, h + 1, w + 1, cin_pad), dtype=torch.bfloat16, device=dz.device)
@@ -162,7 +184,7 @@ class _Head(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         n, hp, wpd, cin = x.shape
         cout = weight.shape[0]
-        wp, bp, cout_pad = _pack_weights(weight, cin)
+        wp, bp, cout_pad = _pack_weights(weight, cin, own_bias=True)
         bp[:cout] = bias.detach().float()
         heat = _conv_raw(x, wp, bp, cout, cout_pad, 1, 1, out_nchw=True)
         ctx.save_for_backward(x, weight)
@@ -218,7 +240,6 @@ class _FuseSum(torch.autograd.Function):
 
 
 def _convbn(x, conv, bn, stride, relu, residual=None):
-    bn.num_batches_tracked += 1
     return _ConvBN.apply(x, conv.weight, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, stride, relu,
                          bn.momentum)
 
@@ -230,7 +251,12 @@ def train_forward(model, x):
         raise _lib.StlError("input must be a CUDA tensor (there is no CPU fallback)")
     x = x.detach().float().contiguous()
     B, _, H, W = x.shape
+    counters = getattr(model, "_bn_counters", None)
+    if counters is None or counters[0].device != x.device:
+        counters = [b for n, b in model.named_buffers() if n.endswith("num_batches_tracked")]
+        model._bn_counters = counters
     with torch.cuda.device(x.device):
+        torch._foreach_add_(counters, 1)                               # every BatchNorm runs once per forward
         t = torch.empty((B, H + 1, W + 1, 16), dtype=torch.bfloat16, device=x.device)
         _lib.check(L.stl_nchw_to_padded(_lib.ptr(x), _lib.ptr(t), B, 3, H, W, 16, _stream()))
         t = _convbn(t, model.conv1, model.bn1, 2, True)
