@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "conv.h"
 #include "ptx.cuh"
@@ -48,6 +49,7 @@ struct WgradParams {
   int tiles_total, tiles_per_split, n_splits;
   float* dw;
   float* ws;                      // [grid][n_acc][128][nt] fp32 partial sums, one slab per CTA
+  int dbg;                        // measurement only: 1 = no MMAs, 2 = no TMA loads (results are garbage)
   int co, ci, ci_real, taps;
 };
 
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
           const int q0 = -kLead + (t_lo + i) * kKT;
           const uint32_t a_dst = smem0 + (uint32_t)s * p.stage_bytes;
           const uint32_t b_dst = a_dst + (uint32_t)p.a_panels * p.a_panel_bytes;
+          if (p.dbg == 2) { mbar_arrive(&full_bar[s]); continue; }
           mbar_expect_tx(&full_bar[s], (uint32_t)p.a_panels * (uint32_t)(p.dz_rows * p.pitch_a) +
                                            (uint32_t)p.b_panels * (uint32_t)(p.x_rows * p.pitch_b));
           for (int a = 0; a < p.a_panels; ++a)
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
           const uint32_t a_src = smem0 + (uint32_t)s * p.stage_bytes;
           const uint32_t b_src = a_src + (uint32_t)p.a_panels * p.a_panel_bytes;
 #pragma unroll 1
-          for (int ks = 0; ks < kKT / 16; ++ks) {
+          for (int ks = 0; ks < (p.dbg == 1 ? 0 : kKT / 16); ++ks) {
             const uint64_t adesc = make_mnmajor_desc(a_src + (uint32_t)(ks * 16 * p.pitch_a), (uint32_t)p.pitch_a, p.lbo_a);
 #pragma unroll 1
             for (int m = 0; m < p.n_mma; ++m) {
@@ -385,6 +388,7 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, 
   }
   p.dw = dw;
   p.ws = static_cast<float*>(workspace);
+  p.dbg = getenv("STL_WGRAD_DBG") ? atoi(getenv("STL_WGRAD_DBG")) : 0;
   const long long P = (long long)N * (H + 1) * (W + 1);
   if (encode_rows(&p.tmDz, dz, cout, P, cout < 64 ? cout : 64, p.dz_rows)) return 1;
   if (encode_rows(&p.tmX, x, cin, P, cin < 64 ? cin : 64, p.x_rows)) return 1;
