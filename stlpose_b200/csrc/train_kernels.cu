@@ -35,6 +35,26 @@ int check(const char* what) {
   return 0;
 }
 
+// Flat 16-byte item index -> (channel group, w, h, n) of the padded layout with multiply-shift division: the 64-bit
+// div/mod of the first version cost more than the memory traffic (1.2 TB/s on the 256-channel tensors).
+struct PixIdx {
+  FastDiv c8, wp, hp;
+  int c8n, Wp, Hp;
+  __host__ void init(int C, int H, int W) {
+    c8n = C / 8; Wp = W + 1; Hp = H + 1;
+    c8.init((uint32_t)c8n); wp.init((uint32_t)Wp); hp.init((uint32_t)Hp);
+  }
+  __device__ __forceinline__ void decode(uint32_t i, int& cg, int& w, int& h, int& n) const {
+    const uint32_t q = c8.div(i);
+    cg = (int)(i - q * (uint32_t)c8n);
+    const uint32_t t = wp.div(q);
+    w = (int)(q - t * (uint32_t)Wp);
+    const uint32_t nn = hp.div(t);
+    h = (int)(t - nn * (uint32_t)Hp);
+    n = (int)nn;
+  }
+};
+
 // ------------------------------------------------------------------ per-channel reductions over all pixels
 // MODE 0: sums[c] = sum a, sums[C+c] = sum a^2                      (BatchNorm forward statistics; a = z)
 // MODE 1: sums[c] = sum g, sums[C+c] = sum g * xhat                 (BatchNorm backward; g = dy masked by y > 0)
@@ -167,14 +187,22 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const __nv_bfloat16* __restrict__ residual, int relu,
-                                                       __nv_bfloat16* __restrict__ y, int N, int H, int W, int C) {
-  const int c8n = C / 8, Wp = W + 1, Hp = H + 1;
-  const long long total = (long long)N * Hp * Wp * c8n;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c8n);
-    const long long q = i / c8n;
-    const int w = (int)(q % Wp), h = (int)((q / Wp) % Hp);
+                                                       __nv_bfloat16* __restrict__ y, int N, int H, int W, int C, const PixIdx px) {
+  const uint32_t total = (uint32_t)N * (uint32_t)(px.Hp * px.Wp * px.c8n);
+  // the grid stride is a multiple of the channel-group count (launcher), so a thread keeps its 8 channels: the
+  // per-channel parameters live in registers instead of 32 scalar loads per 16-byte item
+  float g8[8], m8[8], r8[8], b8[8];
+  {
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cg0 = (int)(i0 - px.c8.div(i0) * (uint32_t)px.c8n);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      g8[k] = gamma[cg0 * 8 + k]; m8[k] = mean[cg0 * 8 + k]; r8[k] = rstd[cg0 * 8 + k]; b8[k] = beta[cg0 * 8 + k];
+    }
+  }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int cg, w, h, n;
+    px.decode(i, cg, w, h, n);
     uint4 out = make_uint4(0, 0, 0, 0);
     if (h < H && w < W) {
       float f[8];
@@ -183,8 +211,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
       if (residual) unpack8(*reinterpret_cast<const uint4*>(residual + (size_t)i * 8), r);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int c = cg * 8 + k;
-        float v = gamma[c] * (f[k] - mean[c]) * rstd[c] + beta[c] + r[k];
+        float v = g8[k] * (f[k] - m8[k]) * r8[k] + b8[k] + r[k];
         f[k] = relu ? fmaxf(v, 0.f) : v;
       }
       out = pack8(f);
@@ -203,14 +230,22 @@ __global__ void __launch_bounds__(256) bn_backward_kernel(const __nv_bfloat16* _
                                                           const float* __restrict__ sums, float count, int relu_mask,
                                                           __nv_bfloat16* __restrict__ dz,
                                                           __nv_bfloat16* __restrict__ dres, int N, int H, int W,
-                                                          int C) {
-  const int c8n = C / 8, Wp = W + 1, Hp = H + 1;
-  const long long total = (long long)N * Hp * Wp * c8n;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c8n);
-    const long long q = i / c8n;
-    const int w = (int)(q % Wp), h = (int)((q / Wp) % Hp);
+                                                          int C, const PixIdx px) {
+  const uint32_t total = (uint32_t)N * (uint32_t)(px.Hp * px.Wp * px.c8n);
+  float gr8[8], m8[8], r8[8], sg8[8], sx8[8];      // gamma*rstd, mean, rstd, sum_g/cnt, sum_gx/cnt of this thread's channels
+  {
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cg0 = (int)(i0 - px.c8.div(i0) * (uint32_t)px.c8n);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cg0 * 8 + k;
+      m8[k] = mean[c]; r8[k] = rstd[c]; gr8[k] = gamma[c] * rstd[c];
+      sg8[k] = sums[c] / count; sx8[k] = sums[C + c] / count;
+    }
+  }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int cg, w, h, n;
+    px.decode(i, cg, w, h, n);
     uint4 o_dz = make_uint4(0, 0, 0, 0), o_dr = o_dz;
     if (h < H && w < W) {
       float g[8], yy[8], zz[8], d[8];
@@ -219,10 +254,9 @@ __global__ void __launch_bounds__(256) bn_backward_kernel(const __nv_bfloat16* _
       if (relu_mask) unpack8(*reinterpret_cast<const uint4*>(y + (size_t)i * 8), yy);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int c = cg * 8 + k;
         if (relu_mask && !(yy[k] > 0.f)) g[k] = 0.f;
-        const float xhat = (zz[k] - mean[c]) * rstd[c];
-        d[k] = gamma[c] * rstd[c] * (g[k] - sums[c] / count - xhat * sums[C + c] / count);
+        const float xhat = (zz[k] - m8[k]) * r8[k];
+        d[k] = gr8[k] * (g[k] - sg8[k] - xhat * sx8[k]);
       }
       o_dz = pack8(d);
       o_dr = pack8(g);
@@ -241,16 +275,11 @@ struct SumArgs {
 };
 
 __global__ void __launch_bounds__(256) sum_relu_kernel(const SumArgs a, __nv_bfloat16* __restrict__ y, int N, int H,
-                                                       int W, int C) {
-  const int c8n = C / 8, Wp = W + 1, Hp = H + 1;
-  const long long total = (long long)N * Hp * Wp * c8n;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c8n);
-    const long long q = i / c8n;
-    const int w = (int)(q % Wp);
-    const long long t = q / Wp;
-    const int h = (int)(t % Hp), n = (int)(t / Hp);
+                                                       int W, int C, const PixIdx px) {
+  const uint32_t total = (uint32_t)N * (uint32_t)(px.Hp * px.Wp * px.c8n);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int cg, w, h, n;
+    px.decode(i, cg, w, h, n);
     uint4 out = make_uint4(0, 0, 0, 0);
     if (h < H && w < W) {
       float f[8] = {0, 0, 0, 0, 0, 0, 0, 0}, r[8];
@@ -321,16 +350,12 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const __nv_bfloat16* 
 // Zero-stuffing: u[n,h,w] = dz[n,h/2,w/2] where h and w are even, 0 elsewhere.  A stride-2 convolution is the stride-1
 // convolution sampled at even positions, so its input and weight gradients are the stride-1 ones of the stuffed dz.
 __global__ void __launch_bounds__(256) zero_stuff_kernel(const __nv_bfloat16* __restrict__ dz,
-                                                         __nv_bfloat16* __restrict__ u, int N, int H, int W, int C) {
-  const int c8n = C / 8, Wp = W + 1, Hp = H + 1, Wo = W / 2, Ho = H / 2;
-  const long long total = (long long)N * Hp * Wp * c8n;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c8n);
-    const long long q = i / c8n;
-    const int w = (int)(q % Wp);
-    const long long t = q / Wp;
-    const int h = (int)(t % Hp), n = (int)(t / Hp);
+                                                         __nv_bfloat16* __restrict__ u, int N, int H, int W, int C, const PixIdx px) {
+  const int Wo = W / 2, Ho = H / 2;
+  const uint32_t total = (uint32_t)N * (uint32_t)(px.Hp * px.Wp * px.c8n);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int cg, w, h, n;
+    px.decode(i, cg, w, h, n);
     uint4 out = make_uint4(0, 0, 0, 0);
     if (h < H && w < W && !(h & 1) && !(w & 1)) {
       const size_t qs = ((size_t)n * (Ho + 1) + (h >> 1)) * (Wo + 1) + (w >> 1);
@@ -486,6 +511,16 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __nv_bfloat16* __
   if (ci < cin_real) atomicAdd(dw + ((size_t)co * cin_real + ci) * taps + tap, acc);
 }
 
+// Grid for a 256-thread grid-stride kernel over `total` items whose stride (grid * 256) must be a multiple of `c8n`
+// (threads then keep their channel group): c8n = 2^a or 3 * 2^a -> round the block count up to a multiple of 3 if needed.
+int grid_mult(long long total, int c8n) {
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  if (256 % c8n) g = (g + 2) / 3 * 3;
+  return (int)g;
+}
+
 int grid_for(long long total, int block, int cap = 148 * 16) {
   long long g = (total + block - 1) / block;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -507,8 +542,12 @@ int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* be
   channel_reduce_kernel<0><<<grid_for(pixels, lanes * 16, kReduceBlocks), 256, 0, st>>>(
       z, nullptr, nullptr, nullptr, nullptr, pixels, C, 0, sums, sums + 2 * C, counter, fin);
   if (check("bn stats")) return 1;
-  bn_apply_kernel<<<grid_for(pixels * (C / 8), 256), 256, 0, st>>>(z, mean, rstd, gamma, beta, residual, relu, y, N, H,
-                                                                  W, C);
+  PixIdx px;
+  px.init(C, H, W);
+  if (pixels * (C / 8) >= (1ll << 31)) { set_error("bn_train_forward: tensor too large for 32-bit item indexing"); return 1; }
+  if (256 % (C / 8) && (C / 8) % 3) { set_error("bn_train_forward: C=%d unsupported", C); return 1; }
+  bn_apply_kernel<<<grid_mult(pixels * (C / 8), C / 8), 256, 0, st>>>(z, mean, rstd, gamma, beta, residual, relu, y, N, H,
+                                                                  W, C, px);
   return check("bn apply");
 }
 
@@ -523,9 +562,13 @@ int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __n
   channel_reduce_kernel<1><<<grid_for(pixels, lanes * 16, kReduceBlocks), 256, 0, st>>>(
       dy, y, z, mean, rstd, pixels, C, relu, sums, sums + 2 * C, counter, BnFinalize{});
   if (check("bn backward reduce")) return 1;
-  bn_backward_kernel<<<grid_for(pixels * (C / 8), 256), 256, 0, st>>>(dy, y, z, mean, rstd, gamma, sums,
+  PixIdx px;
+  px.init(C, H, W);
+  if (pixels * (C / 8) >= (1ll << 31)) { set_error("bn_train_backward: tensor too large for 32-bit item indexing"); return 1; }
+  if (256 % (C / 8) && (C / 8) % 3) { set_error("bn_train_backward: C=%d unsupported", C); return 1; }
+  bn_backward_kernel<<<grid_mult(pixels * (C / 8), C / 8), 256, 0, st>>>(dy, y, z, mean, rstd, gamma, sums,
                                                                      (float)((long long)N * H * W), relu, dz, dres, N,
-                                                                     H, W, C);
+                                                                     H, W, C, px);
   return check("bn backward");
 }
 
@@ -537,7 +580,10 @@ int sum_relu_forward(const __nv_bfloat16* const* same, int n_same, const __nv_bf
   for (int i = 0; i < n_same; ++i) a.same[i] = same[i];
   for (int i = 0; i < n_up; ++i) { a.up[i] = up[i]; a.shift[i] = shift[i]; }
   const long long total = (long long)N * (H + 1) * (W + 1) * (C / 8);
-  sum_relu_kernel<<<grid_for(total, 256), 256, 0, st>>>(a, y, N, H, W, C);
+  PixIdx px;
+  px.init(C, H, W);
+  if (total >= (1ll << 31)) { set_error("sum_relu: tensor too large for 32-bit item indexing"); return 1; }
+  sum_relu_kernel<<<grid_for(total, 256), 256, 0, st>>>(a, y, N, H, W, C, px);
   return check("sum_relu");
 }
 
@@ -566,7 +612,10 @@ int zero_stuff(const __nv_bfloat16* dz, __nv_bfloat16* u, int N, int H, int W, i
   const long long total = (long long)N * (H + 1) * (W + 1) * (C / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  zero_stuff_kernel<<<(int)blocks, 256, 0, st>>>(dz, u, N, H, W, C);
+  PixIdx px;
+  px.init(C, H, W);
+  if (total >= (1ll << 31)) { set_error("zero_stuff: tensor too large for 32-bit item indexing"); return 1; }
+  zero_stuff_kernel<<<(int)blocks, 256, 0, st>>>(dz, u, N, H, W, C, px);
   return check("zero_stuff");
 }
 
