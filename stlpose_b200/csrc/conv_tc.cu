@@ -34,6 +34,7 @@ constexpr uint32_t kCtlBytes = 4096;   // [0,1024): barriers + TMEM base ; [1024
 constexpr uint32_t kBiasOffset = 1024;
 constexpr int kMaxCoutPad = 768;
 constexpr int kEpiStaged = 0, kEpiDirect = 1, kEpiNchw = 2;
+constexpr int kEpiStagedS2 = 3;  // staged epilogue on structured (stride-2) tiles: panels are 4-D TMA boxes (c, w, h, n)
 constexpr size_t kMaxSmem = 227 * 1024;
 
 struct Ctl {
@@ -217,7 +218,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t b_base = a_base + (uint32_t)p.a_stages * p.a_stage_bytes;
 
   constexpr bool NCHW = EPI == kEpiNchw;
-  constexpr bool kFlatOnly = EPI != kEpiDirect;  // staged / NCHW kernels are only ever launched in flat mode
+  constexpr bool kFlatOnly = EPI == kEpiStaged || EPI == kEpiNchw;  // these kernels are only ever launched in flat mode
+  constexpr bool kStruct = EPI == kEpiStagedS2;                     // ... and this one only on structured tiles
+  constexpr bool kStagedEpi = EPI == kEpiStaged || EPI == kEpiStagedS2;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kSpan = 32u * KSTEPS;
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int nti = (int)(tile % p.n_ntiles);
       const long long mt = mtile(tile);
       int q0 = 0, wo0 = 0, ho0 = 0, n0 = 0;
-      if (kFlatOnly || p.mode == 0) {
+      if (kFlatOnly || (!kStruct && p.mode == 0)) {
         q0 = p.q_lo + (int)(mt * (128 * MB));
       } else {
         wo0 = (int)(mt % p.tiles_w) * p.bw;
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               if (!PAIR) mbar_expect_tx(&ctl->a_full[s], p.a_tx_bytes);
               else if (is_leader) mbar_expect_tx(&ctl->a_full[s], 2u * p.a_tx_bytes);
               const uint32_t dst = a_base + s * p.a_stage_bytes;
-              if (kFlatOnly || p.mode == 0) {
+              if (kFlatOnly || (!kStruct && p.mode == 0)) {
                 const int row0 = p.a_shift ? q0 - p.halo : q0 + (kh - 1) * p.in_Wp + (kw - 1);
                 for (int i = 0; i < p.a_pieces; ++i) {
                   if (PAIR)
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ------------------------------------------------------------------ epilogue DMA warp of one group: moves staged
     // panels between shared and global memory with TMA so that the 8 compute warps never wait on an issue slot
     const int group = warp - 18;
-    if (EPI == kEpiStaged && (p.n_accbuf >= 2 || group == 0)) {
+    if (kStagedEpi && (p.n_accbuf >= 2 || group == 0)) {
       const int nt = p.nt, n_ntiles = p.n_ntiles;
       const int panel_ch = p.panel_ch, npanels = nt / panel_ch;
       const int PT = MB * npanels, bp = p.epi_batch;
@@ -513,10 +516,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const int cnt = PT - b0 < bp ? PT - b0 : bp;
           uint64_t* bar = &ctl->res_full[group * 2 + sb];
           mbar_expect_tx(bar, (uint32_t)cnt * 128u * pitch);
+          const long long mt_ = mtile(t);
           for (int i = 0; i < cnt; ++i) {
             const int idx = b0 + i, m = idx / npanels, pn = idx - m * npanels;
-            tma_load_2d_s(stage0 + (sb * (uint32_t)bp + (uint32_t)i) * panel_bytes, &p.tmR, bar,
-                          nti_ * nt + pn * panel_ch, q0 + m * 128);
+            const uint32_t dst = stage0 + (sb * (uint32_t)bp + (uint32_t)i) * panel_bytes;
+            if (kStruct)   // block m of a structured tile = images [n0 + m*bn1, +bn1) of the (bw x bh) window
+              tma_load_4d_s(dst, &p.tmR, bar, nti_ * nt + pn * panel_ch, (int)(mt_ % p.tiles_w) * p.bw,
+                            (int)((mt_ / p.tiles_w) % p.tiles_h) * p.bh,
+                            (int)(mt_ / ((long long)p.tiles_w * p.tiles_h)) * p.bn + m * (p.bn / MB));
+            else
+              tma_load_2d_s(dst, &p.tmR, bar, nti_ * nt + pn * panel_ch, q0 + m * 128);
           }
         };
         uint32_t kb = 0;
@@ -544,10 +553,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_wait(&ctl->epi_done[group * 2 + sb], (kb >> 1) & 1);
             if (skip != 1) {
               const int cnt = PT - b0 < bp ? PT - b0 : bp;
+              const long long mt_ = mtile(tile);
               for (int i = 0; i < cnt; ++i) {
                 const int idx = b0 + i, m = idx / npanels, pn = idx - m * npanels;
-                tma_store_2d_s(&p.tmO, stage0 + (sb * (uint32_t)bp + (uint32_t)i) * panel_bytes,
-                               nti * nt + pn * panel_ch, q0 + m * 128);
+                const uint32_t src = stage0 + (sb * (uint32_t)bp + (uint32_t)i) * panel_bytes;
+                if (kStruct)
+                  tma_store_4d_s(&p.tmO, src, nti * nt + pn * panel_ch, (int)(mt_ % p.tiles_w) * p.bw,
+                                 (int)((mt_ / p.tiles_w) % p.tiles_h) * p.bh,
+                                 (int)(mt_ / ((long long)p.tiles_w * p.tiles_h)) * p.bn + m * (p.bn / MB));
+                else
+                  tma_store_2d_s(&p.tmO, src, nti * nt + pn * panel_ch, q0 + m * 128);
               }
               bulk_commit();
             }
@@ -577,7 +592,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int row0 = quarter * 32 + lane;
     uint32_t acc_it = 0;
     DBG_TICK();
-    if constexpr (EPI == kEpiStaged) {
+    if constexpr (kStagedEpi) {
       // ---- staged epilogue: batches of 128-row x panel_ch panels live in shared memory; the residual arrives by
       // TMA, each thread updates its own row cells in place, finished panels leave by TMA (issued by this group's
       // DMA warp).  Global memory only ever sees whole lines; no block-wide barrier is involved.
@@ -876,20 +891,18 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     cuuint32_t es[2] = {1, 1};
     if (encode(&p.tmA, s.in, 2, dims, strides, box, es, span)) return 1;
   } else {
-    // structured tile (bw x bh x bn output pixels) with bw*bh*bn = 128*mb
+    // structured tile: every 128-row accumulator block is a (bw x bh x bn1) box of output pixels (bw*bh*bn1 = 128, the
+    // widest bw first), so a staged panel is one 4-D TMA box; a tile stacks mb blocks along the image index
     bool found = false;
-    for (; mb >= 1 && !found; --mb) {
-      const int R = 128 * mb;
-      for (int bw = p.W; bw >= 1 && !found; --bw) {
-        if (p.W % bw || R % bw || bw > 128) continue;
-        const int rem = R / bw;
-        for (int bh = p.H; bh >= 1 && !found; --bh) {
-          if (p.H % bh || rem % bh || bh > 128) continue;
-          const int bn = rem / bh;
-          if (bn > 256) continue;
-          p.bw = bw; p.bh = bh; p.bn = bn; p.mb = mb;
-          found = true;
-        }
+    for (int bw = p.W < 128 ? p.W : 128; bw >= 1 && !found; --bw) {
+      if (p.W % bw || 128 % bw) continue;
+      const int rem = 128 / bw;
+      for (int bh = p.H < rem ? p.H : rem; bh >= 1 && !found; --bh) {
+        if (p.H % bh || rem % bh) continue;
+        const int bn1 = rem / bh;
+        if (bn1 * mb > 256) continue;
+        p.bw = bw; p.bh = bh; p.bn = bn1 * mb; p.mb = mb;
+        found = true;
       }
     }
     if (!found) { set_error("conv: no structured tile for %dx%d output", p.H, p.W); return 1; }
@@ -925,7 +938,8 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   // weights stay resident in shared memory when every tile of the layer fits next to >= 2 activation stages;
   // otherwise they stream through a ring (one stage per (chunk, tap))
   // staged (TMA) epilogue for flat-mode bf16 outputs: 2 groups x 2 panel buffers x 16 KB
-  p.epi_tma = (p.mode == 0 && !s.out_nchw && s.n_up == 0 && !getenv("STL_DBG_NO_EPI_TMA")) ? 1 : 0;
+  p.epi_tma = (!s.out_nchw && s.n_up == 0 && !getenv("STL_DBG_NO_EPI_TMA") &&
+               (p.mode == 0 || (p.taps == 9 && !getenv("STL_DBG_NO_EPI_TMA_S2")))) ? 1 : 0;
   p.panel_ch = (p.nt % 64 == 0) ? 64 : p.nt;
   p.panel_swz = p.panel_ch == 64 ? 128 : (p.panel_ch == 32 ? 64 : 0);
   p.epi_panel_bytes = (uint32_t)((p.panel_ch * 2 * 128 + 1023) & ~1023);
@@ -1001,7 +1015,15 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   p.n_mma = (p.b_resident && (p.a_shift || p.taps == 1) && p.mb >= 2 && p.nt <= 32 && !getenv("STL_DBG_SINGLE_MMA")) ? 2 : 1;
   *smem_bytes = kCtlBytes + 1024 + (size_t)a_st * p.a_stage_bytes + p.b_bytes_total + epi_bytes;
   p.epi_base_off = (uint32_t)((size_t)a_st * p.a_stage_bytes + p.b_bytes_total);
-  if (p.epi_tma) {
+  if (p.epi_tma && p.mode == 1) {
+    // valid pixels only (W x H, not Wp x Hp): TMA clips partial tiles and never touches the zero cells
+    cuuint64_t dims[4] = {(cuuint64_t)s.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+    cuuint64_t strides[3] = {(cuuint64_t)s.cout * 2, (cuuint64_t)s.cout * 2 * p.Wp, (cuuint64_t)s.cout * 2 * p.Wp * p.Hp};
+    cuuint32_t box[4] = {(cuuint32_t)p.panel_ch, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)(p.bn / p.mb)};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (encode(&p.tmO, s.out, 4, dims, strides, box, es, (uint32_t)p.panel_swz)) return 1;
+    if (s.residual && encode(&p.tmR, s.residual, 4, dims, strides, box, es, (uint32_t)p.panel_swz)) return 1;
+  } else if (p.epi_tma) {
     cuuint64_t dims[2] = {(cuuint64_t)s.cout, (cuuint64_t)p.P};
     cuuint64_t strides[1] = {(cuuint64_t)s.cout * 2};
     cuuint32_t box[2] = {(cuuint32_t)p.panel_ch, 128};
@@ -1055,6 +1077,7 @@ typedef void (*ConvKernel)(const ConvParams);
 template <int MB, int KSTEPS>
 ConvKernel pick_variant(int taps, int epi, bool pair) {
   if (epi == kEpiNchw) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiNchw, false> : nullptr;
+  if (epi == kEpiStagedS2) return taps == 9 ? conv_tc_kernel<MB, KSTEPS, 9, kEpiStagedS2, false> : nullptr;
   if (epi == kEpiStaged) {
     if (pair) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiStaged, true> : conv_tc_kernel<MB, KSTEPS, 9, kEpiStaged, true>;
     return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiStaged, false> : conv_tc_kernel<MB, KSTEPS, 9, kEpiStaged, false>;
@@ -1078,7 +1101,9 @@ ConvKernel pick_kernel(int mb, int ksteps, int taps, int epi, bool pair) {
   }
   return nullptr;
 }
-int epi_kind(const ConvParams& p) { return p.out_nchw ? kEpiNchw : (p.epi_tma ? kEpiStaged : kEpiDirect); }
+int epi_kind(const ConvParams& p) {
+  return p.out_nchw ? kEpiNchw : (p.epi_tma ? (p.mode == 1 ? kEpiStagedS2 : kEpiStaged) : kEpiDirect);
+}
 }  // namespace
 
 int conv_launch_prepared(const ConvParams& p, int grid, size_t smem_bytes, cudaStream_t stream) {
@@ -1086,7 +1111,7 @@ int conv_launch_prepared(const ConvParams& p, int grid, size_t smem_bytes, cudaS
   if (!attr_set) {
     for (int mb = 1; mb <= 3; ++mb)
       for (int ks = 1; ks <= 4; ks *= 2)
-        for (int epi = 0; epi < 3; ++epi)
+        for (int epi = 0; epi < 4; ++epi)
           for (int taps = 1; taps <= 9; taps += 8)
             for (int pair = 0; pair < 2; ++pair) {
               if (pair && epi != kEpiStaged) continue;
