@@ -127,12 +127,12 @@ def run_reference(args):
         times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     value = sample / (ms / 1e3)
-    desc = f"{sample} crops per step (oracle port: torch-CPU fp32 HRNet-W32 x2 + NumPy flip-average/decode)"
+    desc = f"{sample} crops per step (oracle port: torch-CPU fp32 HRNet-W{WIDTH} x2 + NumPy flip-average/decode)"
     print(json.dumps({
-        "impl": "reference", "metric": "person crops/sec HRNet-W32 256x192 fwd+flip+decode", "value": value,
+        "impl": "reference", "metric": f"person crops/sec HRNet-W{WIDTH} {IMAGE[0]}x{IMAGE[1]} fwd+flip+decode", "value": value,
         "unit": "crops/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "HRNet-W32 256x192 inference + flip-test + get_final_preds decode",
+        "config": {"workload": f"HRNet-W{WIDTH} {IMAGE[0]}x{IMAGE[1]} inference + flip-test + get_final_preds decode",
                    "crops_per_step": sample, "device": "host CPU"},
         "cpu_baseline": {"value": value, "unit": "crops/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -145,7 +145,6 @@ def run_ours(args):
     import torch.distributed as dist
     import stlpose_b200 as S
     from stlpose_b200.pipeline import KeypointPipeline
-    from oracle import hrnet_oracle, pose_oracle   # synthetic checkpoint + boxes only; nothing on the timed path
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -156,16 +155,17 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
 
+    # BASELINE.json config 1/2: random-init weights, torch.manual_seed(0), default nn.Conv2d init, BatchNorm (1, 0, 0, 1)
+    torch.manual_seed(0)
     model = S.PoseHighResolutionNet(width=WIDTH, image_size=IMAGE)
-    model.load_state_dict(hrnet_oracle.synth_state_dict(WIDTH, seed=0), strict=True)
     model = model.to(dev).eval()
     pipe = KeypointPipeline(model, B, IMAGE, flip=True, use_graph=not args.no_graph)
 
     gen = torch.Generator().manual_seed(1000 + rank)
     x_host = torch.randn(B, 3, *IMAGE, generator=gen).pin_memory()
-    c_np, s_np = pose_oracle.synth_boxes(B, seed=rank)
-    c_host = torch.from_numpy(c_np).float().pin_memory()
-    s_host = torch.from_numpy(s_np).float().pin_memory()
+    c_host = (torch.rand(B, 2, generator=gen) * torch.tensor([400.0, 300.0]) + 100.0).pin_memory()   # box centres
+    hgt = torch.rand(B, 1, generator=gen) * 320.0 + 80.0                                                # box heights
+    s_host = (torch.cat([0.75 * hgt, hgt], dim=1) / 200.0 * 1.25).pin_memory()                          # _xywh2cs scale
     p_host = torch.empty(B, 17, 2).pin_memory()
     m_host = torch.empty(B, 17, 1).pin_memory()
     pipe.x.copy_(x_host); pipe.center.copy_(c_host); pipe.scale.copy_(s_host)
@@ -244,12 +244,12 @@ def run_ours(args):
         h2d = x_host.numel() * 4 + c_host.numel() * 4 + s_host.numel() * 4
         d2h = p_host.numel() * 4 + m_host.numel() * 4
         out = {
-            "metric": "person crops/sec HRNet-W32 256x192 fwd+flip+decode", "value": value, "unit": "crops/s",
+            "metric": f"person crops/sec HRNet-W{WIDTH} {IMAGE[0]}x{IMAGE[1]} fwd+flip+decode", "value": value, "unit": "crops/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "HRNet-W32 256x192 inference + flip-test + get_final_preds decode",
+            "config": {"workload": f"HRNet-W{WIDTH} {IMAGE[0]}x{IMAGE[1]} inference + flip-test + get_final_preds decode",
                        "crops_per_gpu_per_step": B, "forwards_per_crop": 2, "cuda_graph": pipe.graph is not None,
-                       "l2": "inputs (302 MB of crops per step) and activations exceed the 126 MB L2; no flush needed",
+                       "l2": f"inputs ({B * 3 * IMAGE[0] * IMAGE[1] * 4 / 1e6:.0f} MB of crops per step) and activations exceed the 126 MB L2; no flush needed",
                        "partition": f"batch sharded over {world} GPU(s); only exchange = all-gather of keypoints "
                                     f"(204 B/crop, inside the timed step when n_gpus > 1)"},
             "clocks": clocks,
@@ -288,8 +288,14 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=64, help="crops in the bounded CPU-baseline sample")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--width", type=int, default=32, choices=[32, 48],
+                    help="32: HRNet-W32 256x192 (the configuration the metric is quoted on); 48: HRNet-W48 384x288 (config 3)")
     ap.add_argument("--dump-ops", default="", help="write the per-launch timing table (JSON) to this path")
     args = ap.parse_args()
+    if args.width == 48:
+        global WIDTH, IMAGE, FLOPS_PER_FORWARD, NCU_TRAFFIC_BYTES_PER_LAUNCH, NCU_TRAFFIC_NOTE
+        WIDTH, IMAGE, FLOPS_PER_FORWARD = 48, (384, 288), 70.6132e9
+        NCU_TRAFFIC_BYTES_PER_LAUNCH, NCU_TRAFFIC_NOTE = None, "no ncu capture for the W48 shapes"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         # torchrun exports OMP_NUM_THREADS=1 and the OpenMP pool is sized when torch is first imported: give the

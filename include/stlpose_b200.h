@@ -54,6 +54,13 @@ int stl_decode(const float* heat, const float* heat_flipped, const float* center
  *   loss = 0.5/(J*B*hw) * sum (tw*(out-tgt))^2 ;  grad = tw^2*(out-tgt)/(J*B*hw)   (grad may be null)
  * out/tgt [B][J][hw] fp32, tw [B][J] fp32, loss: 1 float.  workspace: stl_mse_workspace_bytes() bytes. */
 size_t stl_mse_workspace_bytes(void);
+/* Second decode path: create_pose_from_outputs (lib/pose_parsing.py:138-151) =
+ * F.interpolate(heat, (out_h, out_w), mode="bilinear", align_corners=True) -> get_max_preds_hrnet, used by
+ * 04_evaluate_vases_qualitatively.py:216-220 and 05_create_archdata_retrieval_db.py:114.  Fused: the upsampled tensor
+ * is never written.  coords [B][J][2] = (x, y) in the upsampled grid (zeroed where the maximum is <= 0), maxvals [B][J]. */
+int stl_upsampled_argmax(const float* heat, int B, int J, int h, int w, int out_h, int out_w, float* coords,
+                         float* maxvals, void* stream);
+
 /* Crop extraction, the step in front of the network: TransformDetection.__call__ / crop
  * (lib/transforms.py:30-58, 259-268) and JointsDataset.__getitem__ (data/JointsDataset.py:189-197) call
  * cv2.warpAffine(img, M, (out_w, out_h), flags=INTER_LINEAR) per box.  img: uint8 [img_h][img_w][3] on the device;

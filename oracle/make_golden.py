@@ -110,7 +110,31 @@ def make_crops():
     print("crops", dets.shape, dets.dtype, "mean", dets.mean())
 
 
+def pose_entry_inputs():
+    """Blob heatmaps [3,17,64,48] (float16-exact values so platform libm cannot perturb them) with some weak joints."""
+    hm = pose_oracle.blob_heatmaps(3, 17, 64, 48, seed=21, noise=0.01).astype(np.float16).astype(np.float32)
+    hm[0, 3] *= 0.05            # below the 0.1 confidence threshold
+    hm[1, 7] *= 0.02
+    hm[2, 16] = -np.abs(hm[2, 16])   # nothing positive: coordinates zeroed, visibility 0
+    return hm
+
+
+def make_pose_entries():
+    import torch
+    L = ref_shim.lib()
+    hm = pose_entry_inputs()
+    entries, allk = L.pose_parsing.create_pose_from_outputs(torch.from_numpy(hm), keypoint_thr=0.1)
+    import torch.nn.functional as F
+    scaled = F.interpolate(torch.from_numpy(hm).clone(), (256, 192), mode="bilinear", align_corners=True)
+    coords, maxv = L.pose_parsing.get_max_preds_hrnet(scaled.numpy())
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "pose_entries.npz"), entries=np.array(entries), all_keypoints=allk,
+                        coords=coords, maxvals=maxv)
+    print("pose entries", np.array(entries).shape, allk.shape)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "pose_entries":
+        return make_pose_entries()
     if len(sys.argv) > 1 and sys.argv[1] == "pck":
         return make_pck()
     if len(sys.argv) > 1 and sys.argv[1] == "crops":
@@ -160,6 +184,7 @@ def main():
         print(f"w{width}: y range [{y.min():.3f}, {y.max():.3f}] std {y.std():.3f}")
     make_pck()
     make_crops()
+    make_pose_entries()
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))
 

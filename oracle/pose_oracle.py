@@ -270,6 +270,48 @@ def transform_detection(img, list_coords, det_width=192, det_height=256):
     return dets.transpose(0, 3, 1, 2), centers, scales
 
 
+# ----------------------------------------------------------------------------------------------
+# second decode path: lib/pose_parsing.py:107-151
+# ----------------------------------------------------------------------------------------------
+def create_pose_entries(keypoints, max_vals=None, thr=0.1):
+    """pose_parsing.py:107-135."""
+    if len(keypoints) == 0:
+        all_keypoints = []
+    else:
+        all_keypoints = np.array([(*item, 1, 1) for sublist in keypoints for item in sublist])
+        idx = np.argwhere(all_keypoints == -1)
+        all_keypoints[idx[:, 0], :] = -1
+        if max_vals is not None:
+            idx = np.argwhere(max_vals[:, :, 0] < thr)
+            all_keypoints[idx[:, 0] * 17 + idx[:, 1], -1] = 0
+    pose_entries = []
+    for idx, cur_pose in enumerate(keypoints):
+        entry = np.ones(19) * -1
+        for i, kpt in enumerate(cur_pose):
+            if kpt[0] != -1:
+                entry[i] = 17 * idx + i
+        entry[-2] = len(np.where(entry[:-2] != -1)[0])
+        pose_entries.append(entry)
+    return pose_entries, all_keypoints
+
+
+def upsampled_max_preds(dets, size=(256, 192)):
+    """pose_parsing.py:143-144: F.interpolate(dets, size, bilinear, align_corners=True) (torch, third-party: the same
+    library call the reference makes) -> get_max_preds."""
+    import torch
+    import torch.nn.functional as F
+    scaled = F.interpolate(torch.as_tensor(dets).clone(), size, mode="bilinear", align_corners=True)
+    return get_max_preds(scaled.numpy())
+
+
+def create_pose_from_outputs(dets, keypoint_thr=0.1):
+    """pose_parsing.py:138-151."""
+    coords, max_vals = upsampled_max_preds(dets)
+    pose_entries, all_keypoints = create_pose_entries(coords, max_vals, thr=keypoint_thr)
+    all_keypoints = np.array([all_keypoints[:, 1], all_keypoints[:, 0], all_keypoints[:, 2], all_keypoints[:, 3]]).T
+    return pose_entries, all_keypoints
+
+
 def calc_dists(preds, target, normalize):
     """metrics.py:268-296: normalised distance per (joint, sample); -1 where the target is not > 1 in x and y."""
     preds = preds.astype(np.float32)

@@ -134,6 +134,7 @@ struct FuseArgs {
   int n_up;
   __nv_bfloat16* y;
   int N, H, W, C;
+  FastDiv fd_c8, fd_wp, fd_hp;   // multiply-shift division of the flat item index (items < 2^31)
 };
 
 __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseArgs a) {
@@ -141,11 +142,11 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseArgs a) {
   // four 16-byte loads are in flight before the first one is consumed
   const int c8n = a.C / 8;
   const int Wp = a.W + 1, Hp = a.H + 1;
-  const long long total = (long long)a.N * Hp * Wp * c8n;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+  const uint32_t total = (uint32_t)a.N * (uint32_t)(Hp * Wp * c8n);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
     uint4 u[4];
-    long long idx[4];
+    uint32_t idx[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       idx[k] = i0 + k * stride;
@@ -154,12 +155,12 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseArgs a) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (idx[k] >= total) continue;
-      const int c8 = (int)(idx[k] % c8n);
-      const long long q = idx[k] / c8n;
-      const int w = (int)(q % Wp);
-      const long long t = q / Wp;
-      const int h = (int)(t % Hp);
-      const int n = (int)(t / Hp);
+      const uint32_t q = a.fd_c8.div(idx[k]);
+      const int c8 = (int)(idx[k] - q * (uint32_t)c8n);
+      const uint32_t t = a.fd_wp.div(q);
+      const int w = (int)(q - t * (uint32_t)Wp);
+      const int n = (int)a.fd_hp.div(t);
+      const int h = (int)t - n * Hp;
       uint4 out = make_uint4(0, 0, 0, 0);
       if (h < a.H && w < a.W) {
         float f[8] = {bf16_lo(u[k].x), bf16_hi(u[k].x), bf16_lo(u[k].y), bf16_hi(u[k].y),
@@ -287,8 +288,12 @@ int fuse_sum(const __nv_bfloat16* x, const __nv_bfloat16* const* z, const int* s
   a.x = x; a.y = y; a.n_up = n_up; a.N = N; a.H = H; a.W = W; a.C = C;
   for (int i = 0; i < n_up; ++i) { a.z[i] = z[i]; a.shift[i] = shift[i]; }
   const long long total = (long long)N * (H + 1) * (W + 1) * (C / 8);
+  if (total >= (1ll << 31) - 4ll * 148 * 16 * 256) { set_error("fuse_sum: tensor too large for 32-bit item indexing"); return 1; }
+  a.fd_c8.init((uint32_t)(C / 8));
+  a.fd_wp.init((uint32_t)(W + 1));
+  a.fd_hp.init((uint32_t)(H + 1));
   long long blocks = (total + 4 * 256 - 1) / (4 * 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
   fuse_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
   return check("fuse_sum");
 }

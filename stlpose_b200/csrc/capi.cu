@@ -70,6 +70,13 @@ int stl_decode(const float* heat, const float* heat_flipped, const float* center
 
 size_t stl_mse_workspace_bytes(void) { return mse_workspace_bytes(); }
 
+int stl_upsampled_argmax(const float* heat, int B, int J, int h, int w, int out_h, int out_w, float* coords,
+                         float* maxvals, void* stream) {
+  if (!have_device()) return 1;
+  if (B > 0 && (!heat || !coords || !maxvals)) { set_error("stl_upsampled_argmax: null pointer"); return 1; }
+  return upsampled_argmax(heat, B, J, h, w, out_h, out_w, coords, maxvals, (cudaStream_t)stream);
+}
+
 int stl_warp_affine_crops(const void* img_u8_hwc, int img_h, int img_w, const double* minv, int N, int out_h, int out_w,
                           void* out_u8_nchw, float* out_f32_nchw, const float* mean3_host, const float* std3_host,
                           void* stream) {

@@ -194,6 +194,64 @@ __global__ void mse_final_kernel(const double* __restrict__ partial, int n, doub
   }
 }
 
+// ------------------------------------------------------------------ arg-max of the bilinearly upsampled heatmaps
+// create_pose_from_outputs (lib/pose_parsing.py:138-151; 04_evaluate_vases_qualitatively.py:216-220,
+// 05_create_archdata_retrieval_db.py:114,131-147): F.interpolate(dets, (256, 192), mode="bilinear", align_corners=True)
+// followed by get_max_preds_hrnet.  One warp per (crop, joint) map evaluates the out_h x out_w samples on the fly --
+// the 16x larger tensor is never materialised -- with torch's upsample_bilinear2d arithmetic (fp32: source index =
+// o * (in-1)/(out-1), lambda = index - floor, value = l0h*(l0w*v00 + l1w*v01) + l1h*(l0w*v10 + l1w*v11), no fused
+// multiply-adds) and np.argmax's first-index tie rule.
+__global__ void __launch_bounds__(256) upsampled_argmax_kernel(const float* __restrict__ heat, int B, int J, int h, int w,
+                                                               int out_h, int out_w, float* __restrict__ coords,
+                                                               float* __restrict__ maxvals) {
+  const int lane = threadIdx.x & 31;
+  const long long map = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (map >= (long long)B * J) return;
+  const float* a = heat + map * (long long)h * w;
+  const float sh = out_h > 1 ? (float)(h - 1) / (float)(out_h - 1) : 0.f;
+  const float sw = out_w > 1 ? (float)(w - 1) / (float)(out_w - 1) : 0.f;
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  for (int oy = 0; oy < out_h; ++oy) {
+    const float h1r = __fmul_rn(sh, (float)oy);
+    int h1 = (int)h1r;
+    if (h1 > h - 1) h1 = h - 1;
+    const int h1p = h1 < h - 1 ? 1 : 0;
+    float l1h = __fsub_rn(h1r, (float)h1);
+    l1h = fminf(fmaxf(l1h, 0.f), 1.f);
+    const float l0h = __fsub_rn(1.f, l1h);
+    const float* r0 = a + h1 * w;
+    const float* r1 = r0 + h1p * w;
+    for (int ox = lane; ox < out_w; ox += 32) {
+      const float w1r = __fmul_rn(sw, (float)ox);
+      int w1 = (int)w1r;
+      if (w1 > w - 1) w1 = w - 1;
+      const int w1p = w1 < w - 1 ? 1 : 0;
+      float l1w = __fsub_rn(w1r, (float)w1);
+      l1w = fminf(fmaxf(l1w, 0.f), 1.f);
+      const float l0w = __fsub_rn(1.f, l1w);
+      const float top = __fadd_rn(__fmul_rn(l0w, __ldg(r0 + w1)), __fmul_rn(l1w, __ldg(r0 + w1 + w1p)));
+      const float bot = __fadd_rn(__fmul_rn(l0w, __ldg(r1 + w1)), __fmul_rn(l1w, __ldg(r1 + w1 + w1p)));
+      const float v = __fadd_rn(__fmul_rn(l0h, top), __fmul_rn(l1h, bot));
+      const int i = oy * out_w + ox;
+      if (v > best) { best = v; best_i = i; }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+  }
+  if (lane != 0) return;
+  if (best_i == 0x7fffffff) best_i = 0;
+  float cx = (float)(best_i % out_w), cy = (float)(best_i / out_w);      // pose_parsing.py:44-53
+  if (!(best > 0.f)) { cx = 0.f; cy = 0.f; }
+  coords[map * 2 + 0] = cx;
+  coords[map * 2 + 1] = cy;
+  maxvals[map] = best;
+}
+
 // ------------------------------------------------------------------ crop extraction (the step before the network)
 // cv2.warpAffine(img, M, (out_w, out_h), flags=INTER_LINEAR) of lib/transforms.py:38-43 / JointsDataset.py:189-197 for
 // uint8 HWC images, one launch for all boxes of an image: OpenCV's fixed-point algorithm -- source coordinates in
@@ -352,6 +410,15 @@ int decode(const float* heat, const float* heat_f, const float* center, const fl
   decode_kernel<<<(unsigned)((maps + warps_per_block - 1) / warps_per_block), warps_per_block * 32, 0, st>>>(
       heat, heat_f, center, scale, B, J, h, w, perm, refine, avg_out, preds, maxvals, coords);
   return check("decode");
+}
+
+int upsampled_argmax(const float* heat, int B, int J, int h, int w, int out_h, int out_w, float* coords, float* maxvals,
+                     cudaStream_t st) {
+  const long long maps = (long long)B * J;
+  if (maps <= 0) return 0;
+  if (h <= 0 || w <= 0 || out_h <= 0 || out_w <= 0) { set_error("upsampled_argmax: bad geometry"); return 1; }
+  upsampled_argmax_kernel<<<(unsigned)((maps + 7) / 8), 256, 0, st>>>(heat, B, J, h, w, out_h, out_w, coords, maxvals);
+  return check("upsampled_argmax");
 }
 
 int warp_affine_crops(const uint8_t* img, int ih, int iw, const double* minv, int N, int out_h, int out_w,

@@ -17,6 +17,8 @@ int flip_back(const float* in, float* out, int B, int J, int h, int w, const int
 int decode(const float* heat, const float* heat_f, const float* center, const float* scale, int B, int J, int h,
            int w, const int* pairs, int n_pairs, int refine, float* avg_out, float* preds, float* maxvals,
            float* coords, cudaStream_t st);
+int upsampled_argmax(const float* heat, int B, int J, int h, int w, int out_h, int out_w, float* coords, float* maxvals,
+                     cudaStream_t st);
 int warp_affine_crops(const uint8_t* img, int ih, int iw, const double* minv, int N, int out_h, int out_w,
                       uint8_t* out_u8, float* out_f, const float* mean3, const float* std3, cudaStream_t st);
 int pck_accuracy(const float* pred, const float* tgt, int B, int J, int h, int w, float thr, float* acc, float* avg_acc,

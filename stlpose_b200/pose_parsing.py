@@ -54,3 +54,52 @@ def get_final_preds_hrnet(heatmaps, center, scale, as_tensor=False):
     if as_tensor:
         return preds, maxvals, coords
     return preds.cpu().numpy(), maxvals.cpu().numpy(), coords.cpu().numpy()
+
+
+def get_max_preds_upsampled(heatmaps, size=(256, 192), as_tensor=False):
+    """get_max_preds_hrnet(F.interpolate(heatmaps, size, mode="bilinear", align_corners=True)) without materialising the
+    upsampled tensor (pose_parsing.py:143-144).  -> (preds [N,J,2], maxvals [N,J,1])."""
+    heat = _as_cuda_f32(heatmaps)
+    B, J, h, w = heat.shape
+    if B == 0:
+        return [], []
+    coords = torch.empty((B, J, 2), dtype=torch.float32, device=heat.device)
+    maxvals = torch.empty((B, J, 1), dtype=torch.float32, device=heat.device)
+    with torch.cuda.device(heat.device):
+        _lib.check(_lib.lib().stl_upsampled_argmax(_lib.ptr(heat), B, J, h, w, int(size[0]), int(size[1]),
+                                                   _lib.ptr(coords), _lib.ptr(maxvals), _lib.current_stream()))
+    if as_tensor:
+        return coords, maxvals
+    return coords.cpu().numpy(), maxvals.cpu().numpy()
+
+
+def create_pose_entries(keypoints, max_vals=None, thr=0.1):
+    """pose_parsing.py:107-135: (pose_entries list of 19-vectors, all_keypoints [N*17,4]) from per-person keypoints;
+    keypoints below the confidence threshold get visibility 0.  Small host-side bookkeeping, NumPy like the reference."""
+    if len(keypoints) == 0:
+        all_keypoints = []
+    else:
+        kp = np.asarray(keypoints)
+        all_keypoints = np.concatenate([kp.reshape(-1, kp.shape[-1]), np.ones((kp.shape[0] * kp.shape[1], 2), kp.dtype)], axis=1)
+        rows = np.argwhere(all_keypoints == -1)[:, 0]
+        all_keypoints[rows, :] = -1
+        if max_vals is not None:
+            low = np.argwhere(np.asarray(max_vals)[:, :, 0] < thr)
+            all_keypoints[low[:, 0] * 17 + low[:, 1], -1] = 0
+    pose_entries = []
+    for idx, cur_pose in enumerate(keypoints):
+        entry = np.ones(19) * -1
+        for i, kpt in enumerate(cur_pose):
+            if kpt[0] != -1:
+                entry[i] = 17 * idx + i
+        entry[-2] = len(np.where(entry[:-2] != -1)[0])
+        pose_entries.append(entry)
+    return pose_entries, all_keypoints
+
+
+def create_pose_from_outputs(dets, keypoint_thr=0.1):
+    """pose_parsing.py:138-151: upsample to 256x192, arg-max, pose entries; all_keypoints columns (y, x, 1, visible)."""
+    keypoint_coords, max_vals = get_max_preds_upsampled(dets, (256, 192))
+    pose_entries, all_keypoints = create_pose_entries(keypoint_coords, max_vals, thr=keypoint_thr)
+    all_keypoints = np.array([all_keypoints[:, 1], all_keypoints[:, 0], all_keypoints[:, 2], all_keypoints[:, 3]]).T
+    return pose_entries, all_keypoints

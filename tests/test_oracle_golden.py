@@ -128,3 +128,14 @@ def test_crop_extraction_oracle_matches_reference_fixture(golden):
     assert np.array_equal(pose_oracle.warp_affine_u8(img, m, (192, 256)), g["rot30"])
     d0, c0, s0 = pose_oracle.transform_detection(img, [])
     assert len(d0) == 0 and len(c0) == 0
+
+
+def test_upsampled_decode_and_pose_entries_match_reference_fixture(golden):
+    from oracle.make_golden import pose_entry_inputs
+    g = golden("pose_entries.npz")
+    hm = pose_entry_inputs()
+    coords, maxv = pose_oracle.upsampled_max_preds(hm)
+    assert np.array_equal(coords, g["coords"]) and np.allclose(maxv, g["maxvals"], rtol=1e-6, atol=1e-7)
+    entries, allk = pose_oracle.create_pose_from_outputs(hm, keypoint_thr=0.1)
+    assert np.array_equal(np.array(entries), g["entries"]) and np.array_equal(allk, g["all_keypoints"])
+    assert allk[0 * 17 + 3, 3] == 0 and allk[1 * 17 + 7, 3] == 0 and allk[2 * 17 + 16, 3] == 0

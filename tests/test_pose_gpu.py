@@ -195,3 +195,30 @@ def test_crop_extraction_bit_exact(golden):
     assert len(e_d) == 0 and len(e_c) == 0 and len(e_s) == 0
     # end to end: boxes -> network input -> keypoints runs without touching the host with the crops
     assert x.shape == (5, 3, 256, 192)
+
+
+def test_upsampled_decode_and_pose_entries(golden):
+    """Fused bilinear-upsample + arg-max (stl_upsampled_argmax) and create_pose_from_outputs vs the reference fixture."""
+    from oracle.make_golden import pose_entry_inputs
+    from stlpose_b200 import pose_parsing as PP
+    g = golden("pose_entries.npz")
+    hm = pose_entry_inputs()
+    coords, maxv = PP.get_max_preds_upsampled(hm, (256, 192))
+    assert coords.shape == (3, 17, 2) and maxv.shape == (3, 17, 1)
+    assert np.allclose(maxv, g["maxvals"], rtol=2e-6, atol=1e-7)
+    assert np.array_equal(coords, g["coords"])              # blob maxima: top-2 margin far above the 1-ulp arithmetic slack
+    entries, allk = PP.create_pose_from_outputs(torch.from_numpy(hm).cuda(), keypoint_thr=0.1)
+    assert np.array_equal(np.array(entries), g["entries"]) and np.array_equal(allk, g["all_keypoints"])
+    # other sizes, random maps: compare against torch's own upsample (the reference's library call) with a margin rule
+    rng = np.random.default_rng(9)
+    for (h, w, oh, ow) in ((96, 72, 384, 288), (16, 12, 50, 37), (8, 6, 8, 6)):
+        x = rng.standard_normal((5, 17, h, w)).astype(np.float32)
+        c, m = PP.get_max_preds_upsampled(x, (oh, ow))
+        up = torch.nn.functional.interpolate(torch.from_numpy(x), (oh, ow), mode="bilinear", align_corners=True).numpy()
+        rc, rm = pose_oracle.get_max_preds(up)
+        assert np.allclose(m, rm, rtol=2e-6, atol=1e-6)
+        flat = np.sort(up.reshape(5, 17, -1), axis=2)
+        clear = (flat[..., -1] - flat[..., -2]) > 1e-5        # ties within float rounding may resolve either way
+        assert clear.mean() > 0.9 and np.array_equal(c[clear], rc[clear])
+    e0, k0 = PP.create_pose_entries([], None)
+    assert e0 == [] and k0 == []
