@@ -102,6 +102,14 @@ int stl_padded_to_nchw(const void* y_padded, float* x_nchw, int N, int C, int H,
 int stl_pack_conv_weights(const float* w_oihw, const float* bn_gamma, const float* bn_beta, const float* bn_mean,
                           const float* bn_var, const float* conv_bias, float eps, int Cout, int Cin, int ksize,
                           int Cout_pad, int Cin_pad, void* w_packed, float* bias_packed, void* stream);
+/* One BasicBlock (models/HRnet.py:45-61, eval mode, BatchNorm folded by stl_pack_conv_weights) in one kernel:
+ *   y = relu(conv2(relu(conv1(x) + bias1)) + bias2 + x), both convolutions 3x3 / stride 1 / C -> C, C = 32.
+ * The intermediate activation stays in shared memory (conv1's accumulators are written as conv2's tensor-core operand).
+ * x, y: padded-linear bf16 [N][H+1][W+1][C] (distinct buffers); w*_packed: [9][C][C] bf16; bias*: C fp32.
+ * Results are bit-identical to two stl_conv2d calls. */
+int stl_basic_block(const void* x, void* y, const void* w1_packed, const float* bias1, const void* w2_packed,
+                    const float* bias2, int N, int H, int W, int C, void* stream);
+
 /* Weights for the convolution that IS the stride-1 input gradient: dx = stl_conv2d(dz, W'), W'[ci][co][kh][kw] =
  * W[co][ci][k-1-kh][k-1-kw].  w: fp32 OIHW of the forward layer; result [k*k][Rows_pad][K_pad] bf16 with Rows_pad >= Cin
  * (multiple of 16) and K_pad >= Cout (the channel count of dz); bias_packed (Rows_pad floats, may be null) is zeroed. */

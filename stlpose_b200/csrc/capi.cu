@@ -131,6 +131,15 @@ int stl_pack_conv_weights(const float* w, const float* g, const float* b, const 
                       reinterpret_cast<__nv_bfloat16*>(w_packed), bias_packed, (cudaStream_t)stream);
 }
 
+int stl_basic_block(const void* x, void* y, const void* w1_packed, const float* bias1, const void* w2_packed,
+                    const float* bias2, int N, int H, int W, int C, void* stream) {
+  if (!have_device()) return 1;
+  if (!x || !y || !w1_packed || !bias1 || !w2_packed || !bias2) { set_error("stl_basic_block: null pointer"); return 1; }
+  if (!basic_block_supported(H, W, C)) { set_error("stl_basic_block: unsupported shape C=%d %dx%d", C, H, W); return 1; }
+  return basic_block_launch((const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)w1_packed, bias1,
+                            (const __nv_bfloat16*)w2_packed, bias2, N, H, W, 0, (cudaStream_t)stream);
+}
+
 int stl_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, int Rows_pad, int K_pad, void* w_packed,
                                 float* bias_packed, void* stream) {
   if (!have_device()) return 1;

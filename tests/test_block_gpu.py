@@ -1,0 +1,57 @@
+"""Fused BasicBlock kernel (stl_basic_block) vs the same block as two fused convolutions (stl_conv2d) and vs torch."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import bf16_round, from_padded, pack, padded_border_is_zero, to_padded
+from stlpose_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _bn(c, g):
+    return dict(weight=torch.rand(c, device=DEV, generator=g) + 0.5, bias=torch.randn(c, device=DEV, generator=g) * 0.1,
+                running_mean=torch.randn(c, device=DEV, generator=g) * 0.1,
+                running_var=torch.rand(c, device=DEV, generator=g) + 0.5)
+
+
+def _conv(L, xin, out, n, h, w, c, wp, bp, residual=None):
+    d = _lib.ConvDesc()
+    d.in_ = xin.data_ptr(); d.N, d.H, d.W, d.Cin = n, h, w, c
+    d.out = out.data_ptr(); d.Cout, d.Cout_pad = c, c
+    d.ksize, d.stride = 3, 1
+    d.w_packed = wp.data_ptr(); d.bias_packed = bp.data_ptr()
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.relu = 1
+    _lib.check(L.stl_conv2d(ctypes.byref(d), _lib.current_stream()))
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 64, 48), (3, 64, 48), (70, 64, 48), (5, 16, 12), (2, 8, 6), (130, 32, 24)])
+def test_fused_basic_block_equals_two_convs(n, h, w):
+    L = _lib.lib()
+    c = 32
+    g = torch.Generator(device=DEV).manual_seed(n * 100 + h)
+    x = bf16_round(torch.randn(n, c, h, w, device=DEV, generator=g))
+    w1 = torch.randn(c, c, 3, 3, device=DEV, generator=g) / (c * 9) ** 0.5
+    w2 = torch.randn(c, c, 3, 3, device=DEV, generator=g) / (c * 9) ** 0.5
+    wp1, bp1, wf1, bf1, _ = pack(w1, _bn(c, g))
+    wp2, bp2, wf2, bf2, _ = pack(w2, _bn(c, g))
+    xin = to_padded(x)
+    mid = torch.empty_like(xin)
+    y2 = torch.empty_like(xin)
+    _conv(L, xin, mid, n, h, w, c, wp1, bp1)
+    _conv(L, mid, y2, n, h, w, c, wp2, bp2, residual=xin)
+    yf = torch.full_like(xin, 0x7f)                      # poison: the fused kernel must write every cell
+    _lib.check(L.stl_basic_block(_lib.ptr(xin), _lib.ptr(yf), _lib.ptr(wp1), _lib.ptr(bp1), _lib.ptr(wp2), _lib.ptr(bp2),
+                                 n, h, w, c, _lib.current_stream()))
+    torch.cuda.synchronize()
+    assert padded_border_is_zero(yf, n, c, h, w)
+    assert torch.equal(yf, y2), (yf != y2).float().mean().item()
+    # and against torch fp32 on the folded weights (bf16 operands, bf16 intermediate)
+    t1 = bf16_round(F.relu(F.conv2d(x, bf16_round(wf1), bf1, 1, 1)))
+    ref = F.relu(F.conv2d(t1, bf16_round(wf2), bf2, 1, 1) + x)
+    got = from_padded(yf, n, c, h, w)
+    assert (got - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
