@@ -13,10 +13,11 @@
 // taps of both convs are row-shifted UMMA descriptors on those tiles.  Zero cells of the layout and pixels outside the
 // tensor are written as zeros into the intermediate tile (they are conv2's zero padding).
 //
-// Warps: 0 TMA producer (weights of both convs once, then x tiles, 2 stages) | 1 MMA issuer (conv1 of tile i, then
-// conv2 of tile i-1, so the tensor pipe works on conv1(i) while the epilogue converts conv1(i-1)... ) | 2-9 epilogue 1
-// (TMEM -> +b1, ReLU -> bf16 -> intermediate tile) | 10-17 epilogue 2 (TMEM -> +b2 + residual, ReLU -> staging panels)
-// | 18 DMA (TMA: residual panels in, finished panels out).  All hand-offs are mbarriers.
+// Warps: 0 TMA producer (weights of both convs once, then x tiles, 3 stages; a stage is overwritten in place by the
+// tile's intermediate activation once conv1 has consumed it and is released by conv2) | 1 MMA issuer of conv1 | 19 MMA issuer of
+// conv2 (conv2 of tile i-1 overlaps conv1 of tile i) | 2-9 epilogue 1 (TMEM -> +b1, ReLU -> bf16 -> intermediate tile) |
+// 10-17 epilogue 2 (TMEM -> +b2 + residual, ReLU -> staging panels) | 18 DMA (TMA: residual panels in, finished panels
+// out).  All hand-offs are mbarriers.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -35,7 +36,7 @@ constexpr int kOutRows = 384;          // output pixels per tile (3 accumulator 
 constexpr int kMidRows = 512;          // conv1 pixels per tile (4 accumulator blocks)
 constexpr int kMaxHalo = 64;
 constexpr int kXPieces = 3;
-constexpr int kBlkThreads = 19 * 32;
+constexpr int kBlkThreads = 20 * 32;
 constexpr int kTapBytes = kC * kPitch; // one filter tap: 32 output channels x 64 B = 2 KB
 
 struct BlockParams {
@@ -52,10 +53,10 @@ struct BlockParams {
 
 struct BlkCtl {
   uint64_t w_full;
-  uint64_t x_full[2], x_empty[2];
+  uint64_t x_full[3], x_empty[3];      // x tile stages; a stage then holds the tile's intermediate activation
   uint64_t acc1_full[2], acc1_empty[2];
   uint64_t acc2_full[2], acc2_empty[2];
-  uint64_t mid_full, mid_empty;
+  uint64_t mid_full[3];
   uint64_t res_full[2], out_done[2];
   uint32_t tmem_base;
 };
@@ -86,9 +87,8 @@ __global__ void __launch_bounds__(kBlkThreads, 1) basic_block_kernel(const __gri
   float* sbias = reinterpret_cast<float*>(smem + 512);            // [2][32]
   const uint32_t base = smem_u32(smem) + 1024;
   const uint32_t w_base = base;                                   // 2 convs x 9 taps x 2 KB = 36 KB
-  const uint32_t x_base = w_base + 2 * 9 * kTapBytes;             // 2 stages
-  const uint32_t mid_base = x_base + 2 * p.x_stage_bytes;         // 512 x 64 B = 32 KB
-  const uint32_t out_base = mid_base + kMidRows * kPitch;         // 2 buffers x 3 panels x 8 KB
+  const uint32_t x_base = w_base + 2 * 9 * kTapBytes;             // 3 stages: x tile, then (in place) the intermediate tile
+  const uint32_t out_base = x_base + 3 * p.x_stage_bytes;         // 2 buffers x 3 panels x 8 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tile0 = blockIdx.x, tstride = gridDim.x;
@@ -96,14 +96,12 @@ __global__ void __launch_bounds__(kBlkThreads, 1) basic_block_kernel(const __gri
 
   if (threadIdx.x == 0) {
     mbar_init(&ctl->w_full, 1);
+    for (int i = 0; i < 3; ++i) { mbar_init(&ctl->x_full[i], 1); mbar_init(&ctl->x_empty[i], 1); mbar_init(&ctl->mid_full[i], 8); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&ctl->x_full[i], 1); mbar_init(&ctl->x_empty[i], 1);
       mbar_init(&ctl->acc1_full[i], 1); mbar_init(&ctl->acc1_empty[i], 8);
       mbar_init(&ctl->acc2_full[i], 1); mbar_init(&ctl->acc2_empty[i], 8);
       mbar_init(&ctl->res_full[i], 1); mbar_init(&ctl->out_done[i], 8);
     }
-    mbar_init(&ctl->mid_full, 8);
-    mbar_init(&ctl->mid_empty, 1);
     fence_mbar_init();
     tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW1); tma_prefetch_desc(&p.tmW2);
     tma_prefetch_desc(&p.tmR); tma_prefetch_desc(&p.tmO);
@@ -126,8 +124,8 @@ __global__ void __launch_bounds__(kBlkThreads, 1) basic_block_kernel(const __gri
       }
       uint32_t i = 0;
       for (long long tile = tile0; tile < p.total_tiles; tile += tstride, ++i) {
-        const uint32_t s = i & 1, ph = (i >> 1) & 1;
-        mbar_wait(&ctl->x_empty[s], ph ^ 1u);
+        const uint32_t s = i % 3, ph = (i / 3) & 1;
+        mbar_wait(&ctl->x_empty[s], ph ^ 1u);                    // conv2 of the tile that last used this stage is done
         const long long q1 = tile * kOutRows - halo;             // first conv1 pixel; x tile starts another halo earlier
         mbar_expect_tx(&ctl->x_full[s], (uint32_t)(kXPieces * p.x_piece_rows * kPitch));
         for (int pc = 0; pc < kXPieces; ++pc)
@@ -136,7 +134,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) basic_block_kernel(const __gri
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ MMA issuer of conv1 (x tile -> accumulators 1)
     const uint32_t idesc = make_idesc_bf16(128, kC);
     mbar_wait(&ctl->w_full, 0);
     tc_fence_after();
@@ -144,61 +142,65 @@ __global__ void __launch_bounds__(kBlkThreads, 1) basic_block_kernel(const __gri
 #pragma unroll
     for (int t = 0; t < 9; ++t) offs[t] = (t / 3 - 1) * p.Wp + (t % 3 - 1) + halo;     // tap row offset + halo >= 0
     uint32_t i = 0;
-    long long tile = tile0;
-    const bool any = tile0 < p.total_tiles;
-    for (; any; tile += tstride, ++i) {
-      const bool have1 = tile < p.total_tiles;     // conv1 of tile i
-      const bool have2 = i > 0;                    // conv2 of tile i-1
-      if (have1) {
-        const uint32_t s = i & 1, ph = (i >> 1) & 1;
-        mbar_wait(&ctl->x_full[s], ph);
-        mbar_wait(&ctl->acc1_empty[s], ph ^ 1u);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t xs = x_base + s * p.x_stage_bytes;
-          const uint32_t d0 = tmem_base + s * 128u;
+    for (long long tile = tile0; tile < p.total_tiles; tile += tstride, ++i) {
+      const uint32_t s = i & 1, ph = (i >> 1) & 1, s3 = i % 3, ph3 = (i / 3) & 1;
+      mbar_wait(&ctl->x_full[s3], ph3);
+      mbar_wait(&ctl->acc1_empty[s], ph ^ 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t xs = x_base + s3 * p.x_stage_bytes;
+        const uint32_t d0 = tmem_base + s * 128u;
 #pragma unroll 1
-          for (int m = 0; m < 4; ++m) {
+        for (int m = 0; m < 4; ++m) {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
+          for (int t = 0; t < 9; ++t) {
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t ad = make_kmajor_desc(xs + (uint32_t)((m * 128 + offs[t]) * kPitch + ks * 32), kPitch);
-                const uint64_t bd = make_kmajor_desc(w_base + (uint32_t)(t * kTapBytes + ks * 32), kPitch);
-                umma_bf16(d0 + (uint32_t)(m * kC), ad, bd, idesc, (t | ks) ? 1u : 0u);
-              }
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t ad = make_kmajor_desc(xs + (uint32_t)((m * 128 + offs[t]) * kPitch + ks * 32), kPitch);
+              const uint64_t bd = make_kmajor_desc(w_base + (uint32_t)(t * kTapBytes + ks * 32), kPitch);
+              umma_bf16(d0 + (uint32_t)(m * kC), ad, bd, idesc, (t | ks) ? 1u : 0u);
             }
           }
-          umma_commit(&ctl->x_empty[s]);
-          umma_commit(&ctl->acc1_full[s]);
         }
-        __syncwarp();
+        umma_commit(&ctl->acc1_full[s]);
       }
-      if (have2) {
-        const uint32_t j = i - 1, s = j & 1, ph = (j >> 1) & 1;
-        mbar_wait(&ctl->mid_full, j & 1);
-        mbar_wait(&ctl->acc2_empty[s], ph ^ 1u);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t d0 = tmem_base + 256u + s * 96u;
+      __syncwarp();
+    }
+  } else if (warp == 19) {
+    // ------------------------------------------------------------------ MMA issuer of conv2 (intermediate tile -> accumulators 2)
+    // A second issuing thread: one thread sustains a tcgen05.mma every ~50 cycles whatever its size, and these
+    // 128x32x16 MMAs are shorter than that; conv2 of tile i-1 overlaps conv1 of tile i on the tensor pipe.
+    const uint32_t idesc = make_idesc_bf16(128, kC);
+    mbar_wait(&ctl->w_full, 0);
+    tc_fence_after();
+    int offs[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) offs[t] = (t / 3 - 1) * p.Wp + (t % 3 - 1) + halo;
+    uint32_t j = 0;
+    for (long long tile = tile0; tile < p.total_tiles; tile += tstride, ++j) {
+      const uint32_t s = j & 1, ph = (j >> 1) & 1, s3 = j % 3, ph3 = (j / 3) & 1;
+      mbar_wait(&ctl->mid_full[s3], ph3);
+      mbar_wait(&ctl->acc2_empty[s], ph ^ 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t mid_base = x_base + s3 * p.x_stage_bytes;
+        const uint32_t d0 = tmem_base + 256u + s * 96u;
 #pragma unroll 1
-          for (int m = 0; m < 3; ++m) {
+        for (int m = 0; m < 3; ++m) {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
+          for (int t = 0; t < 9; ++t) {
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t ad = make_kmajor_desc(mid_base + (uint32_t)((m * 128 + offs[t]) * kPitch + ks * 32), kPitch);
-                const uint64_t bd = make_kmajor_desc(w_base + (uint32_t)((9 + t) * kTapBytes + ks * 32), kPitch);
-                umma_bf16(d0 + (uint32_t)(m * kC), ad, bd, idesc, (t | ks) ? 1u : 0u);
-              }
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t ad = make_kmajor_desc(mid_base + (uint32_t)((m * 128 + offs[t]) * kPitch + ks * 32), kPitch);
+              const uint64_t bd = make_kmajor_desc(w_base + (uint32_t)((9 + t) * kTapBytes + ks * 32), kPitch);
+              umma_bf16(d0 + (uint32_t)(m * kC), ad, bd, idesc, (t | ks) ? 1u : 0u);
             }
           }
-          umma_commit(&ctl->mid_empty);
-          umma_commit(&ctl->acc2_full[s]);
         }
-        __syncwarp();
+        umma_commit(&ctl->x_empty[s3]);                           // stage free for the x tile three tiles ahead
+        umma_commit(&ctl->acc2_full[s]);
       }
-      if (!have1) break;                           // the iteration after the last tile only ran its conv2
+      __syncwarp();
     }
   } else if (warp < 10) {
     // ------------------------------------------------------------------ epilogue 1: conv1 accumulators -> intermediate tile
@@ -209,11 +211,11 @@ __global__ void __launch_bounds__(kBlkThreads, 1) basic_block_kernel(const __gri
     const uint32_t xr = (uint32_t)((row0 >> 1) & 3);
     uint32_t i = 0;
     for (long long tile = tile0; tile < p.total_tiles; tile += tstride, ++i) {
-      const uint32_t s = i & 1, ph = (i >> 1) & 1;
+      const uint32_t s = i & 1, ph = (i >> 1) & 1, s3 = i % 3;
       const long long q1 = tile * kOutRows - halo;
+      const uint32_t mid_base = x_base + s3 * p.x_stage_bytes;   // conv1 has consumed the x tile: overwrite it in place
       mbar_wait(&ctl->acc1_full[s], ph);
       tc_fence_after();
-      if (i > 0) mbar_wait(&ctl->mid_empty, (i - 1) & 1);       // conv2 of the previous tile has consumed the tile
 #pragma unroll 1
       for (int m = 0; m < 4; ++m) {
         uint32_t v[16];
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) basic_block_kernel(const __gri
       tc_fence_before();
       fence_async_smem();                                        // generic-proxy stores -> visible to the tensor core
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&ctl->acc1_empty[s]); mbar_arrive(&ctl->mid_full); }
+      if (lane == 0) { mbar_arrive(&ctl->acc1_empty[s]); mbar_arrive(&ctl->mid_full[s3]); }
     }
   } else if (warp < 18) {
     // ------------------------------------------------------------------ epilogue 2: conv2 accumulators + residual -> panels
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) basic_block_kernel(const __gri
       __syncwarp();
       if (lane == 0) { mbar_arrive(&ctl->acc2_empty[s]); mbar_arrive(&ctl->out_done[s]); }
     }
-  } else {
+  } else if (warp == 18) {
     // ------------------------------------------------------------------ DMA warp: residual panels in, finished panels out
     if (lane == 0) {
       auto load_res = [&](long long tile, uint32_t s) {
@@ -377,7 +379,7 @@ int basic_block_launch(const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bflo
     if (enc(&p.tmW1, w1, 3, wd, ws, wb)) return 1;
     if (enc(&p.tmW2, w2, 3, wd, ws, wb)) return 1;
   }
-  const size_t smem = 1024 + 1024 + 2 * 9 * kTapBytes + 2 * (size_t)p.x_stage_bytes + kMidRows * kPitch + 2 * 3 * 128 * kPitch;
+  const size_t smem = 1024 + 1024 + 2 * 9 * kTapBytes + 3 * (size_t)p.x_stage_bytes + 2 * 3 * 128 * kPitch;
   if (smem > 227 * 1024) { set_error("basic_block: shared memory budget exceeded (%zu)", smem); return 1; }
   static bool attr = false;
   cudaError_t e;
