@@ -153,22 +153,35 @@ struct Plan::Builder {
         for (int b = 0; b < nb; ++b) {
           // the 2 x blocks convs of a branch form a group: executed sub-batch by sub-batch so that the three
           // activation buffers they cycle through stay resident in L2 (bind() picks the sub-batch size)
+          // 32-channel branches: each BasicBlock is ONE kernel (block_tc.cu), the intermediate never leaves the SM
+          const bool fused = P.fuse_blocks && basic_block_supported(bh(b), bw(b), ch[b]);
           Plan::Group grp;
           grp.first = (int)P.ops.size();
           for (int k = 0; k < c.blocks; ++k) {
             snprintf(k1, sizeof k1, "%s.branches.%d.%d", mp.c_str(), b, k);
             const std::string bp = k1;
-            int tmp = acquire(ch[b], bh(b), bw(b));
-            conv(layer(bp + ".conv1", bp + ".bn1", ch[b], ch[b], 3, 1), xs[b], tmp, -1, true);
+            const int l1 = layer(bp + ".conv1", bp + ".bn1", ch[b], ch[b], 3, 1);
+            const int l2 = layer(bp + ".conv2", bp + ".bn2", ch[b], ch[b], 3, 1);
             int o = acquire(ch[b], bh(b), bw(b));
-            conv(layer(bp + ".conv2", bp + ".bn2", ch[b], ch[b], 3, 1), tmp, o, xs[b], true);
-            release(tmp);
+            if (fused) {
+              Plan::Op op;
+              op.kind = Plan::OP_BLOCK;
+              op.layer = l1; op.layer2 = l2; op.in = xs[b]; op.out = o; op.res = xs[b]; op.relu = true;
+              P.ops.push_back(op);
+            } else {
+              int tmp = acquire(ch[b], bh(b), bw(b));
+              conv(l1, xs[b], tmp, -1, true);
+              conv(l2, tmp, o, xs[b], true);
+              release(tmp);
+            }
             release(xs[b]);
             xs[b] = o;
           }
-          grp.count = (int)P.ops.size() - grp.first;
-          for (int i = 0; i < grp.count; ++i) P.ops[grp.first + i].group = (int)P.groups.size();
-          P.groups.push_back(grp);
+          if (!fused) {
+            grp.count = (int)P.ops.size() - grp.first;
+            for (int i = 0; i < grp.count; ++i) P.ops[grp.first + i].group = (int)P.groups.size();
+            P.groups.push_back(grp);
+          }
         }
         // fuse layers (HRnet.py:188-243, 255-264)
         std::vector<int> ys(n_out);
@@ -235,6 +248,7 @@ Plan* Plan::create(const stl_hrnet_cfg& cfg) {
     if (cfg.stage_modules[i] < 1) { set_error("plan: stage_modules must be >= 1"); return nullptr; }
   Plan* p = new Plan();
   p->cfg = cfg;
+  if (const char* e = getenv("STLPOSE_FUSE_BLOCK")) p->fuse_blocks = atoi(e);
   Builder b(*p);
   b.build();
   return p;
@@ -392,6 +406,19 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
         if (conv_launch_prepared(pr.params, pr.grid, pr.smem, st)) return 1;
         break;
       }
+      case OP_BLOCK: {
+        const Slot& so = slots[op.out];
+        const Layer& L1 = layers[op.layer];
+        const Layer& L2 = layers[op.layer2];
+        if (basic_block_launch(reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.in]),
+                               reinterpret_cast<__nv_bfloat16*>(slot_ptr[op.out]),
+                               reinterpret_cast<const __nv_bfloat16*>(wbase + L1.w_off),
+                               reinterpret_cast<const float*>(wbase + L1.b_off),
+                               reinterpret_cast<const __nv_bfloat16*>(wbase + L2.w_off),
+                               reinterpret_cast<const float*>(wbase + L2.b_off), n_images, so.H, so.W, 0, st))
+          return 1;
+        break;
+      }
       case OP_FUSE: {
         const Slot& so = slots[op.out];
         const __nv_bfloat16* z[kMaxUp];
@@ -434,6 +461,14 @@ int Plan::op_info(int i, stl_op_info* info) const {
     info->out_h = so->H; info->out_w = so->W; info->cout = so->C; info->cin = so->C;
     info->bytes_per_image = 2.0 * so->H * so->W * so->C * 2;
     for (int u = 0; u < op.n_up; ++u) info->bytes_per_image += (double)slots[op.up[u]].H * slots[op.up[u]].W * so->C * 2;
+    return 0;
+  }
+  if (op.kind == OP_BLOCK) {   // two 3x3 convs; algorithmic traffic: read x, write y
+    const Layer& L1 = layers[op.layer];
+    info->out_h = so->H; info->out_w = so->W; info->cin = L1.cin; info->cout = L1.cout; info->ksize = 3; info->stride = 1;
+    info->flops_per_image = 2.0 * (2.0 * L1.cout * L1.cin * 9 * so->H * so->W);
+    info->bytes_per_image = 2.0 * so->H * so->W * so->C * 2;
+    info->mb = 3; info->nt = L1.cout; info->ck = L1.cin; info->grid = 148;
     return 0;
   }
   const Layer& L = layers[op.layer];

@@ -18,10 +18,11 @@ struct Plan {
     size_t w_off, b_off;
   };
   struct Slot { int C, H, W; };
-  enum OpKind { OP_STEM, OP_CONV, OP_FUSE };
+  enum OpKind { OP_STEM, OP_CONV, OP_FUSE, OP_BLOCK };   // OP_BLOCK: one BasicBlock (two convs) in one kernel
   struct Op {
     OpKind kind = OP_CONV;
     int layer = -1, in = -1, out = -1, res = -1;
+    int layer2 = -1;  // OP_BLOCK: the block's second convolution
     int n_up = 0;
     int up[kMaxUp] = {-1, -1, -1};
     int up_shift[kMaxUp] = {0, 0, 0};
@@ -43,6 +44,7 @@ struct Plan {
   std::vector<Op> ops;
   size_t weight_bytes = 0;
   int tap_reload = 0;  // debugging: force one TMA load per filter tap
+  int fuse_blocks = 1; // BasicBlocks of 32-channel branches run as one fused kernel (STLPOSE_FUSE_BLOCK=0: two convs)
 
   // binding state
   bool bound = false;
