@@ -25,11 +25,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WIDTH, IMAGE = 32, (256, 192)
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel shape, from the committed
-# `ncu --set full` capture profiles/r01_ncu_conv.md (prof5_c32): 417.67 MB read + 176.53 MB written
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 594.2e6
-NCU_TRAFFIC_NOTE = ("conv_tc_kernel<3,2,9,staged>, 32->32 3x3 @64x48 + residual over 1024 images (64 of the 293 conv "
-                    "launches per forward, 22 % of step time); algorithmic bytes of that launch: 604 MB")
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the most expensive kernel shape, from the committed
+# `ncu --set full` capture profiles/r01_ncu_conv.md (prof_block): 208.92 MB read + 167.07 MB written
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 376.0e6
+NCU_TRAFFIC_NOTE = ("basic_block_kernel (two 32->32 3x3 convs @64x48 + residual fused, 1024 images; 32 launches per "
+                    "forward, 20 % of step time); algorithmic bytes of that launch: 417 MB (x read once, y written; "
+                    "the residual re-read of x hits L2).  The unfused conv_tc_kernel<3,2,9,staged> launch it replaces: "
+                    "594.9 MB measured / 604 MB algorithmic")
 FLOPS_PER_FORWARD = 15.290007552e9   # HRNet-W32 @256x192, 2*MACs over the 293 convs (oracle.conv_flops_per_crop)
 
 
@@ -257,7 +259,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "crops/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": pipe.launches_per_step * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": achieved_tf, "peak": peak_tf,
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + basic_block_kernel (tcgen05 convolutions)", "achieved": achieved_tf, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
                          "traffic_note": NCU_TRAFFIC_NOTE,
                          "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)",
