@@ -125,6 +125,47 @@ __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict_
   }
 }
 
+// Stem as a GEMM: the first convolution (HRnet.py:286, 3 -> 64 channels, 3x3, stride 2, pad 1) has K = 27.  Packing the
+// network input as its im2col matrix - one 32-channel bf16 row per OUTPUT pixel, k = ci*9 + kh*3 + kw (the OIHW order of
+// the filter), rows 27..31 zero - makes it a 1x1 convolution for the tensor-core kernel (flat tiles, staged epilogue)
+// and halves the bytes the 16-channel-per-input-pixel packing wrote.  y: padded-linear [n_total][H/2+1][W/2+1][32]
+// (zero cells untouched); images n >= n_plain are image n - n_plain mirrored in W (flip test, lib/inference.py:21).
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                          int n_total, int n_plain, int H, int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)n_total * Ho * Wo;
+  const size_t plane = (size_t)H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % Wo);
+    const long long t = i / Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const bool flip = n >= n_plain;
+    const float* src = x + (size_t)(flip ? n - n_plain : n) * 3 * plane;
+    float v[32];
+#pragma unroll
+    for (int k = 27; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = 2 * ho + kh - 1;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = 2 * wo + kw - 1;
+        const bool ok = h >= 0 && h < H && w >= 0 && w < W;
+        const size_t off = (size_t)(ok ? h : 0) * W + (ok ? (flip ? W - 1 - w : w) : 0);
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) v[ci * 9 + kh * 3 + kw] = ok ? __ldg(src + ci * plane + off) : 0.f;
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)n * (Ho + 1) + ho) * (Wo + 1) + wo) * 32);
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      dst[g] = make_uint4(pack_bf16(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16(v[g * 8 + 2], v[g * 8 + 3]),
+                          pack_bf16(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16(v[g * 8 + 6], v[g * 8 + 7]));
+  }
+}
+
 // ------------------------------------------------------------------ fuse-layer sum at the highest resolution
 // y = relu(x + sum_u upsample_nearest(z_u))   (HRnet.py:258-264, row i = 0), padded-linear layout, 8 ch / thread
 struct FuseArgs {
@@ -280,6 +321,12 @@ int stem_pack_input(const float* x, __nv_bfloat16* y, int n_total, int n_plain, 
   const long long total = (long long)n_total * H * W;
   stem_pack_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, y, n_total, n_plain, H, W);
   return check("stem_pack_input");
+}
+
+int stem_im2col(const float* x, __nv_bfloat16* y, int n_total, int n_plain, int H, int W, cudaStream_t st) {
+  const long long total = (long long)n_total * (H / 2) * (W / 2);
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, y, n_total, n_plain, H, W);
+  return check("stem_im2col");
 }
 
 int fuse_sum(const __nv_bfloat16* x, const __nv_bfloat16* const* z, const int* shift, int n_up, __nv_bfloat16* y,

@@ -13,6 +13,7 @@ int pack_weights(const float* w, const float* gamma, const float* beta, const fl
 // network input (fp32 NCHW, 3 channels) -> padded-linear NHWC bf16 with 16 channels; images >= n_plain are mirrored
 int pack_weights_dgrad(const float* w, int Cout, int Cin, int k, int Rows_pad, int K_pad, __nv_bfloat16* wp,
                        float* bias_out, cudaStream_t st);
+int stem_im2col(const float* x, __nv_bfloat16* y, int n_total, int n_plain, int H, int W, cudaStream_t st);
 int stem_pack_input(const float* x, __nv_bfloat16* y, int n_total, int n_plain, int H, int W, cudaStream_t st);
 int fuse_sum(const __nv_bfloat16* x, const __nv_bfloat16* const* z, const int* shift, int n_up, __nv_bfloat16* y,
              int N, int H, int W, int C, cudaStream_t st);

@@ -31,15 +31,17 @@ struct Plan::Builder {
 
   explicit Builder(Plan& p) : P(p) {}
 
-  int layer(const std::string& conv_key, const std::string& bn_key, int cout, int cin, int k, int stride) {
+  int layer(const std::string& conv_key, const std::string& bn_key, int cout, int cin, int k, int stride,
+            bool im2col = false) {
     Layer L;
     L.conv_key = conv_key;
     L.bn_key = bn_key;
     L.cout = cout; L.cin = cin; L.k = k; L.stride = stride;
+    L.im2col = im2col;
     L.cout_pad = (int)align_up(cout, 16);
-    L.cin_pad = (int)align_up(cin, 16);   // the 3-channel network input is padded to one UMMA K-step
+    L.cin_pad = im2col ? 32 : (int)align_up(cin, 16);   // (without im2col the 3-channel input is padded to one K-step)
     L.w_off = P.weight_bytes;
-    P.weight_bytes += align_up((size_t)k * k * L.cout_pad * L.cin_pad * 2, 256);
+    P.weight_bytes += align_up((size_t)(im2col ? 1 : k * k) * L.cout_pad * L.cin_pad * 2, 256);
     L.b_off = P.weight_bytes;
     P.weight_bytes += align_up(sizeof(float) * L.cout_pad, 256);
     P.layers.push_back(L);
@@ -90,15 +92,16 @@ struct Plan::Builder {
     char k1[128], k2[128];
 
     // stem (HRnet.py:434-439)
-    int xin = acquire(16, c.image_h, c.image_w);
+    const bool im2col = P.stem_im2col != 0;
+    int xin = im2col ? acquire(32, c.image_h / 2, c.image_w / 2) : acquire(16, c.image_h, c.image_w);
     {
       Plan::Op op;
-      op.kind = Plan::OP_STEM;   // fp32 NCHW network input -> padded NHWC bf16 (3 -> 16 channels, flip half mirrored)
+      op.kind = Plan::OP_STEM;   // fp32 NCHW network input -> im2col rows of conv1 (or 16-channel padded NHWC), flip half mirrored
       op.out = xin;
       P.ops.push_back(op);
     }
     int t0 = acquire(64, c.image_h / 2, c.image_w / 2);
-    conv(layer("conv1", "bn1", 64, 3, 3, 2), xin, t0, -1, true);
+    conv(layer("conv1", "bn1", 64, 3, 3, 2, im2col), xin, t0, -1, true);
     release(xin);
     int x = acquire(64, H4, W4);
     conv(layer("conv2", "bn2", 64, 64, 3, 2), t0, x, -1, true);
@@ -249,6 +252,7 @@ Plan* Plan::create(const stl_hrnet_cfg& cfg) {
   Plan* p = new Plan();
   p->cfg = cfg;
   if (const char* e = getenv("STLPOSE_FUSE_BLOCK")) p->fuse_blocks = atoi(e);
+  if (const char* e = getenv("STLPOSE_STEM_IM2COL")) p->stem_im2col = atoi(e);
   Builder b(*p);
   b.build();
   return p;
@@ -269,6 +273,9 @@ int Plan::pack_conv(int index, const float* w, const float* gamma, const float* 
   const Layer& L = layers[index];
   uint8_t* base = reinterpret_cast<uint8_t*>(arena);
   bound = false;  // packed parameters changed; tensor maps stay valid but be conservative
+  if (L.im2col)   // OIHW [cout][cin][k][k] read as a 1x1 filter over cin*k*k "channels" (the im2col K order)
+    return pack_weights(w, gamma, beta, mean, var, cbias, eps, L.cout, L.cin * L.k * L.k, 1, L.cout_pad, L.cin_pad,
+                        reinterpret_cast<__nv_bfloat16*>(base + L.w_off), reinterpret_cast<float*>(base + L.b_off), st);
   return pack_weights(w, gamma, beta, mean, var, cbias, eps, L.cout, L.cin, L.k, L.cout_pad, L.cin_pad,
                       reinterpret_cast<__nv_bfloat16*>(base + L.w_off), reinterpret_cast<float*>(base + L.b_off), st);
 }
@@ -327,8 +334,8 @@ int Plan::bind(int n_images, const void* arena, void* workspace, size_t ws_bytes
     s.out = op.out >= 0 ? slot_ptr[op.out] : nullptr;  // head output is patched per forward
     s.cout = L.cout;
     s.cout_pad = L.cout_pad;
-    s.ksize = L.k;
-    s.stride = L.stride;
+    s.ksize = L.im2col ? 1 : L.k;
+    s.stride = L.im2col ? 1 : L.stride;
     s.weights = reinterpret_cast<const __nv_bfloat16*>(wbase + L.w_off);
     s.bias = reinterpret_cast<const float*>(wbase + L.b_off);
     s.residual = op.res >= 0 ? reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.res]) : nullptr;
@@ -395,8 +402,10 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
     const Op& op = ops[i];
     switch (op.kind) {
       case OP_STEM: {
-        if (stem_pack_input(x, reinterpret_cast<__nv_bfloat16*>(slot_ptr[op.out]), n_images, B, cfg.image_h,
-                            cfg.image_w, st))
+        if (stem_im2col ? stl::stem_im2col(x, reinterpret_cast<__nv_bfloat16*>(slot_ptr[op.out]), n_images, B, cfg.image_h,
+                                           cfg.image_w, st)
+                        : stem_pack_input(x, reinterpret_cast<__nv_bfloat16*>(slot_ptr[op.out]), n_images, B, cfg.image_h,
+                                          cfg.image_w, st))
           return 1;
         break;
       }
@@ -453,8 +462,8 @@ int Plan::op_info(int i, stl_op_info* info) const {
   const Slot* so = op.out >= 0 ? &slots[op.out] : nullptr;
   const Slot* si = op.in >= 0 ? &slots[op.in] : nullptr;
   if (op.kind == OP_STEM) {
-    info->out_h = cfg.image_h; info->out_w = cfg.image_w; info->cin = 3; info->cout = 16;
-    info->bytes_per_image = (double)cfg.image_h * cfg.image_w * (3 * 4 + 16 * 2);
+    info->out_h = cfg.image_h; info->out_w = cfg.image_w; info->cin = 3; info->cout = so->C;
+    info->bytes_per_image = (double)cfg.image_h * cfg.image_w * 3 * 4 + (double)so->H * so->W * so->C * 2;
     return 0;
   }
   if (op.kind == OP_FUSE) {
@@ -473,10 +482,10 @@ int Plan::op_info(int i, stl_op_info* info) const {
   }
   const Layer& L = layers[op.layer];
   const int ih = si ? si->H : cfg.image_h, iw = si ? si->W : cfg.image_w;
-  info->out_h = ih / L.stride; info->out_w = iw / L.stride;
+  info->out_h = L.im2col ? ih : ih / L.stride; info->out_w = L.im2col ? iw : iw / L.stride;
   info->cin = L.cin; info->cout = L.cout; info->ksize = L.k; info->stride = L.stride;
   info->flops_per_image = 2.0 * L.cout * L.cin * L.k * L.k * info->out_h * info->out_w;
-  const double in_b = (double)ih * iw * L.cin * (si ? 2 : 4);
+  const double in_b = (double)ih * iw * (L.im2col ? L.cin_pad : L.cin) * (si ? 2 : 4);
   const double out_b = (double)info->out_h * info->out_w * L.cout * (op.out_nchw ? 4 : 2);
   info->bytes_per_image = in_b + out_b + (op.res >= 0 ? out_b : 0);
   for (int u = 0; u < op.n_up; ++u) info->bytes_per_image += (double)slots[op.up[u]].H * slots[op.up[u]].W * L.cout * 2;

@@ -15,6 +15,7 @@ struct Plan {
   struct Layer {
     std::string conv_key, bn_key;
     int cout, cin, k, stride, cout_pad, cin_pad;
+    bool im2col = false;  // stem conv1: executed as a 1x1 conv over the im2col-packed network input (K = cin*k*k -> 32)
     size_t w_off, b_off;
   };
   struct Slot { int C, H, W; };
@@ -44,6 +45,7 @@ struct Plan {
   std::vector<Op> ops;
   size_t weight_bytes = 0;
   int tap_reload = 0;  // debugging: force one TMA load per filter tap
+  int stem_im2col = 1; // STLPOSE_STEM_IM2COL=0: 16-channel input packing + stride-2 3x3 tensor-core conv instead
   int fuse_blocks = 1; // BasicBlocks of 32-channel branches run as one fused kernel (STLPOSE_FUSE_BLOCK=0: two convs)
 
   // binding state
