@@ -54,6 +54,13 @@ int stl_decode(const float* heat, const float* heat_flipped, const float* center
  *   loss = 0.5/(J*B*hw) * sum (tw*(out-tgt))^2 ;  grad = tw^2*(out-tgt)/(J*B*hw)   (grad may be null)
  * out/tgt [B][J][hw] fp32, tw [B][J] fp32, loss: 1 float.  workspace: stl_mse_workspace_bytes() bytes. */
 size_t stl_mse_workspace_bytes(void);
+/* Training targets: JointsDataset.generate_target (data/JointsDataset.py:230-286) for a batch.
+ * joints, joints_vis: [B][J][3] fp64 on the device (x, y in crop pixels; visibility in column 0); joints_weight: [J] fp32
+ * or null (use_different_joints_weight); outputs target fp32 [B][J][h][w] (every element written) and target_weight
+ * fp32 [B][J].  Heatmap stride = image size / heatmap size; sigma as in the reference's config (2). */
+int stl_generate_target(const double* joints, const double* joints_vis, const float* joints_weight, int B, int J, int h,
+                        int w, int image_h, int image_w, int sigma, float* target, float* target_weight, void* stream);
+
 /* Second decode path: create_pose_from_outputs (lib/pose_parsing.py:138-151) =
  * F.interpolate(heat, (out_h, out_w), mode="bilinear", align_corners=True) -> get_max_preds_hrnet, used by
  * 04_evaluate_vases_qualitatively.py:216-220 and 05_create_archdata_retrieval_db.py:114.  Fused: the upsampled tensor

@@ -132,7 +132,43 @@ def make_pose_entries():
     print("pose entries", np.array(entries).shape, allk.shape)
 
 
+def target_inputs():
+    """Joints [B,17,3] in crop pixels (256x192) and visibilities: inside, on every border, far outside, invisible."""
+    rng = np.random.default_rng(99)
+    B, J = 6, 17
+    joints = np.zeros((B, J, 3))
+    joints[..., 0] = rng.uniform(-40, 232, size=(B, J))
+    joints[..., 1] = rng.uniform(-40, 296, size=(B, J))
+    joints[0, 0, :2] = (0.0, 0.0)
+    joints[0, 1, :2] = (191.9, 255.9)
+    joints[0, 2, :2] = (-30.0, 100.0)       # patch entirely left of the map
+    joints[0, 3, :2] = (100.0, 290.0)       # patch entirely below
+    joints[0, 4, :2] = (-22.1, -22.1)       # patch just touching the corner
+    vis = (rng.random((B, J)) > 0.25).astype(np.float64)
+    joints_vis = np.stack([vis, vis, np.zeros_like(vis)], axis=2)
+    return joints, joints_vis
+
+
+def make_targets():
+    import types
+    f = ref_shim.generate_target_function()
+    joints, joints_vis = target_inputs()
+    jw = np.array([1., 1., 1., 1., 1., 1., 1., 1.2, 1.2, 1.5, 1.5, 1., 1., 1.2, 1.2, 1.5, 1.5], np.float32).reshape(17, 1)
+    outs = {}
+    for tag, diff in (("plain", False), ("weighted", True)):
+        me = types.SimpleNamespace(num_joints=17, target_type="gaussian", heatmap_size=np.array([48, 64]),
+                                   image_size=np.array([192, 256]), sigma=2, use_different_joints_weight=diff,
+                                   joints_weight=jw)
+        res = [f(me, joints[b], joints_vis[b]) for b in range(joints.shape[0])]
+        outs[f"target_{tag}"] = np.stack([r[0] for r in res])
+        outs[f"weight_{tag}"] = np.stack([r[1] for r in res])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "targets.npz"), **outs)
+    print("targets", outs["target_plain"].shape, float(outs["target_plain"].sum()), outs["weight_weighted"][0, :6, 0])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "targets":
+        return make_targets()
     if len(sys.argv) > 1 and sys.argv[1] == "pose_entries":
         return make_pose_entries()
     if len(sys.argv) > 1 and sys.argv[1] == "pck":
@@ -185,6 +221,7 @@ def main():
     make_pck()
     make_crops()
     make_pose_entries()
+    make_targets()
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))
 

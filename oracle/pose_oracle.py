@@ -271,6 +271,37 @@ def transform_detection(img, list_coords, det_width=192, det_height=256):
 
 
 # ----------------------------------------------------------------------------------------------
+# training targets: data/JointsDataset.py:230-286
+# ----------------------------------------------------------------------------------------------
+def generate_target(joints, joints_vis, image_size=(192, 256), heatmap_size=(48, 64), sigma=2, joints_weight=None):
+    """JointsDataset.generate_target for one sample: joints, joints_vis [J,3] -> (target f32 [J,h,w], target_weight f32
+    [J,1]).  A 13x13 (sigma 2) unnormalised Gaussian centred on the rounded heatmap position of every visible joint
+    whose patch touches the map; joints whose patch lies outside get weight 0."""
+    J = joints.shape[0]
+    W, H = heatmap_size
+    weight = np.ones((J, 1), dtype=np.float32)
+    weight[:, 0] = joints_vis[:, 0]
+    target = np.zeros((J, H, W), dtype=np.float32)
+    rad = sigma * 3
+    stride = np.asarray(image_size) / np.asarray(heatmap_size)
+    ax = np.arange(0, 2 * rad + 1, 1, np.float32)
+    gauss = np.exp(-((ax - rad) ** 2 + (ax[:, None] - rad) ** 2) / (2 * sigma ** 2))
+    for j in range(J):
+        mx = int(joints[j][0] / stride[0] + 0.5)
+        my = int(joints[j][1] / stride[1] + 0.5)
+        x0, y0, x1, y1 = int(mx - rad), int(my - rad), int(mx + rad + 1), int(my + rad + 1)
+        if x0 >= W or y0 >= H or x1 < 0 or y1 < 0:
+            weight[j] = 0
+            continue
+        if weight[j] > 0.5:
+            xa, xb, ya, yb = max(0, x0), min(x1, W), max(0, y0), min(y1, H)
+            target[j, ya:yb, xa:xb] = gauss[ya - y0:yb - y0, xa - x0:xb - x0]
+    if joints_weight is not None:
+        weight = np.multiply(weight, joints_weight)
+    return target, weight
+
+
+# ----------------------------------------------------------------------------------------------
 # second decode path: lib/pose_parsing.py:107-151
 # ----------------------------------------------------------------------------------------------
 def create_pose_entries(keypoints, max_vals=None, thr=0.1):

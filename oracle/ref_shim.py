@@ -156,3 +156,22 @@ def metrics_functions():
         end = next(i for i in range(start + 1, len(lines)) if lines[i].startswith("def "))
         exec(compile("\n".join(lines[start:end]), f"{path}:{start + 1}", "exec"), ns)
     return types.SimpleNamespace(calc_dists=ns["calc_dists"], dist_acc=ns["dist_acc"])
+
+
+def generate_target_function():
+    """``JointsDataset.generate_target`` (data/JointsDataset.py:230-286) executed from its unmodified source text; the
+    module itself does not import here (pycocotools, removed NumPy aliases).  Returns f(self_like, joints, joints_vis)
+    where ``self_like`` carries num_joints, target_type, heatmap_size, image_size, sigma, use_different_joints_weight,
+    joints_weight."""
+    import textwrap
+    import numpy as np
+    path = os.path.join(REF_SRC, "data", "JointsDataset.py")
+    lines = open(path).read().split("\n")
+    start = next(i for i, l in enumerate(lines) if l.strip().startswith("def generate_target("))
+    indent = len(lines[start]) - len(lines[start].lstrip())
+    end = start + 1
+    while end < len(lines) and (not lines[end].strip() or len(lines[end]) - len(lines[end].lstrip()) > indent):
+        end += 1
+    ns = {"np": np}
+    exec(compile(textwrap.dedent("\n".join(lines[start:end])), f"{path}:{start + 1}", "exec"), ns)
+    return ns["generate_target"]

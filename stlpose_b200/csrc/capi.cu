@@ -70,6 +70,14 @@ int stl_decode(const float* heat, const float* heat_flipped, const float* center
 
 size_t stl_mse_workspace_bytes(void) { return mse_workspace_bytes(); }
 
+int stl_generate_target(const double* joints, const double* joints_vis, const float* joints_weight, int B, int J, int h,
+                        int w, int image_h, int image_w, int sigma, float* target, float* target_weight, void* stream) {
+  if (!have_device()) return 1;
+  if (B > 0 && (!joints || !joints_vis || !target || !target_weight)) { set_error("stl_generate_target: null pointer"); return 1; }
+  return generate_target(joints, joints_vis, joints_weight, B, J, h, w, image_h, image_w, sigma, target, target_weight,
+                         (cudaStream_t)stream);
+}
+
 int stl_upsampled_argmax(const float* heat, int B, int J, int h, int w, int out_h, int out_w, float* coords,
                          float* maxvals, void* stream) {
   if (!have_device()) return 1;

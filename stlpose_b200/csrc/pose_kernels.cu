@@ -194,6 +194,40 @@ __global__ void mse_final_kernel(const double* __restrict__ partial, int n, doub
   }
 }
 
+// ------------------------------------------------------------------ training targets
+// JointsDataset.generate_target (data/JointsDataset.py:230-286) for a whole batch: joints / joints_vis [B][J][3] fp64
+// (crop pixels) -> target fp32 [B][J][h][w], target_weight fp32 [B][J].  mu = int(joint / stride + 0.5) in fp64 like
+// the reference; a (6*sigma+1)^2 unnormalised Gaussian patch exp(-(dx^2+dy^2)/(2 sigma^2)) in fp32; a joint whose patch
+// lies entirely outside the map gets weight 0; invisible joints (weight <= 0.5) get an all-zero map.  One block per map.
+__global__ void __launch_bounds__(256) generate_target_kernel(const double* __restrict__ joints,
+                                                              const double* __restrict__ joints_vis,
+                                                              const float* __restrict__ joints_weight, int J, int h,
+                                                              int w, double stride_x, double stride_y, int sigma,
+                                                              float* __restrict__ target, float* __restrict__ weight) {
+  const long long map = blockIdx.x;
+  const int j = (int)(map % J);
+  const int rad = sigma * 3;
+  const int mx = (int)(joints[map * 3 + 0] / stride_x + 0.5);       // C cast = Python int(): truncation towards zero
+  const int my = (int)(joints[map * 3 + 1] / stride_y + 0.5);
+  const int x0 = mx - rad, y0 = my - rad, x1 = mx + rad + 1, y1 = my + rad + 1;
+  float wgt = (float)joints_vis[map * 3 + 0];
+  const bool outside = x0 >= w || y0 >= h || x1 < 0 || y1 < 0;
+  if (outside) wgt = 0.f;
+  const bool draw = !outside && wgt > 0.5f;
+  const float inv = 1.0f / (float)(2 * sigma * sigma);
+  float* t = target + map * (long long)h * w;
+  for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+    const int y = i / w, x = i - y * w;
+    float v = 0.f;
+    if (draw && x >= x0 && x < x1 && y >= y0 && y < y1) {
+      const float dx = (float)(x - mx), dy = (float)(y - my);
+      v = expf(-(dx * dx + dy * dy) * inv);
+    }
+    t[i] = v;
+  }
+  if (threadIdx.x == 0) weight[map] = joints_weight ? wgt * joints_weight[j] : wgt;
+}
+
 // ------------------------------------------------------------------ arg-max of the bilinearly upsampled heatmaps
 // create_pose_from_outputs (lib/pose_parsing.py:138-151; 04_evaluate_vases_qualitatively.py:216-220,
 // 05_create_archdata_retrieval_db.py:114,131-147): F.interpolate(dets, (256, 192), mode="bilinear", align_corners=True)
@@ -410,6 +444,16 @@ int decode(const float* heat, const float* heat_f, const float* center, const fl
   decode_kernel<<<(unsigned)((maps + warps_per_block - 1) / warps_per_block), warps_per_block * 32, 0, st>>>(
       heat, heat_f, center, scale, B, J, h, w, perm, refine, avg_out, preds, maxvals, coords);
   return check("decode");
+}
+
+int generate_target(const double* joints, const double* joints_vis, const float* joints_weight, int B, int J, int h, int w,
+                    int image_h, int image_w, int sigma, float* target, float* weight, cudaStream_t st) {
+  const long long maps = (long long)B * J;
+  if (maps <= 0) return 0;
+  if (h <= 0 || w <= 0 || sigma <= 0) { set_error("generate_target: bad geometry"); return 1; }
+  generate_target_kernel<<<(unsigned)maps, 256, 0, st>>>(joints, joints_vis, joints_weight, J, h, w, (double)image_w / w,
+                                                       (double)image_h / h, sigma, target, weight);
+  return check("generate_target");
 }
 
 int upsampled_argmax(const float* heat, int B, int J, int h, int w, int out_h, int out_w, float* coords, float* maxvals,

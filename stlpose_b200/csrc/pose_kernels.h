@@ -17,6 +17,8 @@ int flip_back(const float* in, float* out, int B, int J, int h, int w, const int
 int decode(const float* heat, const float* heat_f, const float* center, const float* scale, int B, int J, int h,
            int w, const int* pairs, int n_pairs, int refine, float* avg_out, float* preds, float* maxvals,
            float* coords, cudaStream_t st);
+int generate_target(const double* joints, const double* joints_vis, const float* joints_weight, int B, int J, int h, int w,
+                    int image_h, int image_w, int sigma, float* target, float* weight, cudaStream_t st);
 int upsampled_argmax(const float* heat, int B, int J, int h, int w, int out_h, int out_w, float* coords, float* maxvals,
                      cudaStream_t st);
 int warp_affine_crops(const uint8_t* img, int ih, int iw, const double* minv, int N, int out_h, int out_w,

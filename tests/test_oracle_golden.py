@@ -139,3 +139,17 @@ def test_upsampled_decode_and_pose_entries_match_reference_fixture(golden):
     entries, allk = pose_oracle.create_pose_from_outputs(hm, keypoint_thr=0.1)
     assert np.array_equal(np.array(entries), g["entries"]) and np.array_equal(allk, g["all_keypoints"])
     assert allk[0 * 17 + 3, 3] == 0 and allk[1 * 17 + 7, 3] == 0 and allk[2 * 17 + 16, 3] == 0
+
+
+def test_generate_target_oracle_matches_reference_fixture(golden):
+    from oracle.make_golden import target_inputs
+    g = golden("targets.npz")
+    joints, vis = target_inputs()
+    jw = np.array([1., 1., 1., 1., 1., 1., 1., 1.2, 1.2, 1.5, 1.5, 1., 1., 1.2, 1.2, 1.5, 1.5], np.float32).reshape(17, 1)
+    for b in range(joints.shape[0]):
+        t, w = pose_oracle.generate_target(joints[b], vis[b])
+        assert np.array_equal(t, g["target_plain"][b]) and np.array_equal(w, g["weight_plain"][b])
+        t, w = pose_oracle.generate_target(joints[b], vis[b], joints_weight=jw)
+        assert np.array_equal(w, g["weight_weighted"][b])
+    assert g["weight_plain"][0, 3, 0] == 0                  # patch entirely below the map: weight forced to 0
+    assert not g["target_plain"][0, 2].any()                # patch touching the left border from outside: empty map

@@ -222,3 +222,29 @@ def test_upsampled_decode_and_pose_entries(golden):
         assert clear.mean() > 0.9 and np.array_equal(c[clear], rc[clear])
     e0, k0 = PP.create_pose_entries([], None)
     assert e0 == [] and k0 == []
+
+
+def test_generate_target_matches_reference_fixture(golden):
+    """stl_generate_target (batched, device) vs targets produced by the reference's JointsDataset.generate_target."""
+    from oracle.make_golden import target_inputs
+    from stlpose_b200 import targets
+    g = golden("targets.npz")
+    joints, vis = target_inputs()
+    t, w = targets.generate_target(joints, vis)
+    assert t.shape == (6, 17, 64, 48) and w.shape == (6, 17, 1) and t.is_cuda
+    assert np.array_equal(w.cpu().numpy(), g["weight_plain"])
+    assert np.abs(t.cpu().numpy() - g["target_plain"]).max() < 3e-7           # expf vs libm: <= 2 ulp of values <= 1
+    assert np.array_equal(t.cpu().numpy() > 0, g["target_plain"] > 0)         # identical support
+    jw = [1., 1., 1., 1., 1., 1., 1., 1.2, 1.2, 1.5, 1.5, 1., 1., 1.2, 1.2, 1.5, 1.5]
+    _, ww = targets.generate_target(joints, vis, joints_weight=jw)
+    assert np.array_equal(ww.cpu().numpy(), g["weight_weighted"])
+    t1, w1 = targets.generate_target(joints[1], vis[1])                       # single sample, like the reference method
+    assert t1.shape == (17, 64, 48) and np.abs(t1.cpu().numpy() - g["target_plain"][1]).max() < 3e-7
+    # other geometry (W48: 288x384 crops -> 72x96 maps, sigma 3) vs the oracle
+    rng = np.random.default_rng(4)
+    j2 = np.zeros((3, 17, 3)); j2[..., 0] = rng.uniform(-20, 300, (3, 17)); j2[..., 1] = rng.uniform(-20, 400, (3, 17))
+    v2 = np.ones((3, 17, 3))
+    t2, w2 = targets.generate_target(j2, v2, image_size=(288, 384), heatmap_size=(72, 96), sigma=3)
+    for b in range(3):
+        ot, ow = pose_oracle.generate_target(j2[b], v2[b], (288, 384), (72, 96), 3)
+        assert np.abs(t2[b].cpu().numpy() - ot).max() < 3e-7 and np.array_equal(w2[b].cpu().numpy(), ow)
