@@ -53,7 +53,31 @@ def _worker(rank, world, port, q):
                 want = sd0[n].cuda() - lr * g
                 err = (sd[n].detach() - want).norm() / (lr * g).norm().clamp_min(1e-12)
                 ok_ref = ok_ref and err.item() < 2e-2
-        q.put((rank, bool(same), bool(ok_ref)))
+        # eager step with bucket all-reduces launched from autograd hooks (overlapping the rest of backward) must give
+        # the same update as the graph-replayed step followed by reduce_all()
+        m2 = S.PoseHighResolutionNet(width=32)
+        m2.load_state_dict(sd0, strict=True)
+        m2 = m2.cuda().train()
+        opt2 = torch.optim.SGD(m2.parameters(), lr=lr)
+        red2 = GradientReducer(m2.parameters(), local_batch=hi - lo, bucket_bytes=8 << 20).attach_hooks()
+        assert len(red2.buckets) > 4
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            loss2 = S.PersonMSELoss()(m2(x[lo:hi].cuda()), tgt[lo:hi].cuda(), tw[lo:hi].cuda())
+            opt2.zero_grad()
+            loss2.backward()
+            red2.finish_step()
+            opt2.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        sd2 = dict(m2.named_parameters())
+        ok_hooks = True
+        for n in names:
+            upd = (sd[n].detach() - sd0[n].cuda())
+            err = (sd2[n].detach() - sd[n].detach()).norm() / upd.norm().clamp_min(1e-12)
+            ok_hooks = ok_hooks and err.item() < 1e-3
+        q.put((rank, bool(same), bool(ok_ref and ok_hooks)))
     finally:
         dist.destroy_process_group()
 
