@@ -353,7 +353,7 @@ bool basic_block_supported(int H, int W, int C) { return C == kC && W + 2 <= kMa
 
 // x, y: padded-linear bf16 [N][H+1][W+1][32]; w1, w2: packed [9][32][32] bf16; b1, b2: 32 fp32 (folded BatchNorm).
 int basic_block_launch(const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bfloat16* w1, const float* b1,
-                       const __nv_bfloat16* w2, const float* b2, int N, int H, int W, int pdl, cudaStream_t stream) {
+                       const __nv_bfloat16* w2, const float* b2, int N, int H, int W, int max_ctas, cudaStream_t stream) {
   if (!basic_block_supported(H, W, kC)) { set_error("basic_block: unsupported geometry %dx%d", H, W); return 1; }
   BlockParams p{};
   p.Wp = W + 1; p.Hp = H + 1; p.H = H; p.W = W; p.halo = W + 2;
@@ -394,8 +394,8 @@ int basic_block_launch(const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bflo
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const long long grid = p.total_tiles < sms ? p.total_tiles : sms;
-  (void)pdl;
+  long long grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   basic_block_kernel<<<(unsigned)grid, kBlkThreads, smem, stream>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("basic_block launch: %s", cudaGetErrorString(e)); return 1; }

@@ -126,7 +126,7 @@ int conv_launch(const ConvSpec& spec, cudaStream_t stream);
 // Fused BasicBlock (block_tc.cu): y = relu(conv2(relu(conv1(x) + b1)) + b2 + x), both 3x3 / stride 1 / 32 -> 32 channels.
 bool basic_block_supported(int H, int W, int C);
 int basic_block_launch(const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bfloat16* w1, const float* b1,
-                       const __nv_bfloat16* w2, const float* b2, int N, int H, int W, int pdl, cudaStream_t stream);
+                       const __nv_bfloat16* w2, const float* b2, int N, int H, int W, int max_ctas, cudaStream_t stream);
 
 // Reference CUDA-core direct convolution with the same fused epilogue (validation only; slow).
 int conv_launch_naive(const ConvSpec& spec, cudaStream_t stream);

@@ -958,7 +958,7 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   // Measured on B200: for layers whose weights stay resident (N <= 64, every 1x1) pairs are slower - the MMA rate is
   // bound by the A-operand fetch (128 rows x 32 B per SM per instruction), which pairing does not reduce.  For
   // layers that stream their weights (C >= 128) each CTA of a pair streams only half of the rows: half the L2 traffic.
-  const bool pair_ok = p.mode == 0 && p.epi_tma && p.nt % 32 == 0 && !s.max_ctas && !getenv("STL_DBG_NO_PAIR");
+  const bool pair_ok = p.mode == 0 && p.epi_tma && p.nt % 32 == 0 && !getenv("STL_DBG_NO_PAIR");
   size_t resident = 0;
   p.pair = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
@@ -1048,7 +1048,8 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   long long g = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   if (s.max_ctas > 0 && g > s.max_ctas) g = s.max_ctas;
   if (p.pair) {  // one cluster of two CTAs per tile pair
-    const long long pairs = p.total_tiles < num_sms() / 2 ? p.total_tiles : num_sms() / 2;
+    long long pairs = p.total_tiles < num_sms() / 2 ? p.total_tiles : num_sms() / 2;
+    if (s.max_ctas > 1 && pairs > s.max_ctas / 2) pairs = s.max_ctas / 2;
     g = 2 * pairs;
   }
   *grid = (int)g;

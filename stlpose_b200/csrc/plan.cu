@@ -152,8 +152,12 @@ struct Plan::Builder {
         const int n_out = (stage == 4 && m == n_mod - 1) ? 1 : nb;  // HRnet.py:413-416
         snprintf(k1, sizeof k1, "stage%d.%d", stage, m);
         const std::string mp = k1;
-        // branches: `blocks` BasicBlocks each (HRnet.py:32-61, 252-253)
+        // branches: `blocks` BasicBlocks each (HRnet.py:32-61, 252-253).  They are independent of each other and CAN run
+        // concurrently, each on its share of the SMs (Plan::branch_streams, measured slower and off by default)
+        static const int kShares[5][4] = {{0, 0, 0, 0}, {148, 0, 0, 0}, {84, 64, 0, 0}, {62, 48, 38, 0}, {50, 36, 30, 32}};
+        const int par_id = P.n_par_groups++;
         for (int b = 0; b < nb; ++b) {
+          const size_t branch_first_op = P.ops.size();
           // the 2 x blocks convs of a branch form a group: executed sub-batch by sub-batch so that the three
           // activation buffers they cycle through stay resident in L2 (bind() picks the sub-batch size)
           // 32-channel branches: each BasicBlock is ONE kernel (block_tc.cu), the intermediate never leaves the SM
@@ -184,6 +188,11 @@ struct Plan::Builder {
             grp.count = (int)P.ops.size() - grp.first;
             for (int i = 0; i < grp.count; ++i) P.ops[grp.first + i].group = (int)P.groups.size();
             P.groups.push_back(grp);
+          }
+          for (size_t i = branch_first_op; i < P.ops.size(); ++i) {
+            P.ops[i].par_group = par_id;
+            P.ops[i].stream = b;
+            P.ops[i].sm_share = kShares[nb][b];
           }
         }
         // fuse layers (HRnet.py:188-243, 255-264)
@@ -252,6 +261,7 @@ Plan* Plan::create(const stl_hrnet_cfg& cfg) {
   Plan* p = new Plan();
   p->cfg = cfg;
   if (const char* e = getenv("STLPOSE_FUSE_BLOCK")) p->fuse_blocks = atoi(e);
+  if (const char* e = getenv("STLPOSE_BRANCH_STREAMS")) p->branch_streams = atoi(e);
   if (const char* e = getenv("STLPOSE_STEM_IM2COL")) p->stem_im2col = atoi(e);
   Builder b(*p);
   b.build();
@@ -359,6 +369,9 @@ int Plan::bind(int n_images, const void* arena, void* workspace, size_t ws_bytes
       Prepared& pr = prepared[i][sb];
       if (s.img_lo >= n_images && subs > 1) { pr.grid = 0; continue; }
       if (conv_prepare(s, &pr.params, &pr.grid, &pr.smem)) return 1;
+      pr.grid_par = pr.grid;
+      if (op.sm_share > 0 && pr.grid > op.sm_share)
+        pr.grid_par = pr.params.pair ? 2 * (op.sm_share / 2) : op.sm_share;
     }
   }
   launches.clear();
@@ -397,9 +410,40 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
     std::vector<cudaEvent_t>& v;
     ~EvGuard() { for (auto e : v) cudaEventDestroy(e); }
   } guard{ev};
+  // branches of a HighResolutionModule run concurrently on side streams (forked from / joined back into `st`, which
+  // also works under stream capture); a timed forward stays sequential so that per-launch times mean something
+  const bool par = branch_streams && !op_ms_host;
+  if (par && !ev_fork) {
+    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    for (int s = 1; s < 4; ++s) {
+      cudaStreamCreateWithFlags(&side[s], cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&ev_join[s], cudaEventDisableTiming);
+    }
+  }
+  int cur_par = -1;
+  unsigned used = 0;   // side streams used by the current module
+  auto join = [&]() {
+    for (int s = 1; s < 4; ++s)
+      if (used & (1u << s)) { cudaEventRecord(ev_join[s], side[s]); cudaStreamWaitEvent(st, ev_join[s], 0); }
+    used = 0;
+    cur_par = -1;
+  };
+  cudaStream_t main_st = st;
   for (size_t li = 0; li < launches.size(); ++li) {
     const int i = launches[li].op;
     const Op& op = ops[i];
+    st = main_st;
+    if (par) {
+      if (op.par_group != cur_par) {
+        if (cur_par >= 0) join();
+        if (op.par_group >= 0) { cudaEventRecord(ev_fork, main_st); cur_par = op.par_group; }
+      }
+      if (op.par_group >= 0 && op.stream > 0) {
+        if (!(used & (1u << op.stream))) { cudaStreamWaitEvent(side[op.stream], ev_fork, 0); used |= 1u << op.stream; }
+        st = side[op.stream];
+      }
+    }
+    const bool limited = par && op.par_group >= 0;
     switch (op.kind) {
       case OP_STEM: {
         if (stem_im2col ? stl::stem_im2col(x, reinterpret_cast<__nv_bfloat16*>(slot_ptr[op.out]), n_images, B, cfg.image_h,
@@ -412,7 +456,7 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
       case OP_CONV: {
         Prepared& pr = prepared[i][launches[li].sub];
         if (op.out_nchw) pr.params.out = heat;
-        if (conv_launch_prepared(pr.params, pr.grid, pr.smem, st)) return 1;
+        if (conv_launch_prepared(pr.params, limited ? pr.grid_par : pr.grid, pr.smem, st)) return 1;
         break;
       }
       case OP_BLOCK: {
@@ -424,7 +468,8 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
                                reinterpret_cast<const __nv_bfloat16*>(wbase + L1.w_off),
                                reinterpret_cast<const float*>(wbase + L1.b_off),
                                reinterpret_cast<const __nv_bfloat16*>(wbase + L2.w_off),
-                               reinterpret_cast<const float*>(wbase + L2.b_off), n_images, so.H, so.W, 0, st))
+                               reinterpret_cast<const float*>(wbase + L2.b_off), n_images, so.H, so.W,
+                               limited ? op.sm_share : 0, st))
           return 1;
         break;
       }
@@ -440,6 +485,8 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
     }
     if (op_ms_host) cudaEventRecord(ev[li + 1], st);
   }
+  st = main_st;
+  if (par && cur_par >= 0) join();
   if (op_ms_host) {
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { set_error("plan: timed forward failed: %s", cudaGetErrorString(e)); return 1; }

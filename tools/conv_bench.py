@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--impl", type=int, default=0)
     ap.add_argument("--n", type=int, default=1024)
     ap.add_argument("--mb", type=int, default=0)
+    ap.add_argument("--max-ctas", type=int, default=0, help="restrict the launch to this many CTAs (SM partitioning experiments)")
     ap.add_argument("--counters", action="store_true", help="print per-role cycle counters of the last launch")
     args = ap.parse_args()
     L = _lib.lib()
@@ -67,7 +68,7 @@ def main():
         d.ksize, d.stride = k, s
         d.w_packed = wp.data_ptr(); d.bias_packed = bp.data_ptr()
         d.residual = res.data_ptr() if res is not None else None
-        d.relu = 1; d.out_nchw = int(nchw); d.impl = args.impl; d.force_mb = args.mb
+        d.relu = 1; d.out_nchw = int(nchw); d.impl = args.impl; d.force_mb = args.mb; d.max_ctas = args.max_ctas
         st = _lib.current_stream()
         counters = torch.zeros((148, 3, 4), dtype=torch.int64, device=dev)
         if args.counters:
