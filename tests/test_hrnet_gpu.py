@@ -126,3 +126,47 @@ def test_batch_independence_at_bench_scale():
         n = hi - lo
         assert torch.equal(small[:n], big[lo:hi]) and torch.equal(small[n:], big[B + lo:B + hi])
     assert torch.isfinite(big).all()
+
+
+def test_boxes_to_keypoints_pipeline_vs_oracle():
+    """The evaluation loop either side of the network, as 04_evaluate_vases_qualitatively.py:206-220 / 03_evaluate.py:124-152
+    run it: person boxes -> TransformDetection crops -> ToTensor + Normalize -> forward_pass(flip=True) ->
+    get_final_preds_hrnet (and the PCK of the loop), device path vs the oracle chain on the same image."""
+    import stlpose_b200 as S
+    from oracle.make_golden import crop_inputs
+    from stlpose_b200 import metrics
+    from stlpose_b200.transforms import TransformDetection
+    img, boxes = crop_inputs()
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    # oracle chain
+    dets, c_ref, s_ref = pose_oracle.transform_detection(img, boxes)
+    x_ref = (torch.from_numpy(dets).float().div(255) - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    sd = hrnet_oracle.synth_state_dict(32, seed=0)
+    h0 = hrnet_oracle.hrnet_forward(sd, x_ref, 32).numpy()
+    h1 = hrnet_oracle.hrnet_forward(sd, x_ref.flip(3), 32).numpy()
+    heat_ref = pose_oracle.flip_average(h0, h1)
+    preds_ref, maxv_ref, _ = pose_oracle.get_final_preds(heat_ref, c_ref, s_ref)
+    # device chain: nothing but the image and the boxes crosses the host boundary
+    m = _model(32, (256, 192))
+    x, c, s = TransformDetection().extract_normalized(img, boxes, mean, std)
+    assert torch.equal(x.cpu(), x_ref) and np.array_equal(c, c_ref) and np.array_equal(s, s_ref)
+    heat = S.forward_pass(m, x, "HRNet", device="cuda", flip=True)
+    assert np.abs(heat.cpu().numpy() - heat_ref).max() < HEAT_TOL
+    preds, maxv, _ = S.get_final_preds_hrnet(heat, c, s)
+    flat = np.sort(heat_ref.reshape(len(boxes), 17, -1), axis=2)
+    sure = (flat[:, :, -1] - flat[:, :, -2]) > 2 * HEAT_TOL
+    k = (s_ref[:, 0] * 200.0 / 48.0)[:, None, None]                  # image pixels per heatmap pixel
+    if sure.any():
+        assert (np.abs(preds - preds_ref) / k)[sure].max() <= 0.25 + 1e-3
+    assert np.abs(maxv - maxv_ref).max() < HEAT_TOL
+    # PCK of the loop against a target built from the oracle's own keypoints: same verdicts on both paths
+    tgt = np.zeros_like(heat_ref)
+    _, _, coords_ref = pose_oracle.get_final_preds(heat_ref, c_ref, s_ref)
+    for n in range(len(boxes)):
+        for j in range(17):
+            tgt[n, j, int(coords_ref[n, j, 1]), int(coords_ref[n, j, 0])] = 1.0
+    acc_dev = metrics.accuracy(heat, tgt)
+    acc_ref = pose_oracle.accuracy(heat_ref, tgt)
+    assert acc_dev[2] == acc_ref[2]
+    if sure.all():
+        assert abs(acc_dev[1] - acc_ref[1]) < 1e-6
