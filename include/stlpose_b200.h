@@ -54,6 +54,17 @@ int stl_decode(const float* heat, const float* heat_flipped, const float* center
  *   loss = 0.5/(J*B*hw) * sum (tw*(out-tgt))^2 ;  grad = tw^2*(out-tgt)/(J*B*hw)   (grad may be null)
  * out/tgt [B][J][hw] fp32, tw [B][J] fp32, loss: 1 float.  workspace: stl_mse_workspace_bytes() bytes. */
 size_t stl_mse_workspace_bytes(void);
+/* OKS rescoring + greedy OKS-NMS: generate_submission_hrnet (lib/metrics.py:232-258) and
+ * nms.oks_nms / oks_iou (lib/nms.py:10-74) for all images of an evaluation at once.  Persons are grouped by image:
+ * persons [image_offsets[i], image_offsets[i+1]) belong to image i (at most 128 per image; pass the maximum).
+ * keypoints [M][J][3] fp32 (x, y, score; J <= 64), area / box_score [M] fp64, vars [J] fp64 = (2*sigma_j)^2.
+ * rescore != 0: score = mean(joint scores > in_vis_thr) * box_score, else box_score is the score.  nms_vis_thr < 0: all
+ * joints enter the OKS (what the reference's call does); otherwise only joints of the candidate with score > nms_vis_thr.
+ * Outputs: score_out [M] fp64, keep_rank [M] (position in the image's keep list, -1 = suppressed). */
+int stl_oks_nms(const float* keypoints, const double* area, const double* box_score, const int* image_offsets,
+                int n_images, int max_persons_per_image, int J, const double* vars, float in_vis_thr, double oks_thr,
+                float nms_vis_thr, int rescore, double* score_out, int* keep_rank, void* stream);
+
 /* Training targets: JointsDataset.generate_target (data/JointsDataset.py:230-286) for a batch.
  * joints, joints_vis: [B][J][3] fp64 on the device (x, y in crop pixels; visibility in column 0); joints_weight: [J] fp32
  * or null (use_different_joints_weight); outputs target fp32 [B][J][h][w] (every element written) and target_weight

@@ -166,7 +166,62 @@ def make_targets():
     print("targets", outs["target_plain"].shape, float(outs["target_plain"].sum()), outs["weight_weighted"][0, :6, 0])
 
 
+def submission_inputs():
+    """Persons of an evaluation: all_preds [M,17,3] float32 (x, y, max value), all_bboxes [M,6] float64 (center, scale,
+    area, box score), image ids interleaved across images.  Images hold 1..24 persons; many are jittered duplicates of
+    another person of the same image (so the OKS-NMS suppresses), one person has no joint above the visibility threshold."""
+    rng = np.random.default_rng(2024)
+    preds, boxes, ids = [], [], []
+    for img, n in enumerate((1, 2, 5, 24, 9, 3)):
+        base = []
+        for p in range(n):
+            if base and rng.random() < 0.55:
+                src = base[rng.integers(len(base))]
+                k = src + rng.normal(0, rng.choice([0.3, 2.0, 8.0]), size=src.shape)
+            else:
+                c = rng.uniform(60, 500, 2)
+                k = c + rng.normal(0, 40, size=(17, 2))
+                base.append(k)
+            sc = rng.uniform(0.05, 0.98, size=(17, 1))
+            scale = rng.uniform(0.4, 2.5) * np.array([0.75, 1.0])
+            preds.append(np.concatenate([k, sc], axis=1).astype(np.float32))
+            boxes.append(np.concatenate([k.mean(0), scale, [np.prod(scale * 200)], [rng.uniform(0.3, 1.0)]]))
+            ids.append(1000 + 7 * img)
+    preds, boxes = np.stack(preds), np.stack(boxes)
+    preds[0, :, 2] = rng.uniform(0.01, 0.19, 17).astype(np.float32)      # nothing visible: rescored to 0 (kept: alone)
+    perm = rng.permutation(len(ids))                                     # images interleaved, as batches arrive
+    return preds[perm], boxes[perm], [ids[i] for i in perm]
+
+
+def make_submission():
+    import json
+    import tempfile
+    F = ref_shim.submission_functions()
+    preds, boxes, ids = submission_inputs()
+    path = os.path.join(tempfile.mkdtemp(prefix="stlpose_sub_"), "preds.json")
+    # the reference takes lists of per-batch arrays (03_evaluate.py:185-186) and concatenates them
+    F.generate_submission_hrnet([preds[:20].copy(), preds[20:].copy()], [boxes[:20].copy(), boxes[20:].copy()], list(ids), path)
+    results = json.load(open(path))
+    out = {"image_id": np.array([r["image_id"] for r in results]),
+           "keypoints": np.array([r["keypoints"] for r in results]),
+           "score": np.array([r["score"] for r in results]),
+           "center": np.array([r["center"] for r in results]), "scale": np.array([r["scale"] for r in results])}
+    # lib.nms.oks_nms directly on the biggest image: default call, other thresholds, the visibility mask
+    big = [m for m, i in enumerate(ids) if i == 1000 + 7 * 3]
+    db = [{"keypoints": preds[m], "area": boxes[m, 4], "score": boxes[m, 5]} for m in big]
+    for tag, kw in (("t09", dict(thresh=0.9)), ("t05", dict(thresh=0.5)), ("t07_vis", dict(thresh=0.7, in_vis_thre=0.4))):
+        out[f"keep_{tag}"] = np.array(F.nms.oks_nms(db, **kw))
+    g = preds[big[0]].reshape(-1)
+    d = np.stack([preds[m].reshape(-1) for m in big[1:]])
+    out["iou_plain"] = F.nms.oks_iou(g, d, boxes[big[0], 4], boxes[big[1:], 4])
+    out["iou_vis"] = F.nms.oks_iou(g, d, boxes[big[0], 4], boxes[big[1:], 4], in_vis_thre=0.4)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "submission.npz"), **out)
+    print("submission", len(results), "of", len(ids), "persons kept;", {k: v.tolist() for k, v in out.items() if k.startswith("keep")})
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "submission":
+        return make_submission()
     if len(sys.argv) > 1 and sys.argv[1] == "targets":
         return make_targets()
     if len(sys.argv) > 1 and sys.argv[1] == "pose_entries":

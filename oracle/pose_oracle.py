@@ -387,6 +387,83 @@ def accuracy(output, target, thr=0.5):
     return acc, avg_acc, cnt, pred
 
 
+COCO_SIGMAS = np.array([.26, .25, .25, .35, .35, .79, .79, .72, .72, .62, .62, 1.07, 1.07, .87, .87, .89, .89]) / 10.0
+
+
+def oks_iou(g, d, a_g, a_d, sigmas=None, in_vis_thre=None):
+    """lib/nms.py:49-74: OKS of one person g [3J] against persons d [n,3J] (x, y, v interleaved).  Vectorised over the
+    persons; dtypes as the reference (float32 keypoints: differences and squares in float32, the divisions in float64).
+    The reference's mask ``list(vg > t) and list(vd > t)`` evaluates to the SECOND list, i.e. the candidate's mask."""
+    sig = sigmas if isinstance(sigmas, np.ndarray) else COCO_SIGMAS
+    var = (sig * 2) ** 2
+    ious = np.zeros(d.shape[0])
+    dx = d[:, 0::3] - g[0::3]
+    dy = d[:, 1::3] - g[1::3]
+    e = (dx ** 2 + dy ** 2) / var / ((a_g + a_d) / 2 + np.spacing(1))[:, None] / 2
+    for n in range(d.shape[0]):
+        en = e[n][d[n, 2::3] > in_vis_thre] if in_vis_thre is not None else e[n]
+        ious[n] = np.sum(np.exp(-np.ascontiguousarray(en))) / en.shape[0] if en.shape[0] != 0 else 0.0
+    return ious
+
+
+def oks_nms(kpts, scores, areas, thresh, sigmas=None, in_vis_thre=None):
+    """lib/nms.py:10-46 on arrays: kpts [n,J,3], scores [n], areas [n] -> indices to keep, best first."""
+    if len(kpts) == 0:
+        return []
+    flat = np.asarray(kpts).reshape(len(kpts), -1)
+    order = np.asarray(scores).argsort()[::-1]
+    keep = []
+    while order.size > 0:
+        i = order[0]
+        keep.append(int(i))
+        ovr = oks_iou(flat[i], flat[order[1:]], areas[i], areas[order[1:]], sigmas, in_vis_thre)
+        order = order[np.where(ovr <= thresh)[0] + 1]
+    return keep
+
+
+def rescore(all_preds, box_scores, in_vis_thr=0.2):
+    """lib/metrics.py:239-250: score = mean of the joint scores above in_vis_thr (float32 running sum in joint order,
+    0 when there is none) times the box score (float64)."""
+    out = np.zeros(len(all_preds))
+    for m, kpt in enumerate(all_preds):
+        s, n = 0, 0
+        for j in range(kpt.shape[0]):
+            if kpt[j][2] > in_vis_thr:
+                s = s + kpt[j][2]
+                n += 1
+        if n:
+            s = s / n
+        out[m] = s * box_scores[m]
+    return out
+
+
+def rescore_and_nms(all_preds, all_bboxes, image_ids, in_vis_thr=0.2, oks_thr=0.9):
+    """lib/metrics.py:211-258 (generate_submission_hrnet up to the JSON packing): group by image in first-appearance
+    order, rescore, OKS-NMS.  -> list per image of (person index m, rescored score), best first."""
+    groups = {}
+    for m, img in enumerate(image_ids):
+        groups.setdefault(img, []).append(m)
+    scores = rescore(all_preds, all_bboxes[:, 5], in_vis_thr)
+    out = []
+    for img, ms in groups.items():
+        ms = np.array(ms)
+        keep = oks_nms(all_preds[ms], scores[ms], all_bboxes[ms, 4], oks_thr)
+        out.append([(int(ms[k]), scores[ms[k]]) for k in keep])
+    return out
+
+
+def coco_results(all_preds, all_bboxes, image_ids, kept):
+    """data/data_processing.py:52-82 (convert_keypoints_to_coco_format) on the output of rescore_and_nms: one result dict
+    per kept person, 'keypoints' = 51 float64 values (x, y, score per joint)."""
+    results = []
+    for persons in kept:
+        for m, score in persons:
+            results.append({"image_id": image_ids[m], "category_id": 1,
+                            "keypoints": list(all_preds[m].astype(np.float64).reshape(-1)), "score": score,
+                            "center": list(all_bboxes[m][0:2]), "scale": list(all_bboxes[m][2:4])})
+    return results
+
+
 def synth_boxes(n, seed=0):
     """Synthetic person boxes as SURVEY.md 8(d) config 1: center, scale as _xywh2cs would make them
     (data/HRNet_Coco.py:233-248): scale = (0.75*h, h)/200*1.25."""

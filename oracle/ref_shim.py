@@ -175,3 +175,30 @@ def generate_target_function():
     ns = {"np": np}
     exec(compile(textwrap.dedent("\n".join(lines[start:end])), f"{path}:{start + 1}", "exec"), ns)
     return ns["generate_target"]
+
+
+def submission_functions():
+    """``generate_submission_hrnet`` (lib/metrics.py:192-265) and ``convert_keypoints_to_coco_format``
+    (data/data_processing.py:52-82) executed from their unmodified source text, around the reference's importable
+    ``lib.nms``.  Neither module imports here (pycocotools; ``REORDER_MAP``); the only stand-in is ``np.float`` (removed
+    from NumPy >= 1.24, used at data_processing.py:62), supplied as an attribute of the namespace's ``np``."""
+    import json
+    from collections import defaultdict
+    import numpy as np
+    _install()
+    nms_lib = importlib.import_module("lib.nms")
+
+    def cut(path, name):
+        lines = open(path).read().split("\n")
+        start = next(i for i, l in enumerate(lines) if l.startswith(f"def {name}("))
+        end = next((i for i in range(start + 1, len(lines)) if lines[i].startswith("def ")), len(lines))
+        return compile("\n" * start + "\n".join(lines[start:end]), path, "exec")
+
+    np_ns = types.SimpleNamespace(**{k: getattr(np, k) for k in ("array", "zeros", "concatenate")}, float=np.float64)
+    dp_ns = {"np": np_ns}
+    exec(cut(os.path.join(REF_SRC, "data", "data_processing.py"), "convert_keypoints_to_coco_format"), dp_ns)
+    m_ns = {"np": np, "json": json, "defaultdict": defaultdict, "nms_lib": nms_lib,
+            "data_processing": types.SimpleNamespace(convert_keypoints_to_coco_format=dp_ns["convert_keypoints_to_coco_format"])}
+    exec(cut(os.path.join(REF_SRC, "lib", "metrics.py"), "generate_submission_hrnet"), m_ns)
+    return types.SimpleNamespace(generate_submission_hrnet=m_ns["generate_submission_hrnet"], nms=nms_lib,
+                                 convert_keypoints_to_coco_format=dp_ns["convert_keypoints_to_coco_format"])

@@ -59,6 +59,8 @@ PROTOTYPES = {
     "stl_decode": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p,
                                   ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]),
     "stl_mse_workspace_bytes": (ctypes.c_size_t, []),
+    "stl_oks_nms": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_float,
+                                   ctypes.c_double, ctypes.c_float, ctypes.c_int, vp, vp, vp]),
     "stl_generate_target": (ctypes.c_int, [vp, vp, vp] + [ctypes.c_int] * 7 + [vp, vp, vp]),
     "stl_upsampled_argmax": (ctypes.c_int, [vp] + [ctypes.c_int] * 6 + [vp, vp, vp]),
     "stl_warp_affine_crops": (ctypes.c_int, [vp] + [ctypes.c_int] * 2 + [vp] + [ctypes.c_int] * 3 + [vp, vp, vp, vp, vp]),

@@ -70,6 +70,20 @@ int stl_decode(const float* heat, const float* heat_flipped, const float* center
 
 size_t stl_mse_workspace_bytes(void) { return mse_workspace_bytes(); }
 
+int stl_oks_nms(const float* keypoints, const double* area, const double* box_score, const int* image_offsets,
+                int n_images, int max_persons_per_image, int J, const double* vars, float in_vis_thr, double oks_thr,
+                float nms_vis_thr, int rescore, double* score_out, int* keep_rank, void* stream) {
+  if (!have_device()) return 1;
+  if (n_images > 0 && (!keypoints || !area || !box_score || !image_offsets || !vars || !score_out || !keep_rank)) {
+    set_error("stl_oks_nms: null pointer");
+    return 1;
+  }
+  if (J < 1 || J > kMaxJoints) { set_error("stl_oks_nms: 1..%d joints supported (got %d)", kMaxJoints, J); return 1; }
+  if (max_persons_per_image > 128) { set_error("stl_oks_nms: at most 128 persons per image (got %d)", max_persons_per_image); return 1; }
+  return oks_nms(keypoints, area, box_score, image_offsets, n_images, J, vars, in_vis_thr, oks_thr, nms_vis_thr, rescore,
+                 score_out, keep_rank, (cudaStream_t)stream);
+}
+
 int stl_generate_target(const double* joints, const double* joints_vis, const float* joints_weight, int B, int J, int h,
                         int w, int image_h, int image_w, int sigma, float* target, float* target_weight, void* stream) {
   if (!have_device()) return 1;

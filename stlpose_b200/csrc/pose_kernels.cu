@@ -194,6 +194,93 @@ __global__ void mse_final_kernel(const double* __restrict__ partial, int n, doub
   }
 }
 
+// ------------------------------------------------------------------ OKS rescoring + greedy OKS-NMS per image
+// generate_submission_hrnet (lib/metrics.py:232-258) + nms.oks_nms / oks_iou (lib/nms.py:10-74): per person,
+// score = mean(joint scores > in_vis_thr) * box score; per image, persons are visited by descending score and a person
+// is dropped when its OKS with an already kept one exceeds oks_thr.  OKS = mean_j exp(-(d_j^2 / var_j) / ((a_g+a_d)/2 + eps) / 2)
+// over the joints selected by vis_thr (the reference's `list(vg > t) and list(vd > t)` keeps the mask of d only; < 0 = all).
+// One block per image (persons [off[i], off[i+1]), at most kMaxPersons); float64 like NumPy; joint scores are summed in
+// float32 in joint order like the reference's scalar loop.  keep_rank[m] = position in the keep list or -1.
+constexpr int kMaxPersons = 128;
+__global__ void __launch_bounds__(128) oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ area,
+                                                      const double* __restrict__ box_score, const int* __restrict__ off,
+                                                      int J, const double* __restrict__ vars, float in_vis_thr,
+                                                      double oks_thr, float nms_vis_thr, int rescore,
+                                                      double* __restrict__ score_out, int* __restrict__ keep_rank) {
+  __shared__ double s_score[kMaxPersons];
+  __shared__ int s_order[kMaxPersons];
+  __shared__ unsigned char s_dead[kMaxPersons];
+  const int lo = off[blockIdx.x], n = off[blockIdx.x + 1] - lo;
+  if (n <= 0) return;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float* kp = kpts + (size_t)(lo + i) * J * 3;
+    double sc = box_score[lo + i];
+    if (rescore) {
+      float acc = 0.f;
+      int valid = 0;
+      for (int j = 0; j < J; ++j) {
+        const float js = kp[j * 3 + 2];
+        if (js > in_vis_thr) { acc = acc + js; ++valid; }
+      }
+      if (valid) acc = acc / (float)valid;
+      sc = (double)acc * sc;
+    }
+    s_score[i] = sc;
+    score_out[lo + i] = sc;
+    s_dead[i] = 0;
+    keep_rank[lo + i] = -1;
+  }
+  __syncthreads();
+  // descending order by rank counting (ties: the later index first, like argsort()[::-1] on distinct scores)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int r = 0;
+    for (int k = 0; k < n; ++k) r += (s_score[k] > s_score[i]) || (s_score[k] == s_score[i] && k > i);
+    s_order[r] = i;
+  }
+  __syncthreads();
+  int kept = 0;
+  for (int a = 0; a < n; ++a) {
+    const int g = s_order[a];
+    if (s_dead[g]) { __syncthreads(); continue; }        // uniform: s_dead was published by the barrier below
+    if (threadIdx.x == 0) keep_rank[lo + g] = kept;
+    ++kept;
+    const float* kg = kpts + (size_t)(lo + g) * J * 3;
+    for (int b = a + 1 + (int)threadIdx.x; b < n; b += blockDim.x) {
+      const int d = s_order[b];
+      if (s_dead[d]) continue;
+      const float* kd = kpts + (size_t)(lo + d) * J * 3;
+      const double denom = (area[lo + g] + area[lo + d]) / 2 + 2.220446049250313e-16;
+      // e_j as the reference's array expression: differences, squares and their sum in float32 (keypoints are float32,
+      // no FMA contraction), the divisions in float64; joints dropped by the visibility mask are compacted away first
+      double e[kMaxJoints];
+      int cnt = 0;
+      for (int j = 0; j < J; ++j) {
+        if (nms_vis_thr >= 0.f && !(kd[j * 3 + 2] > nms_vis_thr)) continue;
+        const float dx = __fsub_rn(kd[j * 3], kg[j * 3]), dy = __fsub_rn(kd[j * 3 + 1], kg[j * 3 + 1]);
+        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        e[cnt++] = exp(-((double)d2 / vars[j] / denom / 2));
+      }
+      // np.sum of a contiguous float64 array of n <= 128 elements: 8 running partial sums over the multiple-of-8 prefix,
+      // combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail in order (plain loop below 8 elements)
+      double sum = 0.0;
+      if (cnt < 8) {
+        for (int j = 0; j < cnt; ++j) sum += e[j];
+      } else {
+        double r[8];
+        for (int k = 0; k < 8; ++k) r[k] = e[k];
+        int j = 8;
+        for (; j < cnt - (cnt % 8); j += 8)
+          for (int k = 0; k < 8; ++k) r[k] += e[j + k];
+        sum = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; j < cnt; ++j) sum += e[j];
+      }
+      const double oks = cnt ? sum / cnt : 0.0;
+      if (oks > oks_thr) s_dead[d] = 1;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------ training targets
 // JointsDataset.generate_target (data/JointsDataset.py:230-286) for a whole batch: joints / joints_vis [B][J][3] fp64
 // (crop pixels) -> target fp32 [B][J][h][w], target_weight fp32 [B][J].  mu = int(joint / stride + 0.5) in fp64 like
@@ -444,6 +531,15 @@ int decode(const float* heat, const float* heat_f, const float* center, const fl
   decode_kernel<<<(unsigned)((maps + warps_per_block - 1) / warps_per_block), warps_per_block * 32, 0, st>>>(
       heat, heat_f, center, scale, B, J, h, w, perm, refine, avg_out, preds, maxvals, coords);
   return check("decode");
+}
+
+int oks_nms(const float* kpts, const double* area, const double* box_score, const int* offsets, int n_images, int J,
+            const double* vars, float in_vis_thr, double oks_thr, float nms_vis_thr, int rescore, double* score_out,
+            int* keep_rank, cudaStream_t st) {
+  if (n_images <= 0) return 0;
+  oks_nms_kernel<<<n_images, 128, 0, st>>>(kpts, area, box_score, offsets, J, vars, in_vis_thr, oks_thr, nms_vis_thr,
+                                          rescore, score_out, keep_rank);
+  return check("oks_nms");
 }
 
 int generate_target(const double* joints, const double* joints_vis, const float* joints_weight, int B, int J, int h, int w,

@@ -153,3 +153,29 @@ def test_generate_target_oracle_matches_reference_fixture(golden):
         assert np.array_equal(w, g["weight_weighted"][b])
     assert g["weight_plain"][0, 3, 0] == 0                  # patch entirely below the map: weight forced to 0
     assert not g["target_plain"][0, 2].any()                # patch touching the left border from outside: empty map
+
+
+def test_oks_rescoring_nms_oracle_matches_reference_fixture(golden):
+    """Oracle restatement of generate_submission_hrnet's rescoring + lib.nms.oks_nms / oks_iou + the COCO result
+    packing vs the JSON the unmodified reference wrote (tests/golden/submission.npz)."""
+    from oracle.make_golden import submission_inputs
+    g = golden("submission.npz")
+    preds, boxes, ids = submission_inputs()
+    kept = pose_oracle.rescore_and_nms(preds, boxes, ids)
+    res = pose_oracle.coco_results(preds, boxes, ids, kept)
+    assert len(res) == len(g["score"]) and len(res) < len(ids)             # something was suppressed
+    assert [r["image_id"] for r in res] == g["image_id"].tolist()
+    assert np.array_equal(np.array([r["score"] for r in res]), g["score"])  # bit-exact rescoring
+    assert np.array_equal(np.array([r["keypoints"] for r in res]), g["keypoints"])
+    assert np.array_equal(np.array([r["center"] for r in res]), g["center"])
+    assert np.array_equal(np.array([r["scale"] for r in res]), g["scale"])
+    assert (g["score"] == 0).sum() == 1                                     # the person without a visible joint
+    big = [m for m, i in enumerate(ids) if i == 1000 + 7 * 3]
+    kp, ar, sc = preds[big], boxes[big, 4], boxes[big, 5]
+    assert pose_oracle.oks_nms(kp, sc, ar, 0.9) == g["keep_t09"].tolist()
+    assert pose_oracle.oks_nms(kp, sc, ar, 0.5) == g["keep_t05"].tolist()
+    assert pose_oracle.oks_nms(kp, sc, ar, 0.7, in_vis_thre=0.4) == g["keep_t07_vis"].tolist()
+    flat = kp.reshape(len(big), -1)
+    assert np.array_equal(pose_oracle.oks_iou(flat[0], flat[1:], ar[0], ar[1:]), g["iou_plain"])
+    assert np.array_equal(pose_oracle.oks_iou(flat[0], flat[1:], ar[0], ar[1:], in_vis_thre=0.4), g["iou_vis"])
+    assert pose_oracle.oks_nms(kp[:0], sc[:0], ar[:0], 0.9) == []

@@ -248,3 +248,49 @@ def test_generate_target_matches_reference_fixture(golden):
     for b in range(3):
         ot, ow = pose_oracle.generate_target(j2[b], v2[b], (288, 384), (72, 96), 3)
         assert np.abs(t2[b].cpu().numpy() - ot).max() < 3e-7 and np.array_equal(w2[b].cpu().numpy(), ow)
+
+
+def test_oks_rescoring_nms_matches_reference_fixture(golden, tmp_path):
+    """stl_oks_nms (rescoring + greedy OKS-NMS for all images in one launch) through the reference-shaped drop-ins vs
+    the JSON written by the unmodified reference (tests/golden/submission.npz) and vs the oracle on larger random sets."""
+    import json
+    from oracle.make_golden import submission_inputs
+    from stlpose_b200 import nms
+    g = golden("submission.npz")
+    preds, boxes, ids = submission_inputs()
+    path = tmp_path / "preds.json"
+    nms.generate_submission_hrnet([preds[:20].copy(), preds[20:].copy()], [boxes[:20].copy(), boxes[20:].copy()], list(ids),
+                                  str(path))
+    res = json.load(open(path))
+    assert [r["image_id"] for r in res] == g["image_id"].tolist()
+    assert np.array_equal(np.array([r["score"] for r in res]), g["score"])          # bit-exact (float32 sum, fp64 product)
+    assert np.array_equal(np.array([r["keypoints"] for r in res]), g["keypoints"])
+    assert np.array_equal(np.array([r["center"] for r in res]), g["center"])
+    assert np.array_equal(np.array([r["scale"] for r in res]), g["scale"])
+    big = [m for m, i in enumerate(ids) if i == 1000 + 7 * 3]
+    db = [{"keypoints": preds[m], "area": boxes[m, 4], "score": boxes[m, 5]} for m in big]
+    assert nms.oks_nms(db, 0.9) == g["keep_t09"].tolist()
+    assert nms.oks_nms(db, 0.5) == g["keep_t05"].tolist()
+    assert nms.oks_nms(db, 0.7, in_vis_thre=0.4) == g["keep_t07_vis"].tolist()
+    assert nms.oks_nms([], 0.9) == []
+    # larger evaluation: 300 images x up to 40 persons vs the oracle
+    rng = np.random.default_rng(5)
+    P, B, I = [], [], []
+    for img in range(300):
+        n = int(rng.integers(1, 41))
+        c = rng.uniform(50, 600, (max(1, n // 3), 1, 2))
+        k = c[rng.integers(len(c), size=n)] + rng.normal(0, 30, (1, 17, 2)) + rng.normal(0, 3, (n, 17, 2))
+        P.append(np.concatenate([k, rng.uniform(0, 1, (n, 17, 1))], axis=2).astype(np.float32))
+        sc = rng.uniform(0.3, 2.0, (n, 1)) * np.array([0.75, 1.0])
+        B.append(np.concatenate([k.mean(1), sc, np.prod(sc * 200, 1, keepdims=True), rng.uniform(0.2, 1, (n, 1))], axis=1))
+        I += [img] * n
+    P, B = np.concatenate(P), np.concatenate(B)
+    got = nms.rescore_and_nms(P, B, I)
+    want = pose_oracle.rescore_and_nms(P, B, I)
+    assert len(got) == len(want) == 300
+    kept = 0
+    for gi, wi in zip(got, want):
+        assert [p["score"] for p in gi] == [s for _, s in wi]
+        assert all(np.array_equal(p["keypoints"], P[m]) for p, (m, _) in zip(gi, wi))
+        kept += len(wi)
+    assert kept < len(I) * 0.8                                                        # the NMS really suppressed
