@@ -149,7 +149,9 @@ typedef struct stl_conv_desc {
   int relu;
   int out_nchw;
   int impl;                /* 0 = tcgen05 (shifted-descriptor taps), 1 = tcgen05 (one TMA load per tap),
-                              2 = CUDA-core reference kernel (validation only) */
+                              2 = CUDA-core reference kernel (validation only),
+                              3 = tcgen05 with the three taps of a filter row merged into one MMA (N = 3*Cout) where
+                                  the layer allows it (stride-1 3x3, resident weights), else as 0 */
   int force_mb;            /* 0 = auto */
   int max_ctas;            /* 0 = auto */
   void* dbg_counters;      /* optional int64 [148][3][4]: per-CTA cycle counters of the producer / MMA / epilogue

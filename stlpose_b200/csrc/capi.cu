@@ -193,6 +193,7 @@ int stl_conv2d(const stl_conv_desc* d, void* stream) {
   s.relu = d->relu;
   s.out_nchw = d->out_nchw;
   s.force_tap_reload = d->impl == 1;
+  s.kw_merge = d->impl == 3 ? 1 : 0;
   s.force_mb = d->force_mb;
   s.max_ctas = d->max_ctas;
   s.dbg_counters = d->dbg_counters;

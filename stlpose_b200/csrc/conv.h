@@ -44,6 +44,7 @@ struct ConvSpec {
   // tuning / debugging knobs (0 = let the engine decide)
   int force_tap_reload = 0;                // 1: one aligned TMA load per filter tap instead of shifted descriptors
   int force_mb = 0;
+  int kw_merge = 0;                        // 1: kw-merged MMA shape where supported, -1: never, 0: STLPOSE_KW_MERGE=1 decides
   int max_ctas = 0;
   int pdl = 0;                             // 1: programmatic dependent launch (weights and bias must not be produced
                                            //    by the preceding kernel in the stream; activations may be)
@@ -79,6 +80,10 @@ struct ConvParams {
   int nt;          // UMMA N
   int n_ntiles;
   int mb;          // 128-row accumulator blocks per tile
+  int kwm;         // 1: the three taps of a filter row share one MMA (N = 3*nt); the epilogue adds the three column
+                   //    groups at row shifts 2 / 1 / 0 (conv_tc.cu, "kw-merged" mode).  mb = 1, 126 outputs per tile
+  int tile_rows;   // output pixels per tile: 128*mb, or 126 in kw-merged mode
+  uint32_t xch_off;  // kw-merged mode: byte offset (from the activation stages) of the cross-warp row exchange area
   int a_shift;     // 1: halo'd tile loaded once per chunk, taps addressed by shifted descriptors
   int halo;        // rows in front of the tile in shift mode (Wp+1 for 3x3, 0 for 1x1)
   int a_box_rows, a_pieces;

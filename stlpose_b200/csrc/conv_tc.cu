@@ -30,11 +30,22 @@ namespace {
 constexpr int kThreads = 672;          // warp 0: TMA, warp 1: MMA, warps 2..17: two epilogue groups of 8 warps,
                                        // warps 18..19: one epilogue DMA warp per group (panel loads / stores),
                                        // warp 20: second MMA issuer (burst mode: the 128-row blocks of a tile are split)
+constexpr int kThreadsKW = 640;         // kw-merged kernels: no second MMA issuer, 96 registers per thread instead of 80
 constexpr uint32_t kCtlBytes = 4096;   // [0,1024): barriers + TMEM base ; [1024,4096): fp32 bias for all channels
 constexpr uint32_t kBiasOffset = 1024;
 constexpr int kMaxCoutPad = 768;
 constexpr int kEpiStaged = 0, kEpiDirect = 1, kEpiNchw = 2;
 constexpr int kEpiStagedS2 = 3;  // staged epilogue on structured (stride-2) tiles: panels are 4-D TMA boxes (c, w, h, n)
+// kw-merged 3x3 (flat mode, resident weights, staged epilogue).  An N <= 64 tcgen05.mma is bound by its A-operand fetch
+// from shared memory (128 rows x 32 B in ~45 cycles, whatever N is), so narrow layers run at a third to a half of the
+// tensor rate.  Here the three taps of a filter ROW share one instruction: B = the three tap tiles (contiguous in the
+// resident weight block) = N 3*Cout, A = the tile shifted by the row offset (kh-1)*Wp only:
+//   D_kw[q'] = sum_{kh,ci} X[q' + (kh-1)*Wp][ci] * W[kh][kw][co][ci]      (column group kw of the accumulator)
+//   out[q]   = D_0[q-1] + D_1[q] + D_2[q+1]
+// The epilogue thread of accumulator row r adds group 0 of row r-2, group 1 of row r-1 and its own group 2 (warp shuffles;
+// the two rows below a 32-lane quarter come from the neighbouring warp through shared memory) and so holds output pixel
+// q_tile + r - 2: a 128-row block yields 126 outputs, tiles advance by 126 pixels, panels are 126-row TMA boxes.
+constexpr int kEpiStagedKW = 4;
 constexpr size_t kMaxSmem = 227 * 1024;
 
 struct Ctl {
@@ -81,7 +92,7 @@ struct RowPos {
 __device__ __forceinline__ RowPos row_position(const ConvParams& p, long long mt, int r) {
   RowPos pos;
   if (p.mode == 0) {
-    const long long q = p.q_lo + mt * (128 * p.mb) + r;
+    const long long q = p.q_lo + mt * p.tile_rows + r;
     pos.valid = q < p.P;
     pos.q = (int)q;
     const uint32_t t = p.fd_Wp.div((uint32_t)pos.q);
@@ -112,6 +123,15 @@ struct EpiParams {
   const __nv_bfloat16* residual;
   int cout, relu, n_up, H, W, skip;
 };
+
+// Packed fp32x2 add on register pairs (FADD2): (a0, a1) += (b0, b1), operands as raw bits.
+__device__ __forceinline__ void fadd2(uint32_t& a0, uint32_t& a1, uint32_t b0, uint32_t b1) {
+  uint64_t a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "r"(b0), "r"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "l"(a));
+}
 
 __device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
   uint32_t r;
@@ -207,7 +227,7 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, const EpiPar
 // Code size matters here: ten warps run four different roles out of one instruction cache, so everything that
 // does not have to be unrolled is a rolled loop and every epilogue path exists exactly once per kernel.
 template <int MB, int KSTEPS, int TAPS, int EPI, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle-128B atoms (8 rows x 128 B) must start on their natural boundary.
   const uint32_t raw = smem_u32(smem_raw);
@@ -218,13 +238,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t b_base = a_base + (uint32_t)p.a_stages * p.a_stage_bytes;
 
   constexpr bool NCHW = EPI == kEpiNchw;
-  constexpr bool kFlatOnly = EPI == kEpiStaged || EPI == kEpiNchw;  // these kernels are only ever launched in flat mode
+  constexpr bool KWM = EPI == kEpiStagedKW;                         // kw-merged 3x3 (MB = 1, TAPS = 9, never PAIR)
+  constexpr bool kFlatOnly = EPI == kEpiStaged || EPI == kEpiNchw || KWM;  // these kernels are only ever launched in flat mode
   constexpr bool kStruct = EPI == kEpiStagedS2;                     // ... and this one only on structured tiles
-  constexpr bool kStagedEpi = EPI == kEpiStaged || EPI == kEpiStagedS2;
+  constexpr bool kStagedEpi = EPI == kEpiStaged || EPI == kEpiStagedS2 || KWM;
+  constexpr int kPanelRows = KWM ? 126 : 128;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kSpan = 32u * KSTEPS;
-  const uint32_t acc_cols = (uint32_t)(MB * p.nt);
+  const uint32_t acc_cols = (uint32_t)((KWM ? 3 : MB) * p.nt);
   // weights resident + (shifted-descriptor taps or 1x1): the whole K loop of a chunk is one straight MMA burst
   const bool burst = p.b_resident && (p.a_shift || TAPS == 1);
   // PAIR: two CTAs (one cluster) share every tcgen05.mma: cta_group::2, M = 256 = 128 rows of each CTA, each CTA
@@ -249,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     tma_prefetch_desc(&p.tmB);
     if (p.epi_tma) { tma_prefetch_desc(&p.tmO); if (p.residual) tma_prefetch_desc(&p.tmR); }
   }
-  for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) sbias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.cout_pad; i += (int)blockDim.x) sbias[i] = p.bias[i];
   if (warp == 1) {
     if (PAIR) tmem_alloc_pair(&ctl->tmem_base, p.tmem_cols); else tmem_alloc(&ctl->tmem_base, p.tmem_cols);
   }
@@ -306,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const long long mt = mtile(tile);
       int q0 = 0, wo0 = 0, ho0 = 0, n0 = 0;
       if (kFlatOnly || (!kStruct && p.mode == 0)) {
-        q0 = p.q_lo + (int)(mt * (128 * MB));
+        q0 = p.q_lo + (int)(mt * p.tile_rows) - (KWM ? 1 : 0);  // KWM: accumulator row r <-> pixel q0 + r, output q0 + r - 1
       } else {
         wo0 = (int)(mt % p.tiles_w) * p.bw;
         ho0 = (int)((mt / p.tiles_w) % p.tiles_h) * p.bh;
@@ -376,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int m_lo = part == 0 ? 0 : m_split, m_hi = part == 0 ? m_split : MB;
     if ((part == 1 && p.n_mma != 2) || (PAIR && !is_leader)) goto role_done;
     {
-    const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, (uint32_t)p.nt);
+    const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, (uint32_t)(KWM ? 3 * p.nt : p.nt));
     const uint64_t desc_hi = make_kmajor_desc(0, kSpan) & 0xFFFFFFFF00000000ull;
     const uint32_t desc_lo_flags = (uint32_t)(make_kmajor_desc(0, kSpan) & 0xFFFFFFFFull);
     // descriptors differ only in the 14-bit start-address field (16-byte units) of the low word
@@ -409,6 +431,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (elect_one()) {
             const uint32_t a_lo0 = a_lo_base + a_stage * a_stage_u;
             const uint32_t b_lo0 = b_lo_base + ((nti * p.n_chunks + chunk) * TAPS) * b_stage_u;
+            if constexpr (KWM) {
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) {
+                  const uint64_t da = desc_hi | (uint64_t)(a_lo0 + (uint32_t)kh * wp_u + (uint32_t)((k * 32) >> 4));
+                  const uint64_t db = desc_hi | (uint64_t)(b_lo0 + (uint32_t)(3 * kh) * b_stage_u + (uint32_t)((k * 32) >> 4));
+                  umma_bf16(d_base, da, db, idesc, (kh | k) != 0 ? 1u : (uint32_t)chunk);
+                }
+              }
+            } else
 #pragma unroll
             for (int tap = 0; tap < TAPS; ++tap) {
               const uint32_t a_lo = a_lo0 + (TAPS == 9 ? (uint32_t)(tap / 3) * wp_u + (uint32_t)(tap % 3) * (kSpan >> 4) : 0u);
@@ -512,10 +545,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // residual of batch (tile, b0) -> staging buffer sb
         auto load_res = [&](long long t, int b0, uint32_t sb) {
           const int nti_ = (int)(t % n_ntiles);
-          const int q0 = p.q_lo + (int)(mtile(t) * (128 * MB));
+          const int q0 = p.q_lo + (int)(mtile(t) * p.tile_rows);
           const int cnt = PT - b0 < bp ? PT - b0 : bp;
           uint64_t* bar = &ctl->res_full[group * 2 + sb];
-          mbar_expect_tx(bar, (uint32_t)cnt * 128u * pitch);
+          mbar_expect_tx(bar, (uint32_t)cnt * (uint32_t)kPanelRows * pitch);
           const long long mt_ = mtile(t);
           for (int i = 0; i < cnt; ++i) {
             const int idx = b0 + i, m = idx / npanels, pn = idx - m * npanels;
@@ -533,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll 1
         for (long long tile = first_tile; tile < total_tiles; tile += tile_step) {
           const int nti = (int)(tile % n_ntiles);
-          const int q0 = p.q_lo + (int)(mtile(tile) * (128 * MB));
+          const int q0 = p.q_lo + (int)(mtile(tile) * p.tile_rows);
 #pragma unroll 1
           for (int b0 = 0; b0 < PT; b0 += bp, ++kb) {
             const uint32_t sb = kb & 1;
@@ -592,7 +625,146 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int row0 = quarter * 32 + lane;
     uint32_t acc_it = 0;
     DBG_TICK();
-    if constexpr (kStagedEpi) {
+    if constexpr (KWM) {
+      // ---- kw-merged staged epilogue (one 126-row panel per tile, one tile per batch).  The tensor pipe needs only
+      // ~1000 cycles per tile here, so this loop is written for instruction count: no generic tile / panel index math,
+      // packed fp32x2 adds, the zero-cell test once per tile.
+      const int spp = nt >> 4;                              // 16-channel slices of the panel (panel_ch == nt)
+      const uint32_t pitch = (uint32_t)nt * 2u, swz = (uint32_t)p.panel_swz;
+      const uint32_t panel_bytes = p.epi_panel_bytes;
+      const uint32_t stage0 = a_base + p.epi_base_off + (uint32_t)group * 2u * panel_bytes;
+      const int prow = row0 - 2;                            // panel row = tile-local output pixel (rows 0, 1: none)
+      const uint32_t xr = swz == 128 ? (uint32_t)(prow & 7) : (swz == 64 ? (uint32_t)((prow >> 1) & 3) : 0u);
+      const uint32_t row_off = (uint32_t)prow * pitch;
+      // exchange area [group][sub][parity][quarter][3 rows x 16 fp32]: rows = group 0 of lanes 30, 31, group 1 of lane 31
+      const uint32_t xch = a_base + p.xch_off + (uint32_t)((group * 2 + sub) * 2) * (4u * 192u) + (uint32_t)quarter * 192u;
+      const uint32_t bar_id = 1u + (uint32_t)(group * 2 + sub);
+      const bool x_rd = quarter > 0 && lane < 2;
+      const int Wp = p.Wp, Hp = p.Hp;
+      const FastDiv fdW = p.fd_Wp, fdH = p.fd_Hp;
+      const int ntiles = (int)total_tiles, tstep = 2 * (int)tstride;
+      int q = p.q_lo + ((int)tile0 + group * (int)tstride) * 126 + prow;   // this thread's output pixel
+      const int qstep = tstep * 126;
+      uint32_t kb = 0, xk = 0;
+      acc_it = (uint32_t)group;
+#pragma unroll 1
+      for (int tile = (int)tile0 + group * (int)tstride; tile < ntiles; tile += tstep, acc_it += 2, ++kb, q += qstep) {
+        const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+        const uint32_t t_tile = tmem_base + buf * acc_cols + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t sbuf = kb & 1u;
+        const uint32_t base = stage0 + sbuf * panel_bytes + row_off;
+        bool is_pad = false;
+        if (prow >= 0) {
+          const uint32_t t = fdW.div((uint32_t)q);
+          const int w = q - (int)t * Wp;
+          const int h = (int)t - (int)fdH.div(t) * Hp;
+          is_pad = (w == e.W) || (h == e.H);
+        }
+        DBG_TOCK(1);
+        mbar_wait(&ctl->acc_full[buf], aph);
+        DBG_TOCK(0);
+        tc_fence_after();
+        bool ready = false;
+#pragma unroll 1
+        for (int sl = sub; sl < spp; sl += 2) {
+          uint32_t v0[16], v1[16], v[16];
+          tmem_ld16(t_tile + (uint32_t)(sl * 16), v0);
+          tmem_ld16(t_tile + (uint32_t)(nt + sl * 16), v1);
+          tmem_ld16(t_tile + (uint32_t)(2 * nt + sl * 16), v);
+          const uint32_t c0 = (uint32_t)sl * 2u;
+          const uint32_t ad0 = base + ((c0 ^ xr) << 4), ad1 = base + (((c0 + 1) ^ xr) << 4);
+          float4 bias[4];
+          const float4* b4 = reinterpret_cast<const float4*>(sbias + sl * 16);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) bias[g] = b4[g];
+          if (!ready) {
+            if (has_res) mbar_wait(&ctl->res_full[group * 2 + sbuf], (kb >> 1) & 1);
+            else mbar_wait(&ctl->epi_free[group * 2 + sbuf], ((kb >> 1) & 1) ^ 1);
+            ready = true;
+            DBG_TOCK(3);
+          }
+          uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+          if (has_res && prow >= 0) { r0 = lds128(ad0); r1 = lds128(ad1); }
+          tmem_ld_wait();
+          // out[row - 2] = D0[row - 2] + D1[row - 1] + D2[row]: the rows below this warp's 32 lanes come from the
+          // neighbouring quarter's warp (same group, same slice sequence) through the exchange area
+          const uint32_t xq = xch + (xk & 1u) * (4u * 192u);
+          ++xk;
+          if (lane >= 30) {
+            const uint32_t a = xq + (uint32_t)(lane - 30) * 64u;
+            sts128(a, make_uint4(v0[0], v0[1], v0[2], v0[3]));
+            sts128(a + 16, make_uint4(v0[4], v0[5], v0[6], v0[7]));
+            sts128(a + 32, make_uint4(v0[8], v0[9], v0[10], v0[11]));
+            sts128(a + 48, make_uint4(v0[12], v0[13], v0[14], v0[15]));
+            if (lane == 31) {
+              sts128(a + 64, make_uint4(v1[0], v1[1], v1[2], v1[3]));
+              sts128(a + 80, make_uint4(v1[4], v1[5], v1[6], v1[7]));
+              sts128(a + 96, make_uint4(v1[8], v1[9], v1[10], v1[11]));
+              sts128(a + 112, make_uint4(v1[12], v1[13], v1[14], v1[15]));
+            }
+          }
+          named_bar_sync(bar_id, 128u);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v0[i] = __shfl_up_sync(0xFFFFFFFFu, v0[i], 2);
+            v1[i] = __shfl_up_sync(0xFFFFFFFFu, v1[i], 1);
+          }
+          if (x_rd) {
+            const uint32_t a = xq - 192u + (uint32_t)lane * 64u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 t = lds128(a + 16u * g);
+              v0[g * 4 + 0] = t.x; v0[g * 4 + 1] = t.y; v0[g * 4 + 2] = t.z; v0[g * 4 + 3] = t.w;
+            }
+            if (lane == 0) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 t = lds128(xq - 192u + 128u + 16u * g);
+                v1[g * 4 + 0] = t.x; v1[g * 4 + 1] = t.y; v1[g * 4 + 2] = t.z; v1[g * 4 + 3] = t.w;
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            fadd2(v0[i], v0[i + 1], v1[i], v1[i + 1]);
+            fadd2(v[i], v[i + 1], v0[i], v0[i + 1]);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            fadd2(v[g * 4 + 0], v[g * 4 + 1], __float_as_uint(bias[g].x), __float_as_uint(bias[g].y));
+            fadd2(v[g * 4 + 2], v[g * 4 + 3], __float_as_uint(bias[g].z), __float_as_uint(bias[g].w));
+          }
+          fadd2(v[0], v[1], r0.x << 16, r0.x & 0xFFFF0000u);   fadd2(v[2], v[3], r0.y << 16, r0.y & 0xFFFF0000u);
+          fadd2(v[4], v[5], r0.z << 16, r0.z & 0xFFFF0000u);   fadd2(v[6], v[7], r0.w << 16, r0.w & 0xFFFF0000u);
+          fadd2(v[8], v[9], r1.x << 16, r1.x & 0xFFFF0000u);   fadd2(v[10], v[11], r1.y << 16, r1.y & 0xFFFF0000u);
+          fadd2(v[12], v[13], r1.z << 16, r1.z & 0xFFFF0000u); fadd2(v[14], v[15], r1.w << 16, r1.w & 0xFFFF0000u);
+          const float* f = reinterpret_cast<const float*>(v);
+          uint4 o0, o1;
+          if (e.relu) {
+            o0 = make_uint4(pack_bf16_relu(f[0], f[1]), pack_bf16_relu(f[2], f[3]), pack_bf16_relu(f[4], f[5]),
+                            pack_bf16_relu(f[6], f[7]));
+            o1 = make_uint4(pack_bf16_relu(f[8], f[9]), pack_bf16_relu(f[10], f[11]), pack_bf16_relu(f[12], f[13]),
+                            pack_bf16_relu(f[14], f[15]));
+          } else {
+            o0 = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            o1 = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+          }
+          if (is_pad) { o0 = make_uint4(0, 0, 0, 0); o1 = o0; }  // zero cells of the padded layout stay zero
+          if (prow >= 0) {
+            sts128(ad0, o0);
+            sts128(ad1, o1);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
+        DBG_TOCK(1);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->epi_done[group * 2 + sbuf]);
+        DBG_TOCK(2);
+      }
+    } else if constexpr (kStagedEpi) {
       // ---- staged epilogue: batches of 128-row x panel_ch panels live in shared memory; the residual arrives by
       // TMA, each thread updates its own row cells in place, finished panels leave by TMA (issued by this group's
       // DMA warp).  Global memory only ever sees whole lines; no block-wide barrier is involved.
@@ -868,8 +1040,19 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   }
   if ((long long)gi.pixels() >= (1ll << 31) || p.P >= (1ll << 31)) { set_error("conv: tensor too large"); return 1; }
 
+  // kw-merged MMA shape (see kEpiStagedKW): stride-1 3x3 with one N tile, 3*nt accumulator columns x 2 buffers, the three
+  // tap tiles of a filter row contiguous in the resident weight block (no padding between stages), staged epilogue.
+  // Falls back (recursive call with kw_merge = -1) when the weights turn out not to stay resident.
+  // Measured on B200: the MMA stream gets 40 % shorter but the epilogue's row exchange makes the
+  // drain the bottleneck, 89 vs 83 us on the 64-channel layers - so it is off unless asked for (spec.kw_merge = 1 /
+  // stl_conv_desc.impl = 3 / STLPOSE_KW_MERGE=1).
+  const bool kwm_wanted = s.kw_merge == 1 || (s.kw_merge == 0 && getenv("STLPOSE_KW_MERGE") && atoi(getenv("STLPOSE_KW_MERGE")) == 1);
+  const bool kwm = kwm_wanted && p.mode == 0 && p.taps == 9 && !s.force_tap_reload && !s.force_mb && !s.out_nchw &&
+                   s.n_up == 0 && p.n_ntiles == 1 && 3 * p.nt <= 256 && (p.nt * span) % 1024 == 0 && s.img_hi == 0 &&
+                   !getenv("STL_DBG_NO_EPI_TMA") && !getenv("STL_DBG_NO_RESIDENT") && !getenv("STL_DBG_PAIR_ALL");
+  p.kwm = kwm ? 1 : 0;
   // accumulator blocks per tile: keep two accumulator buffers in 512 TMEM columns when possible
-  int mb = s.force_mb ? s.force_mb : (p.nt <= 64 ? 3 : 2);
+  int mb = s.force_mb ? s.force_mb : (kwm ? 1 : (p.nt <= 64 ? 3 : 2));
   if (mb > 3) mb = 3;
   while (mb > 1 && mb * p.nt > 256) --mb;
   if (p.mode == 0) {
@@ -880,11 +1063,12 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   if (p.mode == 0) {
     p.mb = mb;
     p.a_shift = (p.taps == 9 && !s.force_tap_reload) ? 1 : 0;
-    p.halo = p.a_shift ? p.in_Wp + 1 : 0;
+    p.halo = p.a_shift ? p.in_Wp + (kwm ? 0 : 1) : 0;   // kw-merged: the A operand only shifts by whole image rows
+    p.tile_rows = kwm ? 126 : 128 * mb;
     const int rows_needed = 128 * mb + 2 * p.halo;
     p.a_pieces = (rows_needed + 255) / 256;
     p.a_box_rows = (((rows_needed + p.a_pieces - 1) / p.a_pieces) + 7) & ~7;
-    p.total_tiles = ((p.P - p.q_lo + 128 * mb - 1) / (128 * mb)) * p.n_ntiles;
+    p.total_tiles = ((p.P - p.q_lo + p.tile_rows - 1) / p.tile_rows) * p.n_ntiles;
     cuuint64_t dims[2] = {(cuuint64_t)gi.C, (cuuint64_t)gi.pixels()};
     cuuint64_t strides[1] = {(cuuint64_t)gi.C * 2};
     cuuint32_t box[2] = {(cuuint32_t)p.ck, (cuuint32_t)p.a_box_rows};
@@ -931,8 +1115,9 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   // Four buffers (STL_DBG_ACC4) were measured on B200 and change nothing: the narrow layers are not limited by the
   // TMEM hand-off but by operand fetch and HBM.
   p.n_accbuf = (4 * p.mb * p.nt <= 512 && getenv("STL_DBG_ACC4")) ? 4 : ((2 * p.mb * p.nt <= 512) ? 2 : 1);
+  if (kwm) p.n_accbuf = 2;   // 2 x 3*nt <= 512 columns by construction
   uint32_t cols = 32;
-  while (cols < (uint32_t)(p.n_accbuf * p.mb * p.nt)) cols <<= 1;
+  while (cols < (uint32_t)(p.n_accbuf * (kwm ? 3 : p.mb) * p.nt)) cols <<= 1;
   p.tmem_cols = cols;
 
   // weights stay resident in shared memory when every tile of the layer fits next to >= 2 activation stages;
@@ -952,13 +1137,14 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     while (p.epi_batch > 1 && p.epi_batch * ((spp + 1) / 2) > 3) --p.epi_batch;
     if ((spp + 1) / 2 > 3) p.epi_tma = 0;
   }
-  const size_t epi_bytes = p.epi_tma ? (size_t)2 * 2 * p.epi_batch * p.epi_panel_bytes : 0;
+  const size_t xch_bytes = kwm ? 2 * 2 * 2 * 4 * 192 : 0;   // [group][sub][parity][quarter][3 rows x 16 fp32]
+  const size_t epi_bytes = (p.epi_tma ? (size_t)2 * 2 * p.epi_batch * p.epi_panel_bytes : 0) + xch_bytes;
   const size_t budget = kMaxSmem - kCtlBytes - 1024 - epi_bytes;
   // CTA pairs (cta_group::2): flat mode, staged epilogue, burst-capable; each CTA then keeps half of the weight rows
   // Measured on B200: for layers whose weights stay resident (N <= 64, every 1x1) pairs are slower - the MMA rate is
   // bound by the A-operand fetch (128 rows x 32 B per SM per instruction), which pairing does not reduce.  For
   // layers that stream their weights (C >= 128) each CTA of a pair streams only half of the rows: half the L2 traffic.
-  const bool pair_ok = p.mode == 0 && p.epi_tma && p.nt % 32 == 0 && !getenv("STL_DBG_NO_PAIR");
+  const bool pair_ok = p.mode == 0 && p.epi_tma && p.nt % 32 == 0 && !kwm && !getenv("STL_DBG_NO_PAIR");
   size_t resident = 0;
   p.pair = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
@@ -1011,10 +1197,16 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   if (const char* e = getenv("STL_DBG_A_STAGES")) { int v = atoi(e); if (v >= 1 && v <= a_st) a_st = v; }
   p.a_stages = a_st;
   p.b_stages = b_st;
+  if (kwm && !(p.b_resident && p.epi_tma && !p.pair)) {   // the merged shape needs the whole weight block in place
+    ConvSpec s2 = s;
+    s2.kw_merge = -1;
+    return conv_prepare(s2, pp, grid, smem_bytes);
+  }
   // measured on B200: a second issuer pays off only for N <= 32 (16-cycle MMAs); at N = 64 the two streams interfere
   p.n_mma = (p.b_resident && (p.a_shift || p.taps == 1) && p.mb >= 2 && p.nt <= 32 && !getenv("STL_DBG_SINGLE_MMA")) ? 2 : 1;
   *smem_bytes = kCtlBytes + 1024 + (size_t)a_st * p.a_stage_bytes + p.b_bytes_total + epi_bytes;
   p.epi_base_off = (uint32_t)((size_t)a_st * p.a_stage_bytes + p.b_bytes_total);
+  p.xch_off = p.epi_base_off + (uint32_t)(epi_bytes - xch_bytes);
   if (p.epi_tma && p.mode == 1) {
     // valid pixels only (W x H, not Wp x Hp): TMA clips partial tiles and never touches the zero cells
     cuuint64_t dims[4] = {(cuuint64_t)s.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
@@ -1026,7 +1218,7 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   } else if (p.epi_tma) {
     cuuint64_t dims[2] = {(cuuint64_t)s.cout, (cuuint64_t)p.P};
     cuuint64_t strides[1] = {(cuuint64_t)s.cout * 2};
-    cuuint32_t box[2] = {(cuuint32_t)p.panel_ch, 128};
+    cuuint32_t box[2] = {(cuuint32_t)p.panel_ch, (cuuint32_t)(kwm ? 126 : 128)};
     cuuint32_t es[2] = {1, 1};
     if (encode(&p.tmO, s.out, 2, dims, strides, box, es, (uint32_t)p.panel_swz)) return 1;
     if (s.residual && encode(&p.tmR, s.residual, 2, dims, strides, box, es, (uint32_t)p.panel_swz)) return 1;
@@ -1079,6 +1271,10 @@ template <int MB, int KSTEPS>
 ConvKernel pick_variant(int taps, int epi, bool pair) {
   if (epi == kEpiNchw) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiNchw, false> : nullptr;
   if (epi == kEpiStagedS2) return taps == 9 ? conv_tc_kernel<MB, KSTEPS, 9, kEpiStagedS2, false> : nullptr;
+  if (epi == kEpiStagedKW) {
+    if constexpr (MB == 1) return taps == 9 ? conv_tc_kernel<1, KSTEPS, 9, kEpiStagedKW, false> : nullptr;
+    return nullptr;
+  }
   if (epi == kEpiStaged) {
     if (pair) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiStaged, true> : conv_tc_kernel<MB, KSTEPS, 9, kEpiStaged, true>;
     return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiStaged, false> : conv_tc_kernel<MB, KSTEPS, 9, kEpiStaged, false>;
@@ -1103,7 +1299,7 @@ ConvKernel pick_kernel(int mb, int ksteps, int taps, int epi, bool pair) {
   return nullptr;
 }
 int epi_kind(const ConvParams& p) {
-  return p.out_nchw ? kEpiNchw : (p.epi_tma ? (p.mode == 1 ? kEpiStagedS2 : kEpiStaged) : kEpiDirect);
+  return p.out_nchw ? kEpiNchw : (p.epi_tma ? (p.mode == 1 ? kEpiStagedS2 : (p.kwm ? kEpiStagedKW : kEpiStaged)) : kEpiDirect);
 }
 }  // namespace
 
@@ -1112,7 +1308,7 @@ int conv_launch_prepared(const ConvParams& p, int grid, size_t smem_bytes, cudaS
   if (!attr_set) {
     for (int mb = 1; mb <= 3; ++mb)
       for (int ks = 1; ks <= 4; ks *= 2)
-        for (int epi = 0; epi < 4; ++epi)
+        for (int epi = 0; epi < 5; ++epi)
           for (int taps = 1; taps <= 9; taps += 8)
             for (int pair = 0; pair < 2; ++pair) {
               if (pair && epi != kEpiStaged) continue;
@@ -1130,7 +1326,7 @@ int conv_launch_prepared(const ConvParams& p, int grid, size_t smem_bytes, cudaS
   if (p.pair || p.pdl) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(p.kwm ? kThreadsKW : kThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -1152,7 +1348,7 @@ int conv_launch_prepared(const ConvParams& p, int grid, size_t smem_bytes, cudaS
     e = cudaLaunchKernelEx(&cfg, kern, p);
     if (e != cudaSuccess) { set_error("conv_tc_kernel (attributed) launch: %s", cudaGetErrorString(e)); return 1; }
   } else {
-    kern<<<grid, kThreads, smem_bytes, stream>>>(p);
+    kern<<<grid, p.kwm ? kThreadsKW : kThreads, smem_bytes, stream>>>(p);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("conv_tc_kernel launch: %s", cudaGetErrorString(e)); return 1; }

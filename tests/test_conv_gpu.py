@@ -53,3 +53,21 @@ def test_conv_tile_sizes_and_persistence(mb):
     # few CTAs -> every CTA walks many tiles: exercises ring wrap-around and accumulator double buffering
     err, scale = conv_case(N=6, cin=64, cout=64, H=32, W=24, k=3, stride=1, with_res=True, force_mb=mb, max_ctas=3)
     assert err <= 1e-2 * max(scale, 1.0)
+
+
+KW_MERGED = [
+    # layers the kw-merged MMA shape (impl 3: N = 3 x Cout, row-shifted sum in the epilogue) covers; many tiles per CTA
+    # exercise the cross-warp row exchange, accumulator double buffering and the 126-row panels at tensor / image borders
+    dict(N=3, cin=64, cout=64, H=32, W=24, k=3, stride=1, with_res=True),
+    dict(N=2, cin=64, cout=64, H=64, W=48, k=3, stride=1),
+    dict(N=2, cin=32, cout=32, H=64, W=48, k=3, stride=1, with_res=True),
+    dict(N=7, cin=64, cout=64, H=32, W=24, k=3, stride=1, with_res=True, max_ctas=3),
+    dict(N=1, cin=64, cout=64, H=8, W=6, k=3, stride=1, relu=False),
+    dict(N=5, cin=128, cout=128, H=16, W=12, k=3, stride=1, with_res=True),   # not covered: must fall back to impl 0
+]
+
+
+@pytest.mark.parametrize("case", KW_MERGED, ids=lambda c: "c{cin}-{cout}_{H}x{W}_N{N}".format(**c))
+def test_kw_merged_conv_matches_torch(case):
+    err, scale = conv_case(impl=3, **case)
+    assert err <= 1e-2 * max(scale, 1.0), f"max err {err} vs ref max {scale}"
