@@ -178,6 +178,8 @@ struct FuseArgs {
   FastDiv fd_c8, fd_wp, fd_hp;   // multiply-shift division of the flat item index (items < 2^31)
 };
 
+// NUP = number of upsampled addends (compile time: their gathers are all issued before the first one is consumed)
+template <int NUP>
 __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseArgs a) {
   // flat walk over (padded pixel, 8-channel group) items, 4 independent items per thread per iteration so that
   // four 16-byte loads are in flight before the first one is consumed
@@ -206,10 +208,16 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseArgs a) {
       if (h < a.H && w < a.W) {
         float f[8] = {bf16_lo(u[k].x), bf16_hi(u[k].x), bf16_lo(u[k].y), bf16_hi(u[k].y),
                       bf16_lo(u[k].z), bf16_hi(u[k].z), bf16_lo(u[k].w), bf16_hi(u[k].w)};
-        for (int j = 0; j < a.n_up; ++j) {
+        uint4 zz[NUP];
+#pragma unroll
+        for (int j = 0; j < NUP; ++j) {
           const int s = a.shift[j];
           const size_t qs = ((size_t)n * ((a.H >> s) + 1) + (h >> s)) * ((a.W >> s) + 1) + (w >> s);
-          const uint4 z = __ldg(reinterpret_cast<const uint4*>(a.z[j] + qs * a.C + c8 * 8));
+          zz[j] = __ldg(reinterpret_cast<const uint4*>(a.z[j] + qs * a.C + c8 * 8));
+        }
+#pragma unroll
+        for (int j = 0; j < NUP; ++j) {
+          const uint4 z = zz[j];
           f[0] += bf16_lo(z.x); f[1] += bf16_hi(z.x); f[2] += bf16_lo(z.y); f[3] += bf16_hi(z.y);
           f[4] += bf16_lo(z.z); f[5] += bf16_hi(z.z); f[6] += bf16_lo(z.w); f[7] += bf16_hi(z.w);
         }
@@ -341,7 +349,12 @@ int fuse_sum(const __nv_bfloat16* x, const __nv_bfloat16* const* z, const int* s
   a.fd_hp.init((uint32_t)(H + 1));
   long long blocks = (total + 4 * 256 - 1) / (4 * 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  fuse_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  switch (n_up) {
+    case 1: fuse_sum_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+    case 2: fuse_sum_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+    case 3: fuse_sum_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+    default: set_error("fuse_sum: %d upsampled addends (1..3 supported)", n_up); return 1;
+  }
   return check("fuse_sum");
 }
 
