@@ -134,6 +134,21 @@ int stl_basic_block(const void* x, void* y, const void* w1_packed, const float* 
 int stl_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, int Rows_pad, int K_pad, void* w_packed,
                                 float* bias_packed, void* stream);
 
+/* All raw (no BatchNorm folding) weight repacks of a training step in ONE launch: the forward layout of
+ * stl_pack_conv_weights (dgrad = 0: [k*k][rows_pad >= Cout][cols_pad >= Cin]) and the input-gradient layout of
+ * stl_pack_conv_weights_dgrad (dgrad = 1: [k*k][rows_pad >= Cin][cols_pad >= Cout], taps reversed).  items_dev: n_items
+ * descriptors in DEVICE memory; block_offsets_dev: n_items + 1 ints (device), item i owns thread blocks
+ * [block_offsets[i], block_offsets[i+1]) of 256 threads x 4 elements; total_blocks = block_offsets[n_items]. */
+typedef struct stl_pack_item {
+  const float* w;        /* fp32 OIHW master weights */
+  void* w_packed;        /* bf16 destination */
+  int Cout, Cin, ksize;
+  int rows_pad, cols_pad;
+  int dgrad;
+} stl_pack_item;
+int stl_pack_conv_weights_batched(const stl_pack_item* items_dev, const int* block_offsets_dev, int n_items,
+                                  int total_blocks, void* stream);
+
 typedef struct stl_conv_desc {
   const void* in;          /* padded-linear bf16 [N][H+1][W+1][Cin] */
   int N, H, W, Cin;        /* input geometry */
@@ -245,6 +260,17 @@ int stl_bn_train_forward(const void* z, const float* gamma, const float* beta, c
 int stl_bn_train_backward(const void* dy, const void* y, const void* z, const float* mean, const float* rstd,
                           const float* gamma, int relu, int N, int H, int W, int C, void* dz, void* dres, float* sums,
                           void* stream);
+
+/* The same two calls for a step that is captured once and replayed (TrainStep): no memset node per call and no copy of the
+ * parameter gradients.  `ticket` is a caller-owned device word that is ZERO on entry and is left zero; launches that may
+ * run concurrently must not share one (one per BatchNorm layer and direction).  backward: the channel sums go to
+ * dbeta_dgamma ([2C], a tensor of their own: dbeta | dgamma); workspace holds stl_bn_workspace_floats(C) floats. */
+int stl_bn_train_forward_ticket(const void* z, const float* gamma, const float* beta, const void* residual, int relu,
+                                float eps, float momentum, int N, int H, int W, int C, void* y, float* sums, float* mean,
+                                float* rstd, float* running_mean, float* running_var, unsigned* ticket, void* stream);
+int stl_bn_train_backward_ticket(const void* dy, const void* y, const void* z, const float* mean, const float* rstd,
+                                 const float* gamma, int relu, int N, int H, int W, int C, void* dz, void* dres,
+                                 float* dbeta_dgamma, float* workspace, unsigned* ticket, void* stream);
 
 /* Fuse-layer row (HRnet.py:255-264): y = relu(sum same[i] + sum nearest_upsample(up[j], 2^shift[j])).
  * same_host / up_host: host arrays of device pointers (n_same <= 4, n_up <= 3). */

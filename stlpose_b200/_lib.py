@@ -87,9 +87,13 @@ PROTOTYPES = {
     "stl_plan_forward_timed": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_size_t, vp,
                                               c_float_p]),
     "stl_plan_op_info": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(OpInfo)]),
+    "stl_pack_conv_weights_batched": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp]),
     "stl_bn_train_forward": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_float, ctypes.c_float] +
                              [ctypes.c_int] * 4 + [vp] * 7),
     "stl_bn_train_backward": (ctypes.c_int, [vp] * 6 + [ctypes.c_int] * 5 + [vp] * 4),
+    "stl_bn_train_forward_ticket": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_float, ctypes.c_float] +
+                                    [ctypes.c_int] * 4 + [vp] * 8),
+    "stl_bn_train_backward_ticket": (ctypes.c_int, [vp] * 6 + [ctypes.c_int] * 5 + [vp] * 6),
     "stl_sum_relu_forward": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, ctypes.POINTER(vp), c_int_p, ctypes.c_int,
                                             vp] + [ctypes.c_int] * 4 + [vp]),
     "stl_relu_mask": (ctypes.c_int, [vp, vp, vp, ctypes.c_longlong, vp]),

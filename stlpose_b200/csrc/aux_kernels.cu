@@ -230,6 +230,34 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseArgs a) {
   }
 }
 
+// Every raw weight repack of a training step in one launch (a step re-packs 293 forward + 292 dgrad layouts; as separate
+// launches they are 585 graph nodes of a few microseconds each).  Block -> item by binary search over the block offsets.
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackItem* __restrict__ items,
+                                                                   const int* __restrict__ block_offsets, int n_items) {
+  int lo = 0, hi = n_items - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (block_offsets[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackItem it = items[lo];
+  const int taps = it.k * it.k;
+  const int total = taps * it.rows_pad * it.cols_pad;
+  const int base = ((int)blockIdx.x - block_offsets[lo]) * 1024;
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(it.wp);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = base + j * 256 + (int)threadIdx.x;
+    if (i >= total) break;
+    const int col = i % it.cols_pad;
+    const int row = (i / it.cols_pad) % it.rows_pad;
+    const int t = i / (it.cols_pad * it.rows_pad);
+    const int co = it.dgrad ? col : row, ci = it.dgrad ? row : col;
+    float v = 0.f;
+    if (co < it.Cout && ci < it.Cin) v = it.w[((size_t)co * it.Cin + ci) * taps + (it.dgrad ? taps - 1 - t : t)];
+    wp[i] = __float2bfloat16(v);
+  }
+}
+
 // ------------------------------------------------------------------ CUDA-core reference convolution
 struct NaiveArgs {
   const __nv_bfloat16* in;
@@ -323,6 +351,12 @@ int pack_weights_dgrad(const float* w, int Cout, int Cin, int k, int Rows_pad, i
   const long long total = (long long)k * k * Rows_pad * K_pad;
   pack_weights_dgrad_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, Cout, Cin, k, Rows_pad, K_pad, wp, bias_out);
   return check("pack_weights_dgrad");
+}
+
+int pack_weights_batched(const PackItem* items, const int* block_offsets, int n_items, int total_blocks, cudaStream_t st) {
+  if (n_items <= 0 || total_blocks <= 0) return 0;
+  pack_weights_batched_kernel<<<total_blocks, 256, 0, st>>>(items, block_offsets, n_items);
+  return check("pack_weights_batched");
 }
 
 int stem_pack_input(const float* x, __nv_bfloat16* y, int n_total, int n_plain, int H, int W, cudaStream_t st) {

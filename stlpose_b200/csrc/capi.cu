@@ -170,6 +170,15 @@ int stl_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, in
                             bias_packed, (cudaStream_t)stream);
 }
 
+int stl_pack_conv_weights_batched(const stl_pack_item* items_dev, const int* block_offsets_dev, int n_items,
+                                  int total_blocks, void* stream) {
+  if (!have_device()) return 1;
+  if (n_items > 0 && (!items_dev || !block_offsets_dev)) { set_error("stl_pack_conv_weights_batched: null pointer"); return 1; }
+  static_assert(sizeof(stl_pack_item) == sizeof(PackItem), "stl_pack_item and PackItem must have the same layout");
+  return pack_weights_batched(reinterpret_cast<const PackItem*>(items_dev), block_offsets_dev, n_items, total_blocks,
+                              (cudaStream_t)stream);
+}
+
 int stl_conv2d(const stl_conv_desc* d, void* stream) {
   if (!have_device()) return 1;
   if (!d || !d->in || !d->out || !d->w_packed || !d->bias_packed) { set_error("stl_conv2d: null pointer"); return 1; }
@@ -282,7 +291,20 @@ int stl_bn_train_forward(const void* z, const float* gamma, const float* beta, c
   if (!z || !gamma || !beta || !y || !sums || !mean || !rstd) { set_error("stl_bn_train_forward: null pointer"); return 1; }
   typedef const __nv_bfloat16* P;
   return bn_train_forward((P)z, gamma, beta, (P)residual, relu, eps, momentum, N, H, W, C, (__nv_bfloat16*)y, sums, mean,
-                          rstd, running_mean, running_var, (cudaStream_t)stream);
+                          rstd, running_mean, running_var, nullptr, (cudaStream_t)stream);
+}
+
+int stl_bn_train_forward_ticket(const void* z, const float* gamma, const float* beta, const void* residual, int relu,
+                                float eps, float momentum, int N, int H, int W, int C, void* y, float* sums, float* mean,
+                                float* rstd, float* running_mean, float* running_var, unsigned* ticket, void* stream) {
+  if (!have_device()) return 1;
+  if (!z || !gamma || !beta || !y || !sums || !mean || !rstd || !ticket) {
+    set_error("stl_bn_train_forward_ticket: null pointer");
+    return 1;
+  }
+  typedef const __nv_bfloat16* P;
+  return bn_train_forward((P)z, gamma, beta, (P)residual, relu, eps, momentum, N, H, W, C, (__nv_bfloat16*)y, sums, mean,
+                          rstd, running_mean, running_var, ticket, (cudaStream_t)stream);
 }
 
 int stl_bn_train_backward(const void* dy, const void* y, const void* z, const float* mean, const float* rstd,
@@ -295,7 +317,20 @@ int stl_bn_train_backward(const void* dy, const void* y, const void* z, const fl
   }
   typedef const __nv_bfloat16* P;
   return bn_train_backward((P)dy, (P)y, (P)z, mean, rstd, gamma, relu, N, H, W, C, (__nv_bfloat16*)dz,
-                           (__nv_bfloat16*)dres, sums, (cudaStream_t)stream);
+                           (__nv_bfloat16*)dres, sums, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int stl_bn_train_backward_ticket(const void* dy, const void* y, const void* z, const float* mean, const float* rstd,
+                                 const float* gamma, int relu, int N, int H, int W, int C, void* dz, void* dres,
+                                 float* dbeta_dgamma, float* workspace, unsigned* ticket, void* stream) {
+  if (!have_device()) return 1;
+  if (!dy || !z || !mean || !rstd || !gamma || !dz || !dbeta_dgamma || !workspace || !ticket || (relu && !y)) {
+    set_error("stl_bn_train_backward_ticket: null pointer");
+    return 1;
+  }
+  typedef const __nv_bfloat16* P;
+  return bn_train_backward((P)dy, (P)y, (P)z, mean, rstd, gamma, relu, N, H, W, C, (__nv_bfloat16*)dz,
+                           (__nv_bfloat16*)dres, dbeta_dgamma, workspace, ticket, (cudaStream_t)stream);
 }
 
 int stl_sum_relu_forward(const void* const* same_host, int n_same, const void* const* up_host, const int* shift_host,

@@ -532,11 +532,13 @@ size_t bn_workspace_floats(int C) { return (size_t)2 * C * (1 + kReduceBlocks) +
 
 int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* beta, const __nv_bfloat16* residual,
                      int relu, float eps, float momentum, int N, int H, int W, int C, __nv_bfloat16* y, float* sums,
-                     float* mean, float* rstd, float* run_mean, float* run_var, cudaStream_t st) {
+                     float* mean, float* rstd, float* run_mean, float* run_var, unsigned* ticket, cudaStream_t st) {
   if (C % 8 || C > 2048) { set_error("bn_train_forward: C=%d unsupported", C); return 1; }
   const long long pixels = (long long)N * (H + 1) * (W + 1);
-  unsigned* counter = reinterpret_cast<unsigned*>(sums + (size_t)2 * C * (1 + kReduceBlocks));
-  cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+  // the last-block ticket: a caller-owned word that is zero between launches (the kernel resets it), or the tail of the
+  // workspace cleared here
+  unsigned* counter = ticket ? ticket : reinterpret_cast<unsigned*>(sums + (size_t)2 * C * (1 + kReduceBlocks));
+  if (!ticket) cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   const int lanes = 256 / (C / 8);
   BnFinalize fin{(float)((long long)N * H * W), eps, momentum, mean, rstd, run_mean, run_var};
   channel_reduce_kernel<0><<<grid_for(pixels, lanes * 16, kReduceBlocks), 256, 0, st>>>(
@@ -553,14 +555,17 @@ int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* be
 
 int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* z, const float* mean,
                       const float* rstd, const float* gamma, int relu, int N, int H, int W, int C,
-                      __nv_bfloat16* dz, __nv_bfloat16* dres, float* sums, cudaStream_t st) {
+                      __nv_bfloat16* dz, __nv_bfloat16* dres, float* sums, float* partial, unsigned* ticket,
+                      cudaStream_t st) {
   if (C % 8 || C > 2048) { set_error("bn_train_backward: C=%d unsupported", C); return 1; }
   const long long pixels = (long long)N * (H + 1) * (W + 1);
-  unsigned* counter = reinterpret_cast<unsigned*>(sums + (size_t)2 * C * (1 + kReduceBlocks));
-  cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+  // partial == null: one workspace [sums 2C | partial rows | ticket]; else `sums` ([2C], dbeta | dgamma) is a tensor of its own
+  if (!partial) partial = sums + 2 * C;
+  unsigned* counter = ticket ? ticket : reinterpret_cast<unsigned*>(partial + (size_t)2 * C * kReduceBlocks);
+  if (!ticket) cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   const int lanes = 256 / (C / 8);
   channel_reduce_kernel<1><<<grid_for(pixels, lanes * 16, kReduceBlocks), 256, 0, st>>>(
-      dy, y, z, mean, rstd, pixels, C, relu, sums, sums + 2 * C, counter, BnFinalize{});
+      dy, y, z, mean, rstd, pixels, C, relu, sums, partial, counter, BnFinalize{});
   if (check("bn backward reduce")) return 1;
   PixIdx px;
   px.init(C, H, W);

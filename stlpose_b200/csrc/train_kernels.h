@@ -8,10 +8,11 @@ namespace stl {
 size_t bn_workspace_floats(int C);
 int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* beta, const __nv_bfloat16* residual,
                      int relu, float eps, float momentum, int N, int H, int W, int C, __nv_bfloat16* y, float* sums,
-                     float* mean, float* rstd, float* run_mean, float* run_var, cudaStream_t st);
+                     float* mean, float* rstd, float* run_mean, float* run_var, unsigned* ticket, cudaStream_t st);
 int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* z, const float* mean,
                       const float* rstd, const float* gamma, int relu, int N, int H, int W, int C,
-                      __nv_bfloat16* dz, __nv_bfloat16* dres, float* sums, cudaStream_t st);
+                      __nv_bfloat16* dz, __nv_bfloat16* dres, float* sums, float* partial, unsigned* ticket,
+                      cudaStream_t st);
 int sum_relu_forward(const __nv_bfloat16* const* same, int n_same, const __nv_bfloat16* const* up, const int* shift,
                      int n_up, __nv_bfloat16* y, int N, int H, int W, int C, cudaStream_t st);
 int relu_mask(const __nv_bfloat16* dy, const __nv_bfloat16* y, __nv_bfloat16* g, long long elems, cudaStream_t st);

@@ -41,11 +41,76 @@ def _zero_bias(n, device):
     return _ZERO_BIAS[key]
 
 
+# Weights packed ahead of time by one batched launch per step (see _Prepack): (data_ptr, cols_pad, dgrad) ->
+# (packed view, rows_pad, weight version at pack time, weakref to the weight).
+_PREPACKED = {}
+
+
+def _prepacked(w, cols_pad, dgrad):
+    hit = _PREPACKED.get((w.data_ptr(), cols_pad, dgrad))
+    if hit is not None and hit[2] == w._version and hit[3]() is w:
+        return hit[0], hit[1]
+    return None
+
+
+class _Prepack:
+    """All forward / input-gradient weight layouts of a model's BatchNorm-followed convolutions, re-packed from the fp32
+    masters by ONE launch at the start of every training forward (stl_pack_conv_weights_batched) instead of one launch
+    per layer and direction (585 per step).  Entries are only used while the weight's version counter is unchanged."""
+
+    def __init__(self, model, device):
+        import weakref
+        import numpy as np
+        convs = [m for m in model.modules() if isinstance(m, torch.nn.Conv2d) and m is not model.final_layer]
+        self.weights = [c.weight for c in convs]
+        self.ptrs = tuple(w.data_ptr() for w in self.weights)
+        self.device = device
+        specs, off = [], 0
+        for w in self.weights:
+            cout, cin, k, _ = w.shape
+            cin_pad, cout_pad = (cin + 15) // 16 * 16, (cout + 15) // 16 * 16
+            layouts = [(0, cout_pad, cin_pad)]
+            if cin == cin_pad:
+                layouts.append((1, cin_pad, cout_pad))       # stride-1 dgrad as a convolution (conv_dgrad)
+            for dgrad, rows, cols in layouts:
+                nbytes = k * k * rows * cols * 2
+                specs.append((w, dgrad, rows, cols, off, nbytes))
+                off += (nbytes + 255) // 256 * 256
+        self.arena = torch.empty(off, dtype=torch.uint8, device=device)
+        item = np.dtype([("w", "<u8"), ("wp", "<u8"), ("Cout", "<i4"), ("Cin", "<i4"), ("k", "<i4"), ("rows", "<i4"),
+                         ("cols", "<i4"), ("dgrad", "<i4")])
+        items = np.zeros(len(specs), dtype=item)
+        offsets = np.zeros(len(specs) + 1, dtype=np.int32)
+        self.entries = []
+        for i, (w, dgrad, rows, cols, o, nbytes) in enumerate(specs):
+            cout, cin, k, _ = w.shape
+            items[i] = (w.data_ptr(), self.arena.data_ptr() + o, cout, cin, k, rows, cols, dgrad)
+            offsets[i + 1] = offsets[i] + (k * k * rows * cols + 1023) // 1024
+            self.entries.append(((w.data_ptr(), cols, dgrad), self.arena[o:o + nbytes], rows, weakref.ref(w)))
+        self.items = torch.from_numpy(items.view(np.uint8).copy()).to(device)
+        self.offsets = torch.from_numpy(offsets).to(device)
+        self.n, self.blocks = len(specs), int(offsets[-1])
+
+    def valid_for(self, device):
+        return self.device == device and self.ptrs == tuple(w.data_ptr() for w in self.weights) and \
+            all(w.dtype == torch.float32 and w.is_contiguous() for w in self.weights)
+
+    def run(self):
+        _lib.check(_lib.lib().stl_pack_conv_weights_batched(_lib.ptr(self.items), _lib.ptr(self.offsets), self.n,
+                                                            self.blocks, _stream()))
+        for key, view, rows, ref in self.entries:
+            _PREPACKED[key] = (view, rows, ref()._version, ref)
+
+
 def _pack_weights(w, cin_pad, own_bias=False):
     """fp32 OIHW -> ([k*k][cout_pad][cin_pad] bf16 buffer, zero fp32 bias)."""
     L = _lib.lib()
     cout, cin, k, _ = w.shape
     cout_pad = (cout + 15) // 16 * 16
+    if not own_bias:
+        hit = _prepacked(w, cin_pad, 0)
+        if hit is not None and hit[1] == cout_pad:
+            return hit[0], _zero_bias(cout_pad, w.device), cout_pad
     wp = torch.empty(k * k * cout_pad * cin_pad * 2, dtype=torch.uint8, device=w.device)
     bp = torch.empty(cout_pad, dtype=torch.float32, device=w.device) if own_bias else None
     w32 = w.detach().float().contiguous()
@@ -60,6 +125,9 @@ def _pack_weights_dgrad(w, k_pad):
     L = _lib.lib()
     cout, cin, k, _ = w.shape
     rows_pad = (cin + 15) // 16 * 16
+    hit = _prepacked(w, k_pad, 1)
+    if hit is not None and hit[1] == rows_pad:
+        return hit[0], _zero_bias(rows_pad, w.device), rows_pad
     wp = torch.empty(k * k * rows_pad * k_pad * 2, dtype=torch.uint8, device=w.device)
     w32 = w.detach().float().contiguous()
     _lib.check(L.stl_pack_conv_weights_dgrad(_lib.ptr(w32), cout, cin, k, rows_pad, k_pad, _lib.ptr(wp), None, _stream()))
@@ -135,7 +203,7 @@ class _ConvBN(torch.autograd.Function):
     """conv (no bias) + train-mode BatchNorm [+ residual] [+ ReLU] on padded bf16 activations."""
 
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, residual, run_mean, run_var, stride, relu, momentum):
+    def forward(ctx, x, weight, gamma, beta, residual, run_mean, run_var, stride, relu, momentum, tickets):
         L = _lib.lib()
         n, hp, wpd, cin_pad = x.shape
         h, w = hp - 1, wpd - 1
@@ -148,10 +216,11 @@ class _ConvBN(torch.autograd.Function):
         mean = torch.empty(cout, dtype=torch.float32, device=x.device)
         rstd = torch.empty(cout, dtype=torch.float32, device=x.device)
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        _lib.check(L.stl_bn_train_forward(_lib.ptr(z), _lib.ptr(g32), _lib.ptr(b32), _lib.ptr(residual), int(relu),
-                                          BN_EPS, float(momentum), n, ho, wo, cout, _lib.ptr(y), _lib.ptr(sums),
-                                          _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(run_mean), _lib.ptr(run_var),
-                                          _stream()))
+        _lib.check(L.stl_bn_train_forward_ticket(_lib.ptr(z), _lib.ptr(g32), _lib.ptr(b32), _lib.ptr(residual), int(relu),
+                                                 BN_EPS, float(momentum), n, ho, wo, cout, _lib.ptr(y), _lib.ptr(sums),
+                                                 _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(run_mean), _lib.ptr(run_var),
+                                                 tickets.data_ptr(), _stream()))
+        ctx.tickets = tickets
         ctx.save_for_backward(x, weight, z, y, mean, rstd, g32)
         ctx.meta = (n, h, w, cin_pad, cin_real, cout, k, stride, bool(relu), residual is not None)
         return y
@@ -165,16 +234,17 @@ class _ConvBN(torch.autograd.Function):
         dy = dy.contiguous()
         dz = torch.empty_like(z)
         dres = torch.empty_like(z) if has_res else None
-        sums = torch.empty(L.stl_bn_workspace_floats(cout), dtype=torch.float32, device=x.device)
-        _lib.check(L.stl_bn_train_backward(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(z), _lib.ptr(mean), _lib.ptr(rstd),
-                                           _lib.ptr(g32), int(relu), n, ho, wo, cout, _lib.ptr(dz), _lib.ptr(dres),
-                                           _lib.ptr(sums), _stream()))
-        dbeta, dgamma = sums[:cout].clone(), sums[cout:2 * cout].clone()
+        ws = torch.empty(L.stl_bn_workspace_floats(cout), dtype=torch.float32, device=x.device)
+        sums = torch.empty(2 * cout, dtype=torch.float32, device=x.device)     # dbeta | dgamma, returned as views
+        _lib.check(L.stl_bn_train_backward_ticket(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(z), _lib.ptr(mean), _lib.ptr(rstd),
+                                                  _lib.ptr(g32), int(relu), n, ho, wo, cout, _lib.ptr(dz), _lib.ptr(dres),
+                                                  _lib.ptr(sums), _lib.ptr(ws), ctx.tickets.data_ptr() + 4, _stream()))
+        dbeta, dgamma = sums[:cout], sums[cout:]
         if stride == 2 and cin_pad % 32 == 0:
             dz = zero_stuff(dz, n, h, w)               # shared by dgrad and wgrad
         dx = conv_dgrad(dz, weight, n, h, w, cin_pad, stride) if ctx.needs_input_grad[0] else None
         dw = conv_wgrad(x, dz, weight.shape, n, h, w, stride)
-        return dx, dw, dgamma, dbeta, dres, None, None, None, None, None
+        return dx, dw, dgamma, dbeta, dres, None, None, None, None, None, None
 
 
 class _Head(torch.autograd.Function):
@@ -239,9 +309,19 @@ class _FuseSum(torch.autograd.Function):
         return (None, None, *grads)
 
 
+def _tickets(bn, device):
+    """Two zero-initialised device words per BatchNorm layer (forward / backward reduction tickets, see
+    stl_bn_train_*_ticket): the reduction kernels leave them zero, so no memset is needed per call."""
+    t = getattr(bn, "_stl_tickets", None)
+    if t is None or t.device != device:
+        t = torch.zeros(2, dtype=torch.int32, device=device)
+        bn._stl_tickets = t
+    return t
+
+
 def _convbn(x, conv, bn, stride, relu, residual=None):
     return _ConvBN.apply(x, conv.weight, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, stride, relu,
-                         bn.momentum)
+                         bn.momentum, _tickets(bn, x.device))
 
 
 def train_forward(model, x):
@@ -256,6 +336,12 @@ def train_forward(model, x):
         counters = [b for n, b in model.named_buffers() if n.endswith("num_batches_tracked")]
         model._bn_counters = counters
     with torch.cuda.device(x.device):
+        pre = getattr(model, "_stl_prepack", None)
+        if pre is None or not pre.valid_for(x.device):
+            pre = model._stl_prepack = _Prepack(model, x.device) if all(
+                p.dtype == torch.float32 and p.is_contiguous() for p in model.parameters()) else None
+        if pre is not None:
+            pre.run()                                                  # every weight layout of this step, one launch
         torch._foreach_add_(counters, 1)                               # every BatchNorm runs once per forward
         t = torch.empty((B, H + 1, W + 1, 16), dtype=torch.bfloat16, device=x.device)
         _lib.check(L.stl_nchw_to_padded(_lib.ptr(x), _lib.ptr(t), B, 3, H, W, 16, _stream()))
