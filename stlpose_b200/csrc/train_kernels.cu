@@ -89,36 +89,68 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
     for (int i = 0; i < 8; ++i) { mu[i] = mean[cg * 8 + i]; rs[i] = rstd[cg * 8 + i]; }
   }
   if (pl < lanes) {
-#pragma unroll 4
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < pixels; p += (long long)gridDim.x * lanes) {
-      const size_t off = (size_t)p * C + cg * 8;
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(a + off), f);
-      if (MODE == 0) {
+    // explicit batches: all loads of kBatch pixels are issued before the first one is consumed (the rolled loop kept
+    // only two 16-byte loads in flight per thread: 0.7 TB/s on the large tensors, latency-bound on the small ones)
+    constexpr int kBatch = MODE == 0 ? 8 : 4;
+    const long long pstep = (long long)gridDim.x * lanes;
+    for (long long p0 = (long long)blockIdx.x * lanes + pl; p0 < pixels; p0 += kBatch * pstep) {
+      uint4 ua[kBatch], uy[MODE == 1 ? kBatch : 1], uz[MODE == 1 ? kBatch : 1];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s0[i] += f[i]; s1[i] += f[i] * f[i]; }
-      } else {
-        float yy[8], zz[8];
-        unpack8(*reinterpret_cast<const uint4*>(z + off), zz);
-        if (relu_mask) unpack8(*reinterpret_cast<const uint4*>(y + off), yy);
+      for (int k = 0; k < kBatch; ++k) {
+        const long long p = p0 + k * pstep;
+        const bool in = p < pixels;
+        const size_t off = (size_t)(in ? p : 0) * C + cg * 8;
+        ua[k] = in ? __ldg(reinterpret_cast<const uint4*>(a + off)) : make_uint4(0, 0, 0, 0);
+        if (MODE == 1) {
+          uz[k] = in ? __ldg(reinterpret_cast<const uint4*>(z + off)) : make_uint4(0, 0, 0, 0);
+          uy[k] = (in && relu_mask) ? __ldg(reinterpret_cast<const uint4*>(y + off)) : make_uint4(0, 0, 0, 0);
+        }
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float g = (relu_mask && !(yy[i] > 0.f)) ? 0.f : f[i];
-          s0[i] += g;
-          s1[i] += g * (zz[i] - mu[i]) * rs[i];
+      for (int k = 0; k < kBatch; ++k) {
+        if (p0 + k * pstep >= pixels) break;       // (an all-zero item would also be neutral in MODE 0, not in MODE 1)
+        float f[8];
+        unpack8(ua[k], f);
+        if (MODE == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s0[i] += f[i]; s1[i] += f[i] * f[i]; }
+        } else {
+          float yy[8], zz[8];
+          unpack8(uz[k], zz);
+          unpack8(uy[k], yy);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float g = (relu_mask && !(yy[i] > 0.f)) ? 0.f : f[i];
+            s0[i] += g;
+            s1[i] += g * (zz[i] - mu[i]) * rs[i];
+          }
         }
       }
     }
   }
-  __shared__ float red[2][256][8 + 1];
+  __shared__ __align__(16) float red[2][256][8 + 1];
   __shared__ bool is_last;
+  // pixel lanes that share a warp (32 / c8n of them when c8n < 32) are combined by shuffles first, in a fixed order
+  int lane_step = c8n;      // after the loop: lanes pl with (pl * c8n) % 32 == 0 hold a warp's sum
+  if (c8n < 32 && (32 % c8n) == 0) {
+    for (int off = c8n; off < 32; off <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s0[i] += __shfl_down_sync(0xFFFFFFFFu, s0[i], off);
+        s1[i] += __shfl_down_sync(0xFFFFFFFFu, s1[i], off);
+      }
+    }
+    lane_step = 32;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) { red[0][threadIdx.x][i] = s0[i]; red[1][threadIdx.x][i] = s1[i]; }
   __syncthreads();
   if (pl == 0) {
-    for (int l = 1; l < lanes; ++l)
+    // remaining partial sums: one per warp (lane_step == 32: threads cg, 32 + cg, ...) or one per pixel lane
+    const int nthreads = lanes * c8n;
+    for (int t = lane_step + cg; t < nthreads; t += lane_step)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s0[i] += red[0][l * c8n + cg][i]; s1[i] += red[1][l * c8n + cg][i]; }
+      for (int i = 0; i < 8; ++i) { s0[i] += red[0][t][i]; s1[i] += red[1][t][i]; }
     float* row = partial + (size_t)blockIdx.x * 2 * C;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { row[cg * 8 + i] = s0[i]; row[C + cg * 8 + i] = s1[i]; }
@@ -129,38 +161,46 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // fixed-order sum of the rows: `parts` thread groups each take an interleaved quarter (or less) of the rows with four
-  // independent accumulators (loads in flight), then the groups are combined in order through shared memory
+  // fixed-order sum of the rows with 16-byte loads: thread = (row group `part`, 4 consecutive columns); every group
+  // walks its interleaved share of the rows with four independent accumulators per column (4 x 16 B in flight), then
+  // the groups are combined in order through shared memory.  2C is a multiple of 16.
   {
-    const int C2 = 2 * C;
-    const int parts = C2 >= 256 ? 1 : 256 / C2;                 // C2 is a multiple of 16
-    const int part = threadIdx.x / C2, cc = threadIdx.x % C2;
-    float* comb = &red[0][0][0];                                // 256 x 9 floats >= parts * C2 when parts > 1
-    for (int c0 = 0; c0 < C2; c0 += 256) {
-      const int c = c0 + cc;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      if (part < parts && c < C2) {
+    const int C2 = 2 * C, q4 = C2 / 4;                          // float4 columns per row
+    float* comb = &red[0][0][0];                                // 2 x 256 x 9 floats >= 256 x 4
+    for (int c0 = 0; c0 < q4; c0 += 256) {
+      const int width = q4 - c0 < 256 ? q4 - c0 : 256;          // float4 columns handled in this pass
+      const int parts = 256 / width;                            // row groups (1 when the pass is 256 columns wide)
+      const int part = threadIdx.x / width, cc = threadIdx.x % width;
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+      if (part < parts) {
+        const float4* src = reinterpret_cast<const float4*>(partial) + c0 + cc;
         unsigned b2 = part;
         for (; b2 + 3 * parts < gridDim.x; b2 += 4 * parts) {
-          a0 += __ldcg(partial + (size_t)b2 * C2 + c);
-          a1 += __ldcg(partial + (size_t)(b2 + parts) * C2 + c);
-          a2 += __ldcg(partial + (size_t)(b2 + 2 * parts) * C2 + c);
-          a3 += __ldcg(partial + (size_t)(b2 + 3 * parts) * C2 + c);
+          const float4 v0 = __ldcg(src + (size_t)b2 * q4), v1 = __ldcg(src + (size_t)(b2 + parts) * q4);
+          const float4 v2 = __ldcg(src + (size_t)(b2 + 2 * parts) * q4), v3 = __ldcg(src + (size_t)(b2 + 3 * parts) * q4);
+          a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+          a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+          a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+          a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
         }
-        for (; b2 < gridDim.x; b2 += parts) a0 += __ldcg(partial + (size_t)b2 * C2 + c);
+        for (; b2 < gridDim.x; b2 += parts) {
+          const float4 v0 = __ldcg(src + (size_t)b2 * q4);
+          a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+        }
       }
-      const float acc = (a0 + a1) + (a2 + a3);
-      if (parts == 1) {
-        if (c < C2) sums[c] = acc;
-      } else {
-        __syncthreads();
-        if (part < parts) comb[part * C2 + cc] = acc;
-        __syncthreads();
-        if (part == 0) {
-          float t = 0.f;
-          for (int q = 0; q < parts; ++q) t += comb[q * C2 + cc];
-          sums[cc] = t;
+      float4 acc;
+      acc.x = (a0.x + a1.x) + (a2.x + a3.x); acc.y = (a0.y + a1.y) + (a2.y + a3.y);
+      acc.z = (a0.z + a1.z) + (a2.z + a3.z); acc.w = (a0.w + a1.w) + (a2.w + a3.w);
+      __syncthreads();                                          // (the block-level reduction above is done with `red`)
+      if (part < parts) reinterpret_cast<float4*>(comb)[part * width + cc] = acc;
+      __syncthreads();
+      if (part == 0) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < parts; ++q) {
+          const float4 v = reinterpret_cast<const float4*>(comb)[q * width + cc];
+          t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
         }
+        reinterpret_cast<float4*>(sums)[c0 + cc] = t;
       }
     }
   }
@@ -541,7 +581,7 @@ int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* be
   if (!ticket) cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   const int lanes = 256 / (C / 8);
   BnFinalize fin{(float)((long long)N * H * W), eps, momentum, mean, rstd, run_mean, run_var};
-  channel_reduce_kernel<0><<<grid_for(pixels, lanes * 16, kReduceBlocks), 256, 0, st>>>(
+  channel_reduce_kernel<0><<<grid_for(pixels, lanes * 8, kReduceBlocks), 256, 0, st>>>(
       z, nullptr, nullptr, nullptr, nullptr, pixels, C, 0, sums, sums + 2 * C, counter, fin);
   if (check("bn stats")) return 1;
   PixIdx px;
@@ -564,7 +604,7 @@ int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __n
   unsigned* counter = ticket ? ticket : reinterpret_cast<unsigned*>(partial + (size_t)2 * C * kReduceBlocks);
   if (!ticket) cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   const int lanes = 256 / (C / 8);
-  channel_reduce_kernel<1><<<grid_for(pixels, lanes * 16, kReduceBlocks), 256, 0, st>>>(
+  channel_reduce_kernel<1><<<grid_for(pixels, lanes * 8, kReduceBlocks), 256, 0, st>>>(
       dy, y, z, mean, rstd, pixels, C, relu, sums, partial, counter, BnFinalize{});
   if (check("bn backward reduce")) return 1;
   PixIdx px;
