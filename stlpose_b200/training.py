@@ -14,6 +14,7 @@ stay in the engine's padded-linear NHWC bf16 layout; parameter gradients are fp3
 so ``torch.optim`` works unchanged.
 """
 import ctypes
+import os
 
 import torch
 
@@ -165,8 +166,29 @@ def zero_stuff(dz, n, h, w):
     return u
 
 
+_SIDE_STREAMS = {}
+SIDE_WGRAD = os.environ.get("STLPOSE_SIDE_WGRAD", "1") != "0"
+
+
+def _side_stream(device):
+    """One extra stream per device: the weight-gradient kernels of a layer run there, next to its input-gradient
+    convolution on the main stream (both only need dz); forked and joined inside the layer's backward, so a captured
+    step records it as two parallel branches."""
+    s = _SIDE_STREAMS.get(device)
+    if s is None:
+        s = _SIDE_STREAMS[device] = torch.cuda.Stream(device=device)
+    return s
+
+
 def conv_wgrad(x, dz, weight_shape, n, h, w, stride):
     """Gradient wrt the OIHW weights (fp32).  `dz` may already be zero-stuffed for a stride-2 layer."""
+    dw, _ = _conv_wgrad(x, dz, weight_shape, n, h, w, stride)
+    return dw if dw.shape[0] == weight_shape[0] else dw[:weight_shape[0]].contiguous()
+
+
+def _conv_wgrad(x, dz, weight_shape, n, h, w, stride, side=None):
+    """-> (dw with cout_pad rows, workspace to keep alive).  side: a stream to launch on; the buffers are still allocated
+    on the current stream and the caller joins the side stream before dw is used or the workspace released."""
     L = _lib.lib()
     cout, cin_real, k, _ = weight_shape
     cin_pad, cout_pad = x.shape[3], dz.shape[3]
@@ -177,9 +199,11 @@ def conv_wgrad(x, dz, weight_shape, n, h, w, stride):
     s_eff = 1 if stuffed else stride
     ws_bytes = L.stl_conv_wgrad_workspace_bytes(n, h, w, cin_pad, cout_pad, k, s_eff, cin_real)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream(x.device))          # dz (and everything allocated above) is ready
     _lib.check(L.stl_conv_wgrad(_lib.ptr(x), _lib.ptr(dz), _lib.ptr(dw), n, h, w, cin_pad, cout_pad, k, s_eff, cin_real,
-                                _lib.ptr(ws), ws_bytes, _stream()))
-    return dw if cout_pad == cout else dw[:cout].contiguous()
+                                _lib.ptr(ws), ws_bytes, side.cuda_stream if side is not None else _stream()))
+    return dw, ws
 
 
 def conv_dgrad(dz, weight, n, h, w, cin_pad, stride):
@@ -242,8 +266,15 @@ class _ConvBN(torch.autograd.Function):
         dbeta, dgamma = sums[:cout], sums[cout:]
         if stride == 2 and cin_pad % 32 == 0:
             dz = zero_stuff(dz, n, h, w)               # shared by dgrad and wgrad
+        # dgrad (main stream) and wgrad (side stream) both only need dz: two parallel branches of the step
+        side = _side_stream(x.device) if (SIDE_WGRAD and ctx.needs_input_grad[0]) else None
+        dw, keep = _conv_wgrad(x, dz, weight.shape, n, h, w, stride, side=side)
         dx = conv_dgrad(dz, weight, n, h, w, cin_pad, stride) if ctx.needs_input_grad[0] else None
-        dw = conv_wgrad(x, dz, weight.shape, n, h, w, stride)
+        if side is not None:
+            torch.cuda.current_stream(x.device).wait_stream(side)       # join before dw / the workspace are touched again
+        del keep
+        if dw.shape[0] != cout:
+            dw = dw[:cout].contiguous()
         return dx, dw, dgamma, dbeta, dres, None, None, None, None, None, None
 
 
