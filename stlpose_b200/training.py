@@ -171,12 +171,27 @@ SIDE_WGRAD = os.environ.get("STLPOSE_SIDE_WGRAD", "1") != "0"
 
 
 def _side_stream(device):
-    """One extra stream per device: the weight-gradient kernels of a layer run there, next to its input-gradient
-    convolution on the main stream (both only need dz); forked and joined inside the layer's backward, so a captured
-    step records it as two parallel branches."""
-    s = _SIDE_STREAMS.get(device)
+    """One extra stream per (device, current stream): the weight-gradient kernels of a layer run there, next to its
+    input-gradient convolution on the current stream (both only need dz); forked and joined inside the layer's backward,
+    so a captured step records it as two parallel branches."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    s = _SIDE_STREAMS.get(key)
     if s is None:
-        s = _SIDE_STREAMS[device] = torch.cuda.Stream(device=device)
+        s = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return s
+
+
+_BRANCH_STREAMS = {}
+BRANCH_STREAMS = os.environ.get("STLPOSE_TRAIN_BRANCH_STREAMS", "1") != "0"
+
+
+def _branch_stream(device, b):
+    """Stream of branch b >= 1 of a HighResolutionModule: the branches of a module are independent chains of small
+    kernels (at fine-tuning batch sizes the low-resolution ones fill a fraction of the SMs), so they run side by side;
+    autograd replays each backward node on its forward stream, so the backward is parallel in the same way."""
+    s = _BRANCH_STREAMS.get((device, b))
+    if s is None:
+        s = _BRANCH_STREAMS[(device, b)] = torch.cuda.Stream(device=device)
     return s
 
 
@@ -399,22 +414,41 @@ def train_forward(model, x):
 def _hr_module(mod, xs):
     """HighResolutionModule.forward, HRnet.py:248-266."""
     xs = list(xs)
+    dev = xs[0].device
+    main = torch.cuda.current_stream(dev)
+    forked = []
     for b, branch in enumerate(mod.branches):
-        for blk in branch:                                           # BasicBlock.forward, HRnet.py:45-61
-            o = _convbn(xs[b], blk.conv1, blk.bn1, 1, True)
-            xs[b] = _convbn(o, blk.conv2, blk.bn2, 1, True, residual=xs[b])
+        st = main
+        if BRANCH_STREAMS and b > 0:
+            st = _branch_stream(dev, b)
+            st.wait_stream(main)                                     # fork: the branch input is ready
+            forked.append(st)
+        with torch.cuda.stream(st):
+            for blk in branch:                                       # BasicBlock.forward, HRnet.py:45-61
+                o = _convbn(xs[b], blk.conv1, blk.bn1, 1, True)
+                xs[b] = _convbn(o, blk.conv2, blk.bn2, 1, True, residual=xs[b])
+    # exchange (fuse) layers: output row i needs every branch, so the streams first wait for each other; then row i runs
+    # on stream i (the rows are independent of each other), and everything joins the main stream at the end
+    streams = [main] + forked
+    for si in streams:
+        for sj in streams:
+            if sj is not si:
+                si.wait_stream(sj)
     outs = []
     for i, row in enumerate(mod.fuse_layers):
-        same, ups, shifts = [xs[i]], [], []
-        for j in range(len(xs)):
-            if j > i:
-                ups.append(_convbn(xs[j], row[j][0], row[j][1], 1, False))
-                shifts.append(j - i)
-            elif j < i:
-                t = xs[j]
-                hops = len(row[j])
-                for k, seq in enumerate(row[j]):
-                    t = _convbn(t, seq[0], seq[1], 2, k != hops - 1)
-                same.append(t)
-        outs.append(_FuseSum.apply(len(same), shifts, *same, *ups))
+        with torch.cuda.stream(streams[i] if i < len(streams) else main):
+            same, ups, shifts = [xs[i]], [], []
+            for j in range(len(xs)):
+                if j > i:
+                    ups.append(_convbn(xs[j], row[j][0], row[j][1], 1, False))
+                    shifts.append(j - i)
+                elif j < i:
+                    t = xs[j]
+                    hops = len(row[j])
+                    for k, seq in enumerate(row[j]):
+                        t = _convbn(t, seq[0], seq[1], 2, k != hops - 1)
+                    same.append(t)
+            outs.append(_FuseSum.apply(len(same), shifts, *same, *ups))
+    for st in forked:
+        main.wait_stream(st)
     return outs
