@@ -141,11 +141,15 @@ class GradientReducer:
             views = torch.split(flat, [p.numel() for p in bucket])
             if self.comm_stream is not None:
                 torch.cuda.current_stream(flat.device).wait_stream(self.comm_stream)
+            dst, src = [], []
             for p, v in zip(bucket, views):
                 if p.grad is None:
                     p.grad = v.view_as(p).clone()
                 else:
-                    p.grad.copy_(v.view_as(p))
+                    dst.append(p.grad)
+                    src.append(v.view_as(p))
+            if dst:
+                torch._foreach_copy_(dst, src)       # one multi-tensor launch per bucket instead of one copy per parameter
         self._works = []
 
     def reduce_all(self):
