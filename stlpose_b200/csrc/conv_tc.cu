@@ -801,16 +801,22 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
             tc_fence_after();
           }
           bool ready = false;
+          // units of this warp: panels pi = 0 .. cnt-1 of the batch, 16-channel slices sl = sub, sub+2, .. of each panel.
+          // Written for instruction count (the drain competes with four other roles for issue slots): incremental
+          // indices, the zero-cell test once per 128-row block, packed fp32x2 adds.
+          int pi = 0, sl = sub, m_cached = -1;
+          bool is_pad = false;
 #pragma unroll 1
           for (int u = 0; u < nunits; ++u) {
-            const int pi = upp == 1 ? u : (upp == 2 ? u >> 1 : u / upp);   // panel inside the batch
-            const int sl = sub + 2 * (u - pi * upp);                        // 16-channel slice inside the panel
             const int idx = b0 + pi;
-            const int m = npanels == 1 ? idx : (npanels == 2 ? idx >> 1 : idx / npanels), pn = idx - m * npanels;
+            const int m = npanels == 1 ? idx : idx >> 1, pn = npanels == 1 ? 0 : idx & 1;   // npanels is 1 or 2 (nt <= 128)
             const int ch = pn * panel_ch + sl * 16;
             uint32_t v[16];
             tmem_ld16(t_tile + (uint32_t)(m * nt + ch), v);
-            const RowPos pos = row_position(p, mt, m * 128 + row0);
+            if (!kStruct && m != m_cached) {          // (structured tiles hold valid pixels only)
+              is_pad = row_position(p, mt, m * 128 + row0).is_pad;
+              m_cached = m;
+            }
             const uint32_t base = stage + (uint32_t)pi * panel_bytes + (uint32_t)row0 * pitch;
             const uint32_t c0 = (uint32_t)sl * 2u;  // 16-byte chunks of the slice in its panel row
             const uint32_t ad0 = base + ((c0 ^ xr) << 4), ad1 = base + (((c0 + 1) ^ xr) << 4);
@@ -828,15 +834,18 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
             uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
             if (has_res) { r0 = lds128(ad0); r1 = lds128(ad1); }
             tmem_ld_wait();
-            float* f = reinterpret_cast<float*>(v);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              f[g * 4 + 0] += bias[g].x; f[g * 4 + 1] += bias[g].y; f[g * 4 + 2] += bias[g].z; f[g * 4 + 3] += bias[g].w;
+              fadd2(v[g * 4 + 0], v[g * 4 + 1], __float_as_uint(bias[g].x), __float_as_uint(bias[g].y));
+              fadd2(v[g * 4 + 2], v[g * 4 + 3], __float_as_uint(bias[g].z), __float_as_uint(bias[g].w));
             }
-            f[0] += bf16_lo(r0.x); f[1] += bf16_hi(r0.x); f[2] += bf16_lo(r0.y); f[3] += bf16_hi(r0.y);
-            f[4] += bf16_lo(r0.z); f[5] += bf16_hi(r0.z); f[6] += bf16_lo(r0.w); f[7] += bf16_hi(r0.w);
-            f[8] += bf16_lo(r1.x); f[9] += bf16_hi(r1.x); f[10] += bf16_lo(r1.y); f[11] += bf16_hi(r1.y);
-            f[12] += bf16_lo(r1.z); f[13] += bf16_hi(r1.z); f[14] += bf16_lo(r1.w); f[15] += bf16_hi(r1.w);
+            if (has_res) {
+              fadd2(v[0], v[1], r0.x << 16, r0.x & 0xFFFF0000u);   fadd2(v[2], v[3], r0.y << 16, r0.y & 0xFFFF0000u);
+              fadd2(v[4], v[5], r0.z << 16, r0.z & 0xFFFF0000u);   fadd2(v[6], v[7], r0.w << 16, r0.w & 0xFFFF0000u);
+              fadd2(v[8], v[9], r1.x << 16, r1.x & 0xFFFF0000u);   fadd2(v[10], v[11], r1.y << 16, r1.y & 0xFFFF0000u);
+              fadd2(v[12], v[13], r1.z << 16, r1.z & 0xFFFF0000u); fadd2(v[14], v[15], r1.w << 16, r1.w & 0xFFFF0000u);
+            }
+            const float* f = reinterpret_cast<const float*>(v);
             uint4 o0, o1;
             if (e.relu) {
               o0 = make_uint4(pack_bf16_relu(f[0], f[1]), pack_bf16_relu(f[2], f[3]), pack_bf16_relu(f[4], f[5]),
@@ -848,9 +857,11 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
               o1 = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
                               pack_bf16(f[14], f[15]));
             }
-            if (pos.is_pad) { o0 = make_uint4(0, 0, 0, 0); o1 = o0; }  // zero cells of the padded layout stay zero
+            if (is_pad) { o0 = make_uint4(0, 0, 0, 0); o1 = o0; }  // zero cells of the padded layout stay zero
             sts128(ad0, o0);
             sts128(ad1, o1);
+            sl += 2;
+            if (sl >= spp) { sl = sub; ++pi; }
           }
           if (!ready) {  // a warp without units in this batch still has to observe the buffer hand-over in order
             if (has_res) mbar_wait(&ctl->res_full[group * 2 + sbuf], (kb >> 1) & 1);
