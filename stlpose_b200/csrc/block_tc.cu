@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(kBlkThreads, 1) basic_block_kernel(const __gri
         if (real) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            f[g * 4 + 0] += bias[g].x; f[g * 4 + 1] += bias[g].y; f[g * 4 + 2] += bias[g].z; f[g * 4 + 3] += bias[g].w;
+            fadd2(v[g * 4 + 0], v[g * 4 + 1], __float_as_uint(bias[g].x), __float_as_uint(bias[g].y));
+            fadd2(v[g * 4 + 2], v[g * 4 + 3], __float_as_uint(bias[g].z), __float_as_uint(bias[g].w));
           }
           o0 = make_uint4(pack_relu(f[0], f[1]), pack_relu(f[2], f[3]), pack_relu(f[4], f[5]), pack_relu(f[6], f[7]));
           o1 = make_uint4(pack_relu(f[8], f[9]), pack_relu(f[10], f[11]), pack_relu(f[12], f[13]), pack_relu(f[14], f[15]));
@@ -270,12 +271,13 @@ __global__ void __launch_bounds__(kBlkThreads, 1) basic_block_kernel(const __gri
         float* f = reinterpret_cast<float*>(v);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          f[g * 4 + 0] += bias[g].x; f[g * 4 + 1] += bias[g].y; f[g * 4 + 2] += bias[g].z; f[g * 4 + 3] += bias[g].w;
+          fadd2(v[g * 4 + 0], v[g * 4 + 1], __float_as_uint(bias[g].x), __float_as_uint(bias[g].y));
+          fadd2(v[g * 4 + 2], v[g * 4 + 3], __float_as_uint(bias[g].z), __float_as_uint(bias[g].w));
         }
-        f[0] += blo(r0.x); f[1] += bhi(r0.x); f[2] += blo(r0.y); f[3] += bhi(r0.y);
-        f[4] += blo(r0.z); f[5] += bhi(r0.z); f[6] += blo(r0.w); f[7] += bhi(r0.w);
-        f[8] += blo(r1.x); f[9] += bhi(r1.x); f[10] += blo(r1.y); f[11] += bhi(r1.y);
-        f[12] += blo(r1.z); f[13] += bhi(r1.z); f[14] += blo(r1.w); f[15] += bhi(r1.w);
+        fadd2(v[0], v[1], r0.x << 16, r0.x & 0xFFFF0000u);   fadd2(v[2], v[3], r0.y << 16, r0.y & 0xFFFF0000u);
+        fadd2(v[4], v[5], r0.z << 16, r0.z & 0xFFFF0000u);   fadd2(v[6], v[7], r0.w << 16, r0.w & 0xFFFF0000u);
+        fadd2(v[8], v[9], r1.x << 16, r1.x & 0xFFFF0000u);   fadd2(v[10], v[11], r1.y << 16, r1.y & 0xFFFF0000u);
+        fadd2(v[12], v[13], r1.z << 16, r1.z & 0xFFFF0000u); fadd2(v[14], v[15], r1.w << 16, r1.w & 0xFFFF0000u);
         uint4 o0 = make_uint4(pack_relu(f[0], f[1]), pack_relu(f[2], f[3]), pack_relu(f[4], f[5]), pack_relu(f[6], f[7]));
         uint4 o1 = make_uint4(pack_relu(f[8], f[9]), pack_relu(f[10], f[11]), pack_relu(f[12], f[13]), pack_relu(f[14], f[15]));
         if (!real) { o0 = make_uint4(0, 0, 0, 0); o1 = o0; }     // zero cells of the padded layout stay zero

@@ -124,15 +124,6 @@ struct EpiParams {
   int cout, relu, n_up, H, W, skip;
 };
 
-// Packed fp32x2 add on register pairs (FADD2): (a0, a1) += (b0, b1), operands as raw bits.
-__device__ __forceinline__ void fadd2(uint32_t& a0, uint32_t& a1, uint32_t b0, uint32_t b1) {
-  uint64_t a, b;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "r"(b0), "r"(b1));
-  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "l"(a));
-}
-
 __device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
   uint32_t r;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));  // first source -> upper half
@@ -806,6 +797,8 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
           // indices, the zero-cell test once per 128-row block, packed fp32x2 adds.
           int pi = 0, sl = sub, m_cached = -1;
           bool is_pad = false;
+          RowPos upos;          // structured tiles with upsampled addends: the output pixel of this thread's row
+          upos.valid = false;
 #pragma unroll 1
           for (int u = 0; u < nunits; ++u) {
             const int idx = b0 + pi;
@@ -813,8 +806,9 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
             const int ch = pn * panel_ch + sl * 16;
             uint32_t v[16];
             tmem_ld16(t_tile + (uint32_t)(m * nt + ch), v);
-            if (!kStruct && m != m_cached) {          // (structured tiles hold valid pixels only)
-              is_pad = row_position(p, mt, m * 128 + row0).is_pad;
+            if (m != m_cached) {
+              if (!kStruct) is_pad = row_position(p, mt, m * 128 + row0).is_pad;   // (structured tiles: valid pixels only)
+              else if (e.n_up) upos = row_position(p, mt, m * 128 + row0);
               m_cached = m;
             }
             const uint32_t base = stage + (uint32_t)pi * panel_bytes + (uint32_t)row0 * pitch;
@@ -844,6 +838,21 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
               fadd2(v[4], v[5], r0.z << 16, r0.z & 0xFFFF0000u);   fadd2(v[6], v[7], r0.w << 16, r0.w & 0xFFFF0000u);
               fadd2(v[8], v[9], r1.x << 16, r1.x & 0xFFFF0000u);   fadd2(v[10], v[11], r1.y << 16, r1.y & 0xFFFF0000u);
               fadd2(v[12], v[13], r1.z << 16, r1.z & 0xFFFF0000u); fadd2(v[14], v[15], r1.w << 16, r1.w & 0xFFFF0000u);
+            }
+            if (kStruct && e.n_up && upos.valid) {
+              // nearest-upsampled addends of the fuse row (HRnet.py:198-209, 258-264), gathered from the low-resolution maps
+#pragma unroll 1
+              for (int uu = 0; uu < e.n_up; ++uu) {
+                const int sh = p.up_shift[uu];
+                const int hs = e.H >> sh, ws = e.W >> sh;
+                const size_t qs = ((size_t)upos.n * (hs + 1) + (upos.h >> sh)) * (ws + 1) + (upos.w >> sh);
+                const uint4* src = reinterpret_cast<const uint4*>(p.up_src[uu] + qs * e.cout + chbase + ch);
+                const uint4 t0 = __ldg(src), t1 = __ldg(src + 1);
+                fadd2(v[0], v[1], t0.x << 16, t0.x & 0xFFFF0000u);   fadd2(v[2], v[3], t0.y << 16, t0.y & 0xFFFF0000u);
+                fadd2(v[4], v[5], t0.z << 16, t0.z & 0xFFFF0000u);   fadd2(v[6], v[7], t0.w << 16, t0.w & 0xFFFF0000u);
+                fadd2(v[8], v[9], t1.x << 16, t1.x & 0xFFFF0000u);   fadd2(v[10], v[11], t1.y << 16, t1.y & 0xFFFF0000u);
+                fadd2(v[12], v[13], t1.z << 16, t1.z & 0xFFFF0000u); fadd2(v[14], v[15], t1.w << 16, t1.w & 0xFFFF0000u);
+              }
             }
             const float* f = reinterpret_cast<const float*>(v);
             uint4 o0, o1;
@@ -1134,8 +1143,9 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   // weights stay resident in shared memory when every tile of the layer fits next to >= 2 activation stages;
   // otherwise they stream through a ring (one stage per (chunk, tap))
   // staged (TMA) epilogue for flat-mode bf16 outputs: 2 groups x 2 panel buffers x 16 KB
-  p.epi_tma = (!s.out_nchw && s.n_up == 0 && !getenv("STL_DBG_NO_EPI_TMA") &&
-               (p.mode == 0 || (p.taps == 9 && !getenv("STL_DBG_NO_EPI_TMA_S2")))) ? 1 : 0;
+  // (upsampled addends: only the structured staged epilogue gathers them - that is where the fuse rows put them)
+  p.epi_tma = (!s.out_nchw && (s.n_up == 0 || (p.mode == 1 && !getenv("STL_DBG_NO_EPI_TMA_UP"))) &&
+               !getenv("STL_DBG_NO_EPI_TMA") && (p.mode == 0 || (p.taps == 9 && !getenv("STL_DBG_NO_EPI_TMA_S2")))) ? 1 : 0;
   p.panel_ch = (p.nt % 64 == 0) ? 64 : p.nt;
   p.panel_swz = p.panel_ch == 64 ? 128 : (p.panel_ch == 32 ? 64 : 0);
   p.epi_panel_bytes = (uint32_t)((p.panel_ch * 2 * 128 + 1023) & ~1023);

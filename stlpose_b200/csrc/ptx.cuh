@@ -60,6 +60,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Packed fp32x2 add on register pairs (FADD2): (a0, a1) += (b0, b1), operands as raw bits.
+__device__ __forceinline__ void fadd2(uint32_t& a0, uint32_t& a1, uint32_t b0, uint32_t b1) {
+  uint64_t a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "r"(b0), "r"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "l"(a));
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
