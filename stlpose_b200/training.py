@@ -99,6 +99,9 @@ class _Prepack:
     def run(self):
         _lib.check(_lib.lib().stl_pack_conv_weights_batched(_lib.ptr(self.items), _lib.ptr(self.offsets), self.n,
                                                             self.blocks, _stream()))
+        dead = [k for k, v in _PREPACKED.items() if v[3]() is None]      # weights of models that no longer exist
+        for k in dead:
+            del _PREPACKED[k]
         for key, view, rows, ref in self.entries:
             _PREPACKED[key] = (view, rows, ref()._version, ref)
 
