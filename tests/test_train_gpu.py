@@ -239,3 +239,35 @@ def test_w48_train_step_runs_on_fallback_kernels():
         opt.zero_grad(); l.backward(); opt.step()
         losses.append(l.item())
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_parallel_streams_give_the_same_training_steps(monkeypatch):
+    """The stream-parallel schedule (module branches and fuse rows side by side, weight gradients next to input
+    gradients) only reorders independent launches: three eager SGD steps must leave bit-identical parameters and
+    running statistics to the same steps issued on one stream (all kernels are deterministic)."""
+    from stlpose_b200 import training
+    results = []
+    for parallel in (True, False):
+        monkeypatch.setattr(training, "BRANCH_STREAMS", parallel)
+        monkeypatch.setattr(training, "SIDE_WGRAD", parallel)
+        S, sd0, x, tgt, tw, m = _setup(B=6, seed=3)
+        m.train()
+        opt = torch.optim.SGD(m.parameters(), lr=1e-2, momentum=0.9, weight_decay=5e-4)
+        crit = S.PersonMSELoss()
+        xd, td, wd = x.cuda(), tgt.cuda().float(), tw.cuda()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # not the default stream (see TrainStep's note on accumulation nodes)
+            for _ in range(3):
+                loss = crit(S.forward_pass(m, xd, "HRNet", device="cuda", flip=False), td, wd)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                m.invalidate_packed_weights()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        results.append(({k: v.detach().clone() for k, v in m.state_dict().items()}, float(loss.detach())))
+    (a, la), (b, lb) = results
+    assert la == lb
+    bad = [k for k in a if not torch.equal(a[k], b[k])]
+    assert not bad, f"{len(bad)} tensors differ, e.g. {bad[:3]}"
