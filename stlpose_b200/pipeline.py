@@ -41,6 +41,7 @@ class KeypointPipeline:
         self._copy_stream = torch.cuda.Stream(device=dev)
         self._calls = 0
         self.graph = None
+        self._stage_graphs = None                    # one graph per staging buffer: the end-to-end call skips the copy into x
         with torch.cuda.device(dev):
             self._step_eager()                       # packs weights, binds the workspace, warms everything up
             torch.cuda.synchronize()
@@ -55,10 +56,17 @@ class KeypointPipeline:
                 with torch.cuda.graph(g):
                     self._step_eager()
                 self.graph = g
+                # the same step reading its crops straight from staging buffer j (same workspace, same outputs)
+                self._stage_graphs = []
+                for j in range(2):
+                    gj = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gj):
+                        self._step_eager(self._stage[j])
+                    self._stage_graphs.append(gj)
 
-    def _step_eager(self):
+    def _step_eager(self, x=None):
         L = _lib.lib()
-        heat = self.model._run(self.x, flip_pair=self.flip)
+        heat = self.model._run(self.x if x is None else x, flip_pair=self.flip)
         self._heat = heat                            # keep the graph's output buffer alive
         hf = heat[self.B:] if self.flip else None
         _lib.check(L.stl_decode(_lib.ptr(heat), _lib.ptr(hf), _lib.ptr(self.center), _lib.ptr(self.scale), self.B,
@@ -76,9 +84,10 @@ class KeypointPipeline:
     def __call__(self, x_host, center_host, scale_host, preds_host=None, maxvals_host=None):
         """End-to-end call with HOST (ideally pinned) buffers: H2D copies, step, D2H of preds and maxvals.
 
-        Everything is enqueued asynchronously: the crops go host -> staging buffer on a copy stream (double
-        buffered, so the copy of the next call overlaps this call's network pass), then staging -> the graph's
-        input on the compute stream.  Synchronise the current stream before reading the returned host tensors."""
+        Everything is enqueued asynchronously: the crops (and, ahead of them, the boxes) go host -> staging buffer on a
+        copy stream (double buffered, so the copy of the next call overlaps this call's network pass); the step is
+        replayed from a graph that reads the staging buffer directly (``self.x`` is only the input of ``step()``).
+        Synchronise the current stream before reading the returned host tensors."""
         cur = torch.cuda.current_stream(self.device)
         j = self._calls & 1
         self._calls += 1
@@ -91,11 +100,13 @@ class KeypointPipeline:
             self._stage[j].copy_(x_host, non_blocking=True)
             self._stage_ready[j].record(self._copy_stream)
         cur.wait_event(self._stage_ready[j])
-        self.x.copy_(self._stage[j], non_blocking=True)
         self.center.copy_(self._stage_c[j], non_blocking=True)
         self.scale.copy_(self._stage_s[j], non_blocking=True)
+        if self._stage_graphs is not None:
+            self._stage_graphs[j].replay()                          # reads the crops from the staging buffer itself
+        else:
+            self._step_eager(self._stage[j])
         self._stage_free[j].record(cur)
-        self.step()
         if preds_host is None:
             preds_host = torch.empty(tuple(self.preds.shape), dtype=torch.float32).pin_memory()
             maxvals_host = torch.empty(tuple(self.maxvals.shape), dtype=torch.float32).pin_memory()
