@@ -79,7 +79,9 @@ template <int NC>
 __device__ __forceinline__ void load_bf16_row(uint4 (&r)[NC / 8], const __nv_bfloat16* src, bool pred) {
   const uint4* s = reinterpret_cast<const uint4*>(src);
 #pragma unroll
-  for (int g = 0; g < NC / 8; ++g) r[g] = pred ? __ldg(s + g) : make_uint4(0, 0, 0, 0);
+  // (ld.global.cg, not the non-coherent path: with programmatic dependent launch this kernel is already resident while
+  // the layer that writes these activations is still running)
+  for (int g = 0; g < NC / 8; ++g) r[g] = pred ? __ldcg(s + g) : make_uint4(0, 0, 0, 0);
 }
 
 struct RowPos {
@@ -180,7 +182,7 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, const EpiPar
         const uint4* src = reinterpret_cast<const uint4*>(p.up_src[u] + qs * e.cout + ch0);
 #pragma unroll
         for (int g = 0; g < NC / 8; ++g) {
-          const uint4 t = __ldg(src + g);
+          const uint4 t = __ldcg(src + g);
           f[g * 8 + 0] += bf16_lo(t.x); f[g * 8 + 1] += bf16_hi(t.x);
           f[g * 8 + 2] += bf16_lo(t.y); f[g * 8 + 3] += bf16_hi(t.y);
           f[g * 8 + 4] += bf16_lo(t.z); f[g * 8 + 5] += bf16_hi(t.z);
@@ -847,7 +849,7 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
                 const int hs = e.H >> sh, ws = e.W >> sh;
                 const size_t qs = ((size_t)upos.n * (hs + 1) + (upos.h >> sh)) * (ws + 1) + (upos.w >> sh);
                 const uint4* src = reinterpret_cast<const uint4*>(p.up_src[uu] + qs * e.cout + chbase + ch);
-                const uint4 t0 = __ldg(src), t1 = __ldg(src + 1);
+                const uint4 t0 = __ldcg(src), t1 = __ldcg(src + 1);   // coherent loads: see load_bf16_row
                 fadd2(v[0], v[1], t0.x << 16, t0.x & 0xFFFF0000u);   fadd2(v[2], v[3], t0.y << 16, t0.y & 0xFFFF0000u);
                 fadd2(v[4], v[5], t0.z << 16, t0.z & 0xFFFF0000u);   fadd2(v[6], v[7], t0.w << 16, t0.w & 0xFFFF0000u);
                 fadd2(v[8], v[9], t1.x << 16, t1.x & 0xFFFF0000u);   fadd2(v[10], v[11], t1.y << 16, t1.y & 0xFFFF0000u);
