@@ -210,8 +210,12 @@ __global__ void __launch_bounds__(128) oks_nms_kernel(const float* __restrict__ 
   __shared__ double s_score[kMaxPersons];
   __shared__ int s_order[kMaxPersons];
   __shared__ unsigned char s_dead[kMaxPersons];
-  const int lo = off[blockIdx.x], n = off[blockIdx.x + 1] - lo;
-  if (n <= 0) return;
+  const int lo = off[blockIdx.x], n_all = off[blockIdx.x + 1] - lo;
+  if (n_all <= 0) return;
+  // (the host wrapper rejects more than kMaxPersons per image; should the offsets say otherwise, the surplus persons are
+  // reported as suppressed rather than indexing past the shared arrays)
+  const int n = n_all < kMaxPersons ? n_all : kMaxPersons;
+  for (int i = n + threadIdx.x; i < n_all; i += blockDim.x) { keep_rank[lo + i] = -1; score_out[lo + i] = box_score[lo + i]; }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float* kp = kpts + (size_t)(lo + i) * J * 3;
     double sc = box_score[lo + i];
