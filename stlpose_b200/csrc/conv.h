@@ -99,6 +99,7 @@ struct ConvParams {
   uint32_t epi_panel_bytes;
   uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes, b_resident_bytes, b_bytes_total;
   int n_accbuf;
+  uint32_t ctl_bytes;     // barriers + bias in front of the activation stages (multiple of 1024)
   uint32_t tmem_cols;
   long long total_tiles;
   // input / output geometry

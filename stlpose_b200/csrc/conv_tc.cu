@@ -31,7 +31,7 @@ constexpr int kThreads = 672;          // warp 0: TMA, warp 1: MMA, warps 2..17:
                                        // warps 18..19: one epilogue DMA warp per group (panel loads / stores),
                                        // warp 20: second MMA issuer (burst mode: the 128-row blocks of a tile are split)
 constexpr int kThreadsKW = 640;         // kw-merged kernels: no second MMA issuer, 96 registers per thread instead of 80
-constexpr uint32_t kCtlBytes = 4096;   // [0,1024): barriers + TMEM base ; [1024,4096): fp32 bias for all channels
+constexpr uint32_t kCtlBytes = 4096;   // [0,1024): barriers + TMEM base ; [1024, ctl_bytes): fp32 bias (ctl_bytes <= 4096)
 constexpr uint32_t kBiasOffset = 1024;
 constexpr int kMaxCoutPad = 768;
 constexpr int kEpiStaged = 0, kEpiDirect = 1, kEpiNchw = 2;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
   float* sbias = reinterpret_cast<float*>(smem + kBiasOffset);
-  const uint32_t a_base = smem_u32(smem + kCtlBytes);
+  const uint32_t a_base = smem_u32(smem + p.ctl_bytes);
   const uint32_t b_base = a_base + (uint32_t)p.a_stages * p.a_stage_bytes;
 
   constexpr bool NCHW = EPI == kEpiNchw;
@@ -1162,7 +1162,11 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   }
   const size_t xch_bytes = kwm ? 2 * 2 * 2 * 4 * 192 : 0;   // [group][sub][parity][quarter][3 rows x 16 fp32]
   const size_t epi_bytes = (p.epi_tma ? (size_t)2 * 2 * p.epi_batch * p.epi_panel_bytes : 0) + xch_bytes;
-  const size_t budget = kMaxSmem - kCtlBytes - 1024 - epi_bytes;
+  // control block: 1 KB of barriers + the bias rounded up to 1 KB (2 KB instead of 4 for <= 256 output channels; gives
+  // 64 -> 64 3x3 @64x48 a third activation stage - measured neutral, 286 vs 283 us)
+  p.ctl_bytes = 1024u + (((uint32_t)s.cout_pad * 4u + 1023u) & ~1023u);
+  if (p.ctl_bytes > kCtlBytes) { set_error("conv: cout_pad %d exceeds the bias area", s.cout_pad); return 1; }
+  const size_t budget = kMaxSmem - p.ctl_bytes - 1024 - epi_bytes;
   // CTA pairs (cta_group::2): flat mode, staged epilogue, burst-capable; each CTA then keeps half of the weight rows
   // Measured on B200: for layers whose weights stay resident (N <= 64, every 1x1) pairs are slower - the MMA rate is
   // bound by the A-operand fetch (128 rows x 32 B per SM per instruction), which pairing does not reduce.  For
@@ -1227,7 +1231,7 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   }
   // measured on B200: a second issuer pays off only for N <= 32 (16-cycle MMAs); at N = 64 the two streams interfere
   p.n_mma = (p.b_resident && (p.a_shift || p.taps == 1) && p.mb >= 2 && p.nt <= 32 && !getenv("STL_DBG_SINGLE_MMA")) ? 2 : 1;
-  *smem_bytes = kCtlBytes + 1024 + (size_t)a_st * p.a_stage_bytes + p.b_bytes_total + epi_bytes;
+  *smem_bytes = p.ctl_bytes + 1024 + (size_t)a_st * p.a_stage_bytes + p.b_bytes_total + epi_bytes;
   p.epi_base_off = (uint32_t)((size_t)a_st * p.a_stage_bytes + p.b_bytes_total);
   p.xch_off = p.epi_base_off + (uint32_t)(epi_bytes - xch_bytes);
   if (p.epi_tma && p.mode == 1) {
