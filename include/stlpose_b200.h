@@ -293,13 +293,18 @@ int stl_conv_dgrad(const void* dz, const void* w_packed, void* dx, int N, int Hi
 /* stl_conv_wgrad runs stride-1 problems with channel counts of 32/64/128/256 on the tcgen05 tensor cores (stride-2
  * layers get there through stl_zero_stuff): every CTA accumulates a pixel range in TMEM and writes a slab of partial
  * sums to `workspace` (stl_conv_wgrad_workspace_bytes, 0 when the CUDA-core kernel will be used); a second kernel adds
- * the slabs in a fixed order, so the result is deterministic.  Other shapes (native stride 2, the 3-channel stem) use
- * a CUDA-core kernel with fp32 atomics.  stl_conv_wgrad_naive forces the CUDA-core kernel (validation). */
+ * the slabs in a fixed order, so the result is deterministic.  Other shapes (native stride 2, the 3-channel stem,
+ * HRNet-W48's channel counts) use a CUDA-core kernel built the same way: per-block slabs of partial sums in `workspace`
+ * and a fixed-order second pass - no floating-point atomics anywhere, every gradient is bit-reproducible.
+ * stl_conv_wgrad_naive forces the CUDA-core kernel (validation; its workspace size comes from
+ * stl_conv_wgrad_naive_workspace_bytes). */
 size_t stl_conv_wgrad_workspace_bytes(int N, int Hi, int Wi, int Cin, int Cout, int ksize, int stride, int cin_real);
 int stl_conv_wgrad(const void* x, const void* dz, float* dw, int N, int Hi, int Wi, int Cin, int Cout, int ksize,
                    int stride, int cin_real, void* workspace, size_t workspace_bytes, void* stream);
+size_t stl_conv_wgrad_naive_workspace_bytes(int N, int Hi, int Wi, int Cin, int Cout, int ksize, int stride,
+                                            int cin_real);
 int stl_conv_wgrad_naive(const void* x, const void* dz, float* dw, int N, int Hi, int Wi, int Cin, int Cout, int ksize,
-                         int stride, int cin_real, void* stream);
+                         int stride, int cin_real, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

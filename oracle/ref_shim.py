@@ -6,8 +6,9 @@ architecture YAML lives outside the repo at a cwd-relative, file-name-fixed path
 (``models/HRnet.py:280-283``, ``CONFIG.py:14``).  This shim works around exactly those three
 things and nothing else; every FLOP still runs through the reference's own code.
 
-Used only by ``oracle/make_golden.py`` and by tests that are skipped when /root/reference is
-absent (it does not exist on the GPU box).
+Used only by ``oracle/make_golden.py``, by tests that are skipped when the reference is absent, and by
+``bench.py``'s reference arm / ``cpu_baseline`` leg.  On the GPU box /root/reference does not exist; the shim
+then imports the byte-for-byte copies that ``oracle/stage_ref.py`` placed under ``oracle/_ref/src``.
 """
 import copy
 import importlib
@@ -16,7 +17,20 @@ import sys
 import tempfile
 import types
 
-REF_SRC = os.environ.get("STLPOSE_REFERENCE_SRC", "/root/reference/src")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "src")   # oracle/stage_ref.py
+
+
+def _default_src():
+    """/root/reference/src in the build container; on the GPU box the byte-for-byte copies staged under oracle/_ref."""
+    env = os.environ.get("STLPOSE_REFERENCE_SRC")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/src/models/HRnet.py"):
+        return "/root/reference/src"
+    return _STAGED
+
+
+REF_SRC = _default_src()
 
 
 def available():

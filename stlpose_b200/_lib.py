@@ -103,7 +103,8 @@ PROTOTYPES = {
     "stl_conv_wgrad": (ctypes.c_int, [vp, vp, vp] + [ctypes.c_int] * 8 + [vp, ctypes.c_size_t, vp]),
     "stl_bn_workspace_floats": (ctypes.c_size_t, [ctypes.c_int]),
     "stl_zero_stuff": (ctypes.c_int, [vp, vp] + [ctypes.c_int] * 4 + [vp]),
-    "stl_conv_wgrad_naive": (ctypes.c_int, [vp, vp, vp] + [ctypes.c_int] * 8 + [vp]),
+    "stl_conv_wgrad_naive_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 8),
+    "stl_conv_wgrad_naive": (ctypes.c_int, [vp, vp, vp] + [ctypes.c_int] * 8 + [vp, ctypes.c_size_t, vp]),
 }
 
 _lib = None

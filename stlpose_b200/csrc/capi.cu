@@ -366,7 +366,8 @@ int stl_conv_dgrad(const void* dz, const void* w_packed, void* dx, int N, int Hi
 }
 
 size_t stl_conv_wgrad_workspace_bytes(int N, int Hi, int Wi, int Cin, int Cout, int ksize, int stride, int cin_real) {
-  if (!wgrad_tc_supported(Wi, Cin, Cout, cin_real, ksize, stride)) return 0;
+  if (!wgrad_tc_supported(Wi, Cin, Cout, cin_real, ksize, stride))
+    return conv_wgrad_naive_workspace_bytes(N, Hi, Wi, Cin, Cout, ksize, stride, cin_real);
   return wgrad_tc_workspace_bytes(N, Hi, Wi, Cin, Cout, ksize, cin_real);
 }
 
@@ -378,7 +379,7 @@ int stl_conv_wgrad(const void* x, const void* dz, float* dw, int N, int Hi, int 
     return wgrad_tc_launch((const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, dw, N, Hi, Wi, Cin, Cout, ksize, cin_real,
                            workspace, workspace_bytes, (cudaStream_t)stream);
   return conv_wgrad_naive((const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, dw, N, Hi, Wi, Cin, Cout, ksize, stride,
-                          cin_real, (cudaStream_t)stream);
+                          cin_real, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t stl_bn_workspace_floats(int C) { return bn_workspace_floats(C); }
@@ -389,12 +390,17 @@ int stl_zero_stuff(const void* dz, void* u, int N, int H, int W, int C, void* st
   return zero_stuff((const __nv_bfloat16*)dz, (__nv_bfloat16*)u, N, H, W, C, (cudaStream_t)stream);
 }
 
+size_t stl_conv_wgrad_naive_workspace_bytes(int N, int Hi, int Wi, int Cin, int Cout, int ksize, int stride,
+                                            int cin_real) {
+  return conv_wgrad_naive_workspace_bytes(N, Hi, Wi, Cin, Cout, ksize, stride, cin_real);
+}
+
 int stl_conv_wgrad_naive(const void* x, const void* dz, float* dw, int N, int Hi, int Wi, int Cin, int Cout, int ksize,
-                         int stride, int cin_real, void* stream) {
+                         int stride, int cin_real, void* workspace, size_t workspace_bytes, void* stream) {
   if (!have_device()) return 1;
   if (!x || !dz || !dw) { set_error("stl_conv_wgrad_naive: null pointer"); return 1; }
   return conv_wgrad_naive((const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, dw, N, Hi, Wi, Cin, Cout, ksize, stride,
-                          cin_real, (cudaStream_t)stream);
+                          cin_real, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

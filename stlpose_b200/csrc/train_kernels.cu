@@ -408,11 +408,12 @@ __global__ void __launch_bounds__(256) zero_stuff_kernel(const __nv_bfloat16* __
 // ------------------------------------------------------------------ CUDA-core convolution gradients
 // wgrad of the stem's first convolution (HRnet.py:286: 3 -> 64 channels, 3x3, stride 2): 1 728 outputs reduced over
 // N*Ho*Wo pixels.  Thread = (output channel, pixel lane); the 27 input values of a pixel are staged in shared memory
-// and broadcast, each thread keeps 27 fp32 accumulators; block partials are added with atomics (148*4 blocks).
+// and broadcast, each thread keeps 27 fp32 accumulators; every block writes its partial sums to its own slab of the
+// workspace and slab_sum_kernel adds the slabs in block order (bit-reproducible: no floating-point atomics).
 constexpr int kStemPix = 32;   // output pixels per block iteration
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const __nv_bfloat16* __restrict__ x,
                                                          const __nv_bfloat16* __restrict__ dz,
-                                                         float* __restrict__ dw, int N, int Hi, int Wi, int Cin,
+                                                         float* __restrict__ slabs, int N, int Hi, int Wi, int Cin,
                                                          int Cout, int cin_real, long long pix_total) {
   __shared__ float patch[kStemPix][28];
   const int Ho = Hi / 2, Wo = Wi / 2, Wip = Wi + 1, Hip = Hi + 1, Wop = Wo + 1, Hop = Ho + 1;
@@ -450,9 +451,28 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const __nv_bfloat16* __
   for (int i = threadIdx.x; i < 64 * 27; i += 256) {
     const int c = i / 27, r = i % 27, tap = r / 3, ci = r % 3;
     if (ci >= cin_real) continue;
-    const float v = red[0][c][r] + red[1][c][r] + red[2][c][r] + red[3][c][r];
-    atomicAdd(dw + ((size_t)c * cin_real + ci) * 9 + tap, v);
+    const float v = (red[0][c][r] + red[1][c][r]) + (red[2][c][r] + red[3][c][r]);
+    slabs[(size_t)blockIdx.x * (64 * cin_real * 9) + ((size_t)c * cin_real + ci) * 9 + tap] = v;
   }
+}
+
+// out[i] = sum over slabs s (ascending) of slabs[s][i]: the fixed-order second pass of the CUDA-core weight gradients.
+// Four independent partial sums keep four loads in flight; the grouping is a function of n_slabs only.
+__global__ void __launch_bounds__(256) slab_sum_kernel(const float* __restrict__ slabs, float* __restrict__ out, int n,
+                                                       int n_slabs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* src = slabs + i;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int sp = 0;
+  for (; sp + 3 < n_slabs; sp += 4) {
+    a0 += __ldcg(src + (size_t)sp * n);
+    a1 += __ldcg(src + (size_t)(sp + 1) * n);
+    a2 += __ldcg(src + (size_t)(sp + 2) * n);
+    a3 += __ldcg(src + (size_t)(sp + 3) * n);
+  }
+  for (; sp < n_slabs; ++sp) a0 += __ldcg(src + (size_t)sp * n);
+  out[i] = (a0 + a1) + (a2 + a3);
 }
 
 
@@ -503,12 +523,13 @@ __global__ void __launch_bounds__(128) conv_dgrad_kernel(const __nv_bfloat16* __
 
 // wgrad: dW[co][ci][kh][kw] = sum_{n,ho,wo} dz[n,ho,wo,co] * x[n,ho*s+kh-pad,wo*s+kw-pad,ci]   (fp32, OIHW)
 // Block = one (tap, 16 x 16 (co, ci) tile) x one slice of the pixels; 256 threads = the 16 x 16 tile, each thread
-// walks its pixel slice with both operands staged in shared memory 64 pixels at a time; partial sums are added to
-// dW with atomics (the slices of one tile live in different blocks).
+// walks its pixel slice with both operands staged in shared memory 64 pixels at a time; the slices of one tile live in
+// different blocks, each writes its partial sums into slab `slice` of the workspace (every element of a slab is written
+// by exactly one thread) and slab_sum_kernel adds the slabs in slice order: bit-reproducible, no atomics.
 constexpr int kWgPix = 64;
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __nv_bfloat16* __restrict__ x,
                                                          const __nv_bfloat16* __restrict__ dz,
-                                                         float* __restrict__ dw, int N, int Hi, int Wi, int Cin,
+                                                         float* __restrict__ slabs, int N, int Hi, int Wi, int Cin,
                                                          int Cout, int k, int stride, int cin_real, int slices) {
   const int Ho = Hi / stride, Wo = Wi / stride, pad = k / 2, taps = k * k;
   const int ci_tiles = Cin / 16, co_tiles = Cout / 16;
@@ -548,7 +569,8 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __nv_bfloat16* __
     __syncthreads();
   }
   const int co = cot * 16 + tco, ci = cit * 16 + tci;
-  if (ci < cin_real) atomicAdd(dw + ((size_t)co * cin_real + ci) * taps + tap, acc);
+  if (ci < cin_real)
+    slabs[(size_t)slice * ((size_t)Cout * cin_real * taps) + ((size_t)co * cin_real + ci) * taps + tap] = acc;
 }
 
 // Grid for a 256-thread grid-stride kernel over `total` items whose stride (grid * 256) must be a multiple of `c8n`
@@ -664,24 +686,52 @@ int zero_stuff(const __nv_bfloat16* dz, __nv_bfloat16* u, int N, int H, int W, i
   return check("zero_stuff");
 }
 
-int conv_wgrad_naive(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, int N, int Hi, int Wi, int Cin,
-                     int Cout, int k, int stride, int cin_real, cudaStream_t st) {
-  if (Cin % 16 || Cout % 16) { set_error("conv_wgrad: channels must be multiples of 16"); return 1; }
-  if (k == 3 && stride == 2 && Cout == 64 && cin_real <= 3) {      // the stem's first convolution
-    const long long pix = (long long)N * (Hi / 2) * (Wi / 2);
-    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * cin_real * 9, st);
-    stem_wgrad_kernel<<<grid_for(pix, kStemPix, 148 * 4), 256, 0, st>>>(x, dz, dw, N, Hi, Wi, Cin, Cout, cin_real, pix);
-    return check("stem_wgrad");
-  }
+namespace {
+bool is_stem_wgrad(int Cout, int k, int stride, int cin_real) { return k == 3 && stride == 2 && Cout == 64 && cin_real <= 3; }
+int stem_wgrad_blocks(long long pix) { return grid_for(pix, kStemPix, 148 * 4); }
+int wgrad_slices(long long pix, int Cin, int Cout, int k) {
   const int tiles = k * k * (Cin / 16) * (Cout / 16);
-  const long long pix = (long long)N * (Hi / stride) * (Wi / stride);
   int slices = (148 * 8 + tiles - 1) / tiles;
   const long long max_slices = (pix + 4 * kWgPix - 1) / (4 * kWgPix);
   if (slices > max_slices) slices = (int)max_slices;
-  if (slices < 1) slices = 1;
-  cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * cin_real * k * k, st);
-  conv_wgrad_kernel<<<tiles * slices, 256, 0, st>>>(x, dz, dw, N, Hi, Wi, Cin, Cout, k, stride, cin_real, slices);
-  return check("conv_wgrad");
+  return slices < 1 ? 1 : slices;
+}
+}  // namespace
+
+size_t conv_wgrad_naive_workspace_bytes(int N, int Hi, int Wi, int Cin, int Cout, int k, int stride, int cin_real) {
+  if (stride < 1 || k < 1) return 0;
+  const long long pix = (long long)N * (Hi / stride) * (Wi / stride);
+  const size_t n = (size_t)Cout * cin_real * k * k;
+  const int slabs = is_stem_wgrad(Cout, k, stride, cin_real) ? stem_wgrad_blocks(pix) : wgrad_slices(pix, Cin, Cout, k);
+  return sizeof(float) * n * slabs;
+}
+
+int conv_wgrad_naive(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, int N, int Hi, int Wi, int Cin,
+                     int Cout, int k, int stride, int cin_real, void* workspace, size_t workspace_bytes,
+                     cudaStream_t st) {
+  if (Cin % 16 || Cout % 16) { set_error("conv_wgrad: channels must be multiples of 16"); return 1; }
+  const size_t need = conv_wgrad_naive_workspace_bytes(N, Hi, Wi, Cin, Cout, k, stride, cin_real);
+  if (!workspace || workspace_bytes < need) {
+    set_error("conv_wgrad: workspace of %zu bytes required (stl_conv_wgrad_workspace_bytes), got %zu", need,
+              workspace_bytes);
+    return 1;
+  }
+  float* slabs = static_cast<float*>(workspace);
+  const int n = Cout * cin_real * k * k;
+  const long long pix = (long long)N * (Hi / stride) * (Wi / stride);
+  int n_slabs;
+  if (is_stem_wgrad(Cout, k, stride, cin_real)) {      // the stem's first convolution
+    n_slabs = stem_wgrad_blocks(pix);
+    stem_wgrad_kernel<<<n_slabs, 256, 0, st>>>(x, dz, slabs, N, Hi, Wi, Cin, Cout, cin_real, pix);
+    if (check("stem_wgrad")) return 1;
+  } else {
+    const int tiles = k * k * (Cin / 16) * (Cout / 16);
+    n_slabs = wgrad_slices(pix, Cin, Cout, k);
+    conv_wgrad_kernel<<<tiles * n_slabs, 256, 0, st>>>(x, dz, slabs, N, Hi, Wi, Cin, Cout, k, stride, cin_real, n_slabs);
+    if (check("conv_wgrad")) return 1;
+  }
+  slab_sum_kernel<<<(n + 255) / 256, 256, 0, st>>>(slabs, dw, n, n_slabs);
+  return check("wgrad slab sum");
 }
 
 }  // namespace stl

@@ -21,8 +21,11 @@ int upsample_backward(const __nv_bfloat16* g, __nv_bfloat16* dlow, int N, int H,
 int zero_stuff(const __nv_bfloat16* dz, __nv_bfloat16* u, int N, int H, int W, int C, cudaStream_t st);
 int conv_dgrad_naive(const __nv_bfloat16* dz, const __nv_bfloat16* w_packed, __nv_bfloat16* dx, int N, int Hi, int Wi,
                      int Cin, int Cout, int k, int stride, cudaStream_t st);
+// CUDA-core weight gradient: per-block slabs of partial sums in `workspace`, added in a fixed order (deterministic)
+size_t conv_wgrad_naive_workspace_bytes(int N, int Hi, int Wi, int Cin, int Cout, int k, int stride, int cin_real);
 int conv_wgrad_naive(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, int N, int Hi, int Wi, int Cin,
-                     int Cout, int k, int stride, int cin_real, cudaStream_t st);
+                     int Cout, int k, int stride, int cin_real, void* workspace, size_t workspace_bytes,
+                     cudaStream_t st);
 
 // tcgen05 weight gradient for stride-1 convolutions (wgrad_tc.cu)
 bool wgrad_tc_supported(int W, int cin, int cout, int cin_real, int k, int stride);

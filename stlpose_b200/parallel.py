@@ -114,6 +114,7 @@ class GradientReducer:
         self._pending = [0] * len(self.buckets)
         self._works = []
         self._hooks = []
+        self._events = {}          # id(param) -> event recorded on the stream that accumulated its gradient
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
 
     # ---- one bucket: pack (scaled) -> all-reduce -> unpack
@@ -122,6 +123,13 @@ class GradientReducer:
         views = list(torch.split(flat, [p.numel() for p in bucket]))
         grads = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in bucket]
         if self.comm_stream is not None:
+            # The gradients of one bucket are accumulated on different streams (module branches and fuse rows run side
+            # by side, training._branch_stream): wait for the event each parameter's hook recorded on ITS stream, not
+            # only for the stream of the bucket's last gradient.
+            for p in bucket:
+                ev = self._events.pop(id(p), None)
+                if ev is not None:
+                    self.comm_stream.wait_event(ev)
             self.comm_stream.wait_stream(torch.cuda.current_stream(flat.device))
             ctx = torch.cuda.stream(self.comm_stream)
         else:
@@ -165,6 +173,10 @@ class GradientReducer:
 
         def hook(p):
             i = self.bucket_of[id(p)]
+            if self.comm_stream is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(p.device))
+                self._events[id(p)] = ev
             self._pending[i] -= 1
             if self._pending[i] == 0:
                 self._launch(i)

@@ -437,6 +437,14 @@ def _hr_module(mod, xs):
         for sj in streams:
             if sj is not si:
                 si.wait_stream(sj)
+    if forked:
+        # Branch outputs are allocated on their branch's stream and read by the fuse rows on every other stream; tell the
+        # caching allocator, so that a block is never handed out again on its home stream while a kernel queued on
+        # another stream still reads it (the event waits above order the kernels, record_stream orders the memory reuse).
+        for j, t in enumerate(xs):
+            for si in streams:
+                if si is not (streams[j] if j < len(streams) else main):
+                    t.record_stream(si)
     outs = []
     for i, row in enumerate(mod.fuse_layers):
         with torch.cuda.stream(streams[i] if i < len(streams) else main):
@@ -454,4 +462,7 @@ def _hr_module(mod, xs):
             outs.append(_FuseSum.apply(len(same), shifts, *same, *ups))
     for st in forked:
         main.wait_stream(st)
+    for i, t in enumerate(outs):                                     # rows computed on a branch stream are consumed on main
+        if 0 < i < len(streams):
+            t.record_stream(main)
     return outs

@@ -181,9 +181,13 @@ def test_stride1_wgrad_on_tensor_cores(cin, cout, k, hw, n):
     _lib.check(L.stl_conv_wgrad(_lib.ptr(xp), _lib.ptr(dzp), _lib.ptr(dw2), n, h, w, cin, cout, k, 1, cin,
                                 _lib.ptr(ws), wsb, _lib.current_stream()))
     assert torch.equal(dw, dw2)                          # fixed-order reduction: bit-reproducible
-    dn = torch.empty_like(dw)
-    _lib.check(L.stl_conv_wgrad_naive(_lib.ptr(xp), _lib.ptr(dzp), _lib.ptr(dn), n, h, w, cin, cout, k, 1, cin,
-                                      _lib.current_stream()))
+    dn, dn2 = torch.empty_like(dw), torch.empty_like(dw)
+    nwb = L.stl_conv_wgrad_naive_workspace_bytes(n, h, w, cin, cout, k, 1, cin)
+    nws = torch.empty(nwb, dtype=torch.uint8, device=DEV)
+    for out in (dn, dn2):
+        _lib.check(L.stl_conv_wgrad_naive(_lib.ptr(xp), _lib.ptr(dzp), _lib.ptr(out), n, h, w, cin, cout, k, 1, cin,
+                                          _lib.ptr(nws), nwb, _lib.current_stream()))
+    assert torch.equal(dn, dn2)                          # per-block slabs + fixed-order sum: bit-reproducible too
     scale = wr.grad.abs().max().item()
     assert (dn - wr.grad).abs().max().item() < 1e-3 * scale
     err = (dw - wr.grad).abs().max().item()
