@@ -74,16 +74,37 @@ class ShardedKeypointInference:
         return gather_keypoints(preds, maxvals, n, self.group)
 
 
+class _Sink:
+    """Where the training kernels write one parameter gradient (or a BatchNorm's dbeta | dgamma pair): a view into a flat
+    bucket of a bound GradientReducer.  ``done()`` is called by the layer's backward once the kernels that fill the view
+    are enqueued on the current stream."""
+    __slots__ = ("reducer", "bucket", "view", "count")
+
+    def __init__(self, reducer, bucket, view, count):
+        self.reducer, self.bucket, self.view, self.count = reducer, bucket, view, count
+
+    def done(self):
+        self.reducer._written(self.bucket, self.count)
+
+
 class GradientReducer:
     """The one exchange step of data-parallel fine-tuning (replaces DataParallel's replicate / gather / reduce of
     02_train.py:109,203-218): every rank runs forward + backward on its own slice of the batch with its own BatchNorm
     batch statistics (as DataParallel's replicas do), then the parameter gradients are summed over the ranks.
 
     The reference computes ONE loss over the gathered batch (loss.py:87 averages over all B crops), so a rank that
-    averaged over its B_r local crops contributes its gradient scaled by B_r / B.  Gradients are packed into flat fp32
-    buckets in reverse parameter order (the order backward produces them) and each bucket is all-reduced as soon as
-    its last gradient exists (``attach_hooks``: overlaps the remaining backward kernels), or all at once after a
-    graph-replayed backward (``reduce_all``).  Works on NCCL (CUDA) and gloo (CPU) process groups.
+    averaged over its B_r local crops contributes its gradient scaled by B_r / B (``scale``).  Gradients live in flat
+    fp32 buckets in reverse parameter order (the order backward produces them).  Two ways to use it:
+
+    * **bound** (``bind(model)``, what ``TrainStep`` does): every ``p.grad`` IS a view into its bucket and the training
+      kernels write there directly (training._ConvBN / _Head), so there is no pack or unpack copy; the layer that fills
+      the last view of a bucket forks the communication stream, which all-reduces the bucket (``ncclAllReduce`` over
+      NVLink) while the rest of backward keeps running - also inside a captured CUDA graph.  The caller scales the loss
+      gradient by ``scale`` (``loss.backward(gradient=reducer.scale_tensor)``) and calls ``finish_backward()`` after
+      ``loss.backward()``: the current stream then waits for the last bucket.
+    * **unbound** (any autograd graph, CPU/gloo included): ``attach_hooks()`` + ``finish_step()`` launch each bucket from
+      post-accumulate-grad hooks, or ``reduce_all()`` after backward; gradients are packed into the buckets, scaled,
+      all-reduced and copied back.
 
     BatchNorm running statistics are not exchanged: like the reference, which keeps the statistics of GPU 0's
     replica, every rank keeps its own and rank 0's are the ones to checkpoint.
@@ -98,13 +119,15 @@ class GradientReducer:
         if self.world > 1:
             dist.all_reduce(total, group=group)
         self.scale = float(local_batch) / float(total.item())
+        self.scale_tensor = torch.tensor(self.scale, dtype=torch.float32, device=dev)
         self.global_batch = int(round(total.item()))
-        # buckets in reverse registration order
+        # buckets in reverse registration order; a bucket only ends after a weight tensor (ndim > 1), so a BatchNorm's
+        # (bias, weight) pair - adjacent in this order - is never split and can be written as one dbeta | dgamma block
         self.buckets, cur, cur_bytes = [], [], 0
         for p in reversed(self.params):
             cur.append(p)
             cur_bytes += p.numel() * 4
-            if cur_bytes >= bucket_bytes:
+            if cur_bytes >= bucket_bytes and p.dim() > 1:
                 self.buckets.append(cur)
                 cur, cur_bytes = [], 0
         if cur:
@@ -115,9 +138,86 @@ class GradientReducer:
         self._works = []
         self._hooks = []
         self._events = {}          # id(param) -> event recorded on the stream that accumulated its gradient
+        self._bound = None
+        self._bucket_events = [[] for _ in self.buckets]
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
 
-    # ---- one bucket: pack (scaled) -> all-reduce -> unpack
+    def views(self, i):
+        """Per-parameter views (shaped like the parameters) of bucket i."""
+        bucket = self.buckets[i]
+        return [v.view_as(p) for p, v in zip(bucket, torch.split(self.flat[i], [p.numel() for p in bucket]))]
+
+    # ---- bound mode: p.grad is a view of its bucket, kernels write there, buckets are reduced as they fill up
+    def bind(self, model):
+        """Make every parameter's ``.grad`` a view into its bucket and tell the training path of ``model``
+        (stlpose_b200.training) to write parameter gradients there.  Requires all parameters of ``model`` to be in
+        this reducer (a frozen parameter would leave its layer half bound)."""
+        if self.comm_stream is None:
+            raise RuntimeError("GradientReducer.bind needs CUDA parameters")
+        mine = {id(p) for p in self.params}
+        missing = [n for n, p in model.named_parameters() if id(p) not in mine]
+        if missing:
+            raise ValueError(f"GradientReducer.bind: parameters outside the reducer, e.g. {missing[:3]}")
+        offset = {}
+        self._views = [self.views(i) for i in range(len(self.buckets))]
+        for i, bucket in enumerate(self.buckets):
+            off = 0
+            for p, v in zip(bucket, self._views[i]):
+                p.grad = v
+                p._stl_sink = _Sink(self, i, v, 1)
+                offset[id(p)] = (i, off)
+                off += p.numel()
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d) and m.weight is not None:
+                (ib, ob), (iw, ow) = offset[id(m.bias)], offset[id(m.weight)]
+                c = m.bias.numel()
+                if ib != iw or ow != ob + c:
+                    raise ValueError("GradientReducer.bind: a BatchNorm's bias and weight are not adjacent in a bucket")
+                m.bias._stl_sink = _Sink(self, ib, self.flat[ib][ob:ob + 2 * c], 2)       # dbeta | dgamma in one block
+                m.weight._stl_sink = None
+        self._bound = model
+        self._pending = [len(b) for b in self.buckets]
+        return self
+
+    def unbind(self):
+        if self._bound is not None:
+            for p in self.params:
+                if hasattr(p, "_stl_sink"):
+                    del p._stl_sink
+                p.grad = None
+            self._bound = None
+
+    def _written(self, i, count):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.flat[i].device))
+        self._bucket_events[i].append(ev)
+        self._pending[i] -= count
+        if self._pending[i] == 0:
+            with torch.cuda.stream(self.comm_stream):
+                for e in self._bucket_events[i]:       # the views of a bucket are filled on several streams
+                    self.comm_stream.wait_event(e)
+                if self.world > 1:
+                    dist.all_reduce(self.flat[i], group=self.group)
+            self._bucket_events[i] = []
+        elif self._pending[i] < 0:
+            raise RuntimeError("GradientReducer: a gradient was written twice in one step (finish_backward() not called?)")
+
+    def finish_backward(self):
+        """After ``loss.backward()`` of a bound model: every bucket has been launched; the current stream waits for
+        the communication stream, so that ``optimizer.step()`` may follow."""
+        left = [i for i, n in enumerate(self._pending) if n != 0]
+        self._pending = [len(b) for b in self.buckets]
+        if left:
+            for ev in self._bucket_events:
+                ev.clear()
+            raise RuntimeError(f"GradientReducer: {len(left)} gradient bucket(s) were not filled by this backward pass")
+        torch.cuda.current_stream(self.flat[0].device).wait_stream(self.comm_stream)
+        for bucket, views in zip(self.buckets, self._views):      # an optimizer.zero_grad(set_to_none=True) in between
+            for p, v in zip(bucket, views):
+                if p.grad is None:
+                    p.grad = v
+
+    # ---- unbound mode, one bucket: pack (scaled) -> all-reduce -> unpack
     def _launch(self, i):
         bucket, flat = self.buckets[i], self.flat[i]
         views = list(torch.split(flat, [p.numel() for p in bucket]))
@@ -160,15 +260,22 @@ class GradientReducer:
                 torch._foreach_copy_(dst, src)       # one multi-tensor launch per bucket instead of one copy per parameter
         self._works = []
 
+    def _check_unbound(self):
+        if self._bound is not None:
+            raise RuntimeError("GradientReducer is bound to a model (gradients are reduced during backward); "
+                               "use finish_backward(), or unbind() first")
+
     def reduce_all(self):
-        """All buckets, after backward has finished (graph-replayed steps)."""
+        """All buckets, after backward has finished (unbound mode)."""
+        self._check_unbound()
         for i in range(len(self.buckets)):
             self._launch(i)
         self._finish()
 
     def attach_hooks(self):
-        """Eager steps: all-reduce each bucket as soon as backward has produced its last gradient; call
+        """Eager steps (unbound mode): all-reduce each bucket as soon as backward has produced its last gradient; call
         ``finish_step()`` after ``loss.backward()`` and before ``optimizer.step()``."""
+        self._check_unbound()
         self._pending = [len(b) for b in self.buckets]
 
         def hook(p):

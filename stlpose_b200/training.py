@@ -204,13 +204,14 @@ def conv_wgrad(x, dz, weight_shape, n, h, w, stride):
     return dw if dw.shape[0] == weight_shape[0] else dw[:weight_shape[0]].contiguous()
 
 
-def _conv_wgrad(x, dz, weight_shape, n, h, w, stride, side=None):
+def _conv_wgrad(x, dz, weight_shape, n, h, w, stride, side=None, out=None):
     """-> (dw with cout_pad rows, workspace to keep alive).  side: a stream to launch on; the buffers are still allocated
-    on the current stream and the caller joins the side stream before dw is used or the workspace released."""
+    on the current stream and the caller joins the side stream before dw is used or the workspace released.
+    out: fp32 [cout_pad, cin_real, k, k] destination (a view into a gradient bucket) instead of a fresh tensor."""
     L = _lib.lib()
     cout, cin_real, k, _ = weight_shape
     cin_pad, cout_pad = x.shape[3], dz.shape[3]
-    dw = torch.empty((cout_pad, cin_real, k, k), dtype=torch.float32, device=x.device)
+    dw = out if out is not None else torch.empty((cout_pad, cin_real, k, k), dtype=torch.float32, device=x.device)
     stuffed = dz.shape[1] == h + 1
     if stride == 2 and not stuffed and cin_pad % 32 == 0 and cout_pad % 32 == 0:
         dz, stuffed = zero_stuff(dz, n, h, w), True
@@ -245,7 +246,7 @@ class _ConvBN(torch.autograd.Function):
     """conv (no bias) + train-mode BatchNorm [+ residual] [+ ReLU] on padded bf16 activations."""
 
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, residual, run_mean, run_var, stride, relu, momentum, tickets):
+    def forward(ctx, x, weight, gamma, beta, residual, run_mean, run_var, stride, relu, momentum, tickets, sinks=None):
         L = _lib.lib()
         n, hp, wpd, cin_pad = x.shape
         h, w = hp - 1, wpd - 1
@@ -263,6 +264,7 @@ class _ConvBN(torch.autograd.Function):
                                                  _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(run_mean), _lib.ptr(run_var),
                                                  tickets.data_ptr(), _stream()))
         ctx.tickets = tickets
+        ctx.sinks = sinks
         ctx.save_for_backward(x, weight, z, y, mean, rstd, g32)
         ctx.meta = (n, h, w, cin_pad, cin_real, cout, k, stride, bool(relu), residual is not None)
         return y
@@ -277,32 +279,46 @@ class _ConvBN(torch.autograd.Function):
         dz = torch.empty_like(z)
         dres = torch.empty_like(z) if has_res else None
         ws = torch.empty(L.stl_bn_workspace_floats(cout), dtype=torch.float32, device=x.device)
-        sums = torch.empty(2 * cout, dtype=torch.float32, device=x.device)     # dbeta | dgamma, returned as views
+        # parameter gradients: fresh tensors handed to autograd, or - when the parameters are bound to a gradient bucket
+        # (parallel.GradientReducer.bind) - written straight into the bucket by the kernels, nothing returned
+        wsink, bsink = ctx.sinks if ctx.sinks is not None else (None, None)
+        sums = bsink.view if bsink is not None else torch.empty(2 * cout, dtype=torch.float32, device=x.device)   # dbeta | dgamma
         _lib.check(L.stl_bn_train_backward_ticket(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(z), _lib.ptr(mean), _lib.ptr(rstd),
                                                   _lib.ptr(g32), int(relu), n, ho, wo, cout, _lib.ptr(dz), _lib.ptr(dres),
                                                   _lib.ptr(sums), _lib.ptr(ws), ctx.tickets.data_ptr() + 4, _stream()))
         dbeta, dgamma = sums[:cout], sums[cout:]
+        if bsink is not None:
+            bsink.done()
         if stride == 2 and cin_pad % 32 == 0:
             dz = zero_stuff(dz, n, h, w)               # shared by dgrad and wgrad
         # dgrad (main stream) and wgrad (side stream) both only need dz: two parallel branches of the step
         side = _side_stream(x.device) if (SIDE_WGRAD and ctx.needs_input_grad[0]) else None
-        dw, keep = _conv_wgrad(x, dz, weight.shape, n, h, w, stride, side=side)
+        direct = wsink is not None and dz.shape[3] == cout
+        dw, keep = _conv_wgrad(x, dz, weight.shape, n, h, w, stride, side=side, out=wsink.view if direct else None)
         dx = conv_dgrad(dz, weight, n, h, w, cin_pad, stride) if ctx.needs_input_grad[0] else None
         if side is not None:
             torch.cuda.current_stream(x.device).wait_stream(side)       # join before dw / the workspace are touched again
         del keep
+        if wsink is not None:
+            if not direct:
+                wsink.view.copy_(dw[:cout])
+            wsink.done()
+            return dx, None, None if bsink is not None else dgamma, None if bsink is not None else dbeta, dres, \
+                None, None, None, None, None, None, None
         if dw.shape[0] != cout:
             dw = dw[:cout].contiguous()
-        return dx, dw, dgamma, dbeta, dres, None, None, None, None, None, None
+        return dx, dw, None if bsink is not None else dgamma, None if bsink is not None else dbeta, dres, \
+            None, None, None, None, None, None, None
 
 
 class _Head(torch.autograd.Function):
     """final_layer: 1x1 conv with bias, no activation, fp32 NCHW out (HRnet.py:331-337, 466)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, sinks=None):
         n, hp, wpd, cin = x.shape
         cout = weight.shape[0]
+        ctx.sinks = sinks
         wp, bp, cout_pad = _pack_weights(weight, cin, own_bias=True)
         bp[:cout] = bias.detach().float()
         heat = _conv_raw(x, wp, bp, cout, cout_pad, 1, 1, out_nchw=True)
@@ -320,7 +336,15 @@ class _Head(torch.autograd.Function):
         _lib.check(L.stl_nchw_to_padded(_lib.ptr(dheat), _lib.ptr(dz), n, cout, h, w, cout_pad, _stream()))
         dx = conv_dgrad(dz, weight, n, h, w, cin, 1)
         dw = conv_wgrad(x, dz, weight.shape, n, h, w, 1)
-        return dx, dw, dheat.sum(dim=(0, 2, 3))
+        db = dheat.sum(dim=(0, 2, 3))
+        if ctx.sinks is not None:                      # parameters bound to a gradient bucket (see _ConvBN.backward)
+            wsink, bsink = ctx.sinks
+            wsink.view.copy_(dw)
+            bsink.view.copy_(db)
+            wsink.done()
+            bsink.done()
+            return dx, None, None, None
+        return dx, dw, db, None
 
 
 class _FuseSum(torch.autograd.Function):
@@ -368,9 +392,20 @@ def _tickets(bn, device):
     return t
 
 
+def _sinks(weight, bias):
+    """Gradient destinations of a (conv weight, BatchNorm bias [+ weight]) or (head weight, head bias) pair when the
+    parameters are bound to a gradient bucket (parallel.GradientReducer.bind), else None."""
+    ws, bs = getattr(weight, "_stl_sink", None), getattr(bias, "_stl_sink", None)
+    if ws is None and bs is None:
+        return None
+    if ws is None or bs is None:
+        raise _lib.StlError("gradient buckets are bound to only part of a layer's parameters (GradientReducer.bind)")
+    return ws, bs
+
+
 def _convbn(x, conv, bn, stride, relu, residual=None):
     return _ConvBN.apply(x, conv.weight, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, stride, relu,
-                         bn.momentum, _tickets(bn, x.device))
+                         bn.momentum, _tickets(bn, x.device), _sinks(conv.weight, bn.bias))
 
 
 def train_forward(model, x):
@@ -411,7 +446,8 @@ def train_forward(model, x):
                 xs.append(_convbn(xs[-1], seq[0], seq[1], 2, True))
             for mod in getattr(model, f"stage{stage}"):
                 xs = _hr_module(mod, xs)
-        return _Head.apply(xs[0], model.final_layer.weight, model.final_layer.bias)
+        return _Head.apply(xs[0], model.final_layer.weight, model.final_layer.bias,
+                           _sinks(model.final_layer.weight, model.final_layer.bias))
 
 
 def _hr_module(mod, xs):

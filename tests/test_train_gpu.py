@@ -208,6 +208,72 @@ def test_graph_captured_step_matches_eager_steps():
     assert _rel(m_graph(xs).cpu(), m_eager(xs).cpu()) < 5e-2
 
 
+def test_bound_gradient_buckets_give_the_same_step():
+    """TrainStep with a GradientReducer bound to the model (kernels write parameter gradients straight into the flat
+    buckets, which are handed to the communication stream as backward fills them; one process: no collective) must leave
+    bit-identical parameters to the plain TrainStep, whose gradients go through autograd's accumulation nodes."""
+    from stlpose_b200.parallel import GradientReducer
+    S, sd0, x, tgt, tw, m_a = _setup(B=4, seed=9)
+    m_b = S.PoseHighResolutionNet(width=32)
+    m_b.load_state_dict(sd0, strict=True)
+    m_b = m_b.cuda()
+    mk = lambda m: torch.optim.SGD(m.parameters(), lr=0.02, momentum=0.9, weight_decay=5e-4)
+    crit = S.PersonMSELoss()
+    red = GradientReducer(m_b.parameters(), local_batch=4, bucket_bytes=4 << 20)
+    assert len(red.buckets) > 4 and red.scale == 1.0
+    step_a = S.TrainStep(m_a, mk(m_a), crit, batch=4)
+    step_b = S.TrainStep(m_b, mk(m_b), crit, batch=4, reducer=red)
+    assert step_a.optimizer_in_graph and step_b.optimizer_in_graph
+    for _ in range(3):
+        la, lb = step_a(x, tgt, tw).item(), step_b(x, tgt, tw).item()
+        assert la == lb
+    sa, sb = m_a.state_dict(), m_b.state_dict()
+    bad = [k for k in sa if not torch.equal(sa[k], sb[k])]
+    assert not bad, f"{len(bad)} tensors differ, e.g. {bad[:3]}"
+    # every .grad is still a view of its bucket (nothing re-allocated them)
+    for bucket, flat in zip(red.buckets, red.flat):
+        lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+        assert all(lo <= p.grad.data_ptr() < hi for p in bucket)
+
+
+def test_scheduler_changes_reach_the_captured_optimizer():
+    """The captured optimizer step bakes lr / momentum / weight decay into its kernels: TrainStep keeps a
+    signature of param_groups and re-captures when a scheduler changes them.  lr = 0 must therefore freeze the
+    parameters, and restoring lr must move them again; training state survives the re-capture."""
+    S, sd0, x, tgt, tw, m = _setup(B=2, seed=4)
+    opt = torch.optim.SGD(m.parameters(), lr=0.05, weight_decay=5e-4)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.0)       # lib/model_setup.py: StepLR
+    step = S.TrainStep(m, opt, S.PersonMSELoss(), batch=2)
+    assert step.optimizer_in_graph and step.captures == 1
+    step(x, tgt, tw)
+    w1 = m.conv1.weight.detach().clone()
+    rv1 = m.bn1.running_var.detach().clone()
+    assert not torch.equal(w1.cpu(), sd0["conv1.weight"])
+    sched.step()                                                               # lr -> 0
+    step(x, tgt, tw)
+    assert step.captures == 2
+    assert torch.equal(m.conv1.weight.detach(), w1)                            # lr = 0: no update ...
+    assert not torch.equal(m.bn1.running_var, rv1)                             # ... but the step itself ran
+    assert int(m.bn1.num_batches_tracked) == 2                                 # warm-up of the re-capture did not count
+    for g in opt.param_groups:
+        g["lr"] = 0.05
+    step(x, tgt, tw)
+    assert step.captures == 3 and not torch.equal(m.conv1.weight.detach(), w1)
+
+
+def test_uncapturable_optimizers_step_after_the_replay():
+    """torch.optim.Adam(capturable=False) - the reference's other optimizer (lib/model_setup.py:141) - cannot be captured:
+    the graph then holds forward + loss + backward and the optimizer steps eagerly after each replay."""
+    S, sd0, x, tgt, tw, m = _setup(B=2, seed=6)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    step = S.TrainStep(m, opt, S.PersonMSELoss(), batch=2)
+    assert step.graph is not None and not step.optimizer_in_graph
+    assert len(opt.state) == 0                                                 # warm-up state was removed
+    losses = [step(x, tgt, tw).item() for _ in range(4)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    assert int(next(iter(opt.state.values()))["step"]) == 4
+
+
 def test_w48_train_step_runs_on_fallback_kernels():
     """HRNet-W48 channel counts (48/96/192/384) are outside the tensor-core wgrad kernel's shapes: the CUDA-core
     gradient kernels take over.  A few SGD steps on a small crop size must run, stay finite and reduce the loss, and the
@@ -241,33 +307,79 @@ def test_w48_train_step_runs_on_fallback_kernels():
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
 
 
+def _three_sgd_steps(monkeypatch, parallel, delay_seed=None):
+    """Three eager SGD steps on a side stream; parallel: module branches / fuse rows / weight gradients on their own
+    streams.  delay_seed: inject seeded device-side sleeps in front of random units (forward and backward) and on the
+    weight-gradient side stream, so that the interleaving of the streams differs from the undisturbed schedule."""
+    import random
+    from stlpose_b200 import training
+    monkeypatch.setattr(training, "BRANCH_STREAMS", parallel)
+    monkeypatch.setattr(training, "SIDE_WGRAD", parallel)
+    if delay_seed is not None:
+        rng = random.Random(delay_seed)
+
+        def nap(p=0.15, hi=400_000):
+            if rng.random() < p:
+                torch.cuda._sleep(rng.randrange(20_000, hi))        # on the current stream, 10-200 us
+
+        fwd, bwd, wg = training._convbn, training._ConvBN.backward, training._conv_wgrad
+
+        def convbn(*a, **k):
+            nap()
+            return fwd(*a, **k)
+
+        def backward(ctx, dy):
+            nap()
+            return bwd(ctx, dy)
+
+        def conv_wgrad(*a, side=None, **k):
+            if side is not None and rng.random() < 0.15:
+                with torch.cuda.stream(side):
+                    torch.cuda._sleep(rng.randrange(20_000, 400_000))
+            return wg(*a, side=side, **k)
+
+        monkeypatch.setattr(training, "_convbn", convbn)
+        monkeypatch.setattr(training._ConvBN, "backward", staticmethod(backward))
+        monkeypatch.setattr(training, "_conv_wgrad", conv_wgrad)
+    S, sd0, x, tgt, tw, m = _setup(B=6, seed=3)
+    m.train()
+    opt = torch.optim.SGD(m.parameters(), lr=1e-2, momentum=0.9, weight_decay=5e-4)
+    crit = S.PersonMSELoss()
+    xd, td, wd = x.cuda(), tgt.cuda().float(), tw.cuda()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                 # not the default stream (see TrainStep's note on accumulation nodes)
+        for _ in range(3):
+            loss = crit(S.forward_pass(m, xd, "HRNet", device="cuda", flip=False), td, wd)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            m.invalidate_packed_weights()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    monkeypatch.undo()
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}, float(loss.detach())
+
+
+def _assert_same_state(a, b):
+    (sa, la), (sb, lb) = a, b
+    assert la == lb
+    bad = [k for k in sa if not torch.equal(sa[k], sb[k])]
+    assert not bad, f"{len(bad)} tensors differ, e.g. {bad[:3]}"
+
+
 def test_parallel_streams_give_the_same_training_steps(monkeypatch):
     """The stream-parallel schedule (module branches and fuse rows side by side, weight gradients next to input
     gradients) only reorders independent launches: three eager SGD steps must leave bit-identical parameters and
-    running statistics to the same steps issued on one stream (all kernels are deterministic)."""
-    from stlpose_b200 import training
-    results = []
-    for parallel in (True, False):
-        monkeypatch.setattr(training, "BRANCH_STREAMS", parallel)
-        monkeypatch.setattr(training, "SIDE_WGRAD", parallel)
-        S, sd0, x, tgt, tw, m = _setup(B=6, seed=3)
-        m.train()
-        opt = torch.optim.SGD(m.parameters(), lr=1e-2, momentum=0.9, weight_decay=5e-4)
-        crit = S.PersonMSELoss()
-        xd, td, wd = x.cuda(), tgt.cuda().float(), tw.cuda()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):                 # not the default stream (see TrainStep's note on accumulation nodes)
-            for _ in range(3):
-                loss = crit(S.forward_pass(m, xd, "HRNet", device="cuda", flip=False), td, wd)
-                opt.zero_grad()
-                loss.backward()
-                opt.step()
-                m.invalidate_packed_weights()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        results.append(({k: v.detach().clone() for k, v in m.state_dict().items()}, float(loss.detach())))
-    (a, la), (b, lb) = results
-    assert la == lb
-    bad = [k for k in a if not torch.equal(a[k], b[k])]
-    assert not bad, f"{len(bad)} tensors differ, e.g. {bad[:3]}"
+    running statistics to the same steps issued on one stream.  Every training kernel is deterministic (fixed-order
+    slab reductions, no floating-point atomics), so any difference is a missing dependency between streams."""
+    _assert_same_state(_three_sgd_steps(monkeypatch, True), _three_sgd_steps(monkeypatch, False))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_parallel_streams_with_injected_delays(monkeypatch, seed):
+    """Race detector for the cross-stream hand-offs (compute-sanitizer is closed on the B200 pool, profiles/
+    r02_sanitizer.md): seeded device-side sleeps in front of random units and on the weight-gradient side stream change
+    which stream runs ahead; a read before its producer finished, or a block reused while another stream still reads it,
+    would change bits against the single-stream schedule."""
+    _assert_same_state(_three_sgd_steps(monkeypatch, True, delay_seed=seed), _three_sgd_steps(monkeypatch, False))

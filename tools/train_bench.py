@@ -67,13 +67,7 @@ def main():
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-            # exposed exchange time: the all-reduce runs after the replayed backward, nothing overlaps it
-            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(); dist.barrier(); x0.record()
-            for _ in range(5):
-                red.reduce_all()
-            x1.record(); torch.cuda.synchronize()
-            exch = round(x0.elapsed_time(x1) / 5, 3)
+            # (exposed exchange time: bench.py --workload train measures it against a collective-free replay)
         line = dict(workload=f"hrnet_w{a.width}_256x192 train step (fwd + PersonMSELoss + bwd + SGD)", graph=bool(a.graph),
                     batch=B * world, n_gpus=world, ms_per_step=round(ms, 2), crops_per_s=round(B * world / ms * 1e3, 1),
                     allreduce_ms=exch, fwd_ms=fwd, bwd_ms=bwd, opt_ms=upd,
