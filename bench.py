@@ -541,7 +541,7 @@ def run_decode(args):
     def step_e2e():
         for d, src in zip(stage, (hh_host, hf_host, c_host, s_host)):
             d.copy_(src, non_blocking=True)
-        preds, maxvals, _ = pose_parsing._decode(stage[0], stage[2], stage[3], True, heat_flipped=stage[1], pairs=FLIP_PAIRS)
+        preds, maxvals, _, _ = pose_parsing._decode(stage[0], stage[2], stage[3], True, heat_flipped=stage[1], pairs=FLIP_PAIRS)
         p_host.copy_(preds, non_blocking=True)
 
     ms_e2e, _, _ = h.timed(step_e2e, args.steps, max(args.warmup, 3))

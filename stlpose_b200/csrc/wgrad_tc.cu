@@ -249,11 +249,13 @@ int sm_count() {
 
 namespace {
 struct WgradShape { int m_real, R, nt, n_acc, per_kh; };
+// Channel counts that are not a power of two (HRNet-W48: 48 / 96 / 192 / 384) run on the next larger MMA shape: the TMA
+// boxes are 64 channels wide whatever the tensor's channel count, channels beyond it are out of bounds and arrive as
+// zeros, so the surplus accumulator rows / columns are zero and simply not written back (wgrad_reduce_kernel).
 bool wgrad_shape(int W, int cin, int cout, int cin_real, int k, int stride, WgradShape* o) {
   if (stride != 1 || (k != 1 && k != 3)) return false;
-  if (cout % 32 || cin % 32 || cin_real > cin) return false;
-  if (cout > 64 && cout % 128) return false;
-  o->m_real = cout < 128 ? cout : 128;
+  if (cout % 16 || cin % 16 || cout < 32 || cin < 32 || cin_real > cin) return false;
+  o->m_real = cout <= 32 ? 32 : (cout <= 64 ? 64 : 128);       // accumulator rows of one replica of dz
   o->R = 128 / o->m_real;
   // one CTA covers all nine taps when the halo'd x tile fits a TMA box (<= 256 rows); otherwise one filter row per CTA
   o->per_kh = k == 3 && (o->R == 1 || kKT + 2 * (W + 2) > 256);
@@ -261,8 +263,9 @@ bool wgrad_shape(int W, int cin, int cout, int cin_real, int k, int stride, Wgra
   else if (o->per_kh) o->n_acc = o->R >= 3 ? 1 : (o->R == 2 ? 2 : 3);
   else o->n_acc = o->R >= 3 ? 3 : 6;
   o->nt = 0;
-  for (int nt = 128; nt >= 32; nt /= 2)
-    if (nt <= cin && cin % nt == 0 && o->n_acc * nt <= 512) { o->nt = nt; break; }
+  const int want = cin <= 32 ? 32 : (cin <= 64 ? 64 : 128);    // input-channel columns per CTA (zero-filled past cin)
+  for (int nt = want; nt >= 32; nt /= 2)
+    if (o->n_acc * nt <= 512) { o->nt = nt; break; }
   return o->nt != 0;
 }
 }  // namespace
@@ -285,10 +288,10 @@ int wgrad_setup(int N, int H, int W, int cin, int cout, int k, int cin_real, Wgr
   const int R = sh.R;
   p.m_blks = (cout + 127) / 128;
   p.nt = sh.nt;
-  p.n_blks = cin / p.nt;
+  p.n_blks = (cin + p.nt - 1) / p.nt;
   p.n_acc = sh.n_acc;
-  p.pitch_a = (cout < 64 ? cout : 64) * 2;
-  p.pitch_b = (cin < 64 ? cin : 64) * 2;
+  p.pitch_a = (cout <= 32 ? 32 : 64) * 2;      // TMA box width in bytes = swizzle span (64 B or 128 B)
+  p.pitch_b = (cin <= 32 ? 32 : 64) * 2;
   p.a_panels = p.m_real > 64 ? 2 : 1;
   p.b_panels = p.nt > 64 ? 2 : 1;
   p.dz_rows = kKT + kLead;
@@ -390,8 +393,8 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, 
   p.ws = static_cast<float*>(workspace);
   p.dbg = getenv("STL_WGRAD_DBG") ? atoi(getenv("STL_WGRAD_DBG")) : 0;
   const long long P = (long long)N * (H + 1) * (W + 1);
-  if (encode_rows(&p.tmDz, dz, cout, P, cout < 64 ? cout : 64, p.dz_rows)) return 1;
-  if (encode_rows(&p.tmX, x, cin, P, cin < 64 ? cin : 64, p.x_rows)) return 1;
+  if (encode_rows(&p.tmDz, dz, cout, P, p.pitch_a / 2, p.dz_rows)) return 1;
+  if (encode_rows(&p.tmX, x, cin, P, p.pitch_b / 2, p.x_rows)) return 1;
   cudaError_t e;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   static bool attr = false;

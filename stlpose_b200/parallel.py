@@ -132,7 +132,17 @@ class GradientReducer:
                 cur, cur_bytes = [], 0
         if cur:
             self.buckets.append(cur)
-        self.flat = [torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=dev) for b in self.buckets]
+        # every parameter starts on a 16-byte boundary of its bucket (the kernels that write gradients there use float4
+        # stores); a BatchNorm's C-element bias and weight stay adjacent because C is a multiple of 4
+        self.offsets, sizes = [], []
+        for b in self.buckets:
+            offs, off = [], 0
+            for p in b:
+                offs.append(off)
+                off += (p.numel() + 3) // 4 * 4
+            self.offsets.append(offs)
+            sizes.append(off)
+        self.flat = [torch.zeros(n, dtype=torch.float32, device=dev) for n in sizes]
         self.bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
         self._pending = [0] * len(self.buckets)
         self._works = []
@@ -144,8 +154,8 @@ class GradientReducer:
 
     def views(self, i):
         """Per-parameter views (shaped like the parameters) of bucket i."""
-        bucket = self.buckets[i]
-        return [v.view_as(p) for p, v in zip(bucket, torch.split(self.flat[i], [p.numel() for p in bucket]))]
+        flat = self.flat[i]
+        return [flat[o:o + p.numel()].view_as(p) for p, o in zip(self.buckets[i], self.offsets[i])]
 
     # ---- bound mode: p.grad is a view of its bucket, kernels write there, buckets are reduced as they fill up
     def bind(self, model):
@@ -161,12 +171,10 @@ class GradientReducer:
         offset = {}
         self._views = [self.views(i) for i in range(len(self.buckets))]
         for i, bucket in enumerate(self.buckets):
-            off = 0
-            for p, v in zip(bucket, self._views[i]):
+            for p, v, off in zip(bucket, self._views[i], self.offsets[i]):
                 p.grad = v
                 p._stl_sink = _Sink(self, i, v, 1)
                 offset[id(p)] = (i, off)
-                off += p.numel()
         for m in model.modules():
             if isinstance(m, torch.nn.BatchNorm2d) and m.weight is not None:
                 (ib, ob), (iw, ow) = offset[id(m.bias)], offset[id(m.weight)]
@@ -220,7 +228,7 @@ class GradientReducer:
     # ---- unbound mode, one bucket: pack (scaled) -> all-reduce -> unpack
     def _launch(self, i):
         bucket, flat = self.buckets[i], self.flat[i]
-        views = list(torch.split(flat, [p.numel() for p in bucket]))
+        views = [v.reshape(-1) for v in self.views(i)]
         grads = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in bucket]
         if self.comm_stream is not None:
             # The gradients of one bucket are accumulated on different streams (module branches and fuse rows run side
@@ -246,16 +254,16 @@ class GradientReducer:
             if work is not None:
                 work.wait()          # NCCL: makes the current stream wait for the collective
             bucket, flat = self.buckets[i], self.flat[i]
-            views = torch.split(flat, [p.numel() for p in bucket])
+            views = self.views(i)
             if self.comm_stream is not None:
                 torch.cuda.current_stream(flat.device).wait_stream(self.comm_stream)
             dst, src = [], []
             for p, v in zip(bucket, views):
                 if p.grad is None:
-                    p.grad = v.view_as(p).clone()
+                    p.grad = v.clone()
                 else:
                     dst.append(p.grad)
-                    src.append(v.view_as(p))
+                    src.append(v)
             if dst:
                 torch._foreach_copy_(dst, src)       # one multi-tensor launch per bucket instead of one copy per parameter
         self._works = []

@@ -213,7 +213,7 @@ def _conv_wgrad(x, dz, weight_shape, n, h, w, stride, side=None, out=None):
     cin_pad, cout_pad = x.shape[3], dz.shape[3]
     dw = out if out is not None else torch.empty((cout_pad, cin_real, k, k), dtype=torch.float32, device=x.device)
     stuffed = dz.shape[1] == h + 1
-    if stride == 2 and not stuffed and cin_pad % 32 == 0 and cout_pad % 32 == 0:
+    if stride == 2 and not stuffed and cin_pad >= 32 and cout_pad >= 32:    # (the 3-channel stem stays on its own kernel)
         dz, stuffed = zero_stuff(dz, n, h, w), True
     s_eff = 1 if stuffed else stride
     ws_bytes = L.stl_conv_wgrad_workspace_bytes(n, h, w, cin_pad, cout_pad, k, s_eff, cin_real)
@@ -289,7 +289,7 @@ class _ConvBN(torch.autograd.Function):
         dbeta, dgamma = sums[:cout], sums[cout:]
         if bsink is not None:
             bsink.done()
-        if stride == 2 and cin_pad % 32 == 0:
+        if stride == 2 and cin_pad >= 32:
             dz = zero_stuff(dz, n, h, w)               # shared by dgrad and wgrad
         # dgrad (main stream) and wgrad (side stream) both only need dz: two parallel branches of the step
         side = _side_stream(x.device) if (SIDE_WGRAD and ctx.needs_input_grad[0]) else None

@@ -274,10 +274,11 @@ def test_uncapturable_optimizers_step_after_the_replay():
     assert int(next(iter(opt.state.values()))["step"]) == 4
 
 
-def test_w48_train_step_runs_on_fallback_kernels():
-    """HRNet-W48 channel counts (48/96/192/384) are outside the tensor-core wgrad kernel's shapes: the CUDA-core
-    gradient kernels take over.  A few SGD steps on a small crop size must run, stay finite and reduce the loss, and the
-    parameter gradients of one step must agree in direction with torch autograd of the same network in fp32."""
+def test_w48_train_step():
+    """HRNet-W48 channel counts (48/96/192/384) run on the tensor-core gradient kernels through the next larger MMA shape
+    (test_train_kernels_gpu.py checks those shapes one by one).  A few SGD steps on a small crop size must run, stay
+    finite and reduce the loss, and the parameter gradients of one step must agree in direction with torch autograd of
+    the same network in fp32."""
     import stlpose_b200 as S
     torch.manual_seed(0)
     m = S.PoseHighResolutionNet(width=48, image_size=(128, 96)).cuda().train()

@@ -160,7 +160,11 @@ def test_stride1_dgrad_on_tensor_cores(cin, cout, k, hw):
 @pytest.mark.parametrize("cin,cout,k,hw,n", [
     (32, 32, 3, (64, 48), 3), (64, 64, 3, (32, 24), 3), (128, 128, 3, (16, 12), 5), (256, 256, 3, (8, 6), 7),
     (64, 256, 1, (64, 48), 2), (256, 64, 1, (64, 48), 2), (256, 32, 3, (64, 48), 2), (128, 32, 1, (16, 12), 3),
-    (256, 128, 1, (8, 6), 3), (32, 32, 1, (64, 48), 2), (64, 64, 1, (64, 48), 1), (32, 32, 3, (16, 12), 1)])
+    (256, 128, 1, (8, 6), 3), (32, 32, 1, (64, 48), 2), (64, 64, 1, (64, 48), 1), (32, 32, 3, (16, 12), 1),
+    # HRNet-W48 channel counts (48 / 96 / 192 / 384): the next larger MMA shape, surplus channels zero-filled by TMA
+    (48, 48, 3, (96, 72), 2), (96, 96, 3, (48, 36), 2), (192, 192, 3, (24, 18), 3), (384, 384, 3, (12, 9), 3),
+    (256, 48, 3, (96, 72), 1), (96, 48, 1, (48, 36), 2), (384, 96, 1, (12, 9), 3), (192, 48, 1, (24, 18), 2),
+    (48, 32, 1, (96, 72), 1), (384, 192, 1, (12, 9), 2)])
 def test_stride1_wgrad_on_tensor_cores(cin, cout, k, hw, n):
     """stl_conv_wgrad (tcgen05, pixels as the reduction dimension) vs autograd and vs the CUDA-core kernel."""
     L = _lib.lib()
@@ -196,7 +200,9 @@ def test_stride1_wgrad_on_tensor_cores(cin, cout, k, hw, n):
 
 @pytest.mark.parametrize("cin,cout,hw,n", [(32, 64, (64, 48), 2), (64, 128, (32, 24), 3), (32, 32, (64, 48), 2),
                                            (128, 256, (16, 12), 3), (256, 64, (64, 48), 2), (64, 64, (128, 96), 2),
-                                           (32, 128, (32, 24), 2), (64, 256, (16, 12), 2), (32, 256, (16, 12), 2)])
+                                           (32, 128, (32, 24), 2), (64, 256, (16, 12), 2), (32, 256, (16, 12), 2),
+                                           (48, 96, (96, 72), 1), (96, 192, (48, 36), 2), (192, 384, (24, 18), 2),
+                                           (48, 48, (96, 72), 1), (96, 384, (48, 36), 1)])
 def test_stride2_gradients_via_zero_stuffing(cin, cout, hw, n):
     """Stride-2 3x3 layers: zero-stuffed dz + the stride-1 tensor-core dgrad / wgrad kernels vs autograd."""
     from stlpose_b200 import training
