@@ -614,6 +614,9 @@ def main():
                     help="32: HRNet-W32 256x192 (the configuration the metric is quoted on); 48: HRNet-W48 384x288")
     ap.add_argument("--dump-ops", default="", help="infer workload: write the per-launch timing table (JSON) here")
     args = ap.parse_args()
+    if os.environ.get("STL_BENCH_WATCHDOG"):             # debugging aid: dump every thread's stack and exit if the run hangs
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["STL_BENCH_WATCHDOG"]), exit=True)
     if args.workload == "train" and args.batch == 512 and not args.global_batch:
         args.batch = 32                                  # BASELINE config 4 / the reference's default batch per GPU
     if args.impl == "reference":

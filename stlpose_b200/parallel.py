@@ -99,9 +99,9 @@ class GradientReducer:
     * **bound** (``bind(model)``, what ``TrainStep`` does): every ``p.grad`` IS a view into its bucket and the training
       kernels write there directly (training._ConvBN / _Head), so there is no pack or unpack copy; the layer that fills
       the last view of a bucket forks the communication stream, which all-reduces the bucket (``ncclAllReduce`` over
-      NVLink) while the rest of backward keeps running - also inside a captured CUDA graph.  The caller scales the loss
-      gradient by ``scale`` (``loss.backward(gradient=reducer.scale_tensor)``) and calls ``finish_backward()`` after
-      ``loss.backward()``: the current stream then waits for the last bucket.
+      NVLink) while the rest of backward keeps running - also inside a captured CUDA graph.  The caller passes
+      ``loss.backward(gradient=reducer.scale_tensor)`` (the scale, when folding it into the loss gradient is exact) and
+      calls ``finish_backward()`` after ``loss.backward()``: the current stream then waits for the last bucket.
     * **unbound** (any autograd graph, CPU/gloo included): ``attach_hooks()`` + ``finish_step()`` launch each bucket from
       post-accumulate-grad hooks, or ``reduce_all()`` after backward; gradients are packed into the buckets, scaled,
       all-reduced and copied back.
@@ -119,7 +119,12 @@ class GradientReducer:
         if self.world > 1:
             dist.all_reduce(total, group=group)
         self.scale = float(local_batch) / float(total.item())
-        self.scale_tensor = torch.tensor(self.scale, dtype=torch.float32, device=dev)
+        # Bound mode folds the scale into the loss gradient when that is exact - a power of two, i.e. equal slices on
+        # 1/2/4/8 GPUs: scaling a bf16 activation gradient by 2^-k changes no mantissa bit - and otherwise multiplies the
+        # fp32 buckets on the communication stream just before the all-reduce (uneven slices)
+        import math
+        self.fold_scale = math.frexp(self.scale)[0] == 0.5
+        self.scale_tensor = torch.tensor(self.scale if self.fold_scale else 1.0, dtype=torch.float32, device=dev)
         self.global_batch = int(round(total.item()))
         # buckets in reverse registration order; a bucket only ends after a weight tensor (ndim > 1), so a BatchNorm's
         # (bias, weight) pair - adjacent in this order - is never split and can be written as one dbeta | dgamma block
@@ -204,6 +209,8 @@ class GradientReducer:
             with torch.cuda.stream(self.comm_stream):
                 for e in self._bucket_events[i]:       # the views of a bucket are filled on several streams
                     self.comm_stream.wait_event(e)
+                if not self.fold_scale:
+                    self.flat[i].mul_(self.scale)
                 if self.world > 1:
                     dist.all_reduce(self.flat[i], group=self.group)
             self._bucket_events[i] = []

@@ -11,11 +11,25 @@ pytestmark = pytest.mark.gpu
 
 
 def _worker(rank, world, port, q):
+    import faulthandler
+    import traceback
     import torch.distributed as dist
+    faulthandler.dump_traceback_later(200, exit=True)          # a rank stuck in a collective: show where, then die
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
+        _worker_body(rank, world, q, dist)
+    except BaseException:
+        q.put((rank, "error", traceback.format_exc()))
+        q.close()
+        q.join_thread()
+        os._exit(1)                                            # do not wait for the peer in destroy_process_group
+    dist.destroy_process_group()
+
+
+def _worker_body(rank, world, q, dist):
+    if True:
         import sys
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
         import test_train_gpu as T
@@ -40,6 +54,7 @@ def _worker(rank, world, port, q):
             dist.all_gather(both, mine)
             same = same and torch.equal(both[0], both[1])
         ok_ref = True
+        errs = {}
         if rank == 0:                                          # expected update from the two slices' own gradients
             grads = []
             for (a, b) in bounds:
@@ -53,6 +68,7 @@ def _worker(rank, world, port, q):
                 want = sd0[n].cuda() - lr * g
                 err = (sd[n].detach() - want).norm() / (lr * g).norm().clamp_min(1e-12)
                 ok_ref = ok_ref and err.item() < 2e-2
+                errs["ref:" + n] = round(err.item(), 5)
         # eager step with bucket all-reduces launched from autograd hooks (overlapping the rest of backward) must give
         # the same update as the graph-replayed step followed by reduce_all()
         m2 = S.PoseHighResolutionNet(width=32)
@@ -77,9 +93,8 @@ def _worker(rank, world, port, q):
             upd = (sd[n].detach() - sd0[n].cuda())
             err = (sd2[n].detach() - sd[n].detach()).norm() / upd.norm().clamp_min(1e-12)
             ok_hooks = ok_hooks and err.item() < 1e-3
-        q.put((rank, bool(same), bool(ok_ref and ok_hooks)))
-    finally:
-        dist.destroy_process_group()
+            errs["hooks:" + n] = round(err.item(), 5)
+        q.put((rank, bool(same), bool(ok_ref and ok_hooks), errs))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -91,8 +106,14 @@ def test_two_rank_train_step_matches_weighted_slice_gradients():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    for p in procs:
-        p.join(timeout=600)
-        assert p.exitcode == 0
-    results = sorted(q.get(timeout=10) for _ in procs)
-    assert results == [(0, True, True), (1, True, True)], results
+    results = []
+    try:
+        for _ in procs:
+            results.append(q.get(timeout=300))                 # a failing rank reports its traceback instead
+            assert results[-1][1] != "error", results[-1][2]
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    assert sorted(r[:3] for r in results) == [(0, True, True), (1, True, True)], results
