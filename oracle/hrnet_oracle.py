@@ -152,6 +152,7 @@ def default_init_state_dict(width=32, seed=0, joints=NUM_JOINTS):
 # ----------------------------------------------------------------------------------------------
 _TRAIN = False  # set by hrnet_forward_train: BatchNorm uses batch statistics and updates the running ones in place
 _BF16 = False   # set by hrnet_forward_train(bf16_storage=True): tensors are rounded to bf16 where the device path stores them
+_TRACE = None   # set by hrnet_forward_train(trace=[...]): one record per conv + BatchNorm unit (inputs, output)
 
 
 def _q(t):
@@ -172,7 +173,12 @@ def _conv_bn(sd, x, conv, bn, stride=1, relu=False, res=None):
                      sd[bn + ".bias"], _TRAIN, 0.1, BN_EPS)
     if res is not None:
         y = y + res
-    return _q(F.relu(y) if relu else y)
+    y = _q(F.relu(y) if relu else y)
+    if _TRACE is not None:
+        y.retain_grad()                 # after loss.backward(): y.grad = the gradient this unit receives
+        _TRACE.append(dict(conv=conv, bn=bn, stride=stride, relu=relu, x=x.detach(),
+                           res=None if res is None else res.detach(), y=y))
+    return y
 
 
 def _bottleneck(sd, x, p):
@@ -238,7 +244,18 @@ def _transition(sd, stage, ys, width):
     return xs
 
 
-def hrnet_forward_train(sd, x, width=32, bf16_storage=False):
+def conv_bn_unit(sd, x, conv, bn, stride=1, relu=False, res=None, bf16_storage=True):
+    """ONE conv + train-mode BatchNorm [+ residual] [+ ReLU] unit of the training graph (HRnet.py:48-59 under
+    model.train()) on caller-supplied inputs, with live autograd.  Updates sd's running statistics of `bn` in place."""
+    global _TRAIN, _BF16
+    _TRAIN, _BF16 = True, bool(bf16_storage)
+    try:
+        return _conv_bn(sd, x, conv, bn, stride, relu, res)
+    finally:
+        _TRAIN, _BF16 = False, False
+
+
+def hrnet_forward_train(sd, x, width=32, bf16_storage=False, trace=None):
     """PoseHighResolutionNet.forward under model.train() (02_train.py:153, 208): BatchNorm normalises with batch
     statistics (per replica, momentum 0.1 running-stat update in place on `sd`) and autograd is live, so
     ``loss.backward()`` fills ``.grad`` of every tensor of `sd` that requires grad.
@@ -246,13 +263,17 @@ def hrnet_forward_train(sd, x, width=32, bf16_storage=False):
     bf16_storage=True restates the SAME graph with every tensor rounded to bf16 at the points where the device path
     stores it (input, conv weights, raw conv outputs, block outputs and their gradients; arithmetic stays fp32).
     Batch-statistics BatchNorm over a few crops amplifies rounding differences chaotically with depth, so the fp32
-    result is only a loose anchor for a bf16 pipeline in train mode; this variant is the tight one."""
-    global _TRAIN, _BF16
-    _TRAIN, _BF16 = True, bool(bf16_storage)
+    result is only a loose anchor for a bf16 pipeline in train mode; this variant is the tight one.
+
+    trace: a list that receives one record per conv + BatchNorm unit in execution order (keys conv, bn, stride, relu,
+    x, res, y; ``y.grad`` holds the unit's incoming gradient after ``loss.backward()``) - the inputs of the
+    layer-by-layer device parity test."""
+    global _TRAIN, _BF16, _TRACE
+    _TRAIN, _BF16, _TRACE = True, bool(bf16_storage), trace
     try:
         return _forward(sd, x, width)
     finally:
-        _TRAIN, _BF16 = False, False
+        _TRAIN, _BF16, _TRACE = False, False, None
 
 
 @torch.no_grad()

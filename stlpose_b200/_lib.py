@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstlpose_b200.so")
+# STLPOSE_LIB: another build of the same library (measurement builds, e.g. with -DSTL_CONV_COUNTERS)
+LIB_PATH = os.environ.get("STLPOSE_LIB") or os.path.join(_HERE, "libstlpose_b200.so")
 STL_MAX_UP = 3
 
 c_float_p = ctypes.POINTER(ctypes.c_float)

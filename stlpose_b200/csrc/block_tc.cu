@@ -383,19 +383,15 @@ int basic_block_launch(const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bflo
   }
   const size_t smem = 1024 + 1024 + 2 * 9 * kTapBytes + 3 * (size_t)p.x_stage_bytes + 2 * 3 * 128 * kPitch;
   if (smem > 227 * 1024) { set_error("basic_block: shared memory budget exceeded (%zu)", smem); return 1; }
-  static bool attr = false;
+  static DeviceOnce attr_once;
   cudaError_t e;
-  if (!attr) {
-    e = cudaFuncSetAttribute(basic_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { set_error("basic_block attribute: %s", cudaGetErrorString(e)); return 1; }
-    attr = true;
-  }
-  int sms = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  if (attr_once.run([]() {
+        cudaError_t e2 = cudaFuncSetAttribute(basic_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e2 != cudaSuccess) { set_error("basic_block attribute: %s", cudaGetErrorString(e2)); return 1; }
+        return 0;
+      }))
+    return 1;
+  const int sms = device_sm_count();
   long long grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   basic_block_kernel<<<(unsigned)grid, kBlkThreads, smem, stream>>>(p);

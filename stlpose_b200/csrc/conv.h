@@ -7,6 +7,7 @@
 // cell (or outside the tensor, where TMA zero-fills).  A stride-1 conv is then out[q] = sum_t W_t . in[q+off_t]
 // over the flat pixel index, for any batch and any tile boundary.
 #pragma once
+#include <mutex>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -138,5 +139,39 @@ int basic_block_launch(const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bflo
 int conv_launch_naive(const ConvSpec& spec, cudaStream_t stream);
 
 void set_error(const char* fmt, ...);
+
+
+// Per-device state of the launchers.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device and
+// the SM count differs per device, so "done once" flags and cached counts are indexed by device; a mutex makes the
+// first use safe from autograd worker threads.
+struct DeviceOnce {
+  static constexpr int kMaxDevices = 64;
+  std::mutex mu;
+  bool done[kMaxDevices] = {};
+  // runs fn() (-> 0 on success) the first time it is called for the current device
+  template <typename F>
+  int run(F&& fn) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return fn();
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev]) return 0;
+    const int r = fn();
+    if (r == 0) done[dev] = true;
+    return r;
+  }
+};
+inline int device_sm_count() {
+  static std::mutex mu;
+  static int count[DeviceOnce::kMaxDevices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= DeviceOnce::kMaxDevices) return 148;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!count[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    count[dev] = n > 0 ? n : 148;
+  }
+  return count[dev];
+}
 
 }  // namespace stl

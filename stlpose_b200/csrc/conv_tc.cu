@@ -1009,16 +1009,7 @@ int pick_nt(int cout_pad) {
   return 0;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms() { return device_sm_count(); }
 
 }  // namespace
 
@@ -1035,6 +1026,17 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     return 1;
   }
   p.ck = pick_ck(gi.C);
+  // 64 -> 64 3x3 stride 1 (layer1 conv2, the 64-channel branch): two 32-channel K chunks instead of one of 64.  The
+  // activation ring then holds four half-size stages instead of two (same bytes), i.e. loads run 1.5 tiles ahead of the
+  // MMAs instead of one: the issuing warp's wait for activations drops from 25 % to 17 % of its time at 64x48
+  // (301 -> 258 us per launch, 84.7 -> 83.3 us at 32x24; gpurun_out/r02_convprobe2.txt).  STL_DBG_CK overrides.
+  bool ck_split = gi.C == 64 && s.cout_pad == 64 && s.ksize == 3 && s.stride == 1 && !s.force_tap_reload;
+  if (const char* e = getenv("STL_DBG_CK")) {
+    const int v = atoi(e);
+    ck_split = false;
+    if ((v == 16 || v == 32) && gi.C % v == 0 && v < p.ck) p.ck = v;
+  }
+  if (ck_split) p.ck = 32;
   p.nt = pick_nt(s.cout_pad);
   if (!p.ck || !p.nt) { set_error("conv: channels must be multiples of 16 (cin %d cout_pad %d)", gi.C, s.cout_pad); return 1; }
   if (s.stride == 2 && ((gi.H | gi.W) & 1)) { set_error("conv: stride 2 needs even H, W"); return 1; }
@@ -1068,7 +1070,11 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   // Measured on B200: the MMA stream gets 40 % shorter but the epilogue's row exchange makes the
   // drain the bottleneck, 89 vs 83 us on the 64-channel layers - so it is off unless asked for (spec.kw_merge = 1 /
   // stl_conv_desc.impl = 3 / STLPOSE_KW_MERGE=1).
+#ifdef STL_KW_MERGE   // measured-negative variant: only in builds made with -DSTL_KW_MERGE (profiles/r01_kwm_experiment.md)
   const bool kwm_wanted = s.kw_merge == 1 || (s.kw_merge == 0 && getenv("STLPOSE_KW_MERGE") && atoi(getenv("STLPOSE_KW_MERGE")) == 1);
+#else
+  const bool kwm_wanted = false;
+#endif
   const bool kwm = kwm_wanted && p.mode == 0 && p.taps == 9 && !s.force_tap_reload && !s.force_mb && !s.out_nchw &&
                    s.n_up == 0 && p.n_ntiles == 1 && 3 * p.nt <= 256 && (p.nt * span) % 1024 == 0 && s.img_hi == 0 &&
                    !getenv("STL_DBG_NO_EPI_TMA") && !getenv("STL_DBG_NO_RESIDENT") && !getenv("STL_DBG_PAIR_ALL");
@@ -1198,7 +1204,9 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   }
   if (p.pair) p.total_tiles = (((p.P - p.q_lo + 128 * p.mb - 1) / (128 * p.mb) + 1) / 2) * p.n_ntiles;
   const int a_loads_per_tile = p.n_chunks * (p.a_shift || p.taps == 1 ? 1 : p.taps);
-  const int a_want = a_loads_per_tile >= 4 ? 4 : (p.a_shift ? 3 : 4);
+  int a_want = a_loads_per_tile >= 4 ? 4 : (p.a_shift ? 3 : 4);
+  if (ck_split) a_want = 4;
+  if (const char* e = getenv("STL_DBG_A_WANT")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStages) a_want = v; }
   int a_st = 2, b_st = 2;
   p.b_resident = (resident <= 120 * 1024 && resident + 2 * (size_t)p.a_stage_bytes <= budget &&
                   resident < (1u << 20) && !getenv("STL_DBG_NO_RESIDENT")) ? 1 : 0;
@@ -1299,7 +1307,9 @@ ConvKernel pick_variant(int taps, int epi, bool pair) {
   if (epi == kEpiNchw) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiNchw, false> : nullptr;
   if (epi == kEpiStagedS2) return taps == 9 ? conv_tc_kernel<MB, KSTEPS, 9, kEpiStagedS2, false> : nullptr;
   if (epi == kEpiStagedKW) {
+#ifdef STL_KW_MERGE
     if constexpr (MB == 1) return taps == 9 ? conv_tc_kernel<1, KSTEPS, 9, kEpiStagedKW, false> : nullptr;
+#endif
     return nullptr;
   }
   if (epi == kEpiStaged) {
@@ -1331,21 +1341,22 @@ int epi_kind(const ConvParams& p) {
 }  // namespace
 
 int conv_launch_prepared(const ConvParams& p, int grid, size_t smem_bytes, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    for (int mb = 1; mb <= 3; ++mb)
-      for (int ks = 1; ks <= 4; ks *= 2)
-        for (int epi = 0; epi < 5; ++epi)
-          for (int taps = 1; taps <= 9; taps += 8)
-            for (int pair = 0; pair < 2; ++pair) {
-              if (pair && epi != kEpiStaged) continue;
-              ConvKernel k = pick_kernel(mb, ks, taps, epi, pair != 0);
-              if (!k) continue;
-              cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-              if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
-            }
-    attr_set = true;
-  }
+  static DeviceOnce attr_once;
+  if (attr_once.run([]() {
+        for (int mb = 1; mb <= 3; ++mb)
+          for (int ks = 1; ks <= 4; ks *= 2)
+            for (int epi = 0; epi < 5; ++epi)
+              for (int taps = 1; taps <= 9; taps += 8)
+                for (int pair = 0; pair < 2; ++pair) {
+                  if (pair && epi != kEpiStaged) continue;
+                  ConvKernel k = pick_kernel(mb, ks, taps, epi, pair != 0);
+                  if (!k) continue;
+                  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+                  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+                }
+        return 0;
+      }))
+    return 1;
   if (grid <= 0) return 0;
   ConvKernel kern = pick_kernel(p.mb, p.ck / 16, p.taps, epi_kind(p), p.pair != 0);
   if (!kern) { set_error("conv: no kernel for mb %d ck %d taps %d nchw %d", p.mb, p.ck, p.taps, p.out_nchw); return 1; }

@@ -234,16 +234,7 @@ int encode_rows(CUtensorMap* tm, const void* base, int channels, long long rows,
   return 0;
 }
 
-int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int sm_count() { return device_sm_count(); }
 
 }  // namespace
 
@@ -397,12 +388,13 @@ int wgrad_tc_launch(const __nv_bfloat16* x, const __nv_bfloat16* dz, float* dw, 
   if (encode_rows(&p.tmX, x, cin, P, p.pitch_b / 2, p.x_rows)) return 1;
   cudaError_t e;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  static bool attr = false;
-  if (!attr) {
-    e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
-    if (e != cudaSuccess) { set_error("wgrad_tc attribute: %s", cudaGetErrorString(e)); return 1; }
-    attr = true;
-  }
+  static DeviceOnce attr_once;
+  if (attr_once.run([]() {
+        cudaError_t e2 = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+        if (e2 != cudaSuccess) { set_error("wgrad_tc attribute: %s", cudaGetErrorString(e2)); return 1; }
+        return 0;
+      }))
+    return 1;
   wgrad_tc_kernel<<<p.n_groups * p.n_splits, kThreadsW, smem, stream>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("wgrad_tc launch: %s", cudaGetErrorString(e)); return 1; }
