@@ -421,16 +421,30 @@ def run_infer(args):
             "launches_per_step": conv_n, "conv_ms_per_step": conv_ms, "other_kernels_ms": other_ms,
             "whole_step_frac": (2 * FLOPS_FWD[WIDTH] * B / (ms_step * 1e-3) / 1e12) / peak_tf}
         h.cpu_baseline(out)
+    if not args.no_extras:
+        # config 4 next to the headline, so that the scaling runs (which use the default command line) also record the
+        # data-parallel fine-tuning step: 32 crops per GPU, gradients all-reduced inside the captured step
+        del pipe, model
+        torch.cuda.empty_cache()
+        r = measure_train(h, args, steps=10, warmup=3, e2e=False)
+        if out is not None:
+            out["train"] = {
+                "metric": "person crops/sec fine-tuning step (fwd + PersonMSELoss + bwd + SGD), HRNet-W%d" % WIDTH,
+                "value": r["total"] / (r["ms_step"] * 1e-3), "unit": "crops/s", "ms_per_step": r["ms_step"],
+                "crops_per_gpu_per_step": r["B"], "n_gpus": world, "scaling": "weak", "steps": 10,
+                "tensor_frac": r["achieved_tf"] / r["peak_tf"], "kernels_per_step": r["kernel_nodes"],
+                "collective": r["collective"], "loss": r["loss"]}
     h.finish(out, ops)
 
 
-def run_train(args):
+def measure_train(h, args, steps, warmup, e2e=True):
+    """One data-parallel fine-tuning step per step (config 4) on the ranks of harness h -> dict of measurements (rank 0
+    fills in the derived numbers).  Used by --workload train and, briefly, as the `train` object of the default line."""
     import stlpose_b200 as S
     from stlpose_b200.parallel import GradientReducer
-    h = Harness(args)
     torch, dist, dev, world, rank = h.torch, h.dist, h.dev, h.world, h.rank
     IMAGE, WIDTH = SHAPES[args.width], args.width
-    B, total, scaling = per_rank_batch(args, world, rank)
+    B, total, scaling = per_rank_batch(args, world, rank) if args.workload == "train" else (32, 32 * world, "weak")
     H, W = IMAGE
     crit = S.PersonMSELoss()
 
@@ -458,47 +472,59 @@ def run_train(args):
     def step_e2e():                              # pinned host batch in (H2D inside the call), loss scalar out
         loss_host.copy_(step(x_host, t_host, w_host), non_blocking=True)
 
-    ms_step, t0, t1 = h.timed(step_resident, args.steps, args.warmup)
+    ms_step, t0, t1 = h.timed(step_resident, steps, warmup)
     clocks = h.sampler.summary(t0, t1)
-    ms_e2e, _, _ = h.timed(step_e2e, args.steps, max(args.warmup, 3))
-    loss_value = float(step.loss)
-    kernel_nodes = step.kernel_nodes
-    collective = None
+    ms_e2e = h.timed(step_e2e, steps, max(warmup, 3))[0] if e2e else None
+    r = {"B": B, "total": total, "scaling": scaling, "ms_step": ms_step, "ms_e2e": ms_e2e, "clocks": clocks,
+         "loss": float(step.loss), "kernel_nodes": step.kernel_nodes, "graph": step.graph is not None,
+         "optimizer_in_graph": step.optimizer_in_graph, "collective": None,
+         "h2d": (x_host.numel() + t_host.numel() + w_host.numel()) * 4}
     if world > 1:
         n_bytes = sum(f.numel() for f in step.reducer.flat) * 4
         n_buckets = len(step.reducer.flat)
         del step, model
         torch.cuda.empty_cache()
         model, step = build(dry=True)            # the same step without the collective: the difference is what is exposed
-        ms_dry, _, _ = h.timed(step_resident, args.steps, args.warmup)
-        collective = {"op": "ncclAllReduce (fp32 gradient buckets, in the captured step, on a communication stream "
-                            "forked when backward has filled a bucket)", "bytes_per_step": n_bytes, "buckets": n_buckets,
-                      "ms_per_step_without_collective": ms_dry, "exposed_ms": ms_step - ms_dry}
+        ms_dry, _, _ = h.timed(step_resident, steps, warmup)
+        r["collective"] = {"op": "ncclAllReduce (fp32 gradient buckets, nodes of the captured step, on a communication "
+                                 "stream forked when backward has filled a bucket)", "bytes_per_step": n_bytes,
+                           "buckets": n_buckets, "ms_per_step_without_collective": ms_dry,
+                           "exposed_ms": ms_step - ms_dry}
+    del step, model
+    torch.cuda.empty_cache()
+    peaks, peak_kind = measured_peaks()
+    peak_tf = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
+    r["achieved_tf"] = 3 * FLOPS_FWD[WIDTH] * B / (ms_step * 1e-3) / 1e12     # forward + dgrad + wgrad of every conv
+    r["peak_tf"], r["peak_kind"] = peak_tf, peak_kind
+    return r
+
+
+def run_train(args):
+    h = Harness(args)
+    r = measure_train(h, args, args.steps, args.warmup)
     out = None
-    if rank == 0:
+    if h.rank == 0:
+        WIDTH = args.width
         metric, workload = _names(args)
-        peaks, peak_kind = measured_peaks()
-        peak_tf = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
-        flops_step = 3 * FLOPS_FWD[WIDTH] * B            # forward + input gradient + weight gradient of every conv
-        achieved = flops_step / (ms_step * 1e-3) / 1e12
         traffic, traffic_note = ncu_traffic(f"train_w{WIDTH}")
-        out = h.base_line(metric, workload, total / (ms_step * 1e-3), ms_step, clocks, "bf16", scaling)
+        out = h.base_line(metric, workload, r["total"] / (r["ms_step"] * 1e-3), r["ms_step"], r["clocks"], "bf16", r["scaling"])
         out["config"].update({
-            "crops_per_step_total": total, "crops_per_gpu_per_step": B, "optimizer": "SGD momentum 0.9 weight decay 5e-4",
-            "cuda_graph": step.graph is not None, "optimizer_in_graph": step.optimizer_in_graph,
+            "crops_per_step_total": r["total"], "crops_per_gpu_per_step": r["B"],
+            "optimizer": "SGD momentum 0.9 weight decay 5e-4", "cuda_graph": r["graph"],
+            "optimizer_in_graph": r["optimizer_in_graph"],
             "l2": "activations of a step (150 MB per crop) exceed the 126 MB L2; no flush needed",
-            "partition": f"batch sharded over {world} GPU(s), per-rank BatchNorm statistics, gradients all-reduced"})
-        out["e2e"] = {"value": total / (ms_e2e * 1e-3), "unit": "crops/s", "ms_per_step": ms_e2e,
-                      "h2d_bytes_per_step": (x_host.numel() + t_host.numel() + w_host.numel()) * 4, "d2h_bytes_per_step": 4}
-        out["gpu_launches"] = kernel_nodes * args.steps if kernel_nodes else None   # kernel nodes of the captured step
-        out["loss"] = loss_value
+            "partition": f"batch sharded over {h.world} GPU(s), per-rank BatchNorm statistics, gradients all-reduced"})
+        out["e2e"] = {"value": r["total"] / (r["ms_e2e"] * 1e-3), "unit": "crops/s", "ms_per_step": r["ms_e2e"],
+                      "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 4}
+        out["gpu_launches"] = r["kernel_nodes"] * args.steps if r["kernel_nodes"] else None   # kernel nodes of the captured step
+        out["loss"] = r["loss"]
         out["roofline"] = {
             "bound": "tensor", "kernel": "whole step: conv_tc (forward, dgrad) + wgrad_tc + BatchNorm kernels",
-            "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+            "achieved": r["achieved_tf"], "peak": r["peak_tf"], "unit": "TFLOP/s", "frac": r["achieved_tf"] / r["peak_tf"],
             "traffic": traffic, "traffic_note": traffic_note,
-            "peak_source": f"{peak_kind} bf16_tflops_sustained", "flops_per_crop": 3 * FLOPS_FWD[WIDTH]}
-        if collective:
-            out["collective"] = collective
+            "peak_source": f"{r['peak_kind']} bf16_tflops_sustained", "flops_per_crop": 3 * FLOPS_FWD[WIDTH]}
+        if r["collective"]:
+            out["collective"] = r["collective"]
         h.cpu_baseline(out)
     h.finish(out)
 
@@ -610,6 +636,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="decode workload: skip the batch / heatmap-size sweep")
+    ap.add_argument("--no-extras", action="store_true", help="infer workload: skip the short fine-tuning measurement (`train`)")
     ap.add_argument("--width", type=int, default=32, choices=[32, 48],
                     help="32: HRNet-W32 256x192 (the configuration the metric is quoted on); 48: HRNet-W48 384x288")
     ap.add_argument("--dump-ops", default="", help="infer workload: write the per-launch timing table (JSON) here")

@@ -56,7 +56,8 @@ int stl_decode(const float* heat, const float* heat_flipped, const float* center
 size_t stl_mse_workspace_bytes(void);
 /* OKS rescoring + greedy OKS-NMS: generate_submission_hrnet (lib/metrics.py:232-258) and
  * nms.oks_nms / oks_iou (lib/nms.py:10-74) for all images of an evaluation at once.  Persons are grouped by image:
- * persons [image_offsets[i], image_offsets[i+1]) belong to image i (at most 128 per image; pass the maximum).
+ * persons [image_offsets[i], image_offsets[i+1]) belong to image i (any number, like lib/nms.py: pass the largest
+ * count as max_persons_per_image, it sizes the kernel's shared memory; ~15 000 persons fit).
  * keypoints [M][J][3] fp32 (x, y, score; J <= 64), area / box_score [M] fp64, vars [J] fp64 = (2*sigma_j)^2.
  * rescore != 0: score = mean(joint scores > in_vis_thr) * box_score, else box_score is the score.  nms_vis_thr < 0: all
  * joints enter the OKS (what the reference's call does); otherwise only joints of the candidate with score > nms_vis_thr.
@@ -89,6 +90,12 @@ int stl_upsampled_argmax(const float* heat, int B, int J, int h, int w, int out_
 int stl_warp_affine_crops(const void* img_u8_hwc, int img_h, int img_w, const double* minv, int N, int out_h, int out_w,
                           void* out_u8_nchw, float* out_f32_nchw, const float* mean3_host, const float* std3_host,
                           void* stream);
+
+/* The same for float32 HWC images (04_evaluate_vases_qualitatively.py:209-213 hands TransformDetection a float array;
+ * cv2.warpAffine then interpolates in float32 with its bilinear weight table): fp32 [N][3][out_h][out_w], bit-identical
+ * to cv2's result. */
+int stl_warp_affine_crops_f32(const float* img_f32_hwc, int img_h, int img_w, const double* minv, int N, int out_h,
+                              int out_w, float* out_f32_nchw, void* stream);
 
 /* PCK accuracy of the training / evaluation loops (lib/metrics.py:268-364 accuracy -> calc_dists -> dist_acc, called at
  * 02_train.py:223,277 and 03_evaluate.py:142 on output.cpu()): pred_coords / target_coords are the [B][J][2] arg-max

@@ -108,6 +108,12 @@ def make_crops():
     rot = L.transforms.crop(img, centers[1], scales[1], np.array([192, 256]), rot=30)
     np.savez_compressed(os.path.join(GOLDEN_DIR, "crops.npz"), dets=dets, centers=centers, scales=scales, rot30=rot)
     print("crops", dets.shape, dets.dtype, "mean", dets.mean())
+    # float32 image, as 04_evaluate_vases_qualitatively.py:209-210 passes it (a [0, 1] CHW tensor turned HWC): one box
+    # is enough to pin the float interpolation path (stored as float16-exact inputs -> exact float32 outputs)
+    imgf = (img.astype(np.float32) / np.float32(255)).astype(np.float16).astype(np.float32)
+    dets_f, _, _ = L.transforms.TransformDetection()(imgf, boxes[1:2])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "crops_f32.npz"), dets=dets_f)
+    print("crops f32", dets_f.shape, dets_f.dtype, "mean", dets_f.mean())
 
 
 def pose_entry_inputs():

@@ -255,13 +255,49 @@ def warp_affine_u8(img, m, dsize):
     return out
 
 
+def warp_affine_f32(img, m, dsize):
+    """cv2.warpAffine(img, m, dsize, flags=INTER_LINEAR) for float32 HWC images (what 04_evaluate_vases_qualitatively.py:
+    209-213 feeds TransformDetection): the same fixed-point source coordinates as the uint8 path (1/32 px), but the
+    interpolation runs in float32 with OpenCV's bilinear table (imgwarp.cpp initInterTab2D: w = vy[k1] * vx[k2] with
+    v = {1 - i/32, i/32}) and the sum S00 w00 + S01 w01 + S10 w10 + S11 w11 evaluated left to right.
+    Bit-exact against cv2 4.13 in this container (tests/test_oracle_vs_reference.py)."""
+    W, H = dsize
+    mi = invert_affine(m)
+    ab = 1024
+    xs = np.arange(W)
+    adelta = np.rint(mi[0] * xs * ab).astype(np.int64)
+    bdelta = np.rint(mi[3] * xs * ab).astype(np.int64)
+    img = np.asarray(img, np.float32)
+    ih, iw, ch = img.shape
+    pad = np.zeros((ih + 2, iw + 2, ch), np.float32)
+    pad[1:-1, 1:-1] = img
+    out = np.zeros((H, W, ch), np.float32)
+    tab = np.arange(32, dtype=np.float32) / np.float32(32)
+
+    def px(yy, xx):
+        ok = (yy >= 0) & (yy < ih) & (xx >= 0) & (xx < iw)
+        return pad[np.clip(yy, -1, ih) + 1, np.clip(xx, -1, iw) + 1] * ok[:, None].astype(np.float32)
+
+    for y in range(H):
+        x0 = int(np.rint((mi[1] * y + mi[2]) * ab)) + 16
+        y0 = int(np.rint((mi[4] * y + mi[5]) * ab)) + 16
+        X, Y = (x0 + adelta) >> 5, (y0 + bdelta) >> 5
+        sx, sy, fx, fy = X >> 5, Y >> 5, X & 31, Y & 31
+        wx1, wy1 = tab[fx], tab[fy]
+        wx0, wy0 = np.float32(1) - wx1, np.float32(1) - wy1
+        out[y] = (px(sy, sx) * (wy0 * wx0)[:, None] + px(sy, sx + 1) * (wy0 * wx1)[:, None] +
+                  px(sy + 1, sx) * (wy1 * wx0)[:, None] + px(sy + 1, sx + 1) * (wy1 * wx1)[:, None])
+    return out
+
+
 def transform_detection(img, list_coords, det_width=192, det_height=256):
     """TransformDetection.__call__, lib/transforms.py:30-58 -> (detections u8 [N,3,H,W], centers [N,2], scales [N,2])."""
     dets, centers, scales = [], [], []
     for coords in list_coords:
         c, s = coords2cs(coords, det_width, det_height)
         m = forward_affine(c, s, 0, (det_width, det_height))
-        dets.append(warp_affine_u8(img, m, (det_width, det_height)))
+        warp = warp_affine_u8 if np.asarray(img).dtype == np.uint8 else warp_affine_f32
+        dets.append(warp(img, m, (det_width, det_height)))
         centers.append(c)
         scales.append(s)
     dets, centers, scales = np.array(dets), np.array(centers), np.array(scales)

@@ -79,8 +79,7 @@ int stl_oks_nms(const float* keypoints, const double* area, const double* box_sc
     return 1;
   }
   if (J < 1 || J > kMaxJoints) { set_error("stl_oks_nms: 1..%d joints supported (got %d)", kMaxJoints, J); return 1; }
-  if (max_persons_per_image > 128) { set_error("stl_oks_nms: at most 128 persons per image (got %d)", max_persons_per_image); return 1; }
-  return oks_nms(keypoints, area, box_score, image_offsets, n_images, J, vars, in_vis_thr, oks_thr, nms_vis_thr, rescore,
+  return oks_nms(keypoints, area, box_score, image_offsets, n_images, max_persons_per_image, J, vars, in_vis_thr, oks_thr, nms_vis_thr, rescore,
                  score_out, keep_rank, (cudaStream_t)stream);
 }
 
@@ -109,6 +108,13 @@ int stl_warp_affine_crops(const void* img_u8_hwc, int img_h, int img_w, const do
   }
   return warp_affine_crops((const uint8_t*)img_u8_hwc, img_h, img_w, minv, N, out_h, out_w, (uint8_t*)out_u8_nchw,
                            out_f32_nchw, mean3_host, std3_host, (cudaStream_t)stream);
+}
+
+int stl_warp_affine_crops_f32(const float* img_f32_hwc, int img_h, int img_w, const double* minv, int N, int out_h,
+                              int out_w, float* out_f32_nchw, void* stream) {
+  if (!have_device()) return 1;
+  if (N > 0 && (!img_f32_hwc || !minv || !out_f32_nchw)) { set_error("stl_warp_affine_crops_f32: null pointer"); return 1; }
+  return warp_affine_crops_f32(img_f32_hwc, img_h, img_w, minv, N, out_h, out_w, out_f32_nchw, (cudaStream_t)stream);
 }
 
 int stl_pck_accuracy(const float* pred_coords, const float* target_coords, int B, int J, int h, int w, float thr,

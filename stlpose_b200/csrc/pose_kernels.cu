@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "conv.h"
 #include "pose_kernels.h"
 
 namespace stl {
@@ -199,22 +200,23 @@ __global__ void mse_final_kernel(const double* __restrict__ partial, int n, doub
 // score = mean(joint scores > in_vis_thr) * box score; per image, persons are visited by descending score and a person
 // is dropped when its OKS with an already kept one exceeds oks_thr.  OKS = mean_j exp(-(d_j^2 / var_j) / ((a_g+a_d)/2 + eps) / 2)
 // over the joints selected by vis_thr (the reference's `list(vg > t) and list(vd > t)` keeps the mask of d only; < 0 = all).
-// One block per image (persons [off[i], off[i+1]), at most kMaxPersons); float64 like NumPy; joint scores are summed in
+// One block per image (persons [off[i], off[i+1]), any number: lib/nms.py has no limit); float64 like NumPy; joint scores are summed in
 // float32 in joint order like the reference's scalar loop.  keep_rank[m] = position in the keep list or -1.
-constexpr int kMaxPersons = 128;
 __global__ void __launch_bounds__(128) oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ area,
                                                       const double* __restrict__ box_score, const int* __restrict__ off,
                                                       int J, const double* __restrict__ vars, float in_vis_thr,
-                                                      double oks_thr, float nms_vis_thr, int rescore,
+                                                      double oks_thr, float nms_vis_thr, int rescore, int max_persons,
                                                       double* __restrict__ score_out, int* __restrict__ keep_rank) {
-  __shared__ double s_score[kMaxPersons];
-  __shared__ int s_order[kMaxPersons];
-  __shared__ unsigned char s_dead[kMaxPersons];
+  // dynamic shared memory sized by the caller's max_persons_per_image: [scores f64][order i32][dead u8]
+  extern __shared__ __align__(8) unsigned char nms_smem[];
+  double* s_score = reinterpret_cast<double*>(nms_smem);
+  int* s_order = reinterpret_cast<int*>(s_score + max_persons);
+  unsigned char* s_dead = reinterpret_cast<unsigned char*>(s_order + max_persons);
   const int lo = off[blockIdx.x], n_all = off[blockIdx.x + 1] - lo;
   if (n_all <= 0) return;
-  // (the host wrapper rejects more than kMaxPersons per image; should the offsets say otherwise, the surplus persons are
-  // reported as suppressed rather than indexing past the shared arrays)
-  const int n = n_all < kMaxPersons ? n_all : kMaxPersons;
+  // (should the offsets exceed the declared maximum, the surplus persons are reported as suppressed rather than
+  // indexing past the shared arrays)
+  const int n = n_all < max_persons ? n_all : max_persons;
   for (int i = n + threadIdx.x; i < n_all; i += blockDim.x) { keep_rank[lo + i] = -1; score_out[lo + i] = box_score[lo + i]; }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float* kp = kpts + (size_t)(lo + i) * J * 3;
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(128) oks_nms_kernel(const float* __restrict__ 
         const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
         e[cnt++] = exp(-((double)d2 / vars[j] / denom / 2));
       }
-      // np.sum of a contiguous float64 array of n <= 128 elements: 8 running partial sums over the multiple-of-8 prefix,
+      // np.sum of a contiguous float64 array of cnt <= J <= 64 elements: 8 running partial sums over the multiple-of-8 prefix,
       // combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail in order (plain loop below 8 elements)
       double sum = 0.0;
       if (cnt < 8) {
@@ -420,6 +422,44 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const uint8_t* __restr
   }
 }
 
+// The same warp for float32 HWC images (04_evaluate_vases_qualitatively.py:209-213 passes float arrays to
+// TransformDetection): OpenCV keeps the fixed-point SOURCE COORDINATES (1/32 px) but interpolates in float32 with the
+// weight table w[fy][fx] = {(1-fy/32)(1-fx/32), (1-fy/32)(fx/32), (fy/32)(1-fx/32), (fy/32)(fx/32)} (float products of
+// float table entries) and the sum evaluated left to right without contraction - reproduced operation by operation, so
+// the crops are bit-identical to cv2's.  Output fp32 [N][3][out_h][out_w].
+__global__ void __launch_bounds__(256) warp_affine_f32_kernel(const float* __restrict__ img, int ih, int iw,
+                                                              const double* __restrict__ minv, int out_h, int out_w,
+                                                              float* __restrict__ out) {
+  const int n = blockIdx.z, y = blockIdx.y;
+  const double* m = minv + (size_t)n * 6;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < out_w; x += gridDim.x * blockDim.x) {
+    const long long adelta = __double2ll_rn(__dmul_rn(__dmul_rn(m[0], (double)x), 1024.0));
+    const long long bdelta = __double2ll_rn(__dmul_rn(__dmul_rn(m[3], (double)x), 1024.0));
+    const long long x0 = __double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[1], (double)y), m[2]), 1024.0)) + 16;
+    const long long y0 = __double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[4], (double)y), m[5]), 1024.0)) + 16;
+    const long long X = (x0 + adelta) >> 5, Y = (y0 + bdelta) >> 5;
+    long long sxl = X >> 5, syl = Y >> 5;
+    sxl = sxl < -32768 ? -32768 : (sxl > 32767 ? 32767 : sxl);
+    syl = syl < -32768 ? -32768 : (syl > 32767 ? 32767 : syl);
+    const int sx = (int)sxl, sy = (int)syl, fx = (int)(X & 31), fy = (int)(Y & 31);
+    const float wx1 = __fmul_rn((float)fx, 0.03125f), wx0 = __fsub_rn(1.f, wx1);     // i * (1/32) is exact in float
+    const float wy1 = __fmul_rn((float)fy, 0.03125f), wy0 = __fsub_rn(1.f, wy1);
+    const float w00 = __fmul_rn(wy0, wx0), w01 = __fmul_rn(wy0, wx1), w10 = __fmul_rn(wy1, wx0), w11 = __fmul_rn(wy1, wx1);
+    const bool r0 = sy >= 0 && sy < ih, r1 = sy + 1 >= 0 && sy + 1 < ih;
+    const bool c0 = sx >= 0 && sx < iw, c1 = sx + 1 >= 0 && sx + 1 < iw;
+    const float* p00 = img + ((long long)sy * iw + sx) * 3;
+    const float* p10 = p00 + (long long)iw * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v00 = (r0 && c0) ? p00[c] : 0.f, v01 = (r0 && c1) ? p00[3 + c] : 0.f;
+      const float v10 = (r1 && c0) ? p10[c] : 0.f, v11 = (r1 && c1) ? p10[3 + c] : 0.f;
+      const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00, w00), __fmul_rn(v01, w01)), __fmul_rn(v10, w10)),
+                                __fmul_rn(v11, w11));
+      out[(((size_t)n * 3 + c) * out_h + y) * out_w + x] = v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ PCK accuracy on heatmap arg-max coordinates
 // metrics.py:268-364 (calc_dists, dist_acc, accuracy): a joint counts when its target arg-max has x > 1 and y > 1; it is
 // a hit when || (pred - target) / (h/10, w/10) || < thr (the reference divides x by h/10 and y by w/10); acc[1+j] =
@@ -537,12 +577,25 @@ int decode(const float* heat, const float* heat_f, const float* center, const fl
   return check("decode");
 }
 
-int oks_nms(const float* kpts, const double* area, const double* box_score, const int* offsets, int n_images, int J,
-            const double* vars, float in_vis_thr, double oks_thr, float nms_vis_thr, int rescore, double* score_out,
-            int* keep_rank, cudaStream_t st) {
+int oks_nms(const float* kpts, const double* area, const double* box_score, const int* offsets, int n_images,
+            int max_persons, int J, const double* vars, float in_vis_thr, double oks_thr, float nms_vis_thr, int rescore,
+            double* score_out, int* keep_rank, cudaStream_t st) {
   if (n_images <= 0) return 0;
-  oks_nms_kernel<<<n_images, 128, 0, st>>>(kpts, area, box_score, offsets, J, vars, in_vis_thr, oks_thr, nms_vis_thr,
-                                          rescore, score_out, keep_rank);
+  if (max_persons < 1) max_persons = 1;
+  max_persons = (max_persons + 7) & ~7;                                   // keeps the int / byte arrays aligned
+  const size_t smem = (size_t)max_persons * (sizeof(double) + sizeof(int) + 1);
+  if (smem > 200 * 1024) { set_error("oks_nms: %d persons in one image exceed the shared-memory budget", max_persons); return 1; }
+  if (smem > 48 * 1024) {
+    static DeviceOnce attr_once;
+    if (attr_once.run([]() {
+          cudaError_t e = cudaFuncSetAttribute(oks_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          if (e != cudaSuccess) { set_error("oks_nms attribute: %s", cudaGetErrorString(e)); return 1; }
+          return 0;
+        }))
+      return 1;
+  }
+  oks_nms_kernel<<<n_images, 128, smem, st>>>(kpts, area, box_score, offsets, J, vars, in_vis_thr, oks_thr, nms_vis_thr,
+                                             rescore, max_persons, score_out, keep_rank);
   return check("oks_nms");
 }
 
@@ -577,6 +630,18 @@ int warp_affine_crops(const uint8_t* img, int ih, int iw, const double* minv, in
   dim3 grid((out_w + 255) / 256, out_h, N);
   warp_affine_kernel<<<grid, 256, 0, st>>>(img, ih, iw, minv, out_h, out_w, out_u8, out_f, nm);
   return check("warp_affine_crops");
+}
+
+int warp_affine_crops_f32(const float* img, int ih, int iw, const double* minv, int N, int out_h, int out_w, float* out,
+                          cudaStream_t st) {
+  if (N <= 0) return 0;
+  if (ih <= 0 || iw <= 0 || out_h <= 0 || out_w <= 0 || out_h > 65535 || N > 65535) {
+    set_error("warp_affine_crops_f32: bad geometry");
+    return 1;
+  }
+  dim3 grid((out_w + 255) / 256, out_h, N);
+  warp_affine_f32_kernel<<<grid, 256, 0, st>>>(img, ih, iw, minv, out_h, out_w, out);
+  return check("warp_affine_crops_f32");
 }
 
 int pck_accuracy(const float* pred, const float* tgt, int B, int J, int h, int w, float thr, float* acc, float* avg_acc,

@@ -114,13 +114,29 @@ def _invert_for_warp(m):
 def warp_affine_crops(img, matrices, output_size, normalize=None, as_tensor=False):
     """cv2.warpAffine(img, M, output_size, flags=INTER_LINEAR) for every M, on the device.
 
-    img: uint8 HWC image (NumPy array or CUDA tensor); matrices: iterable of 2x3 image -> crop matrices;
+    img: uint8 or float32 HWC image (NumPy array or CUDA tensor); matrices: iterable of 2x3 image -> crop matrices;
     output_size = (width, height).  Returns uint8 crops [N,3,h,w] (NumPy, or CUDA tensor with ``as_tensor``), or, with
-    ``normalize=(mean3, std3)``, the network input fp32 CUDA tensor [N,3,h,w] = (v/255 - mean) / std."""
+    ``normalize=(mean3, std3)``, the network input fp32 CUDA tensor [N,3,h,w] = (v/255 - mean) / std.  A float32 image
+    (what 04_evaluate_vases_qualitatively.py:209-210 passes) gives float32 crops, interpolated like cv2 does for floats."""
     t = img if torch.is_tensor(img) else torch.as_tensor(np.ascontiguousarray(img))
-    if t.dtype != torch.uint8 or t.ndim != 3 or t.shape[2] != 3:
-        raise ValueError("img must be a uint8 [H,W,3] image")
+    if t.dtype == torch.float64:
+        t = t.float()
+    if t.dtype not in (torch.uint8, torch.float32) or t.ndim != 3 or t.shape[2] != 3:
+        raise ValueError("img must be a uint8 or float32 [H,W,3] image")
     t = t.cuda().contiguous() if not t.is_cuda else t.contiguous()
+    if t.dtype == torch.float32:
+        if normalize is not None:
+            raise ValueError("normalize= fuses ToTensor (v / 255) and applies to uint8 images only")
+        mats = [np.asarray(m, np.float64) for m in matrices]
+        out_w, out_h = int(output_size[0]), int(output_size[1])
+        out = torch.empty((len(mats), 3, out_h, out_w), dtype=torch.float32, device=t.device)
+        if mats:
+            minv = torch.as_tensor(np.stack([_invert_for_warp(m) for m in mats])).to(t.device)
+            with torch.cuda.device(t.device):
+                _lib.check(_lib.lib().stl_warp_affine_crops_f32(_lib.ptr(t), t.shape[0], t.shape[1], _lib.ptr(minv),
+                                                                len(mats), out_h, out_w, _lib.ptr(out),
+                                                                _lib.current_stream()))
+        return out if as_tensor else out.cpu().numpy()
     mats = [np.asarray(m, np.float64) for m in matrices]
     n = len(mats)
     out_w, out_h = int(output_size[0]), int(output_size[1])

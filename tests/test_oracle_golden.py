@@ -128,6 +128,11 @@ def test_crop_extraction_oracle_matches_reference_fixture(golden):
     assert np.array_equal(pose_oracle.warp_affine_u8(img, m, (192, 256)), g["rot30"])
     d0, c0, s0 = pose_oracle.transform_detection(img, [])
     assert len(d0) == 0 and len(c0) == 0
+    # float32 image (04_evaluate_vases_qualitatively.py:209-213): cv2 interpolates in float32 with its weight table
+    gf = golden("crops_f32.npz")
+    imgf = (img.astype(np.float32) / np.float32(255)).astype(np.float16).astype(np.float32)
+    dets_f, _, _ = pose_oracle.transform_detection(imgf, boxes[1:2])
+    assert dets_f.dtype == np.float32 and np.array_equal(dets_f, gf["dets"])
 
 
 def test_upsampled_decode_and_pose_entries_match_reference_fixture(golden):

@@ -93,6 +93,10 @@ def test_affine_solve_and_warp_match_cv2_bit_exact():
         assert np.array_equal(m, m_ref)
         assert np.array_equal(pose_oracle.warp_affine_u8(img, m, (48, 64)),
                               cv2.warpAffine(img, m_ref, (48, 64), flags=cv2.INTER_LINEAR))
+        if t < 12:                                          # float32 images: float interpolation, same source coordinates
+            imgf = rng.standard_normal(img.shape).astype(np.float32)
+            assert np.array_equal(pose_oracle.warp_affine_f32(imgf, m, (48, 64)),
+                                  cv2.warpAffine(imgf, m_ref, (48, 64), flags=cv2.INTER_LINEAR))
     td = L.transforms.TransformDetection()
     for box in ([5, 5, 60, 100], [-30, 20, 90, 80], [100, 60, 200, 140]):
         rc, rs = td._coords2cs(box)

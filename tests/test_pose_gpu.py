@@ -193,6 +193,15 @@ def test_crop_extraction_bit_exact(golden):
         assert np.array_equal(got[i].transpose(1, 2, 0), pose_oracle.warp_affine_u8(img2, m, (72, 96))), i
     e_d, e_c, e_s = td(img, [])
     assert len(e_d) == 0 and len(e_c) == 0 and len(e_s) == 0
+    # float32 images (04_evaluate_vases_qualitatively.py:209-213): bit-identical to cv2's float interpolation
+    gf = golden("crops_f32.npz")
+    imgf = (img.astype(np.float32) / np.float32(255)).astype(np.float16).astype(np.float32)
+    dets_f, _, _ = td(imgf, boxes[1:2])
+    assert dets_f.dtype == np.float32 and np.array_equal(dets_f, gf["dets"])
+    img3 = rng.standard_normal((97, 131, 3)).astype(np.float32)
+    got_f = T.warp_affine_crops(torch.from_numpy(img3).cuda(), mats, (72, 96), as_tensor=True).cpu().numpy()
+    for i, m in enumerate(mats):
+        assert np.array_equal(got_f[i].transpose(1, 2, 0), pose_oracle.warp_affine_f32(img3, m, (72, 96))), i
     # end to end: boxes -> network input -> keypoints runs without touching the host with the crops
     assert x.shape == (5, 3, 256, 192)
 
@@ -294,3 +303,17 @@ def test_oks_rescoring_nms_matches_reference_fixture(golden, tmp_path):
         assert all(np.array_equal(p["keypoints"], P[m]) for p, (m, _) in zip(gi, wi))
         kept += len(wi)
     assert kept < len(I) * 0.8                                                        # the NMS really suppressed
+    # crowded images: lib/nms.py has no limit on the persons of one image (the kernel's shared arrays are sized per call)
+    P2, B2, I2 = [], [], []
+    for img, n in enumerate((700, 3, 129)):
+        c = rng.uniform(50, 600, (n // 4 + 1, 1, 2))
+        k = c[rng.integers(len(c), size=n)] + rng.normal(0, 30, (1, 17, 2)) + rng.normal(0, 3, (n, 17, 2))
+        P2.append(np.concatenate([k, rng.uniform(0, 1, (n, 17, 1))], axis=2).astype(np.float32))
+        sc = rng.uniform(0.3, 2.0, (n, 1)) * np.array([0.75, 1.0])
+        B2.append(np.concatenate([k.mean(1), sc, np.prod(sc * 200, 1, keepdims=True), rng.uniform(0.2, 1, (n, 1))], axis=1))
+        I2 += [img] * n
+    P2, B2 = np.concatenate(P2), np.concatenate(B2)
+    got2, want2 = nms.rescore_and_nms(P2, B2, I2), pose_oracle.rescore_and_nms(P2, B2, I2)
+    for gi, wi in zip(got2, want2):
+        assert [p["score"] for p in gi] == [s for _, s in wi]
+        assert all(np.array_equal(p["keypoints"], P2[m]) for p, (m, _) in zip(gi, wi))
