@@ -181,6 +181,14 @@ typedef struct stl_conv_desc {
 } stl_conv_desc;
 
 int stl_conv2d(const stl_conv_desc* desc, void* stream);
+/* The same convolution, additionally accumulating the BatchNorm batch statistics of its output in the epilogue (training:
+ * HRnet.py:48-59 under model.train(), 02_train.py:208): per-channel sum and sum of squares of the STORED bf16 values over
+ * the valid pixels.  `stats`: stl_conv2d_stats_floats(Cout_pad) floats; the launch fills *stats_rows rows of
+ * [2][Cout_pad] (one per CTA) which stl_bn_train_forward_fused adds in a fixed order (deterministic).  *stats_rows == 0:
+ * this shape - or this build: the fused variants were measured slower than the separate statistics pass and are only
+ * compiled with -DSTL_CONV_STATS - has no fused statistics (the convolution still ran): use stl_bn_train_forward. */
+size_t stl_conv2d_stats_floats(int cout_pad);
+int stl_conv2d_stats(const stl_conv_desc* desc, float* stats, int* stats_rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole-network plan: replaces PoseHighResolutionNet.forward (models/HRnet.py:433-468) in eval mode and the
@@ -275,6 +283,12 @@ int stl_bn_train_backward(const void* dy, const void* y, const void* z, const fl
 int stl_bn_train_forward_ticket(const void* z, const float* gamma, const float* beta, const void* residual, int relu,
                                 float eps, float momentum, int N, int H, int W, int C, void* y, float* sums, float* mean,
                                 float* rstd, float* running_mean, float* running_var, unsigned* ticket, void* stream);
+/* Train-mode BatchNorm whose statistics come from stl_conv2d_stats: mean / rstd / running statistics from the `rows` rows
+ * of [2][c_pad] partial sums, then y = [relu](gamma * (z - mean) * rstd + beta [+ residual]) as above. */
+int stl_bn_train_forward_fused(const void* z, const float* stat_rows, int rows, int c_pad, const float* gamma,
+                               const float* beta, const void* residual, int relu, float eps, float momentum, int N, int H,
+                               int W, int C, void* y, float* mean, float* rstd, float* running_mean, float* running_var,
+                               void* stream);
 int stl_bn_train_backward_ticket(const void* dy, const void* y, const void* z, const float* mean, const float* rstd,
                                  const float* gamma, int relu, int N, int H, int W, int C, void* dz, void* dres,
                                  float* dbeta_dgamma, float* workspace, unsigned* ticket, void* stream);

@@ -76,6 +76,10 @@ PROTOTYPES = {
     "stl_basic_block": (ctypes.c_int, [vp] * 6 + [ctypes.c_int] * 4 + [vp]),
     "stl_pack_conv_weights_dgrad": (ctypes.c_int, [vp] + [ctypes.c_int] * 5 + [vp, vp, vp]),
     "stl_conv2d": (ctypes.c_int, [ctypes.POINTER(ConvDesc), vp]),
+    "stl_conv2d_stats_floats": (ctypes.c_size_t, [ctypes.c_int]),
+    "stl_conv2d_stats": (ctypes.c_int, [ctypes.POINTER(ConvDesc), vp, c_int_p, vp]),
+    "stl_bn_train_forward_fused": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int,
+                                                  ctypes.c_float, ctypes.c_float] + [ctypes.c_int] * 4 + [vp] * 6),
     "stl_plan_create": (vp, [ctypes.POINTER(HrnetCfg)]),
     "stl_plan_destroy": (None, [vp]),
     "stl_plan_num_convs": (ctypes.c_int, [vp]),

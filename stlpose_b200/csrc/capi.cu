@@ -185,7 +185,18 @@ int stl_pack_conv_weights_batched(const stl_pack_item* items_dev, const int* blo
                               (cudaStream_t)stream);
 }
 
-int stl_conv2d(const stl_conv_desc* d, void* stream) {
+static int conv2d_impl(const stl_conv_desc* d, float* stats, int* stats_rows, void* stream);
+
+int stl_conv2d(const stl_conv_desc* d, void* stream) { return conv2d_impl(d, nullptr, nullptr, stream); }
+
+size_t stl_conv2d_stats_floats(int cout_pad) { return (size_t)kStatsMaxRows * 2 * (size_t)cout_pad; }
+
+int stl_conv2d_stats(const stl_conv_desc* d, float* stats, int* stats_rows, void* stream) {
+  if (!stats || !stats_rows) { set_error("stl_conv2d_stats: null pointer"); return 1; }
+  return conv2d_impl(d, stats, stats_rows, stream);
+}
+
+static int conv2d_impl(const stl_conv_desc* d, float* stats, int* stats_rows, void* stream) {
   if (!have_device()) return 1;
   if (!d || !d->in || !d->out || !d->w_packed || !d->bias_packed) { set_error("stl_conv2d: null pointer"); return 1; }
   if (d->n_up < 0 || d->n_up > STL_MAX_UP) { set_error("stl_conv2d: n_up out of range"); return 1; }
@@ -212,8 +223,18 @@ int stl_conv2d(const stl_conv_desc* d, void* stream) {
   s.force_mb = d->force_mb;
   s.max_ctas = d->max_ctas;
   s.dbg_counters = d->dbg_counters;
+  if (stats_rows) *stats_rows = 0;
   if (d->impl == 2) return conv_launch_naive(s, (cudaStream_t)stream);
-  return conv_launch(s, (cudaStream_t)stream);
+  if (!stats) return conv_launch(s, (cudaStream_t)stream);
+  s.stats = stats;
+  ConvParams p;
+  int grid = 0;
+  size_t smem = 0;
+  if (conv_prepare(s, &p, &grid, &smem)) return 1;
+  if (grid > kStatsMaxRows) p.stats = nullptr;
+  if (conv_launch_prepared(p, grid, smem, (cudaStream_t)stream)) return 1;
+  *stats_rows = p.stats ? grid : 0;          // 0: this shape has no fused statistics, run the separate reduction
+  return 0;
 }
 
 stl_plan* stl_plan_create(const stl_hrnet_cfg* cfg) {
@@ -311,6 +332,17 @@ int stl_bn_train_forward_ticket(const void* z, const float* gamma, const float* 
   typedef const __nv_bfloat16* P;
   return bn_train_forward((P)z, gamma, beta, (P)residual, relu, eps, momentum, N, H, W, C, (__nv_bfloat16*)y, sums, mean,
                           rstd, running_mean, running_var, ticket, (cudaStream_t)stream);
+}
+
+int stl_bn_train_forward_fused(const void* z, const float* stat_rows, int rows, int c_pad, const float* gamma,
+                               const float* beta, const void* residual, int relu, float eps, float momentum, int N, int H,
+                               int W, int C, void* y, float* mean, float* rstd, float* running_mean, float* running_var,
+                               void* stream) {
+  if (!have_device()) return 1;
+  if (!z || !stat_rows || !gamma || !beta || !y || !mean || !rstd) { set_error("stl_bn_train_forward_fused: null pointer"); return 1; }
+  typedef const __nv_bfloat16* P;
+  return bn_train_forward_fused((P)z, stat_rows, rows, c_pad, gamma, beta, (P)residual, relu, eps, momentum, N, H, W, C,
+                                (__nv_bfloat16*)y, mean, rstd, running_mean, running_var, (cudaStream_t)stream);
 }
 
 int stl_bn_train_backward(const void* dy, const void* y, const void* z, const float* mean, const float* rstd,

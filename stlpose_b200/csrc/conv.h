@@ -51,7 +51,12 @@ struct ConvSpec {
                                            //    by the preceding kernel in the stream; activations may be)
   int img_lo = 0, img_hi = 0;              // stride-1 convs only: restrict the launch to images [img_lo, img_hi) (0,0 = all)
   void* dbg_counters = nullptr;            // optional [grid][3][4] int64 cycle counters (measurement aid)
+  // training: per-channel sum / sum of squares of the stored (bf16-rounded) outputs over the valid pixels, accumulated
+  // in the epilogue (BatchNorm batch statistics, HRnet.py:48-59 under model.train()).  [kStatsMaxRows][2][cout_pad]
+  // floats; the launch fills one row per CTA (conv_stats_rows() of them), a fixed-order second pass adds the rows.
+  float* stats = nullptr;
 };
+constexpr int kStatsMaxRows = 160;           // >= CTAs of any launch (one per SM)
 
 // Exact division of a 31-bit unsigned value by a small constant: q = (x * mul) >> shift  (mul < 2^32, 64-bit product).
 struct FastDiv {
@@ -89,6 +94,7 @@ struct ConvParams {
   int halo;        // rows in front of the tile in shift mode (Wp+1 for 3x3, 0 for 1x1)
   int a_box_rows, a_pieces;
   int a_stages, b_stages;
+  int b_taps;             // filter taps per streamed weight stage: 1, or 3 (a whole filter row per TMA box)
   int pair;        // 1: launched as clusters of two CTAs sharing cta_group::2 MMAs (M = 256)
   int n_mma;       // MMA-issuing warps (2 in burst mode with >= 2 blocks per tile)
   int b_resident;  // 1: all weight tiles of the layer stay in shared memory for the whole kernel
@@ -122,6 +128,7 @@ struct ConvParams {
   int cout, cout_pad;
   int pdl;                // launched with programmatic stream serialization
   int dbg_skip_epilogue;  // measurement only
+  float* stats;           // see ConvSpec::stats (null: off)
   long long* dbg_counters;  // measurement only: [grid][3 roles][4] cycle counters, or null
 };
 

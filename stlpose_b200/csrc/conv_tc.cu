@@ -210,6 +210,32 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, const EpiPar
   }
 }
 
+// Column sums over a warp: every lane holds 16 values (one row, 16 channels); returns, in lane l, the sum over the 32
+// lanes of channel (l >> 1) & 15 (both lanes of a pair hold the same total).  Recursive halving: 16 shuffles, fixed order.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = h4 ? v[i + 8] : v[i], send = h4 ? v[i] : v[i + 8];
+    a[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = h3 ? a[i + 4] : a[i], send = h3 ? a[i] : a[i + 4];
+    b[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = h2 ? b[i + 2] : b[i], send = h2 ? b[i] : b[i + 2];
+    c[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 4);
+  }
+  const float keep = h1 ? c[1] : c[0], send = h1 ? c[0] : c[1];
+  const float d = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 2);
+  return d + __shfl_xor_sync(0xFFFFFFFFu, d, 1);
+}
+constexpr int kStatSlots = 8;   // (n-tile, panel, slice pair) combinations one epilogue warp can meet
+
 // MB    : 128-row accumulator blocks per tile (compile time so that the MMA issue loop fully unrolls)
 // KSTEPS: UMMA K-steps (16 channels each) per K chunk; the smem row / swizzle span is 32*KSTEPS bytes
 // TAPS  : 1 (1x1) or 9 (3x3)
@@ -219,7 +245,8 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, const EpiPar
 //         kEpiNchw   - fp32 NCHW store of the heatmap head
 // Code size matters here: ten warps run four different roles out of one instruction cache, so everything that
 // does not have to be unrolled is a rolled loop and every epilogue path exists exactly once per kernel.
-template <int MB, int KSTEPS, int TAPS, int EPI, bool PAIR>
+// STATS : (staged epilogues) also accumulate per-channel sum / sum of squares of the stored outputs (training, conv.h)
+template <int MB, int KSTEPS, int TAPS, int EPI, bool PAIR, bool STATS = false>
 __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle-128B atoms (8 rows x 128 B) must start on their natural boundary.
@@ -301,6 +328,11 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
 #define DBG_DUMP(role) do { } while (0)
 #endif
 
+  // STATS: per-lane accumulators of this warp's (n-tile, panel, slice pair) slots, see the staged epilogue
+  float st_sum[STATS ? kStatSlots : 1], st_sq[STATS ? kStatSlots : 1];
+#pragma unroll
+  for (int i = 0; i < (STATS ? kStatSlots : 1); ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; }
+
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
     uint32_t a_it = 0, b_it = 0;
@@ -359,7 +391,7 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
             ++a_it;
             DBG_TOCK(2);
           }
-          if (!p.b_resident) {
+          if (!p.b_resident && (p.b_taps == 1 || kw == 0)) {    // (b_taps == 3: one stage per filter row)
             const uint32_t s = b_it % p.b_stages, ph = (b_it / p.b_stages) & 1;
             mbar_wait(&ctl->b_empty[s], ph ^ 1);
             DBG_TOCK(1);
@@ -471,18 +503,21 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
               DBG_TOCK(1);
             }
             uint32_t bs;
+            const bool b_first = p.b_taps == 1 || kw == 0, b_last = p.b_taps == 1 || kw == 2;   // of this weight stage
             if (p.b_resident) {
               bs = (nti * p.n_chunks + chunk) * TAPS + tap;
             } else {
               bs = b_it % p.b_stages;
-              mbar_wait(&ctl->b_full[bs], (b_it / p.b_stages) & 1);
-              DBG_TOCK(2);
+              if (b_first) {
+                mbar_wait(&ctl->b_full[bs], (b_it / p.b_stages) & 1);
+                DBG_TOCK(2);
+              }
             }
             tc_fence_after();
             const bool release_a = !p.a_shift || tap == TAPS - 1;
             if (elect_one()) {
               const uint32_t a_lo = a_lo_base + a_stage * a_stage_u + (p.a_shift ? tap_u : 0u);
-              const uint32_t b_lo = b_lo_base + bs * b_stage_u;
+              const uint32_t b_lo = b_lo_base + bs * b_stage_u + (p.b_taps == 3 ? (uint32_t)kw * (b_stage_u / 3u) : 0u);
               const uint32_t first = (uint32_t)(chunk | tap);
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
@@ -495,15 +530,15 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
                 }
               }
               if (PAIR) {
-                if (!p.b_resident) umma_commit_pair(&ctl->b_empty[bs]);
+                if (!p.b_resident && b_last) umma_commit_pair(&ctl->b_empty[bs]);
                 if (release_a) umma_commit_pair(&ctl->a_empty[a_stage]);
               } else {
-                if (!p.b_resident) umma_commit(&ctl->b_empty[bs]);
+                if (!p.b_resident && b_last) umma_commit(&ctl->b_empty[bs]);
                 if (release_a) umma_commit(&ctl->a_empty[a_stage]);
               }
             }
             __syncwarp();
-            if (!p.b_resident) ++b_it;
+            if (!p.b_resident && b_last) ++b_it;
             if (release_a) ++a_it;
             tap_u += kSpan >> 4;
             if (++kw == 3) { kw = 0; tap_u += wp_u - 3 * (kSpan >> 4); }
@@ -798,7 +833,7 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
           // Written for instruction count (the drain competes with four other roles for issue slots): incremental
           // indices, the zero-cell test once per 128-row block, packed fp32x2 adds.
           int pi = 0, sl = sub, m_cached = -1;
-          bool is_pad = false;
+          bool is_pad = false, stat_ok = false;
           RowPos upos;          // structured tiles with upsampled addends: the output pixel of this thread's row
           upos.valid = false;
 #pragma unroll 1
@@ -809,8 +844,14 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
             uint32_t v[16];
             tmem_ld16(t_tile + (uint32_t)(m * nt + ch), v);
             if (m != m_cached) {
-              if (!kStruct) is_pad = row_position(p, mt, m * 128 + row0).is_pad;   // (structured tiles: valid pixels only)
-              else if (e.n_up) upos = row_position(p, mt, m * 128 + row0);
+              if (!kStruct) {
+                const RowPos rp = row_position(p, mt, m * 128 + row0);
+                is_pad = rp.is_pad;                                                  // (structured tiles: valid pixels only)
+                stat_ok = rp.valid && !rp.is_pad;
+              } else if (e.n_up || STATS) {
+                upos = row_position(p, mt, m * 128 + row0);
+                stat_ok = upos.valid;
+              }
               m_cached = m;
             }
             const uint32_t base = stage + (uint32_t)pi * panel_bytes + (uint32_t)row0 * pitch;
@@ -871,6 +912,26 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
             if (is_pad) { o0 = make_uint4(0, 0, 0, 0); o1 = o0; }  // zero cells of the padded layout stay zero
             sts128(ad0, o0);
             sts128(ad1, o1);
+            if constexpr (STATS) {
+              // batch statistics of the STORED values (what BatchNorm will normalise), valid pixels only
+              float r[16];
+              r[0] = bf16_lo(o0.x); r[1] = bf16_hi(o0.x); r[2] = bf16_lo(o0.y); r[3] = bf16_hi(o0.y);
+              r[4] = bf16_lo(o0.z); r[5] = bf16_hi(o0.z); r[6] = bf16_lo(o0.w); r[7] = bf16_hi(o0.w);
+              r[8] = bf16_lo(o1.x); r[9] = bf16_hi(o1.x); r[10] = bf16_lo(o1.y); r[11] = bf16_hi(o1.y);
+              r[12] = bf16_lo(o1.z); r[13] = bf16_hi(o1.z); r[14] = bf16_lo(o1.w); r[15] = bf16_hi(o1.w);
+              if (!stat_ok) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = 0.f;
+              }
+              const float cs = warp_colsum16(r, lane);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] *= r[i];
+              const float cq = warp_colsum16(r, lane);
+              const int slot = (nti * npanels + pn) * ((spp + 1) >> 1) + (sl >> 1);
+#pragma unroll
+              for (int k = 0; k < kStatSlots; ++k)
+                if (slot == k) { st_sum[k] += cs; st_sq[k] += cq; }
+            }
             sl += 2;
             if (sl >= spp) { sl = sub; ++pi; }
           }
@@ -953,6 +1014,35 @@ role_done:
 
   tc_fence_before();
   if (PAIR) cluster_sync(); else __syncthreads();  // PAIR: neither CTA may retire while the other can still signal it
+  if constexpr (STATS) {
+    // every MMA and every TMA transfer of this CTA has completed: the activation ring is free.  Each epilogue warp writes
+    // its slot accumulators to row (group, quarter) of an [8][2][cout_pad] table there (the two warps of a quarter own
+    // disjoint 16-channel slices), then the rows are added in a fixed order into this CTA's row of p.stats.
+    float* tab = reinterpret_cast<float*>(smem + p.ctl_bytes);
+    const int cp = p.cout_pad;
+    if (warp >= 2 && warp < 18 && !(lane & 1)) {
+      const int e_idx = warp - 2, group = e_idx >> 3, sub = (e_idx >> 2) & 1, quarter = warp & 3;
+      const int panel_ch = p.panel_ch, npanels = p.nt / panel_ch, spp = panel_ch >> 4, pairs = (spp + 1) >> 1;
+      float* row = tab + (size_t)(group * 4 + quarter) * 2 * cp;
+#pragma unroll
+      for (int k = 0; k < kStatSlots; ++k) {
+        const int sp = k % pairs, pnl = (k / pairs) % npanels, nti = k / (pairs * npanels);
+        const int sl = 2 * sp + sub;
+        if (nti < p.n_ntiles && sl < spp) {
+          const int ch = nti * p.nt + pnl * panel_ch + sl * 16 + ((lane >> 1) & 15);
+          row[ch] = st_sum[k];
+          row[cp + ch] = st_sq[k];
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * cp; i += (int)blockDim.x) {
+      float acc = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc += tab[(size_t)r * 2 * cp + i];
+      p.stats[(size_t)blockIdx.x * 2 * cp + i] = acc;
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     if (PAIR) tmem_dealloc_pair(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
@@ -1195,10 +1285,23 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     p.b_stage_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
     resident = (size_t)p.n_ntiles * p.n_chunks * p.taps * p.b_stage_bytes;
   }
+  // Streamed weights (C >= 128 layers): one ring stage holds the three taps of a filter ROW (one 3-D TMA box), so the
+  // issuing warp waits for weights and commits the slot back once per 3 x KSTEPS x MB MMAs instead of once per
+  // KSTEPS x MB.  Measured on B200 with the per-role counters (gpurun_out/r02_convprobe*.txt): with one tap per stage
+  // the leader spends 52 % of its time waiting for the next stage although the ring is full - a fixed ~450 cycles per
+  // (wait, MMAs, commit) round that neither the ring depth nor the bytes moved change.  STL_DBG_B_TAPS=1 restores it.
+  const bool will_stream = !(resident <= 120 * 1024 && resident + 2 * (size_t)p.a_stage_bytes <= budget &&
+                             resident < (1u << 20) && !getenv("STL_DBG_NO_RESIDENT"));
+  p.b_taps = 1;
+  if (will_stream && p.taps == 9 && p.b_tx_bytes % 1024 == 0 && !(getenv("STL_DBG_B_TAPS") && atoi(getenv("STL_DBG_B_TAPS")) == 1)) {
+    p.b_taps = 3;
+    p.b_tx_bytes *= 3;
+    p.b_stage_bytes = p.b_tx_bytes;
+  }
   {
     cuuint64_t dims[3] = {(cuuint64_t)gi.C, (cuuint64_t)s.cout_pad, (cuuint64_t)p.taps};
     cuuint64_t strides[2] = {(cuuint64_t)gi.C * 2, (cuuint64_t)gi.C * 2 * s.cout_pad};
-    cuuint32_t box[3] = {(cuuint32_t)p.ck, (cuuint32_t)(p.pair ? p.nt / 2 : p.nt), 1};
+    cuuint32_t box[3] = {(cuuint32_t)p.ck, (cuuint32_t)(p.pair ? p.nt / 2 : p.nt), (cuuint32_t)p.b_taps};
     cuuint32_t es[3] = {1, 1, 1};
     if (encode(&p.tmB, s.weights, 3, dims, strides, box, es, span)) return 1;
   }
@@ -1219,7 +1322,7 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     auto used = [&](int a, int b) { return (size_t)a * p.a_stage_bytes + (size_t)b * p.b_stage_bytes; };
     if (used(2, 2) > budget) a_st = 1;
     if (used(a_st, b_st) > budget) { set_error("conv: tile does not fit shared memory"); return 1; }
-    const int b_want = 8;
+    const int b_want = p.b_taps == 3 ? 4 : 8;
     bool grew = true;
     while (grew) {
       grew = false;
@@ -1237,6 +1340,21 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     s2.kw_merge = -1;
     return conv_prepare(s2, pp, grid, smem_bytes);
   }
+  // BatchNorm statistics in the epilogue (training): staged epilogues only, at most kStatSlots (n-tile, panel, slice
+  // pair) slots per epilogue warp, and the [8][2][cout_pad] reduction table must fit the activation ring it reuses.
+  // Correct (tests/test_train_kernels_gpu.py::test_conv_epilogue_statistics) but not faster: the epilogue's 32 shuffles
+  // per 16-channel unit cost the forward convolutions +24 %, and the row reduction that replaces the statistics pass is
+  // one more launch - 40.2 vs 39.8 ms per step at batch 128, 17.9 vs 17.3 at batch 32 - so the variants are compiled
+  // only with -DSTL_CONV_STATS and stl_conv2d_stats reports "no fused statistics" otherwise.
+  p.stats = nullptr;
+#ifdef STL_CONV_STATS
+  if (s.stats) {
+    const int spp = p.panel_ch / 16, npanels = p.nt / p.panel_ch;
+    if (p.epi_tma && !kwm && s.cout == s.cout_pad && p.n_ntiles * npanels * ((spp + 1) / 2) <= kStatSlots &&
+        (size_t)64 * s.cout_pad <= (size_t)a_st * p.a_stage_bytes)
+      p.stats = s.stats;
+  }
+#endif
   // measured on B200: a second issuer pays off only for N <= 32 (16-cycle MMAs); at N = 64 the two streams interfere
   p.n_mma = (p.b_resident && (p.a_shift || p.taps == 1) && p.mb >= 2 && p.nt <= 32 && !getenv("STL_DBG_SINGLE_MMA")) ? 2 : 1;
   *smem_bytes = p.ctl_bytes + 1024 + (size_t)a_st * p.a_stage_bytes + p.b_bytes_total + epi_bytes;
@@ -1269,6 +1387,7 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   p.pdl = s.pdl;
   p.dbg_skip_epilogue = getenv("STL_DBG_SKIP_EPILOGUE") ? 1 : (getenv("STL_DBG_SKIP_STORE") ? 2 : 0);
   p.dbg_counters = reinterpret_cast<long long*>(s.dbg_counters);
+  // (p.stats was decided above, next to the stage counts)
   p.cout = s.cout;
   p.cout_pad = s.cout_pad;
 
@@ -1303,7 +1422,17 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
 namespace {
 typedef void (*ConvKernel)(const ConvParams);
 template <int MB, int KSTEPS>
-ConvKernel pick_variant(int taps, int epi, bool pair) {
+ConvKernel pick_variant(int taps, int epi, bool pair, bool stats) {
+  if (stats) {   // training convolutions with BatchNorm statistics in the epilogue: the two staged epilogues only
+#ifndef STL_CONV_STATS
+    return nullptr;   // measured-negative: only in builds made with -DSTL_CONV_STATS
+#else
+    if (epi == kEpiStagedS2) return taps == 9 ? conv_tc_kernel<MB, KSTEPS, 9, kEpiStagedS2, false, true> : nullptr;
+    if (epi != kEpiStaged) return nullptr;
+    if (pair) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiStaged, true, true> : conv_tc_kernel<MB, KSTEPS, 9, kEpiStaged, true, true>;
+    return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiStaged, false, true> : conv_tc_kernel<MB, KSTEPS, 9, kEpiStaged, false, true>;
+#endif
+  }
   if (epi == kEpiNchw) return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiNchw, false> : nullptr;
   if (epi == kEpiStagedS2) return taps == 9 ? conv_tc_kernel<MB, KSTEPS, 9, kEpiStagedS2, false> : nullptr;
   if (epi == kEpiStagedKW) {
@@ -1319,19 +1448,19 @@ ConvKernel pick_variant(int taps, int epi, bool pair) {
   return taps == 1 ? conv_tc_kernel<MB, KSTEPS, 1, kEpiDirect, false> : conv_tc_kernel<MB, KSTEPS, 9, kEpiDirect, false>;
 }
 template <int MB>
-ConvKernel pick_ksteps(int ksteps, int taps, int epi, bool pair) {
+ConvKernel pick_ksteps(int ksteps, int taps, int epi, bool pair, bool stats) {
   switch (ksteps) {
-    case 1: return pick_variant<MB, 1>(taps, epi, pair);
-    case 2: return pick_variant<MB, 2>(taps, epi, pair);
-    case 4: return pick_variant<MB, 4>(taps, epi, pair);
+    case 1: return pick_variant<MB, 1>(taps, epi, pair, stats);
+    case 2: return pick_variant<MB, 2>(taps, epi, pair, stats);
+    case 4: return pick_variant<MB, 4>(taps, epi, pair, stats);
   }
   return nullptr;
 }
-ConvKernel pick_kernel(int mb, int ksteps, int taps, int epi, bool pair) {
+ConvKernel pick_kernel(int mb, int ksteps, int taps, int epi, bool pair, bool stats = false) {
   switch (mb) {
-    case 1: return pick_ksteps<1>(ksteps, taps, epi, pair);
-    case 2: return pick_ksteps<2>(ksteps, taps, epi, pair);
-    case 3: return pick_ksteps<3>(ksteps, taps, epi, pair);
+    case 1: return pick_ksteps<1>(ksteps, taps, epi, pair, stats);
+    case 2: return pick_ksteps<2>(ksteps, taps, epi, pair, stats);
+    case 3: return pick_ksteps<3>(ksteps, taps, epi, pair, stats);
   }
   return nullptr;
 }
@@ -1347,18 +1476,19 @@ int conv_launch_prepared(const ConvParams& p, int grid, size_t smem_bytes, cudaS
           for (int ks = 1; ks <= 4; ks *= 2)
             for (int epi = 0; epi < 5; ++epi)
               for (int taps = 1; taps <= 9; taps += 8)
-                for (int pair = 0; pair < 2; ++pair) {
-                  if (pair && epi != kEpiStaged) continue;
-                  ConvKernel k = pick_kernel(mb, ks, taps, epi, pair != 0);
-                  if (!k) continue;
-                  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-                  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
-                }
+                for (int pair = 0; pair < 2; ++pair)
+                  for (int stats = 0; stats < 2; ++stats) {
+                    if (pair && epi != kEpiStaged) continue;
+                    ConvKernel k = pick_kernel(mb, ks, taps, epi, pair != 0, stats != 0);
+                    if (!k) continue;
+                    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+                    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+                  }
         return 0;
       }))
     return 1;
   if (grid <= 0) return 0;
-  ConvKernel kern = pick_kernel(p.mb, p.ck / 16, p.taps, epi_kind(p), p.pair != 0);
+  ConvKernel kern = pick_kernel(p.mb, p.ck / 16, p.taps, epi_kind(p), p.pair != 0, p.stats != nullptr);
   if (!kern) { set_error("conv: no kernel for mb %d ck %d taps %d nchw %d", p.mb, p.ck, p.taps, p.out_nchw); return 1; }
   cudaError_t e;
   if (p.pair || p.pdl) {

@@ -222,6 +222,49 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
   }
 }
 
+// BatchNorm statistics from the per-CTA rows the convolution epilogue wrote (conv.h ConvSpec::stats: rows x [2][c_pad]
+// floats = sum | sum of squares of the stored conv outputs over the valid pixels): rows added in a fixed order (four
+// independent partial sums per channel), then mean / rstd and the running-statistics update exactly like the tail of
+// channel_reduce_kernel<0>.
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ rows_, int rows, int C, int c_pad,
+                                                          const BnFinalize fin) {
+  // block = 32 channels x 8 row groups: group g adds rows g, g + 8, ... with four independent partial sums per statistic
+  // (8 loads in flight per thread; a single thread per channel walking all ~148 rows was latency-bound at ~12 us), the
+  // groups are then combined in order through shared memory
+  __shared__ float part[2][8][32];
+  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5, c = blockIdx.x * 32 + cl;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    int r = g;
+    for (; r + 24 < rows; r += 32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s[k] += __ldcg(rows_ + (size_t)(r + 8 * k) * 2 * c_pad + c);
+        q[k] += __ldcg(rows_ + (size_t)(r + 8 * k) * 2 * c_pad + c_pad + c);
+      }
+    }
+    for (; r < rows; r += 8) { s[0] += __ldcg(rows_ + (size_t)r * 2 * c_pad + c); q[0] += __ldcg(rows_ + (size_t)r * 2 * c_pad + c_pad + c); }
+  }
+  part[0][g][cl] = (s[0] + s[1]) + (s[2] + s[3]);
+  part[1][g][cl] = (q[0] + q[1]) + (q[2] + q[3]);
+  __syncthreads();
+  if (g == 0 && c < C) {
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sum += part[0][k][cl]; sq += part[1][k][cl]; }
+    const float m = sum / fin.count;
+    float var = sq / fin.count - m * m;
+    var = var > 0.f ? var : 0.f;
+    fin.mean[c] = m;
+    fin.rstd[c] = rsqrtf(var + fin.eps);
+    if (fin.run_mean) {
+      const float unbiased = fin.count > 1.f ? var * fin.count / (fin.count - 1.f) : var;
+      fin.run_mean[c] = (1.f - fin.momentum) * fin.run_mean[c] + fin.momentum * m;
+      fin.run_var[c] = (1.f - fin.momentum) * fin.run_var[c] + fin.momentum * unbiased;
+    }
+  }
+}
+
 // y = [relu]( gamma * (z - mean) * rstd + beta [+ residual] ) on the valid pixels, zero on the zero cells
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ z,
                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -610,6 +653,24 @@ int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* be
   px.init(C, H, W);
   if (pixels * (C / 8) >= (1ll << 31)) { set_error("bn_train_forward: tensor too large for 32-bit item indexing"); return 1; }
   if (256 % (C / 8) && (C / 8) % 3) { set_error("bn_train_forward: C=%d unsupported", C); return 1; }
+  bn_apply_kernel<<<grid_mult(pixels * (C / 8), C / 8), 256, 0, st>>>(z, mean, rstd, gamma, beta, residual, relu, y, N, H,
+                                                                  W, C, px);
+  return check("bn apply");
+}
+
+int bn_train_forward_fused(const __nv_bfloat16* z, const float* stat_rows, int rows, int c_pad, const float* gamma,
+                           const float* beta, const __nv_bfloat16* residual, int relu, float eps, float momentum, int N,
+                           int H, int W, int C, __nv_bfloat16* y, float* mean, float* rstd, float* run_mean, float* run_var,
+                           cudaStream_t st) {
+  if (C % 8 || C > 2048 || rows < 1 || c_pad < C) { set_error("bn_train_forward_fused: bad arguments"); return 1; }
+  const long long pixels = (long long)N * (H + 1) * (W + 1);
+  BnFinalize fin{(float)((long long)N * H * W), eps, momentum, mean, rstd, run_mean, run_var};
+  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(stat_rows, rows, C, c_pad, fin);
+  if (check("bn finalize")) return 1;
+  PixIdx px;
+  px.init(C, H, W);
+  if (pixels * (C / 8) >= (1ll << 31)) { set_error("bn_train_forward_fused: tensor too large for 32-bit item indexing"); return 1; }
+  if (256 % (C / 8) && (C / 8) % 3) { set_error("bn_train_forward_fused: C=%d unsupported", C); return 1; }
   bn_apply_kernel<<<grid_mult(pixels * (C / 8), C / 8), 256, 0, st>>>(z, mean, rstd, gamma, beta, residual, relu, y, N, H,
                                                                   W, C, px);
   return check("bn apply");

@@ -138,8 +138,15 @@ def _pack_weights_dgrad(w, k_pad):
     return wp, _zero_bias(rows_pad, w.device), rows_pad
 
 
-def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bias=None):
-    """Tensor-core convolution on a padded bf16 tensor; returns padded bf16 [N,Ho+1,Wo+1,cout] (or fp32 NCHW)."""
+# BatchNorm statistics accumulated by the convolution's epilogue (stl_conv2d_stats).  Measured slower than the separate
+# statistics pass on B200, so it is off and the kernel variants are only in -DSTL_CONV_STATS builds.
+FUSED_BN_STATS = os.environ.get("STLPOSE_FUSED_BN_STATS", "0") == "1"
+
+
+def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bias=None, stats=None):
+    """Tensor-core convolution on a padded bf16 tensor; returns padded bf16 [N,Ho+1,Wo+1,cout] (or fp32 NCHW).
+    stats: an fp32 buffer of stl_conv2d_stats_floats(cout_pad) elements -> returns (out, rows): the epilogue also left
+    `rows` rows of per-channel sum / sum of squares there (rows == 0: not for this shape)."""
     L = _lib.lib()
     n, hp, wpd, cin = x.shape
     h, w = hp - 1, wpd - 1
@@ -157,6 +164,10 @@ def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bi
     d.ksize, d.stride = k, stride
     d.w_packed = wp.data_ptr(); d.bias_packed = (bias if bias is not None else bp).data_ptr()
     d.relu = 0; d.out_nchw = int(out_nchw)
+    if stats is not None:
+        rows = ctypes.c_int(0)
+        _lib.check(L.stl_conv2d_stats(ctypes.byref(d), _lib.ptr(stats), ctypes.byref(rows), _stream()))
+        return out, rows.value
     _lib.check(L.stl_conv2d(ctypes.byref(d), _stream()))
     return out
 
@@ -252,17 +263,29 @@ class _ConvBN(torch.autograd.Function):
         h, w = hp - 1, wpd - 1
         cout, cin_real, k, _ = weight.shape
         wp, bp, cout_pad = _pack_weights(weight, cin_pad)
-        z = _conv_raw(x, wp, bp, cout, cout_pad, k, stride)
         ho, wo = h // stride, w // stride
-        y = torch.empty_like(z)
-        sums = torch.empty(L.stl_bn_workspace_floats(cout), dtype=torch.float32, device=x.device)
         mean = torch.empty(cout, dtype=torch.float32, device=x.device)
         rstd = torch.empty(cout, dtype=torch.float32, device=x.device)
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        _lib.check(L.stl_bn_train_forward_ticket(_lib.ptr(z), _lib.ptr(g32), _lib.ptr(b32), _lib.ptr(residual), int(relu),
-                                                 BN_EPS, float(momentum), n, ho, wo, cout, _lib.ptr(y), _lib.ptr(sums),
-                                                 _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(run_mean), _lib.ptr(run_var),
-                                                 tickets.data_ptr(), _stream()))
+        rows = 0
+        if FUSED_BN_STATS and cout == cout_pad:
+            # the convolution's epilogue accumulates the batch statistics of z: no separate pass over the tensor
+            part = torch.empty(L.stl_conv2d_stats_floats(cout_pad), dtype=torch.float32, device=x.device)
+            z, rows = _conv_raw(x, wp, bp, cout, cout_pad, k, stride, stats=part)
+        else:
+            z = _conv_raw(x, wp, bp, cout, cout_pad, k, stride)
+        y = torch.empty_like(z)
+        if rows > 0:
+            _lib.check(L.stl_bn_train_forward_fused(_lib.ptr(z), _lib.ptr(part), rows, cout_pad, _lib.ptr(g32), _lib.ptr(b32),
+                                                    _lib.ptr(residual), int(relu), BN_EPS, float(momentum), n, ho, wo, cout,
+                                                    _lib.ptr(y), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(run_mean),
+                                                    _lib.ptr(run_var), _stream()))
+        else:
+            sums = torch.empty(L.stl_bn_workspace_floats(cout), dtype=torch.float32, device=x.device)
+            _lib.check(L.stl_bn_train_forward_ticket(_lib.ptr(z), _lib.ptr(g32), _lib.ptr(b32), _lib.ptr(residual),
+                                                     int(relu), BN_EPS, float(momentum), n, ho, wo, cout, _lib.ptr(y),
+                                                     _lib.ptr(sums), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(run_mean),
+                                                     _lib.ptr(run_var), tickets.data_ptr(), _stream()))
         ctx.tickets = tickets
         ctx.sinks = sinks
         ctx.save_for_backward(x, weight, z, y, mean, rstd, g32)

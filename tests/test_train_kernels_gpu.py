@@ -221,3 +221,60 @@ def test_stride2_gradients_via_zero_stuffing(cin, cout, hw, n):
     assert (_unpadded(dx) - xr.grad).abs().max().item() < 2e-2 * max(1.0, xr.grad.abs().max().item())
     dw = training.conv_wgrad(_padded(x), dzp, wt.shape, n, h, w, 2)
     assert (dw - wr.grad).abs().max().item() < 1e-3 * wr.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,hw,n", [
+    (32, 32, 3, 1, (64, 48), 3), (64, 64, 3, 1, (32, 24), 3), (128, 128, 3, 1, (16, 12), 5), (256, 256, 3, 1, (8, 6), 7),
+    (64, 256, 1, 1, (64, 48), 2), (256, 64, 1, 1, (64, 48), 2), (256, 32, 3, 1, (64, 48), 2), (16, 64, 3, 2, (128, 96), 2),
+    (64, 64, 3, 2, (128, 96), 2), (32, 64, 3, 2, (64, 48), 3), (128, 256, 3, 2, (16, 12), 3), (48, 48, 3, 1, (96, 72), 2),
+    (96, 192, 3, 2, (48, 36), 2), (384, 384, 3, 1, (12, 9), 3), (192, 48, 1, 1, (24, 18), 2), (32, 32, 3, 1, (8, 6), 1)])
+def test_conv_epilogue_statistics(cin, cout, k, stride, hw, n):
+    """stl_conv2d_stats: per-channel sum / sum of squares of the stored conv output, accumulated in the epilogue, vs the
+    sums of the output tensor itself; fixed-order reduction -> bit-reproducible; the normalisation that follows equals
+    the stand-alone BatchNorm kernel's up to fp32 summation order."""
+    from stlpose_b200 import training
+    L = _lib.lib()
+    h, w = hw
+    g = torch.Generator(device=DEV).manual_seed(cin + cout + k + stride)
+    cin_real = 3 if cin == 16 else cin
+    x = bf16_round(torch.randn(n, cin_real, h, w, device=DEV, generator=g))
+    wt = torch.randn(cout, cin_real, k, k, device=DEV, generator=g) / (cin_real * k * k) ** 0.5
+    xp = to_padded(x, cin).view(torch.bfloat16).view(n, h + 1, w + 1, cin)
+    wp, bp, cout_pad = training._pack_weights(wt, cin)
+    part = torch.full((L.stl_conv2d_stats_floats(cout_pad),), float("nan"), device=DEV)
+    z, rows = training._conv_raw(xp, wp, bp, cout, cout_pad, k, stride, stats=part)
+    ho, wo = h // stride, w // stride
+    if rows == 0:
+        pytest.skip("no fused statistics for this shape (falls back to the reduction kernel)")
+    tab = part[: rows * 2 * cout_pad].view(rows, 2, cout_pad).double().sum(0)
+    zf = _unpadded(z).double()
+    ref_s, ref_q = zf.sum(dim=(0, 2, 3)), (zf * zf).sum(dim=(0, 2, 3))
+    assert (tab[0, :cout] - ref_s).abs().max().item() <= 1e-4 * max(1.0, ref_s.abs().max().item())
+    assert (tab[1, :cout] - ref_q).abs().max().item() <= 1e-4 * ref_q.abs().max().item()
+    part2 = torch.zeros_like(part)
+    z2, rows2 = training._conv_raw(xp, wp, bp, cout, cout_pad, k, stride, stats=part2)
+    assert rows2 == rows and torch.equal(part[: rows * 2 * cout_pad], part2[: rows * 2 * cout_pad]) and torch.equal(z, z2)
+    assert (z[:, ho] == 0).all() and (z[:, :, wo] == 0).all()
+    # finalize + apply vs the stand-alone statistics kernel
+    gamma = torch.rand(cout, device=DEV, generator=g) + 0.5
+    beta = torch.randn(cout, device=DEV, generator=g) * 0.1
+    outs = []
+    for fused in (True, False):
+        y = torch.empty_like(z)
+        mean, rstd = torch.empty(cout, device=DEV), torch.empty(cout, device=DEV)
+        rm, rv = torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV)
+        if fused:
+            _lib.check(L.stl_bn_train_forward_fused(_lib.ptr(z), _lib.ptr(part), rows, cout_pad, _lib.ptr(gamma), _lib.ptr(beta),
+                                                    None, 1, 1e-5, 0.1, n, ho, wo, cout, _lib.ptr(y), _lib.ptr(mean),
+                                                    _lib.ptr(rstd), _lib.ptr(rm), _lib.ptr(rv), _lib.current_stream()))
+        else:
+            sums = torch.empty(L.stl_bn_workspace_floats(cout), device=DEV)
+            _lib.check(L.stl_bn_train_forward(_lib.ptr(z), _lib.ptr(gamma), _lib.ptr(beta), None, 1, 1e-5, 0.1, n, ho, wo,
+                                              cout, _lib.ptr(y), _lib.ptr(sums), _lib.ptr(mean), _lib.ptr(rstd),
+                                              _lib.ptr(rm), _lib.ptr(rv), _lib.current_stream()))
+        outs.append((y, mean, rstd, rm, rv))
+    (ya, ma, ra, rma, rva), (yb, mb, rb, rmb, rvb) = outs
+    assert (ma - mb).abs().max().item() < 1e-5 * max(1.0, mb.abs().max().item())
+    assert ((ra - rb).abs() / rb).max().item() < 1e-4
+    assert (rma - rmb).abs().max().item() < 1e-5 and ((rva - rvb).abs() / rvb).max().item() < 1e-4
+    assert (_unpadded(ya) - _unpadded(yb)).abs().max().item() <= 2 ** -7 * max(1.0, _unpadded(yb).abs().max().item())

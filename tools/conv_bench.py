@@ -24,6 +24,8 @@ CASES = {
     "c64nr": dict(cin=64, cout=64, H=32, W=24, k=3, stride=1, res=False),
     "c128": dict(cin=128, cout=128, H=16, W=12, k=3, stride=1, res=True),
     "c256": dict(cin=256, cout=256, H=8, W=6, k=3, stride=1, res=True),
+    "w48c48": dict(cin=48, cout=48, H=96, W=72, k=3, stride=1, res=True),      # HRNet-W48 384x288: the high-resolution branch
+    "w48c96": dict(cin=96, cout=96, H=48, W=36, k=3, stride=1, res=True),
     "c128nr": dict(cin=128, cout=128, H=16, W=12, k=3, stride=1, res=False),
     "c256nr": dict(cin=256, cout=256, H=8, W=6, k=3, stride=1, res=False),
     "l1c1": dict(cin=256, cout=64, H=64, W=48, k=1, stride=1, res=False),
