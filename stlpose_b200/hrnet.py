@@ -159,6 +159,8 @@ class PoseHighResolutionNet(nn.Module):
         # ---- device-side state ---------------------------------------------------------------------
         self._plans = {}          # (H, W) -> plan handle
         self._arena = None        # packed bf16 weights + fp32 biases (layout shared by all plans)
+        self._buffer_generation = 0   # bumped whenever the arena or a workspace is (re)allocated: captured graphs hold
+                                      # the old addresses and must be re-captured (KeypointPipeline checks it)
         self._arena_sig = None
         self._workspaces = {}     # (H, W) -> activation workspace (one per plan: each plan owns its zero cells)
         self._image_size = tuple(kwargs.get("image_size", (256, 192)))
@@ -197,6 +199,7 @@ class PoseHighResolutionNet(nn.Module):
         r = super()._apply(fn, *args, **kwargs)
         self._arena = None
         self._workspaces = {}
+        self._buffer_generation += 1
         self.invalidate_packed_weights()
         return r
 
@@ -229,6 +232,7 @@ class PoseHighResolutionNet(nn.Module):
         nbytes = L.stl_plan_weight_bytes(plan)
         if self._arena is None or self._arena.numel() != nbytes or self._arena.device != dev:
             self._arena = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            self._buffer_generation += 1
         sd = dict(self.named_parameters())
         sd.update(dict(self.named_buffers()))
         info = _lib.ConvInfo()
@@ -287,6 +291,7 @@ class PoseHighResolutionNet(nn.Module):
                 self._workspaces.pop((H, W), None)
                 ws = None
                 ws = self._workspaces[(H, W)] = torch.empty(need, dtype=torch.uint8, device=x.device)
+                self._buffer_generation += 1
             _lib.check(L.stl_plan_forward(plan, _lib.ptr(x), B, int(flip_pair), _lib.ptr(heat), _lib.ptr(self._arena),
                                           _lib.ptr(ws), ws.numel(), _lib.current_stream()))
         return heat
@@ -308,6 +313,7 @@ class PoseHighResolutionNet(nn.Module):
             ws = self._workspaces.get((H, W))
             if ws is None or ws.numel() < need:
                 ws = self._workspaces[(H, W)] = torch.empty(need, dtype=torch.uint8, device=x.device)
+                self._buffer_generation += 1
             n_ops = L.stl_plan_launches_per_forward(plan)
             ms = (ctypes.c_float * n_ops)()
             _lib.check(L.stl_plan_forward_timed(plan, _lib.ptr(x), B, int(flip_pair), _lib.ptr(heat),

@@ -50,12 +50,20 @@ class ShardedKeypointInference:
     ranks return the full, ordered result.  The model must already live on this rank's GPU.
     """
 
-    def __init__(self, model, flip=True, group=None):
-        self.model, self.flip, self.group = model, flip, group
+    def __init__(self, model, flip=True, group=None, use_graph=True):
+        self.model, self.flip, self.group, self.use_graph = model, flip, group, use_graph
+        self._pipes = {}           # (local batch, H, W) -> KeypointPipeline: the slice runs as one captured graph replay
+
+    def _pipeline(self, n_local, h, w):
+        from .pipeline import KeypointPipeline
+        key = (n_local, h, w)
+        if key not in self._pipes:
+            if len(self._pipes) >= 4:                      # a few batch sizes (full batches + the last, short one)
+                self._pipes.pop(next(iter(self._pipes)))
+            self._pipes[key] = KeypointPipeline(self.model, n_local, (h, w), flip=self.flip, use_graph=self.use_graph)
+        return self._pipes[key]
 
     def run(self, imgs, center, scale):
-        from .inference import forward_pass
-        from .pose_parsing import get_final_preds_hrnet
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         n = imgs.shape[0]
@@ -63,11 +71,14 @@ class ShardedKeypointInference:
         dev = self.model.conv1.weight.device
         J = self.model.num_joints
         if hi > lo:
-            x = imgs[lo:hi].to(dev, non_blocking=True)
-            heat = forward_pass(self.model, x, "HRNet", device=dev, flip=self.flip)
-            c = torch.as_tensor(center[lo:hi]).to(dev)
-            s = torch.as_tensor(scale[lo:hi]).to(dev)
-            preds, maxvals, _ = get_final_preds_hrnet(heat, c, s, as_tensor=True)
+            # forward (+ mirrored forward) + flip-average + decode of this rank's slice: one graph replay
+            # (stlpose_b200.pipeline), not ~270 eager launches
+            pipe = self._pipeline(hi - lo, imgs.shape[2], imgs.shape[3])
+            pipe.x.copy_(imgs[lo:hi], non_blocking=True)
+            pipe.center.copy_(torch.as_tensor(center[lo:hi]), non_blocking=True)
+            pipe.scale.copy_(torch.as_tensor(scale[lo:hi]), non_blocking=True)
+            pipe.step()
+            preds, maxvals = pipe.preds.clone(), pipe.maxvals.clone()
         else:
             preds = torch.zeros((0, J, 2), dtype=torch.float32, device=dev)
             maxvals = torch.zeros((0, J, 1), dtype=torch.float32, device=dev)

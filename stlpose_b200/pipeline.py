@@ -42,6 +42,16 @@ class KeypointPipeline:
         self._calls = 0
         self.graph = None
         self._stage_graphs = None                    # one graph per staging buffer: the end-to-end call skips the copy into x
+        self._use_graph = bool(use_graph)
+        self._capture()
+
+    def _capture(self):
+        """(Re)build the captured steps.  The graphs hold raw addresses of the model's weight arena and activation
+        workspace; the model bumps ``_buffer_generation`` whenever it reallocates either (a larger eager batch at the
+        same resolution, ``.to()`` / ``.cuda()``), and ``_ensure_current`` re-captures before the next replay."""
+        model, dev, use_graph = self.model, self.device, self._use_graph
+        H, W = self.x.shape[2], self.x.shape[3]
+        self.graph, self._stage_graphs = None, None
         with torch.cuda.device(dev):
             self._step_eager()                       # packs weights, binds the workspace, warms everything up
             torch.cuda.synchronize()
@@ -63,6 +73,14 @@ class KeypointPipeline:
                     with torch.cuda.graph(gj):
                         self._step_eager(self._stage[j])
                     self._stage_graphs.append(gj)
+        self._generation = model._buffer_generation
+
+    def _ensure_current(self):
+        if self.model._buffer_generation != self._generation:
+            if self.model.conv1.weight.device != self.device:
+                raise _lib.StlError("the model was moved to another device after the pipeline was built")
+            torch.cuda.synchronize(self.device)
+            self._capture()
 
     def _step_eager(self, x=None):
         L = _lib.lib()
@@ -76,6 +94,7 @@ class KeypointPipeline:
 
     def step(self):
         """Run one batch from the static device buffers (x, center, scale) into (preds, maxvals, coords)."""
+        self._ensure_current()
         if self.graph is not None:
             self.graph.replay()
         else:
@@ -88,6 +107,7 @@ class KeypointPipeline:
         copy stream (double buffered, so the copy of the next call overlaps this call's network pass); the step is
         replayed from a graph that reads the staging buffer directly (``self.x`` is only the input of ``step()``).
         Synchronise the current stream before reading the returned host tensors."""
+        self._ensure_current()
         cur = torch.cuda.current_stream(self.device)
         j = self._calls & 1
         self._calls += 1

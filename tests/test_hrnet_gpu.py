@@ -114,6 +114,43 @@ def test_pipeline_graph_matches_eager_calls():
         assert np.array_equal(p_host.numpy(), preds) and np.array_equal(m_host.numpy(), maxv)
 
 
+def test_pipeline_recaptures_when_the_model_reallocates_its_buffers():
+    """The captured steps hold raw addresses of the model's workspace and weight arena: an eager call with a
+    larger batch at the same resolution makes the model reallocate its workspace; the pipeline must notice (generation
+    counter) and re-capture instead of replaying into freed memory.  ShardedKeypointInference runs its slice through
+    the same captured pipeline and must agree with the eager path."""
+    import stlpose_b200 as S
+    from stlpose_b200.parallel import ShardedKeypointInference
+    from stlpose_b200.pipeline import KeypointPipeline
+    B = 3
+    m = _model(32, (256, 192))
+    pipe = KeypointPipeline(m, B, (256, 192), flip=True, use_graph=True)
+    x = torch.randn(B, 3, 256, 192, generator=torch.Generator().manual_seed(4))
+    c_np, s_np = pose_oracle.synth_boxes(B, seed=4)
+    c, s = torch.from_numpy(c_np).float(), torch.from_numpy(s_np).float()
+    pipe.x.copy_(x); pipe.center.copy_(c); pipe.scale.copy_(s)
+    pipe.step()
+    torch.cuda.synchronize()
+    before = (pipe.preds.clone(), pipe.maxvals.clone())
+    gen = pipe._generation
+    big = torch.randn(24, 3, 256, 192, generator=torch.Generator().manual_seed(5)).cuda()
+    keep = [torch.empty(64 << 20, dtype=torch.uint8, device="cuda") for _ in range(4)]     # churn the allocator
+    m(big)                                                    # larger workspace at the same (H, W): reallocation
+    del keep
+    torch.randn(1 << 24, device="cuda").mul_(3.0)             # scribble over whatever was freed
+    assert m._buffer_generation != gen
+    pipe.step()
+    torch.cuda.synchronize()
+    assert pipe._generation == m._buffer_generation
+    assert torch.equal(pipe.preds, before[0]) and torch.equal(pipe.maxvals, before[1])
+    sh = ShardedKeypointInference(m, flip=True)               # one process: the whole batch is this rank's slice
+    preds, maxv = sh.run(x, c_np.astype(np.float32), s_np.astype(np.float32))
+    assert torch.equal(preds, before[0]) and torch.equal(maxv, before[1])
+    heat = S.forward_pass(m, x.cuda(), "HRNet", device="cuda", flip=True)
+    p2, m2, _ = S.get_final_preds_hrnet(heat, c_np.astype(np.float32), s_np.astype(np.float32))
+    assert np.array_equal(preds.cpu().numpy(), p2) and np.array_equal(maxv.cpu().numpy(), m2)
+
+
 def test_batch_independence_at_bench_scale():
     """Crops are independent units: any crop's heatmaps are bit-identical whatever batch (and tile boundaries) it
     travels in.  Run at a batch where every layer spans many tiles and CTAs walk several tiles each."""
