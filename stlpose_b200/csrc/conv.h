@@ -83,6 +83,7 @@ struct ConvParams {
   int taps;        // 1 or 9
   int n_chunks;    // Cin / ck
   int ck;          // channels per K chunk: 16, 32 or 64 (row = 2*ck bytes = swizzle span)
+  int ksteps_last; // MMA K steps issued for the LAST chunk (ck / 16 unless its TMA box reaches past the channel count)
   int nt;          // UMMA N
   int n_ntiles;
   int mb;          // 128-row accumulator blocks per tile

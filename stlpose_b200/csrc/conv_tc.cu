@@ -237,7 +237,9 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
 constexpr int kStatSlots = 8;   // (n-tile, panel, slice pair) combinations one epilogue warp can meet
 
 // MB    : 128-row accumulator blocks per tile (compile time so that the MMA issue loop fully unrolls)
-// KSTEPS: UMMA K-steps (16 channels each) per K chunk; the smem row / swizzle span is 32*KSTEPS bytes
+// KSTEPS: UMMA K-steps (16 channels each) per K chunk; the smem row / swizzle span is 32*KSTEPS bytes.  The LAST chunk
+//         may hold fewer valid channels (HRNet-W48: 48 = 64 - 16, 96 = 64 + 32): its TMA box reaches past the tensor's
+//         channel count, the surplus arrives as zeros and only p.ksteps_last K steps are issued for it
 // TAPS  : 1 (1x1) or 9 (3x3)
 // EPI   : which epilogue the kernel contains (each kernel carries exactly one, for instruction-cache footprint):
 //         kEpiStaged - flat mode, bf16 out: panels staged in shared memory, moved by TMA (the common case)
@@ -456,6 +458,7 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
           if (elect_one()) {
             const uint32_t a_lo0 = a_lo_base + a_stage * a_stage_u;
             const uint32_t b_lo0 = b_lo_base + ((nti * p.n_chunks + chunk) * TAPS) * b_stage_u;
+            const int kmax = chunk == p.n_chunks - 1 ? p.ksteps_last : KSTEPS;   // K steps of this chunk that hold data
             if constexpr (KWM) {
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh) {
@@ -473,6 +476,7 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
               const uint32_t b_lo = b_lo0 + (uint32_t)tap * b_stage_u;
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
+                if (k >= kmax) continue;
 #pragma unroll
                 for (int m = 0; m < MB; ++m) {
                   if (m < m_lo || m >= m_hi) continue;
@@ -519,8 +523,10 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
               const uint32_t a_lo = a_lo_base + a_stage * a_stage_u + (p.a_shift ? tap_u : 0u);
               const uint32_t b_lo = b_lo_base + bs * b_stage_u + (p.b_taps == 3 ? (uint32_t)kw * (b_stage_u / 3u) : 0u);
               const uint32_t first = (uint32_t)(chunk | tap);
+              const int kmax = chunk == p.n_chunks - 1 ? p.ksteps_last : KSTEPS;
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
+                if (k >= kmax) continue;
 #pragma unroll
                 for (int m = 0; m < MB; ++m) {
                   const uint64_t da = desc_hi | (uint64_t)(a_lo + (uint32_t)((m * 128 * (int)kSpan + k * 32) >> 4));
@@ -1127,13 +1133,23 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     if ((v == 16 || v == 32) && gi.C % v == 0 && v < p.ck) p.ck = v;
   }
   if (ck_split) p.ck = 32;
+  // Channel counts that are not a multiple of 32 or 64 (HRNet-W48: 48, 96): as 16- / 32-channel chunks every tap needs
+  // three chunks (48 channels: one K step per chunk, 32-byte swizzle: 22.5 % tensor-pipe activity, profiles/r02_ncu.md).
+  // 64-channel TMA boxes instead - the box of the last chunk reaches past the tensor's channels, which arrive as zeros -
+  // and only the K steps that hold data are issued for that chunk.  STL_DBG_CK=16/32 restores the small chunks.
+  p.ksteps_last = 0;
+  if (gi.C > 32 && gi.C % 64 != 0 && gi.C % 16 == 0 && !getenv("STL_DBG_CK")) {
+    p.ck = 64;
+    p.ksteps_last = (gi.C % 64) / 16;
+  }
   p.nt = pick_nt(s.cout_pad);
   if (!p.ck || !p.nt) { set_error("conv: channels must be multiples of 16 (cin %d cout_pad %d)", gi.C, s.cout_pad); return 1; }
   if (s.stride == 2 && ((gi.H | gi.W) & 1)) { set_error("conv: stride 2 needs even H, W"); return 1; }
   const uint32_t span = 2u * p.ck;
   p.mode = s.stride == 2 ? 1 : 0;
   p.taps = s.ksize * s.ksize;
-  p.n_chunks = gi.C / p.ck;
+  p.n_chunks = (gi.C + p.ck - 1) / p.ck;
+  if (!p.ksteps_last) p.ksteps_last = p.ck / 16;
   p.n_ntiles = s.cout_pad / p.nt;
   p.in_Wp = gi.Wp();
   p.N = gi.N;
