@@ -97,6 +97,13 @@ int stl_warp_affine_crops(const void* img_u8_hwc, int img_h, int img_w, const do
 int stl_warp_affine_crops_f32(const float* img_f32_hwc, int img_h, int img_w, const double* minv, int N, int out_h,
                               int out_w, float* out_f32_nchw, void* stream);
 
+/* conv1 of the stem (models/HRnet.py:286: 3 -> 64 channels, 3x3, stride 2, pad 1) as a 1x1 problem: fp32 NCHW
+ * [N][3][H][W] -> its im2col rows, padded-linear bf16 [N][H/2+1][W/2+1][32] with K index ci*9 + kh*3 + kw (the OIHW
+ * flatten order, 27 values + 5 zeros).  conv1 is then stl_conv2d with ksize 1 on these rows and the weight read as
+ * [64][27][1][1], and its weight gradient a 1x1 stl_conv_wgrad (tensor cores).  The zero cells of `rows` are not
+ * written: clear the buffer once. */
+int stl_stem_im2col(const float* x_nchw, void* rows, int N, int H, int W, void* stream);
+
 /* PCK accuracy of the training / evaluation loops (lib/metrics.py:268-364 accuracy -> calc_dists -> dist_acc, called at
  * 02_train.py:223,277 and 03_evaluate.py:142 on output.cpu()): pred_coords / target_coords are the [B][J][2] arg-max
  * coordinates of the predicted and the ground-truth heatmaps (stl_decode with refine = 0).  A joint is counted when its

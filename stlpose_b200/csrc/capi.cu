@@ -117,6 +117,14 @@ int stl_warp_affine_crops_f32(const float* img_f32_hwc, int img_h, int img_w, co
   return warp_affine_crops_f32(img_f32_hwc, img_h, img_w, minv, N, out_h, out_w, out_f32_nchw, (cudaStream_t)stream);
 }
 
+int stl_stem_im2col(const float* x_nchw, void* rows, int N, int H, int W, void* stream) {
+  if (!have_device()) return 1;
+  if (N > 0 && (!x_nchw || !rows)) { set_error("stl_stem_im2col: null pointer"); return 1; }
+  if (N <= 0) return 0;
+  if ((H | W) & 1) { set_error("stl_stem_im2col: even H, W required"); return 1; }
+  return stem_im2col(x_nchw, (__nv_bfloat16*)rows, N, N, H, W, (cudaStream_t)stream);
+}
+
 int stl_pck_accuracy(const float* pred_coords, const float* target_coords, int B, int J, int h, int w, float thr,
                      float* acc, float* avg_acc, int* cnt, void* stream) {
   if (!have_device()) return 1;

@@ -141,6 +141,7 @@ def _pack_weights_dgrad(w, k_pad):
 # BatchNorm statistics accumulated by the convolution's epilogue (stl_conv2d_stats).  Measured slower than the separate
 # statistics pass on B200, so it is off and the kernel variants are only in -DSTL_CONV_STATS builds.
 FUSED_BN_STATS = os.environ.get("STLPOSE_FUSED_BN_STATS", "0") == "1"
+STEM_IM2COL = os.environ.get("STLPOSE_TRAIN_STEM_IM2COL", "1") != "0"
 
 
 def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bias=None, stats=None):
@@ -450,9 +451,21 @@ def train_forward(model, x):
         if pre is not None:
             pre.run()                                                  # every weight layout of this step, one launch
         torch._foreach_add_(counters, 1)                               # every BatchNorm runs once per forward
-        t = torch.empty((B, H + 1, W + 1, 16), dtype=torch.bfloat16, device=x.device)
-        _lib.check(L.stl_nchw_to_padded(_lib.ptr(x), _lib.ptr(t), B, 3, H, W, 16, _stream()))
-        t = _convbn(t, model.conv1, model.bn1, 2, True)
+        c1 = model.conv1.weight
+        if STEM_IM2COL and tuple(c1.shape[1:]) == (3, 3, 3) and c1.is_contiguous():
+            # conv1 (3 -> 64, 3x3, stride 2) as a 1x1 convolution over its im2col rows (27 -> 32 values per output pixel, K
+            # order = the OIHW flatten order, so the weight is just viewed as [64, 27, 1, 1]): forward and weight gradient
+            # both run on the tensor cores instead of the stride-2 kernel with 3 of 16 channels used and the CUDA-core
+            # stem weight-gradient kernel (1.06 ms per step at batch 128)
+            t = torch.zeros((B, H // 2 + 1, W // 2 + 1, 32), dtype=torch.bfloat16, device=x.device)
+            _lib.check(L.stl_stem_im2col(_lib.ptr(x), _lib.ptr(t), B, H, W, _stream()))
+            bn1 = model.bn1
+            t = _ConvBN.apply(t, c1.view(c1.shape[0], 27, 1, 1), bn1.weight, bn1.bias, None, bn1.running_mean,
+                              bn1.running_var, 1, True, bn1.momentum, _tickets(bn1, x.device), _sinks(c1, bn1.bias))
+        else:
+            t = torch.empty((B, H + 1, W + 1, 16), dtype=torch.bfloat16, device=x.device)
+            _lib.check(L.stl_nchw_to_padded(_lib.ptr(x), _lib.ptr(t), B, 3, H, W, 16, _stream()))
+            t = _convbn(t, model.conv1, model.bn1, 2, True)
         t = _convbn(t, model.conv2, model.bn2, 2, True)
         for blk in model.layer1:                                     # Bottleneck.forward, HRnet.py:82-102
             res = t

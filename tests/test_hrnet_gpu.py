@@ -163,6 +163,15 @@ def test_batch_independence_at_bench_scale():
         n = hi - lo
         assert torch.equal(small[:n], big[lo:hi]) and torch.equal(small[n:], big[B + lo:B + hi])
     assert torch.isfinite(big).all()
+    # ... and at that scale the heatmaps still match the reference algorithm: crops from the first, a middle and the last
+    # tile region of the batch (plain and mirrored pass) against the fp32 oracle, BASELINE's 2e-2 max-abs
+    sd = hrnet_oracle.synth_state_dict(32, seed=0)
+    idx = [0, 79, 159]
+    xs = x[idx].cpu()
+    ref = hrnet_oracle.hrnet_forward(sd, xs, 32)
+    ref_f = hrnet_oracle.hrnet_forward(sd, xs.flip(3), 32)
+    err = max((big[idx].cpu() - ref).abs().max().item(), (big[[B + i for i in idx]].cpu() - ref_f).abs().max().item())
+    assert err < HEAT_TOL, err
 
 
 def test_boxes_to_keypoints_pipeline_vs_oracle():
