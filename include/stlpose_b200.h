@@ -299,6 +299,12 @@ int stl_bn_train_forward_fused(const void* z, const float* stat_rows, int rows, 
 int stl_bn_train_backward_ticket(const void* dy, const void* y, const void* z, const float* mean, const float* rstd,
                                  const float* gamma, int relu, int N, int H, int W, int C, void* dz, void* dres,
                                  float* dbeta_dgamma, float* workspace, unsigned* ticket, void* stream);
+/* The same for a ReLU unit WITHOUT residual: the ReLU mask (y > 0) is recomputed from z - gamma * (z - mean) * rstd + beta
+ * evaluated with exactly the forward's operations - instead of being read from the stored output, which saves one of
+ * the three tensor reads of each backward pass. */
+int stl_bn_train_backward_ticket_z(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
+                                   const float* beta, int N, int H, int W, int C, void* dz, float* dbeta_dgamma,
+                                   float* workspace, unsigned* ticket, void* stream);
 
 /* Fuse-layer row (HRnet.py:255-264): y = relu(sum same[i] + sum nearest_upsample(up[j], 2^shift[j])).
  * same_host / up_host: host arrays of device pointers (n_same <= 4, n_up <= 3). */

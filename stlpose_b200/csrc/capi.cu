@@ -362,7 +362,7 @@ int stl_bn_train_backward(const void* dy, const void* y, const void* z, const fl
     return 1;
   }
   typedef const __nv_bfloat16* P;
-  return bn_train_backward((P)dy, (P)y, (P)z, mean, rstd, gamma, relu, N, H, W, C, (__nv_bfloat16*)dz,
+  return bn_train_backward((P)dy, (P)y, (P)z, mean, rstd, gamma, nullptr, relu ? 1 : 0, N, H, W, C, (__nv_bfloat16*)dz,
                            (__nv_bfloat16*)dres, sums, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -375,8 +375,21 @@ int stl_bn_train_backward_ticket(const void* dy, const void* y, const void* z, c
     return 1;
   }
   typedef const __nv_bfloat16* P;
-  return bn_train_backward((P)dy, (P)y, (P)z, mean, rstd, gamma, relu, N, H, W, C, (__nv_bfloat16*)dz,
+  return bn_train_backward((P)dy, (P)y, (P)z, mean, rstd, gamma, nullptr, relu ? 1 : 0, N, H, W, C, (__nv_bfloat16*)dz,
                            (__nv_bfloat16*)dres, dbeta_dgamma, workspace, ticket, (cudaStream_t)stream);
+}
+
+int stl_bn_train_backward_ticket_z(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
+                                   const float* beta, int N, int H, int W, int C, void* dz, float* dbeta_dgamma,
+                                   float* workspace, unsigned* ticket, void* stream) {
+  if (!have_device()) return 1;
+  if (!dy || !z || !mean || !rstd || !gamma || !beta || !dz || !dbeta_dgamma || !workspace || !ticket) {
+    set_error("stl_bn_train_backward_ticket_z: null pointer");
+    return 1;
+  }
+  typedef const __nv_bfloat16* P;
+  return bn_train_backward((P)dy, nullptr, (P)z, mean, rstd, gamma, beta, 2, N, H, W, C, (__nv_bfloat16*)dz, nullptr,
+                           dbeta_dgamma, workspace, ticket, (cudaStream_t)stream);
 }
 
 int stl_sum_relu_forward(const void* const* same_host, int n_same, const void* const* up_host, const int* shift_host,

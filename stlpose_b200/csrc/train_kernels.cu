@@ -55,6 +55,12 @@ struct PixIdx {
   }
 };
 
+// gamma * (z - mean) * rstd + beta with a FIXED operation order: the forward (bn_apply_kernel) and the backward kernels
+// that recompute the ReLU mask from z instead of reading y must produce the same float, bit for bit.
+__device__ __forceinline__ float bn_affine(float z, float g, float m, float r, float b) {
+  return __fmaf_rn(__fmul_rn(g, __fsub_rn(z, m)), r, b);
+}
+
 // ------------------------------------------------------------------ per-channel reductions over all pixels
 // MODE 0: sums[c] = sum a, sums[C+c] = sum a^2                      (BatchNorm forward statistics; a = z)
 // MODE 1: sums[c] = sum g, sums[C+c] = sum g * xhat                 (BatchNorm backward; g = dy masked by y > 0)
@@ -75,7 +81,9 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
                                                              const __nv_bfloat16* __restrict__ y,
                                                              const __nv_bfloat16* __restrict__ z,
                                                              const float* __restrict__ mean,
-                                                             const float* __restrict__ rstd, long long pixels, int C,
+                                                             const float* __restrict__ rstd,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, long long pixels, int C,
                                                              int relu_mask, float* __restrict__ sums,
                                                              float* __restrict__ partial, unsigned* __restrict__ counter,
                                                              const BnFinalize fin) {
@@ -83,10 +91,13 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
   const int lanes = 256 / c8n;          // pixel lanes per block (C <= 2048 / 8 ... C/8 <= 256)
   const int cg = threadIdx.x % c8n, pl = threadIdx.x / c8n;
   float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  float mu[8], rs[8];
+  float mu[8], rs[8], ga[8], be[8];
   if (MODE == 1) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { mu[i] = mean[cg * 8 + i]; rs[i] = rstd[cg * 8 + i]; }
+    for (int i = 0; i < 8; ++i) {
+      mu[i] = mean[cg * 8 + i]; rs[i] = rstd[cg * 8 + i];
+      ga[i] = relu_mask == 2 ? gamma[cg * 8 + i] : 0.f; be[i] = relu_mask == 2 ? beta[cg * 8 + i] : 0.f;
+    }
   }
   if (pl < lanes) {
     // explicit batches: all loads of kBatch pixels are issued before the first one is consumed (the rolled loop kept
@@ -103,7 +114,7 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
         ua[k] = in ? __ldg(reinterpret_cast<const uint4*>(a + off)) : make_uint4(0, 0, 0, 0);
         if (MODE == 1) {
           uz[k] = in ? __ldg(reinterpret_cast<const uint4*>(z + off)) : make_uint4(0, 0, 0, 0);
-          uy[k] = (in && relu_mask) ? __ldg(reinterpret_cast<const uint4*>(y + off)) : make_uint4(0, 0, 0, 0);
+          uy[k] = (in && relu_mask == 1) ? __ldg(reinterpret_cast<const uint4*>(y + off)) : make_uint4(0, 0, 0, 0);
         }
       }
 #pragma unroll
@@ -120,7 +131,10 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
           unpack8(uy[k], yy);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float g = (relu_mask && !(yy[i] > 0.f)) ? 0.f : f[i];
+            // relu_mask 1: the stored output tells; 2 (no residual): y > 0 <=> the affine value is > 0, recomputed from z
+            const bool off_ = relu_mask == 1 ? !(yy[i] > 0.f)
+                                             : (relu_mask == 2 && !(bn_affine(zz[i], ga[i], mu[i], rs[i], be[i]) > 0.f));
+            const float g = off_ ? 0.f : f[i];
             s0[i] += g;
             s1[i] += g * (zz[i] - mu[i]) * rs[i];
           }
@@ -294,7 +308,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
       if (residual) unpack8(*reinterpret_cast<const uint4*>(residual + (size_t)i * 8), r);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        float v = g8[k] * (f[k] - m8[k]) * r8[k] + b8[k] + r[k];
+        float v = bn_affine(f[k], g8[k], m8[k], r8[k], b8[k]) + r[k];
         f[k] = relu ? fmaxf(v, 0.f) : v;
       }
       out = pack8(f);
@@ -310,12 +324,14 @@ __global__ void __launch_bounds__(256) bn_backward_kernel(const __nv_bfloat16* _
                                                           const float* __restrict__ mean,
                                                           const float* __restrict__ rstd,
                                                           const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta,
                                                           const float* __restrict__ sums, float count, int relu_mask,
                                                           __nv_bfloat16* __restrict__ dz,
                                                           __nv_bfloat16* __restrict__ dres, int N, int H, int W,
                                                           int C, const PixIdx px) {
   const uint32_t total = (uint32_t)N * (uint32_t)(px.Hp * px.Wp * px.c8n);
   float gr8[8], m8[8], r8[8], sg8[8], sx8[8];      // gamma*rstd, mean, rstd, sum_g/cnt, sum_gx/cnt of this thread's channels
+  float ga8[8], be8[8];                            // gamma, beta (relu_mask == 2: the mask is recomputed from z)
   {
     const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int cg0 = (int)(i0 - px.c8.div(i0) * (uint32_t)px.c8n);
@@ -324,6 +340,7 @@ __global__ void __launch_bounds__(256) bn_backward_kernel(const __nv_bfloat16* _
       const int c = cg0 * 8 + k;
       m8[k] = mean[c]; r8[k] = rstd[c]; gr8[k] = gamma[c] * rstd[c];
       sg8[k] = sums[c] / count; sx8[k] = sums[C + c] / count;
+      ga8[k] = gamma[c]; be8[k] = relu_mask == 2 ? beta[c] : 0.f;
     }
   }
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -334,10 +351,11 @@ __global__ void __launch_bounds__(256) bn_backward_kernel(const __nv_bfloat16* _
       float g[8], yy[8], zz[8], d[8];
       unpack8(*reinterpret_cast<const uint4*>(dy + (size_t)i * 8), g);
       unpack8(*reinterpret_cast<const uint4*>(z + (size_t)i * 8), zz);
-      if (relu_mask) unpack8(*reinterpret_cast<const uint4*>(y + (size_t)i * 8), yy);
+      if (relu_mask == 1) unpack8(*reinterpret_cast<const uint4*>(y + (size_t)i * 8), yy);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        if (relu_mask && !(yy[k] > 0.f)) g[k] = 0.f;
+        if (relu_mask == 1 ? !(yy[k] > 0.f)
+                           : (relu_mask == 2 && !(bn_affine(zz[k], ga8[k], m8[k], r8[k], be8[k]) > 0.f))) g[k] = 0.f;
         const float xhat = (zz[k] - m8[k]) * r8[k];
         d[k] = gr8[k] * (g[k] - sg8[k] - xhat * sx8[k]);
       }
@@ -647,7 +665,7 @@ int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* be
   const int lanes = 256 / (C / 8);
   BnFinalize fin{(float)((long long)N * H * W), eps, momentum, mean, rstd, run_mean, run_var};
   channel_reduce_kernel<0><<<grid_for(pixels, lanes * 8, kReduceBlocks), 256, 0, st>>>(
-      z, nullptr, nullptr, nullptr, nullptr, pixels, C, 0, sums, sums + 2 * C, counter, fin);
+      z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pixels, C, 0, sums, sums + 2 * C, counter, fin);
   if (check("bn stats")) return 1;
   PixIdx px;
   px.init(C, H, W);
@@ -677,7 +695,7 @@ int bn_train_forward_fused(const __nv_bfloat16* z, const float* stat_rows, int r
 }
 
 int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* z, const float* mean,
-                      const float* rstd, const float* gamma, int relu, int N, int H, int W, int C,
+                      const float* rstd, const float* gamma, const float* beta, int relu, int N, int H, int W, int C,
                       __nv_bfloat16* dz, __nv_bfloat16* dres, float* sums, float* partial, unsigned* ticket,
                       cudaStream_t st) {
   if (C % 8 || C > 2048) { set_error("bn_train_backward: C=%d unsupported", C); return 1; }
@@ -687,14 +705,15 @@ int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __n
   unsigned* counter = ticket ? ticket : reinterpret_cast<unsigned*>(partial + (size_t)2 * C * kReduceBlocks);
   if (!ticket) cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   const int lanes = 256 / (C / 8);
+  if (relu == 2 && (!beta || dres)) { set_error("bn_train_backward: the z-recomputed mask needs beta and no residual"); return 1; }
   channel_reduce_kernel<1><<<grid_for(pixels, lanes * 8, kReduceBlocks), 256, 0, st>>>(
-      dy, y, z, mean, rstd, pixels, C, relu, sums, partial, counter, BnFinalize{});
+      dy, y, z, mean, rstd, gamma, beta, pixels, C, relu, sums, partial, counter, BnFinalize{});
   if (check("bn backward reduce")) return 1;
   PixIdx px;
   px.init(C, H, W);
   if (pixels * (C / 8) >= (1ll << 31)) { set_error("bn_train_backward: tensor too large for 32-bit item indexing"); return 1; }
   if (256 % (C / 8) && (C / 8) % 3) { set_error("bn_train_backward: C=%d unsupported", C); return 1; }
-  bn_backward_kernel<<<grid_mult(pixels * (C / 8), C / 8), 256, 0, st>>>(dy, y, z, mean, rstd, gamma, sums,
+  bn_backward_kernel<<<grid_mult(pixels * (C / 8), C / 8), 256, 0, st>>>(dy, y, z, mean, rstd, gamma, beta, sums,
                                                                      (float)((long long)N * H * W), relu, dz, dres, N,
                                                                      H, W, C, px);
   return check("bn backward");

@@ -14,8 +14,9 @@ int bn_train_forward_fused(const __nv_bfloat16* z, const float* stat_rows, int r
                            const float* beta, const __nv_bfloat16* residual, int relu, float eps, float momentum, int N,
                            int H, int W, int C, __nv_bfloat16* y, float* mean, float* rstd, float* run_mean, float* run_var,
                            cudaStream_t st);
+// relu: 0 none, 1 mask from the stored output y, 2 mask recomputed from z (needs beta, units without residual)
 int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* z, const float* mean,
-                      const float* rstd, const float* gamma, int relu, int N, int H, int W, int C,
+                      const float* rstd, const float* gamma, const float* beta, int relu, int N, int H, int W, int C,
                       __nv_bfloat16* dz, __nv_bfloat16* dres, float* sums, float* partial, unsigned* ticket,
                       cudaStream_t st);
 int sum_relu_forward(const __nv_bfloat16* const* same, int n_same, const __nv_bfloat16* const* up, const int* shift,

@@ -142,6 +142,7 @@ def _pack_weights_dgrad(w, k_pad):
 # statistics pass on B200, so it is off and the kernel variants are only in -DSTL_CONV_STATS builds.
 FUSED_BN_STATS = os.environ.get("STLPOSE_FUSED_BN_STATS", "0") == "1"
 STEM_IM2COL = os.environ.get("STLPOSE_TRAIN_STEM_IM2COL", "1") != "0"
+MASK_FROM_Z = os.environ.get("STLPOSE_TRAIN_MASK_FROM_Z", "1") != "0"
 
 
 def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bias=None, stats=None):
@@ -289,14 +290,14 @@ class _ConvBN(torch.autograd.Function):
                                                      _lib.ptr(run_var), tickets.data_ptr(), _stream()))
         ctx.tickets = tickets
         ctx.sinks = sinks
-        ctx.save_for_backward(x, weight, z, y, mean, rstd, g32)
+        ctx.save_for_backward(x, weight, z, y, mean, rstd, g32, b32)
         ctx.meta = (n, h, w, cin_pad, cin_real, cout, k, stride, bool(relu), residual is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         L = _lib.lib()
-        x, weight, z, y, mean, rstd, g32 = ctx.saved_tensors
+        x, weight, z, y, mean, rstd, g32, b32 = ctx.saved_tensors
         n, h, w, cin_pad, cin_real, cout, k, stride, relu, has_res = ctx.meta
         ho, wo = h // stride, w // stride
         dy = dy.contiguous()
@@ -307,9 +308,16 @@ class _ConvBN(torch.autograd.Function):
         # (parallel.GradientReducer.bind) - written straight into the bucket by the kernels, nothing returned
         wsink, bsink = ctx.sinks if ctx.sinks is not None else (None, None)
         sums = bsink.view if bsink is not None else torch.empty(2 * cout, dtype=torch.float32, device=x.device)   # dbeta | dgamma
-        _lib.check(L.stl_bn_train_backward_ticket(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(z), _lib.ptr(mean), _lib.ptr(rstd),
-                                                  _lib.ptr(g32), int(relu), n, ho, wo, cout, _lib.ptr(dz), _lib.ptr(dres),
-                                                  _lib.ptr(sums), _lib.ptr(ws), ctx.tickets.data_ptr() + 4, _stream()))
+        if relu and not has_res and MASK_FROM_Z:
+            # ReLU unit without residual: y > 0 <=> gamma * (z - mean) * rstd + beta > 0, recomputed from z with the
+            # forward's exact operations - one tensor read less in each of the two backward passes
+            _lib.check(L.stl_bn_train_backward_ticket_z(_lib.ptr(dy), _lib.ptr(z), _lib.ptr(mean), _lib.ptr(rstd),
+                                                        _lib.ptr(g32), _lib.ptr(b32), n, ho, wo, cout, _lib.ptr(dz),
+                                                        _lib.ptr(sums), _lib.ptr(ws), ctx.tickets.data_ptr() + 4, _stream()))
+        else:
+            _lib.check(L.stl_bn_train_backward_ticket(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(z), _lib.ptr(mean), _lib.ptr(rstd),
+                                                      _lib.ptr(g32), int(relu), n, ho, wo, cout, _lib.ptr(dz), _lib.ptr(dres),
+                                                      _lib.ptr(sums), _lib.ptr(ws), ctx.tickets.data_ptr() + 4, _stream()))
         dbeta, dgamma = sums[:cout], sums[cout:]
         if bsink is not None:
             bsink.done()

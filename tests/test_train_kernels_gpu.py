@@ -278,3 +278,40 @@ def test_conv_epilogue_statistics(cin, cout, k, stride, hw, n):
     assert ((ra - rb).abs() / rb).max().item() < 1e-4
     assert (rma - rmb).abs().max().item() < 1e-5 and ((rva - rvb).abs() / rvb).max().item() < 1e-4
     assert (_unpadded(ya) - _unpadded(yb)).abs().max().item() <= 2 ** -7 * max(1.0, _unpadded(yb).abs().max().item())
+
+
+@pytest.mark.parametrize("shape", [(3, 32, 16, 12), (2, 64, 32, 24), (5, 48, 12, 9), (2, 256, 8, 6)])
+def test_bn_backward_mask_recomputed_from_z_is_bit_identical(shape):
+    """ReLU units without residual: stl_bn_train_backward_ticket_z derives the mask (y > 0) from z with the forward's
+    exact operations instead of reading y; dz and dbeta | dgamma must equal the y-reading kernel bit for bit."""
+    L = _lib.lib()
+    n, c, h, w = shape
+    g = torch.Generator(device=DEV).manual_seed(c * 7 + h)
+    z = bf16_round(torch.randn(shape, device=DEV, generator=g) * 1.3 + 0.2)
+    gamma = torch.rand(c, device=DEV, generator=g) + 0.5
+    beta = torch.randn(c, device=DEV, generator=g) * 0.3
+    zp = _padded(z)
+    y = torch.empty_like(zp)
+    sums = torch.empty(L.stl_bn_workspace_floats(c), device=DEV); mean = torch.empty(c, device=DEV); rstd = torch.empty(c, device=DEV)
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    _lib.check(L.stl_bn_train_forward(_lib.ptr(zp), _lib.ptr(gamma), _lib.ptr(beta), None, 1, 1e-5, 0.1, n, h, w, c,
+                                      _lib.ptr(y), _lib.ptr(sums), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(rm), _lib.ptr(rv),
+                                      _lib.current_stream()))
+    assert 0.2 < (y[:, :h, :w] > 0).float().mean().item() < 0.8           # the mask is non-trivial
+    dyp = _padded(bf16_round(torch.randn(shape, device=DEV, generator=g)))
+    outs = []
+    for from_z in (False, True):
+        dz = torch.empty_like(zp)
+        dbg = torch.empty(2 * c, device=DEV)
+        ws = torch.empty(L.stl_bn_workspace_floats(c), device=DEV)
+        ticket = torch.zeros(2, dtype=torch.int32, device=DEV)
+        if from_z:
+            _lib.check(L.stl_bn_train_backward_ticket_z(_lib.ptr(dyp), _lib.ptr(zp), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma),
+                                                        _lib.ptr(beta), n, h, w, c, _lib.ptr(dz), _lib.ptr(dbg), _lib.ptr(ws),
+                                                        ticket.data_ptr(), _lib.current_stream()))
+        else:
+            _lib.check(L.stl_bn_train_backward_ticket(_lib.ptr(dyp), _lib.ptr(y), _lib.ptr(zp), _lib.ptr(mean), _lib.ptr(rstd),
+                                                      _lib.ptr(gamma), 1, n, h, w, c, _lib.ptr(dz), None, _lib.ptr(dbg),
+                                                      _lib.ptr(ws), ticket.data_ptr(), _lib.current_stream()))
+        outs.append((dz, dbg))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
