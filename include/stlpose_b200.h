@@ -192,9 +192,19 @@ int stl_conv2d(const stl_conv_desc* desc, void* stream);
  * HRnet.py:48-59 under model.train(), 02_train.py:208): per-channel sum and sum of squares of the STORED bf16 values over
  * the valid pixels.  `stats`: stl_conv2d_stats_floats(Cout_pad) floats; the launch fills *stats_rows rows of
  * [2][Cout_pad] (one per CTA) which stl_bn_train_forward_fused adds in a fixed order (deterministic).  *stats_rows == 0:
- * this shape - or this build: the fused variants were measured slower than the separate statistics pass and are only
- * compiled with -DSTL_CONV_STATS - has no fused statistics (the convolution still ran): use stl_bn_train_forward. */
+ * this shape - or this build: the fused variants were measured slower than the separate statistics pass (DESIGN.md
+ * section 4) and are only compiled with -DSTL_CONV_STATS - has no fused statistics (the convolution still ran): use
+ * stl_bn_train_forward. */
+/* stl_conv2d_bn goes one step further: the LAST CTA of the convolution adds the rows in a fixed order and writes
+ * mean[C], rstd[C] and the running statistics (momentum, unbiased variance) itself, so nothing is launched between the
+ * convolution and the normalisation (stl_bn_apply).  `ticket`: a device word that is zero on entry and left zero.
+ * *done == 0: not for this shape - nothing was finalised, use stl_bn_train_forward. */
 size_t stl_conv2d_stats_floats(int cout_pad);
+int stl_conv2d_bn(const stl_conv_desc* desc, float* stats, unsigned* ticket, float eps, float momentum, float* mean,
+                  float* rstd, float* running_mean, float* running_var, int* done, void* stream);
+/* y = [relu](gamma * (z - mean) * rstd + beta [+ residual]) with given statistics (zero cells stay zero). */
+int stl_bn_apply(const void* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                 const void* residual, int relu, int N, int H, int W, int C, void* y, void* stream);
 int stl_conv2d_stats(const stl_conv_desc* desc, float* stats, int* stats_rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

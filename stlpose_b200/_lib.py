@@ -79,6 +79,9 @@ PROTOTYPES = {
     "stl_conv2d": (ctypes.c_int, [ctypes.POINTER(ConvDesc), vp]),
     "stl_conv2d_stats_floats": (ctypes.c_size_t, [ctypes.c_int]),
     "stl_conv2d_stats": (ctypes.c_int, [ctypes.POINTER(ConvDesc), vp, c_int_p, vp]),
+    "stl_conv2d_bn": (ctypes.c_int, [ctypes.POINTER(ConvDesc), vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp,
+                                     c_int_p, vp]),
+    "stl_bn_apply": (ctypes.c_int, [vp] * 6 + [ctypes.c_int] * 5 + [vp, vp]),
     "stl_bn_train_forward_fused": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int,
                                                   ctypes.c_float, ctypes.c_float] + [ctypes.c_int] * 4 + [vp] * 6),
     "stl_plan_create": (vp, [ctypes.POINTER(HrnetCfg)]),

@@ -193,7 +193,12 @@ int stl_pack_conv_weights_batched(const stl_pack_item* items_dev, const int* blo
                               (cudaStream_t)stream);
 }
 
-static int conv2d_impl(const stl_conv_desc* d, float* stats, int* stats_rows, void* stream);
+struct BnFused {   // stl_conv2d_bn: the convolution's last CTA finalises the BatchNorm statistics
+  unsigned* ticket;
+  float eps, momentum;
+  float *mean, *rstd, *run_mean, *run_var;
+};
+static int conv2d_impl(const stl_conv_desc* d, float* stats, int* stats_rows, void* stream, const BnFused* bn = nullptr);
 
 int stl_conv2d(const stl_conv_desc* d, void* stream) { return conv2d_impl(d, nullptr, nullptr, stream); }
 
@@ -204,7 +209,26 @@ int stl_conv2d_stats(const stl_conv_desc* d, float* stats, int* stats_rows, void
   return conv2d_impl(d, stats, stats_rows, stream);
 }
 
-static int conv2d_impl(const stl_conv_desc* d, float* stats, int* stats_rows, void* stream) {
+int stl_conv2d_bn(const stl_conv_desc* d, float* stats, unsigned* ticket, float eps, float momentum, float* mean,
+                  float* rstd, float* running_mean, float* running_var, int* done, void* stream) {
+  if (!stats || !ticket || !mean || !rstd || !done) { set_error("stl_conv2d_bn: null pointer"); return 1; }
+  BnFused bn{ticket, eps, momentum, mean, rstd, running_mean, running_var};
+  int rows = 0;
+  *done = 0;
+  if (conv2d_impl(d, stats, &rows, stream, &bn)) return 1;
+  *done = rows > 0 ? 1 : 0;
+  return 0;
+}
+
+int stl_bn_apply(const void* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                 const void* residual, int relu, int N, int H, int W, int C, void* y, void* stream) {
+  if (!have_device()) return 1;
+  if (!z || !mean || !rstd || !gamma || !beta || !y) { set_error("stl_bn_apply: null pointer"); return 1; }
+  typedef const __nv_bfloat16* P;
+  return bn_apply((P)z, mean, rstd, gamma, beta, (P)residual, relu, N, H, W, C, (__nv_bfloat16*)y, (cudaStream_t)stream);
+}
+
+static int conv2d_impl(const stl_conv_desc* d, float* stats, int* stats_rows, void* stream, const BnFused* bn) {
   if (!have_device()) return 1;
   if (!d || !d->in || !d->out || !d->w_packed || !d->bias_packed) { set_error("stl_conv2d: null pointer"); return 1; }
   if (d->n_up < 0 || d->n_up > STL_MAX_UP) { set_error("stl_conv2d: n_up out of range"); return 1; }
@@ -235,13 +259,19 @@ static int conv2d_impl(const stl_conv_desc* d, float* stats, int* stats_rows, vo
   if (d->impl == 2) return conv_launch_naive(s, (cudaStream_t)stream);
   if (!stats) return conv_launch(s, (cudaStream_t)stream);
   s.stats = stats;
+  if (bn) {
+    s.stats_ticket = bn->ticket;
+    s.stats_count = (float)((long long)d->N * (d->H / d->stride) * (d->W / d->stride));
+    s.stats_eps = bn->eps; s.stats_momentum = bn->momentum;
+    s.stats_mean = bn->mean; s.stats_rstd = bn->rstd; s.stats_run_mean = bn->run_mean; s.stats_run_var = bn->run_var;
+  }
   ConvParams p;
   int grid = 0;
   size_t smem = 0;
   if (conv_prepare(s, &p, &grid, &smem)) return 1;
-  if (grid > kStatsMaxRows) p.stats = nullptr;
+  if (grid > kStatsMaxRows) { p.stats = nullptr; p.stats_ticket = nullptr; }
   if (conv_launch_prepared(p, grid, smem, (cudaStream_t)stream)) return 1;
-  *stats_rows = p.stats ? grid : 0;          // 0: this shape has no fused statistics, run the separate reduction
+  *stats_rows = (p.stats && (!bn || p.stats_ticket)) ? grid : 0;   // 0: no fused statistics for this shape: run the separate reduction
   return 0;
 }
 

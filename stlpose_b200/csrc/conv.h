@@ -55,6 +55,13 @@ struct ConvSpec {
   // in the epilogue (BatchNorm batch statistics, HRnet.py:48-59 under model.train()).  [kStatsMaxRows][2][cout_pad]
   // floats; the launch fills one row per CTA (conv_stats_rows() of them), a fixed-order second pass adds the rows.
   float* stats = nullptr;
+  // ... and, when stats_ticket is set, the LAST CTA to finish adds the rows in a fixed order and finalises the BatchNorm
+  // statistics itself (mean, rstd, running statistics with momentum and the unbiased variance), so that no separate
+  // launch is needed between the convolution and the normalisation.  stats_ticket: a device word that is zero on entry
+  // and left zero.
+  unsigned* stats_ticket = nullptr;
+  float stats_count = 0.f, stats_eps = 0.f, stats_momentum = 0.f;
+  float *stats_mean = nullptr, *stats_rstd = nullptr, *stats_run_mean = nullptr, *stats_run_var = nullptr;
 };
 constexpr int kStatsMaxRows = 160;           // >= CTAs of any launch (one per SM)
 
@@ -130,6 +137,9 @@ struct ConvParams {
   int pdl;                // launched with programmatic stream serialization
   int dbg_skip_epilogue;  // measurement only
   float* stats;           // see ConvSpec::stats (null: off)
+  unsigned* stats_ticket; // see ConvSpec::stats_ticket (null: rows only)
+  float stats_count, stats_eps, stats_momentum;
+  float *stats_mean, *stats_rstd, *stats_run_mean, *stats_run_var;
   long long* dbg_counters;  // measurement only: [grid][3 roles][4] cycle counters, or null
 };
 

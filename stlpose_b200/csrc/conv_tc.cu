@@ -54,6 +54,7 @@ struct Ctl {
   uint64_t acc_full[4], acc_empty[4];
   uint64_t res_full[4], epi_free[4], epi_done[4];  // [epilogue group][staging buffer]
   uint32_t tmem_base;
+  uint32_t last_cta;   // STATS: set in the CTA that arrives last at the statistics ticket
 };
 static_assert(sizeof(Ctl) <= kBiasOffset, "control block too large");
 
@@ -1048,6 +1049,57 @@ role_done:
       for (int r = 0; r < 8; ++r) acc += tab[(size_t)r * 2 * cp + i];
       p.stats[(size_t)blockIdx.x * 2 * cp + i] = acc;
     }
+    if (p.stats_ticket) {
+      // the last CTA to arrive adds the rows of all CTAs in a fixed order and finalises the batch statistics: no launch
+      // between this convolution and the normalisation.  Thread = (column of [2][cout_pad], row group): kGroups row
+      // groups with four independent partial sums each, combined in order through shared memory.
+      // (no static shared memory in this kernel: the dynamic allocation already asks for the 227 KB maximum)
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) ctl->last_cta = atomicAdd(p.stats_ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+      __syncthreads();
+      if (ctl->last_cta) {
+        __threadfence();
+        const int cols = 2 * cp, rows = (int)gridDim.x;         // cols <= blockDim.x (host)
+        int groups = (int)blockDim.x / cols;
+        groups = groups > 8 ? 8 : groups;
+        const int col = (int)threadIdx.x % cols, g = (int)threadIdx.x / cols;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (g < groups) {
+          int r = g;
+          for (; r + 3 * groups < rows; r += 4 * groups) {
+            a0 += __ldcg(p.stats + (size_t)r * cols + col);
+            a1 += __ldcg(p.stats + (size_t)(r + groups) * cols + col);
+            a2 += __ldcg(p.stats + (size_t)(r + 2 * groups) * cols + col);
+            a3 += __ldcg(p.stats + (size_t)(r + 3 * groups) * cols + col);
+          }
+          for (; r < rows; r += groups) a0 += __ldcg(p.stats + (size_t)r * cols + col);
+        }
+        __syncthreads();                                          // (the per-CTA reduction above is done with `tab`)
+        if (g < groups) tab[(size_t)g * cols + col] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        if (g == 0) {
+          float t = 0.f;
+          for (int k = 0; k < groups; ++k) t += tab[(size_t)k * cols + col];
+          tab[(size_t)8 * cols + col] = t;                        // totals: row 8 of the table
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < p.cout; c += (int)blockDim.x) {
+          const float* tot = tab + (size_t)8 * cols;
+          const float m = tot[c] / p.stats_count;
+          float var = tot[cp + c] / p.stats_count - m * m;
+          var = var > 0.f ? var : 0.f;
+          p.stats_mean[c] = m;
+          p.stats_rstd[c] = rsqrtf(var + p.stats_eps);
+          if (p.stats_run_mean) {
+            const float unbiased = p.stats_count > 1.f ? var * p.stats_count / (p.stats_count - 1.f) : var;
+            p.stats_run_mean[c] = (1.f - p.stats_momentum) * p.stats_run_mean[c] + p.stats_momentum * m;
+            p.stats_run_var[c] = (1.f - p.stats_momentum) * p.stats_run_var[c] + p.stats_momentum * unbiased;
+          }
+        }
+        if (threadIdx.x == 0) *p.stats_ticket = 0u;
+      }
+    }
   }
   if (warp == 1) {
     tc_fence_after();
@@ -1358,17 +1410,25 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   }
   // BatchNorm statistics in the epilogue (training): staged epilogues only, at most kStatSlots (n-tile, panel, slice
   // pair) slots per epilogue warp, and the [8][2][cout_pad] reduction table must fit the activation ring it reuses.
-  // Correct (tests/test_train_kernels_gpu.py::test_conv_epilogue_statistics) but not faster: the epilogue's 32 shuffles
-  // per 16-channel unit cost the forward convolutions +24 %, and the row reduction that replaces the statistics pass is
-  // one more launch - 40.2 vs 39.8 ms per step at batch 128, 17.9 vs 17.3 at batch 32 - so the variants are compiled
-  // only with -DSTL_CONV_STATS and stl_conv2d_stats reports "no fused statistics" otherwise.
+  // Correct (tests/test_train_kernels_gpu.py::test_conv_epilogue_statistics) but not faster, in either form: with a
+  // separate row-reduction launch 40.2 vs 39.8 ms per step at batch 128 and 17.9 vs 17.3 at batch 32; with the last CTA
+  // finalising the statistics itself (stl_conv2d_bn: 292 kernel nodes fewer per step) 41.9 vs 41.5 and 18.45 vs 18.25.
+  // The epilogue's 32 shuffles per 16-channel unit make the forward convolutions 24 % slower, which costs what the
+  // statistics pass saved.  The variants are therefore compiled only with -DSTL_CONV_STATS; without it stl_conv2d_stats
+  // / stl_conv2d_bn report "not for this shape" and the callers use the separate statistics kernel.
   p.stats = nullptr;
+  p.stats_ticket = nullptr;
 #ifdef STL_CONV_STATS
   if (s.stats) {
     const int spp = p.panel_ch / 16, npanels = p.nt / p.panel_ch;
     if (p.epi_tma && !kwm && s.cout == s.cout_pad && p.n_ntiles * npanels * ((spp + 1) / 2) <= kStatSlots &&
-        (size_t)64 * s.cout_pad <= (size_t)a_st * p.a_stage_bytes)
+        (size_t)72 * s.cout_pad <= (size_t)a_st * p.a_stage_bytes && (!s.stats_ticket || 2 * s.cout_pad <= 640)) {
       p.stats = s.stats;
+      p.stats_ticket = s.stats_ticket;
+      p.stats_count = s.stats_count; p.stats_eps = s.stats_eps; p.stats_momentum = s.stats_momentum;
+      p.stats_mean = s.stats_mean; p.stats_rstd = s.stats_rstd;
+      p.stats_run_mean = s.stats_run_mean; p.stats_run_var = s.stats_run_var;
+    }
   }
 #endif
   // measured on B200: a second issuer pays off only for N <= 32 (16-cycle MMAs); at N = 64 the two streams interfere

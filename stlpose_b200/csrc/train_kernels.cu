@@ -694,6 +694,19 @@ int bn_train_forward_fused(const __nv_bfloat16* z, const float* stat_rows, int r
   return check("bn apply");
 }
 
+int bn_apply(const __nv_bfloat16* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+             const __nv_bfloat16* residual, int relu, int N, int H, int W, int C, __nv_bfloat16* y, cudaStream_t st) {
+  if (C % 8 || C > 2048) { set_error("bn_apply: C=%d unsupported", C); return 1; }
+  const long long pixels = (long long)N * (H + 1) * (W + 1);
+  PixIdx px;
+  px.init(C, H, W);
+  if (pixels * (C / 8) >= (1ll << 31)) { set_error("bn_apply: tensor too large for 32-bit item indexing"); return 1; }
+  if (256 % (C / 8) && (C / 8) % 3) { set_error("bn_apply: C=%d unsupported", C); return 1; }
+  bn_apply_kernel<<<grid_mult(pixels * (C / 8), C / 8), 256, 0, st>>>(z, mean, rstd, gamma, beta, residual, relu, y, N, H,
+                                                                  W, C, px);
+  return check("bn apply");
+}
+
 int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* z, const float* mean,
                       const float* rstd, const float* gamma, const float* beta, int relu, int N, int H, int W, int C,
                       __nv_bfloat16* dz, __nv_bfloat16* dres, float* sums, float* partial, unsigned* ticket,

@@ -14,6 +14,9 @@ int bn_train_forward_fused(const __nv_bfloat16* z, const float* stat_rows, int r
                            const float* beta, const __nv_bfloat16* residual, int relu, float eps, float momentum, int N,
                            int H, int W, int C, __nv_bfloat16* y, float* mean, float* rstd, float* run_mean, float* run_var,
                            cudaStream_t st);
+// normalisation alone (mean / rstd already final, e.g. from stl_conv2d_bn)
+int bn_apply(const __nv_bfloat16* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+             const __nv_bfloat16* residual, int relu, int N, int H, int W, int C, __nv_bfloat16* y, cudaStream_t st);
 // relu: 0 none, 1 mask from the stored output y, 2 mask recomputed from z (needs beta, units without residual)
 int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* z, const float* mean,
                       const float* rstd, const float* gamma, const float* beta, int relu, int N, int H, int W, int C,

@@ -138,17 +138,20 @@ def _pack_weights_dgrad(w, k_pad):
     return wp, _zero_bias(rows_pad, w.device), rows_pad
 
 
-# BatchNorm statistics accumulated by the convolution's epilogue (stl_conv2d_stats).  Measured slower than the separate
-# statistics pass on B200, so it is off and the kernel variants are only in -DSTL_CONV_STATS builds.
+# BatchNorm statistics accumulated by the convolution's epilogue and finalised by its last CTA (stl_conv2d_bn).  Measured
+# slower than the separate statistics pass on B200 in both forms: off, and the kernel variants are
+# only in -DSTL_CONV_STATS builds (without them stl_conv2d_bn reports "not done" and the separate pass runs anyway).
 FUSED_BN_STATS = os.environ.get("STLPOSE_FUSED_BN_STATS", "0") == "1"
 STEM_IM2COL = os.environ.get("STLPOSE_TRAIN_STEM_IM2COL", "1") != "0"
 MASK_FROM_Z = os.environ.get("STLPOSE_TRAIN_MASK_FROM_Z", "1") != "0"
 
 
-def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bias=None, stats=None):
+def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bias=None, stats=None, bn=None):
     """Tensor-core convolution on a padded bf16 tensor; returns padded bf16 [N,Ho+1,Wo+1,cout] (or fp32 NCHW).
     stats: an fp32 buffer of stl_conv2d_stats_floats(cout_pad) elements -> returns (out, rows): the epilogue also left
-    `rows` rows of per-channel sum / sum of squares there (rows == 0: not for this shape)."""
+    `rows` rows of per-channel sum / sum of squares there (rows == 0: not for this shape).
+    bn: (stats buffer, tickets, eps, momentum, mean, rstd, running_mean, running_var) -> returns (out, done): the last
+    CTA also finalised the BatchNorm statistics (done False: not for this shape, nothing written)."""
     L = _lib.lib()
     n, hp, wpd, cin = x.shape
     h, w = hp - 1, wpd - 1
@@ -170,6 +173,12 @@ def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bi
         rows = ctypes.c_int(0)
         _lib.check(L.stl_conv2d_stats(ctypes.byref(d), _lib.ptr(stats), ctypes.byref(rows), _stream()))
         return out, rows.value
+    if bn is not None:
+        part, tickets, eps, momentum, mean, rstd, run_mean, run_var = bn
+        done = ctypes.c_int(0)
+        _lib.check(L.stl_conv2d_bn(ctypes.byref(d), _lib.ptr(part), tickets.data_ptr(), eps, momentum, _lib.ptr(mean),
+                                   _lib.ptr(rstd), _lib.ptr(run_mean), _lib.ptr(run_var), ctypes.byref(done), _stream()))
+        return out, bool(done.value)
     _lib.check(L.stl_conv2d(ctypes.byref(d), _stream()))
     return out
 
@@ -269,19 +278,19 @@ class _ConvBN(torch.autograd.Function):
         mean = torch.empty(cout, dtype=torch.float32, device=x.device)
         rstd = torch.empty(cout, dtype=torch.float32, device=x.device)
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        rows = 0
+        done = False
         if FUSED_BN_STATS and cout == cout_pad:
-            # the convolution's epilogue accumulates the batch statistics of z: no separate pass over the tensor
+            # the convolution's epilogue accumulates the batch statistics of z and its last CTA finalises mean / rstd /
+            # running statistics (forward ticket of this layer): conv -> normalise, nothing in between
             part = torch.empty(L.stl_conv2d_stats_floats(cout_pad), dtype=torch.float32, device=x.device)
-            z, rows = _conv_raw(x, wp, bp, cout, cout_pad, k, stride, stats=part)
+            z, done = _conv_raw(x, wp, bp, cout, cout_pad, k, stride,
+                                bn=(part, tickets, BN_EPS, float(momentum), mean, rstd, run_mean, run_var))
         else:
             z = _conv_raw(x, wp, bp, cout, cout_pad, k, stride)
         y = torch.empty_like(z)
-        if rows > 0:
-            _lib.check(L.stl_bn_train_forward_fused(_lib.ptr(z), _lib.ptr(part), rows, cout_pad, _lib.ptr(g32), _lib.ptr(b32),
-                                                    _lib.ptr(residual), int(relu), BN_EPS, float(momentum), n, ho, wo, cout,
-                                                    _lib.ptr(y), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(run_mean),
-                                                    _lib.ptr(run_var), _stream()))
+        if done:
+            _lib.check(L.stl_bn_apply(_lib.ptr(z), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(g32), _lib.ptr(b32),
+                                      _lib.ptr(residual), int(relu), n, ho, wo, cout, _lib.ptr(y), _stream()))
         else:
             sums = torch.empty(L.stl_bn_workspace_floats(cout), dtype=torch.float32, device=x.device)
             _lib.check(L.stl_bn_train_forward_ticket(_lib.ptr(z), _lib.ptr(g32), _lib.ptr(b32), _lib.ptr(residual),
