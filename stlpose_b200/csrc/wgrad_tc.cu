@@ -119,7 +119,10 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
       }
     } else if (warp == 1) {
       // ------------------------------------------------------------ MMA issuer
-      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.nt) | (1u << 15) | (1u << 16);   // A and B MN-major
+      // dbg 3 / 4 (measurement only, garbage results): A / A and B addressed as K-major operands - what would the MMA
+      // stream cost if the tiles were transposed first?
+      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.nt) | (p.dbg >= 3 ? 0u : (1u << 15)) |
+                             (p.dbg >= 4 ? 0u : (1u << 16));                                  // A and B MN-major
       for (int i = 0; i < n_tiles; ++i) {
         const int s = i % p.stages;
         const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
@@ -130,11 +133,13 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
           const uint32_t b_src = a_src + (uint32_t)p.a_panels * p.a_panel_bytes;
 #pragma unroll 1
           for (int ks = 0; ks < (p.dbg == 1 ? 0 : kKT / 16); ++ks) {
-            const uint64_t adesc = make_mnmajor_desc(a_src + (uint32_t)(ks * 16 * p.pitch_a), (uint32_t)p.pitch_a, p.lbo_a);
+            const uint64_t adesc = p.dbg >= 3 ? make_kmajor_desc(a_src + (uint32_t)((ks & 3) * 32), 128u)
+                                              : make_mnmajor_desc(a_src + (uint32_t)(ks * 16 * p.pitch_a), (uint32_t)p.pitch_a, p.lbo_a);
 #pragma unroll 1
             for (int m = 0; m < p.n_mma; ++m) {
-              const uint64_t bdesc = make_mnmajor_desc(b_src + (uint32_t)((p.mma_b[tg][m] + ks * 16) * p.pitch_b),
-                                                       (uint32_t)p.pitch_b, p.lbo_b);
+              const uint64_t bdesc = p.dbg >= 4 ? make_kmajor_desc(b_src + (uint32_t)((ks & 3) * 32 + m * 1024), 128u)
+                                                : make_mnmajor_desc(b_src + (uint32_t)((p.mma_b[tg][m] + ks * 16) * p.pitch_b),
+                                                                    (uint32_t)p.pitch_b, p.lbo_b);
               umma_bf16(tmem_base + (uint32_t)(p.mma_acc[m] * p.nt), adesc, bdesc, idesc, (i | ks) ? 1u : 0u);
             }
           }
