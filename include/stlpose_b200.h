@@ -97,6 +97,14 @@ int stl_warp_affine_crops(const void* img_u8_hwc, int img_h, int img_w, const do
 int stl_warp_affine_crops_f32(const float* img_f32_hwc, int img_h, int img_w, const double* minv, int N, int out_h,
                               int out_w, float* out_f32_nchw, void* stream);
 
+/* optimizer.step() of the fine-tuning loop (02_train.py:218; torch.optim.SGD of lib/model_setup.py:138-139 with momentum,
+ * weight decay and optional Nesterov momentum, dampening 0) for ALL parameter tensors in one launch.  items: n_items
+ * records {float* p; const float* grad; float* momentum_buffer (null = no momentum); int32 numel; int32 pad} on the
+ * device; block_offsets[i] = first 1 024-element block of item i, total_blocks = their sum.  Same operations in the same
+ * order as torch: g = grad + wd * p; buf = momentum * buf + g (a zeroed buffer gives torch's first step); p -= lr * g. */
+int stl_sgd_step_batched(const void* items, const int* block_offsets, int n_items, int total_blocks, float lr,
+                         float momentum, float weight_decay, int nesterov, void* stream);
+
 /* conv1 of the stem (models/HRnet.py:286: 3 -> 64 channels, 3x3, stride 2, pad 1) as a 1x1 problem: fp32 NCHW
  * [N][3][H][W] -> its im2col rows, padded-linear bf16 [N][H/2+1][W/2+1][32] with K index ci*9 + kh*3 + kw (the OIHW
  * flatten order, 27 values + 5 zeros).  conv1 is then stl_conv2d with ksize 1 on these rows and the weight read as

@@ -65,6 +65,8 @@ PROTOTYPES = {
     "stl_generate_target": (ctypes.c_int, [vp, vp, vp] + [ctypes.c_int] * 7 + [vp, vp, vp]),
     "stl_upsampled_argmax": (ctypes.c_int, [vp] + [ctypes.c_int] * 6 + [vp, vp, vp]),
     "stl_warp_affine_crops": (ctypes.c_int, [vp] + [ctypes.c_int] * 2 + [vp] + [ctypes.c_int] * 3 + [vp, vp, vp, vp, vp]),
+    "stl_sgd_step_batched": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                            ctypes.c_float, ctypes.c_int, vp]),
     "stl_stem_im2col": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "stl_warp_affine_crops_f32": (ctypes.c_int, [vp] + [ctypes.c_int] * 2 + [vp] + [ctypes.c_int] * 3 + [vp, vp]),
     "stl_pck_accuracy": (ctypes.c_int, [vp, vp] + [ctypes.c_int] * 4 + [ctypes.c_float, vp, vp, vp, vp]),

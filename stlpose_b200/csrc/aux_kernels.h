@@ -13,6 +13,10 @@ int pack_weights(const float* w, const float* gamma, const float* beta, const fl
 // network input (fp32 NCHW, 3 channels) -> padded-linear NHWC bf16 with 16 channels; images >= n_plain are mirrored
 struct PackItem { const float* w; void* wp; int Cout, Cin, k, rows_pad, cols_pad, dgrad; };
 int pack_weights_batched(const PackItem* items, const int* block_offsets, int n_items, int total_blocks, cudaStream_t st);
+// one torch.optim.SGD step (dampening 0) over every parameter tensor in one launch; buf may be null (no momentum)
+struct SgdItem { float* p; const float* g; float* buf; int numel; int pad_; };
+int sgd_step_batched(const SgdItem* items, const int* block_offsets, int n_items, int total_blocks, float lr,
+                     float momentum, float weight_decay, int nesterov, cudaStream_t st);
 int pack_weights_dgrad(const float* w, int Cout, int Cin, int k, int Rows_pad, int K_pad, __nv_bfloat16* wp,
                        float* bias_out, cudaStream_t st);
 int stem_im2col(const float* x, __nv_bfloat16* y, int n_total, int n_plain, int H, int W, cudaStream_t st);

@@ -117,6 +117,15 @@ int stl_warp_affine_crops_f32(const float* img_f32_hwc, int img_h, int img_w, co
   return warp_affine_crops_f32(img_f32_hwc, img_h, img_w, minv, N, out_h, out_w, out_f32_nchw, (cudaStream_t)stream);
 }
 
+int stl_sgd_step_batched(const void* items, const int* block_offsets, int n_items, int total_blocks, float lr,
+                         float momentum, float weight_decay, int nesterov, void* stream) {
+  if (!have_device()) return 1;
+  if (n_items > 0 && (!items || !block_offsets)) { set_error("stl_sgd_step_batched: null pointer"); return 1; }
+  static_assert(sizeof(SgdItem) == 32, "stl_sgd_step_batched item layout");
+  return sgd_step_batched(reinterpret_cast<const SgdItem*>(items), block_offsets, n_items, total_blocks, lr, momentum,
+                          weight_decay, nesterov, (cudaStream_t)stream);
+}
+
 int stl_stem_im2col(const float* x_nchw, void* rows, int N, int H, int W, void* stream) {
   if (!have_device()) return 1;
   if (N > 0 && (!x_nchw || !rows)) { set_error("stl_stem_im2col: null pointer"); return 1; }

@@ -26,7 +26,12 @@ under ``torch.cuda.stream(side_stream)`` are fine.
 """
 import torch
 
+import os
+
+from . import optim as _optim
 from .inference import forward_pass
+
+FUSED_SGD = os.environ.get("STLPOSE_FUSED_SGD", "1") != "0"
 
 _HYPER_SKIP = ("params",)
 
@@ -103,6 +108,10 @@ class TrainStep:
         self.use_graph = bool(use_graph)
         self.warmup = warmup
         self.optimizer_in_graph = bool(use_graph and capture_optimizer and _capturable(optimizer))
+        # plain torch.optim.SGD: the whole update as one launch (stlpose_b200.optim) instead of ~47 foreach launches;
+        # same arithmetic, the optimizer's own state, so schedulers / state_dict() are unaffected
+        self.fused_sgd = bool(FUSED_SGD and _optim.supports(optimizer))
+        self._sgd_tables = None
         self._hyper = None
         model.train()
         if reducer is not None:
@@ -116,6 +125,8 @@ class TrainStep:
         snapshot = self._snapshot()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        if self.fused_sgd:
+            self._sgd_tables = _optim.make_tables(self.optimizer)      # warm-up tables (eager gradient addresses)
         with torch.cuda.stream(side):                      # warm-up: lazy optimizer state, one-time attributes, NCCL setup
             for _ in range(self.warmup if first else 1):
                 self._eager(update=True)
@@ -124,6 +135,10 @@ class TrainStep:
         self._restore(snapshot)                            # warm-up steps must not count as training
         if self.reducer is None:
             self.optimizer.zero_grad(set_to_none=True)
+        if self.fused_sgd:
+            # the captured step uploads its pointer table from a pinned buffer on every replay: a fresh set, allocated
+            # before the capture begins and never refilled afterwards
+            self._sgd_tables = _optim.make_tables(self.optimizer)
         self.graph = torch.cuda.CUDAGraph(keep_graph=True) if self._count_kernels else torch.cuda.CUDAGraph()
         # thread_local: the NCCL watchdog thread polls its events while this thread captures
         mode = "thread_local" if (self.reducer is not None and self.reducer.world > 1) else "global"
@@ -178,9 +193,21 @@ class TrainStep:
             loss.backward(gradient=self.reducer.scale_tensor)
             self.reducer.finish_backward()
         if update:
-            self.optimizer.step()
+            self._optimizer_step()
         self.output = out.detach()
         self.loss.copy_(loss.detach())
+
+    def _optimizer_step(self):
+        if self.fused_sgd:
+            if self._sgd_tables is None or (self.graph is not None and self.optimizer_in_graph is False):
+                # eager steps (no graph, or an optimizer that steps after the replay): their own tables
+                if getattr(self, "_sgd_tables_eager", None) is None:
+                    self._sgd_tables_eager = _optim.make_tables(self.optimizer)
+                _optim.fused_sgd_step(self.optimizer, self._sgd_tables_eager)
+            else:
+                _optim.fused_sgd_step(self.optimizer, self._sgd_tables)
+        else:
+            self.optimizer.step()
 
     def __call__(self, imgs, target, target_weight):
         """Copies the batch into the static buffers (host or device sources), runs the step, returns the device loss."""
@@ -192,7 +219,7 @@ class TrainStep:
                 self._recapture()                          # a scheduler changed lr / momentum / ...: bake the new values
             self.graph.replay()
             if not self.optimizer_in_graph:
-                self.optimizer.step()
+                self._optimizer_step()
         else:
             self._eager(update=True)
         self.model.invalidate_packed_weights()

@@ -384,3 +384,33 @@ def test_parallel_streams_with_injected_delays(monkeypatch, seed):
     which stream runs ahead; a read before its producer finished, or a block reused while another stream still reads it,
     would change bits against the single-stream schedule."""
     _assert_same_state(_three_sgd_steps(monkeypatch, True, delay_seed=seed), _three_sgd_steps(monkeypatch, False))
+
+
+@pytest.mark.parametrize("momentum,wd,nesterov", [(0.9, 5e-4, False), (0.0, 0.0, False), (0.9, 1e-3, True)])
+def test_fused_sgd_step_equals_torch(momentum, wd, nesterov):
+    """stlpose_b200.optim.fused_sgd_step (one launch for all parameter tensors) vs torch.optim.SGD.step() on the same
+    gradients: same operations in the same order, so the parameters and momentum buffers agree bit for bit over
+    several steps (the first one creates the buffers), including tensors whose size is not a multiple of 4."""
+    from stlpose_b200 import optim as O
+    g = torch.Generator(device="cuda").manual_seed(0)
+    shapes = [(64, 3, 3, 3), (17,), (17, 32, 1, 1), (256,), (33, 7), (1,), (128, 128, 3, 3)]
+    pa = [torch.randn(s, device="cuda", generator=g).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = torch.optim.SGD(pa, lr=0.05, momentum=momentum, weight_decay=wd, nesterov=nesterov)
+    ob = torch.optim.SGD(pb, lr=0.05, momentum=momentum, weight_decay=wd, nesterov=nesterov)
+    assert O.supports(ob) and not O.supports(torch.optim.SGD(pb, lr=0.1, momentum=0.9, dampening=0.1))
+    tables = O.make_tables(ob)
+    for step in range(4):
+        for a, b in zip(pa, pb):
+            a.grad = torch.randn(a.shape, device="cuda", generator=g)
+            b.grad = a.grad.clone()
+        if step == 2:
+            for o in (oa, ob):
+                o.param_groups[0]["lr"] = 0.01                       # a scheduler step
+        oa.step()
+        O.fused_sgd_step(ob, tables)
+        for a, b in zip(pa, pb):
+            assert torch.equal(a, b), (step, a.shape)
+            if momentum:
+                assert torch.equal(oa.state[a]["momentum_buffer"], ob.state[b]["momentum_buffer"])
+    assert set(ob.state_dict()["state"].keys()) == set(oa.state_dict()["state"].keys())
