@@ -323,6 +323,19 @@ int stl_bn_train_backward_ticket(const void* dy, const void* y, const void* z, c
 int stl_bn_train_backward_ticket_z(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
                                    const float* beta, int N, int H, int W, int C, void* dz, float* dbeta_dgamma,
                                    float* workspace, unsigned* ticket, void* stream);
+/* The forward pair (statistics, normalisation) and the backward pair (channel sums, gradient) of a BatchNorm layer as ONE
+ * cooperative launch each: the block that finishes the reduction publishes its result, the others wait for it inside the
+ * kernel, then all normalise.  At fine-tuning batch sizes the separate launches are latency, not bandwidth.  `sync`: two
+ * device words that are zero on entry and left zero (one pair per layer and direction).  backward relu: 0 none, 1 mask
+ * from y, 2 mask recomputed from z (needs beta, no residual).  Same results as the separate entry points, bit for bit. */
+int stl_bn_train_forward_coop(const void* z, const float* gamma, const float* beta, const void* residual, int relu,
+                              float eps, float momentum, int N, int H, int W, int C, void* y, float* sums, float* mean,
+                              float* rstd, float* running_mean, float* running_var, unsigned* ticket, unsigned* sync,
+                              void* stream);
+int stl_bn_train_backward_coop(const void* dy, const void* y, const void* z, const float* mean, const float* rstd,
+                               const float* gamma, const float* beta, int relu, int N, int H, int W, int C, void* dz,
+                               void* dres, float* dbeta_dgamma, float* workspace, unsigned* ticket, unsigned* sync,
+                               void* stream);
 
 /* Fuse-layer row (HRnet.py:255-264): y = relu(sum same[i] + sum nearest_upsample(up[j], 2^shift[j])).
  * same_host / up_host: host arrays of device pointers (n_same <= 4, n_up <= 3). */

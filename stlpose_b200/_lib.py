@@ -106,6 +106,9 @@ PROTOTYPES = {
     "stl_bn_train_forward_ticket": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_float, ctypes.c_float] +
                                     [ctypes.c_int] * 4 + [vp] * 8),
     "stl_bn_train_backward_ticket": (ctypes.c_int, [vp] * 6 + [ctypes.c_int] * 5 + [vp] * 6),
+    "stl_bn_train_forward_coop": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_float, ctypes.c_float] +
+                                  [ctypes.c_int] * 4 + [vp] * 8 + [vp]),
+    "stl_bn_train_backward_coop": (ctypes.c_int, [vp] * 7 + [ctypes.c_int] * 5 + [vp] * 6 + [vp]),
     "stl_bn_train_backward_ticket_z": (ctypes.c_int, [vp] * 6 + [ctypes.c_int] * 4 + [vp] * 5),
     "stl_sum_relu_forward": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, ctypes.POINTER(vp), c_int_p, ctypes.c_int,
                                             vp] + [ctypes.c_int] * 4 + [vp]),

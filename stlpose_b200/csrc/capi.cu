@@ -381,6 +381,35 @@ int stl_bn_train_forward_ticket(const void* z, const float* gamma, const float* 
                           rstd, running_mean, running_var, ticket, (cudaStream_t)stream);
 }
 
+int stl_bn_train_forward_coop(const void* z, const float* gamma, const float* beta, const void* residual, int relu,
+                              float eps, float momentum, int N, int H, int W, int C, void* y, float* sums, float* mean,
+                              float* rstd, float* running_mean, float* running_var, unsigned* ticket, unsigned* sync,
+                              void* stream) {
+  if (!have_device()) return 1;
+  if (!z || !gamma || !beta || !y || !sums || !mean || !rstd || !ticket || !sync) {
+    set_error("stl_bn_train_forward_coop: null pointer");
+    return 1;
+  }
+  typedef const __nv_bfloat16* P;
+  return bn_train_forward_coop((P)z, gamma, beta, (P)residual, relu, eps, momentum, N, H, W, C, (__nv_bfloat16*)y, sums,
+                               mean, rstd, running_mean, running_var, ticket, sync, (cudaStream_t)stream);
+}
+
+int stl_bn_train_backward_coop(const void* dy, const void* y, const void* z, const float* mean, const float* rstd,
+                               const float* gamma, const float* beta, int relu, int N, int H, int W, int C, void* dz,
+                               void* dres, float* dbeta_dgamma, float* workspace, unsigned* ticket, unsigned* sync,
+                               void* stream) {
+  if (!have_device()) return 1;
+  if (!dy || !z || !mean || !rstd || !gamma || !dz || !dbeta_dgamma || !workspace || !ticket || !sync ||
+      (relu == 1 && !y) || (relu == 2 && !beta)) {
+    set_error("stl_bn_train_backward_coop: null pointer");
+    return 1;
+  }
+  typedef const __nv_bfloat16* P;
+  return bn_train_backward_coop((P)dy, (P)y, (P)z, mean, rstd, gamma, beta, relu, N, H, W, C, (__nv_bfloat16*)dz,
+                                (__nv_bfloat16*)dres, dbeta_dgamma, workspace, ticket, sync, (cudaStream_t)stream);
+}
+
 int stl_bn_train_forward_fused(const void* z, const float* stat_rows, int rows, int c_pad, const float* gamma,
                                const float* beta, const void* residual, int relu, float eps, float momentum, int N, int H,
                                int W, int C, void* y, float* mean, float* rstd, float* running_mean, float* running_var,

@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "conv.h"
 #include "train_kernels.h"
 
@@ -70,6 +72,7 @@ __device__ __forceinline__ float bn_affine(float z, float g, float m, float r, f
 // counter) adds the rows in a fixed order -- no floating-point atomics, so the statistics are deterministic -- and, in
 // MODE 0, also derives mean / rstd and updates the running statistics (momentum, unbiased variance: nn.BatchNorm2d).
 constexpr int kReduceBlocks = 296;   // 2 per SM
+constexpr int kCoopMaxC = 512;       // cooperative BatchNorm kernels stage 2 x C floats in shared memory
 
 struct BnFinalize {
   float count, eps, momentum;
@@ -77,7 +80,7 @@ struct BnFinalize {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16* __restrict__ a,
+__device__ __forceinline__ bool channel_reduce_body(const __nv_bfloat16* __restrict__ a,
                                                              const __nv_bfloat16* __restrict__ y,
                                                              const __nv_bfloat16* __restrict__ z,
                                                              const float* __restrict__ mean,
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
   __syncthreads();
   if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
   __syncthreads();
-  if (!is_last) return;
+  if (!is_last) return false;
   __threadfence();
   // fixed-order sum of the rows with 16-byte loads: thread = (row group `part`, 4 consecutive columns); every group
   // walks its interleaved share of the rows with four independent accumulators per column (4 x 16 B in flight), then
@@ -234,6 +237,46 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
       }
     }
   }
+  return true;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16* __restrict__ a,
+                                                             const __nv_bfloat16* __restrict__ y,
+                                                             const __nv_bfloat16* __restrict__ z,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, long long pixels, int C,
+                                                             int relu_mask, float* __restrict__ sums,
+                                                             float* __restrict__ partial, unsigned* __restrict__ counter,
+                                                             const BnFinalize fin) {
+  channel_reduce_body<MODE>(a, y, z, mean, rstd, gamma, beta, pixels, C, relu_mask, sums, partial, counter, fin);
+}
+
+// Grid-wide hand-over inside ONE cooperative launch (all blocks co-resident): the block that finished the reduction
+// (`is_last`) publishes its results and raises `flag`; every other block waits for it.  sync[0] = flag, sync[1] = number
+// of blocks that have left; the last one to leave clears both, so the words are zero again between launches.
+__device__ __forceinline__ void grid_handover(unsigned* sync, bool is_last) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (is_last) {
+      __threadfence();
+      atomicExch(sync, 1u);
+    } else {
+      while (atomicAdd(sync, 0u) == 0u) __nanosleep(32);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void grid_leave(unsigned* sync) {
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(sync + 1, 1u) == gridDim.x - 1) {
+    sync[0] = 0u;
+    sync[1] = 0u;
+    __threadfence();
+  }
 }
 
 // BatchNorm statistics from the per-CTA rows the convolution epilogue wrote (conv.h ConvSpec::stats: rows x [2][c_pad]
@@ -280,11 +323,11 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
 }
 
 // y = [relu]( gamma * (z - mean) * rstd + beta [+ residual] ) on the valid pixels, zero on the zero cells
-__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ z,
-                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       const __nv_bfloat16* __restrict__ residual, int relu,
-                                                       __nv_bfloat16* __restrict__ y, int N, int H, int W, int C, const PixIdx px) {
+__device__ __forceinline__ void bn_apply_body(const __nv_bfloat16* __restrict__ z,
+                                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                              const __nv_bfloat16* __restrict__ residual, int relu,
+                                              __nv_bfloat16* __restrict__ y, int N, int H, int W, int C, const PixIdx& px) {
   const uint32_t total = (uint32_t)N * (uint32_t)(px.Hp * px.Wp * px.c8n);
   // the grid stride is a multiple of the channel-group count (launcher), so a thread keeps its 8 channels: the
   // per-channel parameters live in registers instead of 32 scalar loads per 16-byte item
@@ -317,8 +360,39 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
   }
 }
 
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ z,
+                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const __nv_bfloat16* __restrict__ residual, int relu,
+                                                       __nv_bfloat16* __restrict__ y, int N, int H, int W, int C, const PixIdx px) {
+  bn_apply_body(z, mean, rstd, gamma, beta, residual, relu, y, N, H, W, C, px);
+}
+
+// Batch statistics + normalisation of one BatchNorm layer in ONE cooperative launch: phase 1 = channel_reduce_kernel<0>
+// (the last block finalises mean / rstd / running statistics), grid hand-over, phase 2 = bn_apply_kernel.  At fine-tuning
+// batch sizes the two separate launches are latency, not bandwidth (8 + 5 us on tensors of a few hundred KB).
+__global__ void __launch_bounds__(256) bn_forward_coop_kernel(const __nv_bfloat16* __restrict__ z,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta,
+                                                              const __nv_bfloat16* __restrict__ residual, int relu,
+                                                              __nv_bfloat16* __restrict__ y, long long pixels, int N, int H,
+                                                              int W, int C, float* __restrict__ sums,
+                                                              float* __restrict__ partial, unsigned* __restrict__ counter,
+                                                              unsigned* __restrict__ sync, const BnFinalize fin,
+                                                              const PixIdx px) {
+  const bool last = channel_reduce_body<0>(z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pixels, C, 0, sums,
+                                           partial, counter, fin);
+  grid_handover(sync, last);
+  // mean / rstd were written by another block of THIS launch: read them once, past L1, into shared memory
+  __shared__ float s_stat[2 * kCoopMaxC];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { s_stat[c] = __ldcg(fin.mean + c); s_stat[kCoopMaxC + c] = __ldcg(fin.rstd + c); }
+  __syncthreads();
+  bn_apply_body(z, s_stat, s_stat + kCoopMaxC, gamma, beta, residual, relu, y, N, H, W, C, px);
+  grid_leave(sync);
+}
+
 // dz = gamma * rstd * (g - sum_g/cnt - xhat * sum_gx/cnt),  g = dy masked by (y > 0) when relu; d_res = g
-__global__ void __launch_bounds__(256) bn_backward_kernel(const __nv_bfloat16* __restrict__ dy,
+__device__ __forceinline__ void bn_backward_body(const __nv_bfloat16* __restrict__ dy,
                                                           const __nv_bfloat16* __restrict__ y,
                                                           const __nv_bfloat16* __restrict__ z,
                                                           const float* __restrict__ mean,
@@ -328,7 +402,7 @@ __global__ void __launch_bounds__(256) bn_backward_kernel(const __nv_bfloat16* _
                                                           const float* __restrict__ sums, float count, int relu_mask,
                                                           __nv_bfloat16* __restrict__ dz,
                                                           __nv_bfloat16* __restrict__ dres, int N, int H, int W,
-                                                          int C, const PixIdx px) {
+                                                          int C, const PixIdx& px) {
   const uint32_t total = (uint32_t)N * (uint32_t)(px.Hp * px.Wp * px.c8n);
   float gr8[8], m8[8], r8[8], sg8[8], sx8[8];      // gamma*rstd, mean, rstd, sum_g/cnt, sum_gx/cnt of this thread's channels
   float ga8[8], be8[8];                            // gamma, beta (relu_mask == 2: the mask is recomputed from z)
@@ -365,6 +439,46 @@ __global__ void __launch_bounds__(256) bn_backward_kernel(const __nv_bfloat16* _
     *reinterpret_cast<uint4*>(dz + (size_t)i * 8) = o_dz;
     if (dres) *reinterpret_cast<uint4*>(dres + (size_t)i * 8) = o_dr;
   }
+}
+
+__global__ void __launch_bounds__(256) bn_backward_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                          const __nv_bfloat16* __restrict__ y,
+                                                          const __nv_bfloat16* __restrict__ z,
+                                                          const float* __restrict__ mean,
+                                                          const float* __restrict__ rstd,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta,
+                                                          const float* __restrict__ sums, float count, int relu_mask,
+                                                          __nv_bfloat16* __restrict__ dz,
+                                                          __nv_bfloat16* __restrict__ dres, int N, int H, int W,
+                                                          int C, const PixIdx px) {
+  bn_backward_body(dy, y, z, mean, rstd, gamma, beta, sums, count, relu_mask, dz, dres, N, H, W, C, px);
+}
+
+// Both passes of the BatchNorm backward in ONE cooperative launch (phase 1 = channel_reduce_kernel<1>: dbeta | dgamma,
+// grid hand-over, phase 2 = bn_backward_kernel).
+__global__ void __launch_bounds__(256) bn_backward_coop_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                               const __nv_bfloat16* __restrict__ y,
+                                                               const __nv_bfloat16* __restrict__ z,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float count, int relu_mask,
+                                                               __nv_bfloat16* __restrict__ dz,
+                                                               __nv_bfloat16* __restrict__ dres, long long pixels, int N,
+                                                               int H, int W, int C, float* __restrict__ sums,
+                                                               float* __restrict__ partial,
+                                                               unsigned* __restrict__ counter,
+                                                               unsigned* __restrict__ sync, const PixIdx px) {
+  const bool last = channel_reduce_body<1>(dy, y, z, mean, rstd, gamma, beta, pixels, C, relu_mask, sums, partial, counter,
+                                           BnFinalize{});
+  grid_handover(sync, last);
+  // dbeta | dgamma were written by another block of THIS launch: read them once, past L1, into shared memory
+  __shared__ float s_sums[2 * kCoopMaxC];
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) s_sums[c] = __ldcg(sums + c);
+  __syncthreads();
+  bn_backward_body(dy, y, z, mean, rstd, gamma, beta, s_sums, count, relu_mask, dz, dres, N, H, W, C, px);
+  grid_leave(sync);
 }
 
 // ------------------------------------------------------------------ fuse-layer sum (HRnet.py:255-264) and backward
@@ -649,6 +763,16 @@ int grid_for(long long total, int block, int cap = 148 * 16) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+// Block count of the channel reductions (<= kReduceBlocks rows of partial sums): a multiple of 3 when the channel-group
+// count has a factor 3, so that the cooperative kernels - whose second phase needs that - reduce in the same order and
+// give the same bits as the separate launches.
+int reduce_grid(long long pixels, int C) {
+  const int lanes = 256 / (C / 8);
+  int g = grid_for(pixels, lanes * 8, kReduceBlocks);
+  if (256 % (C / 8)) g = (g + 2) / 3 * 3 > kReduceBlocks ? kReduceBlocks / 3 * 3 : (g + 2) / 3 * 3;
+  return g;
+}
+
 }  // namespace
 
 size_t bn_workspace_floats(int C) { return (size_t)2 * C * (1 + kReduceBlocks) + 32; }
@@ -662,9 +786,8 @@ int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* be
   // workspace cleared here
   unsigned* counter = ticket ? ticket : reinterpret_cast<unsigned*>(sums + (size_t)2 * C * (1 + kReduceBlocks));
   if (!ticket) cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
-  const int lanes = 256 / (C / 8);
   BnFinalize fin{(float)((long long)N * H * W), eps, momentum, mean, rstd, run_mean, run_var};
-  channel_reduce_kernel<0><<<grid_for(pixels, lanes * 8, kReduceBlocks), 256, 0, st>>>(
+  channel_reduce_kernel<0><<<reduce_grid(pixels, C), 256, 0, st>>>(
       z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pixels, C, 0, sums, sums + 2 * C, counter, fin);
   if (check("bn stats")) return 1;
   PixIdx px;
@@ -674,6 +797,86 @@ int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* be
   bn_apply_kernel<<<grid_mult(pixels * (C / 8), C / 8), 256, 0, st>>>(z, mean, rstd, gamma, beta, residual, relu, y, N, H,
                                                                   W, C, px);
   return check("bn apply");
+}
+
+namespace {
+// largest co-resident grid of a cooperative BatchNorm kernel on the current device (blocks per SM x SMs), cached per device
+template <typename K>
+int coop_capacity(K kernel, int slot) {
+  static std::mutex mu;
+  static int cap[2][DeviceOnce::kMaxDevices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= DeviceOnce::kMaxDevices) return 0;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!cap[slot][dev]) {
+    int per_sm = 0, coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) == cudaSuccess && per_sm > 0)
+      cap[slot][dev] = per_sm * device_sm_count();
+    else
+      cap[slot][dev] = -1;
+  }
+  return cap[slot][dev] > 0 ? cap[slot][dev] : 0;
+}
+// grid of the fused kernels: the reduction's block count, a multiple of 3 when the channel-group count has a factor 3
+// (the normalisation phase keeps a thread on its channel group), within the co-resident capacity
+int coop_grid(long long pixels, int C, int capacity) {
+  int g = reduce_grid(pixels, C);
+  if (g > capacity) g = capacity / 3 * 3;
+  return g;
+}
+}  // namespace
+
+int bn_train_forward_coop(const __nv_bfloat16* z, const float* gamma, const float* beta, const __nv_bfloat16* residual,
+                          int relu, float eps, float momentum, int N, int H, int W, int C, __nv_bfloat16* y, float* sums,
+                          float* mean, float* rstd, float* run_mean, float* run_var, unsigned* ticket, unsigned* sync,
+                          cudaStream_t st) {
+  if (C % 8 || C > 2048 || (256 % (C / 8) && (C / 8) % 3)) { set_error("bn_train_forward_coop: C=%d unsupported", C); return 1; }
+  if (C > kCoopMaxC)
+    return bn_train_forward(z, gamma, beta, residual, relu, eps, momentum, N, H, W, C, y, sums, mean, rstd, run_mean, run_var,
+                            ticket, st);
+  const long long pixels = (long long)N * (H + 1) * (W + 1);
+  if (pixels * (C / 8) >= (1ll << 31)) { set_error("bn_train_forward_coop: tensor too large for 32-bit item indexing"); return 1; }
+  const int cap = coop_capacity(bn_forward_coop_kernel, 0);
+  const int grid = cap ? coop_grid(pixels, C, cap) : 0;
+  if (grid < 1)    // no cooperative launch on this device: the two separate launches
+    return bn_train_forward(z, gamma, beta, residual, relu, eps, momentum, N, H, W, C, y, sums, mean, rstd, run_mean, run_var,
+                            ticket, st);
+  BnFinalize fin{(float)((long long)N * H * W), eps, momentum, mean, rstd, run_mean, run_var};
+  PixIdx px;
+  px.init(C, H, W);
+  long long pixels_ = pixels;
+  float* partial = sums + 2 * C;
+  void* args[] = {(void*)&z, (void*)&gamma, (void*)&beta, (void*)&residual, (void*)&relu, (void*)&y, (void*)&pixels_,
+                  (void*)&N, (void*)&H, (void*)&W, (void*)&C, (void*)&sums, (void*)&partial, (void*)&ticket, (void*)&sync,
+                  (void*)&fin, (void*)&px};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)bn_forward_coop_kernel, dim3(grid), dim3(256), args, 0, st);
+  if (e != cudaSuccess) { set_error("bn_forward_coop launch: %s", cudaGetErrorString(e)); return 1; }
+  return check("bn forward (cooperative)");
+}
+
+int bn_train_backward_coop(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* z, const float* mean,
+                           const float* rstd, const float* gamma, const float* beta, int relu, int N, int H, int W, int C,
+                           __nv_bfloat16* dz, __nv_bfloat16* dres, float* sums, float* partial, unsigned* ticket,
+                           unsigned* sync, cudaStream_t st) {
+  if (C % 8 || C > 2048 || (256 % (C / 8) && (C / 8) % 3)) { set_error("bn_train_backward_coop: C=%d unsupported", C); return 1; }
+  if (relu == 2 && (!beta || dres)) { set_error("bn_train_backward_coop: the z-recomputed mask needs beta and no residual"); return 1; }
+  const long long pixels = (long long)N * (H + 1) * (W + 1);
+  if (pixels * (C / 8) >= (1ll << 31)) { set_error("bn_train_backward_coop: tensor too large for 32-bit item indexing"); return 1; }
+  const int cap = C <= kCoopMaxC ? coop_capacity(bn_backward_coop_kernel, 1) : 0;
+  const int grid = cap ? coop_grid(pixels, C, cap) : 0;
+  if (grid < 1)
+    return bn_train_backward(dy, y, z, mean, rstd, gamma, beta, relu, N, H, W, C, dz, dres, sums, partial, ticket, st);
+  PixIdx px;
+  px.init(C, H, W);
+  long long pixels_ = pixels;
+  float count = (float)((long long)N * H * W);
+  void* args[] = {(void*)&dy, (void*)&y, (void*)&z, (void*)&mean, (void*)&rstd, (void*)&gamma, (void*)&beta, (void*)&count,
+                  (void*)&relu, (void*)&dz, (void*)&dres, (void*)&pixels_, (void*)&N, (void*)&H, (void*)&W, (void*)&C,
+                  (void*)&sums, (void*)&partial, (void*)&ticket, (void*)&sync, (void*)&px};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)bn_backward_coop_kernel, dim3(grid), dim3(256), args, 0, st);
+  if (e != cudaSuccess) { set_error("bn_backward_coop launch: %s", cudaGetErrorString(e)); return 1; }
+  return check("bn backward (cooperative)");
 }
 
 int bn_train_forward_fused(const __nv_bfloat16* z, const float* stat_rows, int rows, int c_pad, const float* gamma,
@@ -717,9 +920,8 @@ int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __n
   if (!partial) partial = sums + 2 * C;
   unsigned* counter = ticket ? ticket : reinterpret_cast<unsigned*>(partial + (size_t)2 * C * kReduceBlocks);
   if (!ticket) cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
-  const int lanes = 256 / (C / 8);
   if (relu == 2 && (!beta || dres)) { set_error("bn_train_backward: the z-recomputed mask needs beta and no residual"); return 1; }
-  channel_reduce_kernel<1><<<grid_for(pixels, lanes * 8, kReduceBlocks), 256, 0, st>>>(
+  channel_reduce_kernel<1><<<reduce_grid(pixels, C), 256, 0, st>>>(
       dy, y, z, mean, rstd, gamma, beta, pixels, C, relu, sums, partial, counter, BnFinalize{});
   if (check("bn backward reduce")) return 1;
   PixIdx px;

@@ -9,6 +9,16 @@ size_t bn_workspace_floats(int C);
 int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* beta, const __nv_bfloat16* residual,
                      int relu, float eps, float momentum, int N, int H, int W, int C, __nv_bfloat16* y, float* sums,
                      float* mean, float* rstd, float* run_mean, float* run_var, unsigned* ticket, cudaStream_t st);
+// statistics + normalisation (backward: both passes) in ONE cooperative launch; `sync`: two device words, zero between
+// launches; falls back to the two separate launches on a device without cooperative launch
+int bn_train_forward_coop(const __nv_bfloat16* z, const float* gamma, const float* beta, const __nv_bfloat16* residual,
+                          int relu, float eps, float momentum, int N, int H, int W, int C, __nv_bfloat16* y, float* sums,
+                          float* mean, float* rstd, float* run_mean, float* run_var, unsigned* ticket, unsigned* sync,
+                          cudaStream_t st);
+int bn_train_backward_coop(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* z, const float* mean,
+                           const float* rstd, const float* gamma, const float* beta, int relu, int N, int H, int W, int C,
+                           __nv_bfloat16* dz, __nv_bfloat16* dres, float* sums, float* partial, unsigned* ticket,
+                           unsigned* sync, cudaStream_t st);
 // statistics from the rows a convolution launched with ConvSpec::stats left behind, then the normalisation
 int bn_train_forward_fused(const __nv_bfloat16* z, const float* stat_rows, int rows, int c_pad, const float* gamma,
                            const float* beta, const __nv_bfloat16* residual, int relu, float eps, float momentum, int N,

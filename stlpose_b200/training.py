@@ -144,6 +144,21 @@ def _pack_weights_dgrad(w, k_pad):
 FUSED_BN_STATS = os.environ.get("STLPOSE_FUSED_BN_STATS", "0") == "1"
 STEM_IM2COL = os.environ.get("STLPOSE_TRAIN_STEM_IM2COL", "1") != "0"
 MASK_FROM_Z = os.environ.get("STLPOSE_TRAIN_MASK_FROM_Z", "1") != "0"
+# statistics + normalisation (and both backward passes) of a BatchNorm layer as one cooperative launch each: saves two
+# graph nodes per layer, but the in-kernel hand-over makes the kernel itself slower than the pair (15 vs 13 us at 6 MB,
+# 69 vs 65 us at 52 MB).  "auto": only for tensors <= 16 MB and only in a single-GPU process - a cooperative grid that
+# spins for its last blocks next to in-flight NCCL kernels is not something to rely on.  "1" / "0" force it on / off.
+COOP_BN = os.environ.get("STLPOSE_TRAIN_COOP_BN", "auto")
+_COOP_BN_MAX_BYTES = 16 << 20
+
+
+def _use_coop_bn(z):
+    if COOP_BN in ("0", "1"):
+        return COOP_BN == "1"
+    if z.numel() * z.element_size() > _COOP_BN_MAX_BYTES:
+        return False
+    import torch.distributed as dist
+    return not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
 
 
 def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bias=None, stats=None, bn=None):
@@ -293,10 +308,17 @@ class _ConvBN(torch.autograd.Function):
                                       _lib.ptr(residual), int(relu), n, ho, wo, cout, _lib.ptr(y), _stream()))
         else:
             sums = torch.empty(L.stl_bn_workspace_floats(cout), dtype=torch.float32, device=x.device)
-            _lib.check(L.stl_bn_train_forward_ticket(_lib.ptr(z), _lib.ptr(g32), _lib.ptr(b32), _lib.ptr(residual),
-                                                     int(relu), BN_EPS, float(momentum), n, ho, wo, cout, _lib.ptr(y),
-                                                     _lib.ptr(sums), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(run_mean),
-                                                     _lib.ptr(run_var), tickets.data_ptr(), _stream()))
+            if _use_coop_bn(z):
+                _lib.check(L.stl_bn_train_forward_coop(_lib.ptr(z), _lib.ptr(g32), _lib.ptr(b32), _lib.ptr(residual),
+                                                       int(relu), BN_EPS, float(momentum), n, ho, wo, cout, _lib.ptr(y),
+                                                       _lib.ptr(sums), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(run_mean),
+                                                       _lib.ptr(run_var), tickets.data_ptr(), tickets.data_ptr() + 8,
+                                                       _stream()))
+            else:
+                _lib.check(L.stl_bn_train_forward_ticket(_lib.ptr(z), _lib.ptr(g32), _lib.ptr(b32), _lib.ptr(residual),
+                                                         int(relu), BN_EPS, float(momentum), n, ho, wo, cout, _lib.ptr(y),
+                                                         _lib.ptr(sums), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(run_mean),
+                                                         _lib.ptr(run_var), tickets.data_ptr(), _stream()))
         ctx.tickets = tickets
         ctx.sinks = sinks
         ctx.save_for_backward(x, weight, z, y, mean, rstd, g32, b32)
@@ -317,7 +339,13 @@ class _ConvBN(torch.autograd.Function):
         # (parallel.GradientReducer.bind) - written straight into the bucket by the kernels, nothing returned
         wsink, bsink = ctx.sinks if ctx.sinks is not None else (None, None)
         sums = bsink.view if bsink is not None else torch.empty(2 * cout, dtype=torch.float32, device=x.device)   # dbeta | dgamma
-        if relu and not has_res and MASK_FROM_Z:
+        if _use_coop_bn(z):
+            mode = 0 if not relu else (2 if (not has_res and MASK_FROM_Z) else 1)
+            _lib.check(L.stl_bn_train_backward_coop(_lib.ptr(dy), _lib.ptr(y) if mode == 1 else None, _lib.ptr(z), _lib.ptr(mean),
+                                                    _lib.ptr(rstd), _lib.ptr(g32), _lib.ptr(b32), mode, n, ho, wo, cout,
+                                                    _lib.ptr(dz), _lib.ptr(dres), _lib.ptr(sums), _lib.ptr(ws),
+                                                    ctx.tickets.data_ptr() + 4, ctx.tickets.data_ptr() + 16, _stream()))
+        elif relu and not has_res and MASK_FROM_Z:
             # ReLU unit without residual: y > 0 <=> gamma * (z - mean) * rstd + beta > 0, recomputed from z with the
             # forward's exact operations - one tensor read less in each of the two backward passes
             _lib.check(L.stl_bn_train_backward_ticket_z(_lib.ptr(dy), _lib.ptr(z), _lib.ptr(mean), _lib.ptr(rstd),
@@ -424,11 +452,11 @@ class _FuseSum(torch.autograd.Function):
 
 
 def _tickets(bn, device):
-    """Two zero-initialised device words per BatchNorm layer (forward / backward reduction tickets, see
-    stl_bn_train_*_ticket): the reduction kernels leave them zero, so no memset is needed per call."""
+    """Zero-initialised device words per BatchNorm layer (forward / backward reduction tickets and the hand-over words of
+    the cooperative kernels, see stl_bn_train_*_ticket / _coop): the kernels leave them zero, so no memset per call."""
     t = getattr(bn, "_stl_tickets", None)
     if t is None or t.device != device:
-        t = torch.zeros(2, dtype=torch.int32, device=device)
+        t = torch.zeros(8, dtype=torch.int32, device=device)   # [0] fwd ticket, [1] bwd ticket, [2:4] / [4:6] fwd / bwd hand-over
         bn._stl_tickets = t
     return t
 

@@ -281,7 +281,7 @@ def test_conv_epilogue_statistics(cin, cout, k, stride, hw, n):
     assert (rma - rmb).abs().max().item() < 1e-5 and ((rva - rvb).abs() / rvb).max().item() < 1e-4
     assert (_unpadded(ya) - _unpadded(yb)).abs().max().item() <= 2 ** -7 * max(1.0, _unpadded(yb).abs().max().item())
     # stl_conv2d_bn: the convolution's last CTA finalises the statistics itself (twice: the ticket must be left at zero)
-    tickets = torch.zeros(2, dtype=torch.int32, device=DEV)
+    tickets = torch.zeros(8, dtype=torch.int32, device=DEV)
     for _ in range(2):
         mean, rstd = torch.full((cout,), float("nan"), device=DEV), torch.full((cout,), float("nan"), device=DEV)
         rm, rv = torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV)
@@ -331,3 +331,64 @@ def test_bn_backward_mask_recomputed_from_z_is_bit_identical(shape):
                                                       _lib.ptr(ws), ticket.data_ptr(), _lib.current_stream()))
         outs.append((dz, dbg))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("shape", [(3, 32, 16, 12), (2, 64, 32, 24), (5, 48, 12, 9), (2, 256, 8, 6), (6, 32, 64, 48)])
+@pytest.mark.parametrize("relu,with_res", [(True, True), (True, False), (False, False)])
+def test_cooperative_bn_kernels_equal_the_separate_launches(shape, relu, with_res):
+    """stl_bn_train_forward_coop / _backward_coop (reduction, in-kernel hand-over, normalisation in one cooperative
+    launch) vs the two-launch entry points: identical outputs, statistics and gradients, bit for bit; the ticket and
+    hand-over words are left at zero (second call on the same words)."""
+    L = _lib.lib()
+    n, c, h, w = shape
+    g = torch.Generator(device=DEV).manual_seed(c * 3 + h)
+    z = bf16_round(torch.randn(shape, device=DEV, generator=g) * 1.2 + 0.1)
+    res = _padded(bf16_round(torch.randn(shape, device=DEV, generator=g))) if with_res else None
+    gamma = torch.rand(c, device=DEV, generator=g) + 0.5
+    beta = torch.randn(c, device=DEV, generator=g) * 0.2
+    zp = _padded(z)
+    dyp = _padded(bf16_round(torch.randn(shape, device=DEV, generator=g)))
+    words = torch.zeros(8, dtype=torch.int32, device=DEV)
+
+    def run(coop):
+        y = torch.empty_like(zp)
+        sums = torch.empty(L.stl_bn_workspace_floats(c), device=DEV)
+        mean, rstd = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+        rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+        if coop:
+            _lib.check(L.stl_bn_train_forward_coop(_lib.ptr(zp), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(res), int(relu),
+                                                   1e-5, 0.1, n, h, w, c, _lib.ptr(y), _lib.ptr(sums), _lib.ptr(mean),
+                                                   _lib.ptr(rstd), _lib.ptr(rm), _lib.ptr(rv), words.data_ptr(),
+                                                   words.data_ptr() + 8, _lib.current_stream()))
+        else:
+            _lib.check(L.stl_bn_train_forward_ticket(_lib.ptr(zp), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(res), int(relu),
+                                                     1e-5, 0.1, n, h, w, c, _lib.ptr(y), _lib.ptr(sums), _lib.ptr(mean),
+                                                     _lib.ptr(rstd), _lib.ptr(rm), _lib.ptr(rv), words.data_ptr(),
+                                                     _lib.current_stream()))
+        dz = torch.empty_like(zp)
+        dres = torch.empty_like(zp) if with_res else None
+        dbg = torch.empty(2 * c, device=DEV)
+        ws = torch.empty(L.stl_bn_workspace_floats(c), device=DEV)
+        mode = 0 if not relu else (1 if with_res else 2)
+        if coop:
+            _lib.check(L.stl_bn_train_backward_coop(_lib.ptr(dyp), _lib.ptr(y) if mode == 1 else None, _lib.ptr(zp),
+                                                    _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma), _lib.ptr(beta), mode, n, h,
+                                                    w, c, _lib.ptr(dz), _lib.ptr(dres), _lib.ptr(dbg), _lib.ptr(ws),
+                                                    words.data_ptr() + 4, words.data_ptr() + 16, _lib.current_stream()))
+        elif mode == 2:
+            _lib.check(L.stl_bn_train_backward_ticket_z(_lib.ptr(dyp), _lib.ptr(zp), _lib.ptr(mean), _lib.ptr(rstd),
+                                                        _lib.ptr(gamma), _lib.ptr(beta), n, h, w, c, _lib.ptr(dz), _lib.ptr(dbg),
+                                                        _lib.ptr(ws), words.data_ptr() + 4, _lib.current_stream()))
+        else:
+            _lib.check(L.stl_bn_train_backward_ticket(_lib.ptr(dyp), _lib.ptr(y), _lib.ptr(zp), _lib.ptr(mean), _lib.ptr(rstd),
+                                                      _lib.ptr(gamma), int(relu), n, h, w, c, _lib.ptr(dz), _lib.ptr(dres),
+                                                      _lib.ptr(dbg), _lib.ptr(ws), words.data_ptr() + 4, _lib.current_stream()))
+        torch.cuda.synchronize()
+        assert int(words.abs().sum()) == 0
+        return y, mean, rstd, rm, rv, dz, dres, dbg
+
+    ref = run(False)
+    for _ in range(2):
+        got = run(True)
+        for a, b in zip(got, ref):
+            assert (a is None and b is None) or torch.equal(a, b)

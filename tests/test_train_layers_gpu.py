@@ -83,7 +83,7 @@ def test_every_unit_matches_the_oracle_unit(width, hw):
         wd = w.clone().requires_grad_(True)
         gd, bd = sd0[bn + ".weight"].cuda().requires_grad_(True), sd0[bn + ".bias"].cuda().requires_grad_(True)
         rm, rv = sd0[bn + ".running_mean"].cuda().clone(), sd0[bn + ".running_var"].cuda().clone()
-        tickets = torch.zeros(2, dtype=torch.int32, device="cuda")
+        tickets = torch.zeros(8, dtype=torch.int32, device="cuda")
         yd = training._ConvBN.apply(xp, wd, gd, bd, rp, rm, rv, stride, relu, 0.1, tickets, None)
         yd.backward(_padded(dy.cuda()))
         torch.cuda.synchronize()
