@@ -193,6 +193,11 @@ typedef struct stl_conv_desc {
   int max_ctas;            /* 0 = auto */
   void* dbg_counters;      /* optional int64 [148][3][4]: per-CTA cycle counters of the producer / MMA / epilogue
                               roles (measurement aid; null in normal use) */
+  const void* in2;         /* optional second input of a 1x1 / stride-1 convolution, padded-linear bf16 [N][H+1][W+1][Cin2]:
+                              K = [in | in2], w_packed has Cin + Cin2 columns.  Two 1x1 convolutions that are summed
+                              before the activation (Bottleneck conv3 + downsample, models/HRnet.py:88-101) run as one
+                              launch; their sum stays in the fp32 accumulator.  impl 0 only. */
+  int Cin2;
 } stl_conv_desc;
 
 int stl_conv2d(const stl_conv_desc* desc, void* stream);

@@ -411,6 +411,19 @@ int stem_im2col(const float* x, __nv_bfloat16* y, int n_total, int n_plain, int 
   return check("stem_im2col");
 }
 
+namespace {
+__global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+}  // namespace
+
+int add_f32(const float* a, const float* b, float* out, int n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  add_f32_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, b, out, n);
+  return check("add_f32");
+}
+
 int fuse_sum(const __nv_bfloat16* x, const __nv_bfloat16* const* z, const int* shift, int n_up, __nv_bfloat16* y,
              int N, int H, int W, int C, cudaStream_t st) {
   FuseArgs a{};

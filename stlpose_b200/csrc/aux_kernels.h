@@ -19,6 +19,7 @@ int sgd_step_batched(const SgdItem* items, const int* block_offsets, int n_items
                      float momentum, float weight_decay, int nesterov, cudaStream_t st);
 int pack_weights_dgrad(const float* w, int Cout, int Cin, int k, int Rows_pad, int K_pad, __nv_bfloat16* wp,
                        float* bias_out, cudaStream_t st);
+int add_f32(const float* a, const float* b, float* out, int n, cudaStream_t st);   // out = a + b
 int stem_im2col(const float* x, __nv_bfloat16* y, int n_total, int n_plain, int H, int W, cudaStream_t st);
 int stem_pack_input(const float* x, __nv_bfloat16* y, int n_total, int n_plain, int H, int W, cudaStream_t st);
 int fuse_sum(const __nv_bfloat16* x, const __nv_bfloat16* const* z, const int* shift, int n_up, __nv_bfloat16* y,

@@ -264,6 +264,11 @@ static int conv2d_impl(const stl_conv_desc* d, float* stats, int* stats_rows, vo
   s.force_mb = d->force_mb;
   s.max_ctas = d->max_ctas;
   s.dbg_counters = d->dbg_counters;
+  if (d->in2) {
+    if (d->impl != 0 || d->Cin2 <= 0) { set_error("stl_conv2d: a second input needs impl 0 and Cin2 > 0"); return 1; }
+    s.in2 = reinterpret_cast<const __nv_bfloat16*>(d->in2);
+    s.in2_C = d->Cin2;
+  }
   if (stats_rows) *stats_rows = 0;
   if (d->impl == 2) return conv_launch_naive(s, (cudaStream_t)stream);
   if (!stats) return conv_launch(s, (cudaStream_t)stream);

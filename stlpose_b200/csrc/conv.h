@@ -29,6 +29,11 @@ struct PaddedGeom {
 struct ConvSpec {
   const __nv_bfloat16* in = nullptr;   // padded-linear NHWC, Cin channels
   PaddedGeom in_geom{};
+  // optional second input of a 1x1 convolution (same N, H, W; in2_C channels): the K dimension is the concatenation
+  // [in | in2] and the packed weights have in_geom.C + in2_C columns.  Two 1x1 convolutions that are added before the
+  // activation (Bottleneck conv3 + downsample, HRnet.py:88-101) become ONE launch whose sum stays in the fp32 accumulator
+  const __nv_bfloat16* in2 = nullptr;
+  int in2_C = 0;
   void* out = nullptr;                 // padded-linear NHWC bf16 (out_nchw=0) or fp32 NCHW (out_nchw=1)
   int cout = 0;                        // real output channels
   int cout_pad = 0;                    // multiple of 16; packed weights/bias have this many rows
@@ -83,12 +88,14 @@ struct FastDiv {
 // Kernel parameters (passed __grid_constant__).
 struct ConvParams {
   CUtensorMap tmA;
+  CUtensorMap tmA2;  // second input tensor (ConvSpec::in2): K chunks >= n_chunks_a are loaded from it
   CUtensorMap tmB;
   CUtensorMap tmO;   // output tensor   (flat mode, bf16 out): epilogue stores whole panels with TMA
   CUtensorMap tmR;   // residual tensor (same geometry): panels are pre-loaded into the staging buffer
   int mode;        // 0: stride-1 flat-pixel tiles, 1: stride-2 structured tiles
   int taps;        // 1 or 9
-  int n_chunks;    // Cin / ck
+  int n_chunks;    // Cin / ck (both inputs)
+  int n_chunks_a;  // chunks that come from tmA (= n_chunks without a second input)
   int ck;          // channels per K chunk: 16, 32 or 64 (row = 2*ck bytes = swizzle span)
   int ksteps_last; // MMA K steps issued for the LAST chunk (ck / 16 unless its TMA box reaches past the channel count)
   int nt;          // UMMA N

@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
     for (int i = 0; i < 4; ++i) { mbar_init(&ctl->res_full[i], 1); mbar_init(&ctl->epi_free[i], 1); mbar_init(&ctl->epi_done[i], 8); }
     fence_mbar_init();
     tma_prefetch_desc(&p.tmA);
+    if (p.n_chunks_a < p.n_chunks) tma_prefetch_desc(&p.tmA2);
     tma_prefetch_desc(&p.tmB);
     if (p.epi_tma) { tma_prefetch_desc(&p.tmO); if (p.residual) tma_prefetch_desc(&p.tmR); }
   }
@@ -378,12 +379,16 @@ __global__ void __launch_bounds__(EPI == kEpiStagedKW ? kThreadsKW : kThreads, 1
               const uint32_t dst = a_base + s * p.a_stage_bytes;
               if (kFlatOnly || (!kStruct && p.mode == 0)) {
                 const int row0 = p.a_shift ? q0 - p.halo : q0 + (kh - 1) * p.in_Wp + (kw - 1);
+                // (two-input 1x1 convolutions: the K chunks past the first tensor's channels come from the second)
+                const bool second = chunk >= p.n_chunks_a;
+                const CUtensorMap* tm = second ? &p.tmA2 : &p.tmA;
+                const int c0 = (second ? chunk - p.n_chunks_a : chunk) * p.ck;
                 for (int i = 0; i < p.a_pieces; ++i) {
                   if (PAIR)
-                    tma_load_2d_pair(dst + (uint32_t)(i * p.a_box_rows) * kSpan, &p.tmA, &ctl->a_full[s], chunk * p.ck,
+                    tma_load_2d_pair(dst + (uint32_t)(i * p.a_box_rows) * kSpan, tm, &ctl->a_full[s], c0,
                                      row0 + i * p.a_box_rows);
                   else
-                    tma_load_2d_s(dst + (uint32_t)(i * p.a_box_rows) * kSpan, &p.tmA, &ctl->a_full[s], chunk * p.ck,
+                    tma_load_2d_s(dst + (uint32_t)(i * p.a_box_rows) * kSpan, tm, &ctl->a_full[s], c0,
                                   row0 + i * p.a_box_rows);
                 }
               } else {
@@ -1173,7 +1178,13 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     set_error("conv: bad cout %d / cout_pad %d", s.cout, s.cout_pad);
     return 1;
   }
-  p.ck = pick_ck(gi.C);
+  // K = the channels of both inputs (ConvSpec::in2: 1x1 / stride 1 only, each a whole number of K chunks)
+  const int cin_total = gi.C + (s.in2 ? s.in2_C : 0);
+  if (s.in2 && (s.ksize != 1 || s.stride != 1 || s.in2_C <= 0 || s.in2_C % 16)) {
+    set_error("conv: a second input needs a 1x1 stride-1 convolution and a multiple of 16 channels");
+    return 1;
+  }
+  p.ck = s.in2 ? pick_ck(gi.C) < pick_ck(s.in2_C) ? pick_ck(gi.C) : pick_ck(s.in2_C) : pick_ck(gi.C);
   // 64 -> 64 3x3 stride 1 (layer1 conv2, the 64-channel branch): two 32-channel K chunks instead of one of 64.  The
   // activation ring then holds four half-size stages instead of two (same bytes), i.e. loads run 1.5 tiles ahead of the
   // MMAs instead of one: the issuing warp's wait for activations drops from 25 % to 17 % of its time at 64x48
@@ -1190,7 +1201,7 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   // 64-channel TMA boxes instead - the box of the last chunk reaches past the tensor's channels, which arrive as zeros -
   // and only the K steps that hold data are issued for that chunk.  STL_DBG_CK=16/32 restores the small chunks.
   p.ksteps_last = 0;
-  if (gi.C > 32 && gi.C % 64 != 0 && gi.C % 16 == 0 && !getenv("STL_DBG_CK")) {
+  if (!s.in2 && gi.C > 32 && gi.C % 64 != 0 && gi.C % 16 == 0 && !getenv("STL_DBG_CK")) {
     p.ck = 64;
     p.ksteps_last = (gi.C % 64) / 16;
   }
@@ -1200,7 +1211,8 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
   const uint32_t span = 2u * p.ck;
   p.mode = s.stride == 2 ? 1 : 0;
   p.taps = s.ksize * s.ksize;
-  p.n_chunks = (gi.C + p.ck - 1) / p.ck;
+  p.n_chunks = (cin_total + p.ck - 1) / p.ck;
+  p.n_chunks_a = s.in2 ? gi.C / p.ck : p.n_chunks;
   if (!p.ksteps_last) p.ksteps_last = p.ck / 16;
   p.n_ntiles = s.cout_pad / p.nt;
   p.in_Wp = gi.Wp();
@@ -1260,6 +1272,11 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     cuuint32_t box[2] = {(cuuint32_t)p.ck, (cuuint32_t)p.a_box_rows};
     cuuint32_t es[2] = {1, 1};
     if (encode(&p.tmA, s.in, 2, dims, strides, box, es, span)) return 1;
+    if (s.in2) {
+      cuuint64_t dims2[2] = {(cuuint64_t)s.in2_C, (cuuint64_t)gi.pixels()};
+      cuuint64_t strides2[1] = {(cuuint64_t)s.in2_C * 2};
+      if (encode(&p.tmA2, s.in2, 2, dims2, strides2, box, es, span)) return 1;
+    }
   } else {
     // structured tile: every 128-row accumulator block is a (bw x bh x bn1) box of output pixels (bw*bh*bn1 = 128, the
     // widest bw first), so a staged panel is one 4-D TMA box; a tile stacks mb blocks along the image index
@@ -1367,8 +1384,8 @@ int conv_prepare(const ConvSpec& s, ConvParams* pp, int* grid, size_t* smem_byte
     p.b_stage_bytes = p.b_tx_bytes;
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)gi.C, (cuuint64_t)s.cout_pad, (cuuint64_t)p.taps};
-    cuuint64_t strides[2] = {(cuuint64_t)gi.C * 2, (cuuint64_t)gi.C * 2 * s.cout_pad};
+    cuuint64_t dims[3] = {(cuuint64_t)cin_total, (cuuint64_t)s.cout_pad, (cuuint64_t)p.taps};
+    cuuint64_t strides[2] = {(cuuint64_t)cin_total * 2, (cuuint64_t)cin_total * 2 * s.cout_pad};
     cuuint32_t box[3] = {(cuuint32_t)p.ck, (cuuint32_t)(p.pair ? p.nt / 2 : p.nt), (cuuint32_t)p.b_taps};
     cuuint32_t es[3] = {1, 1, 1};
     if (encode(&p.tmB, s.weights, 3, dims, strides, box, es, span)) return 1;

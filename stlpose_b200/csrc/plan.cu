@@ -118,6 +118,27 @@ struct Plan::Builder {
       conv(layer(p + ".conv2", p + ".bn2", 64, 64, 3, 1), a, bb, -1, true);
       release(a);
       int res = x;
+      if (b == 0 && P.fuse_downsample) {
+        // out = relu(bn3(conv3(bb)) + bn_d(downsample(x))) as one 1x1 convolution over K = [bb | x]: the 256-channel
+        // downsample tensor is neither written nor read back (3.3 GB of HBM traffic per 1 024 images at 64x48)
+        const int ld = layer(p + ".downsample.0", p + ".downsample.1", 256, 64, 1, 1);
+        const int l3 = layer(p + ".conv3", p + ".bn3", 256, 64, 1, 1);
+        Plan::Cat cat;
+        cat.la = l3; cat.lb = ld;
+        cat.w_off = P.weight_bytes;
+        P.weight_bytes += align_up((size_t)P.layers[l3].cout_pad * (P.layers[l3].cin_pad + P.layers[ld].cin_pad) * 2, 256);
+        cat.b_off = P.weight_bytes;
+        P.weight_bytes += align_up(sizeof(float) * P.layers[l3].cout_pad, 256);
+        P.cats.push_back(cat);
+        int o = acquire(256, H4, W4);
+        conv(l3, bb, o, -1, true);
+        P.ops.back().in2 = x;
+        P.ops.back().cat = (int)P.cats.size() - 1;
+        release(bb);
+        release(x);
+        x = o;
+        continue;
+      }
       if (b == 0) {
         res = acquire(256, H4, W4);
         conv(layer(p + ".downsample.0", p + ".downsample.1", 256, 64, 1, 1), x, res, -1, false);
@@ -261,6 +282,7 @@ Plan* Plan::create(const stl_hrnet_cfg& cfg) {
   Plan* p = new Plan();
   p->cfg = cfg;
   if (const char* e = getenv("STLPOSE_FUSE_BLOCK")) p->fuse_blocks = atoi(e);
+  if (const char* e = getenv("STLPOSE_FUSE_DOWNSAMPLE")) p->fuse_downsample = atoi(e);
   if (const char* e = getenv("STLPOSE_BRANCH_STREAMS")) p->branch_streams = atoi(e);
   if (const char* e = getenv("STLPOSE_STEM_IM2COL")) p->stem_im2col = atoi(e);
   Builder b(*p);
@@ -286,8 +308,27 @@ int Plan::pack_conv(int index, const float* w, const float* gamma, const float* 
   if (L.im2col)   // OIHW [cout][cin][k][k] read as a 1x1 filter over cin*k*k "channels" (the im2col K order)
     return pack_weights(w, gamma, beta, mean, var, cbias, eps, L.cout, L.cin * L.k * L.k, 1, L.cout_pad, L.cin_pad,
                         reinterpret_cast<__nv_bfloat16*>(base + L.w_off), reinterpret_cast<float*>(base + L.b_off), st);
-  return pack_weights(w, gamma, beta, mean, var, cbias, eps, L.cout, L.cin, L.k, L.cout_pad, L.cin_pad,
-                      reinterpret_cast<__nv_bfloat16*>(base + L.w_off), reinterpret_cast<float*>(base + L.b_off), st);
+  if (pack_weights(w, gamma, beta, mean, var, cbias, eps, L.cout, L.cin, L.k, L.cout_pad, L.cin_pad,
+                   reinterpret_cast<__nv_bfloat16*>(base + L.w_off), reinterpret_cast<float*>(base + L.b_off), st))
+    return 1;
+  // member of a concatenated pair: rebuild [cout_pad][cin_a | cin_b] and the summed bias from both members' packed
+  // parameters (stream-ordered behind the packing above; the other member is (re)packed by its own call)
+  for (const Cat& c : cats) {
+    if (index != c.la && index != c.lb) continue;
+    const Layer& A = layers[c.la];
+    const Layer& B = layers[c.lb];
+    const size_t pitch = (size_t)(A.cin_pad + B.cin_pad) * 2;
+    cudaError_t e = cudaMemcpy2DAsync(base + c.w_off, pitch, base + A.w_off, (size_t)A.cin_pad * 2, (size_t)A.cin_pad * 2,
+                                      A.cout_pad, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(base + c.w_off + (size_t)A.cin_pad * 2, pitch, base + B.w_off, (size_t)B.cin_pad * 2,
+                            (size_t)B.cin_pad * 2, B.cout_pad, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { set_error("pack_conv: concatenating weights: %s", cudaGetErrorString(e)); return 1; }
+    if (add_f32(reinterpret_cast<const float*>(base + A.b_off), reinterpret_cast<const float*>(base + B.b_off),
+                reinterpret_cast<float*>(base + c.b_off), A.cout_pad, st))
+      return 1;
+  }
+  return 0;
 }
 
 int Plan::bind(int n_images, const void* arena, void* workspace, size_t ws_bytes, cudaStream_t st) {
@@ -348,6 +389,12 @@ int Plan::bind(int n_images, const void* arena, void* workspace, size_t ws_bytes
     s.stride = L.im2col ? 1 : L.stride;
     s.weights = reinterpret_cast<const __nv_bfloat16*>(wbase + L.w_off);
     s.bias = reinterpret_cast<const float*>(wbase + L.b_off);
+    if (op.cat >= 0) {
+      s.weights = reinterpret_cast<const __nv_bfloat16*>(wbase + cats[op.cat].w_off);
+      s.bias = reinterpret_cast<const float*>(wbase + cats[op.cat].b_off);
+      s.in2 = reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.in2]);
+      s.in2_C = slots[op.in2].C;
+    }
     s.residual = op.res >= 0 ? reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.res]) : nullptr;
     s.n_up = op.n_up;
     for (int u = 0; u < op.n_up; ++u) {
@@ -530,9 +577,10 @@ int Plan::op_info(int i, stl_op_info* info) const {
   const Layer& L = layers[op.layer];
   const int ih = si ? si->H : cfg.image_h, iw = si ? si->W : cfg.image_w;
   info->out_h = L.im2col ? ih : ih / L.stride; info->out_w = L.im2col ? iw : iw / L.stride;
-  info->cin = L.cin; info->cout = L.cout; info->ksize = L.k; info->stride = L.stride;
-  info->flops_per_image = 2.0 * L.cout * L.cin * L.k * L.k * info->out_h * info->out_w;
-  const double in_b = (double)ih * iw * (L.im2col ? L.cin_pad : L.cin) * (si ? 2 : 4);
+  const int cin = L.cin + (op.cat >= 0 ? layers[cats[op.cat].lb].cin : 0);   // both inputs of a concatenated pair
+  info->cin = cin; info->cout = L.cout; info->ksize = L.k; info->stride = L.stride;
+  info->flops_per_image = 2.0 * L.cout * cin * L.k * L.k * info->out_h * info->out_w;
+  const double in_b = (double)ih * iw * (L.im2col ? L.cin_pad : cin) * (si ? 2 : 4);
   const double out_b = (double)info->out_h * info->out_w * L.cout * (op.out_nchw ? 4 : 2);
   info->bytes_per_image = in_b + out_b + (op.res >= 0 ? out_b : 0);
   for (int u = 0; u < op.n_up; ++u) info->bytes_per_image += (double)slots[op.up[u]].H * slots[op.up[u]].W * L.cout * 2;

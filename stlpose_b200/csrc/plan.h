@@ -24,6 +24,8 @@ struct Plan {
     OpKind kind = OP_CONV;
     int layer = -1, in = -1, out = -1, res = -1;
     int layer2 = -1;  // OP_BLOCK: the block's second convolution
+    int in2 = -1;     // OP_CONV with cat >= 0: the second input (K = [in | in2])
+    int cat = -1;     // index into Plan::cats: this op runs two summed 1x1 convolutions as one (concatenated weights)
     int n_up = 0;
     int up[kMaxUp] = {-1, -1, -1};
     int up_shift[kMaxUp] = {0, 0, 0};
@@ -34,6 +36,10 @@ struct Plan {
     int sm_share = 0;    // ... each restricted to its share of the SMs (CTAs of its persistent kernels)
   };
   struct Group { int first = 0, count = 0; };
+  // Two 1x1 convolutions whose outputs are added before the activation (Bottleneck conv3 + downsample of layer1.0,
+  // HRnet.py:88-101) as ONE convolution over the concatenated inputs: weights [cout_pad][cin_a + cin_b] and the summed
+  // bias live in their own arena region, rebuilt by pack_conv whenever either member is packed.
+  struct Cat { int la = -1, lb = -1; size_t w_off = 0, b_off = 0; };
   struct Launch { int op, sub; };
   struct Prepared {
     ConvParams params;
@@ -47,6 +53,8 @@ struct Plan {
   std::vector<Layer> layers;
   std::vector<Slot> slots;
   std::vector<Op> ops;
+  std::vector<Cat> cats;
+  int fuse_downsample = 1;  // STLPOSE_FUSE_DOWNSAMPLE=0: downsample and conv3 of layer1.0 as two launches
   size_t weight_bytes = 0;
   int tap_reload = 0;  // debugging: force one TMA load per filter tap
   int stem_im2col = 1; // STLPOSE_STEM_IM2COL=0: 16-channel input packing + stride-2 3x3 tensor-core conv instead

@@ -71,3 +71,49 @@ KW_MERGED = [
 def test_kw_merged_conv_matches_torch(case):
     err, scale = conv_case(impl=3, **case)
     assert err <= 1e-2 * max(scale, 1.0), f"max err {err} vs ref max {scale}"
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 256, 64, 48), (3, 64, 64, 256, 16, 12), (2, 32, 64, 64, 32, 24),
+                                   (5, 128, 64, 128, 8, 6), (2, 256, 64, 256, 16, 12)],
+                         ids=lambda s: "c{1}+{2}-{3}_{4}x{5}_N{0}".format(*s))
+@pytest.mark.parametrize("max_ctas", [0, 3])
+def test_two_input_1x1_conv_equals_the_sum_of_two_convs(shape, max_ctas):
+    """stl_conv_desc.in2: one 1x1 convolution over K = [in | in2] = relu(bn_a(conv_a(in)) + bn_b(conv_b(in2))), the
+    Bottleneck tail of layer1.0 (conv3 + downsample, models/HRnet.py:88-101), against torch fp32 on the same
+    bf16-rounded operands.  max_ctas = 3: every CTA walks many tiles (ring wrap-around with alternating tensor maps)."""
+    import ctypes
+    import torch
+    import torch.nn.functional as F
+    from stlpose_b200 import _lib
+    from gpu_util import bf16_round, to_padded, from_padded, pack, rand_bn, padded_border_is_zero
+    n, ca, cb, cout, h, w = shape
+    dev = "cuda"
+    gen = torch.Generator(device=dev).manual_seed(ca + 7 * cb + h)
+    xa = bf16_round(torch.randn(n, ca, h, w, device=dev, generator=gen))
+    xb = bf16_round(torch.randn(n, cb, h, w, device=dev, generator=gen))
+    wa = torch.randn(cout, ca, 1, 1, device=dev, generator=gen) / ca ** 0.5
+    wb = torch.randn(cout, cb, 1, 1, device=dev, generator=gen) / cb ** 0.5
+    wpa, bpa, wfa, bfa, cout_pad = pack(wa, rand_bn(cout, gen, dev))
+    wpb, bpb, wfb, bfb, _ = pack(wb, rand_bn(cout, gen, dev))
+    # concatenated packed parameters, as Plan::pack_conv builds them: [cout_pad][ca | cb] bf16, summed bias
+    wcat = torch.cat([wpa.view(torch.bfloat16).view(cout_pad, ca), wpb.view(torch.bfloat16).view(cout_pad, cb)], 1).contiguous()
+    bcat = (bpa + bpb).contiguous()
+    ina, inb = to_padded(xa), to_padded(xb)
+    out = to_padded(torch.full((n, cout, h, w), 3.0e38, dtype=torch.float32, device=dev))
+    d = _lib.ConvDesc()
+    d.in_ = ina.data_ptr(); d.N, d.H, d.W, d.Cin = n, h, w, ca
+    d.in2 = inb.data_ptr(); d.Cin2 = cb
+    d.out = out.data_ptr(); d.Cout, d.Cout_pad = cout, cout_pad
+    d.ksize, d.stride = 1, 1
+    d.w_packed = wcat.data_ptr(); d.bias_packed = bcat.data_ptr()
+    d.relu = 1; d.max_ctas = max_ctas
+    _lib.check(_lib.lib().stl_conv2d(ctypes.byref(d), _lib.current_stream()))
+    torch.cuda.synchronize()
+    assert padded_border_is_zero(out, n, cout, h, w)
+    y = from_padded(out, n, cout, h, w)
+    ref = F.relu(F.conv2d(xa, bf16_round(wfa)) + F.conv2d(xb, bf16_round(wfb)) + (bfa + bfb).view(1, -1, 1, 1))
+    err, scale = (y - ref).abs().max().item(), ref.abs().max().item()
+    assert err <= 1e-2 * max(scale, 1.0), f"max err {err} vs ref max {scale}"
+    # a second input on anything but a 1x1 / stride-1 convolution is refused
+    d.ksize = 3
+    assert _lib.lib().stl_conv2d(ctypes.byref(d), _lib.current_stream()) != 0

@@ -37,6 +37,21 @@ def test_forward_w48_matches_reference_golden(golden, golden_inputs):
     assert y.shape == (1, 17, 96, 72) and err < HEAT_TOL, f"heatmap max-abs error {err}"
 
 
+def test_concatenated_downsample_matches_the_two_launch_form(golden_inputs, monkeypatch):
+    """layer1.0's conv3 + downsample as ONE 1x1 convolution over [conv2 output | block input] (plan.cu, the default) vs
+    the two launches with a bf16 round trip of the downsample branch in between (STLPOSE_FUSE_DOWNSAMPLE=0): same
+    heatmaps up to that rounding (measured 7.5e-3 max-abs; both are within HEAT_TOL of the reference), and one kernel
+    launch fewer per forward."""
+    x = torch.from_numpy(golden_inputs["x_w32"]).cuda()
+    m1 = _model(32, (256, 192))
+    y1 = m1(x)
+    monkeypatch.setenv("STLPOSE_FUSE_DOWNSAMPLE", "0")
+    m0 = _model(32, (256, 192))
+    y0 = m0(x)
+    assert (y1 - y0).abs().max().item() < 0.5 * HEAT_TOL
+    assert m0.launches_per_forward() == m1.launches_per_forward() + 1
+
+
 def test_flip_test_and_keypoints_vs_oracle():
     import stlpose_b200 as S
     B = 5
