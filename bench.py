@@ -387,7 +387,7 @@ def run_infer(args):
 
     # live per-kernel timing of the dominant kernels (tcgen05 convolutions) over one step, CUDA events on the launch stream
     ops = model.profile_ops(pipe.x, flip_pair=True)
-    tc_kinds = ("conv_tc", "block_tc")   # block_tc = two convs of a BasicBlock fused
+    tc_kinds = ("conv_tc", "block_tc", "link_tc")   # block_tc / link_tc = two convolutions fused in one kernel
     conv_ms = sum(o["ms"] for o in ops if o["kind"] in tc_kinds)
     conv_flops = sum(o["flops"] for o in ops if o["kind"] in tc_kinds)
     conv_n = sum(1 for o in ops if o["kind"] in tc_kinds)

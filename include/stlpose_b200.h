@@ -150,6 +150,18 @@ int stl_pack_conv_weights(const float* w_oihw, const float* bn_gamma, const floa
 int stl_basic_block(const void* x, void* y, const void* w1_packed, const float* bias1, const void* w2_packed,
                     const float* bias2, int N, int H, int W, int C, void* stream);
 
+/* The junction of two Bottlenecks (models/HRnet.py:88-101 of one block, :82-84 of the next; eval mode, BatchNorm
+ * folded) in one kernel:
+ *   out = relu(conv3(t) + bias3 + x)        1x1, 64 -> 256, x = the block's input (the residual)
+ *   a   = relu(conv1n(out) + bias1n)        1x1, 256 -> 64, conv1 of the NEXT Bottleneck
+ * The finished bf16 tile of `out`, staged in shared memory for its store, is also the tensor-core operand of the second
+ * product: the 256-channel tensor crosses HBM once instead of being written and read back.
+ * t, a: padded-linear bf16 [N][H+1][W+1][64]; x, out: [..][256] (distinct buffers); w3_packed [256][64],
+ * w1n_packed [64][256] bf16; bias3: 256, bias1n: 64 fp32.  `out` is bit-identical to stl_conv2d with the residual, `a`
+ * to stl_conv2d on that `out`.  max_ctas: 0 = one CTA per SM. */
+int stl_bottleneck_link(const void* t, const void* x, void* out, void* a, const void* w3_packed, const float* bias3,
+                        const void* w1n_packed, const float* bias1n, int N, int H, int W, int max_ctas, void* stream);
+
 /* Weights for the convolution that IS the stride-1 input gradient: dx = stl_conv2d(dz, W'), W'[ci][co][kh][kw] =
  * W[co][ci][k-1-kh][k-1-kw].  w: fp32 OIHW of the forward layer; result [k*k][Rows_pad][K_pad] bf16 with Rows_pad >= Cin
  * (multiple of 16) and K_pad >= Cout (the channel count of dz); bias_packed (Rows_pad floats, may be null) is zeroed. */
@@ -274,7 +286,8 @@ int stl_plan_forward_timed(stl_plan* plan, const float* x_nchw, int B, int flip_
                            float* op_ms_host);
 
 typedef struct stl_op_info {
-  int kind;                 /* 0 = stem conv (CUDA cores), 1 = tcgen05 conv, 2 = fuse-sum */
+  int kind;                 /* 0 = stem input packing, 1 = tcgen05 conv, 2 = fuse-sum, 3 = fused BasicBlock (two 3x3
+                               convs), 4 = Bottleneck junction (conv3 + the next block's conv1, two 1x1 convs) */
   int layer;                /* conv index for stl_plan_conv_info, -1 for fuse-sum */
   int cin, cout, ksize, stride, out_h, out_w;
   double flops_per_image;   /* 2*MACs */

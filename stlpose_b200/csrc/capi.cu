@@ -185,6 +185,14 @@ int stl_basic_block(const void* x, void* y, const void* w1_packed, const float* 
                             (const __nv_bfloat16*)w2_packed, bias2, N, H, W, 0, (cudaStream_t)stream);
 }
 
+int stl_bottleneck_link(const void* t, const void* x, void* out, void* a, const void* w3_packed, const float* bias3,
+                        const void* w1n_packed, const float* bias1n, int N, int H, int W, int max_ctas, void* stream) {
+  if (!have_device()) return 1;
+  typedef const __nv_bfloat16* P;
+  return bottleneck_link_launch((P)t, (P)x, (__nv_bfloat16*)out, (__nv_bfloat16*)a, (P)w3_packed, bias3, (P)w1n_packed,
+                                bias1n, N, H, W, max_ctas, (cudaStream_t)stream);
+}
+
 int stl_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, int Rows_pad, int K_pad, void* w_packed,
                                 float* bias_packed, void* stream) {
   if (!have_device()) return 1;

@@ -108,12 +108,19 @@ struct Plan::Builder {
     release(t0);
 
     // layer1: 4 Bottlenecks (HRnet.py:297, 64-102)
+    int a_next = -1;   // conv1 output of the coming block when the previous junction already computed it (OP_LINK)
+    int l1_next = -1;
     for (int b = 0; b < 4; ++b) {
       const int cin = b == 0 ? 64 : 256;
       snprintf(k1, sizeof k1, "layer1.%d", b);
       const std::string p = k1;
-      int a = acquire(64, H4, W4);
-      conv(layer(p + ".conv1", p + ".bn1", 64, cin, 1, 1), x, a, -1, true);
+      const int l1 = l1_next >= 0 ? l1_next : layer(p + ".conv1", p + ".bn1", 64, cin, 1, 1);
+      int a = a_next;
+      if (a < 0) {
+        a = acquire(64, H4, W4);
+        conv(l1, x, a, -1, true);
+      }
+      a_next = l1_next = -1;
       int bb = acquire(64, H4, W4);
       conv(layer(p + ".conv2", p + ".bn2", 64, 64, 3, 1), a, bb, -1, true);
       release(a);
@@ -145,7 +152,21 @@ struct Plan::Builder {
         release(x);
       }
       int o = acquire(256, H4, W4);
-      conv(layer(p + ".conv3", p + ".bn3", 256, 64, 1, 1), bb, o, res, true);
+      const int l3 = layer(p + ".conv3", p + ".bn3", 256, 64, 1, 1);
+      if (b >= 1 && b < 3 && P.fuse_links && bottleneck_link_supported(64, 256, 64)) {
+        // conv3 of this block and conv1 of the next in one kernel (link_tc.cu): the 256-channel output is written once
+        // and not read back by the next block's conv1
+        snprintf(k2, sizeof k2, "layer1.%d", b + 1);
+        const std::string pn = k2;
+        l1_next = layer(pn + ".conv1", pn + ".bn1", 64, 256, 1, 1);
+        a_next = acquire(64, H4, W4);
+        Plan::Op op;
+        op.kind = Plan::OP_LINK;
+        op.layer = l3; op.layer2 = l1_next; op.in = bb; op.res = res; op.out = o; op.out2 = a_next; op.relu = true;
+        P.ops.push_back(op);
+      } else {
+        conv(l3, bb, o, res, true);
+      }
       release(bb);
       release(res);
       x = o;
@@ -283,6 +304,7 @@ Plan* Plan::create(const stl_hrnet_cfg& cfg) {
   p->cfg = cfg;
   if (const char* e = getenv("STLPOSE_FUSE_BLOCK")) p->fuse_blocks = atoi(e);
   if (const char* e = getenv("STLPOSE_FUSE_DOWNSAMPLE")) p->fuse_downsample = atoi(e);
+  if (const char* e = getenv("STLPOSE_FUSE_LINK")) p->fuse_links = atoi(e);
   if (const char* e = getenv("STLPOSE_BRANCH_STREAMS")) p->branch_streams = atoi(e);
   if (const char* e = getenv("STLPOSE_STEM_IM2COL")) p->stem_im2col = atoi(e);
   Builder b(*p);
@@ -520,6 +542,21 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
           return 1;
         break;
       }
+      case OP_LINK: {
+        const Slot& so = slots[op.out];
+        const Layer& L3 = layers[op.layer];
+        const Layer& L1 = layers[op.layer2];
+        if (bottleneck_link_launch(reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.in]),
+                                   reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.res]),
+                                   reinterpret_cast<__nv_bfloat16*>(slot_ptr[op.out]),
+                                   reinterpret_cast<__nv_bfloat16*>(slot_ptr[op.out2]),
+                                   reinterpret_cast<const __nv_bfloat16*>(wbase + L3.w_off),
+                                   reinterpret_cast<const float*>(wbase + L3.b_off),
+                                   reinterpret_cast<const __nv_bfloat16*>(wbase + L1.w_off),
+                                   reinterpret_cast<const float*>(wbase + L1.b_off), n_images, so.H, so.W, 0, st))
+          return 1;
+        break;
+      }
       case OP_FUSE: {
         const Slot& so = slots[op.out];
         const __nv_bfloat16* z[kMaxUp];
@@ -564,6 +601,15 @@ int Plan::op_info(int i, stl_op_info* info) const {
     info->out_h = so->H; info->out_w = so->W; info->cout = so->C; info->cin = so->C;
     info->bytes_per_image = 2.0 * so->H * so->W * so->C * 2;
     for (int u = 0; u < op.n_up; ++u) info->bytes_per_image += (double)slots[op.up[u]].H * slots[op.up[u]].W * so->C * 2;
+    return 0;
+  }
+  if (op.kind == OP_LINK) {    // two 1x1 convs; algorithmic traffic: read t and the residual, write out and a
+    const Layer& L3 = layers[op.layer];
+    const Layer& L1 = layers[op.layer2];
+    info->out_h = so->H; info->out_w = so->W; info->cin = L3.cin; info->cout = L3.cout; info->ksize = 1; info->stride = 1;
+    info->flops_per_image = 2.0 * ((double)L3.cout * L3.cin + (double)L1.cout * L1.cin) * so->H * so->W;
+    info->bytes_per_image = (double)so->H * so->W * 2 * (L3.cin + 2.0 * L3.cout + L1.cout);
+    info->mb = 1; info->nt = 128; info->ck = 64; info->grid = 148;
     return 0;
   }
   if (op.kind == OP_BLOCK) {   // two 3x3 convs; algorithmic traffic: read x, write y

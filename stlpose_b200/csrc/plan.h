@@ -19,11 +19,13 @@ struct Plan {
     size_t w_off, b_off;
   };
   struct Slot { int C, H, W; };
-  enum OpKind { OP_STEM, OP_CONV, OP_FUSE, OP_BLOCK };   // OP_BLOCK: one BasicBlock (two convs) in one kernel
+  enum OpKind { OP_STEM, OP_CONV, OP_FUSE, OP_BLOCK, OP_LINK };   // OP_BLOCK: one BasicBlock (two convs) in one kernel;
+                                                                  // OP_LINK: conv3 of a Bottleneck + conv1 of the next
   struct Op {
     OpKind kind = OP_CONV;
     int layer = -1, in = -1, out = -1, res = -1;
-    int layer2 = -1;  // OP_BLOCK: the block's second convolution
+    int layer2 = -1;  // OP_BLOCK: the block's second convolution; OP_LINK: conv1 of the next Bottleneck
+    int out2 = -1;    // OP_LINK: that convolution's output
     int in2 = -1;     // OP_CONV with cat >= 0: the second input (K = [in | in2])
     int cat = -1;     // index into Plan::cats: this op runs two summed 1x1 convolutions as one (concatenated weights)
     int n_up = 0;
@@ -54,6 +56,7 @@ struct Plan {
   std::vector<Slot> slots;
   std::vector<Op> ops;
   std::vector<Cat> cats;
+  int fuse_links = 1;       // STLPOSE_FUSE_LINK=0: conv3 of a layer1 Bottleneck and conv1 of the next as two launches
   int fuse_downsample = 1;  // STLPOSE_FUSE_DOWNSAMPLE=0: downsample and conv3 of layer1.0 as two launches
   size_t weight_bytes = 0;
   int tap_reload = 0;  // debugging: force one TMA load per filter tap

@@ -324,7 +324,7 @@ class PoseHighResolutionNet(nn.Module):
         for i in range(n_ops):
             _lib.check(L.stl_plan_op_info(plan, i, ctypes.byref(info)))
             d = {n: getattr(info, n) for n, _ in _lib.OpInfo._fields_}
-            d["kind"] = ("stem", "conv_tc", "fuse_sum", "block_tc")[info.kind]
+            d["kind"] = ("stem", "conv_tc", "fuse_sum", "block_tc", "link_tc")[info.kind]
             d["key"] = ""
             if info.layer >= 0:
                 _lib.check(L.stl_plan_conv_info(plan, info.layer, ctypes.byref(cinfo)))

@@ -55,3 +55,51 @@ def test_fused_basic_block_equals_two_convs(n, h, w):
     ref = F.relu(F.conv2d(t1, bf16_round(wf2), bf2, 1, 1) + x)
     got = from_padded(yf, n, c, h, w)
     assert (got - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("n,h,w,max_ctas", [(1, 64, 48, 0), (3, 64, 48, 0), (70, 64, 48, 0), (9, 64, 48, 3), (5, 16, 12, 2),
+                                            (2, 8, 6, 0), (40, 32, 24, 1)])
+def test_bottleneck_link_equals_two_convs(n, h, w, max_ctas):
+    """stl_bottleneck_link (conv3 + residual + ReLU of a Bottleneck and conv1 + ReLU of the next one in one kernel,
+    models/HRnet.py:88-101 / :82-84) vs the same two 1x1 convolutions as stl_conv2d launches: bit-identical `out` and `a`,
+    zero cells kept, and vs torch fp32 on the folded weights.  max_ctas > 0: every CTA walks many tiles (all rings wrap)."""
+    L = _lib.lib()
+    ct, co, ca = 64, 256, 64
+    g = torch.Generator(device=DEV).manual_seed(n * 10 + h)
+    t = bf16_round(torch.randn(n, ct, h, w, device=DEV, generator=g))
+    x = bf16_round(torch.randn(n, co, h, w, device=DEV, generator=g))
+    w3 = torch.randn(co, ct, 1, 1, device=DEV, generator=g) / ct ** 0.5
+    w1 = torch.randn(ca, co, 1, 1, device=DEV, generator=g) / co ** 0.5
+    wp3, bp3, wf3, bf3, _ = pack(w3, _bn(co, g))
+    wp1, bp1, wf1, bf1, _ = pack(w1, _bn(ca, g))
+    tin, xin = to_padded(t), to_padded(x)
+
+    def conv1x1(src, cin, dst, cout, wp, bp, residual=None):
+        d = _lib.ConvDesc()
+        d.in_ = src.data_ptr(); d.N, d.H, d.W, d.Cin = n, h, w, cin
+        d.out = dst.data_ptr(); d.Cout, d.Cout_pad = cout, cout
+        d.ksize, d.stride = 1, 1
+        d.w_packed = wp.data_ptr(); d.bias_packed = bp.data_ptr()
+        d.residual = residual.data_ptr() if residual is not None else None
+        d.relu = 1
+        _lib.check(L.stl_conv2d(ctypes.byref(d), _lib.current_stream()))
+
+    out2 = torch.zeros_like(xin)
+    a2 = torch.zeros_like(tin)
+    conv1x1(tin, ct, out2, co, wp3, bp3, residual=xin)
+    conv1x1(out2, co, a2, ca, wp1, bp1)
+    out1 = torch.full_like(xin, 0x7f)                      # poison: the fused kernel must write every cell
+    a1 = torch.full_like(tin, 0x7f)
+    _lib.check(L.stl_bottleneck_link(_lib.ptr(tin), _lib.ptr(xin), _lib.ptr(out1), _lib.ptr(a1), _lib.ptr(wp3), _lib.ptr(bp3),
+                                     _lib.ptr(wp1), _lib.ptr(bp1), n, h, w, max_ctas, _lib.current_stream()))
+    torch.cuda.synchronize()
+    assert padded_border_is_zero(out1, n, co, h, w) and padded_border_is_zero(a1, n, ca, h, w)
+    assert torch.equal(out1, out2), (out1 != out2).float().mean().item()
+    assert torch.equal(a1, a2), (a1 != a2).float().mean().item()
+    o_ref = F.relu(F.conv2d(t, bf16_round(wf3), bf3) + x)
+    a_ref = F.relu(F.conv2d(bf16_round(o_ref), bf16_round(wf1), bf1))
+    assert (from_padded(out1, n, co, h, w) - o_ref).abs().max().item() < 1e-2 * max(1.0, o_ref.abs().max().item())
+    assert (from_padded(a1, n, ca, h, w) - a_ref).abs().max().item() < 2e-2 * max(1.0, a_ref.abs().max().item())
+    # the residual must not alias the output
+    assert L.stl_bottleneck_link(_lib.ptr(tin), _lib.ptr(out1), _lib.ptr(out1), _lib.ptr(a1), _lib.ptr(wp3), _lib.ptr(bp3),
+                                 _lib.ptr(wp1), _lib.ptr(bp1), n, h, w, 0, _lib.current_stream()) != 0

@@ -50,6 +50,14 @@ def test_concatenated_downsample_matches_the_two_launch_form(golden_inputs, monk
     y0 = m0(x)
     assert (y1 - y0).abs().max().item() < 0.5 * HEAT_TOL
     assert m0.launches_per_forward() == m1.launches_per_forward() + 1
+    # conv3 + the next block's conv1 of layer1.1 / layer1.2 as one kernel each (link_tc.cu) is bit-identical to the two
+    # launches (STLPOSE_FUSE_LINK=0)
+    monkeypatch.delenv("STLPOSE_FUSE_DOWNSAMPLE")
+    monkeypatch.setenv("STLPOSE_FUSE_LINK", "0")
+    m2 = _model(32, (256, 192))
+    y2 = m2(x)
+    assert torch.equal(y1, y2)
+    assert m2.launches_per_forward() == m1.launches_per_forward() + 2
 
 
 def test_flip_test_and_keypoints_vs_oracle():
