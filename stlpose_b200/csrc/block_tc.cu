@@ -94,6 +94,10 @@ __global__ void __launch_bounds__(kBlkThreads, 1) basic_block_kernel(const __gri
   const long long tile0 = blockIdx.x, tstride = gridDim.x;
   const int halo = p.halo;
 
+  // programmatic dependent launch (conv_tc.cu): the next kernel may start its prologue as our CTAs retire; everything here
+  // that touches activations waits for the previous kernel below (producer: x tiles; DMA warp: residual loads AND stores -
+  // the output buffer may be one the previous kernel is still reading)
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     mbar_init(&ctl->w_full, 1);
     for (int i = 0; i < 3; ++i) { mbar_init(&ctl->x_full[i], 1); mbar_init(&ctl->x_empty[i], 1); mbar_init(&ctl->mid_full[i], 8); }
@@ -122,6 +126,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) basic_block_kernel(const __gri
         tma_load_3d_s(w_base + t * kTapBytes, &p.tmW1, &ctl->w_full, 0, 0, t);
         tma_load_3d_s(w_base + (9 + t) * kTapBytes, &p.tmW2, &ctl->w_full, 0, 0, t);
       }
+      pdl_wait();
       uint32_t i = 0;
       for (long long tile = tile0; tile < p.total_tiles; tile += tstride, ++i) {
         const uint32_t s = i % 3, ph = (i / 3) & 1;
@@ -292,6 +297,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) basic_block_kernel(const __gri
   } else if (warp == 18) {
     // ------------------------------------------------------------------ DMA warp: residual panels in, finished panels out
     if (lane == 0) {
+      pdl_wait();
       auto load_res = [&](long long tile, uint32_t s) {
         mbar_expect_tx(&ctl->res_full[s], 3u * 128u * kPitch);
         for (int m = 0; m < 3; ++m)
@@ -355,7 +361,8 @@ bool basic_block_supported(int H, int W, int C) { return C == kC && W + 2 <= kMa
 
 // x, y: padded-linear bf16 [N][H+1][W+1][32]; w1, w2: packed [9][32][32] bf16; b1, b2: 32 fp32 (folded BatchNorm).
 int basic_block_launch(const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bfloat16* w1, const float* b1,
-                       const __nv_bfloat16* w2, const float* b2, int N, int H, int W, int max_ctas, cudaStream_t stream) {
+                       const __nv_bfloat16* w2, const float* b2, int N, int H, int W, int max_ctas, cudaStream_t stream,
+                       int pdl) {
   if (!basic_block_supported(H, W, kC)) { set_error("basic_block: unsupported geometry %dx%d", H, W); return 1; }
   BlockParams p{};
   p.Wp = W + 1; p.Hp = H + 1; p.H = H; p.W = W; p.halo = W + 2;
@@ -394,7 +401,22 @@ int basic_block_launch(const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bflo
   const int sms = device_sm_count();
   long long grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  basic_block_kernel<<<(unsigned)grid, kBlkThreads, smem, stream>>>(p);
+  if (pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kBlkThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, basic_block_kernel, p);
+    if (e != cudaSuccess) { set_error("basic_block (attributed) launch: %s", cudaGetErrorString(e)); return 1; }
+  } else {
+    basic_block_kernel<<<(unsigned)grid, kBlkThreads, smem, stream>>>(p);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("basic_block launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;

@@ -158,14 +158,15 @@ int conv_launch(const ConvSpec& spec, cudaStream_t stream);
 // Fused BasicBlock (block_tc.cu): y = relu(conv2(relu(conv1(x) + b1)) + b2 + x), both 3x3 / stride 1 / 32 -> 32 channels.
 bool basic_block_supported(int H, int W, int C);
 int basic_block_launch(const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bfloat16* w1, const float* b1,
-                       const __nv_bfloat16* w2, const float* b2, int N, int H, int W, int max_ctas, cudaStream_t stream);
+                       const __nv_bfloat16* w2, const float* b2, int N, int H, int W, int max_ctas, cudaStream_t stream,
+                       int pdl = 0);   // pdl: programmatic dependent launch (parameters must not come from the previous kernel)
 
 // Junction of two layer1 Bottlenecks (link_tc.cu): out = relu(conv3(t) + b3 + x), a = relu(conv1'(out) + b1'), both 1x1
 // (64 -> 256 -> 64 channels); `out` crosses HBM once instead of being written and read back.
 bool bottleneck_link_supported(int ct, int co, int ca);
 int bottleneck_link_launch(const __nv_bfloat16* t, const __nv_bfloat16* x, __nv_bfloat16* out, __nv_bfloat16* a,
                            const __nv_bfloat16* w3, const float* b3, const __nv_bfloat16* w1, const float* b1, int N, int H,
-                           int W, int max_ctas, cudaStream_t stream);
+                           int W, int max_ctas, cudaStream_t stream, int pdl = 0);
 
 // Reference CUDA-core direct convolution with the same fused epilogue (validation only; slow).
 int conv_launch_naive(const ConvSpec& spec, cudaStream_t stream);

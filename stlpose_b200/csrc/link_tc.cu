@@ -95,6 +95,9 @@ __global__ void __launch_bounds__(kLinkThreads, 1) bottleneck_link_kernel(const 
   const uint32_t n_my = tile0 < p.total_tiles ? (uint32_t)((p.total_tiles - tile0 + tstride - 1) / tstride) : 0u;
   const uint32_t n_units = 2u * n_my;
 
+  // programmatic dependent launch (conv_tc.cu): the producer and the DMA warp - the only ones that touch activations -
+  // wait for the previous kernel before their first load / store
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     mbar_init(&ctl->w_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -123,6 +126,7 @@ __global__ void __launch_bounds__(kLinkThreads, 1) bottleneck_link_kernel(const 
       mbar_expect_tx(&ctl->w_full, kW3Bytes + kW1Bytes);
       tma_load_2d_s(w3_base, &p.tmW3, &ctl->w_full, 0, 0);
       for (int c = 0; c < 4; ++c) tma_load_2d_s(w1_base + (uint32_t)(c * kCa * kRowBytes), &p.tmW1, &ctl->w_full, c * 64, 0);
+      pdl_wait();
       for (uint32_t i = 0; i < n_my; ++i) {
         const uint32_t s = i & 1, ph = (i >> 1) & 1;
         mbar_wait(&ctl->t_empty[s], ph ^ 1u);
@@ -262,6 +266,7 @@ __global__ void __launch_bounds__(kLinkThreads, 1) bottleneck_link_kernel(const 
   } else if (warp == 18) {
     // ------------------------------------------------------------------ DMA warp: residual panels in, `out` panels and `a` tiles out
     if (lane == 0 && n_units > 0) {
+      pdl_wait();
       auto row_of = [&](uint32_t u) { return (int)((tile0 + (long long)(u >> 1) * tstride) * kRows); };
       auto load_res = [&](uint32_t u) {
         const uint32_t sb = u % 3;
@@ -345,7 +350,7 @@ bool bottleneck_link_supported(int ct, int co, int ca) { return ct == kCt && co 
 // w1: packed [64][256] bf16; b3: 256 fp32, b1: 64 fp32 (folded BatchNorm).  out must not alias x.
 int bottleneck_link_launch(const __nv_bfloat16* t, const __nv_bfloat16* x, __nv_bfloat16* out, __nv_bfloat16* a,
                            const __nv_bfloat16* w3, const float* b3, const __nv_bfloat16* w1, const float* b1, int N, int H,
-                           int W, int max_ctas, cudaStream_t stream) {
+                           int W, int max_ctas, cudaStream_t stream, int pdl) {
   if (N <= 0 || H <= 0 || W <= 0) { set_error("bottleneck_link: bad geometry"); return 1; }
   if (!t || !x || !out || !a || !w3 || !b3 || !w1 || !b1) { set_error("bottleneck_link: null pointer"); return 1; }
   if (out == x) { set_error("bottleneck_link: out must not alias the residual"); return 1; }
@@ -373,8 +378,24 @@ int bottleneck_link_launch(const __nv_bfloat16* t, const __nv_bfloat16* x, __nv_
   const int sms = device_sm_count();
   long long grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  bottleneck_link_kernel<<<(unsigned)grid, kLinkThreads, smem, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if (pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kLinkThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, bottleneck_link_kernel, p);
+    if (e != cudaSuccess) { set_error("bottleneck_link (attributed) launch: %s", cudaGetErrorString(e)); return 1; }
+  } else {
+    bottleneck_link_kernel<<<(unsigned)grid, kLinkThreads, smem, stream>>>(p);
+  }
+  e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("bottleneck_link launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;
 }

@@ -394,7 +394,7 @@ int Plan::bind(int n_images, const void* arena, void* workspace, size_t ws_bytes
   }
   const uint8_t* wbase = reinterpret_cast<const uint8_t*>(arena);
   // programmatic dependent launch between consecutive layers (the weight arena is static during a forward)
-  const int use_pdl = getenv("STLPOSE_PDL") ? atoi(getenv("STLPOSE_PDL")) : 1;
+  use_pdl = getenv("STLPOSE_PDL") ? atoi(getenv("STLPOSE_PDL")) : 1;
   prepared.assign(ops.size(), std::vector<Prepared>());
   for (size_t i = 0; i < ops.size(); ++i) {
     const Op& op = ops[i];
@@ -489,6 +489,8 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
       cudaEventCreateWithFlags(&ev_join[s], cudaEventDisableTiming);
     }
   }
+  // (STLPOSE_PDL_FUSED=0: programmatic dependent launch only between the plain convolutions, not for the fused kernels)
+  const bool pdl_fused = use_pdl && !op_ms_host && !(getenv("STLPOSE_PDL_FUSED") && atoi(getenv("STLPOSE_PDL_FUSED")) == 0);
   int cur_par = -1;
   unsigned used = 0;   // side streams used by the current module
   auto join = [&]() {
@@ -538,7 +540,7 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
                                reinterpret_cast<const float*>(wbase + L1.b_off),
                                reinterpret_cast<const __nv_bfloat16*>(wbase + L2.w_off),
                                reinterpret_cast<const float*>(wbase + L2.b_off), n_images, so.H, so.W,
-                               limited ? op.sm_share : 0, st))
+                               limited ? op.sm_share : 0, st, pdl_fused && !limited))
           return 1;
         break;
       }
@@ -553,7 +555,8 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
                                    reinterpret_cast<const __nv_bfloat16*>(wbase + L3.w_off),
                                    reinterpret_cast<const float*>(wbase + L3.b_off),
                                    reinterpret_cast<const __nv_bfloat16*>(wbase + L1.w_off),
-                                   reinterpret_cast<const float*>(wbase + L1.b_off), n_images, so.H, so.W, 0, st))
+                                   reinterpret_cast<const float*>(wbase + L1.b_off), n_images, so.H, so.W, 0, st,
+                                   pdl_fused))
           return 1;
         break;
       }
