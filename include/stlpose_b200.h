@@ -210,6 +210,10 @@ typedef struct stl_conv_desc {
                               before the activation (Bottleneck conv3 + downsample, models/HRnet.py:88-101) run as one
                               launch; their sum stays in the fp32 accumulator.  impl 0 only. */
   int Cin2;
+  int pdl;                 /* 1: launch with programmatic stream serialization - the kernel's prologue (barriers, tensor
+                              memory, resident weights) overlaps the tail of the previous kernel of the stream and
+                              everything that touches activations waits for that kernel to complete.  w_packed and
+                              bias_packed must not be written by the immediately preceding kernel. */
 } stl_conv_desc;
 
 int stl_conv2d(const stl_conv_desc* desc, void* stream);

@@ -29,7 +29,7 @@ class ConvDesc(ctypes.Structure):
         ("n_up", ctypes.c_int), ("up_src", vp * STL_MAX_UP), ("up_shift", ctypes.c_int * STL_MAX_UP),
         ("relu", ctypes.c_int), ("out_nchw", ctypes.c_int), ("impl", ctypes.c_int),
         ("force_mb", ctypes.c_int), ("max_ctas", ctypes.c_int), ("dbg_counters", vp),
-        ("in2", vp), ("Cin2", ctypes.c_int),
+        ("in2", vp), ("Cin2", ctypes.c_int), ("pdl", ctypes.c_int),
     ]
 
 

@@ -272,6 +272,7 @@ static int conv2d_impl(const stl_conv_desc* d, float* stats, int* stats_rows, vo
   s.force_mb = d->force_mb;
   s.max_ctas = d->max_ctas;
   s.dbg_counters = d->dbg_counters;
+  s.pdl = d->pdl ? 1 : 0;
   if (d->in2) {
     if (d->impl != 0 || d->Cin2 <= 0) { set_error("stl_conv2d: a second input needs impl 0 and Cin2 > 0"); return 1; }
     s.in2 = reinterpret_cast<const __nv_bfloat16*>(d->in2);

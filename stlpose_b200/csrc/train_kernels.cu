@@ -11,6 +11,7 @@
 #include <mutex>
 
 #include "conv.h"
+#include "ptx.cuh"
 #include "train_kernels.h"
 
 namespace stl {
@@ -251,6 +252,10 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
                                                              int relu_mask, float* __restrict__ sums,
                                                              float* __restrict__ partial, unsigned* __restrict__ counter,
                                                              const BnFinalize fin) {
+  // programmatic dependent launch (no-ops without the launch attribute): the next kernel of the stream may be scheduled
+  // as soon as all our blocks have started; we touch memory only once the previous kernel has completed
+  pdl_launch_dependents();
+  pdl_wait();
   channel_reduce_body<MODE>(a, y, z, mean, rstd, gamma, beta, pixels, C, relu_mask, sums, partial, counter, fin);
 }
 
@@ -365,6 +370,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const __nv_bfloat16* __restrict__ residual, int relu,
                                                        __nv_bfloat16* __restrict__ y, int N, int H, int W, int C, const PixIdx px) {
+  pdl_launch_dependents();
+  pdl_wait();
   bn_apply_body(z, mean, rstd, gamma, beta, residual, relu, y, N, H, W, C, px);
 }
 
@@ -380,6 +387,7 @@ __global__ void __launch_bounds__(256) bn_forward_coop_kernel(const __nv_bfloat1
                                                               float* __restrict__ partial, unsigned* __restrict__ counter,
                                                               unsigned* __restrict__ sync, const BnFinalize fin,
                                                               const PixIdx px) {
+  pdl_launch_dependents();   // (a following convolution launched with the attribute may start its prologue)
   const bool last = channel_reduce_body<0>(z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pixels, C, 0, sums,
                                            partial, counter, fin);
   grid_handover(sync, last);
@@ -452,6 +460,8 @@ __global__ void __launch_bounds__(256) bn_backward_kernel(const __nv_bfloat16* _
                                                           __nv_bfloat16* __restrict__ dz,
                                                           __nv_bfloat16* __restrict__ dres, int N, int H, int W,
                                                           int C, const PixIdx px) {
+  pdl_launch_dependents();
+  pdl_wait();
   bn_backward_body(dy, y, z, mean, rstd, gamma, beta, sums, count, relu_mask, dz, dres, N, H, W, C, px);
 }
 
@@ -470,6 +480,7 @@ __global__ void __launch_bounds__(256) bn_backward_coop_kernel(const __nv_bfloat
                                                                float* __restrict__ partial,
                                                                unsigned* __restrict__ counter,
                                                                unsigned* __restrict__ sync, const PixIdx px) {
+  pdl_launch_dependents();
   const bool last = channel_reduce_body<1>(dy, y, z, mean, rstd, gamma, beta, pixels, C, relu_mask, sums, partial, counter,
                                            BnFinalize{});
   grid_handover(sync, last);
@@ -775,6 +786,35 @@ int reduce_grid(long long pixels, int C) {
 
 }  // namespace
 
+namespace {
+// STLPOSE_TRAIN_PDL=1: the BatchNorm kernels of the separate-launch path carry the programmatic stream serialization
+// attribute (they wait with griddepcontrol.wait before touching memory), so that their launch latency hides behind the
+// tail of the preceding kernel, inside captured graphs too.  Measured on B200 together with the same attribute on the
+// training convolutions: no gain (17.6-17.8 vs 17.3-17.6 ms per step at batch 32, 43.4 vs 43.1 at 128) - off by default.
+bool train_pdl() {
+  static const bool on = getenv("STLPOSE_TRAIN_PDL") && atoi(getenv("STLPOSE_TRAIN_PDL")) == 1;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+void launch_bn(void (*kern)(KArgs...), int grid, cudaStream_t st, Args&&... args) {
+  if (!train_pdl()) {
+    kern<<<grid, 256, 0, st>>>(args...);
+    return;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);   // (errors surface in check())
+}
+}  // namespace
+
 size_t bn_workspace_floats(int C) { return (size_t)2 * C * (1 + kReduceBlocks) + 32; }
 
 int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* beta, const __nv_bfloat16* residual,
@@ -787,15 +827,16 @@ int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* be
   unsigned* counter = ticket ? ticket : reinterpret_cast<unsigned*>(sums + (size_t)2 * C * (1 + kReduceBlocks));
   if (!ticket) cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   BnFinalize fin{(float)((long long)N * H * W), eps, momentum, mean, rstd, run_mean, run_var};
-  channel_reduce_kernel<0><<<reduce_grid(pixels, C), 256, 0, st>>>(
-      z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pixels, C, 0, sums, sums + 2 * C, counter, fin);
+  launch_bn(channel_reduce_kernel<0>, reduce_grid(pixels, C), st, z, (const __nv_bfloat16*)nullptr,
+            (const __nv_bfloat16*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr,
+            (const float*)nullptr, pixels, C, 0, sums, sums + 2 * C, counter, fin);
   if (check("bn stats")) return 1;
   PixIdx px;
   px.init(C, H, W);
   if (pixels * (C / 8) >= (1ll << 31)) { set_error("bn_train_forward: tensor too large for 32-bit item indexing"); return 1; }
   if (256 % (C / 8) && (C / 8) % 3) { set_error("bn_train_forward: C=%d unsupported", C); return 1; }
-  bn_apply_kernel<<<grid_mult(pixels * (C / 8), C / 8), 256, 0, st>>>(z, mean, rstd, gamma, beta, residual, relu, y, N, H,
-                                                                  W, C, px);
+  launch_bn(bn_apply_kernel, grid_mult(pixels * (C / 8), C / 8), st, z, (const float*)mean, (const float*)rstd, gamma, beta,
+            residual, relu, y, N, H, W, C, px);
   return check("bn apply");
 }
 
@@ -921,16 +962,15 @@ int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __n
   unsigned* counter = ticket ? ticket : reinterpret_cast<unsigned*>(partial + (size_t)2 * C * kReduceBlocks);
   if (!ticket) cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   if (relu == 2 && (!beta || dres)) { set_error("bn_train_backward: the z-recomputed mask needs beta and no residual"); return 1; }
-  channel_reduce_kernel<1><<<reduce_grid(pixels, C), 256, 0, st>>>(
-      dy, y, z, mean, rstd, gamma, beta, pixels, C, relu, sums, partial, counter, BnFinalize{});
+  launch_bn(channel_reduce_kernel<1>, reduce_grid(pixels, C), st, dy, y, z, mean, rstd, gamma, beta, pixels, C, relu, sums,
+            partial, counter, BnFinalize{});
   if (check("bn backward reduce")) return 1;
   PixIdx px;
   px.init(C, H, W);
   if (pixels * (C / 8) >= (1ll << 31)) { set_error("bn_train_backward: tensor too large for 32-bit item indexing"); return 1; }
   if (256 % (C / 8) && (C / 8) % 3) { set_error("bn_train_backward: C=%d unsupported", C); return 1; }
-  bn_backward_kernel<<<grid_mult(pixels * (C / 8), C / 8), 256, 0, st>>>(dy, y, z, mean, rstd, gamma, beta, sums,
-                                                                     (float)((long long)N * H * W), relu, dz, dres, N,
-                                                                     H, W, C, px);
+  launch_bn(bn_backward_kernel, grid_mult(pixels * (C / 8), C / 8), st, dy, y, z, mean, rstd, gamma, beta,
+            (const float*)sums, (float)((long long)N * H * W), relu, dz, dres, N, H, W, C, px);
   return check("bn backward");
 }
 

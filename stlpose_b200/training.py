@@ -32,13 +32,15 @@ def _padded_zeros(n, h, w, c, device):
 
 
 _ZERO_BIAS = {}
+_CONV_CALLS = 0        # number of _conv_raw calls so far (see _zero_bias)
 
 
 def _zero_bias(n, device):
     """Shared all-zero fp32 bias (BatchNorm follows every conv of the training graph; only the head has a bias)."""
     key = (device, n)
     if key not in _ZERO_BIAS:
-        _ZERO_BIAS[key] = torch.zeros(n, dtype=torch.float32, device=device)
+        t = _ZERO_BIAS[key] = torch.zeros(n, dtype=torch.float32, device=device)
+        t._stl_fresh_call = _CONV_CALLS     # its fill kernel was just enqueued: the next convolution must not pre-load it
     return _ZERO_BIAS[key]
 
 
@@ -121,6 +123,7 @@ def _pack_weights(w, cin_pad, own_bias=False):
     scratch = bp if own_bias else torch.empty(cout_pad, dtype=torch.float32, device=w.device)
     _lib.check(L.stl_pack_conv_weights(_lib.ptr(w32), None, None, None, None, None, 0.0, cout, cin, k, cout_pad,
                                        cin_pad, _lib.ptr(wp), _lib.ptr(scratch), _stream()))
+    wp._stl_fresh = True      # written by the kernel just enqueued: the consuming convolution must not pre-load it (no PDL)
     return wp, (bp if own_bias else _zero_bias(cout_pad, w.device)), cout_pad
 
 
@@ -135,6 +138,7 @@ def _pack_weights_dgrad(w, k_pad):
     wp = torch.empty(k * k * rows_pad * k_pad * 2, dtype=torch.uint8, device=w.device)
     w32 = w.detach().float().contiguous()
     _lib.check(L.stl_pack_conv_weights_dgrad(_lib.ptr(w32), cout, cin, k, rows_pad, k_pad, _lib.ptr(wp), None, _stream()))
+    wp._stl_fresh = True
     return wp, _zero_bias(rows_pad, w.device), rows_pad
 
 
@@ -150,6 +154,10 @@ MASK_FROM_Z = os.environ.get("STLPOSE_TRAIN_MASK_FROM_Z", "1") != "0"
 # spins for its last blocks next to in-flight NCCL kernels is not something to rely on.  "1" / "0" force it on / off.
 COOP_BN = os.environ.get("STLPOSE_TRAIN_COOP_BN", "auto")
 _COOP_BN_MAX_BYTES = 16 << 20
+# programmatic dependent launch for the convolutions of the training path (stl_conv_desc.pdl): their packed weights are
+# written once at the start of a step, never by the kernel in front of them.  (The BatchNorm kernels read the same switch
+# in the library.)  Measured on B200: no gain (17.6-17.8 vs 17.3-17.6 ms per step at batch 32) - off by default.
+TRAIN_PDL = os.environ.get("STLPOSE_TRAIN_PDL", "0") == "1"
 
 
 def _use_coop_bn(z):
@@ -184,6 +192,10 @@ def _conv_raw(x, wp, bp, cout, cout_pad, k, stride, out=None, out_nchw=False, bi
     d.ksize, d.stride = k, stride
     d.w_packed = wp.data_ptr(); d.bias_packed = (bias if bias is not None else bp).data_ptr()
     d.relu = 0; d.out_nchw = int(out_nchw)
+    global _CONV_CALLS
+    d.pdl = int(TRAIN_PDL and not getattr(wp, "_stl_fresh", False) and bias is None and
+                getattr(bp, "_stl_fresh_call", -1) != _CONV_CALLS)
+    _CONV_CALLS += 1
     if stats is not None:
         rows = ctypes.c_int(0)
         _lib.check(L.stl_conv2d_stats(ctypes.byref(d), _lib.ptr(stats), ctypes.byref(rows), _stream()))
