@@ -161,6 +161,12 @@ int stl_basic_block(const void* x, void* y, const void* w1_packed, const float* 
  * to stl_conv2d on that `out`.  max_ctas: 0 = one CTA per SM. */
 int stl_bottleneck_link(const void* t, const void* x, void* out, void* a, const void* w3_packed, const float* bias3,
                         const void* w1n_packed, const float* bias1n, int N, int H, int W, int max_ctas, void* stream);
+/* The junction after the FIRST Bottleneck (layer1.0 -> layer1.1), whose shortcut is a convolution: no residual, GEMM1 runs
+ * over two inputs instead,  out = relu([W3 | Wd] . [t | t2] + bias3)  with t2 = the block's 64-channel input,
+ * w3cat_packed [256][128] and bias3 = the summed folded biases (see stl_conv_desc.in2), then a as above.
+ * Bit-identical to the two-input stl_conv2d followed by the 256 -> 64 stl_conv2d. */
+int stl_bottleneck_link2(const void* t, const void* t2, void* out, void* a, const void* w3cat_packed, const float* bias3,
+                         const void* w1n_packed, const float* bias1n, int N, int H, int W, int max_ctas, void* stream);
 
 /* Weights for the convolution that IS the stride-1 input gradient: dx = stl_conv2d(dz, W'), W'[ci][co][kh][kw] =
  * W[co][ci][k-1-kh][k-1-kw].  w: fp32 OIHW of the forward layer; result [k*k][Rows_pad][K_pad] bf16 with Rows_pad >= Cin

@@ -79,6 +79,7 @@ PROTOTYPES = {
     "stl_pack_conv_weights": (ctypes.c_int, [vp] * 6 + [ctypes.c_float] + [ctypes.c_int] * 5 + [vp, vp, vp]),
     "stl_basic_block": (ctypes.c_int, [vp] * 6 + [ctypes.c_int] * 4 + [vp]),
     "stl_bottleneck_link": (ctypes.c_int, [vp] * 8 + [ctypes.c_int] * 4 + [vp]),
+    "stl_bottleneck_link2": (ctypes.c_int, [vp] * 8 + [ctypes.c_int] * 4 + [vp]),
     "stl_pack_conv_weights_dgrad": (ctypes.c_int, [vp] + [ctypes.c_int] * 5 + [vp, vp, vp]),
     "stl_conv2d": (ctypes.c_int, [ctypes.POINTER(ConvDesc), vp]),
     "stl_conv2d_stats_floats": (ctypes.c_size_t, [ctypes.c_int]),

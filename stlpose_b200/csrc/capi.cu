@@ -189,8 +189,16 @@ int stl_bottleneck_link(const void* t, const void* x, void* out, void* a, const 
                         const void* w1n_packed, const float* bias1n, int N, int H, int W, int max_ctas, void* stream) {
   if (!have_device()) return 1;
   typedef const __nv_bfloat16* P;
-  return bottleneck_link_launch((P)t, (P)x, (__nv_bfloat16*)out, (__nv_bfloat16*)a, (P)w3_packed, bias3, (P)w1n_packed,
-                                bias1n, N, H, W, max_ctas, (cudaStream_t)stream);
+  return bottleneck_link_launch((P)t, nullptr, (P)x, (__nv_bfloat16*)out, (__nv_bfloat16*)a, (P)w3_packed, bias3,
+                                (P)w1n_packed, bias1n, N, H, W, max_ctas, (cudaStream_t)stream);
+}
+
+int stl_bottleneck_link2(const void* t, const void* t2, void* out, void* a, const void* w3cat_packed, const float* bias3,
+                         const void* w1n_packed, const float* bias1n, int N, int H, int W, int max_ctas, void* stream) {
+  if (!have_device()) return 1;
+  typedef const __nv_bfloat16* P;
+  return bottleneck_link_launch((P)t, (P)t2, nullptr, (__nv_bfloat16*)out, (__nv_bfloat16*)a, (P)w3cat_packed, bias3,
+                                (P)w1n_packed, bias1n, N, H, W, max_ctas, (cudaStream_t)stream);
 }
 
 int stl_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, int Rows_pad, int K_pad, void* w_packed,

@@ -162,11 +162,12 @@ int basic_block_launch(const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bflo
                        int pdl = 0);   // pdl: programmatic dependent launch (parameters must not come from the previous kernel)
 
 // Junction of two layer1 Bottlenecks (link_tc.cu): out = relu(conv3(t) + b3 + x), a = relu(conv1'(out) + b1'), both 1x1
-// (64 -> 256 -> 64 channels); `out` crosses HBM once instead of being written and read back.
+// (64 -> 256 -> 64 channels); `out` crosses HBM once instead of being written and read back.  With a second input t2
+// instead of the residual x: out = relu([W3 | Wd] . [t | t2] + b3), the conv3 + downsample pair of layer1.0.
 bool bottleneck_link_supported(int ct, int co, int ca);
-int bottleneck_link_launch(const __nv_bfloat16* t, const __nv_bfloat16* x, __nv_bfloat16* out, __nv_bfloat16* a,
-                           const __nv_bfloat16* w3, const float* b3, const __nv_bfloat16* w1, const float* b1, int N, int H,
-                           int W, int max_ctas, cudaStream_t stream, int pdl = 0);
+int bottleneck_link_launch(const __nv_bfloat16* t, const __nv_bfloat16* t2, const __nv_bfloat16* x, __nv_bfloat16* out,
+                           __nv_bfloat16* a, const __nv_bfloat16* w3, const float* b3, const __nv_bfloat16* w1,
+                           const float* b1, int N, int H, int W, int max_ctas, cudaStream_t stream, int pdl = 0);
 
 // Reference CUDA-core direct convolution with the same fused epilogue (validation only; slow).
 int conv_launch_naive(const ConvSpec& spec, cudaStream_t stream);

@@ -14,6 +14,10 @@
 // after the second unit: epilogue 2 (+ b1', ReLU) -> `a` tile -> TMA store.  Three 32 KB staging buffers: the residual of
 // unit u+2 is in flight while unit u is converted and unit u-1 drains.
 //
+// Variant KC = 2 (layer1.0 -> layer1.1): GEMM1 runs over TWO input tensors, K = [t | x64] with the concatenated weights
+// [W3 | Wd] - conv3 + downsample of the first Bottleneck (conv.h, ConvSpec::in2) - and there is no residual; two staging
+// buffers and one t stage keep it inside 208 KB of shared memory.
+//
 // Warps: 0 TMA producer (weights once, then t tiles, 2 stages) | 1 MMA issuer of GEMM1 | 19 MMA issuer of GEMM2 |
 // 2-9 epilogue 1 | 10-17 epilogue 2 | 18 DMA (residual panels in, `out` panels and `a` tiles out).  All hand-offs are
 // mbarriers.  TMEM: GEMM1 accumulators 2 x 128 columns, GEMM2 accumulators 2 x 64 columns.
@@ -36,11 +40,11 @@ constexpr int kRows = 128;              // pixels per tile
 constexpr int kRowBytes = 128;          // one shared-memory row: 64 bf16 = the 128-byte swizzle span
 constexpr int kPanel = kRows * kRowBytes;           // 16 KB: 128 pixels x 64 channels
 constexpr int kLinkThreads = 20 * 32;
-constexpr uint32_t kW3Bytes = kCo * kRowBytes;      // 32 KB: [256 output channels][64 input channels]
+constexpr uint32_t kW3Bytes = kCo * kRowBytes;      // 32 KB per K chunk: [256 output channels][64 input channels]
 constexpr uint32_t kW1Bytes = 4 * kCa * kRowBytes;  // 32 KB: 4 K chunks of [64 output channels][64 input channels]
 
 struct LinkParams {
-  CUtensorMap tmT, tmW3, tmW1, tmR, tmO, tmA;
+  CUtensorMap tmT, tmT2, tmW3, tmW1, tmR, tmO, tmA;
   const float* bias3;
   const float* bias1;
   int Wp, Hp, H, W;
@@ -77,6 +81,9 @@ __device__ __forceinline__ bool real_pixel(const LinkParams& p, long long q) {
   return w != p.W && h != p.H;
 }
 
+// KC: input tensors of GEMM1 (K chunks of 64 channels); HAS_RES: residual added in epilogue 1; NSTG: staging buffers;
+// NTST: t tile stages
+template <int KC, bool HAS_RES, int NSTG, int NTST>
 __global__ void __launch_bounds__(kLinkThreads, 1) bottleneck_link_kernel(const __grid_constant__ LinkParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -85,10 +92,10 @@ __global__ void __launch_bounds__(kLinkThreads, 1) bottleneck_link_kernel(const 
   float* sbias = reinterpret_cast<float*>(smem + 512);            // [256] b3 | [64] b1'
   const uint32_t base = smem_u32(smem) + 2048;
   const uint32_t w3_base = base;
-  const uint32_t w1_base = w3_base + kW3Bytes;
-  const uint32_t t_base = w1_base + kW1Bytes;                     // 2 stages x 16 KB
-  const uint32_t stg_base = t_base + 2 * kPanel;                  // 3 buffers x 2 panels x 16 KB
-  const uint32_t a_base = stg_base + 3 * 2 * kPanel;              // 16 KB
+  const uint32_t w1_base = w3_base + KC * kW3Bytes;
+  const uint32_t t_base = w1_base + kW1Bytes;                     // NTST stages x KC x 16 KB
+  const uint32_t stg_base = t_base + NTST * KC * kPanel;          // NSTG buffers x 2 panels x 16 KB
+  const uint32_t a_base = stg_base + NSTG * 2 * kPanel;           // 16 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tile0 = blockIdx.x, tstride = gridDim.x;
@@ -110,7 +117,9 @@ __global__ void __launch_bounds__(kLinkThreads, 1) bottleneck_link_kernel(const 
     mbar_init(&ctl->a_free, 1);
     fence_mbar_init();
     tma_prefetch_desc(&p.tmT); tma_prefetch_desc(&p.tmW3); tma_prefetch_desc(&p.tmW1);
-    tma_prefetch_desc(&p.tmR); tma_prefetch_desc(&p.tmO); tma_prefetch_desc(&p.tmA);
+    if (KC == 2) tma_prefetch_desc(&p.tmT2);
+    if (HAS_RES) tma_prefetch_desc(&p.tmR);
+    tma_prefetch_desc(&p.tmO); tma_prefetch_desc(&p.tmA);
   }
   for (int i = threadIdx.x; i < kCo + kCa; i += kLinkThreads) sbias[i] = i < kCo ? p.bias3[i] : p.bias1[i - kCo];
   if (warp == 1) tmem_alloc(&ctl->tmem_base, 512);
@@ -123,15 +132,17 @@ __global__ void __launch_bounds__(kLinkThreads, 1) bottleneck_link_kernel(const 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      mbar_expect_tx(&ctl->w_full, kW3Bytes + kW1Bytes);
-      tma_load_2d_s(w3_base, &p.tmW3, &ctl->w_full, 0, 0);
+      mbar_expect_tx(&ctl->w_full, KC * kW3Bytes + kW1Bytes);
+      for (int kc = 0; kc < KC; ++kc) tma_load_2d_s(w3_base + kc * kW3Bytes, &p.tmW3, &ctl->w_full, kc * 64, 0);
       for (int c = 0; c < 4; ++c) tma_load_2d_s(w1_base + (uint32_t)(c * kCa * kRowBytes), &p.tmW1, &ctl->w_full, c * 64, 0);
       pdl_wait();
       for (uint32_t i = 0; i < n_my; ++i) {
-        const uint32_t s = i & 1, ph = (i >> 1) & 1;
+        const uint32_t s = i % NTST, ph = (i / NTST) & 1;
+        const int row = (int)((tile0 + (long long)i * tstride) * kRows);
         mbar_wait(&ctl->t_empty[s], ph ^ 1u);
-        mbar_expect_tx(&ctl->t_full[s], (uint32_t)kPanel);
-        tma_load_2d_s(t_base + s * kPanel, &p.tmT, &ctl->t_full[s], 0, (int)((tile0 + (long long)i * tstride) * kRows));
+        mbar_expect_tx(&ctl->t_full[s], (uint32_t)(KC * kPanel));
+        tma_load_2d_s(t_base + s * (KC * kPanel), &p.tmT, &ctl->t_full[s], 0, row);
+        if (KC == 2) tma_load_2d_s(t_base + s * (KC * kPanel) + kPanel, &p.tmT2, &ctl->t_full[s], 0, row);
       }
     }
   } else if (warp == 1) {
@@ -140,16 +151,20 @@ __global__ void __launch_bounds__(kLinkThreads, 1) bottleneck_link_kernel(const 
     mbar_wait(&ctl->w_full, 0);
     tc_fence_after();
     for (uint32_t u = 0; u < n_units; ++u) {
-      const uint32_t i = u >> 1, h = u & 1, s = i & 1, b = u & 1;
-      if (h == 0) mbar_wait(&ctl->t_full[s], (i >> 1) & 1);
+      const uint32_t i = u >> 1, h = u & 1, s = i % NTST, b = u & 1;
+      if (h == 0) mbar_wait(&ctl->t_full[s], (i / NTST) & 1);
       mbar_wait(&ctl->acc1_empty[b], ((u >> 1) & 1) ^ 1u);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ad = make_kmajor_desc(t_base + s * kPanel + (uint32_t)(ks * 32), kRowBytes);
-          const uint64_t bd = make_kmajor_desc(w3_base + h * (uint32_t)(128 * kRowBytes) + (uint32_t)(ks * 32), kRowBytes);
-          umma_bf16(tmem_base + b * 128u, ad, bd, idesc, ks ? 1u : 0u);
+        for (int kc = 0; kc < KC; ++kc) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = make_kmajor_desc(t_base + s * (KC * kPanel) + kc * kPanel + (uint32_t)(ks * 32), kRowBytes);
+            const uint64_t bd = make_kmajor_desc(w3_base + kc * kW3Bytes + h * (uint32_t)(128 * kRowBytes) + (uint32_t)(ks * 32),
+                                                 kRowBytes);
+            umma_bf16(tmem_base + b * 128u, ad, bd, idesc, (kc | ks) ? 1u : 0u);
+          }
         }
         umma_commit(&ctl->acc1_full[b]);
         if (h == 1) umma_commit(&ctl->t_empty[s]);
@@ -162,8 +177,8 @@ __global__ void __launch_bounds__(kLinkThreads, 1) bottleneck_link_kernel(const 
     mbar_wait(&ctl->w_full, 0);
     tc_fence_after();
     for (uint32_t u = 0; u < n_units; ++u) {
-      const uint32_t i = u >> 1, h = u & 1, sb = u % 3, b2 = i & 1;
-      mbar_wait(&ctl->out_ready[sb], (u / 3) & 1);
+      const uint32_t i = u >> 1, h = u & 1, sb = u % NSTG, b2 = i & 1;
+      mbar_wait(&ctl->out_ready[sb], (u / NSTG) & 1);
       if (h == 0) mbar_wait(&ctl->acc2_empty[b2], ((i >> 1) & 1) ^ 1u);
       tc_fence_after();
       if (elect_one()) {
@@ -187,12 +202,12 @@ __global__ void __launch_bounds__(kLinkThreads, 1) bottleneck_link_kernel(const 
     const int row0 = quarter * 32 + lane;
     const uint32_t xr = (uint32_t)(row0 & 7);
     for (uint32_t u = 0; u < n_units; ++u) {
-      const uint32_t i = u >> 1, h = u & 1, sb = u % 3, b = u & 1;
+      const uint32_t i = u >> 1, h = u & 1, sb = u % NSTG, b = u & 1;
       const long long q = (tile0 + (long long)i * tstride) * kRows + row0;
       const bool real = real_pixel(p, q);
       mbar_wait(&ctl->acc1_full[b], (u >> 1) & 1);
       tc_fence_after();
-      mbar_wait(&ctl->res_full[sb], (u / 3) & 1);
+      mbar_wait(&ctl->res_full[sb], (u / NSTG) & 1);             // residual landed, or (no residual) the buffer is free
 #pragma unroll 1
       for (int sl = sub; sl < 8; sl += 2) {
         uint32_t v[16];
@@ -200,7 +215,8 @@ __global__ void __launch_bounds__(kLinkThreads, 1) bottleneck_link_kernel(const 
         const uint32_t rowaddr = stg_base + (sb * 2 + (uint32_t)(sl >> 2)) * kPanel + (uint32_t)row0 * kRowBytes;
         const uint32_t c0 = (uint32_t)(sl & 3) * 2u;
         const uint32_t a0 = rowaddr + ((c0 ^ xr) << 4), a1 = rowaddr + (((c0 + 1) ^ xr) << 4);
-        const uint4 r0 = lds128(a0), r1 = lds128(a1);
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+        if (HAS_RES) { r0 = lds128(a0); r1 = lds128(a1); }
         const float4* b4 = reinterpret_cast<const float4*>(sbias + h * 128 + sl * 16);
         const float4 bias[4] = {b4[0], b4[1], b4[2], b4[3]};
         tmem_ld_wait();
@@ -210,10 +226,12 @@ __global__ void __launch_bounds__(kLinkThreads, 1) bottleneck_link_kernel(const 
           fadd2(v[g * 4 + 0], v[g * 4 + 1], __float_as_uint(bias[g].x), __float_as_uint(bias[g].y));
           fadd2(v[g * 4 + 2], v[g * 4 + 3], __float_as_uint(bias[g].z), __float_as_uint(bias[g].w));
         }
-        fadd2(v[0], v[1], r0.x << 16, r0.x & 0xFFFF0000u);   fadd2(v[2], v[3], r0.y << 16, r0.y & 0xFFFF0000u);
-        fadd2(v[4], v[5], r0.z << 16, r0.z & 0xFFFF0000u);   fadd2(v[6], v[7], r0.w << 16, r0.w & 0xFFFF0000u);
-        fadd2(v[8], v[9], r1.x << 16, r1.x & 0xFFFF0000u);   fadd2(v[10], v[11], r1.y << 16, r1.y & 0xFFFF0000u);
-        fadd2(v[12], v[13], r1.z << 16, r1.z & 0xFFFF0000u); fadd2(v[14], v[15], r1.w << 16, r1.w & 0xFFFF0000u);
+        if (HAS_RES) {
+          fadd2(v[0], v[1], r0.x << 16, r0.x & 0xFFFF0000u);   fadd2(v[2], v[3], r0.y << 16, r0.y & 0xFFFF0000u);
+          fadd2(v[4], v[5], r0.z << 16, r0.z & 0xFFFF0000u);   fadd2(v[6], v[7], r0.w << 16, r0.w & 0xFFFF0000u);
+          fadd2(v[8], v[9], r1.x << 16, r1.x & 0xFFFF0000u);   fadd2(v[10], v[11], r1.y << 16, r1.y & 0xFFFF0000u);
+          fadd2(v[12], v[13], r1.z << 16, r1.z & 0xFFFF0000u); fadd2(v[14], v[15], r1.w << 16, r1.w & 0xFFFF0000u);
+        }
         uint4 o0 = make_uint4(pack_relu2(f[0], f[1]), pack_relu2(f[2], f[3]), pack_relu2(f[4], f[5]), pack_relu2(f[6], f[7]));
         uint4 o1 = make_uint4(pack_relu2(f[8], f[9]), pack_relu2(f[10], f[11]), pack_relu2(f[12], f[13]), pack_relu2(f[14], f[15]));
         if (!real) { o0 = make_uint4(0, 0, 0, 0); o1 = o0; }     // zero cells of the padded layout stay zero
@@ -268,24 +286,28 @@ __global__ void __launch_bounds__(kLinkThreads, 1) bottleneck_link_kernel(const 
     if (lane == 0 && n_units > 0) {
       pdl_wait();
       auto row_of = [&](uint32_t u) { return (int)((tile0 + (long long)(u >> 1) * tstride) * kRows); };
+      // staging buffer of unit u: its residual panels (or, without a residual, just "free") -> res_full
       auto load_res = [&](uint32_t u) {
-        const uint32_t sb = u % 3;
-        mbar_expect_tx(&ctl->res_full[sb], 2u * kPanel);
-        for (int pn = 0; pn < 2; ++pn)
-          tma_load_2d_s(stg_base + (sb * 2 + pn) * kPanel, &p.tmR, &ctl->res_full[sb], (int)(u & 1) * 128 + pn * 64, row_of(u));
+        const uint32_t sb = u % NSTG;
+        if (HAS_RES) {
+          mbar_expect_tx(&ctl->res_full[sb], 2u * kPanel);
+          for (int pn = 0; pn < 2; ++pn)
+            tma_load_2d_s(stg_base + (sb * 2 + pn) * kPanel, &p.tmR, &ctl->res_full[sb], (int)(u & 1) * 128 + pn * 64, row_of(u));
+        } else {
+          mbar_arrive(&ctl->res_full[sb]);
+        }
       };
-      load_res(0);
-      if (n_units > 1) load_res(1);
+      for (uint32_t u = 0; u + 1 < (uint32_t)NSTG && u < n_units; ++u) load_res(u);
       bool a_inflight = false;
       for (uint32_t u = 0; u < n_units; ++u) {
-        const uint32_t sb = u % 3;
+        const uint32_t sb = u % NSTG;
         if (u >= 1) {
           bulk_wait_read<0>();                                   // every store issued so far has read its source
           if (a_inflight) { mbar_arrive(&ctl->a_free); a_inflight = false; }
         }
-        if (u + 2 < n_units) {                                   // buffer of unit u-1: drained by its store (above) and by GEMM2
-          if (u >= 1) mbar_wait(&ctl->g2_done[(u - 1) % 3], ((u - 1) / 3) & 1);
-          load_res(u + 2);
+        if (u + NSTG - 1 < n_units) {                            // buffer of unit u-1: drained by its store (above) and by GEMM2
+          if (u >= 1) mbar_wait(&ctl->g2_done[(u - 1) % NSTG], ((u - 1) / NSTG) & 1);
+          load_res(u + NSTG - 1);
         }
         if (u >= 2 && !(u & 1)) {                                // the previous tile's `a`
           const uint32_t ip = (u >> 1) - 1;
@@ -294,7 +316,7 @@ __global__ void __launch_bounds__(kLinkThreads, 1) bottleneck_link_kernel(const 
           bulk_commit();
           a_inflight = true;
         }
-        mbar_wait(&ctl->out_ready[sb], (u / 3) & 1);
+        mbar_wait(&ctl->out_ready[sb], (u / NSTG) & 1);
         for (int pn = 0; pn < 2; ++pn)
           tma_store_2d_s(&p.tmO, stg_base + (sb * 2 + pn) * kPanel, (int)(u & 1) * 128 + pn * 64, row_of(u));
         bulk_commit();
@@ -346,38 +368,20 @@ int enc2d(CUtensorMap* tm, const void* basep, long long cols, long long rows, in
 
 bool bottleneck_link_supported(int ct, int co, int ca) { return ct == kCt && co == kCo && ca == kCa; }
 
-// t: padded-linear bf16 [N][H+1][W+1][64]; x (residual), out: [..][256]; a: [..][64]; w3: packed [256][64] bf16;
-// w1: packed [64][256] bf16; b3: 256 fp32, b1: 64 fp32 (folded BatchNorm).  out must not alias x.
-int bottleneck_link_launch(const __nv_bfloat16* t, const __nv_bfloat16* x, __nv_bfloat16* out, __nv_bfloat16* a,
-                           const __nv_bfloat16* w3, const float* b3, const __nv_bfloat16* w1, const float* b1, int N, int H,
-                           int W, int max_ctas, cudaStream_t stream, int pdl) {
-  if (N <= 0 || H <= 0 || W <= 0) { set_error("bottleneck_link: bad geometry"); return 1; }
-  if (!t || !x || !out || !a || !w3 || !b3 || !w1 || !b1) { set_error("bottleneck_link: null pointer"); return 1; }
-  if (out == x) { set_error("bottleneck_link: out must not alias the residual"); return 1; }
-  LinkParams p{};
-  p.Wp = W + 1; p.Hp = H + 1; p.H = H; p.W = W;
-  p.P = (long long)N * p.Hp * p.Wp;
-  if (p.P + kRows >= (1ll << 31)) { set_error("bottleneck_link: tensor too large"); return 1; }
-  p.bias3 = b3; p.bias1 = b1;
-  p.fd_Wp.init((uint32_t)p.Wp); p.fd_Hp.init((uint32_t)p.Hp);
-  p.total_tiles = (p.P + kRows - 1) / kRows;
-  if (enc2d(&p.tmT, t, kCt, p.P, kRows)) return 1;
-  if (enc2d(&p.tmR, x, kCo, p.P, kRows)) return 1;
-  if (enc2d(&p.tmO, out, kCo, p.P, kRows)) return 1;
-  if (enc2d(&p.tmA, a, kCa, p.P, kRows)) return 1;
-  if (enc2d(&p.tmW3, w3, kCt, kCo, kCo)) return 1;      // one box: all 256 rows
-  if (enc2d(&p.tmW1, w1, kCo, kCa, kCa)) return 1;      // four boxes of 64 columns x 64 rows
-  const size_t smem = 1024 + 2048 + kW3Bytes + kW1Bytes + 2 * kPanel + 3 * 2 * kPanel + kPanel;
-  static DeviceOnce attr_once;
-  if (attr_once.run([smem]() {
-        cudaError_t e2 = cudaFuncSetAttribute(bottleneck_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+namespace {
+template <int KC, bool HAS_RES, int NSTG, int NTST>
+int launch_variant(const LinkParams& p, long long grid, cudaStream_t stream, int pdl) {
+  auto kern = bottleneck_link_kernel<KC, HAS_RES, NSTG, NTST>;
+  const size_t smem = 1024 + 2048 + KC * kW3Bytes + kW1Bytes + (size_t)NTST * KC * kPanel + (size_t)NSTG * 2 * kPanel + kPanel;
+  static_assert(1024 + 2048 + KC * kW3Bytes + kW1Bytes + NTST * KC * kPanel + NSTG * 2 * kPanel + kPanel <= 227 * 1024,
+                "bottleneck_link: shared memory budget");
+  static DeviceOnce attr_once;   // (one per instantiation)
+  if (attr_once.run([&]() {
+        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e2 != cudaSuccess) { set_error("bottleneck_link attribute: %s", cudaGetErrorString(e2)); return 1; }
         return 0;
       }))
     return 1;
-  const int sms = device_sm_count();
-  long long grid = p.total_tiles < sms ? p.total_tiles : sms;
-  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   cudaError_t e;
   if (pdl) {
     cudaLaunchConfig_t cfg{};
@@ -390,14 +394,48 @@ int bottleneck_link_launch(const __nv_bfloat16* t, const __nv_bfloat16* x, __nv_
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, bottleneck_link_kernel, p);
+    e = cudaLaunchKernelEx(&cfg, kern, p);
     if (e != cudaSuccess) { set_error("bottleneck_link (attributed) launch: %s", cudaGetErrorString(e)); return 1; }
   } else {
-    bottleneck_link_kernel<<<(unsigned)grid, kLinkThreads, smem, stream>>>(p);
+    kern<<<(unsigned)grid, kLinkThreads, smem, stream>>>(p);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("bottleneck_link launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;
+}
+}  // namespace
+
+// t: padded-linear bf16 [N][H+1][W+1][64]; out: [..][256]; a: [..][64]; w1: packed [64][256] bf16; b3: 256 fp32,
+// b1: 64 fp32 (folded BatchNorm).  Either  x (residual, [..][256], must not alias out) with w3 packed [256][64],
+// or       t2 (second input of GEMM1, [..][64]) with w3 packed [256][128] = [W3 | Wd] and b3 the summed bias, no residual.
+int bottleneck_link_launch(const __nv_bfloat16* t, const __nv_bfloat16* t2, const __nv_bfloat16* x, __nv_bfloat16* out,
+                           __nv_bfloat16* a, const __nv_bfloat16* w3, const float* b3, const __nv_bfloat16* w1,
+                           const float* b1, int N, int H, int W, int max_ctas, cudaStream_t stream, int pdl) {
+  if (N <= 0 || H <= 0 || W <= 0) { set_error("bottleneck_link: bad geometry"); return 1; }
+  if (!t || !out || !a || !w3 || !b3 || !w1 || !b1 || (!x && !t2) || (x && t2)) {
+    set_error("bottleneck_link: null pointer (exactly one of residual / second input)");
+    return 1;
+  }
+  if (out == x) { set_error("bottleneck_link: out must not alias the residual"); return 1; }
+  LinkParams p{};
+  p.Wp = W + 1; p.Hp = H + 1; p.H = H; p.W = W;
+  p.P = (long long)N * p.Hp * p.Wp;
+  if (p.P + kRows >= (1ll << 31)) { set_error("bottleneck_link: tensor too large"); return 1; }
+  p.bias3 = b3; p.bias1 = b1;
+  p.fd_Wp.init((uint32_t)p.Wp); p.fd_Hp.init((uint32_t)p.Hp);
+  p.total_tiles = (p.P + kRows - 1) / kRows;
+  const int kc = t2 ? 2 : 1;
+  if (enc2d(&p.tmT, t, kCt, p.P, kRows)) return 1;
+  if (t2 && enc2d(&p.tmT2, t2, kCt, p.P, kRows)) return 1;
+  if (x && enc2d(&p.tmR, x, kCo, p.P, kRows)) return 1;
+  if (enc2d(&p.tmO, out, kCo, p.P, kRows)) return 1;
+  if (enc2d(&p.tmA, a, kCa, p.P, kRows)) return 1;
+  if (enc2d(&p.tmW3, w3, kCt * kc, kCo, kCo)) return 1;    // one 64-column box of all 256 rows per K chunk
+  if (enc2d(&p.tmW1, w1, kCo, kCa, kCa)) return 1;         // four boxes of 64 columns x 64 rows
+  const int sms = device_sm_count();
+  long long grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  return t2 ? launch_variant<2, false, 2, 1>(p, grid, stream, pdl) : launch_variant<1, true, 3, 2>(p, grid, stream, pdl);
 }
 
 }  // namespace stl

@@ -138,9 +138,20 @@ struct Plan::Builder {
         P.weight_bytes += align_up(sizeof(float) * P.layers[l3].cout_pad, 256);
         P.cats.push_back(cat);
         int o = acquire(256, H4, W4);
-        conv(l3, bb, o, -1, true);
-        P.ops.back().in2 = x;
-        P.ops.back().cat = (int)P.cats.size() - 1;
+        if (P.fuse_links && bottleneck_link_supported(64, 256, 64)) {
+          // ... and conv1 of layer1.1 in the same kernel (link_tc.cu, two-input variant)
+          l1_next = layer("layer1.1.conv1", "layer1.1.bn1", 64, 256, 1, 1);
+          a_next = acquire(64, H4, W4);
+          Plan::Op op;
+          op.kind = Plan::OP_LINK;
+          op.layer = l3; op.layer2 = l1_next; op.in = bb; op.in2 = x; op.cat = (int)P.cats.size() - 1;
+          op.out = o; op.out2 = a_next; op.relu = true;
+          P.ops.push_back(op);
+        } else {
+          conv(l3, bb, o, -1, true);
+          P.ops.back().in2 = x;
+          P.ops.back().cat = (int)P.cats.size() - 1;
+        }
         release(bb);
         release(x);
         x = o;
@@ -548,12 +559,14 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
         const Slot& so = slots[op.out];
         const Layer& L3 = layers[op.layer];
         const Layer& L1 = layers[op.layer2];
+        const bool two_in = op.cat >= 0;   // layer1.0 -> .1: concatenated conv3 | downsample weights, no residual
         if (bottleneck_link_launch(reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.in]),
-                                   reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.res]),
+                                   two_in ? reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.in2]) : nullptr,
+                                   two_in ? nullptr : reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.res]),
                                    reinterpret_cast<__nv_bfloat16*>(slot_ptr[op.out]),
                                    reinterpret_cast<__nv_bfloat16*>(slot_ptr[op.out2]),
-                                   reinterpret_cast<const __nv_bfloat16*>(wbase + L3.w_off),
-                                   reinterpret_cast<const float*>(wbase + L3.b_off),
+                                   reinterpret_cast<const __nv_bfloat16*>(wbase + (two_in ? cats[op.cat].w_off : L3.w_off)),
+                                   reinterpret_cast<const float*>(wbase + (two_in ? cats[op.cat].b_off : L3.b_off)),
                                    reinterpret_cast<const __nv_bfloat16*>(wbase + L1.w_off),
                                    reinterpret_cast<const float*>(wbase + L1.b_off), n_images, so.H, so.W, 0, st,
                                    pdl_fused))
@@ -610,8 +623,10 @@ int Plan::op_info(int i, stl_op_info* info) const {
     const Layer& L3 = layers[op.layer];
     const Layer& L1 = layers[op.layer2];
     info->out_h = so->H; info->out_w = so->W; info->cin = L3.cin; info->cout = L3.cout; info->ksize = 1; info->stride = 1;
-    info->flops_per_image = 2.0 * ((double)L3.cout * L3.cin + (double)L1.cout * L1.cin) * so->H * so->W;
-    info->bytes_per_image = (double)so->H * so->W * 2 * (L3.cin + 2.0 * L3.cout + L1.cout);
+    const int cin1 = L3.cin + (op.cat >= 0 ? layers[cats[op.cat].lb].cin : 0);
+    info->cin = cin1;
+    info->flops_per_image = 2.0 * ((double)L3.cout * cin1 + (double)L1.cout * L1.cin) * so->H * so->W;
+    info->bytes_per_image = (double)so->H * so->W * 2 * (cin1 + (op.cat >= 0 ? 1.0 : 2.0) * L3.cout + L1.cout);
     info->mb = 1; info->nt = 128; info->ck = 64; info->grid = 148;
     return 0;
   }

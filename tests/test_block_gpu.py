@@ -103,3 +103,54 @@ def test_bottleneck_link_equals_two_convs(n, h, w, max_ctas):
     # the residual must not alias the output
     assert L.stl_bottleneck_link(_lib.ptr(tin), _lib.ptr(out1), _lib.ptr(out1), _lib.ptr(a1), _lib.ptr(wp3), _lib.ptr(bp3),
                                  _lib.ptr(wp1), _lib.ptr(bp1), n, h, w, 0, _lib.current_stream()) != 0
+
+
+@pytest.mark.parametrize("n,h,w,max_ctas", [(1, 64, 48, 0), (70, 64, 48, 0), (9, 64, 48, 3), (5, 16, 12, 2), (2, 8, 6, 0),
+                                            (40, 32, 24, 1)])
+def test_bottleneck_link_two_inputs_equals_two_convs(n, h, w, max_ctas):
+    """stl_bottleneck_link2 (layer1.0 -> layer1.1: conv3 + downsample over K = [t | t2] with concatenated weights, ReLU,
+    then conv1 + ReLU of the next block, one kernel) vs the two-input stl_conv2d followed by the 256 -> 64 stl_conv2d:
+    bit-identical, zero cells kept; and vs torch fp32 as two separate convolutions summed (models/HRnet.py:88-101)."""
+    L = _lib.lib()
+    ct, co, ca = 64, 256, 64
+    g = torch.Generator(device=DEV).manual_seed(n * 10 + h + 1)
+    t = bf16_round(torch.randn(n, ct, h, w, device=DEV, generator=g))
+    t2 = bf16_round(torch.randn(n, ct, h, w, device=DEV, generator=g))
+    w3 = torch.randn(co, ct, 1, 1, device=DEV, generator=g) / ct ** 0.5
+    wd = torch.randn(co, ct, 1, 1, device=DEV, generator=g) / ct ** 0.5
+    w1 = torch.randn(ca, co, 1, 1, device=DEV, generator=g) / co ** 0.5
+    wp3, bp3, wf3, bf3, _ = pack(w3, _bn(co, g))
+    wpd, bpd, wfd, bfd, _ = pack(wd, _bn(co, g))
+    wp1, bp1, wf1, bf1, _ = pack(w1, _bn(ca, g))
+    wcat = torch.cat([wp3.view(torch.bfloat16).view(co, ct), wpd.view(torch.bfloat16).view(co, ct)], 1).contiguous()
+    bcat = (bp3 + bpd).contiguous()
+    tin, t2in = to_padded(t), to_padded(t2)
+    out2 = to_padded(torch.zeros(n, co, h, w, device=DEV))
+    a2 = torch.zeros_like(tin)
+    d = _lib.ConvDesc()
+    d.in_ = tin.data_ptr(); d.N, d.H, d.W, d.Cin = n, h, w, ct
+    d.in2 = t2in.data_ptr(); d.Cin2 = ct
+    d.out = out2.data_ptr(); d.Cout, d.Cout_pad = co, co
+    d.ksize, d.stride = 1, 1
+    d.w_packed = wcat.data_ptr(); d.bias_packed = bcat.data_ptr()
+    d.relu = 1
+    _lib.check(L.stl_conv2d(ctypes.byref(d), _lib.current_stream()))
+    d2 = _lib.ConvDesc()
+    d2.in_ = out2.data_ptr(); d2.N, d2.H, d2.W, d2.Cin = n, h, w, co
+    d2.out = a2.data_ptr(); d2.Cout, d2.Cout_pad = ca, ca
+    d2.ksize, d2.stride = 1, 1
+    d2.w_packed = wp1.data_ptr(); d2.bias_packed = bp1.data_ptr()
+    d2.relu = 1
+    _lib.check(L.stl_conv2d(ctypes.byref(d2), _lib.current_stream()))
+    out1 = torch.full_like(out2, 0x7f)
+    a1 = torch.full_like(tin, 0x7f)
+    _lib.check(L.stl_bottleneck_link2(_lib.ptr(tin), _lib.ptr(t2in), _lib.ptr(out1), _lib.ptr(a1), _lib.ptr(wcat),
+                                      _lib.ptr(bcat), _lib.ptr(wp1), _lib.ptr(bp1), n, h, w, max_ctas, _lib.current_stream()))
+    torch.cuda.synchronize()
+    assert padded_border_is_zero(out1, n, co, h, w) and padded_border_is_zero(a1, n, ca, h, w)
+    assert torch.equal(out1, out2), (out1 != out2).float().mean().item()
+    assert torch.equal(a1, a2), (a1 != a2).float().mean().item()
+    o_ref = F.relu(F.conv2d(t, bf16_round(wf3), bf3) + F.conv2d(t2, bf16_round(wfd), bfd))
+    a_ref = F.relu(F.conv2d(bf16_round(o_ref), bf16_round(wf1), bf1))
+    assert (from_padded(out1, n, co, h, w) - o_ref).abs().max().item() < 1e-2 * max(1.0, o_ref.abs().max().item())
+    assert (from_padded(a1, n, ca, h, w) - a_ref).abs().max().item() < 2e-2 * max(1.0, a_ref.abs().max().item())
