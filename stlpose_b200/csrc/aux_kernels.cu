@@ -230,6 +230,84 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseArgs a) {
   }
 }
 
+// The last fuse row of the network and the heatmap head in one pass (HRnet.py:255-264 with n_out = 1, then :466):
+//   y = relu(x + sum up(z))  (rounded to bf16 like the stored tensor it replaces)  ->  heat[j] = sum_c W[j][c] y[c] + b[j]
+// C = 32 channels, J <= 32 joints.  One thread per padded pixel: 64 B of x, the gathers, 17 x 32 FMAs against the weights
+// in shared memory (broadcast reads), fp32 NCHW stores that are coalesced along w.  y is never written: two passes over
+// the 32-channel map (209 MB each per 1 024 images at 64x48) and one launch less.
+struct FuseHeadArgs {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* z[kMaxUp];
+  int shift[kMaxUp];
+  const __nv_bfloat16* w;      // packed [J_pad][32] bf16
+  const float* bias;           // [J_pad]
+  float* heat;                 // fp32 [N][J][H][W]
+  int N, H, W, J;
+  FastDiv fd_wp, fd_hp;
+};
+
+template <int NUP>
+__global__ void __launch_bounds__(256) fuse_head_kernel(const FuseHeadArgs a) {
+  __shared__ __align__(16) float sw[32 * 32];
+  __shared__ float sb[32];
+  for (int i = threadIdx.x; i < a.J * 32; i += blockDim.x) sw[i] = __bfloat162float(a.w[i]);
+  if (threadIdx.x < a.J) sb[threadIdx.x] = a.bias[threadIdx.x];
+  __syncthreads();
+  const int Wp = a.W + 1, Hp = a.H + 1;
+  const uint32_t total = (uint32_t)a.N * (uint32_t)(Hp * Wp);
+  const size_t plane = (size_t)a.H * a.W;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+    const uint32_t t = a.fd_wp.div(q);
+    const int w = (int)(q - t * (uint32_t)Wp);
+    const int n = (int)a.fd_hp.div(t);
+    const int h = (int)t - n * Hp;
+    if (h >= a.H || w >= a.W) continue;
+    const uint4* xp = reinterpret_cast<const uint4*>(a.x) + (size_t)q * 4;
+    uint4 u[4], zz[NUP][4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) u[g] = __ldcs(xp + g);
+#pragma unroll
+    for (int j = 0; j < NUP; ++j) {
+      const int s = a.shift[j];
+      const size_t qs = ((size_t)n * ((a.H >> s) + 1) + (h >> s)) * ((a.W >> s) + 1) + (w >> s);
+      const uint4* zp = reinterpret_cast<const uint4*>(a.z[j]) + qs * 4;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) zz[j][g] = __ldg(zp + g);
+    }
+    float f[32];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      f[g * 8 + 0] = bf16_lo(u[g].x); f[g * 8 + 1] = bf16_hi(u[g].x); f[g * 8 + 2] = bf16_lo(u[g].y); f[g * 8 + 3] = bf16_hi(u[g].y);
+      f[g * 8 + 4] = bf16_lo(u[g].z); f[g * 8 + 5] = bf16_hi(u[g].z); f[g * 8 + 6] = bf16_lo(u[g].w); f[g * 8 + 7] = bf16_hi(u[g].w);
+    }
+#pragma unroll
+    for (int j = 0; j < NUP; ++j) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint4 z = zz[j][g];
+        f[g * 8 + 0] += bf16_lo(z.x); f[g * 8 + 1] += bf16_hi(z.x); f[g * 8 + 2] += bf16_lo(z.y); f[g * 8 + 3] += bf16_hi(z.y);
+        f[g * 8 + 4] += bf16_lo(z.z); f[g * 8 + 5] += bf16_hi(z.z); f[g * 8 + 6] += bf16_lo(z.w); f[g * 8 + 7] += bf16_hi(z.w);
+      }
+    }
+    // ReLU, then the bf16 rounding of the tensor this replaces (the head convolution read y from memory)
+#pragma unroll
+    for (int c = 0; c < 32; ++c) f[c] = __bfloat162float(__float2bfloat16_rn(fmaxf(f[c], 0.f)));
+    float* out = a.heat + ((size_t)n * a.J * a.H + h) * a.W + w;
+#pragma unroll 1
+    for (int j = 0; j < a.J; ++j) {
+      const float4* wr = reinterpret_cast<const float4*>(sw + j * 32);
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 ww = wr[c4];
+        acc0 = fmaf(f[c4 * 4 + 0], ww.x, acc0); acc1 = fmaf(f[c4 * 4 + 1], ww.y, acc1);
+        acc2 = fmaf(f[c4 * 4 + 2], ww.z, acc2); acc3 = fmaf(f[c4 * 4 + 3], ww.w, acc3);
+      }
+      __stcs(out + (size_t)j * plane, (acc0 + acc1) + (acc2 + acc3) + sb[j]);
+    }
+  }
+}
+
 // Every raw weight repack of a training step in one launch (a step re-packs 293 forward + 292 dgrad layouts; as separate
 // launches they are 585 graph nodes of a few microseconds each).  Block -> item by binary search over the block offsets.
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackItem* __restrict__ items,
@@ -443,6 +521,26 @@ int fuse_sum(const __nv_bfloat16* x, const __nv_bfloat16* const* z, const int* s
     default: set_error("fuse_sum: %d upsampled addends (1..3 supported)", n_up); return 1;
   }
   return check("fuse_sum");
+}
+
+int fuse_head(const __nv_bfloat16* x, const __nv_bfloat16* const* z, const int* shift, int n_up, const __nv_bfloat16* w,
+              const float* bias, float* heat, int N, int H, int W, int C, int J, cudaStream_t st) {
+  if (C != 32 || J < 1 || J > 32 || n_up < 1 || n_up > kMaxUp) { set_error("fuse_head: C=%d J=%d n_up=%d unsupported", C, J, n_up); return 1; }
+  FuseHeadArgs a{};
+  a.x = x; a.w = w; a.bias = bias; a.heat = heat; a.N = N; a.H = H; a.W = W; a.J = J;
+  for (int i = 0; i < n_up; ++i) { a.z[i] = z[i]; a.shift[i] = shift[i]; }
+  const long long total = (long long)N * (H + 1) * (W + 1);
+  if (total >= (1ll << 31) - 148ll * 16 * 256) { set_error("fuse_head: tensor too large for 32-bit pixel indexing"); return 1; }
+  a.fd_wp.init((uint32_t)(W + 1));
+  a.fd_hp.init((uint32_t)(H + 1));
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  switch (n_up) {
+    case 1: fuse_head_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+    case 2: fuse_head_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+    case 3: fuse_head_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+  }
+  return check("fuse_head");
 }
 
 int conv_launch_naive(const ConvSpec& s, cudaStream_t st) {

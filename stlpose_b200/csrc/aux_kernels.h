@@ -25,4 +25,8 @@ int stem_pack_input(const float* x, __nv_bfloat16* y, int n_total, int n_plain, 
 int fuse_sum(const __nv_bfloat16* x, const __nv_bfloat16* const* z, const int* shift, int n_up, __nv_bfloat16* y,
              int N, int H, int W, int C, cudaStream_t st);
 
+// y = relu(x + sum up(z)) (C = 32) and the 1x1 heatmap head on it in one pass: heat fp32 [N][J][H][W]; y is not written
+int fuse_head(const __nv_bfloat16* x, const __nv_bfloat16* const* z, const int* shift, int n_up, const __nv_bfloat16* w,
+              const float* bias, float* heat, int N, int H, int W, int C, int J, cudaStream_t st);
+
 }  // namespace stl

@@ -297,7 +297,15 @@ struct Plan::Builder {
       }
     }
     // head (HRnet.py:331-337, 466): 1x1 conv with bias, no activation, fp32 NCHW out
-    conv(layer("final_layer", "", c.num_joints, ch[0], 1, 1), xs[0], -1, -1, false, 0, nullptr, nullptr, true);
+    const int lh = layer("final_layer", "", c.num_joints, ch[0], 1, 1);
+    Plan::Op& last = P.ops.back();
+    if (P.fuse_head && last.kind == Plan::OP_FUSE && last.out == xs[0] && ch[0] == 32 && c.num_joints <= 32 && last.n_up >= 1) {
+      // the last fuse row feeds nothing but the head: both in one pass, the fused map is never written (aux_kernels.cu)
+      last.layer = lh;
+      last.out_nchw = true;
+    } else {
+      conv(lh, xs[0], -1, -1, false, 0, nullptr, nullptr, true);
+    }
     release(xs[0]);
   }
 };
@@ -316,6 +324,7 @@ Plan* Plan::create(const stl_hrnet_cfg& cfg) {
   if (const char* e = getenv("STLPOSE_FUSE_BLOCK")) p->fuse_blocks = atoi(e);
   if (const char* e = getenv("STLPOSE_FUSE_DOWNSAMPLE")) p->fuse_downsample = atoi(e);
   if (const char* e = getenv("STLPOSE_FUSE_LINK")) p->fuse_links = atoi(e);
+  if (const char* e = getenv("STLPOSE_FUSE_HEAD")) p->fuse_head = atoi(e);
   if (const char* e = getenv("STLPOSE_BRANCH_STREAMS")) p->branch_streams = atoi(e);
   if (const char* e = getenv("STLPOSE_STEM_IM2COL")) p->stem_im2col = atoi(e);
   Builder b(*p);
@@ -577,6 +586,14 @@ int Plan::forward(const float* x, int B, int flip_pair, float* heat, const void*
         const Slot& so = slots[op.out];
         const __nv_bfloat16* z[kMaxUp];
         for (int u = 0; u < op.n_up; ++u) z[u] = reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.up[u]]);
+        if (op.layer >= 0) {   // + the heatmap head
+          const Layer& Lh = layers[op.layer];
+          if (stl::fuse_head(reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.in]), z, op.up_shift, op.n_up,
+                        reinterpret_cast<const __nv_bfloat16*>(wbase + Lh.w_off), reinterpret_cast<const float*>(wbase + Lh.b_off),
+                        heat, n_images, so.H, so.W, so.C, Lh.cout, st))
+            return 1;
+          break;
+        }
         if (fuse_sum(reinterpret_cast<const __nv_bfloat16*>(slot_ptr[op.in]), z, op.up_shift, op.n_up,
                      reinterpret_cast<__nv_bfloat16*>(slot_ptr[op.out]), n_images, so.H, so.W, so.C, st))
           return 1;
@@ -617,6 +634,12 @@ int Plan::op_info(int i, stl_op_info* info) const {
     info->out_h = so->H; info->out_w = so->W; info->cout = so->C; info->cin = so->C;
     info->bytes_per_image = 2.0 * so->H * so->W * so->C * 2;
     for (int u = 0; u < op.n_up; ++u) info->bytes_per_image += (double)slots[op.up[u]].H * slots[op.up[u]].W * so->C * 2;
+    if (op.layer >= 0) {   // + heatmap head: the fused map is not written, fp32 heatmaps are
+      const Layer& Lh = layers[op.layer];
+      info->cout = Lh.cout; info->ksize = 1; info->stride = 1;
+      info->flops_per_image = 2.0 * Lh.cout * Lh.cin * so->H * so->W;
+      info->bytes_per_image += (double)so->H * so->W * (Lh.cout * 4.0 - so->C * 2.0);
+    }
     return 0;
   }
   if (op.kind == OP_LINK) {    // two 1x1 convs; algorithmic traffic: read t and the residual, write out and a

@@ -56,6 +56,7 @@ struct Plan {
   std::vector<Slot> slots;
   std::vector<Op> ops;
   std::vector<Cat> cats;
+  int fuse_head = 1;        // STLPOSE_FUSE_HEAD=0: the last fuse row and the heatmap head as two launches
   int use_pdl = 1;          // STLPOSE_PDL=0: no programmatic dependent launch between consecutive kernels
   int fuse_links = 1;       // STLPOSE_FUSE_LINK=0: conv3 of a layer1 Bottleneck and conv1 of the next as two launches
   int fuse_downsample = 1;  // STLPOSE_FUSE_DOWNSAMPLE=0: downsample and conv3 of layer1.0 as two launches

@@ -148,22 +148,27 @@ def _pack_weights_dgrad(w, k_pad):
 FUSED_BN_STATS = os.environ.get("STLPOSE_FUSED_BN_STATS", "0") == "1"
 STEM_IM2COL = os.environ.get("STLPOSE_TRAIN_STEM_IM2COL", "1") != "0"
 MASK_FROM_Z = os.environ.get("STLPOSE_TRAIN_MASK_FROM_Z", "1") != "0"
-# statistics + normalisation (and both backward passes) of a BatchNorm layer as one cooperative launch each: saves two
-# graph nodes per layer, but the in-kernel hand-over makes the kernel itself slower than the pair (15 vs 13 us at 6 MB,
-# 69 vs 65 us at 52 MB).  "auto": only for tensors <= 16 MB and only in a single-GPU process - a cooperative grid that
-# spins for its last blocks next to in-flight NCCL kernels is not something to rely on.  "1" / "0" force it on / off.
+# statistics + normalisation / both backward passes of a BatchNorm layer as ONE cooperative launch per direction.  The
+# backward pair re-reads dy and z right after the reduction read them, which hits L2 inside one launch (104 vs 120 us at
+# 52 MB, 24 vs 35 us at 13 MB); the forward pair gains nothing but the saved graph node and its in-kernel hand-over makes
+# it slower than the two launches (15 vs 13 us at 6 MB, 69 vs 65 us at 52 MB).  Measured per step (batch 32 / 128):
+# neither 17.6 / 42.8 ms, both for tensors <= 16 MB 17.2-17.5 / 42.9-43.1, backward only at every size 16.75 / 41.3.
+# "auto" = that last policy, and only in a single-GPU process - a cooperative grid that spins for its last blocks next to
+# in-flight NCCL kernels is not something to rely on.  "1" / "0" force both directions on / off.
 COOP_BN = os.environ.get("STLPOSE_TRAIN_COOP_BN", "auto")
-_COOP_BN_MAX_BYTES = 16 << 20
+# size limits of "auto" per direction, in MB (measurement knobs)
+_COOP_BN_MAX_BYTES = (int(os.environ.get("STLPOSE_TRAIN_COOP_BN_FWD_MB", "0")) << 20,
+                      int(os.environ.get("STLPOSE_TRAIN_COOP_BN_BWD_MB", "1000000")) << 20)
 # programmatic dependent launch for the convolutions of the training path (stl_conv_desc.pdl): their packed weights are
 # written once at the start of a step, never by the kernel in front of them.  (The BatchNorm kernels read the same switch
 # in the library.)  Measured on B200: no gain (17.6-17.8 vs 17.3-17.6 ms per step at batch 32) - off by default.
 TRAIN_PDL = os.environ.get("STLPOSE_TRAIN_PDL", "0") == "1"
 
 
-def _use_coop_bn(z):
+def _use_coop_bn(z, backward=False):
     if COOP_BN in ("0", "1"):
         return COOP_BN == "1"
-    if z.numel() * z.element_size() > _COOP_BN_MAX_BYTES:
+    if z.numel() * z.element_size() > _COOP_BN_MAX_BYTES[1 if backward else 0]:
         return False
     import torch.distributed as dist
     return not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
@@ -351,7 +356,7 @@ class _ConvBN(torch.autograd.Function):
         # (parallel.GradientReducer.bind) - written straight into the bucket by the kernels, nothing returned
         wsink, bsink = ctx.sinks if ctx.sinks is not None else (None, None)
         sums = bsink.view if bsink is not None else torch.empty(2 * cout, dtype=torch.float32, device=x.device)   # dbeta | dgamma
-        if _use_coop_bn(z):
+        if _use_coop_bn(z, backward=True):
             mode = 0 if not relu else (2 if (not has_res and MASK_FROM_Z) else 1)
             _lib.check(L.stl_bn_train_backward_coop(_lib.ptr(dy), _lib.ptr(y) if mode == 1 else None, _lib.ptr(z), _lib.ptr(mean),
                                                     _lib.ptr(rstd), _lib.ptr(g32), _lib.ptr(b32), mode, n, ho, wo, cout,

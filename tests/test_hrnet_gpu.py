@@ -58,6 +58,14 @@ def test_concatenated_downsample_matches_the_two_launch_form(golden_inputs, monk
     y2 = m2(x)
     assert torch.equal(y1, y2)
     assert m2.launches_per_forward() == m1.launches_per_forward() + 3
+    # the last fuse row + the heatmap head in one pass (fuse_head_kernel, fp32 FMA chain on the bf16-rounded fused map) vs
+    # fuse_sum + the tensor-core head convolution (STLPOSE_FUSE_HEAD=0): same operands, fp32 summation order differs
+    monkeypatch.delenv("STLPOSE_FUSE_LINK")
+    monkeypatch.setenv("STLPOSE_FUSE_HEAD", "0")
+    m3 = _model(32, (256, 192))
+    y3 = m3(x)
+    assert (y1 - y3).abs().max().item() < 1e-5 * max(1.0, y3.abs().max().item())
+    assert m3.launches_per_forward() == m1.launches_per_forward() + 1
 
 
 def test_flip_test_and_keypoints_vs_oracle():
