@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
 }
 
 // y = [relu]( gamma * (z - mean) * rstd + beta [+ residual] ) on the valid pixels, zero on the zero cells
+template <int NB>
 __device__ __forceinline__ void bn_apply_body(const __nv_bfloat16* __restrict__ z,
                                               const float* __restrict__ mean, const float* __restrict__ rstd,
                                               const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -345,26 +346,43 @@ __device__ __forceinline__ void bn_apply_body(const __nv_bfloat16* __restrict__ 
       g8[k] = gamma[cg0 * 8 + k]; m8[k] = mean[cg0 * 8 + k]; r8[k] = rstd[cg0 * 8 + k]; b8[k] = beta[cg0 * 8 + k];
     }
   }
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int cg, w, h, n;
-    px.decode(i, cg, w, h, n);
-    uint4 out = make_uint4(0, 0, 0, 0);
-    if (h < H && w < W) {
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(z + (size_t)i * 8), f);
-      float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (residual) unpack8(*reinterpret_cast<const uint4*>(residual + (size_t)i * 8), r);
+  // NB items per iteration, all loads issued before the first one is consumed (zero cells are loaded too: they are
+  // inside the tensor); the stride keeps a thread on its channel group
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += NB * stride) {
+    uint32_t idx[NB];
+    uint4 uz[NB], ur[NB];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float v = bn_affine(f[k], g8[k], m8[k], r8[k], b8[k]) + r[k];
-        f[k] = relu ? fmaxf(v, 0.f) : v;
-      }
-      out = pack8(f);
+    for (int j = 0; j < NB; ++j) {
+      idx[j] = i0 + (uint32_t)j * stride;
+      const bool in = idx[j] < total;
+      uz[j] = in ? *reinterpret_cast<const uint4*>(z + (size_t)idx[j] * 8) : make_uint4(0, 0, 0, 0);
+      ur[j] = (in && residual) ? *reinterpret_cast<const uint4*>(residual + (size_t)idx[j] * 8) : make_uint4(0, 0, 0, 0);
     }
-    *reinterpret_cast<uint4*>(y + (size_t)i * 8) = out;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const uint32_t i = idx[j];
+      if (i >= total) break;
+      int cg, w, h, n;
+      px.decode(i, cg, w, h, n);
+      uint4 out = make_uint4(0, 0, 0, 0);
+      if (h < H && w < W) {
+        float f[8], r[8];
+        unpack8(uz[j], f);
+        unpack8(ur[j], r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float v = bn_affine(f[k], g8[k], m8[k], r8[k], b8[k]) + r[k];
+          f[k] = relu ? fmaxf(v, 0.f) : v;
+        }
+        out = pack8(f);
+      }
+      *reinterpret_cast<uint4*>(y + (size_t)i * 8) = out;
+    }
   }
 }
 
+template <int NB>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ z,
                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -372,7 +390,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
                                                        __nv_bfloat16* __restrict__ y, int N, int H, int W, int C, const PixIdx px) {
   pdl_launch_dependents();
   pdl_wait();
-  bn_apply_body(z, mean, rstd, gamma, beta, residual, relu, y, N, H, W, C, px);
+  bn_apply_body<NB>(z, mean, rstd, gamma, beta, residual, relu, y, N, H, W, C, px);
 }
 
 // Batch statistics + normalisation of one BatchNorm layer in ONE cooperative launch: phase 1 = channel_reduce_kernel<0>
@@ -395,11 +413,12 @@ __global__ void __launch_bounds__(256) bn_forward_coop_kernel(const __nv_bfloat1
   __shared__ float s_stat[2 * kCoopMaxC];
   for (int c = threadIdx.x; c < C; c += blockDim.x) { s_stat[c] = __ldcg(fin.mean + c); s_stat[kCoopMaxC + c] = __ldcg(fin.rstd + c); }
   __syncthreads();
-  bn_apply_body(z, s_stat, s_stat + kCoopMaxC, gamma, beta, residual, relu, y, N, H, W, C, px);
+  bn_apply_body<2>(z, s_stat, s_stat + kCoopMaxC, gamma, beta, residual, relu, y, N, H, W, C, px);
   grid_leave(sync);
 }
 
 // dz = gamma * rstd * (g - sum_g/cnt - xhat * sum_gx/cnt),  g = dy masked by (y > 0) when relu; d_res = g
+template <int NB>
 __device__ __forceinline__ void bn_backward_body(const __nv_bfloat16* __restrict__ dy,
                                                           const __nv_bfloat16* __restrict__ y,
                                                           const __nv_bfloat16* __restrict__ z,
@@ -425,30 +444,48 @@ __device__ __forceinline__ void bn_backward_body(const __nv_bfloat16* __restrict
       ga8[k] = gamma[c]; be8[k] = relu_mask == 2 ? beta[c] : 0.f;
     }
   }
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int cg, w, h, n;
-    px.decode(i, cg, w, h, n);
-    uint4 o_dz = make_uint4(0, 0, 0, 0), o_dr = o_dz;
-    if (h < H && w < W) {
-      float g[8], yy[8], zz[8], d[8];
-      unpack8(*reinterpret_cast<const uint4*>(dy + (size_t)i * 8), g);
-      unpack8(*reinterpret_cast<const uint4*>(z + (size_t)i * 8), zz);
-      if (relu_mask == 1) unpack8(*reinterpret_cast<const uint4*>(y + (size_t)i * 8), yy);
+  // NB items per iteration, all loads issued before the first one is consumed (see bn_apply_body)
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += NB * stride) {
+    uint32_t idx[NB];
+    uint4 ug[NB], uz[NB], uy[NB];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (relu_mask == 1 ? !(yy[k] > 0.f)
-                           : (relu_mask == 2 && !(bn_affine(zz[k], ga8[k], m8[k], r8[k], be8[k]) > 0.f))) g[k] = 0.f;
-        const float xhat = (zz[k] - m8[k]) * r8[k];
-        d[k] = gr8[k] * (g[k] - sg8[k] - xhat * sx8[k]);
-      }
-      o_dz = pack8(d);
-      o_dr = pack8(g);
+    for (int j = 0; j < NB; ++j) {
+      idx[j] = i0 + (uint32_t)j * stride;
+      const bool in = idx[j] < total;
+      ug[j] = in ? *reinterpret_cast<const uint4*>(dy + (size_t)idx[j] * 8) : make_uint4(0, 0, 0, 0);
+      uz[j] = in ? *reinterpret_cast<const uint4*>(z + (size_t)idx[j] * 8) : make_uint4(0, 0, 0, 0);
+      uy[j] = (in && relu_mask == 1) ? *reinterpret_cast<const uint4*>(y + (size_t)idx[j] * 8) : make_uint4(0, 0, 0, 0);
     }
-    *reinterpret_cast<uint4*>(dz + (size_t)i * 8) = o_dz;
-    if (dres) *reinterpret_cast<uint4*>(dres + (size_t)i * 8) = o_dr;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const uint32_t i = idx[j];
+      if (i >= total) break;
+      int cg, w, h, n;
+      px.decode(i, cg, w, h, n);
+      uint4 o_dz = make_uint4(0, 0, 0, 0), o_dr = o_dz;
+      if (h < H && w < W) {
+        float g[8], yy[8], zz[8], d[8];
+        unpack8(ug[j], g);
+        unpack8(uz[j], zz);
+        unpack8(uy[j], yy);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (relu_mask == 1 ? !(yy[k] > 0.f)
+                             : (relu_mask == 2 && !(bn_affine(zz[k], ga8[k], m8[k], r8[k], be8[k]) > 0.f))) g[k] = 0.f;
+          const float xhat = (zz[k] - m8[k]) * r8[k];
+          d[k] = gr8[k] * (g[k] - sg8[k] - xhat * sx8[k]);
+        }
+        o_dz = pack8(d);
+        o_dr = pack8(g);
+      }
+      *reinterpret_cast<uint4*>(dz + (size_t)i * 8) = o_dz;
+      if (dres) *reinterpret_cast<uint4*>(dres + (size_t)i * 8) = o_dr;
+    }
   }
 }
 
+template <int NB>
 __global__ void __launch_bounds__(256) bn_backward_kernel(const __nv_bfloat16* __restrict__ dy,
                                                           const __nv_bfloat16* __restrict__ y,
                                                           const __nv_bfloat16* __restrict__ z,
@@ -462,7 +499,7 @@ __global__ void __launch_bounds__(256) bn_backward_kernel(const __nv_bfloat16* _
                                                           int C, const PixIdx px) {
   pdl_launch_dependents();
   pdl_wait();
-  bn_backward_body(dy, y, z, mean, rstd, gamma, beta, sums, count, relu_mask, dz, dres, N, H, W, C, px);
+  bn_backward_body<NB>(dy, y, z, mean, rstd, gamma, beta, sums, count, relu_mask, dz, dres, N, H, W, C, px);
 }
 
 // Both passes of the BatchNorm backward in ONE cooperative launch (phase 1 = channel_reduce_kernel<1>: dbeta | dgamma,
@@ -488,7 +525,7 @@ __global__ void __launch_bounds__(256) bn_backward_coop_kernel(const __nv_bfloat
   __shared__ float s_sums[2 * kCoopMaxC];
   for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) s_sums[c] = __ldcg(sums + c);
   __syncthreads();
-  bn_backward_body(dy, y, z, mean, rstd, gamma, beta, s_sums, count, relu_mask, dz, dres, N, H, W, C, px);
+  bn_backward_body<2>(dy, y, z, mean, rstd, gamma, beta, s_sums, count, relu_mask, dz, dres, N, H, W, C, px);
   grid_leave(sync);
 }
 
@@ -761,8 +798,8 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __nv_bfloat16* __
 
 // Grid for a 256-thread grid-stride kernel over `total` items whose stride (grid * 256) must be a multiple of `c8n`
 // (threads then keep their channel group): c8n = 2^a or 3 * 2^a -> round the block count up to a multiple of 3 if needed.
-int grid_mult(long long total, int c8n) {
-  long long g = (total + 255) / 256;
+int grid_mult(long long total, int c8n, int nb = 1) {
+  long long g = (total + 256 * nb - 1) / (256 * nb);   // (the kernels take nb items per thread and iteration)
   if (g > 148 * 16) g = 148 * 16;
   if (g < 1) g = 1;
   if (256 % c8n) g = (g + 2) / 3 * 3;
@@ -835,8 +872,19 @@ int bn_train_forward(const __nv_bfloat16* z, const float* gamma, const float* be
   px.init(C, H, W);
   if (pixels * (C / 8) >= (1ll << 31)) { set_error("bn_train_forward: tensor too large for 32-bit item indexing"); return 1; }
   if (256 % (C / 8) && (C / 8) % 3) { set_error("bn_train_forward: C=%d unsupported", C); return 1; }
-  launch_bn(bn_apply_kernel, grid_mult(pixels * (C / 8), C / 8), st, z, (const float*)mean, (const float*)rstd, gamma, beta,
-            residual, relu, y, N, H, W, C, px);
+  // items per thread and iteration (STL_BN_NB_APPLY / _BWD = 1, 2, 4: measurement knobs).  Measured on B200: the backward
+  // kernel gains most from two (13.7 -> 8.7 us at 6.5 MB, 81 -> 58 us at 52 MB, 270 -> 167 us at 209 MB; four: another
+  // 10-15 % on the large tensors only), the normalisation little (5.0 -> 4.6 us at 6.5 MB, unchanged from 26 MB up)
+  static const int nb = getenv("STL_BN_NB_APPLY") ? atoi(getenv("STL_BN_NB_APPLY")) : 2;
+  if (nb == 4)
+    launch_bn(bn_apply_kernel<4>, grid_mult(pixels * (C / 8), C / 8, 4), st, z, (const float*)mean, (const float*)rstd, gamma,
+              beta, residual, relu, y, N, H, W, C, px);
+  else if (nb == 2)
+    launch_bn(bn_apply_kernel<2>, grid_mult(pixels * (C / 8), C / 8, 2), st, z, (const float*)mean, (const float*)rstd, gamma,
+              beta, residual, relu, y, N, H, W, C, px);
+  else
+    launch_bn(bn_apply_kernel<1>, grid_mult(pixels * (C / 8), C / 8, 1), st, z, (const float*)mean, (const float*)rstd, gamma,
+              beta, residual, relu, y, N, H, W, C, px);
   return check("bn apply");
 }
 
@@ -933,7 +981,7 @@ int bn_train_forward_fused(const __nv_bfloat16* z, const float* stat_rows, int r
   px.init(C, H, W);
   if (pixels * (C / 8) >= (1ll << 31)) { set_error("bn_train_forward_fused: tensor too large for 32-bit item indexing"); return 1; }
   if (256 % (C / 8) && (C / 8) % 3) { set_error("bn_train_forward_fused: C=%d unsupported", C); return 1; }
-  bn_apply_kernel<<<grid_mult(pixels * (C / 8), C / 8), 256, 0, st>>>(z, mean, rstd, gamma, beta, residual, relu, y, N, H,
+  bn_apply_kernel<1><<<grid_mult(pixels * (C / 8), C / 8), 256, 0, st>>>(z, mean, rstd, gamma, beta, residual, relu, y, N, H,
                                                                   W, C, px);
   return check("bn apply");
 }
@@ -946,7 +994,7 @@ int bn_apply(const __nv_bfloat16* z, const float* mean, const float* rstd, const
   px.init(C, H, W);
   if (pixels * (C / 8) >= (1ll << 31)) { set_error("bn_apply: tensor too large for 32-bit item indexing"); return 1; }
   if (256 % (C / 8) && (C / 8) % 3) { set_error("bn_apply: C=%d unsupported", C); return 1; }
-  bn_apply_kernel<<<grid_mult(pixels * (C / 8), C / 8), 256, 0, st>>>(z, mean, rstd, gamma, beta, residual, relu, y, N, H,
+  bn_apply_kernel<1><<<grid_mult(pixels * (C / 8), C / 8), 256, 0, st>>>(z, mean, rstd, gamma, beta, residual, relu, y, N, H,
                                                                   W, C, px);
   return check("bn apply");
 }
@@ -969,8 +1017,16 @@ int bn_train_backward(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __n
   px.init(C, H, W);
   if (pixels * (C / 8) >= (1ll << 31)) { set_error("bn_train_backward: tensor too large for 32-bit item indexing"); return 1; }
   if (256 % (C / 8) && (C / 8) % 3) { set_error("bn_train_backward: C=%d unsupported", C); return 1; }
-  launch_bn(bn_backward_kernel, grid_mult(pixels * (C / 8), C / 8), st, dy, y, z, mean, rstd, gamma, beta,
-            (const float*)sums, (float)((long long)N * H * W), relu, dz, dres, N, H, W, C, px);
+  static const int nb = getenv("STL_BN_NB_BWD") ? atoi(getenv("STL_BN_NB_BWD")) : 2;
+  if (nb == 4)
+    launch_bn(bn_backward_kernel<4>, grid_mult(pixels * (C / 8), C / 8, 4), st, dy, y, z, mean, rstd, gamma, beta,
+              (const float*)sums, (float)((long long)N * H * W), relu, dz, dres, N, H, W, C, px);
+  else if (nb == 1)
+    launch_bn(bn_backward_kernel<1>, grid_mult(pixels * (C / 8), C / 8, 1), st, dy, y, z, mean, rstd, gamma, beta,
+              (const float*)sums, (float)((long long)N * H * W), relu, dz, dres, N, H, W, C, px);
+  else
+    launch_bn(bn_backward_kernel<2>, grid_mult(pixels * (C / 8), C / 8, 2), st, dy, y, z, mean, rstd, gamma, beta,
+              (const float*)sums, (float)((long long)N * H * W), relu, dz, dres, N, H, W, C, px);
   return check("bn backward");
 }
 
