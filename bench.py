@@ -414,7 +414,7 @@ def run_infer(args):
                       "d2h_bytes_per_step": d2h}
         out["gpu_launches"] = pipe.launches_per_step * args.steps
         out["roofline"] = {
-            "bound": "tensor", "kernel": "conv_tc_kernel + basic_block_kernel (tcgen05 convolutions)",
+            "bound": "tensor", "kernel": "conv_tc_kernel + basic_block_kernel + bottleneck_link_kernel (tcgen05 convolutions)",
             "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
             "traffic": traffic, "traffic_note": traffic_note,
             "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)",
