@@ -64,3 +64,42 @@ def test_compute_fails_loudly_without_gpu():
     assert b"no CUDA device" in L.stl_last_error()
     with pytest.raises(Exception):
         S.get_max_preds_hrnet(np.zeros((1, 17, 64, 48), np.float32))
+
+
+@pytest.mark.parametrize("env,extra", [({}, 0), ({"STLPOSE_FUSE_LINK": "0"}, 3), ({"STLPOSE_FUSE_DOWNSAMPLE": "0"}, 2),
+                                       ({"STLPOSE_FUSE_HEAD": "0"}, 1), ({"STLPOSE_FUSE_BLOCK": "0"}, 32),
+                                       ({"STLPOSE_FUSE_LINK": "0", "STLPOSE_FUSE_DOWNSAMPLE": "0", "STLPOSE_FUSE_HEAD": "0",
+                                         "STLPOSE_FUSE_BLOCK": "0"}, 37)])
+def test_plan_fusion_switches_keep_every_conv(env, extra, monkeypatch):
+    """Every fusion of the plan (BasicBlock kernel, conv3 + downsample as one two-input convolution, Bottleneck junctions,
+    last fuse row + head) can be switched off by its environment variable; whatever the combination, each of the 293
+    convolutions of the reference's state_dict is packed exactly once, and the launch count moves by the documented
+    amount (no GPU needed: the plan is host-side)."""
+    from stlpose_b200 import _lib
+    import stlpose_b200 as S
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    L = _lib.lib()
+    m = S.PoseHighResolutionNet(width=32, image_size=(256, 192))
+    plan = m._plan(256, 192)
+    n = L.stl_plan_num_convs(plan)
+    info = _lib.ConvInfo()
+    keys = set()
+    for i in range(n):
+        _lib.check(L.stl_plan_conv_info(plan, i, ctypes.byref(info)))
+        keys.add(info.conv_key.decode())
+    assert n == 293 and len(keys) == 293
+    assert L.stl_plan_launches_per_forward(plan) == 293 + 8 + 1 - 4 - 33 + extra
+
+
+def test_cooperative_batchnorm_policy():
+    """training._use_coop_bn ("auto"): the cooperative single-launch BatchNorm is used for the backward direction at
+    every size and never for the forward direction, and is off in multi-process jobs (checked by the
+    world-size-2 tests of test_parallel_cpu.py through the same function)."""
+    from stlpose_b200 import training
+    if training.COOP_BN != "auto":
+        pytest.skip("STLPOSE_TRAIN_COOP_BN is forced")
+    small = torch.empty(4, 9, 7, 32, dtype=torch.bfloat16)
+    big = torch.empty(0, dtype=torch.bfloat16).new_empty((64, 65, 49, 256))
+    assert training._use_coop_bn(small, backward=True) and training._use_coop_bn(big, backward=True)
+    assert not training._use_coop_bn(small) and not training._use_coop_bn(big)
