@@ -34,6 +34,11 @@ def _worker(rank, world, port, n, q):
         lo, hi = shard_bounds(n, world, rank)
         p, m = gather_keypoints(full_p[lo:hi].clone(), full_m[lo:hi].clone(), n)
         ok = torch.equal(p, full_p) and torch.equal(m, full_m)
+        # in a multi-process job the training path keeps the two-launch BatchNorm kernels (no cooperative grid spinning
+        # next to in-flight collectives): training._use_coop_bn, "auto" policy
+        from stlpose_b200 import training
+        if training.COOP_BN == "auto":
+            ok = ok and not training._use_coop_bn(torch.empty(2, 9, 7, 32, dtype=torch.bfloat16), backward=True)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
